@@ -1,0 +1,127 @@
+// Common device/host helpers for the tethys-speech B200 kernels (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/tethys.h"
+
+namespace ts {
+
+typedef __nv_bfloat16 bf16;
+
+// ----------------------------------------------------------------------------------------------
+// Context (one per process x GPU). Holds the last error string and device facts.
+// ----------------------------------------------------------------------------------------------
+struct Ctx {
+  int device = 0;
+  int num_sms = 148;
+  std::string err;
+  // driver entry point for cuTensorMapEncodeTiled, resolved lazily (no link-time libcuda dependency,
+  // so the library still loads on a CPU-only box for the symbol-export test).
+  void* encode_tiled = nullptr;
+  int* d_watchdog = nullptr;   // device int: set non-zero by a kernel whose mbarrier wait timed out
+  void* tmap_cache = nullptr;  // opaque tensor-map cache (gemm_tc.cu)
+};
+
+int set_err(Ctx* c, int code, const char* fmt, ...);
+
+#define TS_CUDA_OK(ctx, expr)                                                              \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return ts::set_err((ctx), TS_ECUDA, "%s failed: %s (%s:%d)", #expr,                  \
+                         cudaGetErrorString(_e), __FILE__, __LINE__);                      \
+  } while (0)
+
+#define TS_LAUNCH_OK(ctx)                                                                  \
+  do {                                                                                     \
+    cudaError_t _e = cudaGetLastError();                                                   \
+    if (_e != cudaSuccess)                                                                 \
+      return ts::set_err((ctx), TS_ECUDA, "kernel launch failed: %s (%s:%d)",              \
+                         cudaGetErrorString(_e), __FILE__, __LINE__);                      \
+  } while (0)
+
+#define TS_REQUIRE(ctx, cond, code, ...)                                                   \
+  do {                                                                                     \
+    if (!(cond)) return ts::set_err((ctx), (code), __VA_ARGS__);                           \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ----------------------------------------------------------------------------------------------
+// dtype helpers
+// ----------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// exact-erf GELU (reference: tf.keras.activations.gelu default / custom gelu, whisper_dist.py:195,
+// wav2vec2_dist.py:132-136) and its derivative.
+__device__ __forceinline__ float gelu_f(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// ----------------------------------------------------------------------------------------------
+// warp / block reductions
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum; `red` is a __shared__ float[32]. All threads get the result.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : -INFINITY;
+  r = warp_max(r);
+  return r;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Counter-based RNG for dropout (stateless; the backward pass regenerates the same mask).
+// keep(idx) is a pure function of (seed, idx): a 64->32 bit mix (splitmix64 finaliser).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix_hash(uint64_t seed, uint64_t idx) {
+  uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (uint32_t)(z >> 32);
+}
+// returns the multiplier to apply: 0 (dropped) or 1/(1-rate) (kept). thr = rate * 2^32.
+__device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, uint32_t thr, float inv_keep) {
+  return (mix_hash(seed, idx) >= thr) ? inv_keep : 0.f;
+}
+
+}  // namespace ts
