@@ -55,7 +55,7 @@ int ts_watchdog_check(ts_ctx* ctx);
  *   W:89-92,141,174,194-205,311-312,545 ; V:240-268,316-319,338-340,371,383-398,553,579,586 and
  *   their autodiff transposes (dgrad, wgrad).
  *
- *   C[m,n] = act(alpha * sum_k A[m,k]*B[n,k] + bias[n]) + residual[m,n]        (per batch)
+ *   C[m,n] = dropout(act(alpha * sum_k A[m,k]*B[n,k] + bias[n])) + residual[m,n]   (per batch)
  *
  * Storage ("major") of the two operands, in elements:
  *   a_major = 0 ("K-major"):  A stored as [m][k], row stride lda   (reduce dim contiguous)
@@ -63,7 +63,7 @@ int ts_watchdog_check(ts_ctx* ctx);
  *   b_major = 0:              B stored as [n][k], row stride ldb
  *   b_major = 1:              B stored as [k][n], row stride ldb   (a Keras Dense kernel [in,out])
  * Rows of A/B may overlap (lda < k) — this is how strided Conv1D windows are fed without im2col.
- * Two batch dims (batch1 fastest) cover (head, batch) for attention.
+ * Two batch dims (batch1 fastest) cover (head, batch) for attention; a batch stride of 0 broadcasts.
  * in_dtype TS_BF16 runs on tcgen05 tensor cores (TMA-fed, TMEM accumulators, fp32 accumulate);
  * in_dtype TS_F32 runs the fp32 CUDA-core engine used by the 1e-5 parity mode.
  */
@@ -86,9 +86,71 @@ typedef struct {
   int32_t accumulate; /* 1: C += result (only with out_dtype TS_F32, no act/residual) */
   void* c_preact;     /* optional second output: value before act (same dtype/ld as C) or NULL */
   int32_t force_engine; /* 0 auto, 1 force CUDA-core engine, 2 force tcgen05 (error if impossible) */
+  float drop;           /* dropout rate applied after act (0 = off); keep-mask = hash(seed, element offset in C) */
+  uint64_t seed;
+  int64_t bias_bs1;     /* bias element stride per batch1 index (grouped conv: one bias slice per group) */
 } ts_gemm_desc;
 
 int ts_gemm(ts_ctx* ctx, const ts_gemm_desc* d, void* stream);
+
+/* ---- K19/K20: gradient clipping + Keras-2.10 legacy Adam over a flat arena ------------------------
+ * Replaces tf.clip_by_global_norm (V:1243, VS:1171), the optimizer's clipnorm=1.0 (V:1274, VS:1206) and
+ * tf.keras.optimizers.Adam.apply_gradients (W:834, V:1246, VS:1174, WS:1179) minus its all-reduce.
+ * A variable is a rows x cols block with row stride ld at `offset` (elements) inside the arenas.
+ *   ts_optim_clip_global : grads *= clip / max(||grads||_2, clip) over ALL variables (local, pre-reduce).
+ *   ts_optim_step        : [per-variable clipnorm] + Adam:  m += (g-m)(1-b1); v += (g*g-v)(1-b2);
+ *                          p -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps); optionally refreshes the bf16
+ *                          compute copy of the parameters in the same pass.
+ * fuse_global_clip = 1 folds the global-norm clip into the step (single-replica path: no all-reduce between).
+ */
+typedef struct ts_optim ts_optim;
+int ts_optim_create(ts_ctx* ctx, int32_t n_vars, const int64_t* offsets, const int32_t* rows, const int32_t* cols,
+                    const int64_t* lds, int64_t arena_elems, ts_optim** out);
+void ts_optim_destroy(ts_optim* o);
+int ts_optim_clip_global(ts_optim* o, float* grads, float clip, float* norm_out_dev /*nullable*/, void* stream);
+int ts_optim_step(ts_optim* o, float* params, const float* grads, float* m, float* v, void* params_bf16 /*nullable*/,
+                  float lr, float beta1, float beta2, float eps, int32_t step, float global_clip /*<=0 off*/,
+                  float clipnorm /*<=0 off*/, int32_t fuse_global_clip, void* stream);
+int ts_cast_f32_to_bf16(ts_ctx* ctx, const float* src, void* dst, int64_t n, void* stream);
+
+/* ---- Wav2Vec2 pre-training program ---------------------------------------------------------------------
+ * Replaces Wav2Vec2ForPreTraining.call(training=True) + _compute_contrastive_loss + _compute_diversity_loss
+ * + tape.gradient of the per-replica step (V:768-905, V:1199-1240; VS:1131-1168; WS:1143-1176).
+ * The negative indices are an input (the TF RNG stream of V:919 cannot be reproduced): neg[b*neg_bs + t*neg_ts + k].
+ * Parameters/gradients live in caller-owned flat fp32 arenas whose layout ts_w2v_param_info describes; the
+ * arena is ordered so that after backward stage s all gradients below ts_w2v_stage_end(s) are final
+ * (stage 0 = heads, 1..L = encoder layers L-1..0, L+1 = feature projection + conv front end), which is what
+ * the host uses to overlap the bucketed gradient all-reduce (K21) with backward.
+ */
+typedef struct {
+  int32_t hidden, layers, heads, ffn;
+  int32_t n_conv;
+  int32_t conv_dim[8], conv_kernel[8], conv_stride[8];
+  int32_t pos_kernel, pos_groups; /* num_conv_pos_embeddings / _groups; pos_groups is also the GroupNorm group count (V:248) */
+  int32_t cv_groups, cv_per_group, cv_dim, proj_dim;
+  int32_t num_negatives;
+  float ln_eps, temperature, diversity_weight;
+  float hidden_dropout, activation_dropout, attention_dropout;
+} ts_w2v_config;
+
+typedef struct ts_w2v ts_w2v;
+int ts_w2v_create(ts_ctx* ctx, const ts_w2v_config* cfg, int precision /*TS_F32 | TS_BF16*/, ts_w2v** out);
+void ts_w2v_destroy(ts_w2v* m);
+int64_t ts_w2v_arena_elems(ts_w2v* m);
+int ts_w2v_num_params(ts_w2v* m);
+int ts_w2v_param_info(ts_w2v* m, int i, char* name, int name_cap, int64_t* offset, int32_t* ndim, int64_t* shape4,
+                      int64_t* ld);
+int ts_w2v_num_stages(ts_w2v* m);
+int64_t ts_w2v_stage_end(ts_w2v* m, int stage);
+int64_t ts_w2v_workspace_bytes(ts_w2v* m, int batch, int n_samples);
+int ts_w2v_bind(ts_w2v* m, float* params, float* grads, void* params_bf16 /*bf16 mode*/, void* workspace,
+                int64_t workspace_bytes);
+int ts_w2v_sync_compute_weights(ts_w2v* m, void* stream); /* fp32 master -> bf16 compute copy */
+int ts_w2v_forward(ts_w2v* m, const float* wave /*[B,N]*/, int batch, int n_samples, const int32_t* neg, int64_t neg_bs,
+                   int64_t neg_ts, float loss_div /*num replicas, V:1231*/, uint64_t seed, int training, void* stream);
+int ts_w2v_backward(ts_w2v* m, int stage_from, int stage_to, void* stream);
+/* named views into the workspace of the last forward ("scalars" = {loss, contrastive, perplexity, raw sum}). */
+int ts_w2v_get_buffer(ts_w2v* m, const char* name, void** ptr, int32_t* dtype, int32_t* ndim, int64_t* shape4);
 
 #ifdef __cplusplus
 }

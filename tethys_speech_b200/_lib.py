@@ -1,0 +1,153 @@
+"""ctypes binding of libtethys.so (include/tethys.h). There is no CPU fallback: if the library or a B200 is
+missing, creating a context raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtethys.so")
+
+TS_F32, TS_BF16, TS_I32, TS_I64 = 0, 1, 2, 3
+
+_STATUS = {0: "TS_OK", -1: "TS_EINVAL", -2: "TS_ESHAPE", -3: "TS_EDTYPE", -4: "TS_ECUDA", -5: "TS_ENCCL",
+           -6: "TS_EUNSUPPORTED", -7: "TS_EWATCHDOG"}
+
+
+class TethysError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{_STATUS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p),
+        ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32),
+        ("a_major", C.c_int32), ("b_major", C.c_int32),
+        ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64),
+        ("batch1", C.c_int32), ("batch2", C.c_int32),
+        ("a_bs1", C.c_int64), ("a_bs2", C.c_int64), ("b_bs1", C.c_int64), ("b_bs2", C.c_int64),
+        ("c_bs1", C.c_int64), ("c_bs2", C.c_int64),
+        ("in_dtype", C.c_int32), ("out_dtype", C.c_int32),
+        ("alpha", C.c_float),
+        ("bias", C.c_void_p),
+        ("act", C.c_int32),
+        ("residual", C.c_void_p),
+        ("ldr", C.c_int64), ("r_bs1", C.c_int64), ("r_bs2", C.c_int64),
+        ("accumulate", C.c_int32),
+        ("c_preact", C.c_void_p),
+        ("force_engine", C.c_int32),
+        ("drop", C.c_float),
+        ("seed", C.c_uint64),
+        ("bias_bs1", C.c_int64),
+    ]
+
+
+class W2VConfig(C.Structure):
+    _fields_ = [
+        ("hidden", C.c_int32), ("layers", C.c_int32), ("heads", C.c_int32), ("ffn", C.c_int32),
+        ("n_conv", C.c_int32),
+        ("conv_dim", C.c_int32 * 8), ("conv_kernel", C.c_int32 * 8), ("conv_stride", C.c_int32 * 8),
+        ("pos_kernel", C.c_int32), ("pos_groups", C.c_int32),
+        ("cv_groups", C.c_int32), ("cv_per_group", C.c_int32), ("cv_dim", C.c_int32), ("proj_dim", C.c_int32),
+        ("num_negatives", C.c_int32),
+        ("ln_eps", C.c_float), ("temperature", C.c_float), ("diversity_weight", C.c_float),
+        ("hidden_dropout", C.c_float), ("activation_dropout", C.c_float), ("attention_dropout", C.c_float),
+    ]
+
+
+class WhisperCfg(C.Structure):
+    _fields_ = [
+        ("d_model", C.c_int32), ("enc_layers", C.c_int32), ("dec_layers", C.c_int32), ("heads", C.c_int32),
+        ("d_ff", C.c_int32), ("n_mels", C.c_int32), ("n_ctx", C.c_int32), ("vocab", C.c_int32),
+        ("max_target", C.c_int32), ("start_token", C.c_int32),
+        ("ln_eps", C.c_float), ("dropout", C.c_float), ("attention_dropout", C.c_float),
+        ("activation_dropout", C.c_float),
+    ]
+
+
+# every symbol include/tethys.h declares: name -> (restype, argtypes)
+_P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+SYMBOLS = {
+    "ts_version": (_I, []),
+    "ts_create": (_I, [_I, C.POINTER(_P)]),
+    "ts_destroy": (None, [_P]),
+    "ts_last_error": (C.c_char_p, [_P]),
+    "ts_watchdog_check": (_I, [_P]),
+    "ts_gemm": (_I, [_P, C.POINTER(GemmDesc), _P]),
+    "ts_optim_create": (_I, [_P, _I, C.POINTER(_L), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L), _L, C.POINTER(_P)]),
+    "ts_optim_destroy": (None, [_P]),
+    "ts_optim_clip_global": (_I, [_P, _P, _F, _P, _P]),
+    "ts_optim_step": (_I, [_P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _I, _F, _F, _I, _P]),
+    "ts_cast_f32_to_bf16": (_I, [_P, _P, _P, _L, _P]),
+    "ts_w2v_create": (_I, [_P, C.POINTER(W2VConfig), _I, C.POINTER(_P)]),
+    "ts_w2v_destroy": (None, [_P]),
+    "ts_w2v_arena_elems": (_L, [_P]),
+    "ts_w2v_num_params": (_I, [_P]),
+    "ts_w2v_param_info": (_I, [_P, _I, C.c_char_p, _I, C.POINTER(_L), C.POINTER(_I), C.POINTER(_L), C.POINTER(_L)]),
+    "ts_w2v_num_stages": (_I, [_P]),
+    "ts_w2v_stage_end": (_L, [_P, _I]),
+    "ts_w2v_workspace_bytes": (_L, [_P, _I, _I]),
+    "ts_w2v_bind": (_I, [_P, _P, _P, _P, _P, _L]),
+    "ts_w2v_sync_compute_weights": (_I, [_P, _P]),
+    "ts_w2v_forward": (_I, [_P, _P, _I, _I, _P, _L, _L, _F, C.c_uint64, _I, _P]),
+    "ts_w2v_backward": (_I, [_P, _I, _I, _P]),
+    "ts_w2v_get_buffer": (_I, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L)]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen libtethys.so and declare every prototype. Raises if the library was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found — run `make` (or __graft_entry__.build()); there is no fallback path")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the export is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class Context:
+    """One per (process, GPU) — wraps ts_ctx."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = _P()
+        rc = self.lib.ts_create(int(device), C.byref(h))
+        if rc != 0:
+            raise TethysError(rc, f"ts_create(device={device}) failed — a B200 (sm_100) GPU is required; no CPU fallback exists")
+        self.h = h
+        self.device = int(device)
+
+    def check(self, rc):
+        if rc != 0:
+            raise TethysError(rc, self.lib.ts_last_error(self.h).decode("utf-8", "replace"))
+
+    def watchdog(self):
+        self.check(self.lib.ts_watchdog_check(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ts_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_contexts = {}
+
+
+def context(device=0):
+    if device not in _contexts:
+        _contexts[device] = Context(device)
+    return _contexts[device]

@@ -90,3 +90,86 @@ int ts_gemm(ts_ctx* ctx, const ts_gemm_desc* d, void* stream) {
 }
 
 }  // extern "C"
+
+// ---- optimizer object ------------------------------------------------------------------------------------
+#include <vector>
+#include "ops.cuh"
+
+namespace ts {
+struct Optim {
+  Ctx* ctx;
+  Segment* d_segs = nullptr;
+  int nseg = 0;
+  long long arena = 0;
+  float* d_sumsq = nullptr;   // [nseg]
+  float* d_scal = nullptr;    // [0] global clip scale, [1] global norm
+};
+}  // namespace ts
+
+extern "C" {
+
+int ts_optim_create(ts_ctx* ctx_, int32_t n, const int64_t* offsets, const int32_t* rows, const int32_t* cols,
+                    const int64_t* lds, int64_t arena_elems, ts_optim** out) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  if (!ctx || !out || n <= 0) return TS_EINVAL;
+  std::vector<ts::Segment> h(n);
+  for (int i = 0; i < n; ++i) {
+    h[i].offset = offsets[i]; h[i].rows = rows[i]; h[i].cols = cols[i]; h[i].ld = lds[i];
+    TS_REQUIRE(ctx, offsets[i] >= 0 && rows[i] > 0 && cols[i] > 0 &&
+                        offsets[i] + (long long)(rows[i] - 1) * lds[i] + cols[i] <= arena_elems,
+               TS_EINVAL, "optim: variable %d outside the arena", i);
+  }
+  ts::Optim* o = new ts::Optim();
+  o->ctx = ctx; o->nseg = n; o->arena = arena_elems;
+  TS_CUDA_OK(ctx, cudaMalloc(&o->d_segs, sizeof(ts::Segment) * n));
+  TS_CUDA_OK(ctx, cudaMemcpy(o->d_segs, h.data(), sizeof(ts::Segment) * n, cudaMemcpyHostToDevice));
+  TS_CUDA_OK(ctx, cudaMalloc(&o->d_sumsq, sizeof(float) * n));
+  TS_CUDA_OK(ctx, cudaMalloc(&o->d_scal, sizeof(float) * 4));
+  *out = reinterpret_cast<ts_optim*>(o);
+  return 0;
+}
+
+void ts_optim_destroy(ts_optim* o_) {
+  ts::Optim* o = reinterpret_cast<ts::Optim*>(o_);
+  if (!o) return;
+  ts::optim_forget(o->d_segs);
+  cudaFree(o->d_segs); cudaFree(o->d_sumsq); cudaFree(o->d_scal);
+  delete o;
+}
+
+int ts_optim_clip_global(ts_optim* o_, float* grads, float clip, float* norm_out_dev, void* stream) {
+  ts::Optim* o = reinterpret_cast<ts::Optim*>(o_);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ts::grad_sumsq(o->ctx, grads, o->d_segs, o->nseg, o->d_sumsq, st);
+  if (rc) return rc;
+  rc = ts::global_clip_scale(o->ctx, o->d_sumsq, o->nseg, clip, o->d_scal, norm_out_dev ? norm_out_dev : o->d_scal + 1, st);
+  if (rc) return rc;
+  return ts::scale_inplace(o->ctx, grads, o->arena, o->d_scal, 1.f, st);
+}
+
+int ts_optim_step(ts_optim* o_, float* params, const float* grads, float* m, float* v, void* params_bf16, float lr,
+                  float beta1, float beta2, float eps, int32_t step, float global_clip, float clipnorm,
+                  int32_t fuse_global_clip, void* stream) {
+  ts::Optim* o = reinterpret_cast<ts::Optim*>(o_);
+  cudaStream_t st = (cudaStream_t)stream;
+  ts::AdamArgs a;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.step = step; a.clipnorm = clipnorm;
+  a.pre_scale = nullptr; a.sumsq = nullptr;
+  if (clipnorm > 0.f || (fuse_global_clip && global_clip > 0.f)) {
+    int rc = ts::grad_sumsq(o->ctx, grads, o->d_segs, o->nseg, o->d_sumsq, st);
+    if (rc) return rc;
+    a.sumsq = o->d_sumsq;
+  }
+  if (fuse_global_clip && global_clip > 0.f) {
+    int rc = ts::global_clip_scale(o->ctx, o->d_sumsq, o->nseg, global_clip, o->d_scal, o->d_scal + 1, st);
+    if (rc) return rc;
+    a.pre_scale = o->d_scal;
+  }
+  return ts::adam_step(o->ctx, params, grads, m, v, params_bf16, o->d_segs, o->nseg, a, st);
+}
+
+int ts_cast_f32_to_bf16(ts_ctx* ctx, const float* src, void* dst, int64_t n, void* stream) {
+  return ts::cast_f32_to_bf16(reinterpret_cast<Ctx*>(ctx), src, dst, n, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,164 @@
+// K12 GELU fwd/bwd, dropout, casts, bias-gradient column sums, transposes: pure HBM-bound helpers
+// (W:195,203-205,329,333,336,342; V:132-136,281,393-396,431). Grid-stride, 16-byte vectors.
+#include "ops.cuh"
+#include "vec.cuh"
+
+namespace ts {
+
+static inline int ew_grid(Ctx* ctx, long long nvec) {
+  long long g = (nvec + 255) / 256;
+  const long long cap = (long long)ctx->num_sms * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+__global__ void cast_kernel(const float* __restrict__ s, bf16* __restrict__ d, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 8;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      float v[8];
+      load8<float>(s + i, v);
+      store8<bf16>(d + i, v);
+    } else {
+      for (long long j = i; j < n; ++j) d[j] = __float2bfloat16_rn(s[j]);
+    }
+  }
+}
+int cast_f32_to_bf16(Ctx* ctx, const float* src, void* dst, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  cast_kernel<<<ew_grid(ctx, (n + 7) / 8), 256, 0, st>>>(src, (bf16*)dst, n);
+  TS_LAUNCH_OK(ctx);
+  return 0;
+}
+
+int fill_zero(Ctx* ctx, void* p, long long bytes, cudaStream_t st) {
+  if (bytes <= 0) return 0;
+  TS_CUDA_OK(ctx, cudaMemsetAsync(p, 0, (size_t)bytes, st));
+  return 0;
+}
+
+// mode 0: out = gelu(a)*mask ; mode 1: out = a*gelu'(b)*mask ; mode 2: out = a*mask ; mode 3: out = a+b
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) ew_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
+                                                 long long n, uint32_t thr, float inv_keep, uint64_t seed) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 8;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    float va[8], vb[8], o[8];
+    if (i + 8 <= n) {
+      load8<T>(a + i, va);
+      if (MODE == 1 || MODE == 3) load8<T>(b + i, vb);
+    } else {
+      for (int j = 0; j < 8; ++j) {
+        va[j] = (i + j < n) ? to_f<T>(a[i + j]) : 0.f;
+        vb[j] = ((MODE == 1 || MODE == 3) && i + j < n) ? to_f<T>(b[i + j]) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float r;
+      if (MODE == 0) r = gelu_f(va[j]);
+      else if (MODE == 1) r = va[j] * gelu_grad_f(vb[j]);
+      else if (MODE == 2) r = va[j];
+      else r = va[j] + vb[j];
+      if (MODE != 3 && thr) r *= dropout_scale(seed, (uint64_t)(i + j), thr, inv_keep);
+      o[j] = r;
+    }
+    if (i + 8 <= n) store8<T>(out + i, o);
+    else
+      for (int j = 0; j < 8 && i + j < n; ++j) out[i + j] = from_f<T>(o[j]);
+  }
+}
+
+static inline void drop_params(float drop, uint32_t* thr, float* inv_keep) {
+  if (drop <= 0.f) { *thr = 0; *inv_keep = 1.f; return; }
+  double t = (double)drop * 4294967296.0;
+  if (t > 4294967295.0) t = 4294967295.0;
+  *thr = (uint32_t)t;
+  *inv_keep = 1.f / (1.f - drop);
+}
+
+template <int MODE>
+static int ew_launch(Ctx* ctx, int dt, const void* a, const void* b, void* out, long long n, float drop, uint64_t seed,
+                     cudaStream_t st) {
+  if (n <= 0) return 0;
+  uint32_t thr; float ik;
+  drop_params(drop, &thr, &ik);
+  const int grid = ew_grid(ctx, (n + 7) / 8);
+  if (dt == TS_F32) ew_kernel<float, MODE><<<grid, 256, 0, st>>>((const float*)a, (const float*)b, (float*)out, n, thr, ik, seed);
+  else if (dt == TS_BF16) ew_kernel<bf16, MODE><<<grid, 256, 0, st>>>((const bf16*)a, (const bf16*)b, (bf16*)out, n, thr, ik, seed);
+  else return set_err(ctx, TS_EDTYPE, "elementwise: dtype %d", dt);
+  TS_LAUNCH_OK(ctx);
+  return 0;
+}
+
+int gelu_fwd(Ctx* ctx, int dt, const void* u, void* out, long long n, float drop, uint64_t seed, cudaStream_t st) {
+  return ew_launch<0>(ctx, dt, u, nullptr, out, n, drop, seed, st);
+}
+int gelu_bwd(Ctx* ctx, int dt, const void* df, const void* u, void* du, long long n, float drop, uint64_t seed, cudaStream_t st) {
+  return ew_launch<1>(ctx, dt, df, u, du, n, drop, seed, st);
+}
+int dropout_apply(Ctx* ctx, int dt, const void* x, void* y, long long n, float drop, uint64_t seed, cudaStream_t st) {
+  return ew_launch<2>(ctx, dt, x, nullptr, y, n, drop, seed, st);
+}
+int add_tensors(Ctx* ctx, int dt, const void* a, const void* b, void* y, long long n, cudaStream_t st) {
+  return ew_launch<3>(ctx, dt, a, b, y, n, 0.f, 0, st);
+}
+
+// column sums: block = 32 x 8 threads over a [rows-chunk, 32-col] slab; smem transpose-free: each thread
+// strides rows, warp lanes map to consecutive columns (coalesced), cross-warp reduce in smem, one atomic per col.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long ld, int rows, int cols,
+                                                     float* __restrict__ out, int rows_per_block) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float s = 0.f;
+  if (col < cols)
+    for (int r = r0 + w; r < r1; r += 8) s += to_f<T>(x[(long long)r * ld + col]);
+  red[w][lane] = s;
+  __syncthreads();
+  if (w == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][lane];
+    if (col < cols) atomicAdd(&out[col], t);
+  }
+}
+int colsum_acc(Ctx* ctx, int dt, const void* x, long long ld, int rows, int cols, float* out, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return 0;
+  const int rpb = 512;
+  dim3 grid(cdiv(cols, 32), cdiv(rows, rpb));
+  if (dt == TS_F32) colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ld, rows, cols, out, rpb);
+  else colsum_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, ld, rows, cols, out, rpb);
+  TS_LAUNCH_OK(ctx);
+  return 0;
+}
+
+// [B,R,C] -> [B,C,R] through a 32x32 smem tile (coalesced both ways)
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) transpose_kernel(const TI* __restrict__ x, TO* __restrict__ y, int R, int C) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < R && c < C) ? to_f<TI>(x[((long long)b * R + r) * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (r < R && c < C) y[((long long)b * C + c) * R + r] = from_f<TO>(tile[tx][i]);
+  }
+}
+int transpose_inner(Ctx* ctx, int dt_in, int dt_out, const void* x, void* y, int B, int R, int C, cudaStream_t st) {
+  dim3 grid(cdiv(C, 32), cdiv(R, 32), B);
+  if (dt_in == TS_F32 && dt_out == TS_F32) transpose_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, R, C);
+  else if (dt_in == TS_F32 && dt_out == TS_BF16) transpose_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)x, (bf16*)y, R, C);
+  else if (dt_in == TS_BF16 && dt_out == TS_BF16) transpose_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)y, R, C);
+  else return set_err(ctx, TS_EDTYPE, "transpose: dtype %d->%d", dt_in, dt_out);
+  TS_LAUNCH_OK(ctx);
+  return 0;
+}
+
+}  // namespace ts

@@ -8,10 +8,11 @@ namespace ts {
 struct SimtParams {
   const void* a; const void* b; void* c; void* c_pre; const void* res; const float* bias;
   long long lda, ldb, ldc, ldr;
-  long long a_bs1, a_bs2, b_bs1, b_bs2, c_bs1, c_bs2, r_bs1, r_bs2;
+  long long a_bs1, a_bs2, b_bs1, b_bs2, c_bs1, c_bs2, r_bs1, r_bs2, bias_bs1;
   int m, n, k, nb1;
   int a_major, b_major;
   float alpha; int act, accumulate;
+  uint32_t drop_thr; float inv_keep; unsigned long long seed;
 };
 
 constexpr int SB_M = 64, SB_N = 64, SB_K = 16;
@@ -78,9 +79,11 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
       const int gn = n0 + tx * 4 + j;
       if (gn >= p.n) continue;
       float v = acc[i][j] * p.alpha;
-      if (p.bias) v += p.bias[gn];
+      if (p.bias) v += p.bias[b1 * p.bias_bs1 + gn];
       if (CP) CP[(long long)gm * p.ldc + gn] = from_f<TO>(v);
       if (p.act == 1) v = gelu_f(v);
+      if (p.drop_thr)
+        v *= dropout_scale(p.seed, (unsigned long long)(b1 * p.c_bs1 + b2 * p.c_bs2 + (long long)gm * p.ldc + gn), p.drop_thr, p.inv_keep);
       if (R) v += to_f<TO>(R[(long long)gm * p.ldr + gn]);
       if (p.accumulate) v += to_f<TO>(C[(long long)gm * p.ldc + gn]);
       C[(long long)gm * p.ldc + gn] = from_f<TO>(v);
@@ -93,12 +96,18 @@ int gemm_simt(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
   p.a = d->a; p.b = d->b; p.c = d->c; p.c_pre = d->c_preact; p.res = d->residual; p.bias = d->bias;
   p.lda = d->lda; p.ldb = d->ldb; p.ldc = d->ldc; p.ldr = d->ldr;
   p.a_bs1 = d->a_bs1; p.a_bs2 = d->a_bs2; p.b_bs1 = d->b_bs1; p.b_bs2 = d->b_bs2;
-  p.c_bs1 = d->c_bs1; p.c_bs2 = d->c_bs2; p.r_bs1 = d->r_bs1; p.r_bs2 = d->r_bs2;
+  p.c_bs1 = d->c_bs1; p.c_bs2 = d->c_bs2; p.r_bs1 = d->r_bs1; p.r_bs2 = d->r_bs2; p.bias_bs1 = d->bias_bs1;
   p.m = d->m; p.n = d->n; p.k = d->k;
   const int nb1 = d->batch1 > 0 ? d->batch1 : 1, nb2 = d->batch2 > 0 ? d->batch2 : 1;
   p.nb1 = nb1;
   p.a_major = d->a_major; p.b_major = d->b_major;
   p.alpha = d->alpha; p.act = d->act; p.accumulate = d->accumulate;
+  p.drop_thr = 0; p.inv_keep = 1.f; p.seed = d->seed;
+  if (d->drop > 0.f) {
+    double t = (double)d->drop * 4294967296.0;
+    p.drop_thr = (uint32_t)(t > 4294967295.0 ? 4294967295.0 : t);
+    p.inv_keep = 1.f / (1.f - d->drop);
+  }
   TS_REQUIRE(ctx, d->m > 0 && d->n > 0 && d->k > 0, TS_ESHAPE, "gemm: empty problem m=%d n=%d k=%d", d->m, d->n, d->k);
   dim3 grid(cdiv(d->m, SB_M), cdiv(d->n, SB_N), nb1 * nb2);
   if (d->in_dtype == TS_F32 && d->out_dtype == TS_F32) gemm_simt_kernel<float, float><<<grid, 256, 0, st>>>(p);

@@ -20,10 +20,12 @@ struct EpiParams {
   void* c_pre;
   const void* res;
   const float* bias;
-  long long ldc, ldr, c_bs1, c_bs2, r_bs1, r_bs2;
+  long long ldc, ldr, c_bs1, c_bs2, r_bs1, r_bs2, bias_bs1;
   float alpha;
   int act, accumulate;
   int m, n, k, nb1;
+  int a_m1, a_m2, b_m1, b_m2;  // 0 => that batch dim is broadcast for the operand (stride 0)
+  uint32_t drop_thr; float inv_keep; unsigned long long seed;
 };
 
 constexpr int BM = 128;
@@ -149,18 +151,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const uint32_t sa = ptx::smem_u32(smem + s * Cfg::kStageBytes);
         const uint32_t sb = sa + Cfg::kABytes;
         if (AMAJ == 0) {
-          ptx::tma_load_4d(sa, &tma_a, &full_bar[s], kb * BK, m0, b1, b2);
+          ptx::tma_load_4d(sa, &tma_a, &full_bar[s], kb * BK, m0, b1 * p.a_m1, b2 * p.a_m2);
         } else {
 #pragma unroll
           for (int c = 0; c < BM / 64; ++c)
-            ptx::tma_load_4d(sa + c * 8192, &tma_a, &full_bar[s], m0 + c * 64, kb * BK, b1, b2);
+            ptx::tma_load_4d(sa + c * 8192, &tma_a, &full_bar[s], m0 + c * 64, kb * BK, b1 * p.a_m1, b2 * p.a_m2);
         }
         if (BMAJ == 0) {
-          ptx::tma_load_4d(sb, &tma_b, &full_bar[s], kb * BK, n0, b1, b2);
+          ptx::tma_load_4d(sb, &tma_b, &full_bar[s], kb * BK, n0, b1 * p.b_m1, b2 * p.b_m2);
         } else {
 #pragma unroll
           for (int c = 0; c < BN / 64; ++c)
-            ptx::tma_load_4d(sb + c * 8192, &tma_b, &full_bar[s], n0 + c * 64, kb * BK, b1, b2);
+            ptx::tma_load_4d(sb + c * 8192, &tma_b, &full_bar[s], n0 + c * 64, kb * BK, b1 * p.b_m1, b2 * p.b_m2);
         }
       }
     }
@@ -220,12 +222,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (p.bias) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (i < nv) v[i] += __ldg(p.bias + col + i);
+              if (i < nv) v[i] += __ldg(p.bias + (long long)b1 * p.bias_bs1 + col + i);
           }
           if (prow) store_vec<OutT>(prow + col, v, nv, p_vec);
           if (p.act == 1) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = gelu_f(v[i]);
+          }
+          if (p.drop_thr) {
+            const unsigned long long base = (unsigned long long)((long long)b1 * p.c_bs1 + (long long)b2 * p.c_bs2 +
+                                                                 (long long)row * p.ldc + col);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(p.seed, base + i, p.drop_thr, p.inv_keep);
           }
           if (rrow) {
             float rv[32];
@@ -336,8 +344,9 @@ bool gemm_tc_supported(const ts_gemm_desc* d) {
   auto s16 = [](long long elems) { return (elems * 2) % 16 == 0 && elems > 0; };
   if (!al(d->a) || !al(d->b)) return false;
   if (!s16(d->lda) || !s16(d->ldb)) return false;
-  if (d->batch1 > 1 && (!s16(d->a_bs1) || !s16(d->b_bs1))) return false;
-  if (d->batch2 > 1 && (!s16(d->a_bs2) || !s16(d->b_bs2))) return false;
+  auto bs_ok = [&](long long e) { return e == 0 || s16(e); };
+  if (d->batch1 > 1 && (!bs_ok(d->a_bs1) || !bs_ok(d->b_bs1))) return false;
+  if (d->batch2 > 1 && (!bs_ok(d->a_bs2) || !bs_ok(d->b_bs2))) return false;
   if (d->m <= 0 || d->n <= 0 || d->k <= 0) return false;
   return true;
 }
@@ -381,27 +390,37 @@ int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
   CUtensorMap ta, tb;
   {
     uint64_t dims[4], str[3];
-    const uint64_t bs1 = (uint64_t)(nb1 > 1 ? d->a_bs1 : d->lda) * 2, bs2 = (uint64_t)(nb2 > 1 ? d->a_bs2 : d->lda) * 2;
+    const bool bc1 = nb1 <= 1 || d->a_bs1 == 0, bc2 = nb2 <= 1 || d->a_bs2 == 0;
+    const uint64_t bs1 = (uint64_t)(bc1 ? d->lda : d->a_bs1) * 2, bs2 = (uint64_t)(bc2 ? d->lda : d->a_bs2) * 2;
     if (d->a_major == 0) { dims[0] = d->k; dims[1] = d->m; } else { dims[0] = d->m; dims[1] = d->k; }
-    dims[2] = nb1; dims[3] = nb2;
+    dims[2] = bc1 ? 1 : nb1; dims[3] = bc2 ? 1 : nb2;
     str[0] = (uint64_t)d->lda * 2; str[1] = bs1; str[2] = bs2;
     int r = get_tmap(ctx, &ta, d->a, dims, str, 64, d->a_major == 0 ? BM : BK);
     if (r) return r;
   }
   {
     uint64_t dims[4], str[3];
-    const uint64_t bs1 = (uint64_t)(nb1 > 1 ? d->b_bs1 : d->ldb) * 2, bs2 = (uint64_t)(nb2 > 1 ? d->b_bs2 : d->ldb) * 2;
+    const bool bc1 = nb1 <= 1 || d->b_bs1 == 0, bc2 = nb2 <= 1 || d->b_bs2 == 0;
+    const uint64_t bs1 = (uint64_t)(bc1 ? d->ldb : d->b_bs1) * 2, bs2 = (uint64_t)(bc2 ? d->ldb : d->b_bs2) * 2;
     if (d->b_major == 0) { dims[0] = d->k; dims[1] = d->n; } else { dims[0] = d->n; dims[1] = d->k; }
-    dims[2] = nb1; dims[3] = nb2;
+    dims[2] = bc1 ? 1 : nb1; dims[3] = bc2 ? 1 : nb2;
     str[0] = (uint64_t)d->ldb * 2; str[1] = bs1; str[2] = bs2;
     int r = get_tmap(ctx, &tb, d->b, dims, str, 64, d->b_major == 0 ? (uint32_t)bn : BK);
     if (r) return r;
   }
   EpiParams ep;
   ep.c = d->c; ep.c_pre = d->c_preact; ep.res = d->residual; ep.bias = d->bias;
-  ep.ldc = d->ldc; ep.ldr = d->ldr; ep.c_bs1 = d->c_bs1; ep.c_bs2 = d->c_bs2; ep.r_bs1 = d->r_bs1; ep.r_bs2 = d->r_bs2;
+  ep.ldc = d->ldc; ep.ldr = d->ldr; ep.c_bs1 = d->c_bs1; ep.c_bs2 = d->c_bs2; ep.r_bs1 = d->r_bs1; ep.r_bs2 = d->r_bs2; ep.bias_bs1 = d->bias_bs1;
   ep.alpha = d->alpha; ep.act = d->act; ep.accumulate = d->accumulate;
   ep.m = d->m; ep.n = d->n; ep.k = d->k; ep.nb1 = nb1;
+  ep.a_m1 = (nb1 > 1 && d->a_bs1 != 0) ? 1 : 0; ep.a_m2 = (nb2 > 1 && d->a_bs2 != 0) ? 1 : 0;
+  ep.b_m1 = (nb1 > 1 && d->b_bs1 != 0) ? 1 : 0; ep.b_m2 = (nb2 > 1 && d->b_bs2 != 0) ? 1 : 0;
+  ep.drop_thr = 0; ep.inv_keep = 1.f; ep.seed = d->seed;
+  if (d->drop > 0.f) {
+    double t = (double)d->drop * 4294967296.0;
+    ep.drop_thr = (uint32_t)(t > 4294967295.0 ? 4294967295.0 : t);
+    ep.inv_keep = 1.f / (1.f - d->drop);
+  }
   ts_gemm_desc dd = *d;
   dd.batch1 = nb1; dd.batch2 = nb2;
   if (d->out_dtype == TS_BF16) {

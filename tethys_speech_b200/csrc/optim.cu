@@ -1,0 +1,151 @@
+// K19 gradient-norm clipping (tf.clip_by_global_norm V:1243, optimizer clipnorm V:1274) and K20 the Keras-2.10
+// legacy Adam update (W:901, V:1271-1275), multi-tensor over the flat parameter arena.
+// One launch covers every variable: the arena is cut into work items (<= 64K elements of one segment each).
+// HBM-bound: 28 B/param fp32 (+2 B/param for the bf16 compute copy written in the same pass).
+#include <vector>
+#include "ops.cuh"
+
+namespace ts {
+
+struct WorkItem { long long start; long long ld; int rows, cols, seg, pad; };
+
+struct ItemCache {
+  const Segment* key = nullptr;
+  int nseg = 0;
+  WorkItem* d_items = nullptr;
+  int nitems = 0;
+};
+static ItemCache g_items[8];
+
+static int get_items(Ctx* ctx, const Segment* d_segs, int nseg, WorkItem** out, int* nitems, cudaStream_t st) {
+  for (auto& c : g_items)
+    if (c.key == d_segs && c.nseg == nseg) { *out = c.d_items; *nitems = c.nitems; return 0; }
+  std::vector<Segment> h(nseg);
+  TS_CUDA_OK(ctx, cudaMemcpyAsync(h.data(), d_segs, sizeof(Segment) * nseg, cudaMemcpyDeviceToHost, st));
+  TS_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  std::vector<WorkItem> items;
+  const long long chunk = 65536;
+  for (int s = 0; s < nseg; ++s) {
+    const Segment& sg = h[s];
+    if (sg.rows == 1) {
+      for (long long c0 = 0; c0 < sg.cols; c0 += chunk)
+        items.push_back({sg.offset + c0, sg.ld, 1, (int)std::min<long long>(chunk, sg.cols - c0), s, 0});
+    } else {
+      const int rpi = (int)std::max<long long>(1, chunk / sg.cols);
+      for (int r0 = 0; r0 < sg.rows; r0 += rpi)
+        items.push_back({sg.offset + (long long)r0 * sg.ld, sg.ld, std::min(rpi, sg.rows - r0), sg.cols, s, 0});
+    }
+  }
+  ItemCache* slot = nullptr;
+  for (auto& c : g_items) if (!c.key) { slot = &c; break; }
+  if (!slot) { slot = &g_items[0]; cudaFree(slot->d_items); }
+  TS_CUDA_OK(ctx, cudaMalloc(&slot->d_items, sizeof(WorkItem) * items.size()));
+  TS_CUDA_OK(ctx, cudaMemcpyAsync(slot->d_items, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice, st));
+  TS_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  slot->key = d_segs; slot->nseg = nseg; slot->nitems = (int)items.size();
+  *out = slot->d_items; *nitems = slot->nitems;
+  return 0;
+}
+
+void optim_forget(const Segment* d_segs) {
+  for (auto& c : g_items)
+    if (c.key == d_segs) { cudaFree(c.d_items); c = ItemCache(); }
+}
+
+__global__ void zero_f32_kernel(float* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.f;
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, const WorkItem* __restrict__ items,
+                                                    float* __restrict__ sumsq) {
+  __shared__ float red[32];
+  const WorkItem it = items[blockIdx.x];
+  float s = 0.f;
+  for (int r = 0; r < it.rows; ++r) {
+    const float* p = g + it.start + (long long)r * it.ld;
+    for (int c = threadIdx.x; c < it.cols; c += 256) { const float v = p[c]; s += v * v; }
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(&sumsq[it.seg], s);
+}
+
+int grad_sumsq(Ctx* ctx, const float* grads, const Segment* d_segs, int nseg, float* sumsq, cudaStream_t st) {
+  WorkItem* items; int n;
+  int rc = get_items(ctx, d_segs, nseg, &items, &n, st);
+  if (rc) return rc;
+  zero_f32_kernel<<<cdiv(nseg, 256), 256, 0, st>>>(sumsq, nseg);
+  sumsq_kernel<<<n, 256, 0, st>>>(grads, items, sumsq);
+  TS_LAUNCH_OK(ctx);
+  return 0;
+}
+
+__global__ void global_clip_kernel(const float* __restrict__ sumsq, int nseg, float clip, float* scale_out, float* norm_out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < nseg; i += blockDim.x) s += sumsq[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    const float n = sqrtf(s);
+    if (norm_out) norm_out[0] = n;
+    scale_out[0] = clip / fmaxf(n, clip);   // tf.clip_by_global_norm: g * clip / max(norm, clip)
+  }
+}
+int global_clip_scale(Ctx* ctx, const float* sumsq, int nseg, float clip, float* scale_out, float* norm_out, cudaStream_t st) {
+  global_clip_kernel<<<1, 256, 0, st>>>(sumsq, nseg, clip, scale_out, norm_out);
+  TS_LAUNCH_OK(ctx);
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, bf16* __restrict__ p16,
+                                                   const WorkItem* __restrict__ items, float lr_t, float omb1, float omb2,
+                                                   float eps, float clipnorm, const float* __restrict__ pre_scale,
+                                                   const float* __restrict__ sumsq) {
+  const WorkItem it = items[blockIdx.x];
+  float sc = pre_scale ? pre_scale[0] : 1.f;
+  if (clipnorm > 0.f && sumsq) {
+    const float n = sqrtf(sumsq[it.seg]) * sc;
+    sc *= clipnorm / fmaxf(n, clipnorm);
+  }
+  for (int r = 0; r < it.rows; ++r) {
+    const long long base = it.start + (long long)r * it.ld;
+    for (int c = threadIdx.x; c < it.cols; c += 256) {
+      const long long i = base + c;
+      const float gi = g[i] * sc;
+      float mi = m[i], vi = v[i];
+      mi = mi + (gi - mi) * omb1;
+      vi = vi + (gi * gi - vi) * omb2;
+      const float pi = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+      m[i] = mi; v[i] = vi; p[i] = pi;
+      if (p16) p16[i] = __float2bfloat16_rn(pi);
+    }
+  }
+}
+
+int adam_step(Ctx* ctx, float* params, const float* grads, float* m, float* v, void* params_bf16, const Segment* d_segs,
+              int nseg, const AdamArgs& a, cudaStream_t st) {
+  TS_REQUIRE(ctx, a.step >= 1, TS_EINVAL, "adam: step must start at 1");
+  WorkItem* items; int n;
+  int rc = get_items(ctx, d_segs, nseg, &items, &n, st);
+  if (rc) return rc;
+  const double lr_t = (double)a.lr * sqrt(1.0 - pow((double)a.beta2, a.step)) / (1.0 - pow((double)a.beta1, a.step));
+  adam_kernel<<<n, 256, 0, st>>>(params, grads, m, v, (bf16*)params_bf16, items, (float)lr_t, 1.f - a.beta1, 1.f - a.beta2,
+                                 a.eps, a.clipnorm, a.pre_scale, a.sumsq);
+  TS_LAUNCH_OK(ctx);
+  return 0;
+}
+
+__global__ void scale_kernel(float* __restrict__ x, long long n, const float* __restrict__ sdev, float shost) {
+  const float s = (sdev ? sdev[0] : 1.f) * shost;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] *= s;
+}
+int scale_inplace(Ctx* ctx, float* x, long long n, const float* scale_dev, float scale_host, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const int grid = (int)min((n + 255) / 256, (long long)ctx->num_sms * 16);
+  scale_kernel<<<grid, 256, 0, st>>>(x, n, scale_dev, scale_host);
+  TS_LAUNCH_OK(ctx);
+  return 0;
+}
+
+}  // namespace ts

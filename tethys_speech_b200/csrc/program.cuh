@@ -1,0 +1,111 @@
+// Shared plumbing of the model programs (Wav2Vec2 / Whisper train steps): parameter table over a flat arena,
+// workspace bump allocator, GEMM descriptor builder.
+#pragma once
+#include <string>
+#include <vector>
+#include <string.h>
+#include "ops.cuh"
+
+namespace ts {
+
+struct ParamDef {
+  std::string name;
+  long long offset;   // element offset in the fp32 arenas (params / grads / m / v) and the bf16 compute copy
+  int ndim;
+  long long shape[4];
+  int rows, cols;     // 2D segment view: rows x cols with row stride ld (dense: rows = 1, cols = numel)
+  long long ld;
+};
+
+struct ParamTable {
+  std::vector<ParamDef> defs;
+  long long n = 0;  // arena elements
+  // dense tensor, 64-element aligned
+  long long add(const std::string& name, std::initializer_list<long long> shape) {
+    ParamDef d;
+    d.name = name;
+    d.ndim = (int)shape.size();
+    long long numel = 1;
+    int i = 0;
+    for (long long s : shape) { d.shape[i++] = s; numel *= s; }
+    for (; i < 4; ++i) d.shape[i] = 1;
+    n = (n + 63) & ~63ll;
+    d.offset = n;
+    d.rows = 1;
+    d.cols = (int)numel;
+    d.ld = numel;
+    n += numel;
+    defs.push_back(d);
+    return d.offset;
+  }
+  // `parts` matrices [rows, cols_each] fused side by side into one [rows, parts*cols_each (+pad)] block
+  long long add_fused(const std::vector<std::string>& names, long long rows, long long cols_each, long long ld) {
+    n = (n + 63) & ~63ll;
+    const long long base = n;
+    for (size_t j = 0; j < names.size(); ++j) {
+      ParamDef d;
+      d.name = names[j];
+      d.ndim = rows > 1 ? 2 : 1;
+      d.shape[0] = rows > 1 ? rows : cols_each;
+      d.shape[1] = rows > 1 ? cols_each : 1;
+      d.shape[2] = d.shape[3] = 1;
+      d.offset = base + (long long)j * cols_each;
+      d.rows = (int)rows;
+      d.cols = (int)cols_each;
+      d.ld = ld;
+      defs.push_back(d);
+    }
+    n += rows * ld;
+    return base;
+  }
+};
+
+struct Bump {
+  char* base = nullptr;
+  size_t off = 0;
+  void* get(size_t bytes) {
+    const size_t a = (off + 255) & ~size_t(255);
+    off = a + bytes;
+    return base ? base + a : nullptr;
+  }
+};
+
+struct GemmB {
+  ts_gemm_desc d;
+  GemmB(int in_dt, int out_dt) {
+    memset(&d, 0, sizeof(d));
+    d.in_dtype = in_dt; d.out_dtype = out_dt; d.alpha = 1.f; d.batch1 = 1; d.batch2 = 1;
+  }
+  GemmB& A(const void* p, int major, long long ld) { d.a = p; d.a_major = major; d.lda = ld; return *this; }
+  GemmB& B(const void* p, int major, long long ld) { d.b = p; d.b_major = major; d.ldb = ld; return *this; }
+  GemmB& C(void* p, long long ld) { d.c = p; d.ldc = ld; return *this; }
+  GemmB& mnk(int m, int n, int k) { d.m = m; d.n = n; d.k = k; return *this; }
+  GemmB& batch(int b1, int b2) { d.batch1 = b1; d.batch2 = b2; return *this; }
+  GemmB& astride(long long s1, long long s2) { d.a_bs1 = s1; d.a_bs2 = s2; return *this; }
+  GemmB& bstride(long long s1, long long s2) { d.b_bs1 = s1; d.b_bs2 = s2; return *this; }
+  GemmB& cstride(long long s1, long long s2) { d.c_bs1 = s1; d.c_bs2 = s2; return *this; }
+  GemmB& bias(const float* b, long long bs1 = 0) { d.bias = b; d.bias_bs1 = bs1; return *this; }
+  GemmB& gelu(void* preact) { d.act = 1; d.c_preact = preact; return *this; }
+  GemmB& res(const void* r, long long ld, long long s1 = 0, long long s2 = 0) { d.residual = r; d.ldr = ld; d.r_bs1 = s1; d.r_bs2 = s2; return *this; }
+  GemmB& alpha(float a) { d.alpha = a; return *this; }
+  GemmB& drop(float rate, uint64_t seed) { d.drop = rate; d.seed = seed; return *this; }
+  GemmB& acc() { d.accumulate = 1; return *this; }
+  int run(Ctx* ctx, cudaStream_t st) { return gemm(ctx, &d, st); }
+};
+
+#define TS_TRY(expr)        \
+  do {                      \
+    int _rc = (expr);       \
+    if (_rc) return _rc;    \
+  } while (0)
+
+static inline uint64_t site_seed(uint64_t base, uint64_t site) { return base * 0x9E3779B97F4A7C15ull + site * 0xD1B54A32D192ED03ull + 0x632BE59BD9B4E019ull; }
+
+static inline void same_pad(int t_in, int k, int s, int* t_out, int* left, int* right) {
+  const int to = (t_in + s - 1) / s;
+  int pt = (to - 1) * s + k - t_in;
+  if (pt < 0) pt = 0;
+  *t_out = to; *left = pt / 2; *right = pt - pt / 2;
+}
+
+}  // namespace ts

@@ -1,0 +1,207 @@
+"""Host-side plumbing shared by the model hosts: tensor intake (DLPack / numpy / torch), arenas, the Keras-style
+Adam front end over ts_optim, and the MultiWorkerMirroredStrategy shim over torch.distributed (NCCL).
+
+PyTorch is used for device memory, streams and the process group only; all math runs in libtethys.so.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_DT = {_lib.TS_F32: torch.float32, _lib.TS_BF16: torch.bfloat16, _lib.TS_I32: torch.int32, _lib.TS_I64: torch.int64}
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def to_device(x, dtype, device):
+    """Accept torch / numpy / any DLPack producer (e.g. a TensorFlow tensor via tf.experimental.dlpack) and return a
+    contiguous CUDA torch tensor of `dtype` on `device` (zero-copy when it already is one)."""
+    if isinstance(x, torch.Tensor):
+        t = x
+    elif isinstance(x, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(x))
+    elif hasattr(x, "__dlpack__"):
+        t = torch.from_dlpack(x)
+    else:
+        t = torch.as_tensor(np.asarray(x))
+    return t.to(device=device, dtype=dtype, non_blocking=True).contiguous()
+
+
+def view_from_ptr(p, shape, ts_dtype, device):
+    """Wrap library-owned workspace memory as a torch tensor (no copy) through the CUDA array interface."""
+    dt = _DT[ts_dtype]
+    n = int(np.prod(shape))
+    typestr = {torch.float32: "<f4", torch.bfloat16: "<i2", torch.int32: "<i4", torch.int64: "<i8"}[dt]
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(p), False), "version": 3, "strides": None}
+    t = torch.as_tensor(h, device=device)
+    if dt == torch.bfloat16:
+        t = t.view(torch.bfloat16)
+    return t.view(*[int(s) for s in shape])
+
+
+class Strategy:
+    """Stand-in for tf.distribute.MultiWorkerMirroredStrategy (W:1047, V:1473): one process per GPU, NCCL over
+    NVLink/NVSwitch through torch.distributed. With a single process it degenerates to one replica."""
+
+    def __init__(self, backend=None):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+
+            if not dist.is_initialized():
+                if backend is None:
+                    backend = "nccl" if torch.cuda.is_available() else "gloo"
+                if backend == "nccl":
+                    torch.cuda.set_device(self.local_rank)
+                dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world)
+            self.dist = dist
+
+    @property
+    def num_replicas_in_sync(self):
+        return self.world
+
+    def scope(self):
+        import contextlib
+
+        return contextlib.nullcontext()
+
+    def run(self, fn, args=()):
+        return fn(*args)
+
+    def reduce(self, op, value, axis=None):
+        """strategy.reduce(SUM, per_replica_losses, axis=None) — W:848, V:1260."""
+        if self.dist is None:
+            return value
+        t = value if isinstance(value, torch.Tensor) else torch.tensor(float(value))
+        t = t.detach().clone().float()
+        if torch.cuda.is_available() and self.dist.get_backend() == "nccl":
+            t = t.cuda()
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t
+
+    def all_reduce_sum_(self, flat, bucket_elems=None):
+        """K21: in-place SUM all-reduce of a flat gradient arena, issued as a few large buckets."""
+        if self.dist is None:
+            return
+        n = flat.numel()
+        if not bucket_elems or bucket_elems >= n:
+            self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM)
+            return
+        works = []
+        for s in range(0, n, bucket_elems):
+            works.append(self.dist.all_reduce(flat[s:s + bucket_elems], op=self.dist.ReduceOp.SUM, async_op=True))
+        for w in works:
+            w.wait()
+
+    def broadcast_(self, flat, src=0):
+        """K23: weights created under strategy.scope() are mirrored from the chief (W:896-898, V:1266-1268)."""
+        if self.dist is not None:
+            self.dist.broadcast(flat, src=src)
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+
+class ReduceOp:
+    SUM = "SUM"
+
+
+_default_strategy = None
+
+
+def get_strategy():
+    global _default_strategy
+    if _default_strategy is None:
+        _default_strategy = Strategy()
+    return _default_strategy
+
+
+class GradientList(list):
+    """What model.gradient() returns: views into the gradient arena, remembering the owning model so that
+    optimizer.apply_gradients(zip(gradients, variables)) can run the fused multi-tensor update."""
+    owner = None
+
+
+class Adam:
+    """tf.keras.optimizers.Adam of Keras 2.10 (legacy OptimizerV2 formula) — W:901, V:1271-1275.
+    State (m, v) lives in flat fp32 arenas shaped like the model's parameter arena."""
+
+    def __init__(self, learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7, clipnorm=None):
+        self.learning_rate = float(learning_rate)
+        self.beta_1, self.beta_2, self.epsilon = float(beta_1), float(beta_2), float(epsilon)
+        self.clipnorm = clipnorm
+        self.iterations = 0
+        self._state = {}
+
+    def _bind(self, model):
+        key = id(model)
+        if key not in self._state:
+            prog = model._prog
+            st = {"m": torch.zeros_like(prog.params), "v": torch.zeros_like(prog.params), "optim": prog.make_optim()}
+            self._state[key] = st
+        return self._state[key]
+
+    def apply_gradients(self, grads_and_vars, strategy=None, global_clip_norm=None, model=None):
+        """All-reduce (SUM, un-normalised: App. A-13) the gradient arena across replicas, apply the per-variable
+        clipnorm, then the Adam update. `global_clip_norm` fuses tf.clip_by_global_norm into the same pass when no
+        all-reduce sits in between (single replica)."""
+        if model is None:
+            gl = grads_and_vars
+            if not isinstance(gl, GradientList):
+                pairs = list(grads_and_vars)
+                gl = None
+                for g, _ in pairs:
+                    gl = getattr(g, "_ts_owner", None)
+                    if gl is not None:
+                        break
+                model = gl
+            else:
+                model = gl.owner
+        if model is None:
+            raise ValueError("apply_gradients: gradients must come from model.gradient()")
+        prog = model._prog
+        st = self._bind(model)
+        strategy = strategy or get_strategy()
+        lib, ctx = prog.lib, prog.ctx
+        fuse = 0
+        gclip = 0.0
+        if global_clip_norm:
+            if strategy.num_replicas_in_sync > 1:
+                ctx.check(lib.ts_optim_clip_global(st["optim"], ptr(prog.grads), float(global_clip_norm), None, stream_ptr()))
+            else:
+                fuse, gclip = 1, float(global_clip_norm)
+        if strategy.num_replicas_in_sync > 1:
+            strategy.all_reduce_sum_(prog.grads, bucket_elems=32 * 1024 * 1024)
+        self.iterations += 1
+        ctx.check(lib.ts_optim_step(st["optim"], ptr(prog.params), ptr(prog.grads), ptr(st["m"]), ptr(st["v"]),
+                                    ptr(prog.params_lp), self.learning_rate, self.beta_1, self.beta_2, self.epsilon,
+                                    self.iterations, gclip, float(self.clipnorm or 0.0), fuse, stream_ptr()))
+        prog.weights_synced = True  # the update refreshed the bf16 compute copy in the same pass
+
+
+def clip_by_global_norm(gradients, clip_norm):
+    """tf.clip_by_global_norm on the gradient arena, in place — V:1243. Returns (gradients, global_norm)."""
+    model = gradients.owner
+    prog = model._prog
+    opt = prog.make_optim()
+    norm = torch.zeros(1, device=prog.device)
+    prog.ctx.check(prog.lib.ts_optim_clip_global(opt, ptr(prog.grads), float(clip_norm), ptr(norm), stream_ptr()))
+    return gradients, norm

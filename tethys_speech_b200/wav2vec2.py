@@ -1,0 +1,431 @@
+"""Host-side mirror of the reference's Wav2Vec2 surface (speech_jobs/wav2vec2_dist.py = V, wav2vec2_single.py = VS,
+whisper_single.py = WS): same class names, call signatures, output dict keys and step functions, driving the
+native program in libtethys.so (csrc/w2v_program.cu) through ctypes. No TensorFlow, no CPU fallback.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .runtime import (Adam, GradientList, ReduceOp, Strategy, clip_by_global_norm, get_strategy, ptr, stream_ptr,
+                      to_device, view_from_ptr)
+
+
+class Wav2Vec2Config:
+    """Same attributes and presets as Wav2Vec2Config — V:24-128 (tiny / small (default) / base), plus the
+    extrapolated 'large' preset of SURVEY.md D8 which the reference does not have."""
+
+    def __init__(self, model_size="small"):
+        if model_size == "small":
+            self.hidden_size, self.num_hidden_layers, self.num_attention_heads, self.intermediate_size = 512, 6, 8, 2048
+            self.conv_dim = [256] * 5
+            self.conv_stride = [5, 2, 2, 2, 2]
+            self.conv_kernel = [10, 3, 3, 3, 2]
+            self.num_conv_pos_embeddings, self.num_conv_pos_embedding_groups = 64, 8
+            self.num_codevectors_per_group, self.codevector_dim, self.proj_codevector_dim = 160, 128, 128
+            self.classifier_proj_size = 128
+        elif model_size == "tiny":
+            self.hidden_size, self.num_hidden_layers, self.num_attention_heads, self.intermediate_size = 256, 4, 4, 1024
+            self.conv_dim = [128] * 4
+            self.conv_stride = [5, 2, 2, 2]
+            self.conv_kernel = [10, 3, 3, 2]
+            self.num_conv_pos_embeddings, self.num_conv_pos_embedding_groups = 32, 4
+            self.num_codevectors_per_group, self.codevector_dim, self.proj_codevector_dim = 80, 64, 64
+            self.classifier_proj_size = 64
+        elif model_size == "large":
+            self.hidden_size, self.num_hidden_layers, self.num_attention_heads, self.intermediate_size = 1024, 24, 16, 4096
+            self.conv_dim = [512] * 7
+            self.conv_stride = [5, 2, 2, 2, 2, 2, 2]
+            self.conv_kernel = [10, 3, 3, 3, 3, 2, 2]
+            self.num_conv_pos_embeddings, self.num_conv_pos_embedding_groups = 128, 16
+            self.num_codevectors_per_group, self.codevector_dim, self.proj_codevector_dim = 320, 768, 768
+            self.classifier_proj_size = 256
+        else:  # base
+            self.hidden_size, self.num_hidden_layers, self.num_attention_heads, self.intermediate_size = 768, 12, 12, 3072
+            self.conv_dim = [512] * 7
+            self.conv_stride = [5, 2, 2, 2, 2, 2, 2]
+            self.conv_kernel = [10, 3, 3, 3, 3, 2, 2]
+            self.num_conv_pos_embeddings, self.num_conv_pos_embedding_groups = 128, 16
+            self.num_codevectors_per_group, self.codevector_dim, self.proj_codevector_dim = 320, 256, 256
+            self.classifier_proj_size = 256
+        self.model_size = model_size
+        self.feat_extract_norm = "group"
+        self.feat_extract_activation = "gelu"
+        self.conv_bias = False
+        self.hidden_act = "gelu"
+        self.hidden_dropout = 0.1
+        self.activation_dropout = 0.1
+        self.attention_dropout = 0.1
+        self.layer_norm_eps = 1e-5
+        self.num_codevector_groups = 2
+        self.contrastive_logits_temperature = 0.1
+        self.num_negatives = 100
+        self.diversity_loss_weight = 0.1
+        self.mask_time_prob = 0.05      # set but never read by the reference
+        self.mask_time_length = 10
+        self.mask_feature_prob = 0.0
+        self.mask_feature_length = 10
+        self.vocab_size = 32
+        self.do_stable_layer_norm = True
+        self.use_weighted_layer_sum = False
+
+
+# Keras trainable_variables order of Wav2Vec2ForPreTraining (attribute-tracking order, V:746-766, V:229-281)
+def _keras_order(cfg):
+    names = []
+    for i in range(len(cfg.conv_dim)):
+        names += [f"fe.conv{i}.kernel", f"fe.conv{i}.gn.gamma", f"fe.conv{i}.gn.beta"]
+    names += ["fe.pos_conv.kernel", "fe.pos_conv.bias", "fe.layer_norm.gamma", "fe.layer_norm.beta",
+              "feature_projection.kernel", "feature_projection.bias",
+              "feature_projection_layer_norm.gamma", "feature_projection_layer_norm.beta"]
+    for l in range(cfg.num_hidden_layers):
+        p = f"encoder.layers.{l}."
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            names += [p + f"attention.{n}.kernel", p + f"attention.{n}.bias"]
+        names += [p + "attention_layer_norm.gamma", p + "attention_layer_norm.beta",
+                  p + "feed_forward.intermediate_dense.kernel", p + "feed_forward.intermediate_dense.bias",
+                  p + "feed_forward.output_dense.kernel", p + "feed_forward.output_dense.bias",
+                  p + "feed_forward_layer_norm.gamma", p + "feed_forward_layer_norm.beta"]
+    names += ["quantizer.codevectors", "quantizer.projection.kernel", "quantizer.projection.bias",
+              "project_hid.dense.kernel", "project_hid.dense.bias", "project_hid.layer_norm.gamma", "project_hid.layer_norm.beta",
+              "project_q.dense.kernel", "project_q.dense.bias", "project_q.layer_norm.gamma", "project_q.layer_norm.beta"]
+    return names
+
+
+class _Program:
+    """Owns the arenas (torch memory) and the ts_w2v handle."""
+
+    def __init__(self, cfg, precision, device):
+        self.ctx = _lib.context(device)
+        self.lib = self.ctx.lib
+        self.device = torch.device("cuda", device)
+        self.precision = {"fp32": _lib.TS_F32, "float32": _lib.TS_F32, "bf16": _lib.TS_BF16, "bfloat16": _lib.TS_BF16}[precision]
+        c = _lib.W2VConfig()
+        c.hidden, c.layers, c.heads, c.ffn = cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads, cfg.intermediate_size
+        c.n_conv = len(cfg.conv_dim)
+        for i in range(c.n_conv):
+            c.conv_dim[i], c.conv_kernel[i], c.conv_stride[i] = cfg.conv_dim[i], cfg.conv_kernel[i], cfg.conv_stride[i]
+        c.pos_kernel, c.pos_groups = cfg.num_conv_pos_embeddings, cfg.num_conv_pos_embedding_groups
+        c.cv_groups, c.cv_per_group = cfg.num_codevector_groups, cfg.num_codevectors_per_group
+        c.cv_dim, c.proj_dim = cfg.codevector_dim, cfg.proj_codevector_dim
+        c.num_negatives = cfg.num_negatives
+        c.ln_eps, c.temperature, c.diversity_weight = cfg.layer_norm_eps, cfg.contrastive_logits_temperature, cfg.diversity_loss_weight
+        c.hidden_dropout, c.activation_dropout, c.attention_dropout = cfg.hidden_dropout, cfg.activation_dropout, cfg.attention_dropout
+        self.ccfg = c
+        h = C.c_void_p()
+        self.ctx.check(self.lib.ts_w2v_create(self.ctx.h, C.byref(c), self.precision, C.byref(h)))
+        self.h = h
+        self.n = int(self.lib.ts_w2v_arena_elems(h))
+        self.params = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        self.grads = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        self.params_lp = torch.zeros(self.n, dtype=torch.bfloat16, device=self.device) if self.precision == _lib.TS_BF16 else None
+        self.workspace = None
+        self.ws_shape = None
+        self.weights_synced = False
+        self.info = {}
+        name = C.create_string_buffer(256)
+        off, nd, ld = C.c_int64(), C.c_int32(), C.c_int64()
+        shape = (C.c_int64 * 4)()
+        for i in range(self.lib.ts_w2v_num_params(h)):
+            self.ctx.check(self.lib.ts_w2v_param_info(h, i, name, 256, C.byref(off), C.byref(nd), shape, C.byref(ld)))
+            shp = tuple(int(shape[j]) for j in range(nd.value))
+            self.info[name.value.decode()] = (int(off.value), shp, int(ld.value))
+        self.stage_ends = [int(self.lib.ts_w2v_stage_end(h, s)) for s in range(self.lib.ts_w2v_num_stages(h))]
+        self._optim = None
+
+    def view(self, arena, name):
+        off, shp, ld = self.info[name]
+        rows = shp[0] if len(shp) == 2 else 1
+        cols = int(np.prod(shp)) // rows
+        if len(shp) == 2 and ld != cols:      # column slice of a fused block (q/k/v)
+            return arena.as_strided((rows, cols), (ld, 1), off)
+        return arena[off:off + int(np.prod(shp))].view(*shp)
+
+    def make_optim(self):
+        if self._optim is None:
+            names = list(self.info)
+            n = len(names)
+            offs = (C.c_int64 * n)(); rows = (C.c_int32 * n)(); cols = (C.c_int32 * n)(); lds = (C.c_int64 * n)()
+            for i, k in enumerate(names):
+                off, shp, ld = self.info[k]
+                r = shp[0] if (len(shp) == 2 and ld != int(np.prod(shp)) // shp[0]) else 1
+                offs[i], rows[i], cols[i], lds[i] = off, r, int(np.prod(shp)) // r, ld if r > 1 else int(np.prod(shp))
+            o = C.c_void_p()
+            self.ctx.check(self.lib.ts_optim_create(self.ctx.h, n, offs, rows, cols, lds, self.n, C.byref(o)))
+            self._optim = o
+        return self._optim
+
+    def ensure_workspace(self, B, N):
+        if self.ws_shape == (B, N):
+            return
+        need = int(self.lib.ts_w2v_workspace_bytes(self.h, B, N))
+        if need < 0:
+            self.ctx.check(-2)
+        if self.workspace is None or self.workspace.numel() < need:
+            self.workspace = None
+            self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        self.ctx.check(self.lib.ts_w2v_bind(self.h, ptr(self.params), ptr(self.grads), ptr(self.params_lp), ptr(self.workspace),
+                                            self.workspace.numel()))
+        self.ws_shape = (B, N)
+
+    def sync_weights(self):
+        if not self.weights_synced:
+            if self.workspace is None:
+                return
+            self.ctx.check(self.lib.ts_w2v_sync_compute_weights(self.h, stream_ptr()))
+            self.weights_synced = True
+
+    def buffer(self, name):
+        p, dt, nd = C.c_void_p(), C.c_int32(), C.c_int32()
+        shape = (C.c_int64 * 4)()
+        self.ctx.check(self.lib.ts_w2v_get_buffer(self.h, name.encode(), C.byref(p), C.byref(dt), C.byref(nd), shape))
+        return view_from_ptr(p.value, [shape[i] for i in range(nd.value)], dt.value, self.device)
+
+
+def _glorot_uniform(gen, shape, fan_in, fan_out, device):
+    limit = math.sqrt(6.0 / (fan_in + fan_out))
+    return (torch.rand(shape, generator=gen, dtype=torch.float32, device=device) * 2 - 1) * limit
+
+
+class Wav2Vec2Model:
+    """Handle mirroring `Wav2Vec2Model` (V:746-825): exposes the sub-layer names the reference code touches."""
+
+    def __init__(self, owner):
+        self._owner = owner
+        self.config = owner.config
+
+    def project_hid(self, hidden_states, training=False):
+        return self._owner._cached("projected_states", hidden_states)
+
+    def project_q(self, hidden_states, training=False):
+        return self._owner._cached("projected_quantized_features", hidden_states)
+
+
+class Wav2Vec2ForPreTraining:
+    """Mirror of `Wav2Vec2ForPreTraining` — V:828-937. `model(inputs, training=True)` returns the same dict keys;
+    `_compute_contrastive_loss` / `_compute_diversity_loss` / `_sample_negative_indices` keep their signatures."""
+
+    def __init__(self, config, precision="bf16", device=None, seed=0):
+        self.config = config
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        self._prog = _Program(config, precision, device)
+        self.wav2vec2 = Wav2Vec2Model(self)
+        self.num_negatives = config.num_negatives
+        self.contrastive_logits_temperature = config.contrastive_logits_temperature
+        self.diversity_loss_weight = config.diversity_loss_weight
+        self._rng = torch.Generator(device=self._prog.device)
+        self._rng.manual_seed(1234 + seed)
+        self._step_seed = seed * 1000003
+        self._last = {}
+        self._init_weights(seed)
+        names = _keras_order(config)
+        assert set(names) == set(self._prog.info), "parameter table mismatch"
+        self.variable_names = names
+        self.trainable_variables = [self._prog.view(self._prog.params, n) for n in names]
+
+    # -- weights ------------------------------------------------------------------------------------------
+    def _init_weights(self, seed):
+        """Keras defaults: glorot_uniform kernels, zero biases, ones/zeros norms, N(0,1) codebook (V:570-577)."""
+        p = self._prog
+        gen = torch.Generator(device=p.device)
+        gen.manual_seed(seed)
+        for name, (off, shp, ld) in p.info.items():
+            v = p.view(p.params, name)
+            if name.endswith(".kernel"):
+                if len(shp) == 3:
+                    k, cin, cout = shp
+                    v.copy_(_glorot_uniform(gen, shp, k * cin, k * cout, p.device))
+                else:
+                    v.copy_(_glorot_uniform(gen, shp, shp[0], shp[1], p.device))
+            elif name.endswith(".gamma"):
+                v.fill_(1.0)
+            elif name == "quantizer.codevectors":
+                v.copy_(torch.randn(shp, generator=gen, dtype=torch.float32, device=p.device))
+            else:
+                v.zero_()
+        p.weights_synced = False
+
+    def set_weights(self, weights):
+        """Load a {name: array} dict (Keras layouts, names as in `variable_names`)."""
+        p = self._prog
+        for k, w in weights.items():
+            p.view(p.params, k).copy_(to_device(w, torch.float32, p.device).view(p.info[k][1]))
+        p.weights_synced = False
+
+    def get_weights(self):
+        p = self._prog
+        return {k: p.view(p.params, k).detach().clone() for k in self.variable_names}
+
+    def broadcast_weights(self, strategy):
+        strategy.broadcast_(self._prog.params)
+        self._prog.weights_synced = False
+
+    # -- forward ------------------------------------------------------------------------------------------
+    def _sample_negative_indices(self, sequence_length, batch_size):
+        """V:907-937: per batch row, the positions of the `actual` smallest of T uniform ints (ties: lower index
+        first), tiled to num_negatives, then the same list for every time step. Returns int32 [B, T, K]."""
+        T, K = int(sequence_length), self.num_negatives
+        actual = max(min(K, T - 1), 1)
+        r = torch.randint(0, T, (int(batch_size), T), generator=self._rng, device=self._prog.device)
+        order = torch.sort(-r.float(), dim=1, descending=True, stable=True).indices[:, :actual]
+        if actual < K:
+            order = order.repeat(1, math.ceil(K / actual))[:, :K]
+        return order.to(torch.int32).unsqueeze(1).expand(-1, T, -1)
+
+    def num_frames(self, n_samples):
+        t = int(n_samples)
+        for s in self.config.conv_stride:
+            t = -(-t // s)
+        return t
+
+    def __call__(self, inputs, attention_mask=None, output_attentions=False, output_hidden_states=False, training=False,
+                 neg_indices=None, loss_div=1.0, dropout=True):
+        """inputs: [B, N] waveform (torch / numpy / DLPack producer). With training=True the quantiser, the projection
+        heads and the loss run too (V:782-789, V:852-861). `neg_indices` ([B,K] or [B,T,K] int32) injects the negative
+        sample positions (parity tests); otherwise they are drawn like V:907-937. `dropout=False` disables the dropout
+        layers (parity runs)."""
+        if attention_mask is not None or output_attentions or output_hidden_states:
+            raise NotImplementedError("attention_mask / output_attentions / output_hidden_states are not on the train path")
+        p = self._prog
+        x = to_device(inputs, torch.float32, p.device)
+        if x.dim() != 2:
+            raise ValueError("inputs must be [batch, samples]")
+        B, N = x.shape
+        p.ensure_workspace(B, N)
+        p.sync_weights()
+        T = self.num_frames(N)
+        if neg_indices is None:
+            neg = self._sample_negative_indices(T, B)[:, 0, :].contiguous()
+        else:
+            neg = to_device(neg_indices, torch.int32, p.device)
+        if neg.dim() == 2:
+            neg_bs, neg_ts = neg.shape[1], 0
+        else:
+            neg = neg.contiguous()
+            neg_bs, neg_ts = neg.shape[1] * neg.shape[2], neg.shape[2]
+        if neg.shape[-1] != self.num_negatives:
+            raise ValueError(f"neg_indices last dim must be num_negatives={self.num_negatives}")
+        self._step_seed += 1
+        p.ctx.check(p.lib.ts_w2v_forward(p.h, ptr(x), B, N, ptr(neg), neg_bs, neg_ts, float(loss_div), self._step_seed,
+                                         1 if (training and dropout) else 0, stream_ptr()))
+        self._last = {"x": x, "neg": neg, "training": training}
+        scal = p.buffer("scalars")
+        out = {"last_hidden_state": p.buffer("last_hidden_state"), "extract_features": p.buffer("extract_features")}
+        if training:
+            out["quantized_features"] = p.buffer("quantized_features")
+            out["codevector_perplexity"] = scal[2]
+            out["projected_quantized_features"] = p.buffer("projected_quantized_features")
+            out["projected_states"] = p.buffer("projected_states")
+            out["code_indices"] = p.buffer("code_indices")
+            out["loss"] = scal[0]
+            out["contrastive_loss"] = scal[1]
+            out["contrastive_logits"] = p.buffer("contrastive_logits")
+        self._last["out"] = out
+        return out
+
+    call = __call__
+
+    def _cached(self, key, _arg):
+        return self._last["out"][key]
+
+    def _compute_contrastive_loss(self, hidden_states, quantized_states):
+        """V:865-899 → (logits [B,T,1+K], mean CE). Computed inside the fused forward of the last call."""
+        o = self._last["out"]
+        return o["contrastive_logits"], o["contrastive_loss"]
+
+    def _compute_diversity_loss(self, perplexity):
+        """V:901-905."""
+        return -perplexity
+
+    # -- backward -----------------------------------------------------------------------------------------
+    def gradient(self, stage_from=0, stage_to=10 ** 6):
+        """tape.gradient(loss, model.trainable_variables) (V:1234) with None→zeros (V:1237-1240): fills the
+        gradient arena and returns views in `trainable_variables` order."""
+        p = self._prog
+        p.ctx.check(p.lib.ts_w2v_backward(p.h, int(stage_from), int(stage_to), stream_ptr()))
+        gl = GradientList(p.view(p.grads, n) for n in self.variable_names)
+        gl.owner = self
+        for g in gl:
+            g._ts_owner = self
+        return gl
+
+    def save_weights(self, path):
+        torch.save({k: v.cpu() for k, v in self.get_weights().items()}, path)
+
+
+def create_full_model(model_type="pretraining", model_size="small", num_negatives=100, mask_time_prob=0.065,
+                      mask_time_length=10, precision="bf16", device=None, seed=0):
+    """V:1157-1182. Only model_type='pretraining' is on the hot path (SURVEY §8 f-2 lists the other heads as next)."""
+    config = Wav2Vec2Config(model_size=model_size)
+    config.num_negatives = num_negatives
+    config.mask_time_prob = mask_time_prob
+    config.mask_time_length = mask_time_length
+    if model_type != "pretraining":
+        raise NotImplementedError(f"model_type={model_type!r}: only the pre-training step is implemented")
+    return Wav2Vec2ForPreTraining(config, precision=precision, device=device, seed=seed)
+
+
+def create_dummy_dataset(batch_size, audio_length=32000, num_samples=50, seed=1234, device=None):
+    """V:1123-1153: 50 × N(0,1) waveforms of `audio_length` samples (+ scalar 0 label), batched with
+    drop_remainder and repeated. Seeded (the reference is not). Yields (features [B,N] pinned host fp32, labels)."""
+    rng = np.random.default_rng(seed)
+    data = torch.from_numpy(rng.standard_normal((num_samples, audio_length), dtype=np.float32))
+    if torch.cuda.is_available():
+        data = data.pin_memory()
+    labels = torch.zeros(num_samples)
+
+    def gen():
+        nb = num_samples // batch_size
+        if nb == 0:
+            raise ValueError("batch_size larger than the dataset")
+        while True:
+            for i in range(nb):
+                yield data[i * batch_size:(i + 1) * batch_size], labels[i * batch_size:(i + 1) * batch_size]
+
+    return gen()
+
+
+def train_step(model, inputs, optimizer, neg_indices=None, dropout=True):
+    """Single-device step — VS:1119-1176: forward, contrastive + diversity loss, NaN guard, gradients (None→0),
+    clip_by_global_norm(1.0), optimizer.apply_gradients (clipnorm + Adam). Returns the loss (device scalar)."""
+    features, labels = inputs
+    if features.shape[0] == 0:
+        return torch.zeros(())
+    outputs = model(features, training=True, neg_indices=neg_indices, dropout=dropout)
+    logits, contrastive_loss = model._compute_contrastive_loss(outputs["projected_states"], outputs["projected_quantized_features"])
+    loss = outputs["loss"]  # = contrastive + diversity_loss_weight * (-perplexity), NaN→0 (V:1220-1228), fused on device
+    gradients = model.gradient()
+    optimizer.apply_gradients(gradients, global_clip_norm=1.0)
+    return loss
+
+
+def legacy_train_step(model, inputs, optimizer, neg_indices=None, dropout=True):
+    """Legacy step of whisper_single.py — WS:1143-1180: no clipping, no NaN guard."""
+    features, labels = inputs
+    outputs = model(features, training=True, neg_indices=neg_indices, dropout=dropout)
+    loss = outputs["loss"]
+    gradients = model.gradient()
+    optimizer.apply_gradients(gradients)
+    return loss
+
+
+def distributed_train_step(strategy, model, dist_inputs, optimizer, neg_indices=None, dropout=True):
+    """V:1186-1260: per replica loss/N → grads → local clip_by_global_norm(1.0) → apply_gradients (all-reduce SUM,
+    per-variable clipnorm, Adam) → strategy.reduce(SUM) of the scaled losses."""
+
+    def step(inputs):
+        features, labels = inputs
+        if features.shape[0] == 0:
+            return torch.zeros((), device=model._prog.device)
+        n = float(strategy.num_replicas_in_sync)
+        outputs = model(features, training=True, neg_indices=neg_indices, loss_div=n, dropout=dropout)
+        scaled_loss = outputs["loss"] / n
+        gradients = model.gradient()
+        optimizer.apply_gradients(gradients, strategy=strategy, global_clip_norm=1.0)
+        return scaled_loss
+
+    per_replica_losses = strategy.run(step, args=(dist_inputs,))
+    return strategy.reduce(ReduceOp.SUM, per_replica_losses, axis=None)
