@@ -49,6 +49,8 @@ void ts_destroy(ts_ctx* ctx);
 const char* ts_last_error(ts_ctx* ctx);
 /* returns TS_EWATCHDOG if any kernel since the last check gave up on an mbarrier wait (synchronises). */
 int ts_watchdog_check(ts_ctx* ctx);
+/* number of kernel-launch sites this context has passed since creation (bench.py's gpu_launches). */
+int64_t ts_launch_count(ts_ctx* ctx);
 
 /* ---- K9: GEMM with fused epilogue ------------------------------------------------------------
  * Replaces every tf.keras.layers.Dense / tf.matmul / Conv1D-as-GEMM on the path:
@@ -151,6 +153,35 @@ int ts_w2v_forward(ts_w2v* m, const float* wave /*[B,N]*/, int batch, int n_samp
 int ts_w2v_backward(ts_w2v* m, int stage_from, int stage_to, void* stream);
 /* named views into the workspace of the last forward ("scalars" = {loss, contrastive, perplexity, raw sum}). */
 int ts_w2v_get_buffer(ts_w2v* m, const char* name, void** ptr, int32_t* dtype, int32_t* ndim, int64_t* shape4);
+
+/* ---- Whisper encoder-decoder program ---------------------------------------------------------------------
+ * Replaces WhisperForConditionalGeneration.call(features, labels=labels, training=True) and tape.gradient of
+ * distributed_train_step's per-replica body (W:547-616, W:826-833). features [B, n_mels, T_mel] fp32,
+ * labels [B, S] int32. Bug-compatible with the reference (anti-causal decoder mask, double label shift).
+ * Backward stages: 0 lm_head + final decoder LN | 1..Ld decoder layers Ld-1..0 | Ld+1 embedding + final encoder LN |
+ * Ld+2..Ld+1+Le encoder layers Le-1..0 | Ld+Le+2 conv stem.
+ */
+typedef struct {
+  int32_t d_model, enc_layers, dec_layers, heads, d_ff, n_mels, n_ctx, vocab, max_target, start_token;
+  float ln_eps, dropout, attention_dropout, activation_dropout;
+} ts_whisper_config;
+
+typedef struct ts_whisper ts_whisper;
+int ts_whisper_create(ts_ctx* ctx, const ts_whisper_config* cfg, int precision, ts_whisper** out);
+void ts_whisper_destroy(ts_whisper* m);
+int64_t ts_whisper_arena_elems(ts_whisper* m);
+int ts_whisper_num_params(ts_whisper* m);
+int ts_whisper_param_info(ts_whisper* m, int i, char* name, int name_cap, int64_t* offset, int32_t* ndim, int64_t* shape4,
+                          int64_t* ld);
+int ts_whisper_num_stages(ts_whisper* m);
+int64_t ts_whisper_stage_end(ts_whisper* m, int stage);
+int64_t ts_whisper_workspace_bytes(ts_whisper* m, int batch, int t_mel, int seq);
+int ts_whisper_bind(ts_whisper* m, float* params, float* grads, void* params_bf16, void* workspace, int64_t workspace_bytes);
+int ts_whisper_sync_compute_weights(ts_whisper* m, void* stream);
+int ts_whisper_forward(ts_whisper* m, const float* features, int batch, int t_mel, const int32_t* labels, int seq, uint64_t seed,
+                       int training, int compute_loss, void* stream);
+int ts_whisper_backward(ts_whisper* m, int stage_from, int stage_to, void* stream);
+int ts_whisper_get_buffer(ts_whisper* m, const char* name, void** ptr, int32_t* dtype, int32_t* ndim, int64_t* shape4);
 
 #ifdef __cplusplus
 }

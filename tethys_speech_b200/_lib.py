@@ -73,6 +73,7 @@ SYMBOLS = {
     "ts_destroy": (None, [_P]),
     "ts_last_error": (C.c_char_p, [_P]),
     "ts_watchdog_check": (_I, [_P]),
+    "ts_launch_count": (_L, [_P]),
     "ts_gemm": (_I, [_P, C.POINTER(GemmDesc), _P]),
     "ts_optim_create": (_I, [_P, _I, C.POINTER(_L), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L), _L, C.POINTER(_P)]),
     "ts_optim_destroy": (None, [_P]),
@@ -92,6 +93,19 @@ SYMBOLS = {
     "ts_w2v_forward": (_I, [_P, _P, _I, _I, _P, _L, _L, _F, C.c_uint64, _I, _P]),
     "ts_w2v_backward": (_I, [_P, _I, _I, _P]),
     "ts_w2v_get_buffer": (_I, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L)]),
+    "ts_whisper_create": (_I, [_P, C.POINTER(WhisperCfg), _I, C.POINTER(_P)]),
+    "ts_whisper_destroy": (None, [_P]),
+    "ts_whisper_arena_elems": (_L, [_P]),
+    "ts_whisper_num_params": (_I, [_P]),
+    "ts_whisper_param_info": (_I, [_P, _I, C.c_char_p, _I, C.POINTER(_L), C.POINTER(_I), C.POINTER(_L), C.POINTER(_L)]),
+    "ts_whisper_num_stages": (_I, [_P]),
+    "ts_whisper_stage_end": (_L, [_P, _I]),
+    "ts_whisper_workspace_bytes": (_L, [_P, _I, _I, _I]),
+    "ts_whisper_bind": (_I, [_P, _P, _P, _P, _P, _L]),
+    "ts_whisper_sync_compute_weights": (_I, [_P, _P]),
+    "ts_whisper_forward": (_I, [_P, _P, _I, _I, _P, _I, C.c_uint64, _I, _I, _P]),
+    "ts_whisper_backward": (_I, [_P, _I, _I, _P]),
+    "ts_whisper_get_buffer": (_I, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L)]),
 }
 
 _lib = None

@@ -83,6 +83,11 @@ int ts_watchdog_check(ts_ctx* ctx) {
   return TS_OK;
 }
 
+int64_t ts_launch_count(ts_ctx* ctx) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  return c ? (int64_t)c->launches : 0;
+}
+
 int ts_gemm(ts_ctx* ctx, const ts_gemm_desc* d, void* stream) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   if (!c || !d) return TS_EINVAL;

@@ -25,6 +25,7 @@ struct Ctx {
   void* encode_tiled = nullptr;
   int* d_watchdog = nullptr;   // device int: set non-zero by a kernel whose mbarrier wait timed out
   void* tmap_cache = nullptr;  // opaque tensor-map cache (gemm_tc.cu)
+  unsigned long long launches = 0;  // kernel-launch sites passed (TS_LAUNCH_OK); reported by ts_launch_count
 };
 
 int set_err(Ctx* c, int code, const char* fmt, ...);
@@ -40,7 +41,8 @@ int set_err(Ctx* c, int code, const char* fmt, ...);
 #define TS_LAUNCH_OK(ctx)                                                                  \
   do {                                                                                     \
     cudaError_t _e = cudaGetLastError();                                                   \
-    if (_e != cudaSuccess)                                                                 \
+    (ctx)->launches++;                                                                     \
+    if (_e != cudaSuccess)                                                          \
       return ts::set_err((ctx), TS_ECUDA, "kernel launch failed: %s (%s:%d)",              \
                          cudaGetErrorString(_e), __FILE__, __LINE__);                      \
   } while (0)

@@ -92,13 +92,19 @@ int contrastive_fwd_bwd(Ctx*, int dt, const float* S, long long ld, const int* n
 // grad_scale/(B*(S-1)), accumulates loss sum.
 int ce_fwd_bwd(Ctx*, int dt, const void* logits, void* dlogits, long long ldv, const int* labels, float* loss_sum,
                int B, int S, int V, float grad_scale, cudaStream_t);
-// embedding gather + positional encoding: out[b,s,:] = table[ids[b,s],:] + pe[s,:]; ids built from labels
-// shifted right with start token (W:559-563) when shift != 0.
+// embedding gather + positional encoding (+ dropout): out[b,s,:] = drop(table[ids[b,s],:] + pe[s,:]); the ids are the
+// labels shifted right with the start token (W:559-563). embed_bwd scatter-adds drop(dout) into the fp32 table grad.
 int embed_fwd(Ctx*, int dt, const void* table, const int* labels, const float* pe, void* out, int B, int S, int D,
-              int start_token, cudaStream_t);
+              int start_token, float drop, uint64_t seed, cudaStream_t);
 int embed_bwd(Ctx*, int dt, const void* dout, const int* labels, float* dtable, int B, int S, int D,
-              int start_token, cudaStream_t);
-int add_pe(Ctx*, int dt, void* x, const float* pe, int B, int S, int D, cudaStream_t);
+              int start_token, float drop, uint64_t seed, cudaStream_t);
+// y[b,t,:] = drop(x[b,t,:] + pe[t,:]); x has rpb_in rows per batch, y is dense [B,T,D]
+int add_pe_rows(Ctx*, int dt, const void* x, long long rpb_in, const float* pe, void* y, int B, int T, int D, float drop,
+                uint64_t seed, cudaStream_t);
+// du = da * gelu'(u) on [B, rpb, C] blocks (rows >= T zeroed); da dense (da_rpb) or col2im of a strided conv's dcol
+int gelu_bwd_rows(Ctx*, int dt, const void* da, long long da_rpb, const Col2imSrc* col, const void* u, void* du,
+                  long long rpb, int B, int T, int C, cudaStream_t);
+int zero_rows(Ctx*, int dt, void* x, long long rpb, int row_from, int B, int C, cudaStream_t);
 
 // ---- optim.cu ------------------------------------------------------------------------------------
 // A parameter "segment": rows x cols block with row stride ld inside the flat arena (dense: rows = 1).

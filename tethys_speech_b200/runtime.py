@@ -53,6 +53,89 @@ def view_from_ptr(p, shape, ts_dtype, device):
     return t.view(*[int(s) for s in shape])
 
 
+class ProgramBase:
+    """Arenas (torch memory) + a native model-program handle (ts_w2v / ts_whisper). `prefix` selects the C-ABI family."""
+
+    def __init__(self, prefix, precision, device, create):
+        self.prefix = prefix
+        self.ctx = _lib.context(device)
+        self.lib = self.ctx.lib
+        self.device = torch.device("cuda", device)
+        self.precision = {"fp32": _lib.TS_F32, "float32": _lib.TS_F32, "bf16": _lib.TS_BF16, "bfloat16": _lib.TS_BF16}[precision]
+        h = C.c_void_p()
+        self.ctx.check(create(self.ctx.h, self.precision, C.byref(h)))
+        self.h = h
+        self.n = int(self._f("arena_elems")(h))
+        self.params = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        self.grads = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        self.params_lp = torch.zeros(self.n, dtype=torch.bfloat16, device=self.device) if self.precision == _lib.TS_BF16 else None
+        self.workspace = None
+        self.ws_key = None
+        self.weights_synced = False
+        self.info = {}
+        name = C.create_string_buffer(256)
+        off, nd, ld = C.c_int64(), C.c_int32(), C.c_int64()
+        shape = (C.c_int64 * 4)()
+        for i in range(self._f("num_params")(h)):
+            self.ctx.check(self._f("param_info")(h, i, name, 256, C.byref(off), C.byref(nd), shape, C.byref(ld)))
+            shp = tuple(int(shape[j]) for j in range(nd.value))
+            self.info[name.value.decode()] = (int(off.value), shp, int(ld.value))
+        self.stage_ends = [int(self._f("stage_end")(h, s)) for s in range(self._f("num_stages")(h))]
+        self._optim = None
+
+    def _f(self, name):
+        return getattr(self.lib, f"{self.prefix}_{name}")
+
+    def view(self, arena, name):
+        off, shp, ld = self.info[name]
+        numel = int(np.prod(shp))
+        if len(shp) == 2 and ld != numel:     # column slice of a fused / padded block (q/k/v, lm_head)
+            return arena.as_strided(shp, (ld, 1), off)
+        return arena[off:off + numel].view(*shp)
+
+    def make_optim(self):
+        if self._optim is None:
+            names = list(self.info)
+            n = len(names)
+            offs = (C.c_int64 * n)(); rows = (C.c_int32 * n)(); cols = (C.c_int32 * n)(); lds = (C.c_int64 * n)()
+            for i, k in enumerate(names):
+                off, shp, ld = self.info[k]
+                numel = int(np.prod(shp))
+                r = shp[0] if (len(shp) == 2 and ld != numel) else 1
+                offs[i], rows[i], cols[i], lds[i] = off, r, numel // r, ld if r > 1 else numel
+            o = C.c_void_p()
+            self.ctx.check(self.lib.ts_optim_create(self.ctx.h, n, offs, rows, cols, lds, self.n, C.byref(o)))
+            self._optim = o
+        return self._optim
+
+    def ensure_workspace(self, *key):
+        if self.ws_key == key:
+            return
+        need = int(self._f("workspace_bytes")(self.h, *key))
+        if need < 0:
+            raise _lib.TethysError(-2, f"unsupported shape {key}: {self.lib.ts_last_error(self.ctx.h).decode()}")
+        if self.workspace is None or self.workspace.numel() < need:
+            self.workspace = None
+            self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        self.ctx.check(self._f("bind")(self.h, ptr(self.params), ptr(self.grads), ptr(self.params_lp), ptr(self.workspace),
+                                      self.workspace.numel()))
+        self.ws_key = key
+
+    def sync_weights(self):
+        if not self.weights_synced and self.workspace is not None:
+            self.ctx.check(self._f("sync_compute_weights")(self.h, stream_ptr()))
+            self.weights_synced = True
+
+    def buffer(self, name):
+        p, dt, nd = C.c_void_p(), C.c_int32(), C.c_int32()
+        shape = (C.c_int64 * 4)()
+        self.ctx.check(self._f("get_buffer")(self.h, name.encode(), C.byref(p), C.byref(dt), C.byref(nd), shape))
+        return view_from_ptr(p.value, [shape[i] for i in range(nd.value)], dt.value, self.device)
+
+    def backward(self, stage_from=0, stage_to=10 ** 6):
+        self.ctx.check(self._f("backward")(self.h, int(stage_from), int(stage_to), stream_ptr()))
+
+
 class Strategy:
     """Stand-in for tf.distribute.MultiWorkerMirroredStrategy (W:1047, V:1473): one process per GPU, NCCL over
     NVLink/NVSwitch through torch.distributed. With a single process it degenerates to one replica."""

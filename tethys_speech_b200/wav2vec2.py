@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .runtime import (Adam, GradientList, ReduceOp, Strategy, clip_by_global_norm, get_strategy, ptr, stream_ptr,
+from .runtime import (Adam, GradientList, ProgramBase, ReduceOp, Strategy, clip_by_global_norm, get_strategy, ptr, stream_ptr,
                       to_device, view_from_ptr)
 
 
@@ -94,14 +94,10 @@ def _keras_order(cfg):
     return names
 
 
-class _Program:
-    """Owns the arenas (torch memory) and the ts_w2v handle."""
+class _Program(ProgramBase):
+    """Arenas + the ts_w2v handle."""
 
     def __init__(self, cfg, precision, device):
-        self.ctx = _lib.context(device)
-        self.lib = self.ctx.lib
-        self.device = torch.device("cuda", device)
-        self.precision = {"fp32": _lib.TS_F32, "float32": _lib.TS_F32, "bf16": _lib.TS_BF16, "bfloat16": _lib.TS_BF16}[precision]
         c = _lib.W2VConfig()
         c.hidden, c.layers, c.heads, c.ffn = cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads, cfg.intermediate_size
         c.n_conv = len(cfg.conv_dim)
@@ -114,74 +110,8 @@ class _Program:
         c.ln_eps, c.temperature, c.diversity_weight = cfg.layer_norm_eps, cfg.contrastive_logits_temperature, cfg.diversity_loss_weight
         c.hidden_dropout, c.activation_dropout, c.attention_dropout = cfg.hidden_dropout, cfg.activation_dropout, cfg.attention_dropout
         self.ccfg = c
-        h = C.c_void_p()
-        self.ctx.check(self.lib.ts_w2v_create(self.ctx.h, C.byref(c), self.precision, C.byref(h)))
-        self.h = h
-        self.n = int(self.lib.ts_w2v_arena_elems(h))
-        self.params = torch.zeros(self.n, dtype=torch.float32, device=self.device)
-        self.grads = torch.zeros(self.n, dtype=torch.float32, device=self.device)
-        self.params_lp = torch.zeros(self.n, dtype=torch.bfloat16, device=self.device) if self.precision == _lib.TS_BF16 else None
-        self.workspace = None
-        self.ws_shape = None
-        self.weights_synced = False
-        self.info = {}
-        name = C.create_string_buffer(256)
-        off, nd, ld = C.c_int64(), C.c_int32(), C.c_int64()
-        shape = (C.c_int64 * 4)()
-        for i in range(self.lib.ts_w2v_num_params(h)):
-            self.ctx.check(self.lib.ts_w2v_param_info(h, i, name, 256, C.byref(off), C.byref(nd), shape, C.byref(ld)))
-            shp = tuple(int(shape[j]) for j in range(nd.value))
-            self.info[name.value.decode()] = (int(off.value), shp, int(ld.value))
-        self.stage_ends = [int(self.lib.ts_w2v_stage_end(h, s)) for s in range(self.lib.ts_w2v_num_stages(h))]
-        self._optim = None
-
-    def view(self, arena, name):
-        off, shp, ld = self.info[name]
-        rows = shp[0] if len(shp) == 2 else 1
-        cols = int(np.prod(shp)) // rows
-        if len(shp) == 2 and ld != cols:      # column slice of a fused block (q/k/v)
-            return arena.as_strided((rows, cols), (ld, 1), off)
-        return arena[off:off + int(np.prod(shp))].view(*shp)
-
-    def make_optim(self):
-        if self._optim is None:
-            names = list(self.info)
-            n = len(names)
-            offs = (C.c_int64 * n)(); rows = (C.c_int32 * n)(); cols = (C.c_int32 * n)(); lds = (C.c_int64 * n)()
-            for i, k in enumerate(names):
-                off, shp, ld = self.info[k]
-                r = shp[0] if (len(shp) == 2 and ld != int(np.prod(shp)) // shp[0]) else 1
-                offs[i], rows[i], cols[i], lds[i] = off, r, int(np.prod(shp)) // r, ld if r > 1 else int(np.prod(shp))
-            o = C.c_void_p()
-            self.ctx.check(self.lib.ts_optim_create(self.ctx.h, n, offs, rows, cols, lds, self.n, C.byref(o)))
-            self._optim = o
-        return self._optim
-
-    def ensure_workspace(self, B, N):
-        if self.ws_shape == (B, N):
-            return
-        need = int(self.lib.ts_w2v_workspace_bytes(self.h, B, N))
-        if need < 0:
-            self.ctx.check(-2)
-        if self.workspace is None or self.workspace.numel() < need:
-            self.workspace = None
-            self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
-        self.ctx.check(self.lib.ts_w2v_bind(self.h, ptr(self.params), ptr(self.grads), ptr(self.params_lp), ptr(self.workspace),
-                                            self.workspace.numel()))
-        self.ws_shape = (B, N)
-
-    def sync_weights(self):
-        if not self.weights_synced:
-            if self.workspace is None:
-                return
-            self.ctx.check(self.lib.ts_w2v_sync_compute_weights(self.h, stream_ptr()))
-            self.weights_synced = True
-
-    def buffer(self, name):
-        p, dt, nd = C.c_void_p(), C.c_int32(), C.c_int32()
-        shape = (C.c_int64 * 4)()
-        self.ctx.check(self.lib.ts_w2v_get_buffer(self.h, name.encode(), C.byref(p), C.byref(dt), C.byref(nd), shape))
-        return view_from_ptr(p.value, [shape[i] for i in range(nd.value)], dt.value, self.device)
+        lib = _lib.load()
+        super().__init__("ts_w2v", precision, device, lambda ctx_h, prec, out: lib.ts_w2v_create(ctx_h, C.byref(c), prec, out))
 
 
 def _glorot_uniform(gen, shape, fan_in, fan_out, device):
@@ -345,7 +275,7 @@ class Wav2Vec2ForPreTraining:
         """tape.gradient(loss, model.trainable_variables) (V:1234) with None→zeros (V:1237-1240): fills the
         gradient arena and returns views in `trainable_variables` order."""
         p = self._prog
-        p.ctx.check(p.lib.ts_w2v_backward(p.h, int(stage_from), int(stage_to), stream_ptr()))
+        p.backward(stage_from, stage_to)
         gl = GradientList(p.view(p.grads, n) for n in self.variable_names)
         gl.owner = self
         for g in gl:

@@ -1,0 +1,255 @@
+"""Host-side mirror of the reference's Whisper surface (speech_jobs/whisper_dist.py = W): WhisperConfig,
+WhisperForConditionalGeneration, create_whisper_model, create_dummy_dataset, distributed_train_step — driving the native
+program in libtethys.so (csrc/whisper_program.cu) through ctypes. No TensorFlow, no CPU fallback.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .runtime import Adam, GradientList, ProgramBase, ReduceOp, Strategy, get_strategy, ptr, stream_ptr, to_device  # noqa: F401
+
+
+class WhisperConfig:
+    """Same attributes as WhisperConfig — W:10-45 (defaults = the CLI's 'small' preset: d768, 12 heads, 4+4 layers)."""
+
+    def __init__(self):
+        self.d_model = 768
+        self.encoder_layers = 4
+        self.encoder_attention_heads = 12
+        self.decoder_layers = 4
+        self.decoder_attention_heads = 12
+        self.d_ff = 3072
+        self.n_mels = 80
+        self.n_ctx = 1500
+        self.vocab_size = 51865
+        self.max_target_positions = 448
+        self.dropout = 0.1
+        self.attention_dropout = 0.1
+        self.activation_dropout = 0.0
+        self.activation_function = "gelu"
+        self.layer_norm_eps = 1e-5
+        self.init_std = 0.02
+        self.pad_token_id = 0
+        self.bos_token_id = 1
+        self.eos_token_id = 2
+        self.use_cache = True
+        self.decoder_start_token_id = 50257
+
+
+def _keras_order(cfg):
+    """trainable_variables order of WhisperForConditionalGeneration (attribute-tracking order, W:73-94, W:210-216,
+    W:240-253, W:305-322, W:376-392, W:536-545)."""
+    names = ["encoder.conv1.kernel", "encoder.conv1.bias", "encoder.conv2.kernel", "encoder.conv2.bias"]
+
+    def attn(p):
+        out = []
+        for n in ("k_proj", "v_proj", "q_proj", "out_proj"):
+            out += [p + n + ".kernel", p + n + ".bias"]
+        return out
+
+    def ln(p):
+        return [p + ".gamma", p + ".beta"]
+
+    def ffn(p):
+        return [p + "fc1.kernel", p + "fc1.bias", p + "fc2.kernel", p + "fc2.bias"]
+
+    for l in range(cfg.encoder_layers):
+        p = f"encoder.layers.{l}."
+        names += attn(p + "self_attn.") + ln(p + "self_attn_layer_norm") + ffn(p + "feed_forward.") + ln(p + "final_layer_norm")
+    names += ln("encoder.layer_norm")
+    names += ["decoder.embed_tokens.embeddings"]
+    for l in range(cfg.decoder_layers):
+        p = f"decoder.layers.{l}."
+        names += (attn(p + "self_attn.") + ln(p + "self_attn_layer_norm") + attn(p + "encoder_attn.") + ln(p + "encoder_attn_layer_norm")
+                  + ffn(p + "feed_forward.") + ln(p + "final_layer_norm"))
+    names += ln("decoder.layer_norm")
+    names += ["lm_head.kernel"]
+    return names
+
+
+class _Program(ProgramBase):
+    def __init__(self, cfg, precision, device):
+        c = _lib.WhisperCfg()
+        c.d_model, c.enc_layers, c.dec_layers, c.heads, c.d_ff = cfg.d_model, cfg.encoder_layers, cfg.decoder_layers, cfg.encoder_attention_heads, cfg.d_ff
+        if cfg.decoder_attention_heads != cfg.encoder_attention_heads:
+            raise ValueError("encoder and decoder head counts must match (they do in every reference preset)")
+        c.n_mels, c.n_ctx, c.vocab, c.max_target = cfg.n_mels, cfg.n_ctx, cfg.vocab_size, cfg.max_target_positions
+        c.start_token = cfg.decoder_start_token_id
+        c.ln_eps, c.dropout, c.attention_dropout, c.activation_dropout = cfg.layer_norm_eps, cfg.dropout, cfg.attention_dropout, cfg.activation_dropout
+        self.ccfg = c
+        lib = _lib.load()
+        super().__init__("ts_whisper", precision, device, lambda ctx_h, prec, out: lib.ts_whisper_create(ctx_h, C.byref(c), prec, out))
+
+
+def _glorot_uniform(gen, shape, fan_in, fan_out, device):
+    limit = math.sqrt(6.0 / (fan_in + fan_out))
+    return (torch.rand(shape, generator=gen, dtype=torch.float32, device=device) * 2 - 1) * limit
+
+
+class WhisperForConditionalGeneration:
+    """Mirror of `WhisperForConditionalGeneration` — W:536-616. `model(features, labels=labels, training=True)` returns a
+    dict with "loss", "logits", "encoder_last_hidden_state", "last_hidden_state" (the remaining reference keys —
+    attentions, hidden state tuples, past_key_values — are inference/debug outputs off the train path and are None)."""
+
+    def __init__(self, config, precision="bf16", device=None, seed=0):
+        self.config = config
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        self._prog = _Program(config, precision, device)
+        self._step_seed = seed * 1000003
+        self._last = {}
+        self._init_weights(seed)
+        names = _keras_order(config)
+        assert set(names) == set(self._prog.info), "parameter table mismatch"
+        self.variable_names = names
+        self.trainable_variables = [self._prog.view(self._prog.params, n) for n in names]
+
+    def _init_weights(self, seed):
+        """Keras defaults: Dense/Conv1D glorot_uniform + zeros, LayerNorm ones/zeros, Embedding uniform(-0.05, 0.05)."""
+        p = self._prog
+        gen = torch.Generator(device=p.device)
+        gen.manual_seed(seed)
+        for name, (off, shp, ld) in p.info.items():
+            v = p.view(p.params, name)
+            if name.endswith(".kernel"):
+                if len(shp) == 3:
+                    k, cin, cout = shp
+                    v.copy_(_glorot_uniform(gen, shp, k * cin, k * cout, p.device))
+                else:
+                    v.copy_(_glorot_uniform(gen, shp, shp[0], shp[1], p.device))
+            elif name.endswith(".embeddings"):
+                v.copy_((torch.rand(shp, generator=gen, dtype=torch.float32, device=p.device) * 2 - 1) * 0.05)
+            elif name.endswith(".gamma"):
+                v.fill_(1.0)
+            else:
+                v.zero_()
+        p.weights_synced = False
+
+    def set_weights(self, weights):
+        p = self._prog
+        for k, w in weights.items():
+            p.view(p.params, k).copy_(to_device(w, torch.float32, p.device).view(p.info[k][1]))
+        p.weights_synced = False
+
+    def get_weights(self):
+        p = self._prog
+        return {k: p.view(p.params, k).detach().clone() for k in self.variable_names}
+
+    def broadcast_weights(self, strategy):
+        strategy.broadcast_(self._prog.params)
+        self._prog.weights_synced = False
+
+    def __call__(self, input_features, decoder_input_ids=None, attention_mask=None, decoder_attention_mask=None,
+                 encoder_outputs=None, past_key_values=None, labels=None, use_cache=None, return_dict=True, training=False,
+                 dropout=True):
+        """input_features [B, n_mels, T_mel]; labels [B, S] int. Only the train-path arguments are supported:
+        decoder_input_ids are derived from the labels (W:557-563); masks / caches must be None."""
+        if any(a is not None for a in (decoder_input_ids, attention_mask, decoder_attention_mask, encoder_outputs, past_key_values)):
+            raise NotImplementedError("only the training call (features, labels=…, training=True) is on the hot path")
+        if labels is None:
+            raise NotImplementedError("labels are required (generation / encoder-only calls are not on the hot path)")
+        p = self._prog
+        x = to_device(input_features, torch.float32, p.device)
+        lab = to_device(labels, torch.int32, p.device)
+        B, nm, Tm = x.shape
+        S = lab.shape[1]
+        p.ensure_workspace(B, Tm, S)
+        p.sync_weights()
+        self._step_seed += 1
+        p.ctx.check(p.lib.ts_whisper_forward(p.h, ptr(x), B, Tm, ptr(lab), S, self._step_seed, 1 if (training and dropout) else 0,
+                                             1 if training else 0, stream_ptr()))
+        self._last = {"x": x, "labels": lab}
+        scal = p.buffer("scalars")
+        out = {"loss": scal[0] if training else None,
+               "logits": p.buffer("logits")[:, :, :self.config.vocab_size],
+               "past_key_values": None,
+               "encoder_last_hidden_state": p.buffer("encoder_last_hidden_state"),
+               "last_hidden_state": p.buffer("last_hidden_state"),
+               "encoder_hidden_states": None, "encoder_attentions": None, "decoder_hidden_states": None,
+               "decoder_attentions": None, "cross_attentions": None}
+        return out
+
+    call = __call__
+
+    def gradient(self, stage_from=0, stage_to=10 ** 6):
+        """tape.gradient(loss, model.trainable_variables) — W:833."""
+        p = self._prog
+        p.backward(stage_from, stage_to)
+        gl = GradientList(p.view(p.grads, n) for n in self.variable_names)
+        gl.owner = self
+        for g in gl:
+            g._ts_owner = self
+        return gl
+
+    def save_weights(self, path):
+        torch.save({k: v.cpu() for k, v in self.get_weights().items()}, path)
+
+
+def create_whisper_model(model_type="small", precision="bf16", device=None, seed=0):
+    """W:852-890."""
+    config = WhisperConfig()
+    if model_type == "tiny":
+        config.d_model, config.encoder_layers, config.decoder_layers, config.d_ff = 384, 4, 4, 1536
+        config.encoder_attention_heads = config.decoder_attention_heads = 6
+    elif model_type == "base":
+        config.d_model, config.encoder_layers, config.decoder_layers, config.d_ff = 512, 6, 6, 2048
+        config.encoder_attention_heads = config.decoder_attention_heads = 8
+    elif model_type == "medium":
+        config.d_model, config.encoder_layers, config.decoder_layers, config.d_ff = 1024, 24, 24, 4096
+        config.encoder_attention_heads = config.decoder_attention_heads = 16
+    elif model_type == "large":
+        config.d_model, config.encoder_layers, config.decoder_layers, config.d_ff = 1280, 32, 32, 5120
+        config.encoder_attention_heads = config.decoder_attention_heads = 20
+    return WhisperForConditionalGeneration(config, precision=precision, device=device, seed=seed)
+
+
+def create_dummy_dataset(batch_size, n_mels=80, seq_len=3000, max_target_length=100, num_samples=50, seed=1234):
+    """W:784-815: 50 samples of N(0,1) mel [n_mels, seq_len] + labels (zeros; len ~ U{50..89}; [0]=1; [1:len-1] ~ U{3..99};
+    [len-1]=2), batched and repeated. Seeded (the reference is not). Yields (features pinned fp32, labels int32)."""
+    rng = np.random.default_rng(seed)
+    feats = torch.from_numpy(rng.standard_normal((num_samples, n_mels, seq_len), dtype=np.float32))
+    labels = np.zeros((num_samples, max_target_length), dtype=np.int32)
+    lens = rng.integers(50, 90, size=num_samples)
+    for i in range(num_samples):
+        n = int(lens[i])
+        labels[i, 0] = 1
+        labels[i, 1:n - 1] = rng.integers(3, 100, size=n - 2)
+        labels[i, n - 1] = 2
+    labels = torch.from_numpy(labels)
+    if torch.cuda.is_available():
+        feats, labels = feats.pin_memory(), labels.pin_memory()
+
+    def gen():
+        while True:
+            for i in range(0, num_samples, batch_size):   # dataset.batch() keeps the ragged last batch (W:815)
+                yield feats[i:i + batch_size], labels[i:i + batch_size]
+
+    return gen()
+
+
+def distributed_train_step(strategy, model, dist_inputs, optimizer, dropout=True):
+    """W:819-848: per replica forward + mean CE loss, gradients, optimizer.apply_gradients (all-reduce SUM across replicas
+    WITHOUT dividing — App. C-3 — then Adam), and strategy.reduce(SUM) of the per-replica losses."""
+
+    def train_step(inputs):
+        features, labels = inputs
+        outputs = model(features, labels=labels, training=True, dropout=dropout)
+        loss = outputs["loss"]
+        gradients = model.gradient()
+        optimizer.apply_gradients(gradients, strategy=strategy)
+        return loss
+
+    per_replica_losses = strategy.run(train_step, args=(dist_inputs,))
+    return strategy.reduce(ReduceOp.SUM, per_replica_losses, axis=None)
+
+
+def train_step(model, inputs, optimizer, dropout=True):
+    """Single-device form of W:823-836 (the reference has no single-GPU Whisper script — SURVEY D1)."""
+    features, labels = inputs
+    outputs = model(features, labels=labels, training=True, dropout=dropout)
+    gradients = model.gradient()
+    optimizer.apply_gradients(gradients)
+    return outputs["loss"]
