@@ -13,6 +13,13 @@ import torch
 from . import tf_ops as T
 
 
+# In fp64 evaluation the masked scores are given the value TF's float32 `scores + (-1e9)` would hold (absorption, App. C-1)
+# while the gradient stays the identity TF's autodiff of the add uses. Tests that compare against finite differences switch
+# this off: with absorption the fully-masked last decoder row is piecewise constant, so FD (= 0 there) and TF's autodiff
+# (= the softmax gradient) legitimately differ.
+EMULATE_FP32_ABSORPTION = True
+
+
 class WhisperConfig:
     """WhisperConfig — W:10-45 with the size presets of create_whisper_model — W:852-890 ('small' = CLI default:
     d768 / 12 heads / d_ff 3072 / 4+4 layers)."""
@@ -117,8 +124,8 @@ def mha(cfg, w, p, x, kv=None, mask=None):
     if mask is not None:
         add = ((1.0 - mask) * -1e9).to(torch.float32)              # [1,L,Lk]
         # TF computes scores + mask in float32: emulate the absorption exactly, keep autograd through s
-        if s.dtype == torch.float32:
-            s = s + add
+        if s.dtype == torch.float32 or not EMULATE_FP32_ABSORPTION:
+            s = s + add.to(s.dtype)
         else:
             s_abs = (s.to(torch.float32) + add).to(s.dtype)        # value TF would hold at the masked entries
             s = torch.where(add != 0, s + (s_abs - s).detach(), s)
