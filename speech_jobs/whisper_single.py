@@ -1,0 +1,27 @@
+#!/usr/bin/env python
+"""Single-GPU Whisper train script: --batch_size 4 --num_batches 40 defaults (WS:1303-1306).
+NOTE: the reference file of this name actually contains Wav2Vec2-base pre-training on 5 s audio with the
+legacy sampler/step. BASELINE config #1 describes Whisper, so the default here is whisper_dist.py's model and step without
+a strategy; `--legacy_wav2vec2` runs what the reference file literally does (Wav2Vec2-base, 80 000 samples, legacy step)."""
+import argparse
+import time
+
+import _path  # noqa: F401
+from tethys_speech_b200 import train
+
+if __name__ == "__main__":
+    parser = argparse.ArgumentParser(description="Whisper single-GPU training")
+    parser.add_argument("--num_batches", type=int, default=40)
+    parser.add_argument("--batch_size", type=int, default=4)
+    parser.add_argument("--legacy_wav2vec2", action="store_true", help="literal behaviour of the reference file (WS:1183-1258)")
+    parser.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
+    args = parser.parse_args()
+    strategy = train.make_strategy()
+    start = time.time()
+    if args.legacy_wav2vec2:
+        train.train_wav2vec2(strategy, "pretraining", "base", batch_size=args.batch_size, num_batches=args.num_batches,
+                             precision=args.precision, audio_length=80000, legacy=True)
+    else:
+        train.train_whisper(strategy, "small", batch_size=args.batch_size, num_batches=args.num_batches, precision=args.precision)
+    print("Training completed.")
+    print("jct:", time.time() - start)

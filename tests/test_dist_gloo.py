@@ -1,0 +1,90 @@
+"""World-size-2 CPU (gloo) tests of the multi-replica host logic: the Strategy shim that stands in for
+MultiWorkerMirroredStrategy (bucketed SUM all-reduce of the flat gradient arena = K21, weight broadcast = K23, scalar loss
+reduce = K22) and the two reduce conventions of the reference: Whisper sums un-normalised gradients
+(W:829-836), Wav2Vec2 divides the loss by N, clips locally BEFORE the reduce and per-variable AFTER it (V:1231-1246).
+The GPU kernels cannot run here; gradients come from the CPU oracle and travel through the same Strategy code."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from oracle import tf_ops as T
+    from oracle import wav2vec2_oracle as O
+    from tethys_speech_b200.runtime import ReduceOp, Strategy
+
+    torch.set_num_threads(1)
+    st = Strategy(backend="gloo")
+    assert st.num_replicas_in_sync == world
+    res = {}
+    # K23 broadcast: replicas start from different "initial" arenas, the chief's wins
+    arena = torch.full((1000,), float(rank + 1))
+    st.broadcast_(arena)
+    res["bcast"] = float(arena.sum())
+    # K21 bucketed all-reduce over a flat arena with a ragged last bucket
+    g = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    st.all_reduce_sum_(g, bucket_elems=300)
+    res["allreduce_ok"] = bool(torch.equal(g, torch.arange(1000, dtype=torch.float32) * 3))
+    # K22 loss reduce
+    res["loss_sum"] = float(st.reduce(ReduceOp.SUM, torch.tensor(0.5 + rank)))
+    # Wav2Vec2 convention end to end on the oracle's gradients
+    cfg = O.Wav2Vec2Config("tiny")
+    w = O.randomize_weights(O.init_weights(cfg, seed=0, dtype=torch.float64), seed=1)
+    gen = torch.Generator().manual_seed(100 + rank)
+    wave = torch.randn(1, 1600, generator=gen, dtype=torch.float64)
+    Tn = O.num_frames(cfg, 1600)
+    neg = O.negative_indices_from_random(torch.randint(0, Tn, (1, Tn), generator=gen), cfg.num_negatives)
+    out, grads = O.loss_and_grads(cfg, w, wave, neg, loss_div=float(world))
+    names = list(w)
+    clipped, _ = T.clip_by_global_norm([grads[k] for k in names], 1.0)                 # local, pre-reduce (V:1243)
+    flat = torch.cat([c.reshape(-1) for c in clipped])
+    st.all_reduce_sum_(flat, bucket_elems=1 << 20)                                       # SUM, not mean (A-13)
+    res["flat"] = flat.numpy().copy()                                                    # by value: the worker exits before the parent reads
+    res["local"] = torch.cat([c.reshape(-1) for c in clipped]).numpy().copy()
+    res["scaled_loss"] = float(st.reduce(ReduceOp.SUM, (out["loss"] / world).detach()))
+    res["loss"] = float(out["loss"])
+    q.put((rank, res))
+    st.barrier()
+
+
+@pytest.mark.timeout(300)
+def test_strategy_shim_world2_gloo():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(world):
+        assert got[r]["bcast"] == 1000.0            # everyone holds the chief's (rank 0) values
+        assert got[r]["allreduce_ok"]
+        assert got[r]["loss_sum"] == 0.5 + 1.5
+    # the reduced gradient is the SUM of the two locally clipped gradients, identical on both ranks
+    import numpy as np
+
+    assert np.array_equal(got[0]["flat"], got[1]["flat"])
+    assert np.allclose(got[0]["flat"], got[0]["local"] + got[1]["local"], rtol=0, atol=1e-15)
+    # each local part has global norm <= 1 (clip before reduce), the sum may exceed it (hence the post-reduce clipnorm)
+    assert np.linalg.norm(got[0]["local"]) <= 1.0 + 1e-12 and np.linalg.norm(got[1]["local"]) <= 1.0 + 1e-12
+    # the reported loss is the SUM over replicas of loss/N = the mean of the per-replica losses (V:1231, V:1260)
+    assert abs(got[0]["scaled_loss"] - 0.5 * (got[0]["loss"] + got[1]["loss"])) < 1e-12

@@ -1,0 +1,137 @@
+"""Train loops and CLI plumbing shared by the drop-in scripts under speech_jobs/ — the thin L3/L4 layers of the
+reference (W:894-958, W:990-1058; V:1263-1376, V:1380-1487; VS:1180-1292; WS:1183-1306) around the native step.
+Same flags, same `Step N, Loss: x.xxxx, Time: …` log line, same jct file; hard-coded /workspace and /result paths are
+overridable (TETHYS_WORKSPACE / TETHYS_RESULT) and failures to write them are non-fatal, as SURVEY §5.6 asks."""
+import json
+import os
+import time
+
+import torch
+
+from . import wav2vec2 as W2V
+from . import whisper as WH
+from .runtime import Adam, Strategy
+
+WORKSPACE = os.environ.get("TETHYS_WORKSPACE", "/workspace")
+RESULT = os.environ.get("TETHYS_RESULT", "/result")
+
+
+def task_from_tf_config():
+    """W:1037-1040 / job_name.py:3-13: task type and index from TF_CONFIG (None when unset)."""
+    tf_config = json.loads(os.environ.get("TF_CONFIG") or "{}")
+    task = tf_config.get("task", {})
+    return task.get("type"), task.get("index")
+
+
+def _log_step(step, loss_value, start_time, step_duration):
+    elapsed = time.time() - start_time
+    print(f"Step {step}, Loss: {loss_value:.4f}, Time: {time.strftime('%H:%M:%S')} (경과: {elapsed:.2f}초, 스텝 시간: {step_duration:.2f}초)", flush=True)
+
+
+def _save_checkpoint(model, name):
+    try:
+        d = os.path.join(WORKSPACE, "checkpoints")
+        os.makedirs(d, exist_ok=True)
+        model.save_weights(os.path.join(d, name + ".pt"))
+    except Exception as e:  # the reference's checkpoint dir is container-specific
+        print(f"checkpoint not written: {e}")
+
+
+def write_jct(jct, task_type, task_index):
+    """W:1013-1021: /result/<model.txt>/<task>_<idx>_jct.txt with '%.2f'."""
+    print("jct:", jct)
+    try:
+        with open(os.path.join(WORKSPACE, "model.txt")) as f:
+            save_dir_name = f.read().strip()
+        path = os.path.join(RESULT, save_dir_name, f"{task_type}_{task_index}_jct.txt")
+        with open(path, "w") as f:
+            f.write("%.2f" % float(jct))
+    except Exception as e:
+        print(f"JCT file not written: {e}")
+
+
+def train_whisper(strategy, model_type="small", num_epochs=1, learning_rate=1e-4, batch_size=1, num_batches=40,
+                  precision="bf16", seq_len=3000):
+    """W:894-958."""
+    with strategy.scope():
+        model = WH.create_whisper_model(model_type=model_type, precision=precision, device=strategy.local_rank)
+        model.broadcast_weights(strategy)
+        optimizer = Adam(learning_rate=learning_rate)
+    global_batch = batch_size * strategy.num_replicas_in_sync
+    dataset = WH.create_dummy_dataset(global_batch, seq_len=seq_len)
+    step = 0
+    start_time = time.time()
+    for epoch in range(num_epochs):
+        print(f"Epoch {epoch + 1}/{num_epochs}")
+        for _ in range(num_batches):
+            feats, labels = next(dataset)
+            lo = strategy.rank * batch_size                      # rank r takes samples [r*B, (r+1)*B) of the global batch
+            feats, labels = feats[lo:lo + batch_size], labels[lo:lo + batch_size]
+            if feats.shape[0] == 0:
+                continue
+            step_start = time.time()
+            loss = WH.distributed_train_step(strategy, model, (feats, labels), optimizer)
+            loss_value = float(loss)                              # device sync (the reference's loss.numpy(), W:951)
+            _log_step(step, loss_value, start_time, time.time() - step_start)
+            step += 1
+        if strategy.rank == 0:
+            _save_checkpoint(model, f"whisper_{model_type}_epoch_{epoch + 1}")
+    return model
+
+
+def train_wav2vec2(strategy, model_type="pretraining", model_size="small", num_epochs=1, learning_rate=3e-5, batch_size=1,
+                   num_batches=5, precision="bf16", audio_length=32000, legacy=False):
+    """V:1263-1376 (legacy=True: the whisper_single.py / stable_jobs variant — WS:1183-1258: 5 s audio, unscaled loss,
+    no clipping, Adam eps 1e-7, seed-42 shuffle sampler)."""
+    with strategy.scope():
+        model = W2V.create_full_model(model_type=model_type, model_size=model_size, precision=precision, device=strategy.local_rank)
+        model.broadcast_weights(strategy)
+        optimizer = Adam(learning_rate=learning_rate, epsilon=1e-7) if legacy else Adam(learning_rate=learning_rate, epsilon=1e-8, clipnorm=1.0)
+    global_batch = batch_size * strategy.num_replicas_in_sync
+    dataset = W2V.create_dummy_dataset(global_batch, audio_length=audio_length)
+    neg_legacy = None
+    if legacy:
+        T = model.num_frames(audio_length)
+        perm = torch.randperm(T, generator=torch.Generator().manual_seed(42))        # tf.random.shuffle(range(T), seed=42) stand-in
+        t = torch.arange(T).unsqueeze(1)
+        k = torch.arange(model.num_negatives).unsqueeze(0)
+        neg_legacy = perm[(k - (t + 1)) % T].to(torch.int32).unsqueeze(0).expand(batch_size, -1, -1).contiguous()   # WS:799-839
+    step = 0
+    start_time = time.time()
+    for epoch in range(num_epochs):
+        print(f"Epoch {epoch + 1}/{num_epochs}")
+        for _ in range(num_batches):
+            try:
+                feats, labels = next(dataset)
+                lo = strategy.rank * batch_size
+                feats = feats[lo:lo + batch_size]
+                step_start = time.time()
+                if legacy:
+                    loss = W2V.legacy_train_step(model, (feats, None), optimizer, neg_indices=neg_legacy)
+                    loss = strategy.reduce("SUM", loss)
+                else:
+                    loss = W2V.distributed_train_step(strategy, model, (feats, None), optimizer)
+                try:
+                    loss_value = float(loss)
+                except Exception:
+                    loss_value = 0.0
+                _log_step(step, loss_value, start_time, time.time() - step_start)
+                step += 1
+                if step % 50 == 0 and strategy.rank == 0:
+                    _save_checkpoint(model, f"model_step_{step}")
+            except StopIteration:
+                break
+            except Exception as e:                               # V:1367-1371 swallows per-step errors
+                print(f"Error at step {step}: {e}")
+                raise
+        if strategy.rank == 0:
+            _save_checkpoint(model, f"model_epoch_{epoch + 1}")
+    return model
+
+
+def make_strategy():
+    """MultiWorkerMirroredStrategy() — W:1047 / V:1473: under torchrun one process per GPU; alone, one replica."""
+    s = Strategy()
+    if torch.cuda.is_available():
+        torch.cuda.set_device(s.local_rank)
+    return s
