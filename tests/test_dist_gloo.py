@@ -87,4 +87,5 @@ def test_strategy_shim_world2_gloo():
     # each local part has global norm <= 1 (clip before reduce), the sum may exceed it (hence the post-reduce clipnorm)
     assert np.linalg.norm(got[0]["local"]) <= 1.0 + 1e-12 and np.linalg.norm(got[1]["local"]) <= 1.0 + 1e-12
     # the reported loss is the SUM over replicas of loss/N = the mean of the per-replica losses (V:1231, V:1260)
-    assert abs(got[0]["scaled_loss"] - 0.5 * (got[0]["loss"] + got[1]["loss"])) < 1e-12
+    mean_loss = 0.5 * (got[0]["loss"] + got[1]["loss"])
+    assert abs(got[0]["scaled_loss"] - mean_loss) < 1e-6 * mean_loss       # the scalar travels as float32, like TF's loss
