@@ -112,18 +112,34 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 
 // ----------------------------------------------------------------------------------------------
 // Counter-based RNG for dropout (stateless; the backward pass regenerates the same mask).
-// keep(idx) is a pure function of (seed, idx): a 64->32 bit mix (splitmix64 finaliser).
+// keep(idx) is a pure function of (seed, idx). One 32-bit hash serves the element pair (idx & ~1): 16 random
+// bits per element, so the drop probability is round(rate * 65536) / 65536 (0.1 -> 0.100006). The hash is the
+// "lowbias32" integer finaliser with the two halves of the 64-bit seed injected before each multiply; it is
+// cheap enough (about 5 integer ops per element) to live in a GEMM epilogue.
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t mix_hash(uint64_t seed, uint64_t idx) {
-  uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (uint32_t)(z >> 32);
+__device__ __forceinline__ uint32_t dropout_word(uint64_t seed, uint64_t idx) {
+  uint32_t x = (uint32_t)(idx >> 1) ^ (uint32_t)seed;
+  const uint32_t k2 = (uint32_t)(seed >> 32) ^ ((uint32_t)(idx >> 33) * 0x85EBCA6Bu);
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x += k2;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
 }
-// returns the multiplier to apply: 0 (dropped) or 1/(1-rate) (kept). thr = rate * 2^32.
+// returns the multiplier to apply: 0 (dropped) or 1/(1-rate) (kept). thr = rate * 2^32 (only the top 16 bits count).
 __device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, uint32_t thr, float inv_keep) {
-  return (mix_hash(seed, idx) >= thr) ? inv_keep : 0.f;
+  const uint32_t w = dropout_word(seed, idx);
+  const uint32_t r = (idx & 1) ? (w >> 16) : (w & 0xffffu);
+  return (r >= (thr >> 16)) ? inv_keep : 0.f;
+}
+// the pair (idx, idx + 1) for EVEN idx from one hash
+__device__ __forceinline__ void dropout_scale2(uint64_t seed, uint64_t idx_even, uint32_t thr, float inv_keep, float& s0,
+                                               float& s1) {
+  const uint32_t w = dropout_word(seed, idx_even);
+  s0 = ((w & 0xffffu) >= (thr >> 16)) ? inv_keep : 0.f;
+  s1 = ((w >> 16) >= (thr >> 16)) ? inv_keep : 0.f;
 }
 
 }  // namespace ts

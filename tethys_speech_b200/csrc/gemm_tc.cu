@@ -1,9 +1,16 @@
-// K9 — tcgen05 GEMM engine (bf16 in, fp32 accumulate in TMEM, fused epilogue).
+// K9 — tcgen05 GEMM engine (bf16 in, fp32 accumulate in TMEM, fused epilogue), persistent and warp-specialised.
 //
-// One CTA computes one 128 x BN output tile:
-//   warp 0 : TMA producer   (cp.async.bulk.tensor 4D boxes -> 128B-swizzled smem ring, mbarrier tx)
-//   warp 1 : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, kind::f16)
-//   warps 2-5 : epilogue    (tcgen05.ld TMEM -> registers -> alpha/bias/GELU/residual -> global)
+// grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, then m, batch,
+// K-split) so that neighbouring CTAs share the same A rows in L2. Roles:
+//   warp 0    : TMA producer   (cp.async.bulk.tensor 4D boxes -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 1    : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, kind::f16)
+//   warps 2-5 : epilogue       (tcgen05.ld TMEM -> registers -> warp-private smem transpose -> coalesced global I/O)
+// The accumulator is double buffered in TMEM (2 x BN columns): the epilogue of tile i overlaps the main loop of tile
+// i+1 (tmem_full / tmem_empty mbarriers). All epilogue math (alpha, bias, pre-activation copy, exact GELU, dropout,
+// residual, accumulate) runs after the transpose, where a lane owns a fixed column pair and consecutive lanes touch
+// consecutive addresses, so every global load/store of the epilogue is coalesced.
+// Split-K (only for fp32 "C += A*B" outputs, i.e. weight gradients with a long reduce dim and few output tiles):
+// each K-slice is its own tile and adds its partial with red.global.add.f32.
 // Both operands may be K-major or MN-major (see include/tethys.h); MN-major operands are loaded as
 // 64-wide MN chunks so Dense kernels [in,out], activations for wgrad and V for P.V need no transposes.
 // Replaces cuBLAS/cuDNN calls behind W:89-92,141,147,167,174,194-205,311-312,545 and V:240-268,
@@ -26,107 +33,119 @@ struct EpiParams {
   int m, n, k, nb1;
   int a_m1, a_m2, b_m1, b_m2;  // 0 => that batch dim is broadcast for the operand (stride 0)
   uint32_t drop_thr; float inv_keep; unsigned long long seed;
+  int mt, nt, nb, splitk, kb_per_split, total_tiles;  // persistent tile schedule
+  int use_red;                                        // fp32 output: add with red.global (split-K partials)
+  int tma_epi;                                        // C (and c_pre) are TMA-storable: swizzled smem box + bulk tensor store
 };
 
 constexpr int BM = 128;
 constexpr int BK = 64;
+constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quarter, alternating column chunks
+constexpr int kThreads = 64 + kEpiWarps * 32;
+constexpr int kStageBytesPerWarp = 4096;     // one 32-row x 128-byte swizzled box per epilogue warp
 
 template <int BN> struct TcCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int kTmemCols = (BN < 32) ? 32 : BN;
+  static constexpr int kSmem = kStages * kStageBytes + kEpiWarps * kStageBytesPerWarp + 1024 /*align slack*/ + 128 /*barriers*/;
+  static constexpr int kTmemCols = 2 * BN;                     // two accumulator stages (power of two >= 32)
 };
 
-template <typename OutT> __device__ __forceinline__ void store_vec(OutT* dst, const float* v, int n, bool vec_ok);
-template <> __device__ __forceinline__ void store_vec<float>(float* dst, const float* v, int n, bool vec_ok) {
-  if (vec_ok && n == 32) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  } else {
-    for (int i = 0; i < n; ++i) dst[i] = v[i];
-  }
+struct TileCoord { int m0, n0, b1, b2, kb0, kb1; };
+__device__ __forceinline__ TileCoord decode_tile(const EpiParams& p, int t, int BN_) {
+  TileCoord tc;
+  const int n = t % p.nt; t /= p.nt;
+  const int m = t % p.mt; t /= p.mt;
+  const int b = t % p.nb; t /= p.nb;
+  tc.m0 = m * BM; tc.n0 = n * BN_;
+  tc.b1 = b % p.nb1; tc.b2 = b / p.nb1;
+  const int nkb = (p.k + BK - 1) / BK;
+  tc.kb0 = t * p.kb_per_split;
+  tc.kb1 = min(nkb, tc.kb0 + p.kb_per_split);
+  return tc;
 }
-template <> __device__ __forceinline__ void store_vec<bf16>(bf16* dst, const float* v, int n, bool vec_ok) {
-  if (vec_ok && n == 32) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 u;
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * i + 0], v[8 * i + 1]);
-      __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-      __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
-      __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-      u.x = *reinterpret_cast<uint32_t*>(&p0);
-      u.y = *reinterpret_cast<uint32_t*>(&p1);
-      u.z = *reinterpret_cast<uint32_t*>(&p2);
-      u.w = *reinterpret_cast<uint32_t*>(&p3);
-      reinterpret_cast<uint4*>(dst)[i] = u;
-    }
-  } else {
-    for (int i = 0; i < n; ++i) dst[i] = __float2bfloat16_rn(v[i]);
-  }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
 }
-template <typename OutT> __device__ __forceinline__ void load_vec(const OutT* src, float* v, int n, bool vec_ok);
-template <> __device__ __forceinline__ void load_vec<float>(const float* src, float* v, int n, bool vec_ok) {
-  if (vec_ok && n == 32) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 f = reinterpret_cast<const float4*>(src)[i];
-      v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
-    }
-  } else {
-    for (int i = 0; i < n; ++i) v[i] = src[i];
-  }
+// 16-byte chunk j (0..7) of row r inside a 32-row x 128-byte SWIZZLE_128B box
+__device__ __forceinline__ uint32_t swz128(uint32_t box, int r, int j) { return box + r * 128 + ((j ^ (r & 7)) << 4); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-template <> __device__ __forceinline__ void load_vec<bf16>(const bf16* src, float* v, int n, bool vec_ok) {
-  if (vec_ok && n == 32) {
+
+// Per-element epilogue math on a thread's NV consecutive columns of one output row.
+template <int NV>
+__device__ __forceinline__ void epi_bias(float (&v)[NV], const EpiParams& p, const float* bias, int col, bool full) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 u = reinterpret_cast<const uint4*>(src)[i];
-      const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+  for (int i = 0; i < NV; ++i) v[i] *= p.alpha;
+  if (bias) {
+    if (full && (reinterpret_cast<uintptr_t>(bias + col) & 15) == 0) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float2 f = __bfloat1622float2(p[j]);
-        v[8 * i + 2 * j] = f.x;
-        v[8 * i + 2 * j + 1] = f.y;
+      for (int i = 0; i < NV; i += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col + i));  // warp-uniform address: one broadcast
+        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
       }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (col + i < p.n) v[i] += __ldg(bias + col + i);
     }
-  } else {
-    for (int i = 0; i < n; ++i) v[i] = __bfloat162float(src[i]);
+  }
+}
+template <int NV>
+__device__ __forceinline__ void epi_act_drop(float (&v)[NV], const EpiParams& p, unsigned long long e0) {
+  if (p.act == 1) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = gelu_f(v[i]);
+  }
+  if (p.drop_thr) {
+    if ((e0 & 1) == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; i += 2) {
+        float s0, s1;
+        dropout_scale2(p.seed, e0 + i, p.drop_thr, p.inv_keep, s0, s1);
+        v[i] *= s0; v[i + 1] *= s1;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] *= dropout_scale(p.seed, e0 + i, p.drop_thr, p.inv_keep);
+    }
   }
 }
 
 template <int BN, int AMAJ, int BMAJ, typename OutT>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_p,
                const EpiParams p, int* watchdog) {
   using Cfg = TcCfg<BN>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms need 1024 B alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint8_t* stage_buf = smem + S * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_buf + kEpiWarps * kStageBytesPerWarp);
   uint64_t* empty_bar = full_bar + S;
-  uint64_t* tmem_full_bar = empty_bar + S;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + S;       // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM;
-  const int n0 = blockIdx.y * BN;
-  const int b1 = blockIdx.z % p.nb1;
-  const int b2 = blockIdx.z / p.nb1;
-  const int nkb = (p.k + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    ptx::mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tmem_full_bar[s], 1);
+      ptx::mbar_init(&tmem_empty_bar[s], kEpiWarps);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -143,26 +162,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (lane == 0) {
       ptx::prefetch_tmap(&tma_a);
       ptx::prefetch_tmap(&tma_b);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % S;
-        const uint32_t ph = (kb / S) & 1;
-        if (!ptx::mbar_wait(&empty_bar[s], ph ^ 1, watchdog, 1)) break;
-        ptx::mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
-        const uint32_t sa = ptx::smem_u32(smem + s * Cfg::kStageBytes);
-        const uint32_t sb = sa + Cfg::kABytes;
-        if (AMAJ == 0) {
-          ptx::tma_load_4d(sa, &tma_a, &full_bar[s], kb * BK, m0, b1 * p.a_m1, b2 * p.a_m2);
-        } else {
+      uint32_t it = 0;
+      bool ok = true;
+      for (int t = blockIdx.x; t < p.total_tiles && ok; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t, BN);
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          if (!ptx::mbar_wait(&empty_bar[s], ph ^ 1, watchdog, 1)) { ok = false; break; }
+          ptx::mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          const uint32_t sa = ptx::smem_u32(smem + s * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+          if (AMAJ == 0) {
+            ptx::tma_load_4d(sa, &tma_a, &full_bar[s], kb * BK, tc.m0, tc.b1 * p.a_m1, tc.b2 * p.a_m2);
+          } else {
 #pragma unroll
-          for (int c = 0; c < BM / 64; ++c)
-            ptx::tma_load_4d(sa + c * 8192, &tma_a, &full_bar[s], m0 + c * 64, kb * BK, b1 * p.a_m1, b2 * p.a_m2);
-        }
-        if (BMAJ == 0) {
-          ptx::tma_load_4d(sb, &tma_b, &full_bar[s], kb * BK, n0, b1 * p.b_m1, b2 * p.b_m2);
-        } else {
+            for (int c = 0; c < BM / 64; ++c)
+              ptx::tma_load_4d(sa + c * 8192, &tma_a, &full_bar[s], tc.m0 + c * 64, kb * BK, tc.b1 * p.a_m1, tc.b2 * p.a_m2);
+          }
+          if (BMAJ == 0) {
+            ptx::tma_load_4d(sb, &tma_b, &full_bar[s], kb * BK, tc.n0, tc.b1 * p.b_m1, tc.b2 * p.b_m2);
+          } else {
 #pragma unroll
-          for (int c = 0; c < BN / 64; ++c)
-            ptx::tma_load_4d(sb + c * 8192, &tma_b, &full_bar[s], n0 + c * 64, kb * BK, b1 * p.b_m1, b2 * p.b_m2);
+            for (int c = 0; c < BN / 64; ++c)
+              ptx::tma_load_4d(sb + c * 8192, &tma_b, &full_bar[s], tc.n0 + c * 64, kb * BK, tc.b1 * p.b_m1, tc.b2 * p.b_m2);
+          }
         }
       }
     }
@@ -170,89 +194,207 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, AMAJ, BMAJ);
+      uint32_t it = 0, tl = 0;
       bool ok = true;
-      for (int kb = 0; kb < nkb && ok; ++kb) {
-        const int s = kb % S;
-        const uint32_t ph = (kb / S) & 1;
-        if (!ptx::mbar_wait(&full_bar[s], ph, watchdog, 2)) { ok = false; break; }
+      for (int t = blockIdx.x; t < p.total_tiles && ok; t += gridDim.x, ++tl) {
+        const TileCoord tc = decode_tile(p, t, BN);
+        const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+        if (!ptx::mbar_wait(&tmem_empty_bar[as], aph ^ 1, watchdog, 4)) { ok = false; break; }
         ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem + s * Cfg::kStageBytes);
-        const uint32_t sb = sa + Cfg::kABytes;
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          if (!ptx::mbar_wait(&full_bar[s], ph, watchdog, 2)) { ok = false; break; }
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + s * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
 #pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk) {
-          const uint64_t adesc = (AMAJ == 0) ? ptx::make_smem_desc(sa + kk * 32, 16, 1024)
-                                             : ptx::make_smem_desc(sa + kk * 2048, 8192, 1024);
-          const uint64_t bdesc = (BMAJ == 0) ? ptx::make_smem_desc(sb + kk * 32, 16, 1024)
-                                             : ptx::make_smem_desc(sb + kk * 2048, 8192, 1024);
-          ptx::umma_f16(tmem_base, adesc, bdesc, idesc, (kb | kk) != 0 ? 1u : 0u);
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t adesc = (AMAJ == 0) ? ptx::make_smem_desc(sa + kk * 32, 16, 1024)
+                                               : ptx::make_smem_desc(sa + kk * 2048, 8192, 1024);
+            const uint64_t bdesc = (BMAJ == 0) ? ptx::make_smem_desc(sb + kk * 32, 16, 1024)
+                                               : ptx::make_smem_desc(sb + kk * 2048, 8192, 1024);
+            ptx::umma_f16(d_tmem, adesc, bdesc, idesc, (kb > tc.kb0 || kk > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
         }
-        ptx::umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+        if (ok) ptx::umma_commit(&tmem_full_bar[as]);  // accumulator of this tile complete
       }
-      ptx::umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
-    // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+    // ===== epilogue: warps 2..9; warp % 4 = TMEM lane quarter, (warp - 2) / 4 = which alternate column chunks =====
+    constexpr bool kF32 = sizeof(OutT) == 4;
+    constexpr int CW = kF32 ? 32 : 64;  // columns per chunk = one 128-byte staging row
+    const int ew = warp - 2;
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
-    const bool ok = ptx::mbar_wait(tmem_full_bar, 0, watchdog, 3);
-    ptx::tc_fence_after();
-    if (ok) {
-      OutT* crow = reinterpret_cast<OutT*>(p.c) + (long long)b1 * p.c_bs1 + (long long)b2 * p.c_bs2 +
-                   (long long)row * p.ldc;
-      OutT* prow = p.c_pre ? reinterpret_cast<OutT*>(p.c_pre) + (long long)b1 * p.c_bs1 +
-                                 (long long)b2 * p.c_bs2 + (long long)row * p.ldc
-                           : nullptr;
-      const OutT* rrow = p.res ? reinterpret_cast<const OutT*>(p.res) + (long long)b1 * p.r_bs1 +
-                                     (long long)b2 * p.r_bs2 + (long long)row * p.ldr
-                               : nullptr;
-      const bool c_vec = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
-      const bool p_vec = prow && ((reinterpret_cast<uintptr_t>(prow) & 15) == 0);
-      const bool r_vec = rrow && ((reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-        ptx::tmem_ld_wait();
-        const int col = n0 + c0;
-        if (row < p.m && col < p.n) {
-          const int nv = min(32, p.n - col);
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-          if (p.bias) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < nv) v[i] += __ldg(p.bias + (long long)b1 * p.bias_bs1 + col + i);
-          }
-          if (prow) store_vec<OutT>(prow + col, v, nv, p_vec);
-          if (p.act == 1) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_f(v[i]);
-          }
-          if (p.drop_thr) {
-            const unsigned long long base = (unsigned long long)((long long)b1 * p.c_bs1 + (long long)b2 * p.c_bs2 +
-                                                                 (long long)row * p.ldc + col);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(p.seed, base + i, p.drop_thr, p.inv_keep);
-          }
-          if (rrow) {
-            float rv[32];
-            load_vec<OutT>(rrow + col, rv, nv, r_vec);
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < nv) v[i] += rv[i];
-          }
-          if (p.accumulate) {
-            float cv[32];
-            load_vec<OutT>(crow + col, cv, nv, c_vec);
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < nv) v[i] += cv[i];
-          }
-          store_vec<OutT>(crow + col, v, nv, c_vec);
+    const int half = ew >> 2;
+    uint8_t* wbuf = stage_buf + ew * kStageBytesPerWarp;
+    const uint32_t wbuf_s = ptx::smem_u32(wbuf);
+    uint32_t tl = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tl) {
+      const TileCoord tc = decode_tile(p, t, BN);
+      const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+      if (!ptx::mbar_wait(&tmem_full_bar[as], aph, watchdog, 3)) break;
+      ptx::tc_fence_after();
+      const long long boff = (long long)tc.b1 * p.c_bs1 + (long long)tc.b2 * p.c_bs2;
+      const float* bias = p.bias ? p.bias + (long long)tc.b1 * p.bias_bs1 : nullptr;
+      const int row0 = tc.m0 + q * 32;
+      const int row = row0 + lane;
+      const uint32_t tm = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+      bool released = false;
+      auto release = [&]() {
+        if (!released) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+          released = true;
         }
+      };
+      if (row0 >= p.m) { release(); continue; }  // this warp's 32 rows are all padding
+      if (p.tma_epi) {
+        // ---- registers -> swizzled smem box -> TMA store / reduce-add (coalesced, clipped at the m/n edges) ----
+#pragma unroll 1
+        for (int c0 = half * CW; c0 < BN; c0 += 2 * CW) {
+          const int col = tc.n0 + c0;
+          if (col >= p.n) break;
+          float v[CW];
+          {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(tm + (uint32_t)c0, r);
+            if constexpr (CW == 64) {
+              uint32_t r2[32];
+              ptx::tmem_ld_32x32(tm + (uint32_t)c0 + 32, r2);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r2[i]);
+            } else {
+              ptx::tmem_ld_wait();
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          }
+          if (c0 + 2 * CW >= BN || tc.n0 + c0 + 2 * CW >= p.n) release();  // last TMEM read of this warp for this tile
+          const bool full = col + CW <= p.n;
+          epi_bias<CW>(v, p, bias, col, full);
+          // the previous TMA store of this warp must have finished reading the staging box
+          if (lane == 0) ptx::bulk_wait_read<0>();
+          __syncwarp();
+          if (p.c_pre) {
+            if (kF32) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                sts128(swz128(wbuf_s, lane, j), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                sts128(swz128(wbuf_s, lane, j), pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                       pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            }
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_4d(&tma_p, wbuf_s, col, row0, tc.b1, tc.b2);
+              ptx::bulk_commit();
+              ptx::bulk_wait_read<0>();
+            }
+            __syncwarp();
+          }
+          epi_act_drop<CW>(v, p, (unsigned long long)(boff + (long long)row * p.ldc + col));
+          if (p.res && row < p.m) {
+            const OutT* rrow = reinterpret_cast<const OutT*>(p.res) + (long long)tc.b1 * p.r_bs1 + (long long)tc.b2 * p.r_bs2 +
+                               (long long)row * p.ldr + col;
+            if (full && (reinterpret_cast<uintptr_t>(rrow) & 15) == 0) {
+              if (kF32) {
+#pragma unroll
+                for (int j = 0; j < CW / 4; ++j) {
+                  const float4 f = __ldg(reinterpret_cast<const float4*>(rrow) + j);
+                  v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < CW / 8; ++j) {
+                  const uint4 u = __ldg(reinterpret_cast<const uint4*>(rrow) + j);
+                  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(h[e]);
+                    v[8 * j + 2 * e] += f.x; v[8 * j + 2 * e + 1] += f.y;
+                  }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < CW; ++i)
+                if (col + i < p.n) v[i] += to_f<OutT>(rrow[i]);
+            }
+          }
+          if (kF32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts128(swz128(wbuf_s, lane, j), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts128(swz128(wbuf_s, lane, j), pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                     pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.accumulate) ptx::tma_reduce_add_4d(&tma_c, wbuf_s, col, row0, tc.b1, tc.b2);
+            else ptx::tma_store_4d(&tma_c, wbuf_s, col, row0, tc.b1, tc.b2);
+            ptx::bulk_commit();
+          }
+        }
+        release();
+      } else {
+        // ---- generic path (unaligned C): 32x32 transpose through the warp's smem box, coalesced plain stores ----
+        float* sbuf = reinterpret_cast<float*>(wbuf);
+        OutT* cbase = reinterpret_cast<OutT*>(p.c) + boff;
+        OutT* pbase = p.c_pre ? reinterpret_cast<OutT*>(p.c_pre) + boff : nullptr;
+        const OutT* rbase = p.res ? reinterpret_cast<const OutT*>(p.res) + (long long)tc.b1 * p.r_bs1 + (long long)tc.b2 * p.r_bs2 : nullptr;
+#pragma unroll 1
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
+          if (tc.n0 + c0 >= p.n) break;
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tm + (uint32_t)c0, r);
+          ptx::tmem_ld_wait();
+          if (c0 + 64 >= BN || tc.n0 + c0 + 64 >= p.n) release();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sbuf[lane * 32 + (j ^ lane)] = __uint_as_float(r[j]);
+          __syncwarp();
+          const int col = tc.n0 + c0 + lane;   // lane = column
+          if (col < p.n) {
+            const float bv = bias ? __ldg(bias + col) : 0.f;
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr) {
+              const int grow = row0 + rr;
+              if (grow >= p.m) break;
+              float v = sbuf[rr * 32 + (lane ^ rr)] * p.alpha + bv;
+              const long long off = (long long)grow * p.ldc + col;
+              if (pbase) pbase[off] = from_f<OutT>(v);
+              if (p.act == 1) v = gelu_f(v);
+              if (p.drop_thr) v *= dropout_scale(p.seed, (unsigned long long)(boff + off), p.drop_thr, p.inv_keep);
+              if (rbase) v += to_f<OutT>(rbase[(long long)grow * p.ldr + col]);
+              if (kF32) {
+                float* dst = reinterpret_cast<float*>(cbase) + off;
+                if (p.use_red) atomicAdd(dst, v);
+                else if (p.accumulate) *dst += v;
+                else *dst = v;
+              } else {
+                if (p.accumulate) v += to_f<OutT>(cbase[off]);
+                cbase[off] = from_f<OutT>(v);
+              }
+            }
+          }
+          __syncwarp();
+        }
+        release();
       }
     }
+    // all bulk stores of this warp must complete before the CTA exits (smem is released at exit)
+    if (lane == 0) ptx::bulk_wait<0>();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -284,6 +426,7 @@ struct TmapKey {
   uint64_t d[4];
   uint64_t s[3];
   uint32_t box[2];
+  uint64_t dtype;
   bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
 };
 struct TmapKeyHash {
@@ -303,7 +446,7 @@ void tmap_cache_free(Ctx* ctx) {
 
 // bf16 tensor map: dims d[0..3] (d[0] innermost, contiguous), strides in BYTES for dims 1..3.
 static int get_tmap(Ctx* ctx, CUtensorMap* out, const void* base, const uint64_t d[4], const uint64_t sbytes[3],
-                    uint32_t box0, uint32_t box1) {
+                    uint32_t box0, uint32_t box1, bool f32 = false) {
   if (resolve_encode(ctx)) return TS_ECUDA;
   if (!ctx->tmap_cache) ctx->tmap_cache = new TmapCache();
   TmapCache& cache = *reinterpret_cast<TmapCache*>(ctx->tmap_cache);
@@ -314,6 +457,7 @@ static int get_tmap(Ctx* ctx, CUtensorMap* out, const void* base, const uint64_t
   for (int i = 0; i < 3; ++i) key.s[i] = sbytes[i];
   key.box[0] = box0;
   key.box[1] = box1;
+  key.dtype = f32 ? 1 : 0;
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return 0; }
   cuuint64_t gd[4] = {d[0], d[1], d[2], d[3]};
@@ -321,7 +465,7 @@ static int get_tmap(Ctx* ctx, CUtensorMap* out, const void* base, const uint64_t
   cuuint32_t bx[4] = {box0, box1, 1, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
-      out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gd, gs, bx, es,
+      out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gd, gs, bx, es,
       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -352,8 +496,8 @@ bool gemm_tc_supported(const ts_gemm_desc* d) {
 }
 
 template <int BN, int AMAJ, int BMAJ, typename OutT>
-static int launch_tc(Ctx* ctx, const ts_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb,
-                     const EpiParams& ep, cudaStream_t st) {
+static int launch_tc(Ctx* ctx, const ts_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                     const CUtensorMap& tp, const EpiParams& ep, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   auto kern = gemm_tc_kernel<BN, AMAJ, BMAJ, OutT>;
   static bool attr_set = false;
@@ -361,19 +505,19 @@ static int launch_tc(Ctx* ctx, const ts_gemm_desc* d, const CUtensorMap& ta, con
     TS_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     attr_set = true;
   }
-  dim3 grid(cdiv(d->m, BM), cdiv(d->n, BN), d->batch1 * d->batch2);
-  kern<<<grid, 192, Cfg::kSmem, st>>>(ta, tb, ep, ctx->d_watchdog);
+  const int grid = ep.total_tiles < ctx->num_sms ? ep.total_tiles : ctx->num_sms;
+  kern<<<grid, kThreads, Cfg::kSmem, st>>>(ta, tb, tc, tp, ep, ctx->d_watchdog);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
 
 template <int BN, typename OutT>
-static int dispatch_major(Ctx* ctx, const ts_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb,
-                          const EpiParams& ep, cudaStream_t st) {
-  if (d->a_major == 0 && d->b_major == 0) return launch_tc<BN, 0, 0, OutT>(ctx, d, ta, tb, ep, st);
-  if (d->a_major == 0 && d->b_major == 1) return launch_tc<BN, 0, 1, OutT>(ctx, d, ta, tb, ep, st);
-  if (d->a_major == 1 && d->b_major == 0) return launch_tc<BN, 1, 0, OutT>(ctx, d, ta, tb, ep, st);
-  return launch_tc<BN, 1, 1, OutT>(ctx, d, ta, tb, ep, st);
+static int dispatch_major(Ctx* ctx, const ts_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                          const CUtensorMap& tp, const EpiParams& ep, cudaStream_t st) {
+  if (d->a_major == 0 && d->b_major == 0) return launch_tc<BN, 0, 0, OutT>(ctx, d, ta, tb, tc, tp, ep, st);
+  if (d->a_major == 0 && d->b_major == 1) return launch_tc<BN, 0, 1, OutT>(ctx, d, ta, tb, tc, tp, ep, st);
+  if (d->a_major == 1 && d->b_major == 0) return launch_tc<BN, 1, 0, OutT>(ctx, d, ta, tb, tc, tp, ep, st);
+  return launch_tc<BN, 1, 1, OutT>(ctx, d, ta, tb, tc, tp, ep, st);
 }
 
 int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
@@ -381,11 +525,35 @@ int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
              "gemm_tc: operands must be bf16 with 16-byte aligned bases/strides");
   TS_REQUIRE(ctx, !(d->accumulate && (d->act || d->residual)), TS_EINVAL, "gemm: accumulate excludes act/residual");
   const int nb1 = d->batch1 > 0 ? d->batch1 : 1, nb2 = d->batch2 > 0 ? d->batch2 : 1;
-  // tile-N choice: cover n with the fewest wasted columns; prefer 128.
-  int bn = 128;
-  if (d->n <= 64) bn = 64;
-  else if (d->n % 128 != 0 && d->n % 64 == 0 && d->n < 512) bn = 64;
-  else if (d->n >= 1024 && d->n % 256 == 0 && (long long)cdiv(d->m, BM) * (d->n / 256) * nb1 * nb2 >= 2 * ctx->num_sms) bn = 256;
+  // tile-N choice: minimise (waves of the persistent grid) x (tile cost); wider tiles read less smem per FLOP.
+  const int mt = cdiv(d->m, BM), nkb = cdiv(d->k, BK), sms = ctx->num_sms;
+  int bn = 64;
+  {
+    double best = 1e30;
+    const int cand[3] = {256, 128, 64};
+    const double eff[3] = {1.0, 1.12, 1.45};
+    for (int i = 0; i < 3; ++i) {
+      if (cand[i] > 64 && d->n <= cand[i] / 2) continue;
+      const long long tiles = (long long)mt * cdiv(d->n, cand[i]) * nb1 * nb2;
+      const double waves = (double)((tiles + sms - 1) / sms);
+      const double fill = tiles < sms ? 1.0 + 0.25 * (double)(sms - tiles) / sms : 1.0;  // few tiles: prefer more, smaller ones
+      const double score = waves * cand[i] * eff[i] * fill;
+      if (score < best) { best = score; bn = cand[i]; }
+    }
+  }
+  const int nt = cdiv(d->n, bn);
+  const long long tiles_ll = (long long)mt * nt * nb1 * nb2;
+  TS_REQUIRE(ctx, tiles_ll < (1ll << 30), TS_ESHAPE, "gemm_tc: too many tiles");
+  // split-K only where partial sums may be added: fp32 "C += A*B" with a plain epilogue
+  int splitk = 1;
+  if (d->out_dtype == TS_F32 && d->accumulate && !d->bias && !d->c_preact && d->drop <= 0.f && tiles_ll * 2 <= sms && nkb >= 16) {
+    int want = (int)(sms / tiles_ll);
+    const int cap = nkb / 8;
+    splitk = want < cap ? want : cap;
+    if (splitk < 1) splitk = 1;
+  }
+  const int kbps = cdiv(nkb, splitk);
+  splitk = cdiv(nkb, kbps);
 
   CUtensorMap ta, tb;
   {
@@ -413,6 +581,8 @@ int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
   ep.ldc = d->ldc; ep.ldr = d->ldr; ep.c_bs1 = d->c_bs1; ep.c_bs2 = d->c_bs2; ep.r_bs1 = d->r_bs1; ep.r_bs2 = d->r_bs2; ep.bias_bs1 = d->bias_bs1;
   ep.alpha = d->alpha; ep.act = d->act; ep.accumulate = d->accumulate;
   ep.m = d->m; ep.n = d->n; ep.k = d->k; ep.nb1 = nb1;
+  ep.mt = mt; ep.nt = nt; ep.nb = nb1 * nb2; ep.splitk = splitk; ep.kb_per_split = kbps;
+  ep.total_tiles = (int)(tiles_ll * splitk); ep.use_red = splitk > 1 ? 1 : 0;
   ep.a_m1 = (nb1 > 1 && d->a_bs1 != 0) ? 1 : 0; ep.a_m2 = (nb2 > 1 && d->a_bs2 != 0) ? 1 : 0;
   ep.b_m1 = (nb1 > 1 && d->b_bs1 != 0) ? 1 : 0; ep.b_m2 = (nb2 > 1 && d->b_bs2 != 0) ? 1 : 0;
   ep.drop_thr = 0; ep.inv_keep = 1.f; ep.seed = d->seed;
@@ -421,16 +591,38 @@ int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
     ep.drop_thr = (uint32_t)(t > 4294967295.0 ? 4294967295.0 : t);
     ep.inv_keep = 1.f / (1.f - d->drop);
   }
+  // TMA-store epilogue when C (and the pre-activation copy) can be described by a tensor map
+  CUtensorMap tc, tp;
+  memset(&tc, 0, sizeof(tc)); memset(&tp, 0, sizeof(tp));
+  {
+    const bool f32 = d->out_dtype == TS_F32;
+    const uint64_t esz = f32 ? 4 : 2;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    auto s16b = [&](long long elems) { return elems > 0 && ((uint64_t)elems * esz) % 16 == 0; };
+    bool ok = al16(d->c) && s16b(d->ldc) && (!d->c_preact || al16(d->c_preact));
+    if (nb1 > 1) ok = ok && s16b(d->c_bs1);
+    if (nb2 > 1) ok = ok && s16b(d->c_bs2);
+    if (!f32 && d->accumulate) ok = false;     // bf16 read-modify-write stays on the generic path
+    if (ok) {
+      uint64_t dims[4] = {(uint64_t)d->n, (uint64_t)d->m, (uint64_t)nb1, (uint64_t)nb2};
+      uint64_t str[3] = {(uint64_t)d->ldc * esz, (uint64_t)(nb1 > 1 ? d->c_bs1 : d->ldc) * esz, (uint64_t)(nb2 > 1 ? d->c_bs2 : d->ldc) * esz};
+      int r = get_tmap(ctx, &tc, d->c, dims, str, f32 ? 32 : 64, 32, f32);
+      if (r) return r;
+      if (d->c_preact) { r = get_tmap(ctx, &tp, d->c_preact, dims, str, f32 ? 32 : 64, 32, f32); if (r) return r; }
+    }
+    ep.tma_epi = ok ? 1 : 0;
+    if (ok && splitk > 1) ep.accumulate = 1;   // split-K partials are added by the TMA reduce
+  }
   ts_gemm_desc dd = *d;
   dd.batch1 = nb1; dd.batch2 = nb2;
   if (d->out_dtype == TS_BF16) {
-    if (bn == 64) return dispatch_major<64, bf16>(ctx, &dd, ta, tb, ep, st);
-    if (bn == 128) return dispatch_major<128, bf16>(ctx, &dd, ta, tb, ep, st);
-    return dispatch_major<256, bf16>(ctx, &dd, ta, tb, ep, st);
+    if (bn == 64) return dispatch_major<64, bf16>(ctx, &dd, ta, tb, tc, tp, ep, st);
+    if (bn == 128) return dispatch_major<128, bf16>(ctx, &dd, ta, tb, tc, tp, ep, st);
+    return dispatch_major<256, bf16>(ctx, &dd, ta, tb, tc, tp, ep, st);
   } else {
-    if (bn == 64) return dispatch_major<64, float>(ctx, &dd, ta, tb, ep, st);
-    if (bn == 128) return dispatch_major<128, float>(ctx, &dd, ta, tb, ep, st);
-    return dispatch_major<256, float>(ctx, &dd, ta, tb, ep, st);
+    if (bn == 64) return dispatch_major<64, float>(ctx, &dd, ta, tb, tc, tp, ep, st);
+    if (bn == 128) return dispatch_major<128, float>(ctx, &dd, ta, tb, tc, tp, ep, st);
+    return dispatch_major<256, float>(ctx, &dd, ta, tb, tc, tp, ep, st);
   }
 }
 

@@ -74,6 +74,12 @@ __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t smem_src
                "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// TMA reduce-add of a smem box into global memory (element-wise atomic add performed by the TMA unit; fp32 maps here)
+__device__ __forceinline__ void tma_reduce_add_4d(const void* tmap, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"((uint64_t)tmap),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");

@@ -327,12 +327,12 @@ static int w2v_forward(W2V* m, const float* wave, const int* neg, long long neg_
   return 0;
 }
 
-// dense layer backward: dW = X^T dY (fp32, overwrite), db += colsum(dY), dX = dY W^T (optional, + residual)
+// dense layer backward: dW += X^T dY (fp32; the gradient arena is zeroed at the start of backward, so split-K partials may be added), db += colsum(dY), dX = dY W^T (optional, + residual)
 static int dense_bwd(W2V* m, const void* X, int K, const void* dY, int Nn, long long w_off, long long ldw, long long b_off,
                      void* dX, const void* dres, int rows, cudaStream_t st) {
   Ctx* ctx = m->ctx;
   const int dt = m->prec;
-  TS_TRY(GemmB(dt, TS_F32).A(X, 1, K).B(dY, 1, Nn).C(m->G + w_off, ldw).mnk(K, Nn, rows).run(ctx, st));
+  TS_TRY(GemmB(dt, TS_F32).A(X, 1, K).B(dY, 1, Nn).C(m->G + w_off, ldw).mnk(K, Nn, rows).acc().run(ctx, st));
   if (b_off >= 0) TS_TRY(colsum_acc(ctx, dt, dY, Nn, rows, Nn, m->G + b_off, st));
   if (dX) {
     GemmB g(dt, dt);
@@ -436,7 +436,7 @@ static int w2v_backward_stage(W2V* m, int stage, cudaStream_t st) {
     // wgrad: dW[(j,c), g*cpg+o] = sum_{b,t} hp[b,t+j,c] * dy[b,t,o]  (uniform rows over all batches; dummy rows hit zeros)
     TS_TRY(GemmB(dt, TS_F32).A(m->hg, 1, cpg).astride((long long)B * Rp * cpg, 0)
                .B((const char*)m->g_dyg + m->E((long long)leftp * cpg), 1, cpg).bstride((long long)B * Rp * cpg, 0)
-               .C(m->G + m->pos_w, C).cstride(cpg, 0).mnk(K * cpg, cpg, B * Rp - leftp).batch(G, 1).run(ctx, st));
+               .C(m->G + m->pos_w, C).cstride(cpg, 0).mnk(K * cpg, cpg, B * Rp - leftp).batch(G, 1).acc().run(ctx, st));
     // dgrad: da[b,tau,g*cpg+c] = dsum + sum_{jj,o} dyp[b,tau+jj,o] * wt[g][jj][o][c]
     TS_TRY(GemmB(dt, dt).A(m->g_dyg, 0, cpg).astride((long long)B * Rp * cpg, (long long)Rp * cpg)
                .B(m->wt_flip, 1, cpg).bstride((long long)K * cpg * cpg, 0)
@@ -462,7 +462,7 @@ static int w2v_backward_stage(W2V* m, int stage, cudaStream_t st) {
       const int Cin = c.conv_dim[i - 1], k = c.conv_kernel[i], s = c.conv_stride[i];
       const int rows = B * m->Rq[i];
       TS_TRY(GemmB(dt, TS_F32).A(m->a[i - 1], 1, (long long)s * Cin).B(m->g_dc, 1, Ci).C(m->G + m->conv_w[i], Ci)
-                 .mnk(k * Cin, Ci, rows).run(ctx, st));
+                 .mnk(k * Cin, Ci, rows).acc().run(ctx, st));
       TS_TRY(GemmB(dt, dt).A(m->g_dc, 0, Ci).B(m->W(m->conv_w[i]), 0, Ci).C(m->g_dcol, (long long)k * Cin)
                  .mnk(rows, k * Cin, Ci).run(ctx, st));
     }

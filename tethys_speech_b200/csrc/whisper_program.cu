@@ -226,12 +226,12 @@ static int attn_backward(Whisper* m, const void* q, long long ldq, const void* k
   return 0;
 }
 
-// dW = X^T dY (fp32 overwrite), db += colsum(dY), dX = dY W^T (+ dres)
+// dW += X^T dY (fp32; gradient arena zeroed at the start of backward), db += colsum(dY), dX = dY W^T (+ dres)
 static int dense_bwd(Whisper* m, const void* X, int K, const void* dY, int Nn, long long w_off, long long ldw, long long b_off,
                      void* dX, const void* dres, long long rows, cudaStream_t st) {
   Ctx* ctx = m->ctx;
   const int dt = m->prec;
-  TS_TRY(GemmB(dt, TS_F32).A(X, 1, K).B(dY, 1, Nn).C(m->G + w_off, ldw).mnk(K, Nn, (int)rows).run(ctx, st));
+  TS_TRY(GemmB(dt, TS_F32).A(X, 1, K).B(dY, 1, Nn).C(m->G + w_off, ldw).mnk(K, Nn, (int)rows).acc().run(ctx, st));
   if (b_off >= 0) TS_TRY(colsum_acc(ctx, dt, dY, Nn, (int)rows, Nn, m->G + b_off, st));
   if (dX) {
     GemmB g(dt, dt);
@@ -373,7 +373,7 @@ static int whisper_backward_stage(Whisper* m, int stage, cudaStream_t st) {
   const int Ld = c.dec_layers, Le = c.enc_layers;
   if (stage == 0) {
     // lm_head: dW = dec_out^T dlogits ; d(dec_out) = dlogits W^T ; final decoder LN
-    TS_TRY(GemmB(dt, TS_F32).A(m->dec_out, 1, d).B(m->dlogits, 1, m->Vp).C(m->G + m->lm_w, m->Vp).mnk(d, (int)m->Vp, (int)Md).run(ctx, st));
+    TS_TRY(GemmB(dt, TS_F32).A(m->dec_out, 1, d).B(m->dlogits, 1, m->Vp).C(m->G + m->lm_w, m->Vp).mnk(d, (int)m->Vp, (int)Md).acc().run(ctx, st));
     TS_TRY(GemmB(dt, dt).A(m->dlogits, 0, m->Vp).B(m->W(m->lm_w), 0, m->Vp).C(m->s_x, d).mnk((int)Md, d, (int)m->Vp).run(ctx, st));
     TS_TRY(layernorm_bwd(ctx, dt, m->s_x, m->g_final, m->P + m->dec_ln_g, m->dec_m, m->dec_r, nullptr, m->s_a, m->G + m->dec_ln_g, m->G + m->dec_ln_b, (int)Md, d, st));
     TS_TRY(fill_zero(ctx, m->s_denc, m->E(Me * d), st));
@@ -438,14 +438,14 @@ static int whisper_backward_stage(Whisper* m, int stage, cudaStream_t st) {
   void* du2 = m->s_du;
   TS_TRY(gelu_bwd_rows(ctx, dt, dh0, T, nullptr, m->u2, du2, m->Rq2, B, T, d, st));
   TS_TRY(colsum_acc(ctx, dt, du2, d, (int)(B * m->Rq2), d, m->G + m->conv2_b, st));
-  TS_TRY(GemmB(dt, TS_F32).A(m->a1, 1, 2 * d).B(du2, 1, d).C(m->G + m->conv2_w, d).mnk(3 * d, d, (int)(B * m->Rq2)).run(ctx, st));
+  TS_TRY(GemmB(dt, TS_F32).A(m->a1, 1, 2 * d).B(du2, 1, d).C(m->G + m->conv2_w, d).mnk(3 * d, d, (int)(B * m->Rq2)).acc().run(ctx, st));
   TS_TRY(GemmB(dt, dt).A(du2, 0, d).B(m->W(m->conv2_w), 0, d).C(m->s_dcol, 3 * d).mnk((int)(B * m->Rq2), 3 * d, d).run(ctx, st));
   Col2imSrc col;
   col.dcol = m->s_dcol; col.rows_per_batch = m->Rq2; col.t_next = T; col.k = 3; col.s = 2; col.left = 0;
   void* du1 = m->s_du;  // du2 is dead once dcol exists
   TS_TRY(gelu_bwd_rows(ctx, dt, nullptr, 0, &col, m->u1, du1, m->Rq1, B, m->Tm, d, st));
   TS_TRY(colsum_acc(ctx, dt, du1, d, (int)(B * m->Rq1), d, m->G + m->conv1_b, st));
-  TS_TRY(GemmB(dt, TS_F32).A(m->xT, 1, c.n_mels).B(du1, 1, d).C(m->G + m->conv1_w, d).mnk(3 * c.n_mels, d, (int)(B * m->Rq1)).run(ctx, st));
+  TS_TRY(GemmB(dt, TS_F32).A(m->xT, 1, c.n_mels).B(du1, 1, d).C(m->G + m->conv1_w, d).mnk(3 * c.n_mels, d, (int)(B * m->Rq1)).acc().run(ctx, st));
   return 0;
 }
 

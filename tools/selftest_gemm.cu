@@ -112,7 +112,7 @@ static int run_case(ts_ctx* ctx, const Case& cs, int engine, bool timing) {
           const double got = hc[z * c_bs + (long long)i * n + j];
           double err = fabs(got - v);
           if (cs.preact) err = fmax(err, fabs((double)hp[z * c_bs + (long long)i * n + j] - pre));
-          const double tol = (cs.out_f32 ? 2e-4 : 1.2e-2) * (1.0 + fabs(v));
+          const double tol = (cs.out_f32 ? 2e-4 : 1.2e-2) * (1.0 + fmax(fabs(v), cs.preact ? fabs(pre) : 0.0));
           if (err > tol) {
             if (bad < 5) printf("    mismatch z=%d i=%d j=%d got=%g ref=%g\n", z, i, j, got, v);
             ++bad;
@@ -164,6 +164,12 @@ int main(int argc, char** argv) {
       {"epi_accumulate", 128, 256, 192, 1, 1, 1, 1, 0, 0, 1, 0, 0, 0, 1, 0, 1.f},
       {"conv_window_rows", 120, 128, 192, 0, 1, 2, 1, 128, 0, 0, 1, 0, 0, 0, 0, 1.f},
       {"conv_window_wgrad", 192, 128, 120, 1, 1, 1, 1, 128, 0, 1, 0, 0, 0, 0, 0, 1.f},
+      {"persist_many_tiles", 2560, 2304, 128, 0, 1, 1, 1, 0, 0, 0, 1, 1, 1, 0, 1, 1.f},
+      {"persist_many_f32", 1920, 1280, 192, 1, 1, 1, 1, 0, 0, 1, 0, 0, 0, 1, 0, 0.5f},
+      {"splitk_wgrad", 256, 256, 4096, 1, 1, 1, 1, 0, 0, 1, 0, 0, 0, 1, 0, 1.f},
+      {"splitk_ragged", 200, 136, 3000, 1, 1, 2, 1, 0, 0, 1, 0, 0, 0, 1, 0, 1.f},
+      {"odd_n_bf16", 150, 75, 72, 0, 0, 2, 1, 0, 0, 0, 1, 1, 1, 0, 1, 1.f},
+      {"batched_many", 300, 300, 64, 0, 0, 12, 8, 0, 0, 0, 0, 0, 0, 0, 0, 0.125f},
   };
   int fails = 0;
   printf("== correctness: tcgen05 engine (2) vs fp64 CPU reference ==\n");
@@ -176,7 +182,13 @@ int main(int argc, char** argv) {
         {"ffn1 6000x3072x768", 6000, 3072, 768, 0, 1, 1, 1, 0, 0, 0, 1, 0, 0, 0, 0, 1.f},
         {"ffn2 6000x768x3072", 6000, 768, 3072, 0, 1, 1, 1, 0, 0, 0, 1, 0, 0, 0, 0, 1.f},
         {"dgrad 6000x768x3072", 6000, 768, 3072, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1.f},
-        {"wgrad 768x3072x6000", 768, 3072, 6000, 1, 1, 1, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1.f},
+        {"ffn1+gelu+preact", 6000, 3072, 768, 0, 1, 1, 1, 0, 0, 0, 1, 1, 0, 0, 1, 1.f},
+        {"qkv 6000x2304x768", 6000, 2304, 768, 0, 1, 1, 1, 0, 0, 0, 1, 0, 0, 0, 0, 1.f},
+        {"out 6000x768x768 +res", 6000, 768, 768, 0, 1, 1, 1, 0, 0, 0, 1, 0, 1, 0, 0, 1.f},
+        {"wgrad 768x3072x6000", 768, 3072, 6000, 1, 1, 1, 1, 0, 0, 1, 0, 0, 0, 1, 0, 1.f},
+        {"wgrad 768x768x6000", 768, 768, 6000, 1, 1, 1, 1, 0, 0, 1, 0, 0, 0, 1, 0, 1.f},
+        {"convwgrad 1536x512x96000", 1536, 512, 96000, 1, 1, 1, 1, 1024, 0, 1, 0, 0, 0, 1, 0, 1.f},
+        {"conv1 192000x512x1536", 192000, 512, 1536, 0, 1, 1, 1, 1024, 0, 0, 0, 0, 0, 0, 0, 1.f},
         {"sq 8192^3", 8192, 8192, 8192, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1.f},
         {"sq 8192^3 kn", 8192, 8192, 8192, 0, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1.f},
         {"qk 750x750x64 x96", 750, 750, 64, 0, 0, 12, 8, 0, 0, 0, 0, 0, 0, 0, 0, 0.125f},
