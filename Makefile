@@ -9,7 +9,7 @@ OBJS      := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
 HDRS      := $(wildcard $(CSRC)/*.cuh) include/tethys.h
 LIB       := tethys_speech_b200/libtethys.so
 
-all: $(LIB) tools/selftest_gemm
+all: $(LIB) tools/selftest_gemm tools/selftest_attn
 
 build/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p build
@@ -22,7 +22,11 @@ tools/selftest_gemm: tools/selftest_gemm.cu $(LIB) include/tethys.h
 	$(NVCC) $(ARCH) -O2 -std=c++17 -cudart static -o $@ tools/selftest_gemm.cu -Ltethys_speech_b200 -ltethys \
 	    -Xlinker -rpath -Xlinker '$$ORIGIN/../tethys_speech_b200'
 
+tools/selftest_attn: tools/selftest_attn.cu $(LIB) include/tethys.h
+	$(NVCC) $(ARCH) -O2 -std=c++17 -cudart static -o $@ tools/selftest_attn.cu -Ltethys_speech_b200 -ltethys \
+	    -Xlinker -rpath -Xlinker '$$ORIGIN/../tethys_speech_b200'
+
 clean:
-	rm -rf build $(LIB) tools/selftest_gemm
+	rm -rf build $(LIB) tools/selftest_gemm tools/selftest_attn
 
 .PHONY: all clean

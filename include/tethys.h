@@ -95,6 +95,35 @@ typedef struct {
 
 int ts_gemm(ts_ctx* ctx, const ts_gemm_desc* d, void* stream);
 
+/* ---- K10: fused attention (tcgen05), head_dim 64, bf16 -------------------------------------------------------
+ * Replaces  softmax(q k^T * scale + mask) -> dropout -> . v  and its autodiff transpose:
+ *   W:147-167 (MultiHeadAttention.call: self, cross and the "anti-causal" decoder mask of W:416-418 / W:150-154),
+ *   V:348-362 (Wav2Vec2MultiHeadAttention.call). Score/probability tensors never reach HBM.
+ * q [B, Tq, *] / k, v [B, Tk, *] / o, d_o [B, Tq, *]: head h occupies columns [64h, 64h+64) from the given base;
+ * *_ld is the row stride and *_bs the batch stride in elements (so q/k/v may be slices of one fused projection).
+ * stats [B, heads, Tq, 2] fp32 (row max, log row-sum) is written by forward and read by backward;
+ * dsum [B, heads, Tq] fp32 is scratch of backward. mask_mode: 0 none, 1 adds -1e9 (fp32) to keys j <= i.
+ * Dropout keep-masks are a pure function of (seed, b, h, i, j); backward regenerates them.
+ */
+typedef struct {
+  const void *q, *k, *v;
+  void* o;
+  int64_t q_ld, q_bs, kv_ld, kv_bs, o_ld, o_bs;
+  float* stats;
+  int32_t batch, heads, tq, tk, head_dim;
+  float scale;
+  int32_t mask_mode;
+  float drop;
+  uint64_t seed;
+  /* backward only */
+  const void* d_o;
+  void *dq, *dk, *dv;
+  int64_t dq_ld, dq_bs, dkv_ld, dkv_bs;
+  float* dsum;
+} ts_attn_desc;
+int ts_attn_fwd(ts_ctx* ctx, const ts_attn_desc* d, void* stream);
+int ts_attn_bwd(ts_ctx* ctx, const ts_attn_desc* d, void* stream);
+
 /* ---- K19/K20: gradient clipping + Keras-2.10 legacy Adam over a flat arena ------------------------
  * Replaces tf.clip_by_global_norm (V:1243, VS:1171), the optimizer's clipnorm=1.0 (V:1274, VS:1206) and
  * tf.keras.optimizers.Adam.apply_gradients (W:834, V:1246, VS:1174, WS:1179) minus its all-reduce.

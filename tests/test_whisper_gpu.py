@@ -44,11 +44,18 @@ def _run(O, W, ocfg, cfg, B, Tm, S, precision, tol, gtol, seed=0):
     bad = {k: v for k, v in errs.items() if not v <= tol}
     assert not bad, f"forward mismatch (tol {tol}): {bad}; all {errs}"
     # App. C-1: the last decoder query sees only masked keys -> exactly uniform attention 1/S
-    P0 = model._prog.buffer("decoder_self_attn_probs0").float()[:, :, S - 1, :S]
-    assert torch.allclose(P0, torch.full_like(P0, 1.0 / S), rtol=1e-2 if precision == "bf16" else 1e-6)
-    # ... and query i attends only to keys j > i
-    Pfull = model._prog.buffer("decoder_self_attn_probs0").float()[0, 0, :S, :S]
-    assert float(torch.tril(Pfull[:-1], diagonal=0).abs().max()) == 0.0
+    if precision == "fp32":
+        P0 = model._prog.buffer("decoder_self_attn_probs0").float()[:, :, S - 1, :S]
+        assert torch.allclose(P0, torch.full_like(P0, 1.0 / S), rtol=1e-6)
+        # ... and query i attends only to keys j > i
+        Pfull = model._prog.buffer("decoder_self_attn_probs0").float()[0, 0, :S, :S]
+        assert float(torch.tril(Pfull[:-1], diagonal=0).abs().max()) == 0.0
+    else:
+        # the fused kernels keep only (row max, log row-sum): a uniform row over S keys at -1e9 has max -1e9 and sum S
+        # (the mask itself is checked element-wise in tests/test_attention_gpu.py)
+        st = model._prog.buffer("decoder_self_attn_stats0")[:, :, S - 1, :]
+        assert float(st[..., 0].max()) <= -9.0e8
+        assert torch.allclose(st[..., 1], torch.full_like(st[..., 1], float(np.log(S))), rtol=1e-5)
     gerrs = {}
     gscale = max(float(v.abs().max()) for v in og.values())
     for name, gg in zip(model.variable_names, grads):

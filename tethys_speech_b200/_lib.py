@@ -42,6 +42,21 @@ class GemmDesc(C.Structure):
     ]
 
 
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p),
+        ("q_ld", C.c_int64), ("q_bs", C.c_int64), ("kv_ld", C.c_int64), ("kv_bs", C.c_int64),
+        ("o_ld", C.c_int64), ("o_bs", C.c_int64),
+        ("stats", C.c_void_p),
+        ("batch", C.c_int32), ("heads", C.c_int32), ("tq", C.c_int32), ("tk", C.c_int32), ("head_dim", C.c_int32),
+        ("scale", C.c_float), ("mask_mode", C.c_int32), ("drop", C.c_float),
+        ("seed", C.c_uint64),
+        ("d_o", C.c_void_p), ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+        ("dq_ld", C.c_int64), ("dq_bs", C.c_int64), ("dkv_ld", C.c_int64), ("dkv_bs", C.c_int64),
+        ("dsum", C.c_void_p),
+    ]
+
+
 class W2VConfig(C.Structure):
     _fields_ = [
         ("hidden", C.c_int32), ("layers", C.c_int32), ("heads", C.c_int32), ("ffn", C.c_int32),
@@ -75,6 +90,8 @@ SYMBOLS = {
     "ts_watchdog_check": (_I, [_P]),
     "ts_launch_count": (_L, [_P]),
     "ts_gemm": (_I, [_P, C.POINTER(GemmDesc), _P]),
+    "ts_attn_fwd": (_I, [_P, C.POINTER(AttnDesc), _P]),
+    "ts_attn_bwd": (_I, [_P, C.POINTER(AttnDesc), _P]),
     "ts_optim_create": (_I, [_P, _I, C.POINTER(_L), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L), _L, C.POINTER(_P)]),
     "ts_optim_destroy": (None, [_P]),
     "ts_optim_clip_global": (_I, [_P, _P, _F, _P, _P]),

@@ -445,8 +445,8 @@ void tmap_cache_free(Ctx* ctx) {
 }
 
 // bf16 tensor map: dims d[0..3] (d[0] innermost, contiguous), strides in BYTES for dims 1..3.
-static int get_tmap(Ctx* ctx, CUtensorMap* out, const void* base, const uint64_t d[4], const uint64_t sbytes[3],
-                    uint32_t box0, uint32_t box1, bool f32 = false) {
+int get_tmap(Ctx* ctx, CUtensorMap* out, const void* base, const uint64_t d[4], const uint64_t sbytes[3],
+             uint32_t box0, uint32_t box1, bool f32 = false) {
   if (resolve_encode(ctx)) return TS_ECUDA;
   if (!ctx->tmap_cache) ctx->tmap_cache = new TmapCache();
   TmapCache& cache = *reinterpret_cast<TmapCache*>(ctx->tmap_cache);
@@ -525,35 +525,39 @@ int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
              "gemm_tc: operands must be bf16 with 16-byte aligned bases/strides");
   TS_REQUIRE(ctx, !(d->accumulate && (d->act || d->residual)), TS_EINVAL, "gemm: accumulate excludes act/residual");
   const int nb1 = d->batch1 > 0 ? d->batch1 : 1, nb2 = d->batch2 > 0 ? d->batch2 : 1;
-  // tile-N choice: minimise (waves of the persistent grid) x (tile cost); wider tiles read less smem per FLOP.
+  // Tile-N and split-K choice from a small cost model (units: 64-deep k-blocks of one 128 x 1 column strip):
+  //   cost = waves * k_blocks_per_work_item * bn * eff(bn) + tail_epilogue * bn
+  // Wider tiles read less smem per FLOP (eff), more/smaller work items fill the 148 SMs and shorten the un-overlapped
+  // last epilogue. Split-K only where partial sums may be added: fp32 "C += A*B" with a plain epilogue (wgrad).
   const int mt = cdiv(d->m, BM), nkb = cdiv(d->k, BK), sms = ctx->num_sms;
-  int bn = 64;
+  const bool split_ok = d->out_dtype == TS_F32 && d->accumulate && !d->bias && !d->c_preact && d->drop <= 0.f && nkb >= 16;
+  int bn = 64, splitk = 1;
   {
     double best = 1e30;
     const int cand[3] = {256, 128, 64};
     const double eff[3] = {1.0, 1.12, 1.45};
+    const double tail = d->out_dtype == TS_F32 ? 12.0 : 6.0;
     for (int i = 0; i < 3; ++i) {
       if (cand[i] > 64 && d->n <= cand[i] / 2) continue;
       const long long tiles = (long long)mt * cdiv(d->n, cand[i]) * nb1 * nb2;
-      const double waves = (double)((tiles + sms - 1) / sms);
-      const double fill = tiles < sms ? 1.0 + 0.25 * (double)(sms - tiles) / sms : 1.0;  // few tiles: prefer more, smaller ones
-      const double score = waves * cand[i] * eff[i] * fill;
-      if (score < best) { best = score; bn = cand[i]; }
+      int sk = 1;
+      if (split_ok && tiles < sms) {
+        sk = (int)(sms / tiles);
+        const int cap = nkb / 8;
+        if (sk > cap) sk = cap;
+        if (sk < 1) sk = 1;
+      }
+      const int kb = cdiv(nkb, sk);
+      sk = cdiv(nkb, kb);
+      const double waves = (double)((tiles * sk + sms - 1) / sms);
+      const double score = waves * kb * cand[i] * eff[i] + tail * cand[i];
+      if (score < best) { best = score; bn = cand[i]; splitk = sk; }
     }
   }
   const int nt = cdiv(d->n, bn);
   const long long tiles_ll = (long long)mt * nt * nb1 * nb2;
-  TS_REQUIRE(ctx, tiles_ll < (1ll << 30), TS_ESHAPE, "gemm_tc: too many tiles");
-  // split-K only where partial sums may be added: fp32 "C += A*B" with a plain epilogue
-  int splitk = 1;
-  if (d->out_dtype == TS_F32 && d->accumulate && !d->bias && !d->c_preact && d->drop <= 0.f && tiles_ll * 2 <= sms && nkb >= 16) {
-    int want = (int)(sms / tiles_ll);
-    const int cap = nkb / 8;
-    splitk = want < cap ? want : cap;
-    if (splitk < 1) splitk = 1;
-  }
+  TS_REQUIRE(ctx, tiles_ll * splitk < (1ll << 30), TS_ESHAPE, "gemm_tc: too many tiles");
   const int kbps = cdiv(nkb, splitk);
-  splitk = cdiv(nkb, kbps);
 
   CUtensorMap ta, tb;
   {

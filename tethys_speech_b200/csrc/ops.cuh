@@ -70,6 +70,11 @@ int softmax_fwd(Ctx*, int dt, void* s, long long ld, int nbatch, int Tq, int Tk,
 int softmax_bwd(Ctx*, int dt, const void* p, void* dp, long long ld, int nbatch, int Tq, int Tk, float scale,
                 float drop, uint64_t seed, cudaStream_t);
 
+// ---- attention_tc.cu: fused tcgen05 attention (bf16, head_dim 64) ----------------------------------
+bool attn_tc_supported(const ts_attn_desc* d);
+int attn_fwd(Ctx*, const ts_attn_desc* d, cudaStream_t);
+int attn_bwd(Ctx*, const ts_attn_desc* d, cudaStream_t);
+
 // ---- vq.cu / contrastive.cu ----------------------------------------------------------------------
 // hard VQ (V:604-660): z [M, G*D] (act dtype), codebook fp32 [G,V,D]; writes q [M, G*D], idx int64 [G,M],
 // hist int32 [G,V] (+=), then perplexity (fp32 scalar) via vq_perplexity.

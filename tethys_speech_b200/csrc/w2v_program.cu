@@ -3,6 +3,7 @@
 // kernel library. All GEMM-shaped work (strided convs as window-GEMMs without im2col, the grouped positional
 // conv as per-group window-GEMMs, Dense layers, attention products, the all-pairs contrastive similarities)
 // goes through ts::gemm (tcgen05 in bf16 mode, fp32 CUDA cores in parity mode).
+#include <stdlib.h>
 #include "program.cuh"
 
 namespace ts {
@@ -17,6 +18,7 @@ struct W2V {
   Ctx* ctx = nullptr;
   ts_w2v_config cfg;
   int prec = TS_F32, esz = 4;
+  bool fused_attn = false;  // bf16 + head_dim 64: tcgen05 flash kernels instead of GEMM/softmax/GEMM
   ParamTable pt;
   // parameter offsets
   long long conv_w[8], conv_g[8], conv_b[8];
@@ -178,7 +180,7 @@ static int plan(W2V* m, int B, int N, Bump& bp) {
     if (l == 0) b.h_in = m->hs;
     b.x1 = bp.get(m->E((long long)M * H));
     b.qkv = bp.get(m->E((long long)M * 3 * H));
-    b.P = bp.get(m->E((long long)B * nh * T * Tp));
+    b.P = m->fused_attn ? bp.get(8ll * B * nh * T) : bp.get(m->E((long long)B * nh * T * Tp));   // fused: [B,nh,T,2] row statistics only
     b.ctx = bp.get(m->E((long long)M * H));
     b.h_mid = bp.get(m->E((long long)M * H));
     b.x2 = bp.get(m->E((long long)M * H));
@@ -205,8 +207,8 @@ static int plan(W2V* m, int B, int N, Bump& bp) {
   m->g_f = bp.get(m->E((long long)M * F));
   m->g_ctx = bp.get(m->E((long long)M * H));
   m->g_qkv = bp.get(m->E((long long)M * 3 * H));
-  m->g_P = bp.get(m->E((long long)B * nh * T * Tp));
-  m->g_Pd = bp.get(m->E((long long)B * nh * T * Tp));
+  if (m->fused_attn) { m->g_P = bp.get(4ll * B * nh * T); m->g_Pd = nullptr; }   // fused: D = rowsum(dO o O) scratch
+  else { m->g_P = bp.get(m->E((long long)B * nh * T * Tp)); m->g_Pd = bp.get(m->E((long long)B * nh * T * Tp)); }
   m->g_small1 = bp.get(m->E((long long)M * std::max(Pj, D)));
   m->g_small2 = bp.get(m->E((long long)M * std::max(Pj, D)));
   m->g_dyg = bp.get(m->E((long long)G * B * Rp * cpg + (long long)K * cpg));
@@ -289,16 +291,26 @@ static int w2v_forward(W2V* m, const float* wave, const int* neg, long long neg_
     TS_TRY(layernorm_fwd(ctx, dt, b.h_in, nullptr, m->P + o.ln1_g, m->P + o.ln1_b, b.x1, nullptr, b.ln1_mean, b.ln1_rstd, M, H, c.ln_eps, st));
     TS_TRY(GemmB(dt, dt).A(b.x1, 0, H).B(m->W(o.qkv_w), 1, 3 * H).C(b.qkv, 3 * H).bias(m->P + o.qkv_b).mnk(M, 3 * H, H).run(ctx, st));
     const char* qkv = (const char*)b.qkv;
-    // scores = q k^T (scaled by 1/sqrt(hd) inside the softmax, V:349)
-    TS_TRY(GemmB(dt, dt).A(qkv, 0, 3 * H).astride(hd, (long long)T * 3 * H)
-               .B(qkv + m->E(H), 0, 3 * H).bstride(hd, (long long)T * 3 * H)
-               .C(b.P, Tp).cstride((long long)T * Tp, (long long)nh * T * Tp).mnk(T, T, hd).batch(nh, B).run(ctx, st));
     const float adrop = m->drop(c.attention_dropout);
-    TS_TRY(softmax_fwd(ctx, dt, b.P, Tp, B * nh, T, T, 1.f / sqrtf((float)hd), 0, adrop, site_seed(seed, 100 + l * 8), m->g_Pd, st));
-    const void* Puse = adrop > 0 ? m->g_Pd : b.P;
-    TS_TRY(GemmB(dt, dt).A(Puse, 0, Tp).astride((long long)T * Tp, (long long)nh * T * Tp)
-               .B(qkv + m->E(2 * H), 1, 3 * H).bstride(hd, (long long)T * 3 * H)
-               .C(b.ctx, H).cstride(hd, (long long)T * H).mnk(T, hd, T).batch(nh, B).run(ctx, st));
+    if (m->fused_attn) {
+      ts_attn_desc a;
+      memset(&a, 0, sizeof(a));
+      a.q = qkv; a.k = qkv + m->E(H); a.v = qkv + m->E(2 * H); a.o = b.ctx;
+      a.q_ld = a.kv_ld = 3 * H; a.q_bs = a.kv_bs = (long long)T * 3 * H; a.o_ld = H; a.o_bs = (long long)T * H;
+      a.stats = (float*)b.P; a.batch = B; a.heads = nh; a.tq = a.tk = T; a.head_dim = hd;
+      a.scale = 1.f / sqrtf((float)hd); a.mask_mode = 0; a.drop = adrop; a.seed = site_seed(seed, 100 + l * 8);
+      TS_TRY(attn_fwd(ctx, &a, st));
+    } else {
+      // scores = q k^T (scaled by 1/sqrt(hd) inside the softmax, V:349)
+      TS_TRY(GemmB(dt, dt).A(qkv, 0, 3 * H).astride(hd, (long long)T * 3 * H)
+                 .B(qkv + m->E(H), 0, 3 * H).bstride(hd, (long long)T * 3 * H)
+                 .C(b.P, Tp).cstride((long long)T * Tp, (long long)nh * T * Tp).mnk(T, T, hd).batch(nh, B).run(ctx, st));
+      TS_TRY(softmax_fwd(ctx, dt, b.P, Tp, B * nh, T, T, 1.f / sqrtf((float)hd), 0, adrop, site_seed(seed, 100 + l * 8), m->g_Pd, st));
+      const void* Puse = adrop > 0 ? m->g_Pd : b.P;
+      TS_TRY(GemmB(dt, dt).A(Puse, 0, Tp).astride((long long)T * Tp, (long long)nh * T * Tp)
+                 .B(qkv + m->E(2 * H), 1, 3 * H).bstride(hd, (long long)T * 3 * H)
+                 .C(b.ctx, H).cstride(hd, (long long)T * H).mnk(T, hd, T).batch(nh, B).run(ctx, st));
+    }
     TS_TRY(GemmB(dt, dt).A(b.ctx, 0, H).B(m->W(o.o_w), 1, H).C(b.h_mid, H).bias(m->P + o.o_b).res(b.h_in, H)
                .drop(m->drop(c.hidden_dropout), site_seed(seed, 101 + l * 8)).mnk(M, H, H).run(ctx, st));
     TS_TRY(layernorm_fwd(ctx, dt, b.h_mid, nullptr, m->P + o.ln2_g, m->P + o.ln2_b, b.x2, nullptr, b.ln2_mean, b.ln2_rstd, M, H, c.ln_eps, st));
@@ -395,23 +407,35 @@ static int w2v_backward_stage(W2V* m, int stage, cudaStream_t st) {
     // attention core
     const float adrop = m->drop(c.attention_dropout);
     const uint64_t aseed = site_seed(seed, 100 + l * 8);
-    const void* Puse = b.P;
-    if (adrop > 0) { TS_TRY(dropout_apply(ctx, dt, b.P, m->g_Pd, (long long)B * nh * T * Tp, adrop, aseed, st)); Puse = m->g_Pd; }
     const char* qkv = (const char*)b.qkv;
     char* dqkv = (char*)m->g_qkv;
-    const long long sP1 = (long long)T * Tp, sP2 = (long long)nh * T * Tp, sQ2 = (long long)T * 3 * H, sC2 = (long long)T * H;
-    // dV = Pd^T dctx
-    TS_TRY(GemmB(dt, dt).A(Puse, 1, Tp).astride(sP1, sP2).B(m->g_ctx, 1, H).bstride(hd, sC2)
-               .C(dqkv + m->E(2 * H), 3 * H).cstride(hd, sQ2).mnk(T, hd, T).batch(nh, B).run(ctx, st));
-    // dPd = dctx V^T
-    TS_TRY(GemmB(dt, dt).A(m->g_ctx, 0, H).astride(hd, sC2).B(qkv + m->E(2 * H), 0, 3 * H).bstride(hd, sQ2)
-               .C(m->g_P, Tp).cstride(sP1, sP2).mnk(T, T, hd).batch(nh, B).run(ctx, st));
-    TS_TRY(softmax_bwd(ctx, dt, b.P, m->g_P, Tp, B * nh, T, T, 1.f / sqrtf((float)hd), adrop, aseed, st));
-    // dQ = dS K ; dK = dS^T Q
-    TS_TRY(GemmB(dt, dt).A(m->g_P, 0, Tp).astride(sP1, sP2).B(qkv + m->E(H), 1, 3 * H).bstride(hd, sQ2)
-               .C(dqkv, 3 * H).cstride(hd, sQ2).mnk(T, hd, T).batch(nh, B).run(ctx, st));
-    TS_TRY(GemmB(dt, dt).A(m->g_P, 1, Tp).astride(sP1, sP2).B(qkv, 1, 3 * H).bstride(hd, sQ2)
-               .C(dqkv + m->E(H), 3 * H).cstride(hd, sQ2).mnk(T, hd, T).batch(nh, B).run(ctx, st));
+    if (m->fused_attn) {
+      ts_attn_desc a;
+      memset(&a, 0, sizeof(a));
+      a.q = qkv; a.k = qkv + m->E(H); a.v = qkv + m->E(2 * H); a.o = b.ctx;
+      a.q_ld = a.kv_ld = 3 * H; a.q_bs = a.kv_bs = (long long)T * 3 * H; a.o_ld = H; a.o_bs = (long long)T * H;
+      a.stats = (float*)b.P; a.batch = B; a.heads = nh; a.tq = a.tk = T; a.head_dim = hd;
+      a.scale = 1.f / sqrtf((float)hd); a.mask_mode = 0; a.drop = adrop; a.seed = aseed;
+      a.d_o = m->g_ctx; a.dq = dqkv; a.dk = dqkv + m->E(H); a.dv = dqkv + m->E(2 * H);
+      a.dq_ld = a.dkv_ld = 3 * H; a.dq_bs = a.dkv_bs = (long long)T * 3 * H; a.dsum = (float*)m->g_P;
+      TS_TRY(attn_bwd(ctx, &a, st));
+    } else {
+      const void* Puse = b.P;
+      if (adrop > 0) { TS_TRY(dropout_apply(ctx, dt, b.P, m->g_Pd, (long long)B * nh * T * Tp, adrop, aseed, st)); Puse = m->g_Pd; }
+      const long long sP1 = (long long)T * Tp, sP2 = (long long)nh * T * Tp, sQ2 = (long long)T * 3 * H, sC2 = (long long)T * H;
+      // dV = Pd^T dctx
+      TS_TRY(GemmB(dt, dt).A(Puse, 1, Tp).astride(sP1, sP2).B(m->g_ctx, 1, H).bstride(hd, sC2)
+                 .C(dqkv + m->E(2 * H), 3 * H).cstride(hd, sQ2).mnk(T, hd, T).batch(nh, B).run(ctx, st));
+      // dPd = dctx V^T
+      TS_TRY(GemmB(dt, dt).A(m->g_ctx, 0, H).astride(hd, sC2).B(qkv + m->E(2 * H), 0, 3 * H).bstride(hd, sQ2)
+                 .C(m->g_P, Tp).cstride(sP1, sP2).mnk(T, T, hd).batch(nh, B).run(ctx, st));
+      TS_TRY(softmax_bwd(ctx, dt, b.P, m->g_P, Tp, B * nh, T, T, 1.f / sqrtf((float)hd), adrop, aseed, st));
+      // dQ = dS K ; dK = dS^T Q
+      TS_TRY(GemmB(dt, dt).A(m->g_P, 0, Tp).astride(sP1, sP2).B(qkv + m->E(H), 1, 3 * H).bstride(hd, sQ2)
+                 .C(dqkv, 3 * H).cstride(hd, sQ2).mnk(T, hd, T).batch(nh, B).run(ctx, st));
+      TS_TRY(GemmB(dt, dt).A(m->g_P, 1, Tp).astride(sP1, sP2).B(qkv, 1, 3 * H).bstride(hd, sQ2)
+                 .C(dqkv + m->E(H), 3 * H).cstride(hd, sQ2).mnk(T, hd, T).batch(nh, B).run(ctx, st));
+    }
     // qkv projection
     TS_TRY(dense_bwd(m, b.x1, H, dqkv, 3 * H, o.qkv_w, 3 * H, o.qkv_b, m->g_x, nullptr, M, st));
     // LN1: dh_in = dh_mid + LNbwd(dx1)
@@ -483,6 +507,7 @@ int ts_w2v_create(ts_ctx* ctx_, const ts_w2v_config* cfg, int precision, ts_w2v*
   TS_REQUIRE(ctx, cfg->n_conv >= 2 && cfg->n_conv <= 8 && cfg->layers <= 64, TS_EINVAL, "w2v: bad config");
   W2V* m = new W2V();
   m->ctx = ctx; m->cfg = *cfg; m->prec = precision; m->esz = precision == TS_BF16 ? 2 : 4;
+  m->fused_attn = precision == TS_BF16 && cfg->heads > 0 && cfg->hidden / cfg->heads == 64 && !getenv("TETHYS_UNFUSED_ATTENTION");
   build_params(m);
   *out = reinterpret_cast<ts_w2v*>(m);
   return 0;

@@ -4,6 +4,7 @@
 // Bug-compatible with the reference: anti-causal decoder mask with fp32 -1e9 absorption, double label
 // shift, untied lm_head, query scaling folded into the score scale (mathematically (Wq x + b) * hd^-0.5).
 #include <math.h>
+#include <stdlib.h>
 #include "program.cuh"
 
 namespace ts {
@@ -22,6 +23,7 @@ struct Whisper {
   Ctx* ctx = nullptr;
   ts_whisper_config cfg;
   int prec = TS_F32, esz = 4;
+  bool fused_attn = false;  // bf16 + head_dim 64: tcgen05 flash kernels instead of GEMM/softmax/GEMM
   ParamTable pt;
   long long conv1_w, conv1_b, conv2_w, conv2_b, enc_ln_g, enc_ln_b, emb, dec_ln_g, dec_ln_b, lm_w;
   long long Vp = 0;  // padded lm_head row stride
@@ -147,7 +149,7 @@ static int plan(Whisper* m, int B, int Tm, int S, Bump& bp) {
     EncLayerBuf& b = m->EB[l];
     b.h_in = h;
     b.x1 = bp.get(m->E(Me * d)); b.qkv = bp.get(m->E(Me * 3 * d));
-    b.P = bp.get(m->E((long long)B * nh * T * Tp));
+    b.P = m->fused_attn ? bp.get(8ll * B * nh * T) : bp.get(m->E((long long)B * nh * T * Tp));   // fused: row statistics only
     b.ctx = bp.get(m->E(Me * d)); b.h_mid = bp.get(m->E(Me * d)); b.x2 = bp.get(m->E(Me * d));
     b.u = bp.get(m->E(Me * F)); b.f = bp.get(m->E(Me * F));
     b.m1 = (float*)bp.get(4 * Me); b.r1 = (float*)bp.get(4 * Me); b.m2 = (float*)bp.get(4 * Me); b.r2 = (float*)bp.get(4 * Me);
@@ -161,9 +163,9 @@ static int plan(Whisper* m, int B, int Tm, int S, Bump& bp) {
   for (int l = 0; l < c.dec_layers; ++l) {
     DecLayerBuf& b = m->DB[l];
     b.g_in = g;
-    b.x1 = bp.get(m->E(Md * d)); b.qkv = bp.get(m->E(Md * 3 * d)); b.P = bp.get(m->E((long long)B * nh * S * Sp));
+    b.x1 = bp.get(m->E(Md * d)); b.qkv = bp.get(m->E(Md * 3 * d)); b.P = m->fused_attn ? bp.get(8ll * B * nh * S) : bp.get(m->E((long long)B * nh * S * Sp));
     b.ctx = bp.get(m->E(Md * d)); b.g1 = bp.get(m->E(Md * d)); b.x2 = bp.get(m->E(Md * d)); b.q = bp.get(m->E(Md * d));
-    b.kv = bp.get(m->E(Me * 2 * d)); b.Pc = bp.get(m->E((long long)B * nh * S * Tp)); b.ctxc = bp.get(m->E(Md * d));
+    b.kv = bp.get(m->E(Me * 2 * d)); b.Pc = m->fused_attn ? bp.get(8ll * B * nh * S) : bp.get(m->E((long long)B * nh * S * Tp)); b.ctxc = bp.get(m->E(Md * d));
     b.g2 = bp.get(m->E(Md * d)); b.x3 = bp.get(m->E(Md * d)); b.u = bp.get(m->E(Md * F)); b.f = bp.get(m->E(Md * F));
     b.m1 = (float*)bp.get(4 * Md); b.r1 = (float*)bp.get(4 * Md); b.m2 = (float*)bp.get(4 * Md); b.r2 = (float*)bp.get(4 * Md);
     b.m3 = (float*)bp.get(4 * Md); b.r3 = (float*)bp.get(4 * Md);
@@ -179,7 +181,8 @@ static int plan(Whisper* m, int B, int Tm, int S, Bump& bp) {
   m->s_a = bp.get(m->E(Mx * d)); m->s_b = bp.get(m->E(Mx * d)); m->s_t = bp.get(m->E(Mx * d)); m->s_x = bp.get(m->E(Mx * d));
   m->s_f = bp.get(m->E(Mx * F)); m->s_ctx = bp.get(m->E(Mx * d)); m->s_qkv = bp.get(m->E(Mx * 3 * d));
   const long long pmax = std::max((long long)B * nh * T * Tp, std::max((long long)B * nh * S * Tp, (long long)B * nh * S * Sp));
-  m->s_P = bp.get(m->E(pmax)); m->s_Pd = bp.get(m->E(pmax));
+  if (m->fused_attn) { m->s_P = bp.get(4ll * B * nh * std::max(T, S)); m->s_Pd = nullptr; }   // fused: D = rowsum(dO o O) scratch
+  else { m->s_P = bp.get(m->E(pmax)); m->s_Pd = bp.get(m->E(pmax)); }
   m->s_denc = bp.get(m->E(Me * d)); m->s_dq = bp.get(m->E(Md * d)); m->s_dkv = bp.get(m->E(Me * 2 * d));
   m->s_dcol = bp.get(m->E((long long)B * m->Rq2 * 3 * d));
   m->s_du = bp.get(m->E((long long)B * m->Rq1 * d));
@@ -193,6 +196,15 @@ static int attn_forward(Whisper* m, const void* q, long long ldq, const void* k,
                         long long ldc, AttnShape s, float scale, int mask, float drop, uint64_t seed, cudaStream_t st) {
   Ctx* ctx = m->ctx;
   const int dt = m->prec;
+  if (m->fused_attn) {  // tcgen05 flash kernel: P is only the [B, nh, Tq, 2] row-statistics buffer
+    ts_attn_desc a;
+    memset(&a, 0, sizeof(a));
+    a.q = q; a.k = k; a.v = v; a.o = ctxo;
+    a.q_ld = ldq; a.q_bs = (long long)s.Tq * ldq; a.kv_ld = ldkv; a.kv_bs = (long long)s.Tk * ldkv; a.o_ld = ldc; a.o_bs = (long long)s.Tq * ldc;
+    a.stats = (float*)P; a.batch = s.B; a.heads = s.nh; a.tq = s.Tq; a.tk = s.Tk; a.head_dim = s.hd;
+    a.scale = scale; a.mask_mode = mask; a.drop = drop; a.seed = seed;
+    return attn_fwd(ctx, &a, st);
+  }
   const long long sP1 = (long long)s.Tq * s.Tkp, sP2 = (long long)s.nh * s.Tq * s.Tkp;
   TS_TRY(GemmB(dt, dt).A(q, 0, ldq).astride(s.hd, (long long)s.Tq * ldq).B(k, 0, ldkv).bstride(s.hd, (long long)s.Tk * ldkv)
              .C(P, s.Tkp).cstride(sP1, sP2).mnk(s.Tq, s.Tk, s.hd).batch(s.nh, s.B).run(ctx, st));
@@ -205,9 +217,20 @@ static int attn_forward(Whisper* m, const void* q, long long ldq, const void* k,
 
 static int attn_backward(Whisper* m, const void* q, long long ldq, const void* k, const void* v, long long ldkv, const void* P,
                          const void* dctx, long long ldc, void* dq, long long lddq, void* dk, void* dv, long long lddkv, AttnShape s,
-                         float scale, float drop, uint64_t seed, cudaStream_t st) {
+                         float scale, float drop, uint64_t seed, cudaStream_t st, const void* ctx_out = nullptr, int mask = 0) {
   Ctx* ctx = m->ctx;
   const int dt = m->prec;
+  if (m->fused_attn) {
+    ts_attn_desc a;
+    memset(&a, 0, sizeof(a));
+    a.q = q; a.k = k; a.v = v; a.o = const_cast<void*>(ctx_out);
+    a.q_ld = ldq; a.q_bs = (long long)s.Tq * ldq; a.kv_ld = ldkv; a.kv_bs = (long long)s.Tk * ldkv; a.o_ld = ldc; a.o_bs = (long long)s.Tq * ldc;
+    a.stats = (float*)const_cast<void*>(P); a.batch = s.B; a.heads = s.nh; a.tq = s.Tq; a.tk = s.Tk; a.head_dim = s.hd;
+    a.scale = scale; a.mask_mode = mask; a.drop = drop; a.seed = seed;
+    a.d_o = dctx; a.dq = dq; a.dk = dk; a.dv = dv; a.dq_ld = lddq; a.dq_bs = (long long)s.Tq * lddq; a.dkv_ld = lddkv; a.dkv_bs = (long long)s.Tk * lddkv;
+    a.dsum = (float*)m->s_P;
+    return attn_bwd(ctx, &a, st);
+  }
   const long long sP1 = (long long)s.Tq * s.Tkp, sP2 = (long long)s.nh * s.Tq * s.Tkp;
   const void* Puse = P;
   if (drop > 0) { TS_TRY(dropout_apply(ctx, dt, P, m->s_Pd, (long long)s.B * s.nh * s.Tq * s.Tkp, drop, seed, st)); Puse = m->s_Pd; }
@@ -392,7 +415,7 @@ static int whisper_backward_stage(Whisper* m, int stage, cudaStream_t st) {
     const char* kv = (const char*)b.kv;
     char* dkv = (char*)m->s_dkv;
     TS_TRY(attn_backward(m, b.q, d, kv, kv + m->E(d), 2 * d, b.Pc, m->s_ctx, d, m->s_dq, d, dkv, dkv + m->E(d), 2 * d, {B, nh, hd, S, T, Tp},
-                         scale, m->drop(c.attention_dropout), site_seed(seed, 1001 + l * 8), st));
+                         scale, m->drop(c.attention_dropout), site_seed(seed, 1001 + l * 8), st, b.ctxc, 0));
     TS_TRY(dense_bwd(m, b.x2, d, m->s_dq, d, o.ca.q_w, d, o.ca.q_b, m->s_x, nullptr, Md, st));
     TS_TRY(dense_bwd(m, m->enc_out, d, dkv, 2 * d, o.ca.kv_w, 2 * d, o.ca.kv_b, m->s_denc, m->s_denc, Me, st));  // d_enc += dkv Wkv^T
     void* dg1 = m->s_a;
@@ -402,7 +425,7 @@ static int whisper_backward_stage(Whisper* m, int stage, cudaStream_t st) {
     const char* qkv = (const char*)b.qkv;
     char* dqkv = (char*)m->s_qkv;
     TS_TRY(attn_backward(m, qkv, 3 * d, qkv + m->E(d), qkv + m->E(2 * d), 3 * d, b.P, m->s_ctx, d, dqkv, 3 * d, dqkv + m->E(d), dqkv + m->E(2 * d), 3 * d,
-                         {B, nh, hd, S, S, Sp}, scale, m->drop(c.attention_dropout), site_seed(seed, 1000 + l * 8), st));
+                         {B, nh, hd, S, S, Sp}, scale, m->drop(c.attention_dropout), site_seed(seed, 1000 + l * 8), st, b.ctx, 1));
     TS_TRY(dense_bwd(m, b.x1, d, dqkv, 3 * d, o.sa.qkv_w, 3 * d, o.sa.qkv_b, m->s_x, nullptr, Md, st));
     // in place over dg1: every thread reads its own dres elements before it writes dx
     TS_TRY(layernorm_bwd(ctx, dt, m->s_x, b.g_in, m->P + o.ln1_g, b.m1, b.r1, dg1, m->s_a, m->G + o.ln1_g, m->G + o.ln1_b, (int)Md, d, st));
@@ -427,7 +450,7 @@ static int whisper_backward_stage(Whisper* m, int stage, cudaStream_t st) {
     const char* qkv = (const char*)b.qkv;
     char* dqkv = (char*)m->s_qkv;
     TS_TRY(attn_backward(m, qkv, 3 * d, qkv + m->E(d), qkv + m->E(2 * d), 3 * d, b.P, m->s_ctx, d, dqkv, 3 * d, dqkv + m->E(d), dqkv + m->E(2 * d), 3 * d,
-                         {B, nh, hd, T, T, Tp}, scale, m->drop(c.attention_dropout), site_seed(seed, 100 + l * 8), st));
+                         {B, nh, hd, T, T, Tp}, scale, m->drop(c.attention_dropout), site_seed(seed, 100 + l * 8), st, b.ctx, 0));
     TS_TRY(dense_bwd(m, b.x1, d, dqkv, 3 * d, o.sa.qkv_w, 3 * d, o.sa.qkv_b, m->s_x, nullptr, Me, st));
     TS_TRY(layernorm_bwd(ctx, dt, m->s_x, b.h_in, m->P + o.ln1_g, b.m1, b.r1, dh_mid, m->s_a, m->G + o.ln1_g, m->G + o.ln1_b, (int)Me, d, st));
     return 0;
@@ -461,6 +484,7 @@ int ts_whisper_create(ts_ctx* ctx_, const ts_whisper_config* cfg, int precision,
   TS_REQUIRE(ctx, precision == TS_F32 || precision == TS_BF16, TS_EDTYPE, "whisper: precision must be TS_F32 or TS_BF16");
   Whisper* m = new Whisper();
   m->ctx = ctx; m->cfg = *cfg; m->prec = precision; m->esz = precision == TS_BF16 ? 2 : 4;
+  m->fused_attn = precision == TS_BF16 && cfg->heads > 0 && cfg->d_model / cfg->heads == 64 && !getenv("TETHYS_UNFUSED_ATTENTION");
   build_params(m);
   // PositionalEncoding tables (W:55-64): float64 math, interleaved sin/cos, cast to fp32
   const int d = cfg->d_model;
@@ -568,7 +592,14 @@ int ts_whisper_get_buffer(ts_whisper* h, const char* name, void** ptr, int32_t* 
   if (s == "encoder_last_hidden_state") return set(m->enc_out, m->prec, 3, B, m->T, d, 1);
   if (s == "last_hidden_state") return set(m->dec_out, m->prec, 3, B, m->S, d, 1);
   if (s == "logits") return set(m->logits, m->prec, 3, B, m->S, m->Vp, 1);   // padded last dim; valid columns [0, vocab)
-  if (s == "decoder_self_attn_probs0") return set(m->DB[0].P, m->prec, 4, B, m->cfg.heads, m->S, m->Sp);
+  if (s == "decoder_self_attn_probs0") {
+    if (m->fused_attn) return set_err(m->ctx, TS_EUNSUPPORTED, "probabilities are not materialised by the fused attention kernels; read decoder_self_attn_stats0");
+    return set(m->DB[0].P, m->prec, 4, B, m->cfg.heads, m->S, m->Sp);
+  }
+  if (s == "decoder_self_attn_stats0") {  // [B, heads, S, 2] = (row max, log row-sum) of the fused kernel
+    if (!m->fused_attn) return set_err(m->ctx, TS_EUNSUPPORTED, "row statistics exist only with the fused attention kernels");
+    return set(m->DB[0].P, TS_F32, 4, B, m->cfg.heads, m->S, 2);
+  }
   return set_err(m->ctx, TS_EINVAL, "whisper_get_buffer: unknown buffer '%s'", name);
 }
 

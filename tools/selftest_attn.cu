@@ -1,0 +1,213 @@
+// Standalone GPU self-test of the fused tcgen05 attention kernels (ts_attn_fwd / ts_attn_bwd): compares O, dQ, dK, dV
+// against a double-precision CPU reference on bf16-rounded inputs — self/cross attention, ragged tiles, the reference's
+// "anti-causal" -1e9 decoder mask (fully masked last row -> uniform) and dropout (the CPU side regenerates the same
+// keep-mask from the documented hash) — and times the Wav2Vec2-base / Whisper shapes.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../include/tethys.h"
+
+static uint32_t rng_state = 777;
+static float frand() {
+  rng_state = rng_state * 1664525u + 1013904223u;
+  return ((rng_state >> 8) & 0xFFFF) / 65536.0f - 0.5f;
+}
+static float bfr(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
+
+// host copy of common.cuh: dropout_word / dropout_scale
+static uint32_t dropout_word(uint64_t seed, uint64_t idx) {
+  uint32_t x = (uint32_t)(idx >> 1) ^ (uint32_t)seed;
+  const uint32_t k2 = (uint32_t)(seed >> 32) ^ ((uint32_t)(idx >> 33) * 0x85EBCA6Bu);
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x += k2; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+static float dropout_scale(uint64_t seed, uint64_t idx, uint32_t thr, float inv_keep) {
+  const uint32_t w = dropout_word(seed, idx);
+  const uint32_t r = (idx & 1) ? (w >> 16) : (w & 0xffffu);
+  return (r >= (thr >> 16)) ? inv_keep : 0.f;
+}
+
+struct Case { const char* name; int B, nh, Tq, Tk, mask; float drop; bool cross; };
+
+static std::vector<__nv_bfloat16> to_bf16(const std::vector<float>& v) {
+  std::vector<__nv_bfloat16> o(v.size());
+  for (size_t i = 0; i < v.size(); ++i) o[i] = __float2bfloat16_rn(v[i]);
+  return o;
+}
+
+static int run_case(ts_ctx* ctx, const Case& cs, bool timing) {
+  const int B = cs.B, nh = cs.nh, Tq = cs.Tq, Tk = cs.Tk, H = nh * 64;
+  // self: one fused [B, T, 3H] buffer (q | k | v); cross: q [B, Tq, H] and kv [B, Tk, 2H]
+  const long long q_ld = cs.cross ? H : 3 * H, kv_ld = cs.cross ? 2 * H : 3 * H;
+  const long long q_bs = (long long)Tq * q_ld, kv_bs = (long long)Tk * kv_ld;
+  std::vector<float> hq((size_t)B * q_bs), hkv(cs.cross ? (size_t)B * kv_bs : 0), hdo((size_t)B * Tq * H);
+  for (auto& v : hq) v = bfr(frand() * 2.f);
+  for (auto& v : hkv) v = bfr(frand() * 2.f);
+  for (auto& v : hdo) v = bfr(frand());
+  const float* Q = hq.data();
+  const float* K = cs.cross ? hkv.data() : hq.data() + H;
+  const float* V = cs.cross ? hkv.data() + H : hq.data() + 2 * H;
+  __nv_bfloat16 *dq_in, *dkv_in = nullptr, *d_o, *d_do, *g_q, *g_kv = nullptr;
+  float *d_stats, *d_dsum;
+  auto q16 = to_bf16(hq), kv16 = to_bf16(hkv), do16 = to_bf16(hdo);
+  cudaMalloc(&dq_in, q16.size() * 2); cudaMemcpy(dq_in, q16.data(), q16.size() * 2, cudaMemcpyHostToDevice);
+  cudaMalloc(&g_q, q16.size() * 2); cudaMemset(g_q, 0, q16.size() * 2);
+  if (cs.cross) {
+    cudaMalloc(&dkv_in, kv16.size() * 2); cudaMemcpy(dkv_in, kv16.data(), kv16.size() * 2, cudaMemcpyHostToDevice);
+    cudaMalloc(&g_kv, kv16.size() * 2); cudaMemset(g_kv, 0, kv16.size() * 2);
+  }
+  cudaMalloc(&d_o, (size_t)B * Tq * H * 2); cudaMemset(d_o, 0, (size_t)B * Tq * H * 2);
+  cudaMalloc(&d_do, do16.size() * 2); cudaMemcpy(d_do, do16.data(), do16.size() * 2, cudaMemcpyHostToDevice);
+  cudaMalloc(&d_stats, (size_t)B * nh * Tq * 2 * 4); cudaMalloc(&d_dsum, (size_t)B * nh * Tq * 4);
+  ts_attn_desc d;
+  memset(&d, 0, sizeof(d));
+  d.q = dq_in; d.k = cs.cross ? dkv_in : dq_in + H; d.v = cs.cross ? dkv_in + H : dq_in + 2 * H;
+  d.o = d_o; d.q_ld = q_ld; d.q_bs = q_bs; d.kv_ld = kv_ld; d.kv_bs = kv_bs; d.o_ld = H; d.o_bs = (long long)Tq * H;
+  d.stats = d_stats; d.batch = B; d.heads = nh; d.tq = Tq; d.tk = Tk; d.head_dim = 64; d.scale = 0.125f; d.mask_mode = cs.mask;
+  d.drop = cs.drop; d.seed = 0x1234567887654321ull;
+  d.d_o = d_do; d.dq = g_q; d.dq_ld = q_ld; d.dq_bs = q_bs;
+  d.dk = cs.cross ? g_kv : g_q + H; d.dv = cs.cross ? g_kv + H : g_q + 2 * H; d.dkv_ld = kv_ld; d.dkv_bs = kv_bs; d.dsum = d_dsum;
+  int rc = ts_attn_fwd(ctx, &d, 0);
+  if (rc) { printf("  [%s] fwd rc=%d %s\n", cs.name, rc, ts_last_error(ctx)); return 1; }
+  rc = ts_attn_bwd(ctx, &d, 0);
+  if (rc) { printf("  [%s] bwd rc=%d %s\n", cs.name, rc, ts_last_error(ctx)); return 1; }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("  [%s] CUDA error %s\n", cs.name, cudaGetErrorString(e)); return 2; }
+  rc = ts_watchdog_check(ctx);
+  if (rc) { printf("  [%s] watchdog: %s\n", cs.name, ts_last_error(ctx)); return 3; }
+  int bad = 0;
+  if (!timing) {
+    std::vector<__nv_bfloat16> ho((size_t)B * Tq * H), hgq(q16.size()), hgkv(kv16.size());
+    cudaMemcpy(ho.data(), d_o, ho.size() * 2, cudaMemcpyDeviceToHost);
+    cudaMemcpy(hgq.data(), g_q, hgq.size() * 2, cudaMemcpyDeviceToHost);
+    if (cs.cross) cudaMemcpy(hgkv.data(), g_kv, hgkv.size() * 2, cudaMemcpyDeviceToHost);
+    const __nv_bfloat16* GQ = hgq.data();
+    const __nv_bfloat16* GK = cs.cross ? hgkv.data() : hgq.data() + H;
+    const __nv_bfloat16* GV = cs.cross ? hgkv.data() + H : hgq.data() + 2 * H;
+    uint32_t thr = 0; float ik = 1.f;
+    if (cs.drop > 0) { thr = (uint32_t)((double)cs.drop * 4294967296.0); ik = 1.f / (1.f - cs.drop); }
+    const long long pitch = ((long long)Tk + 1) & ~1ll;
+    double eo = 0, edq = 0, edk = 0, edv = 0, mo = 0, mdq = 0, mdk = 0, mdv = 0;
+    std::vector<double> P((size_t)Tq * Tk), Z((size_t)Tq * Tk), dS((size_t)Tq * Tk), rdk((size_t)Tk * 64), rdv((size_t)Tk * 64);
+    for (int b = 0; b < B; ++b)
+      for (int h = 0; h < nh; ++h) {
+        const float* q = Q + b * q_bs + h * 64;
+        const float* k = K + b * kv_bs + h * 64;
+        const float* v = V + b * kv_bs + h * 64;
+        const float* go = hdo.data() + (long long)b * Tq * H + h * 64;
+        std::fill(rdk.begin(), rdk.end(), 0.0); std::fill(rdv.begin(), rdv.end(), 0.0);
+        for (int i = 0; i < Tq; ++i) {
+          std::vector<float> s(Tk);
+          float mx = -INFINITY;
+          for (int j = 0; j < Tk; ++j) {
+            double acc = 0;
+            for (int c = 0; c < 64; ++c) acc += (double)q[i * q_ld + c] * k[j * kv_ld + c];
+            float sv = (float)acc * d.scale;
+            if (cs.mask == 1 && j <= i) sv = sv + (-1e9f);
+            s[j] = sv; mx = fmaxf(mx, sv);
+          }
+          double l = 0;
+          for (int j = 0; j < Tk; ++j) { P[(size_t)i * Tk + j] = exp((double)(s[j] - mx)); l += P[(size_t)i * Tk + j]; }
+          double o[64] = {0};
+          for (int j = 0; j < Tk; ++j) {
+            P[(size_t)i * Tk + j] /= l;
+            const uint64_t idx = ((uint64_t)(b * nh + h) * Tq + i) * pitch + j;
+            Z[(size_t)i * Tk + j] = thr ? dropout_scale(d.seed, idx, thr, ik) : 1.0;
+            const double pz = P[(size_t)i * Tk + j] * Z[(size_t)i * Tk + j];
+            for (int c = 0; c < 64; ++c) o[c] += pz * v[j * kv_ld + c];
+          }
+          double D = 0;
+          for (int c = 0; c < 64; ++c) {
+            const double got = __bfloat162float(ho[((long long)b * Tq + i) * H + h * 64 + c]);
+            eo = fmax(eo, fabs(got - o[c])); mo = fmax(mo, fabs(o[c]));
+            D += o[c] * go[i * H + c];
+          }
+          double gq[64] = {0};
+          for (int j = 0; j < Tk; ++j) {
+            double dp = 0;
+            for (int c = 0; c < 64; ++c) dp += (double)go[i * H + c] * v[j * kv_ld + c];
+            const double z = Z[(size_t)i * Tk + j], pp = P[(size_t)i * Tk + j];
+            const double ds = pp * (dp * z - D) * d.scale;
+            for (int c = 0; c < 64; ++c) {
+              gq[c] += ds * k[j * kv_ld + c];
+              rdk[(size_t)j * 64 + c] += ds * q[i * q_ld + c];
+              rdv[(size_t)j * 64 + c] += pp * z * go[i * H + c];
+            }
+          }
+          for (int c = 0; c < 64; ++c) {
+            const double got = __bfloat162float(GQ[b * q_bs + (long long)i * q_ld + h * 64 + c]);
+            edq = fmax(edq, fabs(got - gq[c])); mdq = fmax(mdq, fabs(gq[c]));
+          }
+        }
+        for (int j = 0; j < Tk; ++j)
+          for (int c = 0; c < 64; ++c) {
+            const double gk = __bfloat162float(GK[b * kv_bs + (long long)j * kv_ld + h * 64 + c]);
+            const double gv = __bfloat162float(GV[b * kv_bs + (long long)j * kv_ld + h * 64 + c]);
+            edk = fmax(edk, fabs(gk - rdk[(size_t)j * 64 + c])); mdk = fmax(mdk, fabs(rdk[(size_t)j * 64 + c]));
+            edv = fmax(edv, fabs(gv - rdv[(size_t)j * 64 + c])); mdv = fmax(mdv, fabs(rdv[(size_t)j * 64 + c]));
+          }
+      }
+    const double tol = 2e-2;
+    bad = (eo > tol * mo) + (edq > tol * mdq) + (edk > tol * mdk) + (edv > tol * mdv);
+    printf("  [%-22s] B=%d nh=%d Tq=%d Tk=%d mask=%d drop=%.2f  rel err: O %.2e dQ %.2e dK %.2e dV %.2e  %s\n", cs.name, B, nh, Tq, Tk,
+           cs.mask, cs.drop, eo / mo, edq / mdq, edk / mdk, edv / mdv, bad ? "FAIL" : "ok");
+  } else {
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+    const int iters = 20;
+    for (int i = 0; i < 3; ++i) { ts_attn_fwd(ctx, &d, 0); ts_attn_bwd(ctx, &d, 0); }
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; ++i) ts_attn_fwd(ctx, &d, 0);
+    cudaEventRecord(e1);
+    for (int i = 0; i < iters; ++i) ts_attn_bwd(ctx, &d, 0);
+    cudaEventRecord(e2);
+    cudaEventSynchronize(e2);
+    float mf = 0, mb = 0;
+    cudaEventElapsedTime(&mf, e0, e1); cudaEventElapsedTime(&mb, e1, e2);
+    mf /= iters; mb /= iters;
+    const double fl = 4.0 * B * nh * (double)Tq * Tk * 64;
+    printf("  [time %-17s] B=%d nh=%d Tq=%d Tk=%d drop=%.2f : fwd %.3f ms (%.0f TFLOP/s)  bwd %.3f ms (%.0f TFLOP/s at 2x fwd flops)\n",
+           cs.name, B, nh, Tq, Tk, cs.drop, mf, fl / (mf * 1e-3) / 1e12, mb, 2 * fl / (mb * 1e-3) / 1e12);
+  }
+  cudaFree(dq_in); cudaFree(g_q); if (dkv_in) cudaFree(dkv_in); if (g_kv) cudaFree(g_kv);
+  cudaFree(d_o); cudaFree(d_do); cudaFree(d_stats); cudaFree(d_dsum);
+  return bad;
+}
+
+int main(int argc, char** argv) {
+  ts_ctx* ctx = nullptr;
+  if (ts_create(0, &ctx)) { printf("ts_create failed\n"); return 1; }
+  const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+  std::vector<Case> cases = {
+      {"self_128", 1, 1, 128, 128, 0, 0.f, false},
+      {"self_200_ragged", 2, 3, 200, 200, 0, 0.f, false},
+      {"self_300_3tiles", 1, 2, 300, 300, 0, 0.f, false},
+      {"w2v_T100", 2, 4, 100, 100, 0, 0.f, false},
+      {"cross_100x300", 2, 2, 100, 300, 0, 0.f, true},
+      {"dec_anticausal_100", 2, 2, 100, 100, 1, 0.f, false},
+      {"anticausal_200", 1, 2, 200, 200, 1, 0.f, false},
+      {"self_200_dropout", 1, 2, 200, 200, 0, 0.1f, false},
+      {"cross_dropout", 1, 2, 100, 260, 0, 0.1f, true},
+  };
+  int fails = 0;
+  printf("== fused attention vs fp64 CPU reference ==\n");
+  for (auto& c : cases) fails += run_case(ctx, c, false) != 0;
+  if (!quick) {
+    printf("== timing ==\n");
+    std::vector<Case> t = {
+        {"w2v base 15s", 8, 12, 750, 750, 0, 0.f, false},
+        {"w2v base 15s drop", 8, 12, 750, 750, 0, 0.1f, false},
+        {"whisper enc", 4, 12, 1500, 1500, 0, 0.f, false},
+        {"whisper cross", 4, 12, 100, 1500, 0, 0.f, true},
+        {"whisper dec", 4, 12, 100, 100, 1, 0.f, false},
+    };
+    for (auto& c : t) run_case(ctx, c, true);
+  }
+  printf("== %s (%d failing cases) ==\n", fails ? "ATTN SELFTEST FAILED" : "ATTN SELFTEST PASSED", fails);
+  ts_destroy(ctx);
+  return fails ? 1 : 0;
+}
