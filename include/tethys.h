@@ -103,6 +103,8 @@ int ts_gemm(ts_ctx* ctx, const ts_gemm_desc* d, void* stream);
  * *_ld is the row stride and *_bs the batch stride in elements (so q/k/v may be slices of one fused projection).
  * stats [B, heads, Tq, 2] fp32 (row max, log row-sum) is written by forward and read by backward;
  * dsum [B, heads, Tq] fp32 is scratch of backward. mask_mode: 0 none, 1 adds -1e9 (fp32) to keys j <= i.
+ * o_lo (optional, same layout as o): forward stores the bf16 rounding residual of o there and backward adds it back when
+ * forming D = rowsum(dO o O), which removes the systematic error a bf16-rounded O puts into dQ / dK.
  * Dropout keep-masks are a pure function of (seed, b, h, i, j); backward regenerates them.
  */
 typedef struct {
@@ -120,6 +122,7 @@ typedef struct {
   void *dq, *dk, *dv;
   int64_t dq_ld, dq_bs, dkv_ld, dkv_bs;
   float* dsum;
+  void* o_lo;
 } ts_attn_desc;
 int ts_attn_fwd(ts_ctx* ctx, const ts_attn_desc* d, void* stream);
 int ts_attn_bwd(ts_ctx* ctx, const ts_attn_desc* d, void* stream);

@@ -42,8 +42,8 @@ struct AttnParams {
   int B, nh, Tq, Tk;
   float scale;
   uint32_t drop_thr; float inv_keep; unsigned long long seed;
-  long long drop_pitch;
-  bf16* o; long long o_ld, o_bs;
+  int drop_pitch;   // even row pitch of the per-(batch, head) dropout index space (element = row * pitch + column)
+  bf16* o; bf16* o_lo; long long o_ld, o_bs;
   float* stats;   // [B, nh, Tq, 2]
   const bf16* o_in; const bf16* d_o;  // same layout as o
   float* dsum;    // [B, nh, Tq]
@@ -196,7 +196,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int r = q * 32 + lane;             // row inside the tile
     const int i = q0 + r;                    // query index
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const unsigned long long drow = ((unsigned long long)(b * p.nh + h) * p.Tq + i) * (unsigned long long)p.drop_pitch;
+    const DropKey dkey = make_drop_key(p.seed, (unsigned long long)(b * p.nh + h), p.drop_thr);
+    const uint32_t drow = (uint32_t)i * (uint32_t)p.drop_pitch;   // element index inside this (batch, head) stream
     const float c1 = p.scale * kLog2e;
     float m_run = -INFINITY, l_part = 0.f;
     bool ok = true;
@@ -250,13 +251,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
         for (int t = 0; t < 32; ++t) { sv[t] = ex2f((sv[t] - m_run) * kLog2e); l_part += sv[t]; }
       }
-      if (p.drop_thr) {
-        const unsigned long long e0 = drow + (unsigned long long)col0;
+      if (p.drop_thr) {  // dropped probabilities become 0; the common factor 1/keep is applied to O at the end
+        const uint32_t pb = (drow + (uint32_t)col0) >> 1;
 #pragma unroll
         for (int t = 0; t < 32; t += 2) {
-          float z0, z1;
-          dropout_scale2(p.seed, e0 + t, p.drop_thr, p.inv_keep, z0, z1);
-          sv[t] *= z0; sv[t + 1] *= z1;
+          const uint32_t w = drop_word32(dkey, pb + (t >> 1));
+          sv[t] = drop_keep_even(dkey, w) ? sv[t] : 0.f;
+          sv[t + 1] = drop_keep_odd(dkey, w) ? sv[t + 1] : 0.f;
         }
       }
       if (j >= 2) {  // P buffer `bsel` is free once P.V of tile j-2 has retired
@@ -282,16 +283,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       ptx::tmem_ld_32x16(tO + lane_off + chunk * 16, ro);
       ptx::tmem_ld_wait();
       if (i < p.Tq) {
-        const float inv = 1.f / l_row;
-        bf16* dst = p.o + (long long)b * p.o_bs + (long long)i * p.o_ld + h * AT_D + chunk * 16;
+        const float inv = p.inv_keep / l_row;
+        const long long ooff = (long long)b * p.o_bs + (long long)i * p.o_ld + h * AT_D + chunk * 16;
+        float ov[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) ov[t] = __uint_as_float(ro[t]) * inv;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           uint4 u;
-          u.x = pack2(__uint_as_float(ro[8 * t]) * inv, __uint_as_float(ro[8 * t + 1]) * inv);
-          u.y = pack2(__uint_as_float(ro[8 * t + 2]) * inv, __uint_as_float(ro[8 * t + 3]) * inv);
-          u.z = pack2(__uint_as_float(ro[8 * t + 4]) * inv, __uint_as_float(ro[8 * t + 5]) * inv);
-          u.w = pack2(__uint_as_float(ro[8 * t + 6]) * inv, __uint_as_float(ro[8 * t + 7]) * inv);
-          reinterpret_cast<uint4*>(dst)[t] = u;
+          u.x = pack2(ov[8 * t], ov[8 * t + 1]); u.y = pack2(ov[8 * t + 2], ov[8 * t + 3]);
+          u.z = pack2(ov[8 * t + 4], ov[8 * t + 5]); u.w = pack2(ov[8 * t + 6], ov[8 * t + 7]);
+          reinterpret_cast<uint4*>(p.o + ooff)[t] = u;
+        }
+        if (p.o_lo) {  // bf16 rounding residual, so that backward can form D = rowsum(dO o O) from an (almost) fp32 O
+#pragma unroll
+          for (int t = 0; t < 16; ++t) ov[t] -= __bfloat162float(__float2bfloat16_rn(ov[t]));
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            uint4 u;
+            u.x = pack2(ov[8 * t], ov[8 * t + 1]); u.y = pack2(ov[8 * t + 2], ov[8 * t + 3]);
+            u.z = pack2(ov[8 * t + 4], ov[8 * t + 5]); u.w = pack2(ov[8 * t + 6], ov[8 * t + 7]);
+            reinterpret_cast<uint4*>(p.o_lo + ooff)[t] = u;
+          }
         }
         if (chunk == 0) {
           float* st = p.stats + (((long long)b * p.nh + h) * p.Tq + i) * 2;
@@ -319,7 +332,7 @@ constexpr int kBwdThreads = 64 + kBwdEw * 32;
 template <int MASK, bool RAGGED, bool PZ>
 __device__ __forceinline__ void bwd_chunk(const uint32_t (&rs)[32], const uint32_t (&rd)[32], float (&ds)[32], float (&pz)[32],
                                           const AttnParams& p, float c1, float c0, float m_i, float ll2, float D, int i, int col0,
-                                          unsigned long long e0) {
+                                          const DropKey& dkey, uint32_t pair0) {
 #pragma unroll
   for (int t = 0; t < 32; t += 2) {
     float p0, p1;
@@ -337,12 +350,12 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&rs)[32], const uint32
       if (col0 + t >= p.Tk) p0 = 0.f;
       if (col0 + t + 1 >= p.Tk) p1 = 0.f;
     }
-    if (p.drop_thr) {
-      float z0, z1;
-      dropout_scale2(p.seed, e0 + t, p.drop_thr, p.inv_keep, z0, z1);
-      ds[t] = p0 * fmaf(__uint_as_float(rd[t]), z0, -D);
-      ds[t + 1] = p1 * fmaf(__uint_as_float(rd[t + 1]), z1, -D);
-      if (PZ) { pz[t] = p0 * z0; pz[t + 1] = p1 * z1; }
+    if (p.drop_thr) {  // Z = keep / keep_prob; the 1/keep_prob of P o Z is applied to dV when it is stored
+      const uint32_t w = drop_word32(dkey, pair0 + (t >> 1));
+      const bool k0 = drop_keep_even(dkey, w), k1 = drop_keep_odd(dkey, w);
+      ds[t] = p0 * fmaf(__uint_as_float(rd[t]), k0 ? p.inv_keep : 0.f, -D);
+      ds[t + 1] = p1 * fmaf(__uint_as_float(rd[t + 1]), k1 ? p.inv_keep : 0.f, -D);
+      if (PZ) { pz[t] = k0 ? p0 : 0.f; pz[t + 1] = k1 ? p1 : 0.f; }
     } else {
       ds[t] = p0 * (__uint_as_float(rd[t]) - D);
       ds[t + 1] = p1 * (__uint_as_float(rd[t + 1]) - D);
@@ -459,7 +472,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int i = q0 + r;
     const bool live = i < p.Tq;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const unsigned long long drow = ((unsigned long long)(b * p.nh + h) * p.Tq + i) * (unsigned long long)p.drop_pitch;
+    const DropKey dkey = make_drop_key(p.seed, (unsigned long long)(b * p.nh + h), p.drop_thr);
+    const uint32_t drow = (uint32_t)i * (uint32_t)p.drop_pitch;
     const long long srow = ((long long)b * p.nh + h) * p.Tq + i;
     float m_i = 0.f, ll2 = INFINITY, D = 0.f;
     if (live) {
@@ -467,16 +481,19 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       ll2 = p.stats[srow * 2 + 1] * kLog2e;
       const uint4* po = reinterpret_cast<const uint4*>(p.o_in + (long long)b * p.o_bs + (long long)i * p.o_ld + h * AT_D);
       const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + (long long)b * p.o_bs + (long long)i * p.o_ld + h * AT_D);
+      const uint4* pl = p.o_lo ? reinterpret_cast<const uint4*>(p.o_lo + (long long)b * p.o_bs + (long long)i * p.o_ld + h * AT_D) : nullptr;
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         const uint4 a = __ldg(po + t), g = __ldg(pd + t);
+        const uint4 lo = pl ? __ldg(pl + t) : make_uint4(0, 0, 0, 0);
         const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
         const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&g);
+        const __nv_bfloat162* lh = reinterpret_cast<const __nv_bfloat162*>(&lo);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 x = __bfloat1622float2(ah[e]), y = __bfloat1622float2(gh[e]);
-          D = fmaf(x.x, y.x, D);
-          D = fmaf(x.y, y.y, D);
+          const float2 x = __bfloat1622float2(ah[e]), y = __bfloat1622float2(gh[e]), z = __bfloat1622float2(lh[e]);
+          D = fmaf(x.x + z.x, y.x, D);
+          D = fmaf(x.y + z.y, y.y, D);
         }
       }
       if (chunk == 0) p.dsum[srow] = D;
@@ -492,8 +509,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       ptx::tmem_ld_32x32(tDP + lane_off + chunk * 32, rd);
       ptx::tmem_ld_wait();
       float ds[32], unused[32];
-      if (col0 + 32 > p.Tk) bwd_chunk<MASK, true, false>(rs, rd, ds, unused, p, c1, c0, m_i, ll2, D, i, col0, drow + col0);
-      else bwd_chunk<MASK, false, false>(rs, rd, ds, unused, p, c1, c0, m_i, ll2, D, i, col0, drow + col0);
+      const uint32_t pair0 = (drow + (uint32_t)col0) >> 1;
+      if (col0 + 32 > p.Tk) bwd_chunk<MASK, true, false>(rs, rd, ds, unused, p, c1, c0, m_i, ll2, D, i, col0, dkey, pair0);
+      else bwd_chunk<MASK, false, false>(rs, rd, ds, unused, p, c1, c0, m_i, ll2, D, i, col0, dkey, pair0);
       if (j > 0 && !ptx::mbar_wait(dq_done, (j - 1) & 1, watchdog, 26)) { ok = false; break; }  // dS smem free again
       store_chunk32(sDS, r, chunk, ds);
       ptx::fence_proxy_async_smem();
@@ -611,6 +629,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const int col0 = kv0 + chunk * 32;
     const bool ragged = col0 + 32 > p.Tk;
     const float c1 = p.scale * kLog2e;
+    const DropKey dkey = make_drop_key(p.seed, (unsigned long long)(b * p.nh + h), p.drop_thr);
     bool ok = true;
     for (int it = 0; it < nq && ok; ++it) {
       const int i = it * AT_M + r;
@@ -619,7 +638,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       float m_i = 0.f, ll2 = INFINITY, D = 0.f;
       if (live) { m_i = p.stats[srow * 2]; ll2 = p.stats[srow * 2 + 1] * kLog2e; D = p.dsum[srow]; }
       const float c0 = m_i * kLog2e + ll2;
-      const unsigned long long drow = (unsigned long long)srow * (unsigned long long)p.drop_pitch;
+      const uint32_t pair0 = ((uint32_t)i * (uint32_t)p.drop_pitch + (uint32_t)col0) >> 1;
       if (!ptx::mbar_wait(sdp_full, it & 1, watchdog, 35)) { ok = false; break; }
       ptx::tc_fence_after();
       uint32_t rs[32], rd[32];
@@ -627,8 +646,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       ptx::tmem_ld_32x32(tDP + lane_off + chunk * 32, rd);
       ptx::tmem_ld_wait();
       float ds[32], pz[32];
-      if (ragged) bwd_chunk<MASK, true, true>(rs, rd, ds, pz, p, c1, c0, m_i, ll2, D, i, col0, drow + col0);
-      else bwd_chunk<MASK, false, true>(rs, rd, ds, pz, p, c1, c0, m_i, ll2, D, i, col0, drow + col0);
+      if (ragged) bwd_chunk<MASK, true, true>(rs, rd, ds, pz, p, c1, c0, m_i, ll2, D, i, col0, dkey, pair0);
+      else bwd_chunk<MASK, false, true>(rs, rd, ds, pz, p, c1, c0, m_i, ll2, D, i, col0, dkey, pair0);
       if (it > 0 && !ptx::mbar_wait(acc_done, (it - 1) & 1, watchdog, 36)) { ok = false; break; }  // P / dS smem free again
       store_chunk32(sP, r, chunk, pz);
       store_chunk32(sDS, r, chunk, ds);
@@ -646,7 +665,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       ptx::tmem_ld_wait();
       if (jrow < p.Tk)
         store_row32((chunk < 2 ? p.dv : p.dk) + (long long)b * p.dkv_bs + (long long)jrow * p.dkv_ld + h * AT_D + (chunk & 1) * 32, rg,
-                    chunk < 2 ? 1.f : p.scale);
+                    chunk < 2 ? p.inv_keep : p.scale);
     }
   }
   ptx::tc_fence_before();
@@ -686,8 +705,10 @@ static int fill_params(Ctx* ctx, const ts_attn_desc* d, AttnParams* p) {
   p->B = d->batch; p->nh = d->heads; p->Tq = d->tq; p->Tk = d->tk; p->scale = d->scale;
   drop_params(d->drop, &p->drop_thr, &p->inv_keep);
   p->seed = d->seed;
-  p->drop_pitch = ((long long)d->tk + 1) & ~1ll;
-  p->o = (bf16*)d->o; p->o_ld = d->o_ld; p->o_bs = d->o_bs;
+  p->drop_pitch = (d->tk + 1) & ~1;
+  TS_REQUIRE(ctx, (long long)d->tq * p->drop_pitch < (1ll << 32), TS_ESHAPE, "attention: Tq * Tk must stay below 2^32");
+  p->o = (bf16*)d->o; p->o_lo = (bf16*)d->o_lo; p->o_ld = d->o_ld; p->o_bs = d->o_bs;
+  TS_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d->o_lo) & 15) == 0, TS_EINVAL, "attention: o_lo must be 16-byte aligned");
   p->stats = d->stats;
   return 0;
 }

@@ -142,4 +142,31 @@ __device__ __forceinline__ void dropout_scale2(uint64_t seed, uint64_t idx_even,
   s1 = ((w >> 16) >= (thr >> 16)) ? inv_keep : 0.f;
 }
 
+
+// Cheaper 32-bit variant for kernels that own a whole dropout "stream" (the fused attention kernels: one stream per
+// (batch, head), element index = row * pitch + column < 2^32): two multiply/xor-shift rounds per element PAIR.
+//   keep(even element) <=> low 16 bits of the word >= thr16,  keep(odd element) <=> high 16 bits >= thr16
+struct DropKey { uint32_t k1, k2m, thr_hi; };
+__host__ __device__ __forceinline__ DropKey make_drop_key(uint64_t seed, uint64_t stream, uint32_t thr) {
+  uint64_t z = seed + (stream + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  DropKey k;
+  k.k1 = (uint32_t)z;
+  k.k2m = (uint32_t)(z >> 32) * 0x846ca68bu;
+  k.thr_hi = thr & 0xffff0000u;
+  return k;
+}
+__host__ __device__ __forceinline__ uint32_t drop_word32(const DropKey& k, uint32_t pair) {
+  uint32_t x = pair ^ k.k1;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x = x * 0x846ca68bu + k.k2m;
+  x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ bool drop_keep_even(const DropKey& k, uint32_t w) { return (w << 16) >= k.thr_hi; }
+__host__ __device__ __forceinline__ bool drop_keep_odd(const DropKey& k, uint32_t w) { return w >= k.thr_hi; }
+
 }  // namespace ts

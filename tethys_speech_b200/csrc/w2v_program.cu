@@ -10,7 +10,7 @@ namespace ts {
 
 struct W2VLayerOff { long long qkv_w, qkv_b, o_w, o_b, ln1_g, ln1_b, fc1_w, fc1_b, fc2_w, fc2_b, ln2_g, ln2_b; };
 struct W2VLayerBuf {
-  void *h_in, *x1, *qkv, *P, *ctx, *h_mid, *x2, *u, *f;
+  void *h_in, *x1, *qkv, *P, *ctx, *ctx_lo, *h_mid, *x2, *u, *f;
   float *ln1_mean, *ln1_rstd, *ln2_mean, *ln2_rstd;
 };
 
@@ -182,6 +182,7 @@ static int plan(W2V* m, int B, int N, Bump& bp) {
     b.qkv = bp.get(m->E((long long)M * 3 * H));
     b.P = m->fused_attn ? bp.get(8ll * B * nh * T) : bp.get(m->E((long long)B * nh * T * Tp));   // fused: [B,nh,T,2] row statistics only
     b.ctx = bp.get(m->E((long long)M * H));
+    b.ctx_lo = m->fused_attn ? bp.get(m->E((long long)M * H)) : nullptr;
     b.h_mid = bp.get(m->E((long long)M * H));
     b.x2 = bp.get(m->E((long long)M * H));
     b.u = bp.get(m->E((long long)M * F));
@@ -298,7 +299,7 @@ static int w2v_forward(W2V* m, const float* wave, const int* neg, long long neg_
       a.q = qkv; a.k = qkv + m->E(H); a.v = qkv + m->E(2 * H); a.o = b.ctx;
       a.q_ld = a.kv_ld = 3 * H; a.q_bs = a.kv_bs = (long long)T * 3 * H; a.o_ld = H; a.o_bs = (long long)T * H;
       a.stats = (float*)b.P; a.batch = B; a.heads = nh; a.tq = a.tk = T; a.head_dim = hd;
-      a.scale = 1.f / sqrtf((float)hd); a.mask_mode = 0; a.drop = adrop; a.seed = site_seed(seed, 100 + l * 8);
+      a.scale = 1.f / sqrtf((float)hd); a.mask_mode = 0; a.drop = adrop; a.seed = site_seed(seed, 100 + l * 8); a.o_lo = b.ctx_lo;
       TS_TRY(attn_fwd(ctx, &a, st));
     } else {
       // scores = q k^T (scaled by 1/sqrt(hd) inside the softmax, V:349)
@@ -415,7 +416,7 @@ static int w2v_backward_stage(W2V* m, int stage, cudaStream_t st) {
       a.q = qkv; a.k = qkv + m->E(H); a.v = qkv + m->E(2 * H); a.o = b.ctx;
       a.q_ld = a.kv_ld = 3 * H; a.q_bs = a.kv_bs = (long long)T * 3 * H; a.o_ld = H; a.o_bs = (long long)T * H;
       a.stats = (float*)b.P; a.batch = B; a.heads = nh; a.tq = a.tk = T; a.head_dim = hd;
-      a.scale = 1.f / sqrtf((float)hd); a.mask_mode = 0; a.drop = adrop; a.seed = aseed;
+      a.scale = 1.f / sqrtf((float)hd); a.mask_mode = 0; a.drop = adrop; a.seed = aseed; a.o_lo = b.ctx_lo;
       a.d_o = m->g_ctx; a.dq = dqkv; a.dk = dqkv + m->E(H); a.dv = dqkv + m->E(2 * H);
       a.dq_ld = a.dkv_ld = 3 * H; a.dq_bs = a.dkv_bs = (long long)T * 3 * H; a.dsum = (float*)m->g_P;
       TS_TRY(attn_bwd(ctx, &a, st));

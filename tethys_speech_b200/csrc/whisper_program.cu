@@ -125,6 +125,11 @@ static void build_params(Whisper* m) {
   m->stage_end.push_back(pt.n);
 }
 
+// fused attention keeps, per site, the row statistics [B, nh, Tq, 2] fp32 followed by the bf16 rounding residual of the
+// context tensor [B, Tq, d] (ts_attn_desc.o_lo)
+static inline size_t fused_stats_bytes(int B, int nh, int Tq) { return ((size_t)8 * B * nh * Tq + 255) & ~(size_t)255; }
+static inline size_t fused_aux_bytes(int B, int nh, int Tq, int d) { return fused_stats_bytes(B, nh, Tq) + (size_t)2 * B * Tq * d; }
+
 static int plan(Whisper* m, int B, int Tm, int S, Bump& bp) {
   Ctx* ctx = m->ctx;
   const ts_whisper_config& c = m->cfg;
@@ -149,7 +154,7 @@ static int plan(Whisper* m, int B, int Tm, int S, Bump& bp) {
     EncLayerBuf& b = m->EB[l];
     b.h_in = h;
     b.x1 = bp.get(m->E(Me * d)); b.qkv = bp.get(m->E(Me * 3 * d));
-    b.P = m->fused_attn ? bp.get(8ll * B * nh * T) : bp.get(m->E((long long)B * nh * T * Tp));   // fused: row statistics only
+    b.P = m->fused_attn ? bp.get(fused_aux_bytes(B, nh, T, d)) : bp.get(m->E((long long)B * nh * T * Tp));   // fused: row statistics + O residual
     b.ctx = bp.get(m->E(Me * d)); b.h_mid = bp.get(m->E(Me * d)); b.x2 = bp.get(m->E(Me * d));
     b.u = bp.get(m->E(Me * F)); b.f = bp.get(m->E(Me * F));
     b.m1 = (float*)bp.get(4 * Me); b.r1 = (float*)bp.get(4 * Me); b.m2 = (float*)bp.get(4 * Me); b.r2 = (float*)bp.get(4 * Me);
@@ -163,9 +168,9 @@ static int plan(Whisper* m, int B, int Tm, int S, Bump& bp) {
   for (int l = 0; l < c.dec_layers; ++l) {
     DecLayerBuf& b = m->DB[l];
     b.g_in = g;
-    b.x1 = bp.get(m->E(Md * d)); b.qkv = bp.get(m->E(Md * 3 * d)); b.P = m->fused_attn ? bp.get(8ll * B * nh * S) : bp.get(m->E((long long)B * nh * S * Sp));
+    b.x1 = bp.get(m->E(Md * d)); b.qkv = bp.get(m->E(Md * 3 * d)); b.P = m->fused_attn ? bp.get(fused_aux_bytes(B, nh, S, d)) : bp.get(m->E((long long)B * nh * S * Sp));
     b.ctx = bp.get(m->E(Md * d)); b.g1 = bp.get(m->E(Md * d)); b.x2 = bp.get(m->E(Md * d)); b.q = bp.get(m->E(Md * d));
-    b.kv = bp.get(m->E(Me * 2 * d)); b.Pc = m->fused_attn ? bp.get(8ll * B * nh * S) : bp.get(m->E((long long)B * nh * S * Tp)); b.ctxc = bp.get(m->E(Md * d));
+    b.kv = bp.get(m->E(Me * 2 * d)); b.Pc = m->fused_attn ? bp.get(fused_aux_bytes(B, nh, S, d)) : bp.get(m->E((long long)B * nh * S * Tp)); b.ctxc = bp.get(m->E(Md * d));
     b.g2 = bp.get(m->E(Md * d)); b.x3 = bp.get(m->E(Md * d)); b.u = bp.get(m->E(Md * F)); b.f = bp.get(m->E(Md * F));
     b.m1 = (float*)bp.get(4 * Md); b.r1 = (float*)bp.get(4 * Md); b.m2 = (float*)bp.get(4 * Md); b.r2 = (float*)bp.get(4 * Md);
     b.m3 = (float*)bp.get(4 * Md); b.r3 = (float*)bp.get(4 * Md);
@@ -203,6 +208,7 @@ static int attn_forward(Whisper* m, const void* q, long long ldq, const void* k,
     a.q_ld = ldq; a.q_bs = (long long)s.Tq * ldq; a.kv_ld = ldkv; a.kv_bs = (long long)s.Tk * ldkv; a.o_ld = ldc; a.o_bs = (long long)s.Tq * ldc;
     a.stats = (float*)P; a.batch = s.B; a.heads = s.nh; a.tq = s.Tq; a.tk = s.Tk; a.head_dim = s.hd;
     a.scale = scale; a.mask_mode = mask; a.drop = drop; a.seed = seed;
+    a.o_lo = (char*)P + fused_stats_bytes(s.B, s.nh, s.Tq);
     return attn_fwd(ctx, &a, st);
   }
   const long long sP1 = (long long)s.Tq * s.Tkp, sP2 = (long long)s.nh * s.Tq * s.Tkp;
@@ -229,6 +235,7 @@ static int attn_backward(Whisper* m, const void* q, long long ldq, const void* k
     a.scale = scale; a.mask_mode = mask; a.drop = drop; a.seed = seed;
     a.d_o = dctx; a.dq = dq; a.dk = dk; a.dv = dv; a.dq_ld = lddq; a.dq_bs = (long long)s.Tq * lddq; a.dkv_ld = lddkv; a.dkv_bs = (long long)s.Tk * lddkv;
     a.dsum = (float*)m->s_P;
+    a.o_lo = (char*)const_cast<void*>(P) + fused_stats_bytes(s.B, s.nh, s.Tq);
     return attn_bwd(ctx, &a, st);
   }
   const long long sP1 = (long long)s.Tq * s.Tkp, sP2 = (long long)s.nh * s.Tq * s.Tkp;

@@ -18,17 +18,25 @@ static float frand() {
 }
 static float bfr(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
 
-// host copy of common.cuh: dropout_word / dropout_scale
-static uint32_t dropout_word(uint64_t seed, uint64_t idx) {
-  uint32_t x = (uint32_t)(idx >> 1) ^ (uint32_t)seed;
-  const uint32_t k2 = (uint32_t)(seed >> 32) ^ ((uint32_t)(idx >> 33) * 0x85EBCA6Bu);
-  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x += k2; x *= 0x846ca68bu; x ^= x >> 16;
+// host copy of common.cuh: make_drop_key / drop_word32 (one dropout stream per (batch, head))
+struct DropKey { uint32_t k1, k2m, thr_hi; };
+static DropKey make_drop_key(uint64_t seed, uint64_t stream, uint32_t thr) {
+  uint64_t z = seed + (stream + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  DropKey k; k.k1 = (uint32_t)z; k.k2m = (uint32_t)(z >> 32) * 0x846ca68bu; k.thr_hi = thr & 0xffff0000u;
+  return k;
+}
+static uint32_t drop_word32(const DropKey& k, uint32_t pair) {
+  uint32_t x = pair ^ k.k1;
+  x *= 0x7feb352du; x ^= x >> 15; x = x * 0x846ca68bu + k.k2m; x ^= x >> 16;
   return x;
 }
-static float dropout_scale(uint64_t seed, uint64_t idx, uint32_t thr, float inv_keep) {
-  const uint32_t w = dropout_word(seed, idx);
-  const uint32_t r = (idx & 1) ? (w >> 16) : (w & 0xffffu);
-  return (r >= (thr >> 16)) ? inv_keep : 0.f;
+static float dropout_scale(const DropKey& k, uint32_t idx, float inv_keep) {
+  const uint32_t w = drop_word32(k, idx >> 1);
+  const bool keep = (idx & 1) ? (w >= k.thr_hi) : ((w << 16) >= k.thr_hi);
+  return keep ? inv_keep : 0.f;
 }
 
 struct Case { const char* name; int B, nh, Tq, Tk, mask; float drop; bool cross; };
@@ -61,6 +69,7 @@ static int run_case(ts_ctx* ctx, const Case& cs, bool timing) {
     cudaMalloc(&g_kv, kv16.size() * 2); cudaMemset(g_kv, 0, kv16.size() * 2);
   }
   cudaMalloc(&d_o, (size_t)B * Tq * H * 2); cudaMemset(d_o, 0, (size_t)B * Tq * H * 2);
+  __nv_bfloat16* d_olo; cudaMalloc(&d_olo, (size_t)B * Tq * H * 2); cudaMemset(d_olo, 0, (size_t)B * Tq * H * 2);
   cudaMalloc(&d_do, do16.size() * 2); cudaMemcpy(d_do, do16.data(), do16.size() * 2, cudaMemcpyHostToDevice);
   cudaMalloc(&d_stats, (size_t)B * nh * Tq * 2 * 4); cudaMalloc(&d_dsum, (size_t)B * nh * Tq * 4);
   ts_attn_desc d;
@@ -68,7 +77,7 @@ static int run_case(ts_ctx* ctx, const Case& cs, bool timing) {
   d.q = dq_in; d.k = cs.cross ? dkv_in : dq_in + H; d.v = cs.cross ? dkv_in + H : dq_in + 2 * H;
   d.o = d_o; d.q_ld = q_ld; d.q_bs = q_bs; d.kv_ld = kv_ld; d.kv_bs = kv_bs; d.o_ld = H; d.o_bs = (long long)Tq * H;
   d.stats = d_stats; d.batch = B; d.heads = nh; d.tq = Tq; d.tk = Tk; d.head_dim = 64; d.scale = 0.125f; d.mask_mode = cs.mask;
-  d.drop = cs.drop; d.seed = 0x1234567887654321ull;
+  d.drop = cs.drop; d.seed = 0x1234567887654321ull; d.o_lo = d_olo;
   d.d_o = d_do; d.dq = g_q; d.dq_ld = q_ld; d.dq_bs = q_bs;
   d.dk = cs.cross ? g_kv : g_q + H; d.dv = cs.cross ? g_kv + H : g_q + 2 * H; d.dkv_ld = kv_ld; d.dkv_bs = kv_bs; d.dsum = d_dsum;
   int rc = ts_attn_fwd(ctx, &d, 0);
@@ -115,8 +124,8 @@ static int run_case(ts_ctx* ctx, const Case& cs, bool timing) {
           double o[64] = {0};
           for (int j = 0; j < Tk; ++j) {
             P[(size_t)i * Tk + j] /= l;
-            const uint64_t idx = ((uint64_t)(b * nh + h) * Tq + i) * pitch + j;
-            Z[(size_t)i * Tk + j] = thr ? dropout_scale(d.seed, idx, thr, ik) : 1.0;
+            const uint32_t idx = (uint32_t)i * (uint32_t)pitch + (uint32_t)j;
+            Z[(size_t)i * Tk + j] = thr ? dropout_scale(make_drop_key(d.seed, (uint64_t)(b * nh + h), thr), idx, ik) : 1.0;
             const double pz = P[(size_t)i * Tk + j] * Z[(size_t)i * Tk + j];
             for (int c = 0; c < 64; ++c) o[c] += pz * v[j * kv_ld + c];
           }
@@ -174,7 +183,7 @@ static int run_case(ts_ctx* ctx, const Case& cs, bool timing) {
            cs.name, B, nh, Tq, Tk, cs.drop, mf, fl / (mf * 1e-3) / 1e12, mb, 2 * fl / (mb * 1e-3) / 1e12);
   }
   cudaFree(dq_in); cudaFree(g_q); if (dkv_in) cudaFree(dkv_in); if (g_kv) cudaFree(g_kv);
-  cudaFree(d_o); cudaFree(d_do); cudaFree(d_stats); cudaFree(d_dsum);
+  cudaFree(d_o); cudaFree(d_olo); cudaFree(d_do); cudaFree(d_stats); cudaFree(d_dsum);
   return bad;
 }
 
