@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(256) ew_kernel(const T* __restrict__ a, const 
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float r;
-      if (MODE == 0) r = gelu_f(va[j]);
-      else if (MODE == 1) r = va[j] * gelu_grad_f(vb[j]);
+      if (MODE == 0) r = gelu_t<T>(va[j]);
+      else if (MODE == 1) r = va[j] * gelu_grad_t<T>(vb[j]);
       else if (MODE == 2) r = va[j];
       else r = va[j] + vb[j];
       if (MODE != 3 && thr) r *= dropout_scale(seed, (uint64_t)(i + j), thr, inv_keep);
@@ -124,8 +124,60 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
     if (col < cols) atomicAdd(&out[col], t);
   }
 }
+// vectorised variant (cols % 8 == 0, 16-byte aligned rows): a lane owns 8 consecutive columns (one 16-byte load per
+// row), a warp a 256-column strip, the 8 warps of a block interleave rows; 4 independent loads in flight per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, long long ld, int rows, int cols,
+                                                         float* __restrict__ out, int rows_per_block) {
+  __shared__ float red[8][256 + 8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (col < cols) {
+    int r = r0 + w;
+    for (; r + 24 < r1; r += 32) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load8<T>(x + (long long)(r + 8 * u) * ld + col, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += v[u][i];
+    }
+    for (; r < r1; r += 8) {
+      float v[8];
+      load8<T>(x + (long long)r * ld + col, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[w][lane * 8 + i] = acc[i];
+  __syncthreads();
+  const int c = threadIdx.x;
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += red[i][c];
+  if (blockIdx.x * 256 + c < cols) atomicAdd(&out[blockIdx.x * 256 + c], t);
+}
 int colsum_acc(Ctx* ctx, int dt, const void* x, long long ld, int rows, int cols, float* out, cudaStream_t st) {
   if (rows <= 0 || cols <= 0) return 0;
+  const int esz = dt == TS_F32 ? 4 : 2;
+  if (cols % 8 == 0 && (ld * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int cb = cdiv(cols, 256);
+    int rb = (ctx->num_sms * 3) / cb;
+    if (rb < 1) rb = 1;
+    int rpb = cdiv(rows, rb);
+    rpb = ((rpb + 31) / 32) * 32;
+    dim3 grid(cb, cdiv(rows, rpb));
+    if (dt == TS_F32) colsum_vec_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ld, rows, cols, out, rpb);
+    else colsum_vec_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, ld, rows, cols, out, rpb);
+    TS_LAUNCH_OK(ctx);
+    return 0;
+  }
   const int rpb = 512;
   dim3 grid(cdiv(cols, 32), cdiv(rows, rpb));
   if (dt == TS_F32) colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ld, rows, cols, out, rpb);

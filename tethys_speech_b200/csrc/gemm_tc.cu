@@ -100,7 +100,7 @@ template <int NV>
 __device__ __forceinline__ void epi_act_drop(float (&v)[NV], const EpiParams& p, unsigned long long e0) {
   if (p.act == 1) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = gelu_f(v[i]);
+    for (int i = 0; i < NV; ++i) v[i] = gelu_fast_f(v[i]);   // bf16 operands: fast erf (common.cuh)
   }
   if (p.drop_thr) {
     if ((e0 & 1) == 0) {
@@ -374,7 +374,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               float v = sbuf[rr * 32 + (lane ^ rr)] * p.alpha + bv;
               const long long off = (long long)grow * p.ldc + col;
               if (pbase) pbase[off] = from_f<OutT>(v);
-              if (p.act == 1) v = gelu_f(v);
+              if (p.act == 1) v = gelu_fast_f(v);
               if (p.drop_thr) v *= dropout_scale(p.seed, (unsigned long long)(boff + off), p.drop_thr, p.inv_keep);
               if (rbase) v += to_f<OutT>(rbase[(long long)grow * p.ldr + col]);
               if (kF32) {

@@ -69,78 +69,102 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, co
   }
 }
 
+// backward, part 1: dx (+ dres) — one warp per row, nothing but the row in registers (high occupancy, HBM-bound)
 template <typename T, int NCH>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
-                                                     const float* __restrict__ gamma, const float* __restrict__ mean,
-                                                     const float* __restrict__ rstd, const T* __restrict__ dres,
-                                                     T* __restrict__ dx, float* __restrict__ dgamma,
-                                                     float* __restrict__ dbeta, int rows, int cols) {
-  extern __shared__ float sm[];  // [2][cols]
-  float* sg = sm;
-  float* sb = sm + cols;
-  for (int i = threadIdx.x; i < 2 * cols; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
+__global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                        const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                        const float* __restrict__ rstd, const T* __restrict__ dres,
+                                                        T* __restrict__ dx, int rows, int cols) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float ag[NCH][8], ab[NCH][8], g[NCH][8];
-#pragma unroll
-  for (int ch = 0; ch < NCH; ++ch) {
-    const int col = ch * 256 + lane * 8;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { ag[ch][i] = 0.f; ab[ch][i] = 0.f; g[ch][i] = 0.f; }
-    if (col < cols) load8<float>(gamma + col, g[ch]);
-  }
-  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
-    const float mu = mean[row], rs = rstd[row];
-    float xh[NCH][8], d[NCH][8];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      const int col = ch * 256 + lane * 8;
-      if (col < cols) {
-        load8<T>(x + (long long)row * cols + col, xh[ch]);
-        load8<T>(dy + (long long)row * cols + col, d[ch]);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          xh[ch][i] = (xh[ch][i] - mu) * rs;
-          ag[ch][i] += d[ch][i] * xh[ch][i];
-          ab[ch][i] += d[ch][i];
-          d[ch][i] *= g[ch][i];
-          s1 += d[ch][i];
-          s2 += d[ch][i] * xh[ch][i];
-        }
-      }
-    }
-    s1 = warp_sum(s1) / cols;
-    s2 = warp_sum(s2) / cols;
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      const int col = ch * 256 + lane * 8;
-      if (col < cols) {
-        float o[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = rs * (d[ch][i] - s1 - xh[ch][i] * s2);
-        if (dres) {
-          float r[8];
-          load8<T>(dres + (long long)row * cols + col, r);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] += r[i];
-        }
-        store8<T>(dx + (long long)row * cols + col, o);
-      }
-    }
-  }
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const float mu = mean[row], rs = rstd[row];
+  float xh[NCH][8], d[NCH][8];
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
     const int col = ch * 256 + lane * 8;
     if (col < cols) {
+      float g[8];
+      load8<T>(x + (long long)row * cols + col, xh[ch]);
+      load8<T>(dy + (long long)row * cols + col, d[ch]);
+      load8<float>(gamma + col, g);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { atomicAdd(&sg[col + i], ag[ch][i]); atomicAdd(&sb[col + i], ab[ch][i]); }
+      for (int i = 0; i < 8; ++i) {
+        xh[ch][i] = (xh[ch][i] - mu) * rs;
+        d[ch][i] *= g[i];
+        s1 += d[ch][i];
+        s2 += d[ch][i] * xh[ch][i];
+      }
     }
   }
+  s1 = warp_sum(s1) / cols;
+  s2 = warp_sum(s2) / cols;
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int col = ch * 256 + lane * 8;
+    if (col < cols) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = rs * (d[ch][i] - s1 - xh[ch][i] * s2);
+      if (dres) {
+        float r[8];
+        load8<T>(dres + (long long)row * cols + col, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += r[i];
+      }
+      store8<T>(dx + (long long)row * cols + col, o);
+    }
+  }
+}
+
+// backward, part 2: dgamma += sum_rows dy * xhat, dbeta += sum_rows dy. A lane owns 8 consecutive columns, the 8 warps
+// of a block interleave the rows of the block's row range; cross-warp reduction in smem, one atomic per column and block.
+template <typename T>
+__global__ void __launch_bounds__(256) ln_bwd_param_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int rows,
+                                                           int cols, int rows_per_block) {
+  __shared__ float red[2][8][256 + 8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float ag[8], ab[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
+  if (col < cols) {
+    for (int r = r0 + w; r < r1; r += 16) {
+      float xv[2][8], dv[2][8], mu[2], rs[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int rr = r + 8 * u;
+        if (rr < r1) {
+          load8<T>(x + (long long)rr * cols + col, xv[u]);
+          load8<T>(dy + (long long)rr * cols + col, dv[u]);
+          mu[u] = mean[rr]; rs[u] = rstd[rr];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (r + 8 * u >= r1) break;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          ag[i] = fmaf(dv[u][i], (xv[u][i] - mu[u]) * rs[u], ag[i]);
+          ab[i] += dv[u][i];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[0][w][lane * 8 + i] = ag[i]; red[1][w][lane * 8 + i] = ab[i]; }
   __syncthreads();
-  for (int i = threadIdx.x; i < cols; i += blockDim.x) {
-    atomicAdd(&dgamma[i], sg[i]);
-    atomicAdd(&dbeta[i], sb[i]);
+  const int c = threadIdx.x;
+  float tg = 0.f, tb = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { tg += red[0][i][c]; tb += red[1][i][c]; }
+  if (blockIdx.x * 256 + c < cols) {
+    atomicAdd(&dgamma[blockIdx.x * 256 + c], tg);
+    atomicAdd(&dbeta[blockIdx.x * 256 + c], tb);
   }
 }
 
@@ -176,12 +200,21 @@ static int ln_bwd_t(Ctx* ctx, const void* dy, const void* x, const float* gamma,
                     const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta, int rows, int cols,
                     cudaStream_t st) {
   const int nch = cdiv(cols, 256);
-  const int grid = min(cdiv(rows, 8), ctx->num_sms * 4);
-  const size_t smem = 2 * cols * sizeof(float);
+  const int grid = cdiv(rows, 8);
+  {  // parameter gradients first: dx may alias dy (in-place callers)
+    const int cb = cdiv(cols, 256);
+    int rb = (ctx->num_sms * 3) / cb;
+    if (rb < 1) rb = 1;
+    int rpb = cdiv(rows, rb);
+    rpb = ((rpb + 15) / 16) * 16;
+    dim3 g2(cb, cdiv(rows, rpb));
+    ln_bwd_param_kernel<T><<<g2, 256, 0, st>>>((const T*)dy, (const T*)x, mean, rstd, dgamma, dbeta, rows, cols, rpb);
+    TS_LAUNCH_OK(ctx);
+  }
 #define LN_BWD_CASE(N)                                                                                          \
   case N:                                                                                                       \
-    ln_bwd_kernel<T, N><<<grid, 256, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres,  \
-                                                 (T*)dx, dgamma, dbeta, rows, cols);                            \
+    ln_bwd_dx_kernel<T, N><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres,  \
+                                                 (T*)dx, rows, cols);                                           \
     break;
   switch (nch) {
     LN_BWD_CASE(1) LN_BWD_CASE(2) LN_BWD_CASE(3) LN_BWD_CASE(4) LN_BWD_CASE(5)
@@ -203,9 +236,22 @@ int layernorm_bwd(Ctx* ctx, int dt, const void* dy, const void* x, const float* 
 
 // ------------------------------------------------------------------------------------------------
 // GroupNorm (+ exact GELU)
-// thread <-> 8 consecutive channels of one row; TPR = C/8 threads per row, 256/TPR rows per block step.
+// thread <-> 8 consecutive channels of one row; TPR = C/8 threads per row, RPI = 256/TPR rows per block iteration.
+// Every thread keeps GN_UNROLL rows (independent 16-byte loads) in flight; the number of rows a block owns is chosen on
+// the host so that even the short last conv layers launch several blocks per SM (these kernels are HBM-bound on the
+// long layers and latency-bound on the short ones).
 // ------------------------------------------------------------------------------------------------
-constexpr int GN_ROWS_PER_BLOCK = 256;  // time rows handled by one block
+constexpr int GN_UNROLL = 2;
+
+static inline int gn_rows_per_block(Ctx* ctx, long long rows_per_batch, int B, int C) {
+  const int rpi = 256 / (C / 8);
+  const int step = rpi * GN_UNROLL;
+  long long want = (rows_per_batch * B) / ((long long)ctx->num_sms * 6);
+  long long rpb = ((want + step - 1) / step) * step;
+  if (rpb < step) rpb = step;
+  if (rpb > 256 && rpb > step) rpb = 256 >= step ? 256 : step;
+  return (int)rpb;
+}
 
 __global__ void gn_zero_accum(double* accum, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -213,8 +259,8 @@ __global__ void gn_zero_accum(double* accum, int n) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, double* __restrict__ accum, int T_,
-                                                       int C, int G, long long rpb) {
+__global__ void __launch_bounds__(256, 4) gn_stats_kernel(const T* __restrict__ x, double* __restrict__ accum, int T_,
+                                                       int C, int G, long long rpb, int rows_per_block) {
   __shared__ double sacc[64 * 2];
   const int b = blockIdx.y;
   const int tpr = C / 8, rpi = 256 / tpr;
@@ -223,14 +269,25 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, 
   for (int i = threadIdx.x; i < 2 * G; i += 256) sacc[i] = 0.0;
   __syncthreads();
   float s = 0.f, ss = 0.f;
-  const int t0 = blockIdx.x * GN_ROWS_PER_BLOCK;
-  const int t1 = min(T_, t0 + GN_ROWS_PER_BLOCK);
+  const int t0 = blockIdx.x * rows_per_block;
+  const int t1 = min(T_, t0 + rows_per_block);
   if (tr < rpi) {
-    for (int t = t0 + tr; t < t1; t += rpi) {
-      float v[8];
-      load8<T>(x + ((long long)b * rpb + t) * C + tc * 8, v);
+    const T* xb = x + (long long)b * rpb * C + tc * 8;
+    for (int t = t0 + tr; t < t1; t += rpi * GN_UNROLL) {
+      float v[GN_UNROLL][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { s += v[i]; ss += v[i] * v[i]; }
+      for (int u = 0; u < GN_UNROLL; ++u) {
+        const int tt = t + u * rpi;
+        if (tt < t1) load8<T>(xb + (long long)tt * C, v[u]);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < GN_UNROLL; ++u)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s += v[u][i]; ss += v[u][i] * v[u][i]; }
     }
     const int g = (tc * 8) / cpg;
     atomicAdd(&sacc[2 * g], (double)s);
@@ -256,20 +313,21 @@ int groupnorm_stats(Ctx* ctx, int dt, const void* x, double* accum, float* mean,
   TS_REQUIRE(ctx, C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0 && G <= 64 && C % G == 0 && (C / G) % 8 == 0,
              TS_ESHAPE, "groupnorm: unsupported C=%d G=%d", C, G);
   gn_zero_accum<<<cdiv(B * G * 2, 256), 256, 0, st>>>(accum, B * G * 2);
-  dim3 grid(cdiv(T_, GN_ROWS_PER_BLOCK), B);
-  if (dt == TS_F32) gn_stats_kernel<float><<<grid, 256, 0, st>>>((const float*)x, accum, T_, C, G, rpb);
-  else gn_stats_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, accum, T_, C, G, rpb);
+  const int rows = gn_rows_per_block(ctx, T_, B, C);
+  dim3 grid(cdiv(T_, rows), B);
+  if (dt == TS_F32) gn_stats_kernel<float><<<grid, 256, 0, st>>>((const float*)x, accum, T_, C, G, rpb, rows);
+  else gn_stats_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, accum, T_, C, G, rpb, rows);
   gn_finalize_kernel<<<cdiv(B * G, 256), 256, 0, st>>>(accum, mean, rstd, B * G, (double)T_ * (C / G), eps);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) gn_gelu_fwd_kernel(const T* __restrict__ x, long long x_rpb,
+__global__ void __launch_bounds__(256, 4) gn_gelu_fwd_kernel(const T* __restrict__ x, long long x_rpb,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           T* __restrict__ y, long long y_rpb, int y_left, int T_, int C,
-                                                          int G) {
+                                                          int G, int rows_per_block) {
   const int b = blockIdx.y;
   const int tpr = C / 8, rpi = 256 / tpr;
   const int tc = threadIdx.x % tpr, tr = threadIdx.x / tpr;
@@ -279,46 +337,103 @@ __global__ void __launch_bounds__(256) gn_gelu_fwd_kernel(const T* __restrict__ 
   float ga[8], be[8];
   load8<float>(gamma + tc * 8, ga);
   load8<float>(beta + tc * 8, be);
-  const long long r0 = (long long)blockIdx.x * GN_ROWS_PER_BLOCK;
-  const long long r1 = min(y_rpb, r0 + GN_ROWS_PER_BLOCK);
-  for (long long r = r0 + tr; r < r1; r += rpi) {
-    const long long t = r - y_left;
-    float o[8];
-    if (t >= 0 && t < T_) {
-      float v[8];
-      load8<T>(x + ((long long)b * x_rpb + t) * C + tc * 8, v);
+  // fold the normalisation into one FMA per element: u = x * a + c
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = gelu_f(ga[i] * ((v[i] - mu) * rs) + be[i]);
-    } else {
+  for (int i = 0; i < 8; ++i) { ga[i] *= rs; be[i] = fmaf(-mu, ga[i], be[i]); }
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(y_rpb, r0 + rows_per_block);
+  const T* xb = x + (long long)b * x_rpb * C + tc * 8;
+  T* yb = y + (long long)b * y_rpb * C + tc * 8;
+  for (long long r = r0 + tr; r < r1; r += rpi * GN_UNROLL) {
+    float v[GN_UNROLL][8];
+    bool in[GN_UNROLL];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = 0.f;
+    for (int u = 0; u < GN_UNROLL; ++u) {
+      const long long t = r + u * rpi - y_left;
+      in[u] = (r + u * rpi < r1) && t >= 0 && t < T_;
+      if (in[u]) load8<T>(xb + t * C, v[u]);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
+      }
     }
-    store8<T>(y + ((long long)b * y_rpb + r) * C + tc * 8, o);
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; ++u) {
+      if (r + u * rpi >= r1) break;
+      float o[8];
+      const float keep = in[u] ? 1.f : 0.f;   // rows outside [0, T) are zero padding for the next conv's windows
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = keep * gelu_t<T>(fmaf(v[u][i], ga[i], be[i]));
+      store8<T>(yb + (r + u * rpi) * C, o);
+    }
   }
 }
 
 int groupnorm_gelu_fwd(Ctx* ctx, int dt, const void* x, long long x_rpb, const float* mean, const float* rstd,
                        const float* gamma, const float* beta, void* y, long long y_rpb, int y_left, int B, int T_,
                        int C, int G, cudaStream_t st) {
-  dim3 grid(cdiv(y_rpb, GN_ROWS_PER_BLOCK), B);
+  const int rows = gn_rows_per_block(ctx, y_rpb, B, C);
+  dim3 grid(cdiv(y_rpb, rows), B);
   if (dt == TS_F32)
     gn_gelu_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, x_rpb, mean, rstd, gamma, beta, (float*)y, y_rpb,
-                                                    y_left, T_, C, G);
+                                                    y_left, T_, C, G, rows);
   else
     gn_gelu_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, x_rpb, mean, rstd, gamma, beta, (bf16*)y, y_rpb,
-                                                   y_left, T_, C, G);
+                                                   y_left, T_, C, G, rows);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) gn_gelu_bwd1_kernel(const T* __restrict__ da, long long da_rpb, Col2imSrc col,
-                                                           const T* __restrict__ x, long long x_rpb,
-                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           T* __restrict__ dx, long long dx_rpb, float* __restrict__ dgamma,
-                                                           float* __restrict__ dbeta, double* __restrict__ accum, int T_,
-                                                           int C, int G) {
+// gradient arriving at activation row t: dense `da`, or the col2im gather of the next strided conv's dcol
+// (da[b,t,c] = sum_j dcol[b, (t+left-j)/s, j*C + c] over taps j with (t+left-j) % s == 0 and a valid window index).
+// KS = k * 8 + s for the specialised (k, s) pairs of the Wav2Vec2 conv stacks; 0 = dense da; -1 = generic.
+template <typename T, int KS>
+__device__ __forceinline__ void gn_load_upstream(const T* __restrict__ da_row0, const T* __restrict__ dcol_b, const Col2imSrc& col,
+                                                 int t, int C, float (&d)[8]) {
+  if constexpr (KS == 0) {
+    load8<T>(da_row0 + (long long)t * C, d);
+  } else if constexpr (KS > 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = 0.f;
+    constexpr int K = KS >> 3, S = KS & 7;
+    const long long rowlen = (long long)K * C;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const int q = t + col.left - j;
+      const int w = q / S;   // S is a compile-time power of two here
+      if (q >= 0 && (q % S) == 0 && w < col.t_next) {
+        float v[8];
+        load8<T>(dcol_b + (long long)w * rowlen + (long long)j * C, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] += v[i];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = 0.f;
+    const long long rowlen = (long long)col.k * C;
+    for (int j = 0; j < col.k; ++j) {
+      const int q = t + col.left - j;
+      if (q < 0) break;
+      if (q % col.s) continue;
+      const int w = q / col.s;
+      if (w >= col.t_next) continue;
+      float v[8];
+      load8<T>(dcol_b + (long long)w * rowlen + (long long)j * C, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] += v[i];
+    }
+  }
+}
+
+template <typename T, int KS>
+__global__ void __launch_bounds__(256, 2) gn_gelu_bwd1_kernel(const T* __restrict__ da, long long da_rpb, Col2imSrc col,
+                                                              const T* __restrict__ x, long long x_rpb,
+                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              T* __restrict__ dx, long long dx_rpb, float* __restrict__ dgamma,
+                                                              float* __restrict__ dbeta, double* __restrict__ accum, int T_,
+                                                              int C, int G, int rows_per_block) {
   extern __shared__ float smf[];  // [2][C] floats then [2*G] doubles (8-byte aligned by construction)
   float* sg = smf;
   float* sb = smf + C;
@@ -331,49 +446,53 @@ __global__ void __launch_bounds__(256) gn_gelu_bwd1_kernel(const T* __restrict__
   for (int i = threadIdx.x; i < 2 * G; i += 256) sacc[i] = 0.0;
   __syncthreads();
   if (tr < rpi) {
-    const float mu = mean[b * G + g], rs = rstd[b * G + g];
+    const float rs = rstd[b * G + g], nmr = -mean[b * G + g] * rs;
     float ga[8], be[8], ag[8], ab[8];
     load8<float>(gamma + tc * 8, ga);
     load8<float>(beta + tc * 8, be);
 #pragma unroll
     for (int i = 0; i < 8; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
-    float s1 = 0.f, s2 = 0.f;
-    const int t0 = blockIdx.x * GN_ROWS_PER_BLOCK, t1 = min(T_, t0 + GN_ROWS_PER_BLOCK);
-    const T* dcol = reinterpret_cast<const T*>(col.dcol);
-    for (int t = t0 + tr; t < t1; t += rpi) {
-      float d[8];
-      if (dcol) {
+    const int t0 = blockIdx.x * rows_per_block, t1 = min(T_, t0 + rows_per_block);
+    const T* da_b = KS == 0 ? da + (long long)b * da_rpb * C + tc * 8 : nullptr;
+    const T* dcol_b = KS == 0 ? nullptr
+                              : reinterpret_cast<const T*>(col.dcol) + (long long)b * col.rows_per_batch * ((long long)col.k * C) + tc * 8;
+    const T* xb = x + (long long)b * x_rpb * C + tc * 8;
+    T* dxb = dx + (long long)b * dx_rpb * C + tc * 8;
+    for (int t = t0 + tr; t < t1; t += rpi * GN_UNROLL) {
+      float d[GN_UNROLL][8], v[GN_UNROLL][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] = 0.f;
-        for (int j = 0; j < col.k; ++j) {
-          const int q = t + col.left - j;
-          if (q >= 0 && (q % col.s) == 0 && (q / col.s) < col.t_next) {
-            float v[8];
-            load8<T>(dcol + ((long long)b * col.rows_per_batch + q / col.s) * ((long long)col.k * C) + (long long)j * C + tc * 8, v);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) d[i] += v[i];
-          }
+      for (int u = 0; u < GN_UNROLL; ++u) {
+        const int tt = t + u * rpi;
+        if (tt < t1) {
+          gn_load_upstream<T, KS>(da_b, dcol_b, col, tt, C, d[u]);
+          load8<T>(xb + (long long)tt * C, v[u]);
         }
-      } else {
-        load8<T>(da + ((long long)b * da_rpb + t) * C + tc * 8, d);
       }
-      float v[8], o[8];
-      load8<T>(x + ((long long)b * x_rpb + t) * C + tc * 8, v);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float xh = (v[i] - mu) * rs;
-        const float u = ga[i] * xh + be[i];
-        const float dact = d[i] * gelu_grad_f(u);
-        o[i] = dact;
-        ag[i] += dact * xh;
-        ab[i] += dact;
-        s1 += dact * ga[i];
-        s2 += dact * ga[i] * xh;
+      for (int u = 0; u < GN_UNROLL; ++u) {
+        const int tt = t + u * rpi;
+        if (tt >= t1) break;
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = fmaf(v[u][i], rs, nmr);
+          const float dact = d[u][i] * gelu_grad_t<T>(fmaf(ga[i], xh, be[i]));
+          o[i] = dact;
+          ag[i] = fmaf(dact, xh, ag[i]);
+          ab[i] += dact;
+        }
+        store8<T>(dxb + (long long)tt * C, o);
       }
-      store8<T>(dx + ((long long)b * dx_rpb + t) * C + tc * 8, o);
     }
+    // group sums for pass 2 follow from the per-channel sums: sum(dact*gamma) and sum(dact*gamma*xhat)
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { atomicAdd(&sg[tc * 8 + i], ag[i]); atomicAdd(&sb[tc * 8 + i], ab[i]); }
+    for (int i = 0; i < 8; ++i) {
+      s1 = fmaf(ga[i], ab[i], s1);
+      s2 = fmaf(ga[i], ag[i], s2);
+      atomicAdd(&sg[tc * 8 + i], ag[i]);
+      atomicAdd(&sb[tc * 8 + i], ab[i]);
+    }
     atomicAdd(&sacc[2 * g], (double)s1);
     atomicAdd(&sacc[2 * g + 1], (double)s2);
   }
@@ -383,11 +502,11 @@ __global__ void __launch_bounds__(256) gn_gelu_bwd1_kernel(const T* __restrict__
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) gn_gelu_bwd2_kernel(const T* __restrict__ x, long long x_rpb,
+__global__ void __launch_bounds__(256, 4) gn_gelu_bwd2_kernel(const T* __restrict__ x, long long x_rpb,
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            const float* __restrict__ gamma, T* __restrict__ dx,
                                                            long long dx_rpb, const double* __restrict__ accum, int T_, int C,
-                                                           int G) {
+                                                           int G, int rows_per_block) {
   const int b = blockIdx.y;
   const int tpr = C / 8, rpi = 256 / tpr;
   const int tc = threadIdx.x % tpr, tr = threadIdx.x / tpr;
@@ -398,24 +517,33 @@ __global__ void __launch_bounds__(256) gn_gelu_bwd2_kernel(const T* __restrict__
   const float m1 = (float)(accum[((long long)b * G + g) * 2] / n), m2 = (float)(accum[((long long)b * G + g) * 2 + 1] / n);
   float ga[8];
   load8<float>(gamma + tc * 8, ga);
-  const long long r0 = (long long)blockIdx.x * GN_ROWS_PER_BLOCK, r1 = min(dx_rpb, r0 + GN_ROWS_PER_BLOCK);
-  for (long long t = r0 + tr; t < r1; t += rpi) {
-    float o[8];
-    T* p = dx + ((long long)b * dx_rpb + t) * C + tc * 8;
-    if (t < T_) {
-      float v[8], d[8];
-      load8<T>(x + ((long long)b * x_rpb + t) * C + tc * 8, v);
-      load8<T>(p, d);
+  const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(dx_rpb, r0 + rows_per_block);
+  const T* xb = x + (long long)b * x_rpb * C + tc * 8;
+  T* db = dx + (long long)b * dx_rpb * C + tc * 8;
+  for (long long t = r0 + tr; t < r1; t += rpi * GN_UNROLL) {
+    float v[GN_UNROLL][8], d[GN_UNROLL][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float xh = (v[i] - mu) * rs;
-        o[i] = rs * (d[i] * ga[i] - m1 - xh * m2);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = 0.f;
+    for (int u = 0; u < GN_UNROLL; ++u) {
+      const long long tt = t + u * rpi;
+      if (tt < r1 && tt < T_) { load8<T>(xb + tt * C, v[u]); load8<T>(db + tt * C, d[u]); }
     }
-    store8<T>(p, o);
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; ++u) {
+      const long long tt = t + u * rpi;
+      if (tt >= r1) break;
+      float o[8];
+      if (tt < T_) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (v[u][i] - mu) * rs;
+          o[i] = rs * (d[u][i] * ga[i] - m1 - xh * m2);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = 0.f;
+      }
+      store8<T>(db + tt * C, o);
+    }
   }
 }
 
@@ -427,18 +555,25 @@ int groupnorm_gelu_bwd(Ctx* ctx, int dt, const void* da, long long da_rpb, const
   if (col) c = *col; else { c.dcol = nullptr; c.rows_per_batch = 0; c.t_next = 0; c.k = 0; c.s = 1; c.left = 0; }
   gn_zero_accum<<<cdiv(B * G * 2, 256), 256, 0, st>>>(accum, B * G * 2);
   const size_t smem = 2 * C * sizeof(float) + 2 * G * sizeof(double);
-  dim3 g1(cdiv(T_, GN_ROWS_PER_BLOCK), B), g2(cdiv(dx_rpb, GN_ROWS_PER_BLOCK), B);
+  const int rows1 = gn_rows_per_block(ctx, T_, B, C), rows2 = gn_rows_per_block(ctx, dx_rpb, B, C);
+  dim3 g1(cdiv(T_, rows1), B), g2(cdiv(dx_rpb, rows2), B);
+  int ks = -1;
+  if (!c.dcol) ks = 0;
+  else if (c.k == 3 && c.s == 2) ks = 3 * 8 + 2;
+  else if (c.k == 2 && c.s == 2) ks = 2 * 8 + 2;
+#define GN_BWD1(TT, KS)                                                                                                   \
+  gn_gelu_bwd1_kernel<TT, KS><<<g1, 256, smem, st>>>((const TT*)da, da_rpb, c, (const TT*)x, x_rpb, mean, rstd, gamma, beta, \
+                                                     (TT*)dx, dx_rpb, dgamma, dbeta, accum, T_, C, G, rows1)
   if (dt == TS_F32) {
-    gn_gelu_bwd1_kernel<float><<<g1, 256, smem, st>>>((const float*)da, da_rpb, c, (const float*)x, x_rpb, mean, rstd,
-                                                      gamma, beta, (float*)dx, dx_rpb, dgamma, dbeta, accum, T_, C, G);
+    if (ks == 0) GN_BWD1(float, 0); else if (ks == 26) GN_BWD1(float, 26); else if (ks == 18) GN_BWD1(float, 18); else GN_BWD1(float, -1);
     gn_gelu_bwd2_kernel<float><<<g2, 256, 0, st>>>((const float*)x, x_rpb, mean, rstd, gamma, (float*)dx, dx_rpb, accum,
-                                                   T_, C, G);
+                                                   T_, C, G, rows2);
   } else {
-    gn_gelu_bwd1_kernel<bf16><<<g1, 256, smem, st>>>((const bf16*)da, da_rpb, c, (const bf16*)x, x_rpb, mean, rstd, gamma,
-                                                     beta, (bf16*)dx, dx_rpb, dgamma, dbeta, accum, T_, C, G);
+    if (ks == 0) GN_BWD1(bf16, 0); else if (ks == 26) GN_BWD1(bf16, 26); else if (ks == 18) GN_BWD1(bf16, 18); else GN_BWD1(bf16, -1);
     gn_gelu_bwd2_kernel<bf16><<<g2, 256, 0, st>>>((const bf16*)x, x_rpb, mean, rstd, gamma, (bf16*)dx, dx_rpb, accum, T_,
-                                                  C, G);
+                                                  C, G, rows2);
   }
+#undef GN_BWD1
   TS_LAUNCH_OK(ctx);
   return 0;
 }

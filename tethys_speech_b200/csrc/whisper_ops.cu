@@ -171,7 +171,7 @@ __global__ void gelu_bwd_rows_kernel(const T* __restrict__ da, long long da_rpb,
       }
       load8<T>(u + r * C + c, uv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = d[j] * gelu_grad_f(uv[j]);
+      for (int j = 0; j < 8; ++j) o[j] = d[j] * gelu_grad_t<T>(uv[j]);
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = 0.f;
