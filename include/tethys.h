@@ -127,6 +127,32 @@ typedef struct {
 int ts_attn_fwd(ts_ctx* ctx, const ts_attn_desc* d, void* stream);
 int ts_attn_bwd(ts_ctx* ctx, const ts_attn_desc* d, void* stream);
 
+/* ---- K1: log-mel front end ---------------------------------------------------------------------------------------
+ * Replaces extract_fbank_features (W:739-766): tf.signal.stft(x, 400, 160, fft_length=400) (periodic Hann, no end padding),
+ * power, tf.signal.linear_to_mel_weight_matrix(80, 201, 16000, 0, 8000), log(mel + 1e-6). One kernel; fp32 arithmetic.
+ * wave [batch, n_samples] fp32 with batch stride `wave_batch_stride` (elements); frames F = ts_logmel_num_frames(n_samples).
+ * out: [batch, F, 80] (mel_major = 0, the reference's return layout) or [batch, 80, F] (mel_major = 1, the layout
+ * WhisperEncoder.call consumes, W:326-329); out_dtype TS_F32 or TS_BF16.
+ */
+int ts_logmel_num_frames(int n_samples);
+int ts_logmel(ts_ctx* ctx, const float* wave, int64_t wave_batch_stride, int batch, int n_samples, void* out, int out_dtype,
+              int mel_major, void* stream);
+
+/* ---- K11 / K5: normalisation layers as single operators ---------------------------------------------------------------
+ * ts_layernorm_fwd/bwd: tf.keras.layers.LayerNormalization(epsilon=1e-5) over the last axis of x [rows, cols]
+ *   (W:214,216,245,249,253,322,392; V:280,411,415,554,778). dtype = TS_F32 | TS_BF16 for x / y / dy / dx; gamma, beta,
+ *   mean, rstd and the parameter gradients are fp32. bwd ADDS into dgamma / dbeta; dres (optional) is added to dx.
+ * ts_groupnorm_gelu_fwd: GroupNormalization(groups) + exact-erf GELU of the conv feature encoder (V:132-196, V:248-249) on
+ *   x [batch, T, C]: statistics over (T, C/groups) per (batch, group); writes mean/rstd [batch, groups] and y = gelu(gn(x)).
+ *   accum is scratch of 2 * batch * groups doubles.
+ */
+int ts_layernorm_fwd(ts_ctx* ctx, int dtype, const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                     int rows, int cols, float eps, void* stream);
+int ts_layernorm_bwd(ts_ctx* ctx, int dtype, const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                     const void* dres, void* dx, float* dgamma, float* dbeta, int rows, int cols, void* stream);
+int ts_groupnorm_gelu_fwd(ts_ctx* ctx, int dtype, const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                          float* rstd, double* accum, int batch, int t, int c, int groups, float eps, void* stream);
+
 /* ---- K19/K20: gradient clipping + Keras-2.10 legacy Adam over a flat arena ------------------------
  * Replaces tf.clip_by_global_norm (V:1243, VS:1171), the optimizer's clipnorm=1.0 (V:1274, VS:1206) and
  * tf.keras.optimizers.Adam.apply_gradients (W:834, V:1246, VS:1174, WS:1179) minus its all-reduce.

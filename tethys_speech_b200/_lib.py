@@ -93,6 +93,11 @@ SYMBOLS = {
     "ts_gemm": (_I, [_P, C.POINTER(GemmDesc), _P]),
     "ts_attn_fwd": (_I, [_P, C.POINTER(AttnDesc), _P]),
     "ts_attn_bwd": (_I, [_P, C.POINTER(AttnDesc), _P]),
+    "ts_logmel_num_frames": (_I, [_I]),
+    "ts_logmel": (_I, [_P, _P, _L, _I, _I, _P, _I, _I, _P]),
+    "ts_layernorm_fwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P]),
+    "ts_layernorm_bwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "ts_groupnorm_gelu_fwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "ts_optim_create": (_I, [_P, _I, C.POINTER(_L), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L), _L, C.POINTER(_P)]),
     "ts_optim_destroy": (None, [_P]),
     "ts_optim_clip_global": (_I, [_P, _P, _F, _P, _P]),

@@ -1,6 +1,7 @@
 // C-ABI: context lifecycle, error reporting, GEMM dispatch.
 #include <stdarg.h>
 #include "common.cuh"
+#include "ops.cuh"
 
 namespace ts {
 
@@ -86,6 +87,28 @@ int ts_watchdog_check(ts_ctx* ctx) {
 int64_t ts_launch_count(ts_ctx* ctx) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   return c ? (int64_t)c->launches : 0;
+}
+
+int ts_layernorm_fwd(ts_ctx* ctx, int dtype, const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                     int rows, int cols, float eps, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c) return TS_EINVAL;
+  return ts::layernorm_fwd(c, dtype, x, nullptr, gamma, beta, y, nullptr, mean, rstd, rows, cols, eps, reinterpret_cast<cudaStream_t>(stream));
+}
+int ts_layernorm_bwd(ts_ctx* ctx, int dtype, const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                     const void* dres, void* dx, float* dgamma, float* dbeta, int rows, int cols, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c) return TS_EINVAL;
+  return ts::layernorm_bwd(c, dtype, dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, cols, reinterpret_cast<cudaStream_t>(stream));
+}
+int ts_groupnorm_gelu_fwd(ts_ctx* ctx, int dtype, const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                          float* rstd, double* accum, int batch, int t, int ch, int groups, float eps, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c) return TS_EINVAL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = ts::groupnorm_stats(c, dtype, x, accum, mean, rstd, batch, t, ch, groups, t, eps, st);
+  if (rc) return rc;
+  return ts::groupnorm_gelu_fwd(c, dtype, x, t, mean, rstd, gamma, beta, y, t, 0, batch, t, ch, groups, st);
 }
 
 int ts_gemm(ts_ctx* ctx, const ts_gemm_desc* d, void* stream) {

@@ -75,6 +75,11 @@ bool attn_tc_supported(const ts_attn_desc* d);
 int attn_fwd(Ctx*, const ts_attn_desc* d, cudaStream_t);
 int attn_bwd(Ctx*, const ts_attn_desc* d, cudaStream_t);
 
+// ---- logmel.cu: K1 log-mel front end (W:739-766) ------------------------------------------------------
+// wave [batch, n_samples] fp32 (batch stride wave_bs) -> log-mel [batch, F, 80] (mel_major = 0) or [batch, 80, F] (1)
+int logmel(Ctx*, const float* wave, long long wave_bs, int batch, int n_samples, void* out, int out_dtype, int mel_major,
+           int sample_rate, int n_mels, int n_fft, int hop, cudaStream_t);
+
 // ---- vq.cu / contrastive.cu ----------------------------------------------------------------------
 // hard VQ (V:604-660): z [M, G*D] (act dtype), codebook fp32 [G,V,D]; writes q [M, G*D], idx int64 [G,M],
 // hist int32 [G,V] (+=), then perplexity (fp32 scalar) via vq_perplexity.
