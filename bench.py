@@ -29,12 +29,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (model_size, samples, seconds, train GFLOP/sample)
-    "w2v_base_15s": ("base", 240000, 15.0, 679.4),
-    "w2v_base_5s": ("base", 80000, 5.0, 212.7),
-    "w2v_base_2s": ("base", 32000, 2.0, 83.4),
-    "w2v_tiny_2s": ("tiny", 32000, 2.0, 25.6),
+    # name: (family, model_size, samples (w2v) / mel frames (whisper), audio seconds, train GFLOP/sample)
+    "w2v_base_15s": ("w2v", "base", 240000, 15.0, 679.4),     # BASELINE.json configs[1] — the default
+    "w2v_base_5s": ("w2v", "base", 80000, 5.0, 212.7),        # configs[0] as the reference file literally is
+    "w2v_base_2s": ("w2v", "base", 32000, 2.0, 83.4),
+    "w2v_tiny_2s": ("w2v", "tiny", 32000, 2.0, 25.6),
+    "whisper_small_30s": ("whisper", "small", 3000, 30.0, 449.1),   # configs[0] as BASELINE intends (1a): CLI default preset
+    "whisper_base_30s": ("whisper", "base", 3000, 30.0, 325.5),     # configs[2]
 }
+DEFAULT_BATCH = {"w2v": 8, "whisper": 4}
 
 
 def measured_peaks():
@@ -98,26 +101,40 @@ class ClockSampler:
 # reference arm / cpu baseline: the oracle's train step on host cores
 # ------------------------------------------------------------------------------------------------------------
 def cpu_step_throughput(workload, steps, warmup, max_seconds=150.0):
+    """The oracle's PyTorch-CPU fp32 restatement of the same train step on all host cores, batch 1 (bounded sample)."""
+    import numpy as np
     import torch
-    from oracle import wav2vec2_oracle as O
 
-    size, n_samples, secs, _ = WORKLOADS[workload]
+    family, size, n_samples, secs, _ = WORKLOADS[workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = O.Wav2Vec2Config(size)
+    g = torch.Generator().manual_seed(1234)
+    B = 1
+    if family == "w2v":
+        from oracle import wav2vec2_oracle as O
+        cfg = O.Wav2Vec2Config(size)
+        T = O.num_frames(cfg, n_samples)
+
+        def make():
+            wave = torch.randn(B, n_samples, generator=g)
+            neg = O.negative_indices_from_random(torch.randint(0, T, (B, T), generator=g), cfg.num_negatives)
+            return wave, neg
+    else:
+        from oracle import whisper_oracle as O
+        cfg = O.WhisperConfig(size)
+        rng = np.random.default_rng(1234)
+
+        def make():
+            return torch.randn(B, cfg.n_mels, n_samples, generator=g), O.dummy_labels(rng, B, 100)
     w = O.init_weights(cfg, seed=0, dtype=torch.float32)
     m = {k: torch.zeros_like(v) for k, v in w.items()}
     v = {k: torch.zeros_like(v_) for k, v_ in w.items()}
-    g = torch.Generator().manual_seed(1234)
-    B = 1
-    T = O.num_frames(cfg, n_samples)
     times = []
     t_all = time.perf_counter()
     for it in range(warmup + steps):
-        wave = torch.randn(B, n_samples, generator=g)
-        neg = O.negative_indices_from_random(torch.randint(0, T, (B, T), generator=g), cfg.num_negatives)
+        a, b = make()
         t0 = time.perf_counter()
-        O.train_step(cfg, w, m, v, it + 1, wave, neg)
+        O.train_step(cfg, w, m, v, it + 1, a, b)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
@@ -142,13 +159,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    size, n_samples, secs, gflop = WORKLOADS[args.workload]
+    family, size, n_samples, secs, gflop = WORKLOADS[args.workload]
     r = cpu_step_throughput(args.workload, max(1, min(args.steps, 3)), min(args.warmup, 1))
     line = {"impl": "reference", "metric": "train_samples_per_sec", "value": r["value"], "unit": "samples/s",
             "audio_sec_per_sec": r["value"] * secs, "n_gpus": args.gpus, "steps": r["steps_timed"], "warmup": min(args.warmup, 1),
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "model": f"wav2vec2-{size}", "audio_seconds": secs, "batch_per_step": 1,
+            "config": {"workload": args.workload, "model": f"{'wav2vec2' if family == 'w2v' else 'whisper'}-{size}", "audio_seconds": secs, "batch_per_step": 1,
                        "note": "reference arm = CPU restatement of the reference's TF step on host cores (rank 0 only)"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -159,51 +176,149 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------
-def time_dominant_gemm(ctx, M, N, K, iters=20):
-    """Time the workload's dominant GEMM (FFN fc1: [M,K]x[K,N] + bias + GELU, bf16) alone with CUDA events on the
-    launching stream, flushing L2 between launches."""
-    import ctypes as C
-
+def _timed(fn, flush, iters=10, warm=3):
+    """Average CUDA-event time (s) of fn() on the current stream, L2 flushed (256 MB memset) between launches."""
     import torch
-    from tethys_speech_b200 import _lib
-    from tethys_speech_b200.runtime import ptr, stream_ptr
 
-    dev = torch.device("cuda", ctx.device)
-    a = torch.randn(M, K, device=dev).bfloat16()
-    b = (torch.randn(K, N, device=dev) * 0.05).bfloat16()
-    bias = torch.zeros(N, device=dev)
-    c = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-    pre = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    d = _lib.GemmDesc()
-    d.a, d.b, d.c = a.data_ptr(), b.data_ptr(), c.data_ptr()
-    d.m, d.n, d.k = M, N, K
-    d.a_major, d.b_major = 0, 1
-    d.lda, d.ldb, d.ldc = K, N, N
-    d.batch1 = d.batch2 = 1
-    d.in_dtype = d.out_dtype = _lib.TS_BF16
-    d.alpha = 1.0
-    d.bias = bias.data_ptr()
-    d.act = 1
-    d.c_preact = pre.data_ptr()
-    for _ in range(3):
-        ctx.check(ctx.lib.ts_gemm(ctx.h, C.byref(d), stream_ptr()))
+    for _ in range(warm):
+        fn()
     total = 0.0
     for _ in range(iters):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ctx.check(ctx.lib.ts_gemm(ctx.h, C.byref(d), stream_ptr()))
+        fn()
         e1.record()
         e1.synchronize()
         total += e0.elapsed_time(e1)
     return total / iters * 1e-3
 
 
-def run_ours(args):
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` summary, or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_kernel_summary.json")
+    try:
+        return json.load(open(p)).get(key, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def kernel_rooflines(ctx, peaks, B, T, H, F, nh, n_params):
+    """Live per-kernel roofline fractions at this workload's shapes, each kernel timed alone through the C-ABI.
+    Tensor-bound kernels: algorithmic FLOPs / time vs the measured cuBLAS bf16 burst peak. HBM-bound kernels: algorithmic
+    bytes (every distinct tensor once in, once out — SURVEY §8d) / time vs the measured copy bandwidth."""
+    import ctypes as C
+
     import torch
-    from tethys_speech_b200 import wav2vec2 as W
-    from tethys_speech_b200.runtime import Strategy
+    from tethys_speech_b200 import _lib
+    from tethys_speech_b200.runtime import stream_ptr
+
+    dev = torch.device("cuda", ctx.device)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    M = B * T
+    out = []
+    bf = torch.bfloat16
+
+    def P(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+    def gemm(name, m, n, k, a_major, b_major, out_f32=False, bias=False, act=0, preact=False, res=False, drop=0.0, acc=False,
+             lda=None, key=None):
+        a_rows, a_cols = (m, k) if a_major == 0 else (k, m)
+        b_rows, b_cols = (n, k) if b_major == 0 else (k, n)
+        lda_ = lda or a_cols
+        a = (torch.randn((a_rows - 1) * lda_ + a_cols + 64, device=dev) * 0.5).to(bf)
+        bmat = (torch.randn(b_rows, b_cols, device=dev) * 0.05).to(bf)
+        c = torch.zeros(m, n, device=dev, dtype=torch.float32 if out_f32 else bf)
+        d = _lib.GemmDesc()
+        d.a, d.b, d.c = a.data_ptr(), bmat.data_ptr(), c.data_ptr()
+        d.m, d.n, d.k, d.a_major, d.b_major = m, n, k, a_major, b_major
+        d.lda, d.ldb, d.ldc = lda_, b_cols, n
+        d.batch1 = d.batch2 = 1
+        d.in_dtype, d.out_dtype, d.alpha = _lib.TS_BF16, (_lib.TS_F32 if out_f32 else _lib.TS_BF16), 1.0
+        keep = [a, bmat, c]
+        if bias:
+            bv = torch.zeros(n, device=dev); d.bias = bv.data_ptr(); keep.append(bv)
+        if preact:
+            pv = torch.empty_like(c); d.c_preact = pv.data_ptr(); keep.append(pv)
+        if res:
+            rv = torch.zeros_like(c); d.residual = rv.data_ptr(); d.ldr = n; keep.append(rv)
+        d.act, d.drop, d.seed, d.accumulate = act, drop, 7, 1 if acc else 0
+        t = _timed(lambda: ctx.check(ctx.lib.ts_gemm(ctx.h, C.byref(d), stream_ptr())), flush)
+        tf = 2.0 * m * n * k / t / 1e12
+        out.append({"kernel": name, "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": tf / peaks["bf16_tflops"], "us": t * 1e6, "traffic": ncu_traffic(key) if key else None})
+        return out[-1]
+
+    dominant = gemm(f"gemm_tc_kernel FFN fc1 {M}x{F}x{H} +bias+GELU+dropout (W:194-195 / V:391-393)", M, F, H, 0, 1, bias=True, act=1,
+                    preact=True, drop=0.1, key="gemm_ffn1")
+    gemm(f"gemm_tc_kernel FFN fc2 {M}x{H}x{F} +bias+dropout+residual", M, H, F, 0, 1, bias=True, res=True, drop=0.1)
+    gemm(f"gemm_tc_kernel QKV {M}x{3 * H}x{H} +bias", M, 3 * H, H, 0, 1, bias=True)
+    gemm(f"gemm_tc_kernel dgrad {M}x{H}x{F}", M, H, F, 0, 0)
+    gemm(f"gemm_tc_kernel wgrad {H}x{F}x{M} fp32 split-K", H, F, M, 1, 1, out_f32=True, acc=True)
+    gemm(f"gemm_tc_kernel conv1 window-GEMM {B * 24000}x512x1536 (k3 s2, no im2col; V:254-268)", B * 24000, 512, 1536, 0, 1, lda=1024)
+
+    # fused attention
+    qkv = (torch.randn(B, T, 3 * H, device=dev)).to(bf)
+    o = torch.empty(B, T, H, device=dev, dtype=bf); olo = torch.empty_like(o)
+    do = torch.randn(B, T, H, device=dev).to(bf)
+    dqkv = torch.empty_like(qkv)
+    stats = torch.empty(B, nh, T, 2, device=dev); dsum = torch.empty(B, nh, T, device=dev)
+    a = _lib.AttnDesc()
+    a.q, a.k, a.v, a.o, a.o_lo = qkv.data_ptr(), qkv.data_ptr() + 2 * H, qkv.data_ptr() + 4 * H, o.data_ptr(), olo.data_ptr()
+    a.q_ld = a.kv_ld = 3 * H; a.q_bs = a.kv_bs = T * 3 * H; a.o_ld = H; a.o_bs = T * H
+    a.stats = stats.data_ptr(); a.batch, a.heads, a.tq, a.tk, a.head_dim = B, nh, T, T, H // nh
+    a.scale, a.mask_mode, a.drop, a.seed = 0.125, 0, 0.1, 3
+    a.d_o, a.dq, a.dk, a.dv = do.data_ptr(), dqkv.data_ptr(), dqkv.data_ptr() + 2 * H, dqkv.data_ptr() + 4 * H
+    a.dq_ld = a.dkv_ld = 3 * H; a.dq_bs = a.dkv_bs = T * 3 * H; a.dsum = dsum.data_ptr()
+    fl = 4.0 * B * nh * T * T * (H // nh)
+    t = _timed(lambda: ctx.check(ctx.lib.ts_attn_fwd(ctx.h, C.byref(a), stream_ptr())), flush)
+    out.append({"kernel": f"attn_fwd_kernel B{B} H{nh} T{T} hd64 dropout 0.1 (V:348-362)", "bound": "tensor", "achieved": fl / t / 1e12,
+                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": fl / t / 1e12 / peaks["bf16_tflops"], "us": t * 1e6,
+                "traffic": ncu_traffic("attn_fwd")})
+    t = _timed(lambda: ctx.check(ctx.lib.ts_attn_bwd(ctx.h, C.byref(a), stream_ptr())), flush)
+    out.append({"kernel": "attn_bwd_dq_kernel + attn_bwd_dkv_kernel (same shape; 2x forward FLOPs counted, recompute not)", "bound": "tensor",
+                "achieved": 2 * fl / t / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": 2 * fl / t / 1e12 / peaks["bf16_tflops"],
+                "us": t * 1e6, "traffic": None})
+
+    def hbm(name, nbytes, fn, key=None):
+        t = _timed(fn, flush)
+        gbs = nbytes / t / 1e9
+        out.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                    "us": t * 1e6, "traffic": ncu_traffic(key) if key else None})
+
+    # LayerNorm fwd / bwd on [M, H] bf16
+    x = torch.randn(M, H, device=dev).to(bf); y = torch.empty_like(x); dy = torch.randn(M, H, device=dev).to(bf); dx = torch.empty_like(x)
+    gam = torch.ones(H, device=dev); bet = torch.zeros(H, device=dev); mean = torch.empty(M, device=dev); rstd = torch.empty(M, device=dev)
+    dg = torch.zeros(H, device=dev); db = torch.zeros(H, device=dev)
+    hbm(f"ln_fwd_kernel [{M},{H}] bf16 (V:411)", 2.0 * M * H * 2,
+        lambda: ctx.check(ctx.lib.ts_layernorm_fwd(ctx.h, _lib.TS_BF16, P(x), P(gam), P(bet), P(y), P(mean), P(rstd), M, H, 1e-5, stream_ptr())))
+    hbm(f"ln_bwd_dx_kernel + ln_bwd_param_kernel [{M},{H}] bf16", 3.0 * M * H * 2,
+        lambda: ctx.check(ctx.lib.ts_layernorm_bwd(ctx.h, _lib.TS_BF16, P(dy), P(x), P(gam), P(mean), P(rstd), None, P(dx), P(dg), P(db), M, H,
+                                                   stream_ptr())))
+    # GroupNorm + GELU forward on the conv0 output [B, 48000, 512] bf16 (the largest activation of the step)
+    T0 = 48000
+    xg = torch.randn(B, T0, 512, device=dev).to(bf); yg = torch.empty_like(xg)
+    gmean = torch.empty(B, 16, device=dev); grstd = torch.empty(B, 16, device=dev); acc = torch.zeros(2 * B * 16, dtype=torch.float64, device=dev)
+    g512 = torch.ones(512, device=dev); b512 = torch.zeros(512, device=dev)
+    hbm(f"gn_stats_kernel + gn_gelu_fwd_kernel [{B},{T0},512] bf16 (V:140-196, V:248-249; x read twice: 3 passes of {B * T0 * 512 * 2 / 1e6:.0f} MB)",
+        3.0 * B * T0 * 512 * 2,
+        lambda: ctx.check(ctx.lib.ts_groupnorm_gelu_fwd(ctx.h, _lib.TS_BF16, P(xg), P(g512), P(b512), P(yg), P(gmean), P(grstd), P(acc), B, T0,
+                                                        512, 16, 1e-5, stream_ptr())), key="gn_gelu_fwd")
+    del xg, yg
+    # log-mel front end, B x 30 s
+    wav = torch.randn(B, 480000, device=dev)
+    nf = ctx.lib.ts_logmel_num_frames(480000)
+    mel = torch.empty(B, 80, nf, device=dev)
+    hbm(f"logmel_kernel [{B} x 30 s] fp32 (W:739-766)", B * (480000 * 4.0 + 80 * nf * 4.0),
+        lambda: ctx.check(ctx.lib.ts_logmel(ctx.h, P(wav), 480000, B, 480000, P(mel), _lib.TS_F32, 1, stream_ptr())), key="logmel")
+    return dominant, out
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    from tethys_speech_b200.runtime import Adam, Strategy
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -211,28 +326,55 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py (our arm) needs a B200; there is no CPU fallback"
     torch.cuda.set_device(local)
     strategy = Strategy()
-    size, n_samples, secs, gflop = WORKLOADS[args.workload]
-    B = args.batch
+    family, size, n_samples, secs, gflop = WORKLOADS[args.workload]
+    B = args.batch or DEFAULT_BATCH[family]
     dev = torch.device("cuda", local)
-
-    cfg = W.Wav2Vec2Config(size)
-    model = W.Wav2Vec2ForPreTraining(cfg, precision=args.precision, device=local, seed=0)
-    model.broadcast_weights(strategy)
-    opt = W.Adam(learning_rate=3e-5, epsilon=1e-8, clipnorm=1.0)
-    ctx = model._prog.ctx
-
-    # synthetic data: N(0,1) waveforms, rng = default_rng(1234 + rank); a pool of distinct batches
-    import numpy as np
-
     rng = np.random.default_rng(1234 + rank)
     npool = 4
-    host = [torch.from_numpy(rng.standard_normal((B, n_samples), dtype=np.float32)).pin_memory() for _ in range(npool)]
-    resident = [h.to(dev) for h in host]
+    if family == "w2v":
+        from tethys_speech_b200 import wav2vec2 as W
 
-    def step(features):
-        if world > 1:
-            return W.distributed_train_step(strategy, model, (features, None), opt)
-        return W.train_step(model, (features, None), opt)
+        cfg = W.Wav2Vec2Config(size)
+        model = W.Wav2Vec2ForPreTraining(cfg, precision=args.precision, device=local, seed=0)
+        opt = Adam(learning_rate=3e-5, epsilon=1e-8, clipnorm=1.0)
+        host = [(torch.from_numpy(rng.standard_normal((B, n_samples), dtype=np.float32)).pin_memory(), None) for _ in range(npool)]
+        h2d = B * n_samples * 4
+        step_desc = ("VS:1119-1176 (clip_by_global_norm 1.0 + clipnorm 1.0 + Keras-legacy Adam 3e-5)" if world == 1
+                     else "V:1186-1260 (loss/N, local clip, NCCL all-reduce SUM, clipnorm, Adam)")
+
+        def step(batch):
+            if world > 1:
+                return W.distributed_train_step(strategy, model, batch, opt)
+            return W.train_step(model, batch, opt)
+        T = model.num_frames(n_samples)
+        H, F, nh = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads
+        model_name = f"wav2vec2-{size}"
+    else:
+        from tethys_speech_b200 import whisper as W
+
+        model = W.create_whisper_model(size, precision=args.precision, device=local, seed=0)
+        cfg = model.config
+        opt = Adam(learning_rate=1e-4)
+        labels = np.zeros((B, 100), dtype=np.int32)
+        for i in range(B):
+            n = int(rng.integers(50, 90))
+            labels[i, 0] = 1; labels[i, 1:n - 1] = rng.integers(3, 100, size=n - 2); labels[i, n - 1] = 2
+        host = [(torch.from_numpy(rng.standard_normal((B, 80, n_samples), dtype=np.float32)).pin_memory(),
+                 torch.from_numpy(labels).pin_memory()) for _ in range(npool)]
+        h2d = B * 80 * n_samples * 4 + B * 100 * 4
+        step_desc = ("W:823-836 single replica (forward, shifted CE, backward, Keras-legacy Adam 1e-4)" if world == 1
+                     else "W:819-848 (un-normalised NCCL all-reduce SUM in buckets overlapped with backward, Adam)")
+
+        def step(batch):
+            if world > 1:
+                return W.distributed_train_step(strategy, model, batch, opt)
+            return W.train_step(model, batch, opt)
+        T = n_samples // 2
+        H, F, nh = cfg.d_model, cfg.d_ff, cfg.encoder_attention_heads
+        model_name = f"whisper-{size}"
+    model.broadcast_weights(strategy)
+    ctx = model._prog.ctx
+    resident = [tuple(t.to(dev) if t is not None else None for t in hb) for hb in host]
 
     def sync_all():
         torch.cuda.synchronize()
@@ -257,17 +399,22 @@ def run_ours(args):
     t_dev = e0.elapsed_time(e1) * 1e-3
     clk = clocks.stop() if rank == 0 else None
     # ---- end-to-end timing: pinned host -> device copy of every batch, loss read back every step ----------
-    staging = torch.empty(B, n_samples, dtype=torch.float32, device=dev)
+    staging = tuple(torch.empty_like(t, device=dev) if t is not None else None for t in host[0])
+
+    def e2e_step(i):
+        for dst, src in zip(staging, host[i % npool]):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        return float(step(staging))             # device -> host read of the step's loss
+
     for i in range(2):
-        staging.copy_(host[i % npool], non_blocking=True)
-        float(step(staging))
+        e2e_step(i)
     sync_all()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     last = None
     for i in range(args.steps):
-        staging.copy_(host[i % npool], non_blocking=True)
-        last = float(step(staging))          # device -> host read of the step's loss
+        last = e2e_step(i)
     e3.record()
     sync_all()
     t_e2e = e2.elapsed_time(e3) * 1e-3
@@ -282,31 +429,32 @@ def run_ours(args):
     peaks = measured_peaks()
     sps = B * world * args.steps / t_dev
     sps_e2e = B * world * args.steps / t_e2e
-    T = model.num_frames(n_samples)
-    M, Hd, F = B * T, cfg.hidden_size, cfg.intermediate_size
-    t_gemm = time_dominant_gemm(ctx, M, F, Hd)
-    gemm_tf = 2.0 * M * F * Hd / t_gemm / 1e12
+    n_params = int(model._prog.n)
+    del resident
+    torch.cuda.empty_cache()
+    dominant, kernels = kernel_rooflines(ctx, peaks, B, T if family == "w2v" else 1500, H, F, nh, n_params)
     step_tflops = sps / world * gflop / 1e3
     line = {
         "metric": "train_samples_per_sec", "value": sps, "unit": "samples/s", "audio_sec_per_sec": sps * secs,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "model": f"wav2vec2-{size}", "audio_seconds": secs, "per_gpu_batch": B,
+        "config": {"workload": args.workload, "model": model_name, "audio_seconds": secs, "per_gpu_batch": B,
                    "global_batch": B * world, "parallelism": f"dp{world}", "dropout": "on (0.1, as the reference's training=True)",
-                   "step": "VS:1119-1176 (clip_by_global_norm 1.0 + clipnorm 1.0 + Keras-legacy Adam 3e-5)" if world == 1
-                   else "V:1186-1260 (loss/N, local clip, NCCL all-reduce SUM, clipnorm, Adam)",
-                   "l2": "working set per step (GBs of activations) >> 126 MB L2; 4 distinct input batches cycled"},
+                   "step": step_desc,
+                   "l2": "working set per step (GBs of activations) >> 126 MB L2; 4 distinct input batches cycled; "
+                         "per-kernel timings flush L2 with a 256 MB memset between launches"},
         "clocks": clk,
-        "e2e": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": B * n_samples * 4 + B * cfg.num_negatives * 4,
-                "d2h_bytes_per_step": 4, "ms_per_step": t_e2e / args.steps * 1e3, "last_loss": last},
+        "e2e": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": t_e2e / args.steps * 1e3, "last_loss": last},
         "gpu_launches": launches,
         "launches_per_step": launches / args.steps,
         "step_tflops_per_gpu": step_tflops,
         "step_frac_of_bf16_sustained": step_tflops / peaks["bf16_tflops_sustained"],
-        "roofline": {"bound": "tensor", "kernel": f"gemm_tc_kernel (FFN fc1 {M}x{F}x{Hd}, bias+GELU epilogue)", "achieved": gemm_tf,
-                     "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["bf16_tflops"], "traffic": None,
+        "roofline": {"bound": "tensor", "kernel": dominant["kernel"], "achieved": dominant["achieved"], "peak": peaks["bf16_tflops"],
+                     "unit": "TFLOP/s", "frac": dominant["frac"], "traffic": dominant["traffic"],
                      "peak_source": peaks["source"] + " (burst: kernel timed alone)"},
+        "kernel_rooflines": kernels,
     }
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_step_throughput(args.workload, 1, 1, max_seconds=120.0)
@@ -322,7 +470,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="w2v_base_15s", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch (--batch_size of the reference CLI)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (--batch_size of the reference CLI); default 8 (w2v) / 4 (whisper)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     args = ap.parse_args()

@@ -135,6 +135,24 @@ class ProgramBase:
     def backward(self, stage_from=0, stage_to=10 ** 6):
         self.ctx.check(self._f("backward")(self.h, int(stage_from), int(stage_to), stream_ptr()))
 
+    def backward_allreduce_overlapped(self, strategy, bucket_elems=16 * 1024 * 1024):
+        """K21: backward stage by stage; as soon as the arena prefix of a group of stages is final (the arena is laid out
+        in backward-completion order, ts_*_stage_end) its bucket is all-reduced (SUM) asynchronously: NCCL's stream is
+        ordered after the compute stream at the point of the call, so the reduction of bucket i runs while the later
+        stages of backward are still computing. Returns after queuing a wait for every bucket on the compute stream."""
+        ends = self.stage_ends
+        works = []
+        start = 0
+        for s, end in enumerate(ends):
+            self.backward(s, s)
+            last = s == len(ends) - 1
+            if strategy.dist is not None and (end - start >= bucket_elems or last) and end > start:
+                works.append(strategy.dist.all_reduce(self.grads[start:end], op=strategy.dist.ReduceOp.SUM, async_op=True))
+                start = end
+        for w in works:
+            w.wait()
+        return len(works)
+
 
 class Strategy:
     """Stand-in for tf.distribute.MultiWorkerMirroredStrategy (W:1047, V:1473): one process per GPU, NCCL over
@@ -242,7 +260,7 @@ class Adam:
             self._state[key] = st
         return self._state[key]
 
-    def apply_gradients(self, grads_and_vars, strategy=None, global_clip_norm=None, model=None):
+    def apply_gradients(self, grads_and_vars, strategy=None, global_clip_norm=None, model=None, already_reduced=False):
         """All-reduce (SUM, un-normalised: App. A-13) the gradient arena across replicas, apply the per-variable
         clipnorm, then the Adam update. `global_clip_norm` fuses tf.clip_by_global_norm into the same pass when no
         all-reduce sits in between (single replica)."""
@@ -271,7 +289,7 @@ class Adam:
                 ctx.check(lib.ts_optim_clip_global(st["optim"], ptr(prog.grads), float(global_clip_norm), None, stream_ptr()))
             else:
                 fuse, gclip = 1, float(global_clip_norm)
-        if strategy.num_replicas_in_sync > 1:
+        if strategy.num_replicas_in_sync > 1 and not already_reduced:
             strategy.all_reduce_sum_(prog.grads, bucket_elems=32 * 1024 * 1024)
         self.iterations += 1
         ctx.check(lib.ts_optim_step(st["optim"], ptr(prog.params), ptr(prog.grads), ptr(st["m"]), ptr(st["v"]),

@@ -184,6 +184,16 @@ class WhisperForConditionalGeneration:
             g._ts_owner = self
         return gl
 
+    def gradient_allreduced(self, strategy):
+        """tape.gradient + the cross-replica SUM that apply_gradients performs (W:833-834), with the all-reduce of each
+        arena bucket overlapped with the remaining backward stages. The returned list is marked as already reduced."""
+        p = self._prog
+        p.backward_allreduce_overlapped(strategy)
+        gl = GradientList(p.view(p.grads, n) for n in self.variable_names)
+        gl.owner = self
+        gl.reduced = True
+        return gl
+
     def save_weights(self, path):
         torch.save({k: v.cpu() for k, v in self.get_weights().items()}, path)
 
@@ -238,8 +248,12 @@ def distributed_train_step(strategy, model, dist_inputs, optimizer, dropout=True
         features, labels = inputs
         outputs = model(features, labels=labels, training=True, dropout=dropout)
         loss = outputs["loss"]
-        gradients = model.gradient()
-        optimizer.apply_gradients(gradients, strategy=strategy)
+        if strategy.num_replicas_in_sync > 1:
+            gradients = model.gradient_allreduced(strategy)      # bucketed NCCL all-reduce overlapped with backward
+            optimizer.apply_gradients(gradients, strategy=strategy, already_reduced=True)
+        else:
+            gradients = model.gradient()
+            optimizer.apply_gradients(gradients, strategy=strategy)
         return loss
 
     per_replica_losses = strategy.run(train_step, args=(dist_inputs,))
