@@ -425,6 +425,7 @@ def run_ours(args):
         strategy.dist.all_reduce(tt, op=strategy.dist.ReduceOp.MAX)
         t_dev, t_e2e = float(tt[0]), float(tt[1])
     if rank != 0:
+        strategy.dist.destroy_process_group()
         return 0
     peaks = measured_peaks()
     sps = B * world * args.steps / t_dev
@@ -460,6 +461,8 @@ def run_ours(args):
         r = cpu_step_throughput(args.workload, 1, 1, max_seconds=120.0)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
+    if world > 1:
+        strategy.dist.destroy_process_group()
     return 0
 
 

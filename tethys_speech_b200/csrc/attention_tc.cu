@@ -322,47 +322,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 // ------------------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------------------
-// 16 element-wise warps per CTA: warp % 4 = TMEM lane quarter (rows), (warp - 2) / 4 = 32-column chunk of the tile.
-constexpr int kBwdEw = 16;
+// Both kernels work on 128 x 64 score tiles with 8 element-wise warps (warp % 4 = TMEM lane quarter = 32 tile rows,
+// (warp - 2) / 4 = which 32 of the 64 tile columns) and fit two CTAs per SM (<= 256 TMEM columns, <= 100 KB smem):
+// while one CTA's element-wise warps chew on a tile, the other CTA's MMAs / TMA / barrier hand-offs run underneath.
+constexpr int kBwdEw = 8;
 constexpr int kBwdThreads = 64 + kBwdEw * 32;
+constexpr int kHalfTile = 64 * AT_D * 2;  // 8 KB: a [64 x 64] bf16 operand tile
 
-// One thread's 32 columns of a score tile: probabilities p = exp(s' - m - log l) recomputed from the raw accumulators,
-// dS' = p o (dP o Z - D) (the common factor `scale` is applied to dQ / dK when they are stored) and, if PZ, p o Z.
-//   c1 = scale * log2(e), c0 = m * log2(e) + log2(l)   (c0 = +inf for padding rows: p = 0)
-template <int MASK, bool RAGGED, bool PZ>
-__device__ __forceinline__ void bwd_chunk(const uint32_t (&rs)[32], const uint32_t (&rd)[32], float (&ds)[32], float (&pz)[32],
-                                          const AttnParams& p, float c1, float c0, float m_i, float ll2, float D, int i, int col0,
-                                          const DropKey& dkey, uint32_t pair0) {
-#pragma unroll
-  for (int t = 0; t < 32; t += 2) {
-    float p0, p1;
-    if (MASK == 0) {
-      p0 = ex2f(fmaf(__uint_as_float(rs[t]), c1, -c0));
-      p1 = ex2f(fmaf(__uint_as_float(rs[t + 1]), c1, -c0));
-    } else {
-      float s0 = __uint_as_float(rs[t]) * p.scale, s1 = __uint_as_float(rs[t + 1]) * p.scale;
-      if (col0 + t <= i) s0 += -1e9f;
-      if (col0 + t + 1 <= i) s1 += -1e9f;
-      p0 = ex2f((s0 - m_i) * kLog2e - ll2);
-      p1 = ex2f((s1 - m_i) * kLog2e - ll2);
-    }
-    if (RAGGED) {
-      if (col0 + t >= p.Tk) p0 = 0.f;
-      if (col0 + t + 1 >= p.Tk) p1 = 0.f;
-    }
-    if (p.drop_thr) {  // Z = keep / keep_prob; the 1/keep_prob of P o Z is applied to dV when it is stored
-      const uint32_t w = drop_word32(dkey, pair0 + (t >> 1));
-      const bool k0 = drop_keep_even(dkey, w), k1 = drop_keep_odd(dkey, w);
-      ds[t] = p0 * fmaf(__uint_as_float(rd[t]), k0 ? p.inv_keep : 0.f, -D);
-      ds[t + 1] = p1 * fmaf(__uint_as_float(rd[t + 1]), k1 ? p.inv_keep : 0.f, -D);
-      if (PZ) { pz[t] = k0 ? p0 : 0.f; pz[t + 1] = k1 ? p1 : 0.f; }
-    } else {
-      ds[t] = p0 * (__uint_as_float(rd[t]) - D);
-      ds[t + 1] = p1 * (__uint_as_float(rd[t + 1]) - D);
-      if (PZ) { pz[t] = p0; pz[t + 1] = p1; }
-    }
-  }
-}
 __device__ __forceinline__ void store_chunk32(uint32_t tile, int r, int chunk, const float (&v)[32]) {
 #pragma unroll
   for (int t = 0; t < 4; ++t)
@@ -382,19 +348,53 @@ __device__ __forceinline__ void store_row32(bf16* dst, const uint32_t (&rg)[32],
   }
 }
 
-// ---- dQ (and D = rowsum(dO o O)) ------------------------------------------------------------------------------
-constexpr int kDqSmem = 2 * kTile /*Q, dO*/ + 4 * kTile /*K[2], V[2]*/ + kPTile /*dS*/ + 128;
+// ---- dQ (and D = rowsum(dO o O)): CTA = 128 query rows, loop over 64-row K/V tiles ---------------------------------
+// One thread's 32 columns: p = exp(s' - m - log l) recomputed from the raw accumulators and dS' = p o (dP o Z - D)
+// (the common factor `scale` is applied when dQ is stored). c1 = scale*log2(e), c0 = m*log2(e) + log2(l) (+inf: padding row).
+template <int MASK, bool RAGGED>
+__device__ __forceinline__ void dq_chunk(const uint32_t (&rs)[32], const uint32_t (&rd)[32], float (&ds)[32], const AttnParams& p,
+                                         float c1, float c0, float m_i, float ll2, float D, int i, int col0, const DropKey& dkey,
+                                         uint32_t pair0) {
+#pragma unroll
+  for (int t = 0; t < 32; t += 2) {
+    float p0, p1;
+    if (MASK == 0) {
+      p0 = ex2f(fmaf(__uint_as_float(rs[t]), c1, -c0));
+      p1 = ex2f(fmaf(__uint_as_float(rs[t + 1]), c1, -c0));
+    } else {
+      float s0 = __uint_as_float(rs[t]) * p.scale, s1 = __uint_as_float(rs[t + 1]) * p.scale;
+      if (col0 + t <= i) s0 += -1e9f;
+      if (col0 + t + 1 <= i) s1 += -1e9f;
+      p0 = ex2f((s0 - m_i) * kLog2e - ll2);
+      p1 = ex2f((s1 - m_i) * kLog2e - ll2);
+    }
+    if (RAGGED) {
+      if (col0 + t >= p.Tk) p0 = 0.f;
+      if (col0 + t + 1 >= p.Tk) p1 = 0.f;
+    }
+    if (p.drop_thr) {
+      const uint32_t w = drop_word32(dkey, pair0 + (t >> 1));
+      ds[t] = p0 * fmaf(__uint_as_float(rd[t]), drop_keep_even(dkey, w) ? p.inv_keep : 0.f, -D);
+      ds[t + 1] = p1 * fmaf(__uint_as_float(rd[t + 1]), drop_keep_odd(dkey, w) ? p.inv_keep : 0.f, -D);
+    } else {
+      ds[t] = p0 * (__uint_as_float(rd[t]) - D);
+      ds[t + 1] = p1 * (__uint_as_float(rd[t + 1]) - D);
+    }
+  }
+}
+
+constexpr int kDqSmem = 2 * kTile /*Q, dO*/ + 4 * kHalfTile /*K[2], V[2]*/ + kTile /*dS [128 x 64]*/ + 128;
 
 template <int MASK>
-__global__ void __launch_bounds__(kBwdThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, 2)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do, const AttnParams p,
                    int* watchdog) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if (!smem_aligned(smem, watchdog)) return;
-  const uint32_t sQ = ptx::smem_u32(smem), sDO = sQ + kTile, sK = sDO + kTile, sV = sK + 2 * kTile, sDS = sV + 2 * kTile;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * kTile + kPTile);
+  const uint32_t sQ = ptx::smem_u32(smem), sDO = sQ + kTile, sK = sDO + kTile, sV = sK + 2 * kHalfTile, sDS = sV + 2 * kHalfTile;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * kTile + 4 * kHalfTile);
   uint64_t* q_full = bars;        // Q + dO
   uint64_t* kv_full = bars + 1;   // 2
   uint64_t* kv_empty = bars + 3;  // 2
@@ -405,7 +405,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_M, h = blockIdx.y, b = blockIdx.z;
-  const int nkv = (p.Tk + AT_N - 1) / AT_N;
+  const int nkv = (p.Tk + 63) / 64;
   if (threadIdx.x == 0) {
     ptx::mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&kv_full[s], 1); ptx::mbar_init(&kv_empty[s], 1); }
@@ -414,12 +414,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     ptx::mbar_init(dq_done, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+  if (warp == 1) { ptx::tmem_alloc(tmem_slot, 256); ptx::tmem_relinquish(); }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tDP = tmem + 128, tDQ = tmem + 256;
+  const uint32_t tS = tmem, tDP = tmem + 64, tDQ = tmem + 128;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -430,22 +430,22 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       for (int j = 0; j < nkv; ++j) {
         const int s = j & 1;
         if (!ptx::mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1, watchdog, 21)) break;
-        ptx::mbar_expect_tx(&kv_full[s], 2 * kTile);
-        ptx::tma_load_4d(sK + s * kTile, &tm_k, &kv_full[s], 0, j * AT_N, h, b);
-        ptx::tma_load_4d(sV + s * kTile, &tm_v, &kv_full[s], 0, j * AT_N, h, b);
+        ptx::mbar_expect_tx(&kv_full[s], 2 * kHalfTile);
+        ptx::tma_load_4d(sK + s * kHalfTile, &tm_k, &kv_full[s], 0, j * 64, h, b);
+        ptx::tma_load_4d(sV + s * kHalfTile, &tm_v, &kv_full[s], 0, j * 64, h, b);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = ptx::make_idesc_bf16(AT_M, AT_N, 0, 0);
+      constexpr uint32_t idesc_s = ptx::make_idesc_bf16(AT_M, 64, 0, 0);
       constexpr uint32_t idesc_dq = ptx::make_idesc_bf16(AT_M, AT_D, 0, 1);
       auto issue_sdp = [&](int s) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          ptx::umma_f16(tS, desc_kmajor(sQ, kk), desc_kmajor(sK + s * kTile, kk), idesc_s, kk > 0 ? 1u : 0u);
+          ptx::umma_f16(tS, desc_kmajor(sQ, kk), desc_kmajor(sK + s * kHalfTile, kk), idesc_s, kk > 0 ? 1u : 0u);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          ptx::umma_f16(tDP, desc_kmajor(sDO, kk), desc_kmajor(sV + s * kTile, kk), idesc_s, kk > 0 ? 1u : 0u);
+          ptx::umma_f16(tDP, desc_kmajor(sDO, kk), desc_kmajor(sV + s * kHalfTile, kk), idesc_s, kk > 0 ? 1u : 0u);
         ptx::umma_commit(sdp_full);
       };
       bool ok = ptx::mbar_wait(q_full, 0, watchdog, 22) && ptx::mbar_wait(&kv_full[0], 0, watchdog, 23);
@@ -455,11 +455,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if (!ptx::mbar_wait(ds_full, j & 1, watchdog, 24)) break;
         ptx::tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          ptx::umma_f16(tDQ, desc_p_kmajor(sDS, kk), desc_mn_b(sK + s * kTile, kk), idesc_dq, (j > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < 4; ++kk)
+          ptx::umma_f16(tDQ, desc_kmajor(sDS, kk), desc_mn_b(sK + s * kHalfTile, kk), idesc_dq, (j > 0 || kk > 0) ? 1u : 0u);
         ptx::umma_commit(&kv_empty[s]);
         ptx::umma_commit(dq_done);
-        if (j + 1 < nkv) {  // S / dP of the next tile run behind dQ of this one, while the element-wise warps are idle
+        if (j + 1 < nkv) {
           if (!ptx::mbar_wait(&kv_full[s ^ 1], ((j + 1) >> 1) & 1, watchdog, 23)) break;
           ptx::tc_fence_after();
           issue_sdp(s ^ 1);
@@ -467,7 +467,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       }
     }
   } else {
-    const int q = warp & 3, chunk = (warp - 2) >> 2;
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int i = q0 + r;
     const bool live = i < p.Tq;
@@ -496,24 +496,24 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           D = fmaf(x.y + z.y, y.y, D);
         }
       }
-      if (chunk == 0) p.dsum[srow] = D;
+      if (half == 0) p.dsum[srow] = D;
     }
     const float c1 = p.scale * kLog2e, c0 = m_i * kLog2e + ll2;
     bool ok = true;
     for (int j = 0; j < nkv && ok; ++j) {
       if (!ptx::mbar_wait(sdp_full, j & 1, watchdog, 25)) { ok = false; break; }
       ptx::tc_fence_after();
-      const int col0 = j * AT_N + chunk * 32;
+      const int col0 = j * 64 + half * 32;
       uint32_t rs[32], rd[32];
-      ptx::tmem_ld_32x32(tS + lane_off + chunk * 32, rs);
-      ptx::tmem_ld_32x32(tDP + lane_off + chunk * 32, rd);
+      ptx::tmem_ld_32x32(tS + lane_off + half * 32, rs);
+      ptx::tmem_ld_32x32(tDP + lane_off + half * 32, rd);
       ptx::tmem_ld_wait();
-      float ds[32], unused[32];
+      float ds[32];
       const uint32_t pair0 = (drow + (uint32_t)col0) >> 1;
-      if (col0 + 32 > p.Tk) bwd_chunk<MASK, true, false>(rs, rd, ds, unused, p, c1, c0, m_i, ll2, D, i, col0, dkey, pair0);
-      else bwd_chunk<MASK, false, false>(rs, rd, ds, unused, p, c1, c0, m_i, ll2, D, i, col0, dkey, pair0);
+      if (col0 + 32 > p.Tk) dq_chunk<MASK, true>(rs, rd, ds, p, c1, c0, m_i, ll2, D, i, col0, dkey, pair0);
+      else dq_chunk<MASK, false>(rs, rd, ds, p, c1, c0, m_i, ll2, D, i, col0, dkey, pair0);
       if (j > 0 && !ptx::mbar_wait(dq_done, (j - 1) & 1, watchdog, 26)) { ok = false; break; }  // dS smem free again
-      store_chunk32(sDS, r, chunk, ds);
+      store_chunk32(sDS, r, half, ds);
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       __syncwarp();
@@ -521,33 +521,35 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     }
     if (ok && ptx::mbar_wait(dq_done, (nkv - 1) & 1, watchdog, 27)) {
       ptx::tc_fence_after();
-      if (chunk < 2) {
-        uint32_t rg[32];
-        ptx::tmem_ld_32x32(tDQ + lane_off + chunk * 32, rg);
-        ptx::tmem_ld_wait();
-        if (live) store_row32(p.dq + (long long)b * p.dq_bs + (long long)i * p.dq_ld + h * AT_D + chunk * 32, rg, p.scale);
-      }
+      uint32_t rg[32];
+      ptx::tmem_ld_32x32(tDQ + lane_off + half * 32, rg);
+      ptx::tmem_ld_wait();
+      if (live) store_row32(p.dq + (long long)b * p.dq_bs + (long long)i * p.dq_ld + h * AT_D + half * 32, rg, p.scale);
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem, 512);
+  if (warp == 1) ptx::tmem_dealloc(tmem, 256);
 }
 
-// ---- dK, dV ----------------------------------------------------------------------------------------------------
-constexpr int kDkvSmem = 2 * kTile /*K, V*/ + 4 * kTile /*Q[2], dO[2]*/ + 2 * kPTile /*P, dS*/ + 128;
+// ---- dK, dV: CTA = 128 key rows, loop over 64-row query tiles, TRANSPOSED scores ------------------------------------
+// S^T = K Q^T and dP^T = V dO^T put the key index on the TMEM lanes, so a thread owns one key row and 32 query columns,
+// P^T / dS^T land in smem as plain K-major A operands of dV += P^T dO and dK += dS^T Q, and the accumulators need no
+// transposes. Per-query statistics (c0 = m*log2e + log2 l, D) are staged in smem per tile and read as broadcasts.
+constexpr int kDkvSmem = 2 * kTile /*K, V*/ + 4 * kHalfTile /*Q[2], dO[2]*/ + 2 * kTile /*P^T, dS^T*/ + 2 * 4 * 64 * 4 /*stats*/ + 128;
 
 template <int MASK>
-__global__ void __launch_bounds__(kBwdThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, 2)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do, const AttnParams p,
                     int* watchdog) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if (!smem_aligned(smem, watchdog)) return;
-  const uint32_t sK = ptx::smem_u32(smem), sV = sK + kTile, sQ = sV + kTile, sDO = sQ + 2 * kTile, sP = sDO + 2 * kTile,
-                 sDS = sP + kPTile;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * kTile + 2 * kPTile);
+  const uint32_t sK = ptx::smem_u32(smem), sV = sK + kTile, sQ = sV + kTile, sDO = sQ + 2 * kHalfTile, sPT = sDO + 2 * kHalfTile,
+                 sDST = sPT + kTile;
+  float* s_stat = reinterpret_cast<float*>(smem + 4 * kTile + 4 * kHalfTile);  // [2 buffers][4: c0, D, m, ll2][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 2 * 4 * 64);
   uint64_t* kv_full = bars;        // K + V
   uint64_t* q_full = bars + 1;     // 2 (Q + dO)
   uint64_t* q_empty = bars + 3;    // 2
@@ -558,7 +560,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kv0 = blockIdx.x * AT_N, h = blockIdx.y, b = blockIdx.z;
-  const int nq = (p.Tq + AT_M - 1) / AT_M;
+  const int nq = (p.Tq + 63) / 64;
   if (threadIdx.x == 0) {
     ptx::mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&q_full[s], 1); ptx::mbar_init(&q_empty[s], 1); }
@@ -567,12 +569,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     ptx::mbar_init(acc_done, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+  if (warp == 1) { ptx::tmem_alloc(tmem_slot, 256); ptx::tmem_relinquish(); }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320;
+  const uint32_t tST = tmem, tDPT = tmem + 64, tDV = tmem + 128, tDK = tmem + 192;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -583,22 +585,22 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       for (int it = 0; it < nq; ++it) {
         const int s = it & 1;
         if (!ptx::mbar_wait(&q_empty[s], ((it >> 1) & 1) ^ 1, watchdog, 31)) break;
-        ptx::mbar_expect_tx(&q_full[s], 2 * kTile);
-        ptx::tma_load_4d(sQ + s * kTile, &tm_q, &q_full[s], 0, it * AT_M, h, b);
-        ptx::tma_load_4d(sDO + s * kTile, &tm_do, &q_full[s], 0, it * AT_M, h, b);
+        ptx::mbar_expect_tx(&q_full[s], 2 * kHalfTile);
+        ptx::tma_load_4d(sQ + s * kHalfTile, &tm_q, &q_full[s], 0, it * 64, h, b);
+        ptx::tma_load_4d(sDO + s * kHalfTile, &tm_do, &q_full[s], 0, it * 64, h, b);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = ptx::make_idesc_bf16(AT_M, AT_N, 0, 0);
-      constexpr uint32_t idesc_acc = ptx::make_idesc_bf16(AT_N, AT_D, 1, 1);  // A = P^T / dS^T (MN-major), B = dO / Q (MN-major)
+      constexpr uint32_t idesc_s = ptx::make_idesc_bf16(AT_N, 64, 0, 0);      // [128 keys] x [64 queries]
+      constexpr uint32_t idesc_acc = ptx::make_idesc_bf16(AT_N, AT_D, 0, 1);  // A = P^T / dS^T (K-major), B = dO / Q (MN-major)
       auto issue_sdp = [&](int s) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          ptx::umma_f16(tS, desc_kmajor(sQ + s * kTile, kk), desc_kmajor(sK, kk), idesc_s, kk > 0 ? 1u : 0u);
+          ptx::umma_f16(tST, desc_kmajor(sK, kk), desc_kmajor(sQ + s * kHalfTile, kk), idesc_s, kk > 0 ? 1u : 0u);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          ptx::umma_f16(tDP, desc_kmajor(sDO + s * kTile, kk), desc_kmajor(sV, kk), idesc_s, kk > 0 ? 1u : 0u);
+          ptx::umma_f16(tDPT, desc_kmajor(sV, kk), desc_kmajor(sDO + s * kHalfTile, kk), idesc_s, kk > 0 ? 1u : 0u);
         ptx::umma_commit(sdp_full);
       };
       bool ok = ptx::mbar_wait(kv_full, 0, watchdog, 32) && ptx::mbar_wait(&q_full[0], 0, watchdog, 33);
@@ -608,11 +610,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         if (!ptx::mbar_wait(pds_full, it & 1, watchdog, 34)) break;
         ptx::tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          ptx::umma_f16(tDV, desc_p_mn_a(sP, kk), desc_mn_b(sDO + s * kTile, kk), idesc_acc, (it > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < 4; ++kk)
+          ptx::umma_f16(tDV, desc_kmajor(sPT, kk), desc_mn_b(sDO + s * kHalfTile, kk), idesc_acc, (it > 0 || kk > 0) ? 1u : 0u);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          ptx::umma_f16(tDK, desc_p_mn_a(sDS, kk), desc_mn_b(sQ + s * kTile, kk), idesc_acc, (it > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < 4; ++kk)
+          ptx::umma_f16(tDK, desc_kmajor(sDST, kk), desc_mn_b(sQ + s * kHalfTile, kk), idesc_acc, (it > 0 || kk > 0) ? 1u : 0u);
         ptx::umma_commit(&q_empty[s]);
         ptx::umma_commit(acc_done);
         if (it + 1 < nq) {
@@ -623,34 +625,75 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
     }
   } else {
-    const int q = warp & 3, chunk = (warp - 2) >> 2;
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
+    const int jrow = kv0 + r;                 // key index of this thread
+    const bool rowlive = jrow < p.Tk;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const int col0 = kv0 + chunk * 32;
-    const bool ragged = col0 + 32 > p.Tk;
+    const int et = (warp - 2) * 32 + lane;    // 0..255 among the element-wise threads
     const float c1 = p.scale * kLog2e;
     const DropKey dkey = make_drop_key(p.seed, (unsigned long long)(b * p.nh + h), p.drop_thr);
+    const uint32_t half_pitch = (uint32_t)p.drop_pitch >> 1;
+    const bool odd = lane & 1;                // parity of jrow (kv0 is a multiple of 128)
     bool ok = true;
     for (int it = 0; it < nq && ok; ++it) {
-      const int i = it * AT_M + r;
-      const bool live = i < p.Tq;
-      const long long srow = ((long long)b * p.nh + h) * p.Tq + i;
-      float m_i = 0.f, ll2 = INFINITY, D = 0.f;
-      if (live) { m_i = p.stats[srow * 2]; ll2 = p.stats[srow * 2 + 1] * kLog2e; D = p.dsum[srow]; }
-      const float c0 = m_i * kLog2e + ll2;
-      const uint32_t pair0 = ((uint32_t)i * (uint32_t)p.drop_pitch + (uint32_t)col0) >> 1;
+      const int buf = it & 1;
+      float* st = s_stat + buf * 4 * 64;
+      if (et < 64) {  // stage the per-query statistics of this tile
+        const int i = it * 64 + et;
+        float m_i = 0.f, ll2 = INFINITY, D = 0.f;
+        if (i < p.Tq) {
+          const long long srow = ((long long)b * p.nh + h) * p.Tq + i;
+          m_i = p.stats[srow * 2]; ll2 = p.stats[srow * 2 + 1] * kLog2e; D = p.dsum[srow];
+        }
+        st[et] = m_i * kLog2e + ll2; st[64 + et] = D; st[128 + et] = m_i; st[192 + et] = ll2;
+      }
+      asm volatile("bar.sync 5, 256;" ::: "memory");
       if (!ptx::mbar_wait(sdp_full, it & 1, watchdog, 35)) { ok = false; break; }
       ptx::tc_fence_after();
       uint32_t rs[32], rd[32];
-      ptx::tmem_ld_32x32(tS + lane_off + chunk * 32, rs);
-      ptx::tmem_ld_32x32(tDP + lane_off + chunk * 32, rd);
+      ptx::tmem_ld_32x32(tST + lane_off + half * 32, rs);
+      ptx::tmem_ld_32x32(tDPT + lane_off + half * 32, rd);
       ptx::tmem_ld_wait();
       float ds[32], pz[32];
-      if (ragged) bwd_chunk<MASK, true, true>(rs, rd, ds, pz, p, c1, c0, m_i, ll2, D, i, col0, dkey, pair0);
-      else bwd_chunk<MASK, false, true>(rs, rd, ds, pz, p, c1, c0, m_i, ll2, D, i, col0, dkey, pair0);
-      if (it > 0 && !ptx::mbar_wait(acc_done, (it - 1) & 1, watchdog, 36)) { ok = false; break; }  // P / dS smem free again
-      store_chunk32(sP, r, chunk, pz);
-      store_chunk32(sDS, r, chunk, ds);
+      const int i0 = it * 64 + half * 32;     // first query column of this thread
+      const float* sc0 = st + half * 32;
+      const float* sD = st + 64 + half * 32;
+#pragma unroll
+      for (int t = 0; t < 32; t += 2) {
+        float p0, p1;
+        if (MASK == 0) {
+          p0 = ex2f(fmaf(__uint_as_float(rs[t]), c1, -sc0[t]));
+          p1 = ex2f(fmaf(__uint_as_float(rs[t + 1]), c1, -sc0[t + 1]));
+        } else {
+          float s0 = __uint_as_float(rs[t]) * p.scale, s1 = __uint_as_float(rs[t + 1]) * p.scale;
+          if (jrow <= i0 + t) s0 += -1e9f;
+          if (jrow <= i0 + t + 1) s1 += -1e9f;
+          p0 = ex2f((s0 - st[128 + half * 32 + t]) * kLog2e - st[192 + half * 32 + t]);
+          p1 = ex2f((s1 - st[128 + half * 32 + t + 1]) * kLog2e - st[192 + half * 32 + t + 1]);
+        }
+        if (!rowlive) { p0 = 0.f; p1 = 0.f; }
+        if (p.drop_thr) {
+          // the pair (jrow & ~1, jrow | 1) of query column i shares one hash word: each lane hashes the column whose parity
+          // matches its own and fetches the other column's word from its neighbour lane
+          const uint32_t wo = drop_word32(dkey, (uint32_t)(i0 + t + (odd ? 1 : 0)) * half_pitch + ((uint32_t)jrow >> 1));
+          const uint32_t wn = __shfl_xor_sync(0xffffffffu, wo, 1);
+          const uint32_t w0 = odd ? wn : wo, w1 = odd ? wo : wn;   // words of columns t and t + 1
+          const bool k0 = odd ? drop_keep_odd(dkey, w0) : drop_keep_even(dkey, w0);
+          const bool k1 = odd ? drop_keep_odd(dkey, w1) : drop_keep_even(dkey, w1);
+          ds[t] = p0 * fmaf(__uint_as_float(rd[t]), k0 ? p.inv_keep : 0.f, -sD[t]);
+          ds[t + 1] = p1 * fmaf(__uint_as_float(rd[t + 1]), k1 ? p.inv_keep : 0.f, -sD[t + 1]);
+          pz[t] = k0 ? p0 : 0.f;
+          pz[t + 1] = k1 ? p1 : 0.f;
+        } else {
+          ds[t] = p0 * (__uint_as_float(rd[t]) - sD[t]);
+          ds[t + 1] = p1 * (__uint_as_float(rd[t + 1]) - sD[t + 1]);
+          pz[t] = p0; pz[t + 1] = p1;
+        }
+      }
+      if (it > 0 && !ptx::mbar_wait(acc_done, (it - 1) & 1, watchdog, 36)) { ok = false; break; }  // P^T / dS^T smem free again
+      store_chunk32(sPT, r, half, pz);
+      store_chunk32(sDST, r, half, ds);
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       __syncwarp();
@@ -658,25 +701,24 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     }
     if (ok && ptx::mbar_wait(acc_done, (nq - 1) & 1, watchdog, 37)) {
       ptx::tc_fence_after();
-      const int jrow = kv0 + r;  // key index owned by this thread in the accumulators (M = key rows)
-      // chunk 0,1 -> dV columns [0,32), [32,64); chunk 2,3 -> dK columns
       uint32_t rg[32];
-      ptx::tmem_ld_32x32((chunk < 2 ? tDV : tDK) + lane_off + (chunk & 1) * 32, rg);
+      ptx::tmem_ld_32x32(tDV + lane_off + half * 32, rg);
       ptx::tmem_ld_wait();
-      if (jrow < p.Tk)
-        store_row32((chunk < 2 ? p.dv : p.dk) + (long long)b * p.dkv_bs + (long long)jrow * p.dkv_ld + h * AT_D + (chunk & 1) * 32, rg,
-                    chunk < 2 ? p.inv_keep : p.scale);
+      if (rowlive) store_row32(p.dv + (long long)b * p.dkv_bs + (long long)jrow * p.dkv_ld + h * AT_D + half * 32, rg, p.inv_keep);
+      ptx::tmem_ld_32x32(tDK + lane_off + half * 32, rg);
+      ptx::tmem_ld_wait();
+      if (rowlive) store_row32(p.dk + (long long)b * p.dkv_bs + (long long)jrow * p.dkv_ld + h * AT_D + half * 32, rg, p.scale);
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem, 512);
+  if (warp == 1) ptx::tmem_dealloc(tmem, 256);
 }
 
-static int head_tmap(Ctx* ctx, CUtensorMap* out, const void* base, long long ld, long long bs, int T, int nh, int B) {
+static int head_tmap(Ctx* ctx, CUtensorMap* out, const void* base, long long ld, long long bs, int T, int nh, int B, int box_rows = 128) {
   const uint64_t dims[4] = {(uint64_t)AT_D, (uint64_t)T, (uint64_t)nh, (uint64_t)B};
   const uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)AT_D * 2, (uint64_t)(B > 1 ? bs : ld) * 2};
-  return get_tmap(ctx, out, base, dims, str, AT_D, 128, false);
+  return get_tmap(ctx, out, base, dims, str, AT_D, (uint32_t)box_rows, false);
 }
 
 static void drop_params(float drop, uint32_t* thr, float* inv_keep) {
@@ -742,11 +784,16 @@ int attn_bwd(Ctx* ctx, const ts_attn_desc* d, cudaStream_t st) {
   p.o_in = (const bf16*)d->o; p.d_o = (const bf16*)d->d_o; p.dsum = d->dsum;
   p.dq = (bf16*)d->dq; p.dq_ld = d->dq_ld; p.dq_bs = d->dq_bs;
   p.dk = (bf16*)d->dk; p.dv = (bf16*)d->dv; p.dkv_ld = d->dkv_ld; p.dkv_bs = d->dkv_bs;
-  CUtensorMap tq, tk, tv, tdo;
+  // dQ kernel: Q / dO as 128-row boxes, K / V as 64-row boxes; dK/dV kernel: the other way round
+  CUtensorMap tq, tk, tv, tdo, tq64, tk64, tv64, tdo64;
   TS_TRY_RC(head_tmap(ctx, &tq, d->q, d->q_ld, d->q_bs, d->tq, d->heads, d->batch));
   TS_TRY_RC(head_tmap(ctx, &tk, d->k, d->kv_ld, d->kv_bs, d->tk, d->heads, d->batch));
   TS_TRY_RC(head_tmap(ctx, &tv, d->v, d->kv_ld, d->kv_bs, d->tk, d->heads, d->batch));
   TS_TRY_RC(head_tmap(ctx, &tdo, d->d_o, d->o_ld, d->o_bs, d->tq, d->heads, d->batch));
+  TS_TRY_RC(head_tmap(ctx, &tq64, d->q, d->q_ld, d->q_bs, d->tq, d->heads, d->batch, 64));
+  TS_TRY_RC(head_tmap(ctx, &tk64, d->k, d->kv_ld, d->kv_bs, d->tk, d->heads, d->batch, 64));
+  TS_TRY_RC(head_tmap(ctx, &tv64, d->v, d->kv_ld, d->kv_bs, d->tk, d->heads, d->batch, 64));
+  TS_TRY_RC(head_tmap(ctx, &tdo64, d->d_o, d->o_ld, d->o_bs, d->tq, d->heads, d->batch, 64));
   static bool attr = false;
   if (!attr) {
     TS_CUDA_OK(ctx, cudaFuncSetAttribute(attn_bwd_dq_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem));
@@ -757,13 +804,13 @@ int attn_bwd(Ctx* ctx, const ts_attn_desc* d, cudaStream_t st) {
   }
   dim3 gq(cdiv(d->tq, AT_M), d->heads, d->batch), gk(cdiv(d->tk, AT_N), d->heads, d->batch);
   if (d->mask_mode == 0) {
-    attn_bwd_dq_kernel<0><<<gq, kBwdThreads, kDqSmem, st>>>(tq, tk, tv, tdo, p, ctx->d_watchdog);
+    attn_bwd_dq_kernel<0><<<gq, kBwdThreads, kDqSmem, st>>>(tq, tk64, tv64, tdo, p, ctx->d_watchdog);
     TS_LAUNCH_OK(ctx);
-    attn_bwd_dkv_kernel<0><<<gk, kBwdThreads, kDkvSmem, st>>>(tq, tk, tv, tdo, p, ctx->d_watchdog);
+    attn_bwd_dkv_kernel<0><<<gk, kBwdThreads, kDkvSmem, st>>>(tq64, tk, tv, tdo64, p, ctx->d_watchdog);
   } else {
-    attn_bwd_dq_kernel<1><<<gq, kBwdThreads, kDqSmem, st>>>(tq, tk, tv, tdo, p, ctx->d_watchdog);
+    attn_bwd_dq_kernel<1><<<gq, kBwdThreads, kDqSmem, st>>>(tq, tk64, tv64, tdo, p, ctx->d_watchdog);
     TS_LAUNCH_OK(ctx);
-    attn_bwd_dkv_kernel<1><<<gk, kBwdThreads, kDkvSmem, st>>>(tq, tk, tv, tdo, p, ctx->d_watchdog);
+    attn_bwd_dkv_kernel<1><<<gk, kBwdThreads, kDkvSmem, st>>>(tq64, tk, tv, tdo64, p, ctx->d_watchdog);
   }
   TS_LAUNCH_OK(ctx);
   return 0;

@@ -191,6 +191,13 @@ int main(int argc, char** argv) {
   ts_ctx* ctx = nullptr;
   if (ts_create(0, &ctx)) { printf("ts_create failed\n"); return 1; }
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+  if (argc > 1 && !strcmp(argv[1], "prof")) {  // one timing case only (for ncu)
+    Case c = {"w2v base 15s drop", 8, 12, 750, 750, 0, 0.1f, false};
+    if (argc > 2 && !strcmp(argv[2], "nodrop")) c.drop = 0.f;
+    run_case(ctx, c, true);
+    ts_destroy(ctx);
+    return 0;
+  }
   std::vector<Case> cases = {
       {"self_128", 1, 1, 128, 128, 0, 0.f, false},
       {"self_200_ragged", 2, 3, 200, 200, 0, 0.f, false},

@@ -146,6 +146,12 @@ int main(int argc, char** argv) {
   int rc = ts_create(0, &ctx);
   if (rc) { printf("ts_create failed rc=%d\n", rc); return 1; }
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+  if (argc > 1 && !strcmp(argv[1], "prof")) {  // the workload's dominant GEMM only (for ncu): FFN fc1 + bias + GELU + pre-activation copy
+    Case c = {"ffn1+gelu+preact", 6000, 3072, 768, 0, 1, 1, 1, 0, 0, 0, 1, 1, 0, 0, 1, 1.f};
+    run_case(ctx, c, 2, true);
+    ts_destroy(ctx);
+    return 0;
+  }
   std::vector<Case> cases = {
       // name, m, n, k, amaj, bmaj, nb1, nb2, lda, ldb, out_f32, bias, act, res, acc, preact, alpha
       {"kk_basic", 128, 128, 64, 0, 0, 1, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1.f},
