@@ -82,7 +82,7 @@ typedef struct {
   int32_t out_dtype; /* ts_dtype of C (and residual) */
   float alpha;
   const float* bias; /* [n] fp32 or NULL */
-  int32_t act;       /* 0 none, 1 exact-erf GELU */
+  int32_t act;       /* 0 none, 1 exact-erf GELU, 2 multiply by GELU'(act_aux[m,n]) (backward of a GELU whose input was kept) */
   const void* residual; /* same dtype/shape as C or NULL; added after act */
   int64_t ldr, r_bs1, r_bs2;
   int32_t accumulate; /* 1: C += result (only with out_dtype TS_F32, no act/residual) */
@@ -91,6 +91,8 @@ typedef struct {
   float drop;           /* dropout rate applied after act (0 = off); keep-mask = hash(seed, element offset in C) */
   uint64_t seed;
   int64_t bias_bs1;     /* bias element stride per batch1 index (grouped conv: one bias slice per group) */
+  const void* act_aux;  /* act == 2: the GELU input u, same dtype and batch strides as C, row stride ld_aux */
+  int64_t ld_aux;
 } ts_gemm_desc;
 
 int ts_gemm(ts_ctx* ctx, const ts_gemm_desc* d, void* stream);

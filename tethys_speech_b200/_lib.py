@@ -39,6 +39,7 @@ class GemmDesc(C.Structure):
         ("drop", C.c_float),
         ("seed", C.c_uint64),
         ("bias_bs1", C.c_int64),
+        ("act_aux", C.c_void_p), ("ld_aux", C.c_int64),
     ]
 
 

@@ -1,5 +1,6 @@
 // C-ABI: context lifecycle, error reporting, GEMM dispatch.
 #include <stdarg.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "ops.cuh"
 
@@ -50,6 +51,8 @@ int ts_create(int device, ts_ctx** out) {
   Ctx* c = new Ctx();
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
+  // TETHYS_SM_MARGIN=n: size persistent grids for n fewer SMs (leaves room for NCCL's CTAs when the gradient all-reduce overlaps backward)
+  if (const char* mg = getenv("TETHYS_SM_MARGIN")) { const int n = atoi(mg); if (n > 0 && n < c->num_sms) c->num_sms -= n; }
   if (cudaMalloc(&c->d_watchdog, sizeof(int)) != cudaSuccess) { delete c; return TS_ECUDA; }
   cudaMemset(c->d_watchdog, 0, sizeof(int));
   *out = reinterpret_cast<ts_ctx*>(c);

@@ -56,7 +56,7 @@ int conv0_fwd(Ctx* ctx, int dt, const float* wave, const void* w, void* y, long 
   return 0;
 }
 
-constexpr int C0_WG_ROWS = 1024;  // rows reduced per block
+constexpr int C0_WG_ROWS = 512;  // rows reduced per block
 
 template <typename T, int K>
 __global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restrict__ wave, const T* __restrict__ dy,
@@ -84,14 +84,21 @@ __global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restric
     for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
   const int tend = min(C0_WG_ROWS, T_ - t0);
   if (tr < rpi) {
-    for (int tt = tr; tt < tend; tt += rpi) {
-      float d[8];
-      load8<T>(dy + ((long long)b * dy_rpb + t0 + tt) * C + tc * 8, d);
+    const T* dyb = dy + ((long long)b * dy_rpb + t0) * C + tc * 8;
+    for (int tt = tr; tt < tend; tt += 2 * rpi) {  // two independent 16-byte loads in flight per thread
+      float d[2][8];
+      const bool two = tt + rpi < tend;
+      load8<T>(dyb + (long long)tt * C, d[0]);
+      if (two) load8<T>(dyb + (long long)(tt + rpi) * C, d[1]);
 #pragma unroll
-      for (int j = 0; j < K; ++j) {
-        const float xv = sw[tt * s + j];
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !two) break;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(xv, d[i], acc[j][i]);
+        for (int j = 0; j < K; ++j) {
+          const float xv = sw[(tt + u * rpi) * s + j];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(xv, d[u][i], acc[j][i]);
+        }
       }
     }
 #pragma unroll

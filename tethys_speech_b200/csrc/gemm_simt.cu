@@ -6,8 +6,8 @@
 namespace ts {
 
 struct SimtParams {
-  const void* a; const void* b; void* c; void* c_pre; const void* res; const float* bias;
-  long long lda, ldb, ldc, ldr;
+  const void* a; const void* b; void* c; void* c_pre; const void* res; const float* bias; const void* aux;
+  long long lda, ldb, ldc, ldr, ld_aux;
   long long a_bs1, a_bs2, b_bs1, b_bs2, c_bs1, c_bs2, r_bs1, r_bs2, bias_bs1;
   int m, n, k, nb1;
   int a_major, b_major;
@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
       if (p.bias) v += p.bias[b1 * p.bias_bs1 + gn];
       if (CP) CP[(long long)gm * p.ldc + gn] = from_f<TO>(v);
       if (p.act == 1) v = gelu_f(v);
+      else if (p.act == 2) v *= gelu_grad_f(to_f<TO>(reinterpret_cast<const TO*>(p.aux)[b1 * p.c_bs1 + b2 * p.c_bs2 + (long long)gm * p.ld_aux + gn]));
       if (p.drop_thr)
         v *= dropout_scale(p.seed, (unsigned long long)(b1 * p.c_bs1 + b2 * p.c_bs2 + (long long)gm * p.ldc + gn), p.drop_thr, p.inv_keep);
       if (R) v += to_f<TO>(R[(long long)gm * p.ldr + gn]);
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
 int gemm_simt(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
   SimtParams p;
   p.a = d->a; p.b = d->b; p.c = d->c; p.c_pre = d->c_preact; p.res = d->residual; p.bias = d->bias;
-  p.lda = d->lda; p.ldb = d->ldb; p.ldc = d->ldc; p.ldr = d->ldr;
+  p.lda = d->lda; p.ldb = d->ldb; p.ldc = d->ldc; p.ldr = d->ldr; p.aux = d->act_aux; p.ld_aux = d->ld_aux;
   p.a_bs1 = d->a_bs1; p.a_bs2 = d->a_bs2; p.b_bs1 = d->b_bs1; p.b_bs2 = d->b_bs2;
   p.c_bs1 = d->c_bs1; p.c_bs2 = d->c_bs2; p.r_bs1 = d->r_bs1; p.r_bs2 = d->r_bs2; p.bias_bs1 = d->bias_bs1;
   p.m = d->m; p.n = d->n; p.k = d->k;

@@ -27,6 +27,8 @@ struct EpiParams {
   void* c_pre;
   const void* res;
   const float* bias;
+  const void* aux;   // act == 2: GELU input u (same dtype / batch strides as C), row stride ld_aux
+  long long ld_aux;
   long long ldc, ldr, c_bs1, c_bs2, r_bs1, r_bs2, bias_bs1;
   float alpha;
   int act, accumulate;
@@ -96,11 +98,40 @@ __device__ __forceinline__ void epi_bias(float (&v)[NV], const EpiParams& p, con
     }
   }
 }
-template <int NV>
-__device__ __forceinline__ void epi_act_drop(float (&v)[NV], const EpiParams& p, unsigned long long e0) {
+template <int NV, typename OutT>
+__device__ __forceinline__ void epi_act_drop(float (&v)[NV], const EpiParams& p, unsigned long long e0, const OutT* aux_row, bool row_ok,
+                                             int col, bool full) {
   if (p.act == 1) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = gelu_fast_f(v[i]);   // bf16 operands: fast erf (common.cuh)
+  } else if (p.act == 2 && row_ok) {
+    // backward of a GELU: multiply by GELU'(u) with u read from the kept pre-activation tensor
+    if (full && (reinterpret_cast<uintptr_t>(aux_row) & 15) == 0) {
+      if (sizeof(OutT) == 4) {
+#pragma unroll
+        for (int j = 0; j < NV / 4; ++j) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(aux_row) + j);
+          v[4 * j] *= gelu_grad_fast_f(f.x); v[4 * j + 1] *= gelu_grad_fast_f(f.y);
+          v[4 * j + 2] *= gelu_grad_fast_f(f.z); v[4 * j + 3] *= gelu_grad_fast_f(f.w);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NV / 8; ++j) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(aux_row) + j);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(h[e]);
+            v[8 * j + 2 * e] *= gelu_grad_fast_f(f.x);
+            v[8 * j + 2 * e + 1] *= gelu_grad_fast_f(f.y);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (col + i < p.n) v[i] *= gelu_grad_fast_f(to_f<OutT>(aux_row[i]));
+    }
   }
   if (p.drop_thr) {
     if ((e0 & 1) == 0) {
@@ -300,7 +331,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
             __syncwarp();
           }
-          epi_act_drop<CW>(v, p, (unsigned long long)(boff + (long long)row * p.ldc + col));
+          epi_act_drop<CW, OutT>(v, p, (unsigned long long)(boff + (long long)row * p.ldc + col),
+                                 reinterpret_cast<const OutT*>(p.aux) + boff + (long long)row * p.ld_aux + col, row < p.m, col, full);
           if (p.res && row < p.m) {
             const OutT* rrow = reinterpret_cast<const OutT*>(p.res) + (long long)tc.b1 * p.r_bs1 + (long long)tc.b2 * p.r_bs2 +
                                (long long)row * p.ldr + col;
@@ -375,6 +407,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               const long long off = (long long)grow * p.ldc + col;
               if (pbase) pbase[off] = from_f<OutT>(v);
               if (p.act == 1) v = gelu_fast_f(v);
+              else if (p.act == 2) v *= gelu_grad_fast_f(to_f<OutT>(reinterpret_cast<const OutT*>(p.aux)[boff + (long long)grow * p.ld_aux + col]));
               if (p.drop_thr) v *= dropout_scale(p.seed, (unsigned long long)(boff + off), p.drop_thr, p.inv_keep);
               if (rbase) v += to_f<OutT>(rbase[(long long)grow * p.ldr + col]);
               if (kF32) {
@@ -524,6 +557,7 @@ int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
   TS_REQUIRE(ctx, gemm_tc_supported(d), TS_EUNSUPPORTED,
              "gemm_tc: operands must be bf16 with 16-byte aligned bases/strides");
   TS_REQUIRE(ctx, !(d->accumulate && (d->act || d->residual)), TS_EINVAL, "gemm: accumulate excludes act/residual");
+  TS_REQUIRE(ctx, d->act != 2 || d->act_aux, TS_EINVAL, "gemm: act 2 needs act_aux");
   const int nb1 = d->batch1 > 0 ? d->batch1 : 1, nb2 = d->batch2 > 0 ? d->batch2 : 1;
   // Tile-N and split-K choice from a small cost model (units: 64-deep k-blocks of one 128 x 1 column strip):
   //   cost = waves * k_blocks_per_work_item * bn * eff(bn) + tail_epilogue * bn
@@ -581,7 +615,7 @@ int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
     if (r) return r;
   }
   EpiParams ep;
-  ep.c = d->c; ep.c_pre = d->c_preact; ep.res = d->residual; ep.bias = d->bias;
+  ep.c = d->c; ep.c_pre = d->c_preact; ep.res = d->residual; ep.bias = d->bias; ep.aux = d->act_aux; ep.ld_aux = d->ld_aux;
   ep.ldc = d->ldc; ep.ldr = d->ldr; ep.c_bs1 = d->c_bs1; ep.c_bs2 = d->c_bs2; ep.r_bs1 = d->r_bs1; ep.r_bs2 = d->r_bs2; ep.bias_bs1 = d->bias_bs1;
   ep.alpha = d->alpha; ep.act = d->act; ep.accumulate = d->accumulate;
   ep.m = d->m; ep.n = d->n; ep.k = d->k; ep.nb1 = nb1;

@@ -86,6 +86,7 @@ struct GemmB {
   GemmB& cstride(long long s1, long long s2) { d.c_bs1 = s1; d.c_bs2 = s2; return *this; }
   GemmB& bias(const float* b, long long bs1 = 0) { d.bias = b; d.bias_bs1 = bs1; return *this; }
   GemmB& gelu(void* preact) { d.act = 1; d.c_preact = preact; return *this; }
+  GemmB& gelu_grad(const void* u, long long ld) { d.act = 2; d.act_aux = u; d.ld_aux = ld; return *this; }
   GemmB& res(const void* r, long long ld, long long s1 = 0, long long s2 = 0) { d.residual = r; d.ldr = ld; d.r_bs1 = s1; d.r_bs2 = s2; return *this; }
   GemmB& alpha(float a) { d.alpha = a; return *this; }
   GemmB& drop(float rate, uint64_t seed) { d.drop = rate; d.seed = seed; return *this; }

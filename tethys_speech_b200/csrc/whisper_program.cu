@@ -258,7 +258,8 @@ static int attn_backward(Whisper* m, const void* q, long long ldq, const void* k
 
 // dW += X^T dY (fp32; gradient arena zeroed at the start of backward), db += colsum(dY), dX = dY W^T (+ dres)
 static int dense_bwd(Whisper* m, const void* X, int K, const void* dY, int Nn, long long w_off, long long ldw, long long b_off,
-                     void* dX, const void* dres, long long rows, cudaStream_t st) {
+                     void* dX, const void* dres, long long rows, cudaStream_t st, const void* gelu_u = nullptr, float drop = 0.f,
+                     uint64_t drop_seed = 0) {
   Ctx* ctx = m->ctx;
   const int dt = m->prec;
   TS_TRY(GemmB(dt, TS_F32).A(X, 1, K).B(dY, 1, Nn).C(m->G + w_off, ldw).mnk(K, Nn, (int)rows).acc().run(ctx, st));
@@ -267,6 +268,7 @@ static int dense_bwd(Whisper* m, const void* X, int K, const void* dY, int Nn, l
     GemmB g(dt, dt);
     g.A(dY, 0, Nn).B(m->W(w_off), 0, ldw).C(dX, K).mnk((int)rows, K, Nn);
     if (dres) g.res(dres, K);
+    if (gelu_u) g.gelu_grad(gelu_u, K).drop(drop, drop_seed);   // backward of the GELU (+dropout) this gradient feeds, in the epilogue
     TS_TRY(g.run(ctx, st));
   }
   return 0;

@@ -4,6 +4,7 @@ program in libtethys.so (csrc/whisper_program.cu) through ctypes. No TensorFlow,
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -248,7 +249,7 @@ def distributed_train_step(strategy, model, dist_inputs, optimizer, dropout=True
         features, labels = inputs
         outputs = model(features, labels=labels, training=True, dropout=dropout)
         loss = outputs["loss"]
-        if strategy.num_replicas_in_sync > 1:
+        if strategy.num_replicas_in_sync > 1 and not os.environ.get("TETHYS_NO_OVERLAP"):
             gradients = model.gradient_allreduced(strategy)      # bucketed NCCL all-reduce overlapped with backward
             optimizer.apply_gradients(gradients, strategy=strategy, already_reduced=True)
         else:
