@@ -210,6 +210,9 @@ int ts_w2v_bind(ts_w2v* m, float* params, float* grads, void* params_bf16 /*bf16
 int ts_w2v_sync_compute_weights(ts_w2v* m, void* stream); /* fp32 master -> bf16 compute copy */
 int ts_w2v_forward(ts_w2v* m, const float* wave /*[B,N]*/, int batch, int n_samples, const int32_t* neg, int64_t neg_bs,
                    int64_t neg_ts, float loss_div /*num replicas, V:1231*/, uint64_t seed, int training, void* stream);
+/* Wav2Vec2FeatureExtractor.call only (V:283-298): conv stack + GroupNorm/GELU + positional conv + LayerNorm, inference mode;
+ * result in the "extract_features" buffer. Used by the front-end microbench (BASELINE config 5). */
+int ts_w2v_forward_features(ts_w2v* m, const float* wave, int batch, int n_samples, void* stream);
 int ts_w2v_backward(ts_w2v* m, int stage_from, int stage_to, void* stream);
 /* named views into the workspace of the last forward ("scalars" = {loss, contrastive, perplexity, raw sum}). */
 int ts_w2v_get_buffer(ts_w2v* m, const char* name, void** ptr, int32_t* dtype, int32_t* ndim, int64_t* shape4);

@@ -115,6 +115,7 @@ SYMBOLS = {
     "ts_w2v_bind": (_I, [_P, _P, _P, _P, _P, _L]),
     "ts_w2v_sync_compute_weights": (_I, [_P, _P]),
     "ts_w2v_forward": (_I, [_P, _P, _I, _I, _P, _L, _L, _F, C.c_uint64, _I, _P]),
+    "ts_w2v_forward_features": (_I, [_P, _P, _I, _I, _P]),
     "ts_w2v_backward": (_I, [_P, _I, _I, _P]),
     "ts_w2v_get_buffer": (_I, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L)]),
     "ts_whisper_create": (_I, [_P, C.POINTER(WhisperCfg), _I, C.POINTER(_P)]),

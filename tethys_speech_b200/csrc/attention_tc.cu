@@ -42,7 +42,7 @@ struct AttnParams {
   int B, nh, Tq, Tk;
   float scale;
   uint32_t drop_thr; float inv_keep; unsigned long long seed;
-  int drop_pitch;   // even row pitch of the per-(batch, head) dropout index space (element = row * pitch + column)
+  int drop_pitch;   // 32-key chunks per query row in the per-(batch, head) dropout stream (chunk index = row * pitch + key / 32)
   bf16* o; bf16* o_lo; long long o_ld, o_bs;
   float* stats;   // [B, nh, Tq, 2]
   const bf16* o_in; const bf16* d_o;  // same layout as o
@@ -93,6 +93,24 @@ __device__ __forceinline__ bool smem_aligned(const void* smem, int* watchdog) {
   if (threadIdx.x == 0 && watchdog) atomicExch(watchdog, 99);
   return false;
 }
+
+// zero the dropped ones among a thread's 32 consecutive chunk elements (compile-time unrolled LCG jump-ahead)
+template <int T> struct DropUnroll {
+  static __device__ __forceinline__ void apply(float (&v)[32], uint32_t x0, uint32_t thr) {
+    v[T] = drop_elem<T>(x0) >= thr ? v[T] : 0.f;
+    DropUnroll<T + 1>::apply(v, x0, thr);
+  }
+  // z[t] = keep ? inv_keep : 0
+  static __device__ __forceinline__ void scales(float (&z)[32], uint32_t x0, uint32_t thr, float inv_keep) {
+    z[T] = drop_elem<T>(x0) >= thr ? inv_keep : 0.f;
+    DropUnroll<T + 1>::scales(z, x0, thr, inv_keep);
+  }
+};
+template <> struct DropUnroll<32> {
+  static __device__ __forceinline__ void apply(float (&)[32], uint32_t, uint32_t) {}
+  static __device__ __forceinline__ void scales(float (&)[32], uint32_t, uint32_t, float) {}
+};
+__device__ __forceinline__ void drop_apply32(float (&v)[32], uint32_t x0, uint32_t thr) { DropUnroll<0>::apply(v, x0, thr); }
 
 // ------------------------------------------------------------------------------------------------------------
 // forward
@@ -197,7 +215,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int i = q0 + r;                    // query index
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const DropKey dkey = make_drop_key(p.seed, (unsigned long long)(b * p.nh + h), p.drop_thr);
-    const uint32_t drow = (uint32_t)i * (uint32_t)p.drop_pitch;   // element index inside this (batch, head) stream
+    const uint32_t drow = (uint32_t)i * (uint32_t)p.drop_pitch;   // chunk index of this row's first 32-key chunk in the stream
     const float c1 = p.scale * kLog2e;
     float m_run = -INFINITY, l_part = 0.f;
     bool ok = true;
@@ -252,13 +270,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int t = 0; t < 32; ++t) { sv[t] = ex2f((sv[t] - m_run) * kLog2e); l_part += sv[t]; }
       }
       if (p.drop_thr) {  // dropped probabilities become 0; the common factor 1/keep is applied to O at the end
-        const uint32_t pb = (drow + (uint32_t)col0) >> 1;
-#pragma unroll
-        for (int t = 0; t < 32; t += 2) {
-          const uint32_t w = drop_word32(dkey, pb + (t >> 1));
-          sv[t] = drop_keep_even(dkey, w) ? sv[t] : 0.f;
-          sv[t + 1] = drop_keep_odd(dkey, w) ? sv[t + 1] : 0.f;
-        }
+        const uint32_t x0 = drop_chunk_seed(dkey, drow + ((uint32_t)col0 >> 5));
+        drop_apply32(sv, x0, dkey.thr);
       }
       if (j >= 2) {  // P buffer `bsel` is free once P.V of tile j-2 has retired
         if (!ptx::mbar_wait(&pv_done[bsel], ((j - 2) >> 1) & 1, watchdog, 18)) { ok = false; break; }
@@ -354,32 +367,24 @@ __device__ __forceinline__ void store_row32(bf16* dst, const uint32_t (&rg)[32],
 template <int MASK, bool RAGGED>
 __device__ __forceinline__ void dq_chunk(const uint32_t (&rs)[32], const uint32_t (&rd)[32], float (&ds)[32], const AttnParams& p,
                                          float c1, float c0, float m_i, float ll2, float D, int i, int col0, const DropKey& dkey,
-                                         uint32_t pair0) {
+                                         uint32_t chunk_index) {
+  float z[32];
+  if (p.drop_thr) DropUnroll<0>::scales(z, drop_chunk_seed(dkey, chunk_index), dkey.thr, p.inv_keep);
 #pragma unroll
-  for (int t = 0; t < 32; t += 2) {
-    float p0, p1;
+  for (int t = 0; t < 32; ++t) {
+    float p0;
     if (MASK == 0) {
       p0 = ex2f(fmaf(__uint_as_float(rs[t]), c1, -c0));
-      p1 = ex2f(fmaf(__uint_as_float(rs[t + 1]), c1, -c0));
     } else {
-      float s0 = __uint_as_float(rs[t]) * p.scale, s1 = __uint_as_float(rs[t + 1]) * p.scale;
+      float s0 = __uint_as_float(rs[t]) * p.scale;
       if (col0 + t <= i) s0 += -1e9f;
-      if (col0 + t + 1 <= i) s1 += -1e9f;
       p0 = ex2f((s0 - m_i) * kLog2e - ll2);
-      p1 = ex2f((s1 - m_i) * kLog2e - ll2);
     }
     if (RAGGED) {
       if (col0 + t >= p.Tk) p0 = 0.f;
-      if (col0 + t + 1 >= p.Tk) p1 = 0.f;
     }
-    if (p.drop_thr) {
-      const uint32_t w = drop_word32(dkey, pair0 + (t >> 1));
-      ds[t] = p0 * fmaf(__uint_as_float(rd[t]), drop_keep_even(dkey, w) ? p.inv_keep : 0.f, -D);
-      ds[t + 1] = p1 * fmaf(__uint_as_float(rd[t + 1]), drop_keep_odd(dkey, w) ? p.inv_keep : 0.f, -D);
-    } else {
-      ds[t] = p0 * (__uint_as_float(rd[t]) - D);
-      ds[t + 1] = p1 * (__uint_as_float(rd[t + 1]) - D);
-    }
+    if (p.drop_thr) ds[t] = p0 * fmaf(__uint_as_float(rd[t]), z[t], -D);
+    else ds[t] = p0 * (__uint_as_float(rd[t]) - D);
   }
 }
 
@@ -509,9 +514,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       ptx::tmem_ld_32x32(tDP + lane_off + half * 32, rd);
       ptx::tmem_ld_wait();
       float ds[32];
-      const uint32_t pair0 = (drow + (uint32_t)col0) >> 1;
-      if (col0 + 32 > p.Tk) dq_chunk<MASK, true>(rs, rd, ds, p, c1, c0, m_i, ll2, D, i, col0, dkey, pair0);
-      else dq_chunk<MASK, false>(rs, rd, ds, p, c1, c0, m_i, ll2, D, i, col0, dkey, pair0);
+      const uint32_t cidx = drow + ((uint32_t)col0 >> 5);
+      if (col0 + 32 > p.Tk) dq_chunk<MASK, true>(rs, rd, ds, p, c1, c0, m_i, ll2, D, i, col0, dkey, cidx);
+      else dq_chunk<MASK, false>(rs, rd, ds, p, c1, c0, m_i, ll2, D, i, col0, dkey, cidx);
       if (j > 0 && !ptx::mbar_wait(dq_done, (j - 1) & 1, watchdog, 26)) { ok = false; break; }  // dS smem free again
       store_chunk32(sDS, r, half, ds);
       ptx::fence_proxy_async_smem();
@@ -531,6 +536,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem, 256);
 }
+
+__device__ __forceinline__ uint32_t lcg_a_rt(int t) { uint32_t a = 1u; for (int i = 0; i < t; ++i) a *= 1664525u; return a; }
+__device__ __forceinline__ uint32_t lcg_c_rt(int t) { uint32_t c = 0u; for (int i = 0; i < t; ++i) c = c * 1664525u + 1013904223u; return c; }
 
 // ---- dK, dV: CTA = 128 key rows, loop over 64-row query tiles, TRANSPOSED scores ------------------------------------
 // S^T = K Q^T and dP^T = V dO^T put the key index on the TMEM lanes, so a thread owns one key row and 32 query columns,
@@ -633,8 +641,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const int et = (warp - 2) * 32 + lane;    // 0..255 among the element-wise threads
     const float c1 = p.scale * kLog2e;
     const DropKey dkey = make_drop_key(p.seed, (unsigned long long)(b * p.nh + h), p.drop_thr);
-    const uint32_t half_pitch = (uint32_t)p.drop_pitch >> 1;
-    const bool odd = lane & 1;                // parity of jrow (kv0 is a multiple of 128)
+    // dropout: this warp's 32 key rows are ONE chunk (index jrow >> 5) of every query row; lane t hashes the chunk seed of
+    // query column t, the seed of column c is fetched by shuffle and advanced to this lane's position with its own
+    // jump-ahead constants (a_l, c_l)
+    const uint32_t my_chunk = (uint32_t)jrow >> 5;
+    const uint32_t a_l = lcg_a_rt(lane + 1), c_l = lcg_c_rt(lane + 1);
     bool ok = true;
     for (int it = 0; it < nq && ok; ++it) {
       const int buf = it & 1;
@@ -659,6 +670,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const int i0 = it * 64 + half * 32;     // first query column of this thread
       const float* sc0 = st + half * 32;
       const float* sD = st + 64 + half * 32;
+      // chunk seed of query column (i0 + lane) for this warp's key chunk
+      const uint32_t xseed = p.drop_thr ? drop_chunk_seed(dkey, (uint32_t)(i0 + lane) * (uint32_t)p.drop_pitch + my_chunk) : 0u;
 #pragma unroll
       for (int t = 0; t < 32; t += 2) {
         float p0, p1;
@@ -674,13 +687,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         if (!rowlive) { p0 = 0.f; p1 = 0.f; }
         if (p.drop_thr) {
-          // the pair (jrow & ~1, jrow | 1) of query column i shares one hash word: each lane hashes the column whose parity
-          // matches its own and fetches the other column's word from its neighbour lane
-          const uint32_t wo = drop_word32(dkey, (uint32_t)(i0 + t + (odd ? 1 : 0)) * half_pitch + ((uint32_t)jrow >> 1));
-          const uint32_t wn = __shfl_xor_sync(0xffffffffu, wo, 1);
-          const uint32_t w0 = odd ? wn : wo, w1 = odd ? wo : wn;   // words of columns t and t + 1
-          const bool k0 = odd ? drop_keep_odd(dkey, w0) : drop_keep_even(dkey, w0);
-          const bool k1 = odd ? drop_keep_odd(dkey, w1) : drop_keep_even(dkey, w1);
+          const uint32_t w0 = __shfl_sync(0xffffffffu, xseed, t) * a_l + c_l;
+          const uint32_t w1 = __shfl_sync(0xffffffffu, xseed, t + 1) * a_l + c_l;
+          const bool k0 = w0 >= dkey.thr, k1 = w1 >= dkey.thr;
           ds[t] = p0 * fmaf(__uint_as_float(rd[t]), k0 ? p.inv_keep : 0.f, -sD[t]);
           ds[t + 1] = p1 * fmaf(__uint_as_float(rd[t + 1]), k1 ? p.inv_keep : 0.f, -sD[t + 1]);
           pz[t] = k0 ? p0 : 0.f;
@@ -747,7 +756,7 @@ static int fill_params(Ctx* ctx, const ts_attn_desc* d, AttnParams* p) {
   p->B = d->batch; p->nh = d->heads; p->Tq = d->tq; p->Tk = d->tk; p->scale = d->scale;
   drop_params(d->drop, &p->drop_thr, &p->inv_keep);
   p->seed = d->seed;
-  p->drop_pitch = (d->tk + 1) & ~1;
+  p->drop_pitch = (d->tk + 31) >> 5;
   TS_REQUIRE(ctx, (long long)d->tq * p->drop_pitch < (1ll << 32), TS_ESHAPE, "attention: Tq * Tk must stay below 2^32");
   p->o = (bf16*)d->o; p->o_lo = (bf16*)d->o_lo; p->o_ld = d->o_ld; p->o_bs = d->o_bs;
   TS_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d->o_lo) & 15) == 0, TS_EINVAL, "attention: o_lo must be 16-byte aligned");

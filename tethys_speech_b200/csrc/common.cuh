@@ -177,10 +177,11 @@ __device__ __forceinline__ void dropout_scale2(uint64_t seed, uint64_t idx_even,
 }
 
 
-// Cheaper 32-bit variant for kernels that own a whole dropout "stream" (the fused attention kernels: one stream per
-// (batch, head), element index = row * pitch + column < 2^32): two multiply/xor-shift rounds per element PAIR.
-//   keep(even element) <=> low 16 bits of the word >= thr16,  keep(odd element) <=> high 16 bits >= thr16
-struct DropKey { uint32_t k1, k2m, thr_hi; };
+// Cheapest variant, for kernels that own a whole dropout "stream" and walk it in 32-element chunks (the fused attention
+// kernels: one stream per (batch, head); a chunk = 32 consecutive keys of one query row). One hash per CHUNK seeds a
+// 32-step LCG whose t-th state is reached directly with the jump-ahead constants (x_t = x_0 * A^t + C_t, one IMAD per
+// element), and element t is kept iff x_t >= rate * 2^32. Any kernel can regenerate element (row, chunk, t) on its own.
+struct DropKey { uint32_t k1, k2m, thr; };
 __host__ __device__ __forceinline__ DropKey make_drop_key(uint64_t seed, uint64_t stream, uint32_t thr) {
   uint64_t z = seed + (stream + 1) * 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -189,18 +190,30 @@ __host__ __device__ __forceinline__ DropKey make_drop_key(uint64_t seed, uint64_
   DropKey k;
   k.k1 = (uint32_t)z;
   k.k2m = (uint32_t)(z >> 32) * 0x846ca68bu;
-  k.thr_hi = thr & 0xffff0000u;
+  k.thr = thr;
   return k;
 }
-__host__ __device__ __forceinline__ uint32_t drop_word32(const DropKey& k, uint32_t pair) {
-  uint32_t x = pair ^ k.k1;
+// chunk seed: a full-avalanche hash of the chunk index (row * chunks_per_row + chunk)
+__host__ __device__ __forceinline__ uint32_t drop_chunk_seed(const DropKey& k, uint32_t chunk_index) {
+  uint32_t x = chunk_index ^ k.k1;
+  x ^= x >> 16;
   x *= 0x7feb352du;
   x ^= x >> 15;
   x = x * 0x846ca68bu + k.k2m;
   x ^= x >> 16;
   return x;
 }
-__host__ __device__ __forceinline__ bool drop_keep_even(const DropKey& k, uint32_t w) { return (w << 16) >= k.thr_hi; }
-__host__ __device__ __forceinline__ bool drop_keep_odd(const DropKey& k, uint32_t w) { return w >= k.thr_hi; }
+__host__ __device__ constexpr uint32_t lcg_a(int t) { return t == 0 ? 1u : lcg_a(t - 1) * 1664525u; }
+__host__ __device__ constexpr uint32_t lcg_c(int t) { return t == 0 ? 0u : lcg_c(t - 1) * 1664525u + 1013904223u; }
+// element t (0..31) of the chunk seeded with x0 (t + 1 LCG steps from the seed, so the seed itself is never used)
+template <int T> __host__ __device__ __forceinline__ uint32_t drop_elem(uint32_t x0) {
+  constexpr uint32_t A = lcg_a(T + 1), C = lcg_c(T + 1);
+  return x0 * A + C;
+}
+__host__ __device__ __forceinline__ uint32_t drop_elem_rt(uint32_t x0, int t) {
+  uint32_t x = x0;
+  for (int i = 0; i <= t; ++i) x = x * 1664525u + 1013904223u;
+  return x;
+}
 
 }  // namespace ts

@@ -231,7 +231,8 @@ __global__ void w2v_finalize_scalars(float* s, float inv_rows, float div_w) {
   s[0] = loss;
 }
 
-static int w2v_forward(W2V* m, const float* wave, const int* neg, long long neg_bs, long long neg_ts, cudaStream_t st) {
+static int w2v_forward(W2V* m, const float* wave, const int* neg, long long neg_bs, long long neg_ts, cudaStream_t st,
+                       bool features_only = false) {
   Ctx* ctx = m->ctx;
   const ts_w2v_config& c = m->cfg;
   const int dt = m->prec, B = m->B, n = m->nconv, G = c.pos_groups;
@@ -271,6 +272,7 @@ static int w2v_forward(W2V* m, const float* wave, const int* neg, long long neg_
                          m->fe_rstd, M, C, c.ln_eps, st));
     if (m->drop(c.hidden_dropout) > 0) TS_TRY(dropout_apply(ctx, dt, m->ef, m->ef, (long long)M * C, c.hidden_dropout, site_seed(seed, 1), st));
   }
+  if (features_only) return 0;   // Wav2Vec2FeatureExtractor.call only (V:283-298): front-end microbench / feature export
   // ---- feature projection (V:777-779) -------------------------------------------------------------------
   TS_TRY(GemmB(dt, dt).A(m->ef, 0, C).B(m->W(m->fp_w), 1, H).C(m->fp_out, H).bias(m->P + m->fp_b).mnk(M, H, C).run(ctx, st));
   TS_TRY(layernorm_fwd(ctx, dt, m->fp_out, nullptr, m->P + m->fp_ln_g, m->P + m->fp_ln_b, m->hs, nullptr, m->fp_mean,
@@ -578,6 +580,22 @@ int ts_w2v_forward(ts_w2v* h, const float* wave, int B, int N, const int* neg, i
   TS_TRY(posconv_flip_weight(ctx, m->prec, m->W(m->pos_w), m->wt_flip, m->cfg.pos_kernel, m->cfg.conv_dim[m->cfg.n_conv - 1],
                              m->cfg.pos_groups, st));
   return w2v_forward(m, wave, neg, neg_bs, neg_ts, st);
+}
+int ts_w2v_forward_features(ts_w2v* h, const float* wave, int B, int N, void* stream) {
+  W2V* m = reinterpret_cast<W2V*>(h);
+  Ctx* ctx = m->ctx;
+  cudaStream_t st = (cudaStream_t)stream;
+  TS_REQUIRE(ctx, m->P && m->ws, TS_EINVAL, "w2v_forward_features: call ts_w2v_bind first");
+  TS_REQUIRE(ctx, B > 0 && N > 0 && wave, TS_EINVAL, "w2v_forward_features: bad arguments");
+  if (!m->planned || m->B != B || m->N != N) {
+    Bump bp;
+    bp.base = m->ws;
+    TS_TRY(plan(m, B, N, bp));
+    TS_REQUIRE(ctx, (long long)bp.off <= m->ws_bytes, TS_EINVAL, "w2v_forward_features: workspace too small");
+    m->planned = true;
+  }
+  m->seed = 0; m->training = 0; m->loss_div = 1.f; m->fwd_done = false;
+  return w2v_forward(m, wave, nullptr, 0, 0, st, true);
 }
 int ts_w2v_backward(ts_w2v* h, int stage_from, int stage_to, void* stream) {
   W2V* m = reinterpret_cast<W2V*>(h);

@@ -211,6 +211,18 @@ class Wav2Vec2ForPreTraining:
             t = -(-t // s)
         return t
 
+    def extract_features(self, inputs):
+        """Wav2Vec2FeatureExtractor.call (V:283-298) only: conv stack + GroupNorm/GELU + positional conv + LayerNorm in
+        inference mode. Returns the [B, T, C] feature tensor (a view of the workspace)."""
+        p = self._prog
+        x = to_device(inputs, torch.float32, p.device)
+        B, N = x.shape
+        p.ensure_workspace(B, N)
+        p.sync_weights()
+        p.ctx.check(p.lib.ts_w2v_forward_features(p.h, ptr(x), B, N, stream_ptr()))
+        self._last = {"x": x}
+        return p.buffer("extract_features")
+
     def __call__(self, inputs, attention_mask=None, output_attentions=False, output_hidden_states=False, training=False,
                  neg_indices=None, loss_div=1.0, dropout=True):
         """inputs: [B, N] waveform (torch / numpy / DLPack producer). With training=True the quantiser, the projection

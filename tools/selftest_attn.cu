@@ -18,25 +18,26 @@ static float frand() {
 }
 static float bfr(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
 
-// host copy of common.cuh: make_drop_key / drop_word32 (one dropout stream per (batch, head))
-struct DropKey { uint32_t k1, k2m, thr_hi; };
+// host copy of common.cuh: make_drop_key / drop_chunk_seed / LCG jump (one dropout stream per (batch, head))
+struct DropKey { uint32_t k1, k2m, thr; };
 static DropKey make_drop_key(uint64_t seed, uint64_t stream, uint32_t thr) {
   uint64_t z = seed + (stream + 1) * 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   z = z ^ (z >> 31);
-  DropKey k; k.k1 = (uint32_t)z; k.k2m = (uint32_t)(z >> 32) * 0x846ca68bu; k.thr_hi = thr & 0xffff0000u;
+  DropKey k; k.k1 = (uint32_t)z; k.k2m = (uint32_t)(z >> 32) * 0x846ca68bu; k.thr = thr;
   return k;
 }
-static uint32_t drop_word32(const DropKey& k, uint32_t pair) {
-  uint32_t x = pair ^ k.k1;
-  x *= 0x7feb352du; x ^= x >> 15; x = x * 0x846ca68bu + k.k2m; x ^= x >> 16;
+static uint32_t drop_chunk_seed(const DropKey& k, uint32_t chunk_index) {
+  uint32_t x = chunk_index ^ k.k1;
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x = x * 0x846ca68bu + k.k2m; x ^= x >> 16;
   return x;
 }
-static float dropout_scale(const DropKey& k, uint32_t idx, float inv_keep) {
-  const uint32_t w = drop_word32(k, idx >> 1);
-  const bool keep = (idx & 1) ? (w >= k.thr_hi) : ((w << 16) >= k.thr_hi);
-  return keep ? inv_keep : 0.f;
+// element (row i, key j): chunk index i * chunks_per_row + j / 32, position j % 32 -> (position + 1) LCG steps from the seed
+static float dropout_scale(const DropKey& k, uint32_t i, uint32_t j, uint32_t chunks_per_row, float inv_keep) {
+  uint32_t x = drop_chunk_seed(k, i * chunks_per_row + (j >> 5));
+  for (uint32_t t = 0; t <= (j & 31); ++t) x = x * 1664525u + 1013904223u;
+  return x >= k.thr ? inv_keep : 0.f;
 }
 
 struct Case { const char* name; int B, nh, Tq, Tk, mask; float drop; bool cross; };
@@ -99,7 +100,6 @@ static int run_case(ts_ctx* ctx, const Case& cs, bool timing) {
     const __nv_bfloat16* GV = cs.cross ? hgkv.data() + H : hgq.data() + 2 * H;
     uint32_t thr = 0; float ik = 1.f;
     if (cs.drop > 0) { thr = (uint32_t)((double)cs.drop * 4294967296.0); ik = 1.f / (1.f - cs.drop); }
-    const long long pitch = ((long long)Tk + 1) & ~1ll;
     double eo = 0, edq = 0, edk = 0, edv = 0, mo = 0, mdq = 0, mdk = 0, mdv = 0;
     std::vector<double> P((size_t)Tq * Tk), Z((size_t)Tq * Tk), dS((size_t)Tq * Tk), rdk((size_t)Tk * 64), rdv((size_t)Tk * 64);
     for (int b = 0; b < B; ++b)
@@ -124,8 +124,7 @@ static int run_case(ts_ctx* ctx, const Case& cs, bool timing) {
           double o[64] = {0};
           for (int j = 0; j < Tk; ++j) {
             P[(size_t)i * Tk + j] /= l;
-            const uint32_t idx = (uint32_t)i * (uint32_t)pitch + (uint32_t)j;
-            Z[(size_t)i * Tk + j] = thr ? dropout_scale(make_drop_key(d.seed, (uint64_t)(b * nh + h), thr), idx, ik) : 1.0;
+            Z[(size_t)i * Tk + j] = thr ? dropout_scale(make_drop_key(d.seed, (uint64_t)(b * nh + h), thr), (uint32_t)i, (uint32_t)j, (uint32_t)((Tk + 31) >> 5), ik) : 1.0;
             const double pz = P[(size_t)i * Tk + j] * Z[(size_t)i * Tk + j];
             for (int c = 0; c < 64; ++c) o[c] += pz * v[j * kv_ld + c];
           }
