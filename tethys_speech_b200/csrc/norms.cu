@@ -340,32 +340,42 @@ __global__ void __launch_bounds__(256, 4) gn_gelu_fwd_kernel(const T* __restrict
   // fold the normalisation into one FMA per element: u = x * a + c
 #pragma unroll
   for (int i = 0; i < 8; ++i) { ga[i] *= rs; be[i] = fmaf(-mu, ga[i], be[i]); }
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
-  const long long r1 = min(y_rpb, r0 + rows_per_block);
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min((int)y_rpb, r0 + rows_per_block);
   const T* xb = x + (long long)b * x_rpb * C + tc * 8;
   T* yb = y + (long long)b * y_rpb * C + tc * 8;
-  for (long long r = r0 + tr; r < r1; r += rpi * GN_UNROLL) {
-    float v[GN_UNROLL][8];
-    bool in[GN_UNROLL];
-#pragma unroll
-    for (int u = 0; u < GN_UNROLL; ++u) {
-      const long long t = r + u * rpi - y_left;
-      in[u] = (r + u * rpi < r1) && t >= 0 && t < T_;
-      if (in[u]) load8<T>(xb + t * C, v[u]);
-      else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < GN_UNROLL; ++u) {
-      if (r + u * rpi >= r1) break;
+  // rows of y outside [y_left, y_left + T) are zero padding for the next conv's windows
+  const int d0 = max(r0, y_left), d1 = min(r1, y_left + T_);   // data rows of this block
+  for (int r = r0 + tr; r < r1; r += rpi) {
+    if (r < d0 || r >= d1) {
       float o[8];
-      const float keep = in[u] ? 1.f : 0.f;   // rows outside [0, T) are zero padding for the next conv's windows
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = keep * gelu_t<T>(fmaf(v[u][i], ga[i], be[i]));
-      store8<T>(yb + (r + u * rpi) * C, o);
+      for (int i = 0; i < 8; ++i) o[i] = 0.f;
+      store8<T>(yb + r * C, o);
     }
+  }
+  // main loop: two independent rows in flight per thread, pointer increments only
+  int r = d0 + tr;
+  const T* xp = xb + (r - y_left) * C;
+  T* yp = yb + r * C;
+  const int step = rpi * C;
+  for (; r + rpi < d1; r += 2 * rpi, xp += 2 * step, yp += 2 * step) {
+    float v0[8], v1[8], o[8];
+    load8<T>(xp, v0);
+    load8<T>(xp + step, v1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = gelu_t<T>(fmaf(v0[i], ga[i], be[i]));
+    store8<T>(yp, o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = gelu_t<T>(fmaf(v1[i], ga[i], be[i]));
+    store8<T>(yp + step, o);
+  }
+  if (r < d1) {
+    float v0[8], o[8];
+    load8<T>(xp, v0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = gelu_t<T>(fmaf(v0[i], ga[i], be[i]));
+    store8<T>(yp, o);
   }
 }
 
@@ -391,23 +401,23 @@ template <typename T, int KS>
 __device__ __forceinline__ void gn_load_upstream(const T* __restrict__ da_row0, const T* __restrict__ dcol_b, const Col2imSrc& col,
                                                  int t, int C, float (&d)[8]) {
   if constexpr (KS == 0) {
-    load8<T>(da_row0 + (long long)t * C, d);
-  } else if constexpr (KS > 0) {
+    load8<T>(da_row0 + t * C, d);
+  } else if constexpr (KS == 3 * 8 + 2) {
+    // k = 3, s = 2: an even q = t + left receives taps 0 (window q/2) and 2 (window q/2 - 1), an odd one tap 1 (window (q-1)/2)
+    const int q0 = t + col.left, e = q0 & 1, w = q0 >> 1, rowlen = 3 * C;
+    float a[8], bb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = 0.f; bb[i] = 0.f; }
+    if (w < col.t_next) load8<T>(dcol_b + w * rowlen + e * C, a);
+    if (e == 0 && w >= 1 && w - 1 < col.t_next) load8<T>(dcol_b + (w - 1) * rowlen + 2 * C, bb);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = a[i] + bb[i];
+  } else if constexpr (KS == 2 * 8 + 2) {
+    // k = 2, s = 2: exactly one tap (q & 1) of window q / 2
+    const int q0 = t + col.left, e = q0 & 1, w = q0 >> 1;
 #pragma unroll
     for (int i = 0; i < 8; ++i) d[i] = 0.f;
-    constexpr int K = KS >> 3, S = KS & 7;
-    const long long rowlen = (long long)K * C;
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-      const int q = t + col.left - j;
-      const int w = q / S;   // S is a compile-time power of two here
-      if (q >= 0 && (q % S) == 0 && w < col.t_next) {
-        float v[8];
-        load8<T>(dcol_b + (long long)w * rowlen + (long long)j * C, v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] += v[i];
-      }
-    }
+    if (w < col.t_next) load8<T>(dcol_b + w * (2 * C) + e * C, d);
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) d[i] = 0.f;
@@ -465,7 +475,7 @@ __global__ void __launch_bounds__(256, 2) gn_gelu_bwd1_kernel(const T* __restric
         const int tt = t + u * rpi;
         if (tt < t1) {
           gn_load_upstream<T, KS>(da_b, dcol_b, col, tt, C, d[u]);
-          load8<T>(xb + (long long)tt * C, v[u]);
+          load8<T>(xb + tt * C, v[u]);
         }
       }
 #pragma unroll
@@ -481,7 +491,7 @@ __global__ void __launch_bounds__(256, 2) gn_gelu_bwd1_kernel(const T* __restric
           ag[i] = fmaf(dact, xh, ag[i]);
           ab[i] += dact;
         }
-        store8<T>(dxb + (long long)tt * C, o);
+        store8<T>(dxb + tt * C, o);
       }
     }
     // group sums for pass 2 follow from the per-channel sums: sum(dact*gamma) and sum(dact*gamma*xhat)
@@ -517,33 +527,42 @@ __global__ void __launch_bounds__(256, 4) gn_gelu_bwd2_kernel(const T* __restric
   const float m1 = (float)(accum[((long long)b * G + g) * 2] / n), m2 = (float)(accum[((long long)b * G + g) * 2 + 1] / n);
   float ga[8];
   load8<float>(gamma + tc * 8, ga);
-  const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(dx_rpb, r0 + rows_per_block);
+  const int r0 = blockIdx.x * rows_per_block, r1 = min((int)dx_rpb, r0 + rows_per_block);
   const T* xb = x + (long long)b * x_rpb * C + tc * 8;
   T* db = dx + (long long)b * dx_rpb * C + tc * 8;
-  for (long long t = r0 + tr; t < r1; t += rpi * GN_UNROLL) {
-    float v[GN_UNROLL][8], d[GN_UNROLL][8];
+  const int d1 = min(r1, T_);
+  for (int r = max(r0, T_) + tr; r < r1; r += rpi) {  // rows beyond T are zeroed (window slack of the conv GEMMs)
+    float o[8];
 #pragma unroll
-    for (int u = 0; u < GN_UNROLL; ++u) {
-      const long long tt = t + u * rpi;
-      if (tt < r1 && tt < T_) { load8<T>(xb + tt * C, v[u]); load8<T>(db + tt * C, d[u]); }
-    }
+    for (int i = 0; i < 8; ++i) o[i] = 0.f;
+    store8<T>(db + r * C, o);
+  }
+  // dx = rs * (d * gamma - m1 - xhat * m2) = d * (rs * gamma) + x * (-rs * rs * m2) + (rs * (mu * rs * m2 - m1))
+  float ca[8];
 #pragma unroll
-    for (int u = 0; u < GN_UNROLL; ++u) {
-      const long long tt = t + u * rpi;
-      if (tt >= r1) break;
-      float o[8];
-      if (tt < T_) {
+  for (int i = 0; i < 8; ++i) ca[i] = rs * ga[i];
+  const float cb = -rs * rs * m2, cc = rs * (mu * rs * m2 - m1);
+  int r = r0 + tr;
+  const T* xp = xb + r * C;
+  T* dp = db + r * C;
+  const int step = rpi * C;
+  for (; r + rpi < d1; r += 2 * rpi, xp += 2 * step, dp += 2 * step) {
+    float v0[8], v1[8], g0[8], g1[8], o[8];
+    load8<T>(xp, v0); load8<T>(dp, g0);
+    load8<T>(xp + step, v1); load8<T>(dp + step, g1);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float xh = (v[u][i] - mu) * rs;
-          o[i] = rs * (d[u][i] * ga[i] - m1 - xh * m2);
-        }
-      } else {
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(g0[i], ca[i], fmaf(v0[i], cb, cc));
+    store8<T>(dp, o);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = 0.f;
-      }
-      store8<T>(db + tt * C, o);
-    }
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(g1[i], ca[i], fmaf(v1[i], cb, cc));
+    store8<T>(dp + step, o);
+  }
+  if (r < d1) {
+    float v0[8], g0[8], o[8];
+    load8<T>(xp, v0); load8<T>(dp, g0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(g0[i], ca[i], fmaf(v0[i], cb, cc));
+    store8<T>(dp, o);
   }
 }
 
