@@ -52,6 +52,15 @@ int ts_watchdog_check(ts_ctx* ctx);
 /* number of kernel-launch sites this context has passed since creation (bench.py's gpu_launches). */
 int64_t ts_launch_count(ts_ctx* ctx);
 
+/* ---- device-resident step state (CUDA-graph replay of a whole train step) ----------------------------------------------
+ * The library keeps {dropout salt, optimizer step} in device memory. Every dropout kernel adds the salt to its seed, and
+ * ts_optim_step(step = 0) takes the Adam step count from there. A captured step that starts with ts_step_state_advance
+ * therefore draws fresh dropout masks and uses the right bias correction on every replay, with no host involvement.
+ * Default state is {0, 0}: eager callers that pass their own seeds / step numbers are unaffected.
+ */
+int ts_step_state_set(ts_ctx* ctx, uint64_t salt, int64_t step, void* stream);
+int ts_step_state_advance(ts_ctx* ctx, void* stream);
+
 /* ---- K9: GEMM with fused epilogue ------------------------------------------------------------
  * Replaces every tf.keras.layers.Dense / tf.matmul / Conv1D-as-GEMM on the path:
  *   W:89-92,141,174,194-205,311-312,545 ; V:240-268,316-319,338-340,371,383-398,553,579,586 and
@@ -162,7 +171,8 @@ int ts_groupnorm_gelu_fwd(ts_ctx* ctx, int dtype, const void* x, const float* ga
  *   ts_optim_clip_global : grads *= clip / max(||grads||_2, clip) over ALL variables (local, pre-reduce).
  *   ts_optim_step        : [per-variable clipnorm] + Adam:  m += (g-m)(1-b1); v += (g*g-v)(1-b2);
  *                          p -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps); optionally refreshes the bf16
- *                          compute copy of the parameters in the same pass.
+ *                          compute copy of the parameters in the same pass. step >= 1 is Keras' `iterations + 1`;
+ *                          step = 0 reads it from the device step state (see ts_step_state_advance).
  * fuse_global_clip = 1 folds the global-norm clip into the step (single-replica path: no all-reduce between).
  */
 typedef struct ts_optim ts_optim;

@@ -55,6 +55,8 @@ int ts_create(int device, ts_ctx** out) {
   if (const char* mg = getenv("TETHYS_SM_MARGIN")) { const int n = atoi(mg); if (n > 0 && n < c->num_sms) c->num_sms -= n; }
   if (cudaMalloc(&c->d_watchdog, sizeof(int)) != cudaSuccess) { delete c; return TS_ECUDA; }
   cudaMemset(c->d_watchdog, 0, sizeof(int));
+  if (cudaMalloc(&c->d_state, 2 * sizeof(unsigned long long)) != cudaSuccess) { cudaFree(c->d_watchdog); delete c; return TS_ECUDA; }
+  cudaMemset(c->d_state, 0, 2 * sizeof(unsigned long long));
   *out = reinterpret_cast<ts_ctx*>(c);
   return TS_OK;
 }
@@ -64,6 +66,7 @@ void ts_destroy(ts_ctx* ctx) {
   if (!c) return;
   ts::tmap_cache_free(c);
   if (c->d_watchdog) cudaFree(c->d_watchdog);
+  if (c->d_state) cudaFree(c->d_state);
   delete c;
 }
 
@@ -82,6 +85,8 @@ int ts_watchdog_check(ts_ctx* ctx) {
   if (e != cudaSuccess) return ts::set_err(c, TS_ECUDA, "watchdog read failed: %s", cudaGetErrorString(e));
   if (v != 0) {
     cudaMemset(c->d_watchdog, 0, sizeof(int));
+  if (cudaMalloc(&c->d_state, 2 * sizeof(unsigned long long)) != cudaSuccess) { cudaFree(c->d_watchdog); delete c; return TS_ECUDA; }
+  cudaMemset(c->d_state, 0, 2 * sizeof(unsigned long long));
     return ts::set_err(c, TS_EWATCHDOG, "device mbarrier wait timed out (role code %d)", v);
   }
   return TS_OK;
@@ -90,6 +95,24 @@ int ts_watchdog_check(ts_ctx* ctx) {
 int64_t ts_launch_count(ts_ctx* ctx) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   return c ? (int64_t)c->launches : 0;
+}
+
+__global__ void step_state_set_kernel(unsigned long long* st, unsigned long long salt, unsigned long long step) { st[0] = salt; st[1] = step; }
+__global__ void step_state_advance_kernel(unsigned long long* st) { st[0] += 1ull; st[1] += 1ull; }
+
+int ts_step_state_set(ts_ctx* ctx, uint64_t salt, int64_t step, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c || step < 0) return TS_EINVAL;
+  step_state_set_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(c->d_state, salt, (unsigned long long)step);
+  TS_LAUNCH_OK(c);
+  return 0;
+}
+int ts_step_state_advance(ts_ctx* ctx, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c) return TS_EINVAL;
+  step_state_advance_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(c->d_state);
+  TS_LAUNCH_OK(c);
+  return 0;
 }
 
 int ts_layernorm_fwd(ts_ctx* ctx, int dtype, const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,

@@ -42,6 +42,7 @@ struct AttnParams {
   int B, nh, Tq, Tk;
   float scale;
   uint32_t drop_thr; float inv_keep; unsigned long long seed;
+  const unsigned long long* salt;   // device-resident dropout salt (Ctx::d_state)
   int drop_pitch;   // 32-key chunks per query row in the per-(batch, head) dropout stream (chunk index = row * pitch + key / 32)
   bf16* o; bf16* o_lo; long long o_ld, o_bs;
   float* stats;   // [B, nh, Tq, 2]
@@ -214,7 +215,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int r = q * 32 + lane;             // row inside the tile
     const int i = q0 + r;                    // query index
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const DropKey dkey = make_drop_key(p.seed, (unsigned long long)(b * p.nh + h), p.drop_thr);
+    const DropKey dkey = make_drop_key(p.drop_thr ? salted_seed(p.seed, p.salt) : p.seed, (unsigned long long)(b * p.nh + h), p.drop_thr);
     const uint32_t drow = (uint32_t)i * (uint32_t)p.drop_pitch;   // chunk index of this row's first 32-key chunk in the stream
     const float c1 = p.scale * kLog2e;
     float m_run = -INFINITY, l_part = 0.f;
@@ -477,7 +478,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const int i = q0 + r;
     const bool live = i < p.Tq;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const DropKey dkey = make_drop_key(p.seed, (unsigned long long)(b * p.nh + h), p.drop_thr);
+    const DropKey dkey = make_drop_key(p.drop_thr ? salted_seed(p.seed, p.salt) : p.seed, (unsigned long long)(b * p.nh + h), p.drop_thr);
     const uint32_t drow = (uint32_t)i * (uint32_t)p.drop_pitch;
     const long long srow = ((long long)b * p.nh + h) * p.Tq + i;
     float m_i = 0.f, ll2 = INFINITY, D = 0.f;
@@ -640,7 +641,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int et = (warp - 2) * 32 + lane;    // 0..255 among the element-wise threads
     const float c1 = p.scale * kLog2e;
-    const DropKey dkey = make_drop_key(p.seed, (unsigned long long)(b * p.nh + h), p.drop_thr);
+    const DropKey dkey = make_drop_key(p.drop_thr ? salted_seed(p.seed, p.salt) : p.seed, (unsigned long long)(b * p.nh + h), p.drop_thr);
     // dropout: this warp's 32 key rows are ONE chunk (index jrow >> 5) of every query row; lane t hashes the chunk seed of
     // query column t, the seed of column c is fetched by shuffle and advanced to this lane's position with its own
     // jump-ahead constants (a_l, c_l)
@@ -756,6 +757,7 @@ static int fill_params(Ctx* ctx, const ts_attn_desc* d, AttnParams* p) {
   p->B = d->batch; p->nh = d->heads; p->Tq = d->tq; p->Tk = d->tk; p->scale = d->scale;
   drop_params(d->drop, &p->drop_thr, &p->inv_keep);
   p->seed = d->seed;
+  p->salt = ctx->d_state;
   p->drop_pitch = (d->tk + 31) >> 5;
   TS_REQUIRE(ctx, (long long)d->tq * p->drop_pitch < (1ll << 32), TS_ESHAPE, "attention: Tq * Tk must stay below 2^32");
   p->o = (bf16*)d->o; p->o_lo = (bf16*)d->o_lo; p->o_ld = d->o_ld; p->o_bs = d->o_bs;

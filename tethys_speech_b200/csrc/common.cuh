@@ -26,6 +26,9 @@ struct Ctx {
   int* d_watchdog = nullptr;   // device int: set non-zero by a kernel whose mbarrier wait timed out
   void* tmap_cache = nullptr;  // opaque tensor-map cache (gemm_tc.cu)
   unsigned long long launches = 0;  // kernel-launch sites passed (TS_LAUNCH_OK); reported by ts_launch_count
+  // device-resident step state {dropout salt, optimizer step}: lets a whole train step be captured in a CUDA graph and still
+  // draw fresh dropout masks / use the right Adam bias correction on every replay (ts_step_state_set / _advance)
+  unsigned long long* d_state = nullptr;
 };
 
 int set_err(Ctx* c, int code, const char* fmt, ...);
@@ -176,6 +179,11 @@ __device__ __forceinline__ void dropout_scale2(uint64_t seed, uint64_t idx_even,
   s1 = ((w >> 16) >= (thr >> 16)) ? inv_keep : 0.f;
 }
 
+
+// every dropout kernel folds the device-resident salt (Ctx::d_state[0], 0 unless ts_step_state_* is used) into its seed
+__device__ __forceinline__ unsigned long long salted_seed(unsigned long long seed, const unsigned long long* salt) {
+  return seed + __ldg(salt) * 0x9E3779B97F4A7C15ull;
+}
 
 // Cheapest variant, for kernels that own a whole dropout "stream" and walk it in 32-element chunks (the fused attention
 // kernels: one stream per (batch, head); a chunk = 32 consecutive keys of one query row). One hash per CHUNK seeds a

@@ -39,7 +39,9 @@ int fill_zero(Ctx* ctx, void* p, long long bytes, cudaStream_t st) {
 // mode 0: out = gelu(a)*mask ; mode 1: out = a*gelu'(b)*mask ; mode 2: out = a*mask ; mode 3: out = a+b
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) ew_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
-                                                 long long n, uint32_t thr, float inv_keep, uint64_t seed) {
+                                                 long long n, uint32_t thr, float inv_keep, uint64_t seed,
+                                                 const unsigned long long* __restrict__ salt) {
+  if (MODE != 3 && thr) seed = salted_seed(seed, salt);
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
     float va[8], vb[8], o[8];
@@ -83,8 +85,8 @@ static int ew_launch(Ctx* ctx, int dt, const void* a, const void* b, void* out, 
   uint32_t thr; float ik;
   drop_params(drop, &thr, &ik);
   const int grid = ew_grid(ctx, (n + 7) / 8);
-  if (dt == TS_F32) ew_kernel<float, MODE><<<grid, 256, 0, st>>>((const float*)a, (const float*)b, (float*)out, n, thr, ik, seed);
-  else if (dt == TS_BF16) ew_kernel<bf16, MODE><<<grid, 256, 0, st>>>((const bf16*)a, (const bf16*)b, (bf16*)out, n, thr, ik, seed);
+  if (dt == TS_F32) ew_kernel<float, MODE><<<grid, 256, 0, st>>>((const float*)a, (const float*)b, (float*)out, n, thr, ik, seed, ctx->d_state);
+  else if (dt == TS_BF16) ew_kernel<bf16, MODE><<<grid, 256, 0, st>>>((const bf16*)a, (const bf16*)b, (bf16*)out, n, thr, ik, seed, ctx->d_state);
   else return set_err(ctx, TS_EDTYPE, "elementwise: dtype %d", dt);
   TS_LAUNCH_OK(ctx);
   return 0;

@@ -13,6 +13,7 @@ struct SimtParams {
   int a_major, b_major;
   float alpha; int act, accumulate;
   uint32_t drop_thr; float inv_keep; unsigned long long seed;
+  const unsigned long long* salt;
 };
 
 constexpr int SB_M = 64, SB_N = 64, SB_K = 16;
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
       if (p.act == 1) v = gelu_f(v);
       else if (p.act == 2) v *= gelu_grad_f(to_f<TO>(reinterpret_cast<const TO*>(p.aux)[b1 * p.c_bs1 + b2 * p.c_bs2 + (long long)gm * p.ld_aux + gn]));
       if (p.drop_thr)
-        v *= dropout_scale(p.seed, (unsigned long long)(b1 * p.c_bs1 + b2 * p.c_bs2 + (long long)gm * p.ldc + gn), p.drop_thr, p.inv_keep);
+        v *= dropout_scale(salted_seed(p.seed, p.salt), (unsigned long long)(b1 * p.c_bs1 + b2 * p.c_bs2 + (long long)gm * p.ldc + gn), p.drop_thr, p.inv_keep);
       if (R) v += to_f<TO>(R[(long long)gm * p.ldr + gn]);
       if (p.accumulate) v += to_f<TO>(C[(long long)gm * p.ldc + gn]);
       C[(long long)gm * p.ldc + gn] = from_f<TO>(v);
@@ -103,7 +104,7 @@ int gemm_simt(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
   p.nb1 = nb1;
   p.a_major = d->a_major; p.b_major = d->b_major;
   p.alpha = d->alpha; p.act = d->act; p.accumulate = d->accumulate;
-  p.drop_thr = 0; p.inv_keep = 1.f; p.seed = d->seed;
+  p.drop_thr = 0; p.inv_keep = 1.f; p.seed = d->seed; p.salt = ctx->d_state;
   if (d->drop > 0.f) {
     double t = (double)d->drop * 4294967296.0;
     p.drop_thr = (uint32_t)(t > 4294967295.0 ? 4294967295.0 : t);

@@ -35,6 +35,7 @@ struct EpiParams {
   int m, n, k, nb1;
   int a_m1, a_m2, b_m1, b_m2;  // 0 => that batch dim is broadcast for the operand (stride 0)
   uint32_t drop_thr; float inv_keep; unsigned long long seed;
+  const unsigned long long* salt;                     // device-resident dropout salt (Ctx::d_state)
   int mt, nt, nb, splitk, kb_per_split, total_tiles;  // persistent tile schedule
   int use_red;                                        // fp32 output: add with red.global (split-K partials)
   int tma_epi;                                        // C (and c_pre) are TMA-storable: swizzled smem box + bulk tensor store
@@ -99,7 +100,7 @@ __device__ __forceinline__ void epi_bias(float (&v)[NV], const EpiParams& p, con
   }
 }
 template <int NV, typename OutT>
-__device__ __forceinline__ void epi_act_drop(float (&v)[NV], const EpiParams& p, unsigned long long e0, const OutT* aux_row, bool row_ok,
+__device__ __forceinline__ void epi_act_drop(float (&v)[NV], const EpiParams& p, unsigned long long seed, unsigned long long e0, const OutT* aux_row, bool row_ok,
                                              int col, bool full) {
   if (p.act == 1) {
 #pragma unroll
@@ -138,12 +139,12 @@ __device__ __forceinline__ void epi_act_drop(float (&v)[NV], const EpiParams& p,
 #pragma unroll
       for (int i = 0; i < NV; i += 2) {
         float s0, s1;
-        dropout_scale2(p.seed, e0 + i, p.drop_thr, p.inv_keep, s0, s1);
+        dropout_scale2(seed, e0 + i, p.drop_thr, p.inv_keep, s0, s1);
         v[i] *= s0; v[i + 1] *= s1;
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) v[i] *= dropout_scale(p.seed, e0 + i, p.drop_thr, p.inv_keep);
+      for (int i = 0; i < NV; ++i) v[i] *= dropout_scale(seed, e0 + i, p.drop_thr, p.inv_keep);
     }
   }
 }
@@ -261,6 +262,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int q = warp & 3;
     const int half = ew >> 2;
     uint8_t* wbuf = stage_buf + ew * kStageBytesPerWarp;
+    const unsigned long long seed = p.drop_thr ? salted_seed(p.seed, p.salt) : p.seed;
     const uint32_t wbuf_s = ptx::smem_u32(wbuf);
     uint32_t tl = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tl) {
@@ -331,7 +333,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
             __syncwarp();
           }
-          epi_act_drop<CW, OutT>(v, p, (unsigned long long)(boff + (long long)row * p.ldc + col),
+          epi_act_drop<CW, OutT>(v, p, seed, (unsigned long long)(boff + (long long)row * p.ldc + col),
                                  reinterpret_cast<const OutT*>(p.aux) + boff + (long long)row * p.ld_aux + col, row < p.m, col, full);
           if (p.res && row < p.m) {
             const OutT* rrow = reinterpret_cast<const OutT*>(p.res) + (long long)tc.b1 * p.r_bs1 + (long long)tc.b2 * p.r_bs2 +
@@ -408,7 +410,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               if (pbase) pbase[off] = from_f<OutT>(v);
               if (p.act == 1) v = gelu_fast_f(v);
               else if (p.act == 2) v *= gelu_grad_fast_f(to_f<OutT>(reinterpret_cast<const OutT*>(p.aux)[boff + (long long)grow * p.ld_aux + col]));
-              if (p.drop_thr) v *= dropout_scale(p.seed, (unsigned long long)(boff + off), p.drop_thr, p.inv_keep);
+              if (p.drop_thr) v *= dropout_scale(seed, (unsigned long long)(boff + off), p.drop_thr, p.inv_keep);
               if (rbase) v += to_f<OutT>(rbase[(long long)grow * p.ldr + col]);
               if (kF32) {
                 float* dst = reinterpret_cast<float*>(cbase) + off;
@@ -623,7 +625,7 @@ int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
   ep.total_tiles = (int)(tiles_ll * splitk); ep.use_red = splitk > 1 ? 1 : 0;
   ep.a_m1 = (nb1 > 1 && d->a_bs1 != 0) ? 1 : 0; ep.a_m2 = (nb2 > 1 && d->a_bs2 != 0) ? 1 : 0;
   ep.b_m1 = (nb1 > 1 && d->b_bs1 != 0) ? 1 : 0; ep.b_m2 = (nb2 > 1 && d->b_bs2 != 0) ? 1 : 0;
-  ep.drop_thr = 0; ep.inv_keep = 1.f; ep.seed = d->seed;
+  ep.drop_thr = 0; ep.inv_keep = 1.f; ep.seed = d->seed; ep.salt = ctx->d_state;
   if (d->drop > 0.f) {
     double t = (double)d->drop * 4294967296.0;
     ep.drop_thr = (uint32_t)(t > 4294967295.0 ? 4294967295.0 : t);

@@ -101,7 +101,12 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float* __restrict__ v, bf16* __restrict__ p16,
                                                    const WorkItem* __restrict__ items, float lr_t, float omb1, float omb2,
                                                    float eps, float clipnorm, const float* __restrict__ pre_scale,
-                                                   const float* __restrict__ sumsq) {
+                                                   const float* __restrict__ sumsq, float lr,
+                                                   const unsigned long long* __restrict__ step_state) {
+  if (step_state) {  // CUDA-graph mode: the step count lives on the device (Ctx::d_state[1]); same formula as the host path
+    const double t = (double)step_state[1];
+    lr_t = (float)((double)lr * sqrt(1.0 - pow(1.0 - (double)omb2, t)) / (1.0 - pow(1.0 - (double)omb1, t)));
+  }
   const WorkItem it = items[blockIdx.x];
   float sc = pre_scale ? pre_scale[0] : 1.f;
   if (clipnorm > 0.f && sumsq) {
@@ -125,13 +130,13 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 
 int adam_step(Ctx* ctx, float* params, const float* grads, float* m, float* v, void* params_bf16, const Segment* d_segs,
               int nseg, const AdamArgs& a, cudaStream_t st) {
-  TS_REQUIRE(ctx, a.step >= 1, TS_EINVAL, "adam: step must start at 1");
+  TS_REQUIRE(ctx, a.step >= 0, TS_EINVAL, "adam: step must be >= 1 (or 0 = take it from the device step state)");
   WorkItem* items; int n;
   int rc = get_items(ctx, d_segs, nseg, &items, &n, st);
   if (rc) return rc;
-  const double lr_t = (double)a.lr * sqrt(1.0 - pow((double)a.beta2, a.step)) / (1.0 - pow((double)a.beta1, a.step));
+  const double lr_t = a.step >= 1 ? (double)a.lr * sqrt(1.0 - pow((double)a.beta2, a.step)) / (1.0 - pow((double)a.beta1, a.step)) : 0.0;
   adam_kernel<<<n, 256, 0, st>>>(params, grads, m, v, (bf16*)params_bf16, items, (float)lr_t, 1.f - a.beta1, 1.f - a.beta2,
-                                 a.eps, a.clipnorm, a.pre_scale, a.sumsq);
+                                 a.eps, a.clipnorm, a.pre_scale, a.sumsq, a.lr, a.step >= 1 ? nullptr : ctx->d_state);
   TS_LAUNCH_OK(ctx);
   return 0;
 }

@@ -57,7 +57,9 @@ __device__ __forceinline__ int dec_id(const int* labels, int b, int s, int S, in
 
 template <typename T>
 __global__ void embed_fwd_kernel(const T* __restrict__ table, const int* __restrict__ labels, const float* __restrict__ pe,
-                                 T* __restrict__ out, int S, int D, int start_token, uint32_t thr, float inv_keep, uint64_t seed) {
+                                 T* __restrict__ out, int S, int D, int start_token, uint32_t thr, float inv_keep, uint64_t seed,
+                                 const unsigned long long* __restrict__ salt) {
+  if (thr) seed = salted_seed(seed, salt);
   const long long row = blockIdx.x;
   const int b = (int)(row / S), s = (int)(row % S);
   const long long id = dec_id(labels, b, s, S, start_token);
@@ -69,7 +71,9 @@ __global__ void embed_fwd_kernel(const T* __restrict__ table, const int* __restr
 }
 template <typename T>
 __global__ void embed_bwd_kernel(const T* __restrict__ dout, const int* __restrict__ labels, float* __restrict__ dtable, int S,
-                                 int D, int start_token, uint32_t thr, float inv_keep, uint64_t seed) {
+                                 int D, int start_token, uint32_t thr, float inv_keep, uint64_t seed,
+                                 const unsigned long long* __restrict__ salt) {
+  if (thr) seed = salted_seed(seed, salt);
   const long long row = blockIdx.x;
   const int b = (int)(row / S), s = (int)(row % S);
   const long long id = dec_id(labels, b, s, S, start_token);
@@ -91,8 +95,8 @@ int embed_fwd(Ctx* ctx, int dt, const void* table, const int* labels, const floa
               int start_token, float drop, uint64_t seed, cudaStream_t st) {
   uint32_t thr; float ik;
   drop3(drop, &thr, &ik);
-  if (dt == TS_F32) embed_fwd_kernel<float><<<B * S, 256, 0, st>>>((const float*)table, labels, pe, (float*)out, S, D, start_token, thr, ik, seed);
-  else embed_fwd_kernel<bf16><<<B * S, 256, 0, st>>>((const bf16*)table, labels, pe, (bf16*)out, S, D, start_token, thr, ik, seed);
+  if (dt == TS_F32) embed_fwd_kernel<float><<<B * S, 256, 0, st>>>((const float*)table, labels, pe, (float*)out, S, D, start_token, thr, ik, seed, ctx->d_state);
+  else embed_fwd_kernel<bf16><<<B * S, 256, 0, st>>>((const bf16*)table, labels, pe, (bf16*)out, S, D, start_token, thr, ik, seed, ctx->d_state);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
@@ -100,8 +104,8 @@ int embed_bwd(Ctx* ctx, int dt, const void* dout, const int* labels, float* dtab
               float drop, uint64_t seed, cudaStream_t st) {
   uint32_t thr; float ik;
   drop3(drop, &thr, &ik);
-  if (dt == TS_F32) embed_bwd_kernel<float><<<B * S, 256, 0, st>>>((const float*)dout, labels, dtable, S, D, start_token, thr, ik, seed);
-  else embed_bwd_kernel<bf16><<<B * S, 256, 0, st>>>((const bf16*)dout, labels, dtable, S, D, start_token, thr, ik, seed);
+  if (dt == TS_F32) embed_bwd_kernel<float><<<B * S, 256, 0, st>>>((const float*)dout, labels, dtable, S, D, start_token, thr, ik, seed, ctx->d_state);
+  else embed_bwd_kernel<bf16><<<B * S, 256, 0, st>>>((const bf16*)dout, labels, dtable, S, D, start_token, thr, ik, seed, ctx->d_state);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
@@ -109,7 +113,9 @@ int embed_bwd(Ctx* ctx, int dt, const void* dout, const int* labels, float* dtab
 // ---- y[b,t,:] = dropout(x[b,t,:] + pe[t,:]) with x stored rpb_in rows per batch, y dense [B,T,D] ------------------
 template <typename T>
 __global__ void add_pe_kernel(const T* __restrict__ x, long long rpb_in, const float* __restrict__ pe, T* __restrict__ y, int T_,
-                              int D, uint32_t thr, float inv_keep, uint64_t seed, long long total8) {
+                              int D, uint32_t thr, float inv_keep, uint64_t seed, long long total8,
+                              const unsigned long long* __restrict__ salt) {
+  if (thr) seed = salted_seed(seed, salt);
   const int d8 = D / 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % d8) * 8;
@@ -134,8 +140,8 @@ int add_pe_rows(Ctx* ctx, int dt, const void* x, long long rpb_in, const float* 
   drop3(drop, &thr, &ik);
   const long long total8 = (long long)B * T_ * (D / 8);
   const int grid = (int)min((total8 + 255) / 256, (long long)ctx->num_sms * 16);
-  if (dt == TS_F32) add_pe_kernel<float><<<grid, 256, 0, st>>>((const float*)x, rpb_in, pe, (float*)y, T_, D, thr, ik, seed, total8);
-  else add_pe_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, rpb_in, pe, (bf16*)y, T_, D, thr, ik, seed, total8);
+  if (dt == TS_F32) add_pe_kernel<float><<<grid, 256, 0, st>>>((const float*)x, rpb_in, pe, (float*)y, T_, D, thr, ik, seed, total8, ctx->d_state);
+  else add_pe_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, rpb_in, pe, (bf16*)y, T_, D, thr, ik, seed, total8, ctx->d_state);
   TS_LAUNCH_OK(ctx);
   return 0;
 }

@@ -251,6 +251,7 @@ class Adam:
         self.clipnorm = clipnorm
         self.iterations = 0
         self._state = {}
+        self.device_step = False   # True inside a GraphedTrainStep: the step count comes from the library's device state
 
     def _bind(self, model):
         key = id(model)
@@ -294,8 +295,56 @@ class Adam:
         self.iterations += 1
         ctx.check(lib.ts_optim_step(st["optim"], ptr(prog.params), ptr(prog.grads), ptr(st["m"]), ptr(st["v"]),
                                     ptr(prog.params_lp), self.learning_rate, self.beta_1, self.beta_2, self.epsilon,
-                                    self.iterations, gclip, float(self.clipnorm or 0.0), fuse, stream_ptr()))
+                                    0 if self.device_step else self.iterations, gclip, float(self.clipnorm or 0.0), fuse, stream_ptr()))
         prog.weights_synced = True  # the update refreshed the bf16 compute copy in the same pass
+
+
+class GraphedTrainStep:
+    """One whole train step (forward, loss, backward, clip, Adam) captured in a CUDA graph and replayed: removes the ~430
+    kernel-launch gaps of a step. The library's device-resident step state (ts_step_state_*) gives every replay fresh
+    dropout masks and the right Adam bias correction; inputs are copied into static device buffers before each replay.
+
+        graphed = GraphedTrainStep(lambda batch, aux: train_step(model, batch, optimizer, **aux), model, optimizer,
+                                   example_batch, example_aux)
+        loss = graphed(batch, aux)          # loss is a device scalar (a view of the workspace)
+
+    Single-process use only (a captured NCCL all-reduce would tie the graph to the communicator's streams)."""
+
+    def __init__(self, step_fn, model, optimizer, example_batch, example_aux=None, warmup=3):
+        self.step_fn, self.model, self.opt = step_fn, model, optimizer
+        prog = model._prog
+        self.ctx = prog.ctx
+        dev = prog.device
+        self.static_batch = tuple(None if t is None else to_device(t, t.dtype if isinstance(t, torch.Tensor) else None, dev).clone()
+                                  for t in example_batch)
+        self.static_aux = {k: v.to(dev).clone() for k, v in (example_aux or {}).items()}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):            # allocates the workspace / optimizer state, sets kernel attributes
+                step_fn(self.static_batch, self.static_aux)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.ctx.check(self.ctx.lib.ts_step_state_set(self.ctx.h, 0, int(optimizer.iterations), stream_ptr()))
+        optimizer.device_step = True
+        l0 = self.ctx.lib.ts_launch_count(self.ctx.h)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.ctx.check(self.ctx.lib.ts_step_state_advance(self.ctx.h, stream_ptr()))
+            self.loss = step_fn(self.static_batch, self.static_aux)
+        optimizer.device_step = False
+        optimizer.iterations -= 1              # the capture recorded a step but did not run it
+        self.launches_per_step = int(self.ctx.lib.ts_launch_count(self.ctx.h) - l0)
+
+    def __call__(self, batch, aux=None):
+        for dst, src in zip(self.static_batch, batch):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        for k, v in (aux or {}).items():
+            self.static_aux[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        self.opt.iterations += 1
+        return self.loss
 
 
 def clip_by_global_norm(gradients, clip_norm):
