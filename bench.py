@@ -375,8 +375,9 @@ def run_ours(args):
     model.broadcast_weights(strategy)
     ctx = model._prog.ctx
     resident = [tuple(t.to(dev) if t is not None else None for t in hb) for hb in host]
-    use_graph = world == 1 and not args.no_graph
-    if use_graph:
+    use_graph = not args.no_graph
+    graph_launches = None
+    if use_graph and world == 1:
         # single GPU: the whole step is one CUDA graph (fresh dropout masks / Adam step from the library's device state)
         from tethys_speech_b200.runtime import GraphedTrainStep
 
@@ -389,9 +390,23 @@ def run_ours(args):
             def sample_aux():
                 return None
             graphed = GraphedTrainStep(lambda batch, aux: W.train_step(model, batch, opt), model, opt, resident[0], None)
+        graph_launches = graphed.launches_per_step
 
         def step(batch):  # noqa: F811
             return graphed(batch, sample_aux())
+    elif use_graph:
+        # N > 1: CUDA graphs around the eager NCCL all-reduces (collectives stay outside the graphs and keep overlapping)
+        if family == "w2v":
+            gstep, segs = W.make_graphed_distributed_step(strategy, model, opt, resident[0][0])
+
+            def step(batch):  # noqa: F811
+                return gstep(batch[0])
+        else:
+            gstep, segs = W.make_graphed_distributed_step(strategy, model, opt, resident[0][0], resident[0][1])
+
+            def step(batch):  # noqa: F811
+                return gstep(batch[0], batch[1])
+        graph_launches = segs.launches_per_step
 
     def sync_all():
         torch.cuda.synchronize()
@@ -414,7 +429,7 @@ def run_ours(args):
     sync_all()
     launches = int(ctx.lib.ts_launch_count(ctx.h) - l0)
     if use_graph:
-        launches = graphed.launches_per_step * args.steps   # replays do not pass the host-side launch counter
+        launches = graph_launches * args.steps   # replays do not pass the host-side launch counter
     t_dev = e0.elapsed_time(e1) * 1e-3
     clk = clocks.stop() if rank == 0 else None
     # ---- end-to-end timing: pinned host -> device copy of every batch, loss read back every step ----------

@@ -6,11 +6,11 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _setup(seed=0):
+def _setup(seed=0, precision="bf16"):
     from tethys_speech_b200 import wav2vec2 as W
     from tethys_speech_b200.runtime import Adam
 
-    model = W.Wav2Vec2ForPreTraining(W.Wav2Vec2Config("tiny"), precision="bf16", device=0, seed=seed)
+    model = W.Wav2Vec2ForPreTraining(W.Wav2Vec2Config("tiny"), precision=precision, device=0, seed=seed)
     opt = Adam(learning_rate=1e-4, epsilon=1e-8, clipnorm=1.0)
     g = torch.Generator().manual_seed(3)
     wave = torch.randn(2, 6400, generator=g).cuda()
@@ -49,3 +49,22 @@ def test_graphed_step_draws_new_dropout_masks_each_replay():
     losses = [float(graphed((wave, None), {"neg": neg})) for _ in range(4)]
     assert len(set(losses)) == 4, losses
     m._prog.ctx.watchdog()
+
+
+def test_graphed_step_fp32_step_count_is_exact():
+    """fp32 mode has no split-K atomics: after the same number of steps the graphed and the eager parameters agree to
+    rounding, which pins the device-side Adam step count (a bias-correction step off by one changes the update by >10 %)."""
+    from tethys_speech_b200.runtime import GraphedTrainStep
+
+    W, m1, o1, wave, neg = _setup(2, "fp32")
+    _, m2, o2, _, _ = _setup(2, "fp32")
+    p0 = m2._prog.params.clone()
+    graphed = GraphedTrainStep(lambda batch, aux: W.train_step(m1, batch, o1, neg_indices=aux["neg"], dropout=False), m1, o1,
+                               (wave, None), {"neg": neg}, warmup=1)
+    for _ in range(3):
+        graphed((wave, None), {"neg": neg})
+    for _ in range(4):
+        W.train_step(m2, (wave, None), o2, neg_indices=neg, dropout=False)
+    torch.cuda.synchronize()
+    upd = (m2._prog.params - p0).norm()
+    assert float((m1._prog.params - m2._prog.params).norm() / upd) < 1e-2

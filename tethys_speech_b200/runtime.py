@@ -261,6 +261,23 @@ class Adam:
             self._state[key] = st
         return self._state[key]
 
+    def local_clip(self, model, global_clip_norm):
+        """Phase 1 of the distributed apply (V:1243): clip_by_global_norm on this replica's gradients, in place."""
+        prog = model._prog
+        st = self._bind(model)
+        prog.ctx.check(prog.lib.ts_optim_clip_global(st["optim"], ptr(prog.grads), float(global_clip_norm), None, stream_ptr()))
+
+    def update(self, model):
+        """Phase 3 (after the all-reduce): per-variable clipnorm + Adam, advancing `iterations`."""
+        prog = model._prog
+        st = self._bind(model)
+        self.iterations += 1
+        prog.ctx.check(prog.lib.ts_optim_step(st["optim"], ptr(prog.params), ptr(prog.grads), ptr(st["m"]), ptr(st["v"]),
+                                              ptr(prog.params_lp), self.learning_rate, self.beta_1, self.beta_2, self.epsilon,
+                                              0 if self.device_step else self.iterations, 0.0, float(self.clipnorm or 0.0), 0,
+                                              stream_ptr()))
+        prog.weights_synced = True
+
     def apply_gradients(self, grads_and_vars, strategy=None, global_clip_norm=None, model=None, already_reduced=False):
         """All-reduce (SUM, un-normalised: App. A-13) the gradient arena across replicas, apply the per-variable
         clipnorm, then the Adam update. `global_clip_norm` fuses tf.clip_by_global_norm into the same pass when no
@@ -345,6 +362,47 @@ class GraphedTrainStep:
         self.graph.replay()
         self.opt.iterations += 1
         return self.loss
+
+
+class GraphedSegments:
+    """A train step as an alternating list of captured CUDA graphs and eager hooks (the NCCL collectives):
+        plan = [("graph", fn), ("eager", fn), ("graph", fn), ...]
+    Every fn takes no arguments and works on static device buffers; "graph" items are captured once (after `warmup` eager
+    passes over the whole plan) and replayed, "eager" items are called as they are. This keeps the collectives outside the
+    graphs — so a bucket's all-reduce still overlaps the next graph segment — while removing the launch gaps of the ~430
+    kernels of a step. The first graph segment must start with ts_step_state_advance (see GraphedTrainStep)."""
+
+    def __init__(self, plan, model, optimizer, warmup=3):
+        self.plan, self.opt = plan, optimizer
+        self.ctx = model._prog.ctx
+        dev = model._prog.device
+        for _ in range(warmup):
+            for kind, fn in plan:
+                fn()
+        torch.cuda.synchronize(dev)
+        self.ctx.check(self.ctx.lib.ts_step_state_set(self.ctx.h, 0, int(optimizer.iterations), stream_ptr()))
+        torch.cuda.synchronize(dev)
+        it0 = optimizer.iterations
+        optimizer.device_step = True
+        l0 = self.ctx.lib.ts_launch_count(self.ctx.h)
+        self.items = []
+        for kind, fn in plan:
+            if kind == "graph":
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fn()
+                self.items.append(g.replay)
+            else:
+                self.items.append(fn)
+        optimizer.device_step = False
+        optimizer.iterations = it0              # captures record work, they do not run it
+        self.launches_per_step = int(self.ctx.lib.ts_launch_count(self.ctx.h) - l0)
+        torch.cuda.synchronize(dev)
+
+    def __call__(self):
+        for run in self.items:
+            run()
+        self.opt.iterations += 1
 
 
 def clip_by_global_norm(gradients, clip_norm):

@@ -371,3 +371,42 @@ def distributed_train_step(strategy, model, dist_inputs, optimizer, neg_indices=
 
     per_replica_losses = strategy.run(step, args=(dist_inputs,))
     return strategy.reduce(ReduceOp.SUM, per_replica_losses, axis=None)
+
+
+def make_graphed_distributed_step(strategy, model, optimizer, example_features, dropout=True, warmup=3):
+    """distributed_train_step (V:1186-1260) as CUDA graphs around the eager NCCL all-reduce:
+       graph [advance state, forward (loss / N), backward, local clip_by_global_norm] -> eager all-reduce SUM of the gradient
+       arena (3 buckets) -> graph [per-variable clipnorm + Adam] -> eager strategy.reduce(SUM) of the scaled losses.
+    Returns (step(features) -> reduced loss, segments)."""
+    from .runtime import GraphedSegments
+
+    prog = model._prog
+    n = float(strategy.num_replicas_in_sync)
+    B, N = example_features.shape
+    feats = example_features.to(prog.device).clone()
+    T = model.num_frames(N)
+    neg = model._sample_negative_indices(T, B)[:, 0, :].contiguous().clone()
+    state = {}
+
+    def seg_fwd_bwd():
+        prog.ctx.check(prog.lib.ts_step_state_advance(prog.ctx.h, stream_ptr()))
+        out = model(feats, training=True, neg_indices=neg, loss_div=n, dropout=dropout)
+        state["scaled_loss"] = out["loss"] / n
+        model.gradient()
+        optimizer.local_clip(model, 1.0)
+
+    def seg_reduce():
+        strategy.all_reduce_sum_(prog.grads, bucket_elems=32 * 1024 * 1024)
+
+    def seg_update():
+        optimizer.update(model)
+
+    segs = GraphedSegments([("graph", seg_fwd_bwd), ("eager", seg_reduce), ("graph", seg_update)], model, optimizer, warmup=warmup)
+
+    def step(features):
+        feats.copy_(features, non_blocking=True)
+        neg.copy_(model._sample_negative_indices(T, B)[:, 0, :])      # V:907-937, drawn outside the graph
+        segs()
+        return strategy.reduce(ReduceOp.SUM, state["scaled_loss"], axis=None)
+
+    return step, segs

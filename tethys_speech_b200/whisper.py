@@ -268,3 +268,60 @@ def train_step(model, inputs, optimizer, dropout=True):
     gradients = model.gradient()
     optimizer.apply_gradients(gradients)
     return outputs["loss"]
+
+
+def make_graphed_distributed_step(strategy, model, optimizer, example_features, example_labels, dropout=True, warmup=3,
+                                  bucket_elems=16 * 1024 * 1024):
+    """distributed_train_step (W:819-848) as CUDA graphs between the eager NCCL all-reduces: the backward stages are grouped
+    into buckets (arena prefixes that are final, ts_whisper_stage_end); each group is one graph, and after it the bucket's
+    all-reduce (SUM, un-normalised — App. C-3) is issued asynchronously so that it overlaps the next group's graph.
+    Returns (step(features, labels) -> reduced loss, segments)."""
+    from .runtime import GraphedSegments
+
+    prog = model._prog
+    feats = example_features.to(prog.device).clone()
+    labels = example_labels.to(prog.device).clone()
+    state = {"works": []}
+    ends = prog.stage_ends
+    groups, start, first = [], 0, 0
+    for s_, end in enumerate(ends):
+        if end - start >= bucket_elems or s_ == len(ends) - 1:
+            groups.append((first, s_, start, end))
+            start, first = end, s_ + 1
+    plan = []
+
+    def seg_forward():
+        prog.ctx.check(prog.lib.ts_step_state_advance(prog.ctx.h, stream_ptr()))
+        out = model(feats, labels=labels, training=True, dropout=dropout)
+        state["loss"] = out["loss"]
+
+    for gi, (s0, s1, a0, a1) in enumerate(groups):
+        def seg_bwd(s0=s0, s1=s1, gi=gi):
+            if gi == 0:
+                seg_forward()
+            prog.backward(s0, s1)
+
+        def seg_reduce(a0=a0, a1=a1):
+            if a1 > a0:
+                state["works"].append(strategy.dist.all_reduce(prog.grads[a0:a1], op=strategy.dist.ReduceOp.SUM, async_op=True))
+
+        plan += [("graph", seg_bwd), ("eager", seg_reduce)]
+
+    def seg_wait():
+        for w in state["works"]:
+            w.wait()
+        state["works"] = []
+
+    def seg_update():
+        optimizer.update(model)
+
+    plan += [("eager", seg_wait), ("graph", seg_update)]
+    segs = GraphedSegments(plan, model, optimizer, warmup=warmup)
+
+    def step(features, lab):
+        feats.copy_(features, non_blocking=True)
+        labels.copy_(lab, non_blocking=True)
+        segs()
+        return strategy.reduce(ReduceOp.SUM, state["loss"], axis=None)
+
+    return step, segs
