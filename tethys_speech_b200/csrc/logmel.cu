@@ -23,7 +23,6 @@ constexpr int LM_PAIRS = LM_FPB / 2;
 constexpr int LM_WAVE = (LM_FPB - 1) * LM_HOP + LM_NFFT;     // 4080 samples staged per block
 constexpr int LM_ROW = 21;                                   // padded row (float2) of the 20 x 20 intermediate
 constexpr int LM_MAXW = 16;                                  // widest mel triangle in bins (13 for the reference config)
-constexpr int LM_PSTR = 208;                                 // power row stride (floats)
 
 struct LogmelTables {
   float hann[LM_NFFT];
@@ -83,23 +82,20 @@ __device__ __forceinline__ void dft20(float2 (&x)[20]) {
   }
 }
 
-constexpr int kLogmelSmem = LM_NFFT * 4 /*hann*/ + LM_NFFT * 8 /*w400*/ + LM_WAVE * 4 + LM_PAIRS * 20 * LM_ROW * 8 /*buf*/ +
-                            LM_FPB * LM_PSTR * 4 /*power*/;
+constexpr int kLogmelSmem = LM_WAVE * 4 + LM_PAIRS * 20 * LM_ROW * 8 /*buf*/;   // 56.6 KB: four blocks per SM
 
 template <typename TO>
-__global__ void __launch_bounds__(256) logmel_kernel(const float* __restrict__ wave, long long wave_bs, int n_samples,
+__global__ void __launch_bounds__(256, 4) logmel_kernel(const float* __restrict__ wave, long long wave_bs, int n_samples,
                                                      const LogmelTables* __restrict__ tab, TO* __restrict__ out, int n_frames,
                                                      int mel_major /*0: [B,F,80]  1: [B,80,F]*/) {
   extern __shared__ __align__(16) unsigned char lm_smem[];
-  float* s_hann = reinterpret_cast<float*>(lm_smem);
-  float2* s_w = reinterpret_cast<float2*>(s_hann + LM_NFFT);
-  float* s_wave = reinterpret_cast<float*>(s_w + LM_NFFT);
+  float* s_wave = reinterpret_cast<float*>(lm_smem);
   float2* s_buf = reinterpret_cast<float2*>(s_wave + LM_WAVE);
-  float* s_pow = reinterpret_cast<float*>(s_buf + LM_PAIRS * 20 * LM_ROW);
+  const float* g_hann = tab->hann;        // window / twiddle tables stay in global memory: 4.8 KB, L1-resident
+  const float2* g_w = tab->w400;
   const int b = blockIdx.y, f0 = blockIdx.x * LM_FPB;
   const int tid = threadIdx.x;
-  // ---- stage tables and the waveform chunk --------------------------------------------------------------------
-  for (int i = tid; i < LM_NFFT; i += 256) { s_hann[i] = tab->hann[i]; s_w[i] = tab->w400[i]; }
+  // ---- stage the waveform chunk ----------------------------------------------------------------------------------
   const float* src = wave + (long long)b * wave_bs + (long long)f0 * LM_HOP;
   const int avail = n_samples - f0 * LM_HOP;  // samples left in this sample from the chunk start
   if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
@@ -127,12 +123,12 @@ __global__ void __launch_bounds__(256) logmel_kernel(const float* __restrict__ w
 #pragma unroll
     for (int n1 = 0; n1 < 20; ++n1) {
       const int n = 20 * n1 + j;
-      const float w = s_hann[n];
+      const float w = __ldg(g_hann + n);
       z[n1] = make_float2(w * fa[n], w * fb[n]);
     }
     dft20(z);
 #pragma unroll
-    for (int k1 = 0; k1 < 20; ++k1) s_buf[(p * 20 + k1) * LM_ROW + j] = cmul(z[k1], s_w[j * k1]);
+    for (int k1 = 0; k1 < 20; ++k1) s_buf[(p * 20 + k1) * LM_ROW + j] = cmul(z[k1], __ldg(g_w + j * k1));
   }
   __syncthreads();
   // ---- step 2: DFT-20 over n2 for row k1 = j -> X[k1 + 20 k2] --------------------------------------------------
@@ -148,25 +144,24 @@ __global__ void __launch_bounds__(256) logmel_kernel(const float* __restrict__ w
     for (int k2 = 0; k2 < 20; ++k2) s_x[p * 20 * LM_ROW + j + 20 * k2] = z[k2];
   }
   __syncthreads();
-  // ---- power spectra of both frames of every pair (conjugate symmetry) -----------------------------------------
-  for (int it = tid; it < LM_PAIRS * LM_BINS; it += 256) {
-    const int pp = it / LM_BINS, k = it % LM_BINS;
-    const float2 a = s_x[pp * 20 * LM_ROW + k], c = s_x[pp * 20 * LM_ROW + ((LM_NFFT - k) % LM_NFFT)];
-    const float ar = a.x + c.x, ai = a.y - c.y, br = a.x - c.x, bi = a.y + c.y;
-    s_pow[(2 * pp) * LM_PSTR + k] = 0.25f * (ar * ar + ai * ai);
-    s_pow[(2 * pp + 1) * LM_PSTR + k] = 0.25f * (br * br + bi * bi);
-  }
-  __syncthreads();
-  // ---- sparse mel filter bank + log -------------------------------------------------------------------------------
+  // ---- power (conjugate symmetry separates the two real frames of a pair) + sparse mel filter bank + log -----------------
   for (int it = tid; it < LM_FPB * LM_MELS; it += 256) {
     int fr, m;
     if (mel_major) { m = it / LM_FPB; fr = it % LM_FPB; } else { fr = it / LM_MELS; m = it % LM_MELS; }
     const int f = f0 + fr;
     if (f >= n_frames) continue;
+    const float2* X = s_x + (fr >> 1) * 20 * LM_ROW;
+    const bool second = fr & 1;
     const int st = tab->mel_start[m], cnt = tab->mel_cnt[m];
     float acc = 0.f;
-    for (int q = 0; q < cnt; ++q) acc = fmaf(tab->mel_w[m][q], s_pow[fr * LM_PSTR + st + q], acc);
-    const float v = logf(acc + 1e-6f);
+    for (int q = 0; q < cnt; ++q) {
+      const int k = st + q;                       // 1 <= k <= 200
+      const float2 a = X[k], c = X[LM_NFFT - k];
+      // frame A = (X[k] + conj(X[N-k])) / 2, frame B = (X[k] - conj(X[N-k])) / (2i)
+      const float re = second ? a.x - c.x : a.x + c.x, im = second ? a.y + c.y : a.y - c.y;
+      acc = fmaf(__ldg(&tab->mel_w[m][q]), 0.25f * (re * re + im * im), acc);
+    }
+    const float v = __logf(acc + 1e-6f);
     const long long o = mel_major ? ((long long)b * LM_MELS + m) * n_frames + f : ((long long)b * n_frames + f) * LM_MELS + m;
     out[o] = from_f<TO>(v);
   }
