@@ -491,6 +491,8 @@ int ts_whisper_create(ts_ctx* ctx_, const ts_whisper_config* cfg, int precision,
   Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
   if (!ctx || !cfg || !out) return TS_EINVAL;
   TS_REQUIRE(ctx, precision == TS_F32 || precision == TS_BF16, TS_EDTYPE, "whisper: precision must be TS_F32 or TS_BF16");
+  TS_REQUIRE(ctx, cfg->vocab > 0 && cfg->start_token >= 0 && cfg->start_token < cfg->vocab, TS_EINVAL,
+             "whisper: decoder start token %d outside the vocabulary of %d entries", cfg->start_token, cfg->vocab);
   Whisper* m = new Whisper();
   m->ctx = ctx; m->cfg = *cfg; m->prec = precision; m->esz = precision == TS_BF16 ? 2 : 4;
   m->fused_attn = precision == TS_BF16 && cfg->heads > 0 && cfg->d_model / cfg->heads == 64 && !getenv("TETHYS_UNFUSED_ATTENTION");
