@@ -308,7 +308,7 @@ class Adam:
             else:
                 fuse, gclip = 1, float(global_clip_norm)
         if strategy.num_replicas_in_sync > 1 and not already_reduced:
-            strategy.all_reduce_sum_(prog.grads, bucket_elems=32 * 1024 * 1024)
+            strategy.all_reduce_sum_(prog.grads, bucket_elems=int(os.environ.get("TETHYS_AR_BUCKET_ELEMS", 0)))
         self.iterations += 1
         ctx.check(lib.ts_optim_step(st["optim"], ptr(prog.params), ptr(prog.grads), ptr(st["m"]), ptr(st["v"]),
                                     ptr(prog.params_lp), self.learning_rate, self.beta_1, self.beta_2, self.epsilon,

@@ -3,6 +3,7 @@ whisper_single.py = WS): same class names, call signatures, output dict keys and
 native program in libtethys.so (csrc/w2v_program.cu) through ctypes. No TensorFlow, no CPU fallback.
 """
 import ctypes as C
+import os
 import math
 
 import numpy as np
@@ -396,7 +397,7 @@ def make_graphed_distributed_step(strategy, model, optimizer, example_features, 
         optimizer.local_clip(model, 1.0)
 
     def seg_reduce():
-        strategy.all_reduce_sum_(prog.grads, bucket_elems=32 * 1024 * 1024)
+        strategy.all_reduce_sum_(prog.grads, bucket_elems=int(os.environ.get("TETHYS_AR_BUCKET_ELEMS", 0)))
 
     def seg_update():
         optimizer.update(model)
