@@ -62,9 +62,17 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   __shared__ float red[32];
   const WorkItem it = items[blockIdx.x];
   float s = 0.f;
+  const bool vec = ((it.start | it.ld | (long long)it.cols) & 3) == 0;   // arena blocks are 64-element aligned: the usual case
   for (int r = 0; r < it.rows; ++r) {
     const float* p = g + it.start + (long long)r * it.ld;
-    for (int c = threadIdx.x; c < it.cols; c += 256) { const float v = p[c]; s += v * v; }
+    if (vec) {
+      for (int c = threadIdx.x * 4; c < it.cols; c += 1024) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p + c));
+        s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      }
+    } else {
+      for (int c = threadIdx.x; c < it.cols; c += 256) { const float v = p[c]; s += v * v; }
+    }
   }
   s = block_sum(s, red);
   if (threadIdx.x == 0) atomicAdd(&sumsq[it.seg], s);
@@ -113,17 +121,45 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     const float n = sqrtf(sumsq[it.seg]) * sc;
     sc *= clipnorm / fmaxf(n, clipnorm);
   }
+  const bool vec = ((it.start | it.ld | (long long)it.cols) & 3) == 0;
   for (int r = 0; r < it.rows; ++r) {
     const long long base = it.start + (long long)r * it.ld;
-    for (int c = threadIdx.x; c < it.cols; c += 256) {
-      const long long i = base + c;
-      const float gi = g[i] * sc;
-      float mi = m[i], vi = v[i];
-      mi = mi + (gi - mi) * omb1;
-      vi = vi + (gi * gi - vi) * omb2;
-      const float pi = p[i] - lr_t * mi / (sqrtf(vi) + eps);
-      m[i] = mi; v[i] = vi; p[i] = pi;
-      if (p16) p16[i] = __float2bfloat16_rn(pi);
+    if (vec) {  // 16-byte accesses: 4 parameters per thread and iteration
+      for (int c = threadIdx.x * 4; c < it.cols; c += 1024) {
+        const long long i = base + c;
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(g + i));
+        float4 m4 = *reinterpret_cast<const float4*>(m + i), v4 = *reinterpret_cast<const float4*>(v + i);
+        float4 p4 = *reinterpret_cast<const float4*>(p + i);
+        const float gg[4] = {g4.x * sc, g4.y * sc, g4.z * sc, g4.w * sc};
+        float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, pp[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          mm[k] = mm[k] + (gg[k] - mm[k]) * omb1;
+          vv[k] = vv[k] + (gg[k] * gg[k] - vv[k]) * omb2;
+          pp[k] = pp[k] - lr_t * mm[k] / (sqrtf(vv[k]) + eps);
+        }
+        *reinterpret_cast<float4*>(m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+        *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        *reinterpret_cast<float4*>(p + i) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+        if (p16) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(pp[0], pp[1]), hi = __floats2bfloat162_rn(pp[2], pp[3]);
+          uint2 u;
+          u.x = *reinterpret_cast<uint32_t*>(&lo);
+          u.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(p16 + i) = u;
+        }
+      }
+    } else {
+      for (int c = threadIdx.x; c < it.cols; c += 256) {
+        const long long i = base + c;
+        const float gi = g[i] * sc;
+        float mi = m[i], vi = v[i];
+        mi = mi + (gi - mi) * omb1;
+        vi = vi + (gi * gi - vi) * omb2;
+        const float pi = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+        m[i] = mi; v[i] = vi; p[i] = pi;
+        if (p16) p16[i] = __float2bfloat16_rn(pi);
+      }
     }
   }
 }
