@@ -34,6 +34,7 @@ WORKLOADS = {
     "w2v_base_5s": ("w2v", "base", 80000, 5.0, 212.7),        # configs[0] as the reference file literally is
     "w2v_base_2s": ("w2v", "base", 32000, 2.0, 83.4),
     "w2v_tiny_2s": ("w2v", "tiny", 32000, 2.0, 25.6),
+    "w2v_large_15s": ("w2v", "large", 240000, 15.0, 1769.8),  # configs[3]: EXTRAPOLATED preset, no reference numerics
     "whisper_small_30s": ("whisper", "small", 3000, 30.0, 449.1),   # configs[0] as BASELINE intends (1a): CLI default preset
     "whisper_base_30s": ("whisper", "base", 3000, 30.0, 325.5),     # configs[2]
 }

@@ -164,3 +164,17 @@ def test_w2v_dropout_is_deterministic_and_unbiased():
     assert abs(l1 - l2) / abs(l1) < 1e-6
     assert abs(l1 - l3) / abs(l1) > 1e-5
     assert math.isfinite(l3)
+
+
+def test_w2v_tiny_bf16_batch1_multi_tile_attention():
+    # T = 200 frames: two 128-row query tiles / key tiles with ragged tails through the fused attention kernels
+    _check_forward_backward("tiny", 1, 8000, "bf16", BF16_TOL, 6e-2)
+
+
+def test_w2v_too_short_audio_is_an_error():
+    from tethys_speech_b200 import _lib
+    from tethys_speech_b200 import wav2vec2 as W
+
+    model = W.Wav2Vec2ForPreTraining(W.Wav2Vec2Config("tiny"), precision="bf16", device=0)
+    with pytest.raises(_lib.TethysError):
+        model(torch.randn(1, 30), training=True)

@@ -122,3 +122,9 @@ def test_whisper_train_steps_fp32_match_oracle_adam():
         d_gpu = got[k].double().cpu() - w64[k]
         d_ref = w[k] - w64[k]
         assert rel_l2(d_gpu, d_ref) < 5e-3, (k, rel_l2(d_gpu, d_ref))
+
+
+def test_whisper_bf16_ragged_cross_attention_and_full_length_targets():
+    # encoder T = 300 (three 128-row tiles, ragged), decoder S = 100 (W:786): cross-attention 100 x 300, anti-causal 100 x 100
+    O, W, ocfg, cfg = _small_cfgs(d=128, heads=2, ff=256, n_ctx=320)
+    _run(O, W, ocfg, cfg, 1, 600, 100, "bf16", 2e-2, 6e-2, seed=3)

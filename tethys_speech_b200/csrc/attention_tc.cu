@@ -79,9 +79,6 @@ __device__ __forceinline__ uint64_t desc_p_kmajor(uint32_t tile, int kk) {
 }
 // [128 k-rows x 64] tile read as an MN-major B operand (V in P.V, K in dS.K, dO / Q in the dV / dK products)
 __device__ __forceinline__ uint64_t desc_mn_b(uint32_t tile, int kk) { return ptx::make_smem_desc(tile + kk * 2048, 8192, 1024); }
-// P / dS read as an MN-major A operand: M = the 128 tile columns (two 64-wide chunks 16 KB apart), K = the 128 tile rows
-__device__ __forceinline__ uint64_t desc_p_mn_a(uint32_t tile, int kk) { return ptx::make_smem_desc(tile + kk * 2048, kTile, 1024); }
-
 #define TS_TRY_RC(expr)   \
   do {                   \
     int _rc = (expr);    \
