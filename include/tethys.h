@@ -180,6 +180,9 @@ int ts_optim_create(ts_ctx* ctx, int32_t n_vars, const int64_t* offsets, const i
                     const int64_t* lds, int64_t arena_elems, ts_optim** out);
 void ts_optim_destroy(ts_optim* o);
 int ts_optim_clip_global(ts_optim* o, float* grads, float clip, float* norm_out_dev /*nullable*/, void* stream);
+/* same scale, NOT applied: scale_out_dev[0] = clip / max(||grads||_2, clip). For callers that fold the factor into the
+ * collective (NCCL pre-multiplied sum) instead of spending a pass over the arena. */
+int ts_optim_global_clip_scale(ts_optim* o, const float* grads, float clip, float* scale_out_dev, void* stream);
 int ts_optim_step(ts_optim* o, float* params, const float* grads, float* m, float* v, void* params_bf16 /*nullable*/,
                   float lr, float beta1, float beta2, float eps, int32_t step, float global_clip /*<=0 off*/,
                   float clipnorm /*<=0 off*/, int32_t fuse_global_clip, void* stream);

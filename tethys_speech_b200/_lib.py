@@ -104,6 +104,7 @@ SYMBOLS = {
     "ts_optim_create": (_I, [_P, _I, C.POINTER(_L), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L), _L, C.POINTER(_P)]),
     "ts_optim_destroy": (None, [_P]),
     "ts_optim_clip_global": (_I, [_P, _P, _F, _P, _P]),
+    "ts_optim_global_clip_scale": (_I, [_P, _P, _F, _P, _P]),
     "ts_optim_step": (_I, [_P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _I, _F, _F, _I, _P]),
     "ts_cast_f32_to_bf16": (_I, [_P, _P, _P, _L, _P]),
     "ts_w2v_create": (_I, [_P, C.POINTER(W2VConfig), _I, C.POINTER(_P)]),

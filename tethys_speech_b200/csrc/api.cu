@@ -201,6 +201,15 @@ int ts_optim_clip_global(ts_optim* o_, float* grads, float clip, float* norm_out
   return ts::scale_inplace(o->ctx, grads, o->arena, o->d_scal, 1.f, st);
 }
 
+int ts_optim_global_clip_scale(ts_optim* o_, const float* grads, float clip, float* scale_out_dev, void* stream) {
+  ts::Optim* o = reinterpret_cast<ts::Optim*>(o_);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!o || !grads || !scale_out_dev) return TS_EINVAL;
+  int rc = ts::grad_sumsq(o->ctx, grads, o->d_segs, o->nseg, o->d_sumsq, st);
+  if (rc) return rc;
+  return ts::global_clip_scale(o->ctx, o->d_sumsq, o->nseg, clip, scale_out_dev, o->d_scal + 1, st);
+}
+
 int ts_optim_step(ts_optim* o_, float* params, const float* grads, float* m, float* v, void* params_bf16, float lr,
                   float beta1, float beta2, float eps, int32_t step, float global_clip, float clipnorm,
                   int32_t fuse_global_clip, void* stream) {

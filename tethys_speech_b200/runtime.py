@@ -197,6 +197,19 @@ class Strategy:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return t
 
+    def all_reduce_premul_sum_(self, flat, scale):
+        """SUM over replicas of scale_r * flat_r with the per-replica device scalar `scale` applied inside the collective
+        (ncclRedOpCreatePreMulSum); falls back to an explicit multiply if this torch/NCCL build lacks it."""
+        if self.dist is None:
+            flat.mul_(scale)
+            return
+        try:
+            op = self.dist._make_nccl_premul_sum(scale)
+        except Exception:  # noqa: BLE001 — gloo, or a build without pre-multiplied sums
+            flat.mul_(scale)
+            op = self.dist.ReduceOp.SUM
+        self.dist.all_reduce(flat, op=op)
+
     def all_reduce_sum_(self, flat, bucket_elems=None):
         """K21: in-place SUM all-reduce of a flat gradient arena, issued as a few large buckets."""
         if self.dist is None:
@@ -266,6 +279,13 @@ class Adam:
         prog = model._prog
         st = self._bind(model)
         prog.ctx.check(prog.lib.ts_optim_clip_global(st["optim"], ptr(prog.grads), float(global_clip_norm), None, stream_ptr()))
+
+    def local_clip_scale(self, model, global_clip_norm, out):
+        """clip_by_global_norm's factor for this replica's gradients (V:1243) written to the device scalar `out`, not applied:
+        the distributed step folds it into the all-reduce (NCCL pre-multiplied sum)."""
+        prog = model._prog
+        st = self._bind(model)
+        prog.ctx.check(prog.lib.ts_optim_global_clip_scale(st["optim"], ptr(prog.grads), float(global_clip_norm), ptr(out), stream_ptr()))
 
     def update(self, model):
         """Phase 3 (after the all-reduce): per-variable clipnorm + Adam, advancing `iterations`."""

@@ -388,16 +388,26 @@ def make_graphed_distributed_step(strategy, model, optimizer, example_features, 
     T = model.num_frames(N)
     neg = model._sample_negative_indices(T, B)[:, 0, :].contiguous().clone()
     state = {}
+    # local clip_by_global_norm (V:1243) folded into the collective: sum_r scale_r * g_r in one NCCL pre-multiplied sum
+    premul = (strategy.dist is not None and strategy.dist.get_backend() == "nccl" and hasattr(strategy.dist, "_make_nccl_premul_sum")
+              and not os.environ.get("TETHYS_NO_PREMUL"))
+    clip_scale = torch.ones(1, device=prog.device)
 
     def seg_fwd_bwd():
         prog.ctx.check(prog.lib.ts_step_state_advance(prog.ctx.h, stream_ptr()))
         out = model(feats, training=True, neg_indices=neg, loss_div=n, dropout=dropout)
         state["scaled_loss"] = out["loss"] / n
         model.gradient()
-        optimizer.local_clip(model, 1.0)
+        if premul:
+            optimizer.local_clip_scale(model, 1.0, clip_scale)     # factor only; applied inside the all-reduce
+        else:
+            optimizer.local_clip(model, 1.0)
 
     def seg_reduce():
-        strategy.all_reduce_sum_(prog.grads, bucket_elems=int(os.environ.get("TETHYS_AR_BUCKET_ELEMS", 0)))
+        if premul:
+            strategy.all_reduce_premul_sum_(prog.grads, clip_scale)
+        else:
+            strategy.all_reduce_sum_(prog.grads, bucket_elems=int(os.environ.get("TETHYS_AR_BUCKET_ELEMS", 0)))
 
     def seg_update():
         optimizer.update(model)
