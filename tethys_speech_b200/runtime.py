@@ -108,6 +108,21 @@ class ProgramBase:
             self._optim = o
         return self._optim
 
+    def make_optim_range(self, a0, a1):
+        """ts_optim over the variables that live in the arena range [a0, a1) (one all-reduce bucket); ranges must be cut at
+        backward-stage ends so that fused blocks (q/k/v) are never split."""
+        names = [k for k in self.info if a0 <= self.info[k][0] < a1]
+        n = len(names)
+        offs = (C.c_int64 * n)(); rows = (C.c_int32 * n)(); cols = (C.c_int32 * n)(); lds = (C.c_int64 * n)()
+        for i, k in enumerate(names):
+            off, shp, ld = self.info[k]
+            numel = int(np.prod(shp))
+            r = shp[0] if (len(shp) == 2 and ld != numel) else 1
+            offs[i], rows[i], cols[i], lds[i] = off, r, numel // r, ld if r > 1 else numel
+        o = C.c_void_p()
+        self.ctx.check(self.lib.ts_optim_create(self.ctx.h, n, offs, rows, cols, lds, self.n, C.byref(o)))
+        return o
+
     def ensure_workspace(self, *key):
         if self.ws_key == key:
             return
@@ -298,6 +313,17 @@ class Adam:
                                               stream_ptr()))
         prog.weights_synced = True
 
+    def update_range(self, model, optim_handle):
+        """clipnorm + Adam on the variables of one all-reduce bucket (its own ts_optim); does not touch `iterations` — the
+        caller advances it once per step."""
+        prog = model._prog
+        st = self._bind(model)
+        prog.ctx.check(prog.lib.ts_optim_step(optim_handle, ptr(prog.params), ptr(prog.grads), ptr(st["m"]), ptr(st["v"]),
+                                              ptr(prog.params_lp), self.learning_rate, self.beta_1, self.beta_2, self.epsilon,
+                                              0 if self.device_step else self.iterations + 1, 0.0, float(self.clipnorm or 0.0), 0,
+                                              stream_ptr()))
+        prog.weights_synced = True
+
     def apply_gradients(self, grads_and_vars, strategy=None, global_clip_norm=None, model=None, already_reduced=False):
         """All-reduce (SUM, un-normalised: App. A-13) the gradient arena across replicas, apply the per-variable
         clipnorm, then the Adam update. `global_clip_norm` fuses tf.clip_by_global_norm into the same pass when no
@@ -386,19 +412,33 @@ class GraphedTrainStep:
 
 class GraphedSegments:
     """A train step as an alternating list of captured CUDA graphs and eager hooks (the NCCL collectives):
-        plan = [("graph", fn), ("eager", fn), ("graph", fn), ...]
+        plan = [("graph", fn), ("eager", fn), ("side_graph", fn), ...]
     Every fn takes no arguments and works on static device buffers; "graph" items are captured once (after `warmup` eager
-    passes over the whole plan) and replayed, "eager" items are called as they are. This keeps the collectives outside the
-    graphs — so a bucket's all-reduce still overlaps the next graph segment — while removing the launch gaps of the ~430
-    kernels of a step. The first graph segment must start with ts_step_state_advance (see GraphedTrainStep)."""
+    passes over the whole plan) and replayed on the current stream, "side_graph" items are captured and replayed on
+    `side_stream` (work that may run underneath the main stream, e.g. the Adam update of an already reduced bucket),
+    "eager" items are called as they are. This keeps the collectives outside the graphs — so a bucket's all-reduce still
+    overlaps the next graph segment — while removing the launch gaps of the ~430 kernels of a step. The first graph
+    segment must start with ts_step_state_advance (see GraphedTrainStep). `bump_iterations`: the plan's update items do
+    not advance optimizer.iterations themselves (per-bucket updates), so the step does it once."""
 
-    def __init__(self, plan, model, optimizer, warmup=3):
-        self.plan, self.opt = plan, optimizer
+    def __init__(self, plan, model, optimizer, warmup=3, side_stream=None, bump_iterations=False):
+        self.plan, self.opt, self.bump = plan, optimizer, bump_iterations
         self.ctx = model._prog.ctx
         dev = model._prog.device
+        self.side = side_stream
+
+        def run_side(fn):
+            with torch.cuda.stream(self.side):
+                fn()
+
         for _ in range(warmup):
             for kind, fn in plan:
-                fn()
+                if kind == "side_graph":
+                    run_side(fn)
+                else:
+                    fn()
+            if bump_iterations:
+                optimizer.iterations += 1
         torch.cuda.synchronize(dev)
         self.ctx.check(self.ctx.lib.ts_step_state_set(self.ctx.h, 0, int(optimizer.iterations), stream_ptr()))
         torch.cuda.synchronize(dev)
@@ -407,11 +447,14 @@ class GraphedSegments:
         l0 = self.ctx.lib.ts_launch_count(self.ctx.h)
         self.items = []
         for kind, fn in plan:
-            if kind == "graph":
+            if kind in ("graph", "side_graph"):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     fn()
-                self.items.append(g.replay)
+                if kind == "graph":
+                    self.items.append(g.replay)
+                else:
+                    self.items.append(lambda g=g: run_side(g.replay))
             else:
                 self.items.append(fn)
         optimizer.device_step = False

@@ -272,22 +272,31 @@ def train_step(model, inputs, optimizer, dropout=True):
 
 def make_graphed_distributed_step(strategy, model, optimizer, example_features, example_labels, dropout=True, warmup=3,
                                   bucket_elems=16 * 1024 * 1024):
-    """distributed_train_step (W:819-848) as CUDA graphs between the eager NCCL all-reduces: the backward stages are grouped
-    into buckets (arena prefixes that are final, ts_whisper_stage_end); each group is one graph, and after it the bucket's
-    all-reduce (SUM, un-normalised — App. C-3) is issued asynchronously so that it overlaps the next group's graph.
-    Returns (step(features, labels) -> reduced loss, segments)."""
+    """distributed_train_step (W:819-848) as CUDA graphs between the eager NCCL all-reduces. The backward stages are grouped
+    into buckets (arena prefixes that are final, ts_whisper_stage_end). Per bucket g:
+        main stream : graph [backward stages of g] -> async all-reduce SUM of bucket g (un-normalised — App. C-3)
+    so the reductions of earlier buckets run underneath the remaining backward graphs; after the last bucket the step waits
+    for all reductions and replays the Adam graph. With TETHYS_SIDE_ADAM=1 each bucket is instead updated on a side stream as
+    soon as it is reduced (a bucket's parameters are no longer read by later backward stages). Returns (step(features, labels) -> reduced loss, segments)."""
     from .runtime import GraphedSegments
 
     prog = model._prog
-    feats = example_features.to(prog.device).clone()
-    labels = example_labels.to(prog.device).clone()
-    state = {"works": []}
+    dev = prog.device
+    feats = example_features.to(dev).clone()
+    labels = example_labels.to(dev).clone()
+    state = {}
     ends = prog.stage_ends
     groups, start, first = [], 0, 0
     for s_, end in enumerate(ends):
         if end - start >= bucket_elems or s_ == len(ends) - 1:
-            groups.append((first, s_, start, end))
+            if end > start:
+                groups.append((first, s_, start, end))
             start, first = end, s_ + 1
+    # measured at N=2: updating reduced buckets on a side stream underneath backward does not pay (7.18 vs 7.10 ms: the Adam
+    # passes compete with backward for HBM) — opt-in only
+    side_adam = bool(os.environ.get("TETHYS_SIDE_ADAM"))
+    optims = [prog.make_optim_range(a0, a1) for (_, _, a0, a1) in groups] if side_adam else None
+    side = torch.cuda.Stream(device=dev)
     plan = []
 
     def seg_forward():
@@ -295,6 +304,7 @@ def make_graphed_distributed_step(strategy, model, optimizer, example_features, 
         out = model(feats, labels=labels, training=True, dropout=dropout)
         state["loss"] = out["loss"]
 
+    works = []
     for gi, (s0, s1, a0, a1) in enumerate(groups):
         def seg_bwd(s0=s0, s1=s1, gi=gi):
             if gi == 0:
@@ -302,21 +312,31 @@ def make_graphed_distributed_step(strategy, model, optimizer, example_features, 
             prog.backward(s0, s1)
 
         def seg_reduce(a0=a0, a1=a1):
-            if a1 > a0:
-                state["works"].append(strategy.dist.all_reduce(prog.grads[a0:a1], op=strategy.dist.ReduceOp.SUM, async_op=True))
+            works.append(strategy.dist.all_reduce(prog.grads[a0:a1], op=strategy.dist.ReduceOp.SUM, async_op=True))
 
         plan += [("graph", seg_bwd), ("eager", seg_reduce)]
+        if side_adam:
+            def seg_side_wait():
+                side.wait_stream(torch.cuda.current_stream(dev))    # Adam's state / step counter are ordered after this step's start
+                with torch.cuda.stream(side):
+                    works.pop(0).wait()
 
-    def seg_wait():
-        for w in state["works"]:
-            w.wait()
-        state["works"] = []
+            def seg_side_update(gi=gi):
+                optimizer.update_range(model, optims[gi])
 
-    def seg_update():
-        optimizer.update(model)
+            plan += [("eager", seg_side_wait), ("side_graph", seg_side_update)]
 
-    plan += [("eager", seg_wait), ("graph", seg_update)]
-    segs = GraphedSegments(plan, model, optimizer, warmup=warmup)
+    def seg_join():
+        if side_adam:
+            torch.cuda.current_stream(dev).wait_stream(side)
+        else:
+            while works:
+                works.pop(0).wait()
+
+    plan += [("eager", seg_join)]
+    if not side_adam:
+        plan += [("graph", lambda: optimizer.update(model))]
+    segs = GraphedSegments(plan, model, optimizer, warmup=warmup, side_stream=side, bump_iterations=side_adam)
 
     def step(features, lab):
         feats.copy_(features, non_blocking=True)
