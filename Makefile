@@ -9,7 +9,7 @@ OBJS      := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
 HDRS      := $(wildcard $(CSRC)/*.cuh) include/tethys.h
 LIB       := tethys_speech_b200/libtethys.so
 
-all: $(LIB) tools/selftest_gemm tools/selftest_attn
+all: $(LIB) tools/selftest_gemm tools/selftest_attn tools/nvml_sampler
 
 build/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p build
@@ -26,7 +26,10 @@ tools/selftest_attn: tools/selftest_attn.cu $(LIB) include/tethys.h
 	$(NVCC) $(ARCH) -O2 -std=c++17 -cudart static -o $@ tools/selftest_attn.cu -Ltethys_speech_b200 -ltethys \
 	    -Xlinker -rpath -Xlinker '$$ORIGIN/../tethys_speech_b200'
 
+tools/nvml_sampler: tools/nvml_sampler.cpp
+	g++ -O2 -std=c++17 -Wall -o $@ tools/nvml_sampler.cpp -ldl
+
 clean:
-	rm -rf build $(LIB) tools/selftest_gemm tools/selftest_attn
+	rm -rf build $(LIB) tools/selftest_gemm tools/selftest_attn tools/nvml_sampler
 
 .PHONY: all clean

@@ -164,6 +164,16 @@ int ts_layernorm_bwd(ts_ctx* ctx, int dtype, const void* dy, const void* x, cons
 int ts_groupnorm_gelu_fwd(ts_ctx* ctx, int dtype, const void* x, const float* gamma, const float* beta, void* y, float* mean,
                           float* rstd, double* accum, int batch, int t, int c, int groups, float eps, void* stream);
 
+/* ---- span masking utilities ------------------------------------------------------------------------
+ * apply_time_mask (V:1073-1095, axis = 1) / apply_feature_mask (V:1098-1120, axis = 2) on x [batch, t, h]:
+ *   expanded[b, p] = OR_{i < mask_length} start_mask[b, p - i]   (p = time step or feature index; bit-exact integer work)
+ *   y = x * (1 - expanded)
+ * start_mask: uint8 [batch, t] (axis 1) or [batch, h] (axis 2) — the span starts the reference draws with
+ * tf.random.uniform(...) < mask_prob; expanded_mask (fp32 0/1, same shape) is an output.
+ */
+int ts_span_mask_apply(ts_ctx* ctx, int dtype, const void* x, const unsigned char* start_mask, void* y, float* expanded_mask,
+                       int batch, int t, int h, int axis, int mask_length, void* stream);
+
 /* ---- K19/K20: gradient clipping + Keras-2.10 legacy Adam over a flat arena ------------------------
  * Replaces tf.clip_by_global_norm (V:1243, VS:1171), the optimizer's clipnorm=1.0 (V:1274, VS:1206) and
  * tf.keras.optimizers.Adam.apply_gradients (W:834, V:1246, VS:1174, WS:1179) minus its all-reduce.

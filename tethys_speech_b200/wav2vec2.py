@@ -374,6 +374,37 @@ def distributed_train_step(strategy, model, dist_inputs, optimizer, neg_indices=
     return strategy.reduce(ReduceOp.SUM, per_replica_losses, axis=None)
 
 
+def _span_mask(hidden_states, start_mask, mask_prob, mask_length, axis):
+    dev = torch.device("cuda", torch.cuda.current_device())
+    x = hidden_states if isinstance(hidden_states, torch.Tensor) and hidden_states.is_cuda else to_device(hidden_states, torch.float32, dev)
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    x = x.contiguous()
+    B, T, H = x.shape
+    L = T if axis == 1 else H
+    if start_mask is None:
+        start_mask = torch.rand(B, L, device=x.device) < mask_prob          # tf.random.uniform(shape) < mask_prob (V:1078 / V:1103)
+    start = to_device(start_mask, torch.uint8, x.device)
+    y = torch.empty_like(x)
+    expanded = torch.empty(B, L, dtype=torch.float32, device=x.device)
+    ctx = _lib.context(x.device.index)
+    dt = _lib.TS_F32 if x.dtype == torch.float32 else _lib.TS_BF16
+    ctx.check(ctx.lib.ts_span_mask_apply(ctx.h, dt, ptr(x), ptr(start), ptr(y), ptr(expanded), B, T, H, axis, int(mask_length),
+                                         stream_ptr()))
+    return y, (expanded.unsqueeze(-1) if axis == 1 else expanded.unsqueeze(1))
+
+
+def apply_time_mask(hidden_states, mask_prob=0.05, mask_length=10, start_mask=None):
+    """V:1073-1095 — returns (masked_hidden_states, expanded_mask [B, T, 1]). `start_mask` ([B, T] bool) injects the span
+    starts (parity tests); otherwise they are drawn on the device."""
+    return _span_mask(hidden_states, start_mask, mask_prob, mask_length, 1)
+
+
+def apply_feature_mask(hidden_states, mask_prob=0.05, mask_length=10, start_mask=None):
+    """V:1098-1120 — returns (masked_hidden_states, expanded_mask [B, 1, H])."""
+    return _span_mask(hidden_states, start_mask, mask_prob, mask_length, 2)
+
+
 def make_graphed_distributed_step(strategy, model, optimizer, example_features, dropout=True, warmup=3):
     """distributed_train_step (V:1186-1260) as CUDA graphs around the eager NCCL all-reduce:
        graph [advance state, forward (loss / N), backward, local clip_by_global_norm] -> eager all-reduce SUM of the gradient
