@@ -13,7 +13,7 @@ def main(strategy, args, task_type, task_index):
     print("Whisper 분산 학습 시작...")
     start_time = time.time()
     train.train_whisper(strategy, "small" if args.model_type is None else args.model_type, batch_size=args.batch_size,
-                        num_batches=args.num_batches, precision=args.precision)
+                        num_batches=args.num_batches, precision=args.precision, from_waveform=args.from_waveform)
     jct = time.time() - start_time
     print("Training completed.")
     if strategy.rank == 0:
@@ -26,6 +26,8 @@ if __name__ == "__main__":
     parser.add_argument("--batch_size", type=int, default=1, help="batch size per replica, default is set 1")
     parser.add_argument("--model_type", type=str, default=None, help="extension: tiny|base|small|medium|large (reference: small)")
     parser.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"], help="extension: compute precision")
+    parser.add_argument("--from_waveform", action="store_true",
+                        help="extension (SURVEY f-1): feed raw 30 s waveforms through the fused log-mel kernel (W:739-766)")
     args = parser.parse_args()
     task_type, task_index = train.task_from_tf_config()
     strategy = train.make_strategy()

@@ -15,6 +15,7 @@ if __name__ == "__main__":
     parser.add_argument("--batch_size", type=int, default=4)
     parser.add_argument("--legacy_wav2vec2", action="store_true", help="literal behaviour of the reference file (WS:1183-1258)")
     parser.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
+    parser.add_argument("--from_waveform", action="store_true", help="feed raw 30 s waveforms through the fused log-mel kernel (W:739-766) instead of ready-made mel features")
     args = parser.parse_args()
     strategy = train.make_strategy()
     start = time.time()
@@ -22,6 +23,7 @@ if __name__ == "__main__":
         train.train_wav2vec2(strategy, "pretraining", "base", batch_size=args.batch_size, num_batches=args.num_batches,
                              precision=args.precision, audio_length=80000, legacy=True)
     else:
-        train.train_whisper(strategy, "small", batch_size=args.batch_size, num_batches=args.num_batches, precision=args.precision)
+        train.train_whisper(strategy, "small", batch_size=args.batch_size, num_batches=args.num_batches, precision=args.precision,
+                            from_waveform=args.from_waveform)
     print("Training completed.")
     print("jct:", time.time() - start)

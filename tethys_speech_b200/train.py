@@ -51,14 +51,16 @@ def write_jct(jct, task_type, task_index):
 
 
 def train_whisper(strategy, model_type="small", num_epochs=1, learning_rate=1e-4, batch_size=1, num_batches=40,
-                  precision="bf16", seq_len=3000):
-    """W:894-958."""
+                  precision="bf16", seq_len=3000, from_waveform=False):
+    """W:894-958. from_waveform=True (extension, SURVEY f-1): the dataset yields raw 30 s waveforms and the fused log-mel kernel
+    (extract_fbank_features, W:739-766) produces the model input inside the loop."""
     with strategy.scope():
         model = WH.create_whisper_model(model_type=model_type, precision=precision, device=strategy.local_rank)
         model.broadcast_weights(strategy)
         optimizer = Adam(learning_rate=learning_rate)
     global_batch = batch_size * strategy.num_replicas_in_sync
-    dataset = WH.create_dummy_dataset(global_batch, seq_len=seq_len)
+    dataset = (WH.create_dummy_waveform_dataset(global_batch, audio_seconds=seq_len / 100.0) if from_waveform
+               else WH.create_dummy_dataset(global_batch, seq_len=seq_len))
     step = 0
     start_time = time.time()
     for epoch in range(num_epochs):
@@ -70,6 +72,8 @@ def train_whisper(strategy, model_type="small", num_epochs=1, learning_rate=1e-4
             if feats.shape[0] == 0:
                 continue
             step_start = time.time()
+            if from_waveform:
+                feats = WH.waveform_to_features(feats, device=strategy.local_rank)
             loss = WH.distributed_train_step(strategy, model, (feats, labels), optimizer)
             loss_value = float(loss)                              # device sync (the reference's loss.numpy(), W:951)
             _log_step(step, loss_value, start_time, time.time() - step_start)

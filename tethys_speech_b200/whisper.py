@@ -241,6 +241,43 @@ def create_dummy_dataset(batch_size, n_mels=80, seq_len=3000, max_target_length=
     return gen()
 
 
+def create_dummy_waveform_dataset(batch_size, audio_seconds=30.0, sample_rate=16000, max_target_length=100, num_samples=50, seed=1234):
+    """f-1: the dummy dataset of W:784-815 one stage earlier — N(0,1) WAVEFORMS [num_samples, seconds * 16000]
+    instead of ready-made mel features; `waveform_to_features` turns a batch into the [B, 80, frames] model input with the
+    fused log-mel kernel (extract_fbank_features, W:739-766). Labels as in create_dummy_dataset."""
+    rng = np.random.default_rng(seed)
+    n = int(round(audio_seconds * sample_rate))
+    waves = torch.from_numpy(rng.standard_normal((num_samples, n), dtype=np.float32))
+    labels = np.zeros((num_samples, max_target_length), dtype=np.int32)
+    lens = rng.integers(50, 90, size=num_samples)
+    for i in range(num_samples):
+        k = int(lens[i])
+        labels[i, 0] = 1
+        labels[i, 1:k - 1] = rng.integers(3, 100, size=k - 2)
+        labels[i, k - 1] = 2
+    labels = torch.from_numpy(labels)
+    if torch.cuda.is_available():
+        waves, labels = waves.pin_memory(), labels.pin_memory()
+
+    def gen():
+        while True:
+            for i in range(0, num_samples, batch_size):
+                yield waves[i:i + batch_size], labels[i:i + batch_size]
+
+    return gen()
+
+
+def waveform_to_features(waveform, device=None):
+    """[B, N] waveform -> [B, 80, F] log-mel in the layout WhisperEncoder.call consumes (W:326-329); F is made even by
+    dropping the last frame if necessary (the conv stem halves it)."""
+    from .frontend import extract_fbank_features
+
+    mel = extract_fbank_features(waveform, mel_major=True, device=device)
+    if mel.shape[-1] % 2:
+        mel = mel[..., :-1].contiguous()
+    return mel
+
+
 def distributed_train_step(strategy, model, dist_inputs, optimizer, dropout=True):
     """W:819-848: per replica forward + mean CE loss, gradients, optimizer.apply_gradients (all-reduce SUM across replicas
     WITHOUT dividing — App. C-3 — then Adam), and strategy.reduce(SUM) of the per-replica losses."""
