@@ -216,6 +216,13 @@ typedef struct {
   int32_t num_negatives;
   float ln_eps, temperature, diversity_weight;
   float hidden_dropout, activation_dropout, attention_dropout;
+  /* task head on the trunk (SURVEY f-2): 0 = pre-training (contrastive), 1 = Wav2Vec2ForCTC (V:940-1001),
+   * 2 = Wav2Vec2ForSequenceClassification (V:1004-1070). Heads 1/2 have no project_hid / project_q variables (Keras never
+   * builds them there); the quantizer's exist and get zero gradients, as in the reference (VS:1163-1166). */
+  int32_t head;
+  int32_t vocab_size;       /* head 1: lm_head width (V:104) */
+  int32_t classifier_proj;  /* head 2: classifier_proj_size (V:108-114) */
+  int32_t num_labels;       /* head 2: VS:131 */
 } ts_w2v_config;
 
 typedef struct ts_w2v ts_w2v;
@@ -233,6 +240,13 @@ int ts_w2v_bind(ts_w2v* m, float* params, float* grads, void* params_bf16 /*bf16
 int ts_w2v_sync_compute_weights(ts_w2v* m, void* stream); /* fp32 master -> bf16 compute copy */
 int ts_w2v_forward(ts_w2v* m, const float* wave /*[B,N]*/, int batch, int n_samples, const int32_t* neg, int64_t neg_bs,
                    int64_t neg_ts, float loss_div /*num replicas, V:1231*/, uint64_t seed, int training, void* stream);
+/* heads 1/2: model(features, labels=labels, training=…) of VS:1156-1157. labels: int32 [batch] for head 2 (NULL = zeros, the
+ * dummy dataset's label, V:1139), ignored by head 1 (its stand-in "CTC" loss targets class 0 on every frame, V:997-1000).
+ * training != 0 also runs the quantizer (V:784-789) and computes loss ("scalars"[0]) + the loss gradient for
+ * ts_w2v_backward; dropout != 0 enables the dropout layers of a training call (parity runs switch them off); logits are in
+ * the "head_logits" buffer (fp32). */
+int ts_w2v_forward_head(ts_w2v* m, const float* wave, int batch, int n_samples, const int32_t* labels, float loss_div,
+                        uint64_t seed, int dropout, int training, void* stream);
 /* Wav2Vec2FeatureExtractor.call only (V:283-298): conv stack + GroupNorm/GELU + positional conv + LayerNorm, inference mode;
  * result in the "extract_features" buffer. Used by the front-end microbench (BASELINE config 5). */
 int ts_w2v_forward_features(ts_w2v* m, const float* wave, int batch, int n_samples, void* stream);

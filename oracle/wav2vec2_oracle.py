@@ -59,6 +59,9 @@ class Wav2Vec2Config:
         self.diversity_loss_weight = 0.1
         self.hidden_dropout = self.activation_dropout = self.attention_dropout = 0.1
         self.do_stable_layer_norm = True
+        self.vocab_size = 32                                                             # V:104
+        self.classifier_proj_size = {"small": 128, "tiny": 64}.get(model_size, 256)      # V:108-114
+        self.num_labels = 10                                                             # VS:131
 
 
 def init_weights(cfg, seed=0, dtype=torch.float32):
@@ -299,6 +302,76 @@ def train_step(cfg, w, m, v, t, wave, neg_idx, lr=3e-5, eps=1e-8, legacy=False, 
     T.keras_adam_step([w[k] for k in names], grads, [m[k] for k in names], [v[k] for k in names], t, lr,
                       eps=(1e-7 if legacy else eps))
     out["grads_applied"] = OrderedDict(zip(names, grads))
+    return out
+
+
+# ---- task heads on the trunk: Wav2Vec2ForCTC V:940-1001, Wav2Vec2ForSequenceClassification V:1004-1070 ----
+def init_head_weights(cfg, head, seed=0, dtype=torch.float32):
+    """Variables of a task-head model: the trunk's (Wav2Vec2Model incl. the quantizer, which is called in training mode;
+    project_hid / project_q are never called there and so never built) + the head's Dense layers."""
+    w = init_weights(cfg, seed, dtype)
+    for k in [k for k in w if k.startswith("project_hid.") or k.startswith("project_q.")]:
+        del w[k]
+    g = torch.Generator().manual_seed(seed + 7919)
+    H = cfg.hidden_size
+    if head == "ctc":
+        w["lm_head.kernel"] = T.glorot_uniform(g, (H, cfg.vocab_size), H, cfg.vocab_size, dtype)
+        w["lm_head.bias"] = torch.zeros(cfg.vocab_size, dtype=dtype)
+    elif head == "classification":
+        P = cfg.classifier_proj_size
+        w["classifier_proj.kernel"] = T.glorot_uniform(g, (H, P), H, P, dtype)
+        w["classifier_proj.bias"] = torch.zeros(P, dtype=dtype)
+        w["classifier.kernel"] = T.glorot_uniform(g, (P, cfg.num_labels), P, cfg.num_labels, dtype)
+        w["classifier.bias"] = torch.zeros(cfg.num_labels, dtype=dtype)
+    else:
+        raise ValueError(head)
+    return w
+
+
+def trunk(cfg, w, wave):
+    """Wav2Vec2Model.call(training=True) — V:768-825 — up to last_hidden_state (the quantizer output is unused by the heads)."""
+    ef = feature_extractor(cfg, w, wave)
+    hs = T.layer_norm(T.dense(ef, w["feature_projection.kernel"], w["feature_projection.bias"]),
+                      w["feature_projection_layer_norm.gamma"], w["feature_projection_layer_norm.beta"], cfg.layer_norm_eps)
+    return encoder(cfg, w, hs)
+
+
+def forward_head(cfg, w, wave, labels, head):
+    """head 'ctc': logits = lm_head(hidden) [B,T,V]; loss = mean CE of every frame against class 0 (V:994-1000).
+    head 'classification': pooled = mean_t hidden (V:1043); tanh Dense; Dense; loss = mean sparse CE(labels) (V:1052-1056)."""
+    h = trunk(cfg, w, wave)
+    out = {"last_hidden_state": h}
+    if head == "ctc":
+        logits = T.dense(h, w["lm_head.kernel"], w["lm_head.bias"])
+        tgt = torch.zeros(logits.shape[:2], dtype=torch.long)
+        loss = T.softmax_xent_sparse(logits, tgt).mean()
+    else:
+        pooled = h.mean(dim=1)
+        proj = torch.tanh(T.dense(pooled, w["classifier_proj.kernel"], w["classifier_proj.bias"]))
+        logits = T.dense(proj, w["classifier.kernel"], w["classifier.bias"])
+        loss = T.softmax_xent_sparse(logits, labels.long()).mean()
+        out["pooled_output"] = pooled
+    out["logits"], out["loss"] = logits, loss
+    return out
+
+
+def head_loss_and_grads(cfg, w, wave, labels, head, loss_div=1.0):
+    """tape.gradient(loss, trainable_variables) with None -> zeros (the quantizer's variables) — VS:1163-1166."""
+    ws = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in w.items())
+    out = forward_head(cfg, ws, wave, labels, head)
+    grads = torch.autograd.grad(out["loss"] / loss_div, list(ws.values()), allow_unused=True)
+    g = OrderedDict((k, (torch.zeros_like(v) if gi is None else gi)) for (k, v), gi in zip(ws.items(), grads))
+    return out, g
+
+
+def head_train_step(cfg, w, m, v, t, wave, labels, head, lr=3e-5, eps=1e-8):
+    """VS:1119-1176 for model_type 'asr' / 'classification': grads -> clip_by_global_norm(1.0) -> clipnorm 1.0 -> Adam."""
+    out, g = head_loss_and_grads(cfg, w, wave, labels, head)
+    names = list(w.keys())
+    grads, gnorm = T.clip_by_global_norm([g[k] for k in names], 1.0)
+    out["global_norm"] = gnorm
+    grads = T.clip_by_norm_each(grads, 1.0)
+    T.keras_adam_step([w[k] for k in names], grads, [m[k] for k in names], [v[k] for k in names], t, lr, eps=eps)
     return out
 
 

@@ -14,6 +14,7 @@ if __name__ == "__main__":
     parser.add_argument("--model_size", type=str, default="small", choices=["tiny", "small", "base", "large"])
     parser.add_argument("--audio_length", type=int, default=32000, help="extension: samples per clip (reference: 32000)")
     parser.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
+    parser.add_argument("--resume", type=str, default=None, help="extension (SURVEY f-3): checkpoint file or directory to restore model + optimizer from")
     args = parser.parse_args()
     task_type, task_index = train.task_from_tf_config()
     strategy = train.make_strategy()
@@ -22,7 +23,7 @@ if __name__ == "__main__":
     print(f"num_batches: {args.num_batches}")
     start = time.time()
     train.train_wav2vec2(strategy, "pretraining", args.model_size, batch_size=args.batch_size, num_batches=args.num_batches,
-                         precision=args.precision, audio_length=args.audio_length)
+                         precision=args.precision, audio_length=args.audio_length, resume_from=args.resume)
     jct = time.time() - start
     print("Training completed.")
     if strategy.rank == 0:

@@ -13,7 +13,8 @@ def main(strategy, args, task_type, task_index):
     print("Whisper 분산 학습 시작...")
     start_time = time.time()
     train.train_whisper(strategy, "small" if args.model_type is None else args.model_type, batch_size=args.batch_size,
-                        num_batches=args.num_batches, precision=args.precision, from_waveform=args.from_waveform)
+                        num_batches=args.num_batches, precision=args.precision, from_waveform=args.from_waveform,
+                        resume_from=args.resume)
     jct = time.time() - start_time
     print("Training completed.")
     if strategy.rank == 0:
@@ -28,6 +29,7 @@ if __name__ == "__main__":
     parser.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"], help="extension: compute precision")
     parser.add_argument("--from_waveform", action="store_true",
                         help="extension (SURVEY f-1): feed raw 30 s waveforms through the fused log-mel kernel (W:739-766)")
+    parser.add_argument("--resume", type=str, default=None, help="extension (SURVEY f-3): checkpoint file or directory to restore model + optimizer from")
     args = parser.parse_args()
     task_type, task_index = train.task_from_tf_config()
     strategy = train.make_strategy()

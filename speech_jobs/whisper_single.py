@@ -16,14 +16,15 @@ if __name__ == "__main__":
     parser.add_argument("--legacy_wav2vec2", action="store_true", help="literal behaviour of the reference file (WS:1183-1258)")
     parser.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
     parser.add_argument("--from_waveform", action="store_true", help="feed raw 30 s waveforms through the fused log-mel kernel (W:739-766) instead of ready-made mel features")
+    parser.add_argument("--resume", type=str, default=None, help="extension (SURVEY f-3): checkpoint file or directory to restore model + optimizer from")
     args = parser.parse_args()
     strategy = train.make_strategy()
     start = time.time()
     if args.legacy_wav2vec2:
         train.train_wav2vec2(strategy, "pretraining", "base", batch_size=args.batch_size, num_batches=args.num_batches,
-                             precision=args.precision, audio_length=80000, legacy=True)
+                             precision=args.precision, audio_length=80000, legacy=True, resume_from=args.resume)
     else:
         train.train_whisper(strategy, "small", batch_size=args.batch_size, num_batches=args.num_batches, precision=args.precision,
-                            from_waveform=args.from_waveform)
+                            from_waveform=args.from_waveform, resume_from=args.resume)
     print("Training completed.")
     print("jct:", time.time() - start)

@@ -46,7 +46,7 @@ def test_struct_layouts_match_c():
     from tethys_speech_b200 import _lib
 
     assert ctypes.sizeof(_lib.GemmDesc) % 8 == 0
-    assert ctypes.sizeof(_lib.W2VConfig) == 4 * (5 + 24 + 7) + 4 * 6
+    assert ctypes.sizeof(_lib.W2VConfig) == 4 * (5 + 24 + 7) + 4 * 6 + 4 * 4
 
 
 def test_no_cpu_fallback_without_gpu():

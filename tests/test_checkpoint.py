@@ -1,0 +1,175 @@
+"""Checkpoint save / restore (reference save sites V:1286-1288, V:1341, V:1362, W:956, W:1025).
+CPU: the file container and the arena <-> variable mapping (incl. column slices of fused q/k/v blocks), error behaviour.
+GPU: a restored run continues bit-identically to the uninterrupted one (parameters, Adam moments, step count, dropout seed)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tethys_speech_b200 import checkpoint as CK
+
+
+def _fake_info():
+    # one dense vector, one dense matrix, three column slices of a fused [4, 3*5 (+1 pad)] block, one 3-d kernel
+    return {
+        "ln.gamma": (0, (7,), 7),
+        "dense.kernel": (64, (3, 4), 12),
+        "attn.q.kernel": (128, (4, 5), 16),
+        "attn.k.kernel": (133, (4, 5), 16),
+        "attn.v.kernel": (138, (4, 5), 16),
+        "conv.kernel": (256, (2, 3, 4), 24),
+    }
+
+
+def test_gather_scatter_roundtrip_with_fused_blocks():
+    info = _fake_info()
+    rng = np.random.default_rng(0)
+    arena = rng.standard_normal(320).astype(np.float32)
+    vars_ = CK.gather_variables(arena, info)
+    assert vars_["attn.k.kernel"].shape == (4, 5)
+    # column slice: row r of k starts at 133 + 16 r
+    for r in range(4):
+        np.testing.assert_array_equal(vars_["attn.k.kernel"][r], arena[133 + 16 * r:138 + 16 * r])
+    np.testing.assert_array_equal(vars_["conv.kernel"].reshape(-1), arena[256:280])
+    other = np.full(320, -7.0, np.float32)
+    done = CK.scatter_variables(other, info, vars_)
+    assert sorted(done) == sorted(info)
+    again = CK.gather_variables(other, info)
+    for k in info:
+        np.testing.assert_array_equal(again[k], vars_[k])
+    # bytes outside any variable (alignment gaps, the pad column of the fused block) are left alone
+    assert other[7] == -7.0 and other[128 + 15] == -7.0 and other[300] == -7.0
+
+
+def test_scatter_errors():
+    info = _fake_info()
+    arena = np.zeros(320, np.float32)
+    vars_ = CK.gather_variables(arena, info)
+    missing = {k: v for k, v in vars_.items() if k != "ln.gamma"}
+    with pytest.raises(KeyError):
+        CK.scatter_variables(arena, info, missing)
+    assert "ln.gamma" not in CK.scatter_variables(arena, info, missing, strict=False)
+    bad = dict(vars_)
+    bad["dense.kernel"] = np.zeros((4, 3), np.float32)
+    with pytest.raises(ValueError):
+        CK.scatter_variables(arena, info, bad)
+    extra = dict(vars_)
+    extra["nope"] = np.zeros(1, np.float32)
+    with pytest.raises(KeyError):
+        CK.scatter_variables(arena, info, extra)
+
+
+def test_file_container_roundtrip_alignment_and_truncation(tmp_path):
+    rng = np.random.default_rng(1)
+    tensors = {"model/a": rng.standard_normal((3, 5)).astype(np.float32),
+               "model/b": rng.standard_normal(1).astype(np.float32),
+               "optimizer/m/a": np.zeros((0,), np.float32),
+               "ids": np.arange(11, dtype=np.int64)}
+    path = str(tmp_path / "x.tsckpt")
+    CK.write_file(path, tensors, {"hello": 1})
+    assert not os.path.exists(path + ".tmp")
+    meta, back = CK.read_file(path)
+    assert meta == {"hello": 1}
+    assert list(back) == list(tensors)
+    for k in tensors:
+        assert back[k].dtype == tensors[k].dtype and back[k].shape == tensors[k].shape
+        np.testing.assert_array_equal(back[k], tensors[k])
+    # header is self-describing JSON and every array starts 64-byte aligned in the file
+    raw = open(path, "rb").read()
+    assert raw[:8] == CK.MAGIC
+    hlen = int.from_bytes(raw[8:16], "little")
+    hdr = json.loads(raw[16:16 + hlen])
+    assert (16 + hlen) % 64 == 0 and all(d["offset"] % 64 == 0 for d in hdr["tensors"].values())
+    _, only = CK.read_file(path, keys=lambda k: k.startswith("model/"))
+    assert sorted(only) == ["model/a", "model/b"]
+    with open(path, "wb") as f:
+        f.write(raw[:-8])
+    with pytest.raises(ValueError):
+        CK.read_file(path)
+    with open(path, "wb") as f:
+        f.write(b"not a checkpoint at all")
+    with pytest.raises(ValueError):
+        CK.read_file(path)
+
+
+def test_latest_checkpoint_and_tf_keys(tmp_path):
+    assert CK.latest_checkpoint(str(tmp_path)) is None
+    for n in (1, 2, 10):
+        CK.write_file(str(tmp_path / f"model_step-{n}.tsckpt"), {}, {})
+    assert CK.latest_checkpoint(str(tmp_path)).endswith("model_step-10.tsckpt")
+    assert CK.tf_object_key("encoder.layers.0.attention.q_proj.kernel") == \
+        "model/encoder/layers/0/attention/q_proj/kernel/.ATTRIBUTES/VARIABLE_VALUE"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def _w2v(seed, precision):
+    from tethys_speech_b200 import wav2vec2 as W
+    from tethys_speech_b200.runtime import Adam
+
+    model = W.Wav2Vec2ForPreTraining(W.Wav2Vec2Config("tiny"), precision=precision, device=0, seed=seed)
+    opt = Adam(learning_rate=1e-3, epsilon=1e-8, clipnorm=1.0)
+    return W, model, opt
+
+
+@pytest.mark.gpu
+def test_restore_continues_the_run_w2v_fp32(tmp_path):
+    """Steps 3-4 after a restore must reproduce steps 3-4 of the straight run with dropout on — which needs parameters, m, v,
+    the iteration count and the dropout step seed all restored. fp32 mode differs between two executions only by the order
+    of the atomic adds in the bias / norm gradient reductions, hence the 1e-6 bars (a wrong dropout mask or a bias-correction
+    step off by one changes the loss in the second digit)."""
+    g = torch.Generator().manual_seed(5)
+    wave = torch.randn(2, 6400, generator=g).cuda()
+    W, m1, o1 = _w2v(3, "fp32")
+    T = m1.num_frames(6400)
+    neg = m1._sample_negative_indices(T, 2)[:, 0, :].contiguous()
+    for _ in range(2):
+        W.train_step(m1, (wave, None), o1, neg_indices=neg)
+    ck = CK.Checkpoint(model=m1, optimizer=o1)
+    path = ck.save(str(tmp_path / "ckpt" / "model_step"))
+    assert path.endswith("model_step-1.tsckpt") and CK.latest_checkpoint(str(tmp_path / "ckpt")) == path
+    straight = [float(W.train_step(m1, (wave, None), o1, neg_indices=neg)) for _ in range(2)]
+
+    _, m2, o2 = _w2v(99, "fp32")                      # different init: everything must come from the file
+    meta = CK.Checkpoint(model=m2, optimizer=o2).restore(path)
+    assert meta["optimizer"]["iterations"] == 2 and o2.iterations == 2 and meta["kind"] == "Wav2Vec2ForPreTraining"
+    resumed = [float(W.train_step(m2, (wave, None), o2, neg_indices=neg)) for _ in range(2)]
+    assert all(abs(a - b) <= 1e-6 * abs(b) for a, b in zip(resumed, straight)), (resumed, straight)
+    s1, s2 = o1._bind(m1), o2._bind(m2)
+    for a, b in ((m1._prog.params, m2._prog.params), (s1["m"], s2["m"]), (s1["v"], s2["v"])):
+        assert float((a - b).norm() / b.norm()) < 1e-6
+    # every variable the model lists is in the file under its Keras path, with the fused q/k/v blocks split out again
+    _, tensors = CK.read_file(path)
+    assert {k[6:] for k in tensors if k.startswith("model/")} == set(m1.variable_names)
+    assert tensors["model/encoder.layers.0.attention.q_proj.kernel"].shape == (m1.config.hidden_size, m1.config.hidden_size)
+    m1._prog.ctx.watchdog()
+
+
+@pytest.mark.gpu
+def test_save_weights_load_weights_whisper_bf16(tmp_path):
+    """model.save_weights (W:1025) / load_weights: variables only; the bf16 compute copy is refreshed after a load (same loss)."""
+    from tethys_speech_b200 import whisper as WH
+
+    cfg = WH.WhisperConfig()
+    cfg.d_model, cfg.encoder_layers, cfg.decoder_layers, cfg.d_ff = 128, 1, 1, 256
+    cfg.encoder_attention_heads = cfg.decoder_attention_heads = 2
+    cfg.vocab_size, cfg.decoder_start_token_id = 512, 3
+    m1 = WH.WhisperForConditionalGeneration(cfg, precision="bf16", device=0, seed=1)
+    m2 = WH.WhisperForConditionalGeneration(cfg, precision="bf16", device=0, seed=2)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, cfg.n_mels, 200, generator=g).cuda()
+    lab = torch.randint(3, 100, (2, 12), generator=g).to(torch.int32).cuda()
+    l1 = float(m1(x, labels=lab, training=True, dropout=False)["loss"])
+    l2 = float(m2(x, labels=lab, training=True, dropout=False)["loss"])
+    assert abs(l1 - l2) > 1e-4 * l1
+    path = str(tmp_path / "w.tsckpt")
+    m1.save_weights(path)
+    meta = m2.load_weights(path)
+    assert "optimizer" not in meta
+    assert abs(float(m2(x, labels=lab, training=True, dropout=False)["loss"]) - l1) <= 1e-6 * l1   # loss sum = atomic adds
+    w1, w2 = m1.get_weights(), m2.get_weights()
+    assert all(torch.equal(w1[k], w2[k]) for k in w1)
+    from tethys_speech_b200.runtime import Adam
+    with pytest.raises(KeyError):
+        CK.restore(path, m2, Adam())                  # asks for optimizer state the file does not hold

@@ -69,6 +69,7 @@ class W2VConfig(C.Structure):
         ("num_negatives", C.c_int32),
         ("ln_eps", C.c_float), ("temperature", C.c_float), ("diversity_weight", C.c_float),
         ("hidden_dropout", C.c_float), ("activation_dropout", C.c_float), ("attention_dropout", C.c_float),
+        ("head", C.c_int32), ("vocab_size", C.c_int32), ("classifier_proj", C.c_int32), ("num_labels", C.c_int32),
     ]
 
 
@@ -119,6 +120,7 @@ SYMBOLS = {
     "ts_w2v_bind": (_I, [_P, _P, _P, _P, _P, _L]),
     "ts_w2v_sync_compute_weights": (_I, [_P, _P]),
     "ts_w2v_forward": (_I, [_P, _P, _I, _I, _P, _L, _L, _F, C.c_uint64, _I, _P]),
+    "ts_w2v_forward_head": (_I, [_P, _P, _I, _I, _P, _F, C.c_uint64, _I, _I, _P]),
     "ts_w2v_forward_features": (_I, [_P, _P, _I, _I, _P]),
     "ts_w2v_backward": (_I, [_P, _I, _I, _P]),
     "ts_w2v_get_buffer": (_I, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L)]),

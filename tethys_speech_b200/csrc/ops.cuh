@@ -96,6 +96,17 @@ int contrastive_fwd_bwd(Ctx*, int dt, const float* S, long long ld, const int* n
                         long long neg_ts, void* dS, long long ld_ds, float* logits, float* loss_sum, int B, int T,
                         int K, float temp, float grad_scale, cudaStream_t);
 
+// ---- task_heads.cu: CTC / sequence-classification heads on the Wav2Vec2 trunk (V:940-1070) ----------
+// row-wise sparse softmax CE on fp32 logits [R, ld] (labels NULL = class 0 everywhere, V:997-1000): accumulates the loss
+// sum and writes dlogits (act dtype, [R, ld_d]; nullable) = (softmax - onehot) * grad_scale.
+int ce_rows_fwd_bwd(Ctx*, int dt, const float* logits, long long ld, const int* labels, void* dlogits, long long ld_d,
+                    float* loss_sum, int R, int V, float grad_scale, cudaStream_t);
+int mean_pool_fwd(Ctx*, int dt, const void* x /*[B,T,C]*/, void* y /*[B,C]*/, int B, int T, int C, cudaStream_t);
+int mean_pool_bwd(Ctx*, int dt, const void* dy /*[B,C]*/, void* dx /*[B,T,C]*/, int B, int T, int C, cudaStream_t);
+int tanh_drop_fwd(Ctx*, int dt, const void* x, void* y /*tanh(x)*/, void* y_drop /*tanh(x)*mask*/, long long n, float drop,
+                  uint64_t seed, cudaStream_t);
+int tanh_drop_bwd(Ctx*, int dt, const void* dy, const void* y, void* dx, long long n, float drop, uint64_t seed, cudaStream_t);
+
 // ---- loss_ce.cu (whisper) ------------------------------------------------------------------------
 // shifted sparse softmax CE over logits [B,S,ldv] (valid V): rows s<S-1 with target labels[b,s+1];
 // writes dlogits (act dtype, in place over logits allowed; row S-1 and pad cols get 0) scaled by

@@ -91,6 +91,7 @@ struct GemmB {
   GemmB& alpha(float a) { d.alpha = a; return *this; }
   GemmB& drop(float rate, uint64_t seed) { d.drop = rate; d.seed = seed; return *this; }
   GemmB& acc() { d.accumulate = 1; return *this; }
+  GemmB& simt() { d.force_engine = 1; return *this; }   // tiny / oddly strided problems: CUDA-core engine
   int run(Ctx* ctx, cudaStream_t st) { return gemm(ctx, &d, st); }
 };
 

@@ -25,6 +25,7 @@ struct W2V {
   long long pos_w, pos_b, fe_ln_g, fe_ln_b, fp_w, fp_b, fp_ln_g, fp_ln_b;
   std::vector<W2VLayerOff> L;
   long long cb, qp_w, qp_b, ph_w, ph_b, ph_ln_g, ph_ln_b, pq_w, pq_b, pq_ln_g, pq_ln_b;
+  long long lm_w = -1, lm_b = -1, cp_w = -1, cp_b = -1, cl_w = -1, cl_b = -1;   // task heads (cfg.head 1 / 2)
   std::vector<long long> stage_end;  // arena offset below which grads are final after backward stage s
   // bound memory
   float *P = nullptr, *G = nullptr;
@@ -42,6 +43,10 @@ struct W2V {
   double* gn_accum;
   void *hg, *possum, *ef, *fp_out, *hs, *z, *qfeat, *ph_lin, *ps, *pq_lin, *pq, *dS, *wt_flip;
   float *S, *logits;
+  // task heads: dropped encoder output, fp32 logits + their gradient; pooled / projected states of the classifier
+  void *hd_in, *d_hlogits, *pooled, *cp_pre, *cp_act, *cp_drop, *d_cp, *d_pooled;
+  float* hlogits;
+  int head_rows = 0, head_cols = 0;
   float *fe_mean, *fe_rstd, *fp_mean, *fp_rstd, *ph_mean, *ph_rstd, *pq_mean, *pq_rstd;
   long long* code_idx;
   int* hist;
@@ -67,6 +72,16 @@ static void build_params(W2V* m) {
   ParamTable& pt = m->pt;
   const int H = c.hidden, F = c.ffn, C = c.conv_dim[c.n_conv - 1], D = c.cv_dim, Pj = c.proj_dim;
   // arena order = order in which gradients become final during backward (bucketed all-reduce overlap)
+  if (c.head == 1) {          // Wav2Vec2ForCTC: lm_head (V:950); project_hid / project_q are never built
+    m->lm_w = pt.add("lm_head.kernel", {H, c.vocab_size});
+    m->lm_b = pt.add("lm_head.bias", {c.vocab_size});
+  } else if (c.head == 2) {   // Wav2Vec2ForSequenceClassification: classifier_proj + classifier (V:1013-1015)
+    m->cl_w = pt.add("classifier.kernel", {c.classifier_proj, c.num_labels});
+    m->cl_b = pt.add("classifier.bias", {c.num_labels});
+    m->cp_w = pt.add("classifier_proj.kernel", {H, c.classifier_proj});
+    m->cp_b = pt.add("classifier_proj.bias", {c.classifier_proj});
+  }
+  if (c.head == 0) {
   m->pq_w = pt.add("project_q.dense.kernel", {D, Pj});
   m->pq_b = pt.add("project_q.dense.bias", {Pj});
   m->pq_ln_g = pt.add("project_q.layer_norm.gamma", {Pj});
@@ -75,6 +90,7 @@ static void build_params(W2V* m) {
   m->ph_b = pt.add("project_hid.dense.bias", {Pj});
   m->ph_ln_g = pt.add("project_hid.layer_norm.gamma", {Pj});
   m->ph_ln_b = pt.add("project_hid.layer_norm.beta", {Pj});
+  }
   m->cb = pt.add("quantizer.codevectors", {c.cv_groups, c.cv_per_group, D / c.cv_groups});
   m->qp_w = pt.add("quantizer.projection.kernel", {H, D});
   m->qp_b = pt.add("quantizer.projection.bias", {D});
@@ -193,13 +209,29 @@ static int plan(W2V* m, int B, int N, Bump& bp) {
     if (l + 1 < c.layers) m->LB[l + 1].h_in = h_out; else m->enc_out = h_out;
   }
   if (c.layers == 0) m->enc_out = m->hs;
-  m->ph_lin = bp.get(m->E((long long)M * Pj)); m->ps = bp.get(m->E((long long)M * Pj));
-  m->pq_lin = bp.get(m->E((long long)M * Pj)); m->pq = bp.get(m->E((long long)M * Pj));
-  m->ph_mean = (float*)bp.get(4 * M); m->ph_rstd = (float*)bp.get(4 * M);
-  m->pq_mean = (float*)bp.get(4 * M); m->pq_rstd = (float*)bp.get(4 * M);
-  m->S = (float*)bp.get(4ll * B * T * Tp);
-  m->dS = bp.get(m->E((long long)B * T * Tp));
-  m->logits = (float*)bp.get(4ll * M * (c.num_negatives + 1));
+  if (c.head == 0) {
+    m->ph_lin = bp.get(m->E((long long)M * Pj)); m->ps = bp.get(m->E((long long)M * Pj));
+    m->pq_lin = bp.get(m->E((long long)M * Pj)); m->pq = bp.get(m->E((long long)M * Pj));
+    m->ph_mean = (float*)bp.get(4 * M); m->ph_rstd = (float*)bp.get(4 * M);
+    m->pq_mean = (float*)bp.get(4 * M); m->pq_rstd = (float*)bp.get(4 * M);
+    m->S = (float*)bp.get(4ll * B * T * Tp);
+    m->dS = bp.get(m->E((long long)B * T * Tp));
+    m->logits = (float*)bp.get(4ll * M * (c.num_negatives + 1));
+  } else if (c.head == 1) {
+    m->head_rows = M; m->head_cols = c.vocab_size;
+    m->hd_in = bp.get(m->E((long long)M * H));
+    m->hlogits = (float*)bp.get(4ll * M * c.vocab_size);
+    m->d_hlogits = bp.get(m->E((long long)M * c.vocab_size));
+  } else {
+    const int Pc = c.classifier_proj;
+    m->head_rows = B; m->head_cols = c.num_labels;
+    m->pooled = bp.get(m->E((long long)B * H));
+    m->cp_pre = bp.get(m->E((long long)B * Pc)); m->cp_act = bp.get(m->E((long long)B * Pc)); m->cp_drop = bp.get(m->E((long long)B * Pc));
+    m->hlogits = (float*)bp.get(4ll * B * c.num_labels);
+    m->d_hlogits = bp.get(m->E((long long)B * c.num_labels));
+    m->d_cp = bp.get(m->E((long long)B * Pc));
+    m->d_pooled = bp.get(m->E((long long)B * H));
+  }
   // backward scratch
   m->g_a = bp.get(m->E((long long)M * std::max(H, C)));
   m->g_b = bp.get(m->E((long long)M * std::max(H, C)));
@@ -232,7 +264,7 @@ __global__ void w2v_finalize_scalars(float* s, float inv_rows, float div_w) {
 }
 
 static int w2v_forward(W2V* m, const float* wave, const int* neg, long long neg_bs, long long neg_ts, cudaStream_t st,
-                       bool features_only = false) {
+                       bool features_only = false, const int* labels = nullptr, bool with_loss = true) {
   Ctx* ctx = m->ctx;
   const ts_w2v_config& c = m->cfg;
   const int dt = m->prec, B = m->B, n = m->nconv, G = c.pos_groups;
@@ -278,8 +310,8 @@ static int w2v_forward(W2V* m, const float* wave, const int* neg, long long neg_
   TS_TRY(layernorm_fwd(ctx, dt, m->fp_out, nullptr, m->P + m->fp_ln_g, m->P + m->fp_ln_b, m->hs, nullptr, m->fp_mean,
                        m->fp_rstd, M, H, c.ln_eps, st));
   if (m->drop(c.hidden_dropout) > 0) TS_TRY(dropout_apply(ctx, dt, m->hs, m->hs, (long long)M * H, c.hidden_dropout, site_seed(seed, 2), st));
-  // ---- quantiser on the projected states (V:784-789, V:581-667) ----------------------------------------
-  {
+  // ---- quantiser on the projected states (V:784-789, V:581-667); the task heads run it in training mode only --------
+  if (c.head == 0 || with_loss) {
     const int Gq = c.cv_groups, V = c.cv_per_group, Dg = D / Gq;
     TS_TRY(GemmB(dt, dt).A(m->hs, 0, H).B(m->W(m->qp_w), 1, D).C(m->z, D).bias(m->P + m->qp_b).mnk(M, D, H).run(ctx, st));
     TS_TRY(fill_zero(ctx, m->hist, 4ll * Gq * V, st));
@@ -322,6 +354,35 @@ static int w2v_forward(W2V* m, const float* wave, const int* neg, long long neg_
     TS_TRY(GemmB(dt, dt).A(b.f, 0, F).B(m->W(o.fc2_w), 1, H).C(h_out, H).bias(m->P + o.fc2_b).res(b.h_mid, H)
                .drop(m->drop(c.hidden_dropout), site_seed(seed, 103 + l * 8)).mnk(M, H, F).run(ctx, st));
   }
+  if (c.head == 1) {
+    // ---- Wav2Vec2ForCTC (V:971-1000): dropout -> lm_head -> mean CE against class 0 on every frame ---------------
+    const int V = c.vocab_size;
+    const void* hin = m->enc_out;
+    if (m->drop(c.hidden_dropout) > 0) { TS_TRY(dropout_apply(ctx, dt, m->enc_out, m->hd_in, (long long)M * H, c.hidden_dropout, site_seed(seed, 5), st)); hin = m->hd_in; }
+    TS_TRY(GemmB(dt, TS_F32).A(hin, 0, H).B(m->W(m->lm_w), 1, V).C(m->hlogits, V).bias(m->P + m->lm_b).mnk(M, V, H).simt().run(ctx, st));
+    if (with_loss) {
+      TS_TRY(ce_rows_fwd_bwd(ctx, dt, m->hlogits, V, nullptr, m->d_hlogits, V, m->scalars + 3, M, V, 1.f / (m->loss_div * (float)M), st));
+      w2v_finalize_scalars<<<1, 1, 0, st>>>(m->scalars, 1.f / (float)M, 0.f);
+      TS_LAUNCH_OK(ctx);
+    }
+    m->fwd_done = with_loss;
+    return 0;
+  }
+  if (c.head == 2) {
+    // ---- Wav2Vec2ForSequenceClassification (V:1033-1056): mean over time -> Dense+tanh -> dropout -> Dense -> CE -----
+    const int Pc = c.classifier_proj, NL = c.num_labels;
+    TS_TRY(mean_pool_fwd(ctx, dt, m->enc_out, m->pooled, B, T, H, st));
+    TS_TRY(GemmB(dt, dt).A(m->pooled, 0, H).B(m->W(m->cp_w), 1, Pc).C(m->cp_pre, Pc).bias(m->P + m->cp_b).mnk(B, Pc, H).simt().run(ctx, st));
+    TS_TRY(tanh_drop_fwd(ctx, dt, m->cp_pre, m->cp_act, m->cp_drop, (long long)B * Pc, m->drop(c.hidden_dropout), site_seed(seed, 6), st));
+    TS_TRY(GemmB(dt, TS_F32).A(m->cp_drop, 0, Pc).B(m->W(m->cl_w), 1, NL).C(m->hlogits, NL).bias(m->P + m->cl_b).mnk(B, NL, Pc).simt().run(ctx, st));
+    if (with_loss) {
+      TS_TRY(ce_rows_fwd_bwd(ctx, dt, m->hlogits, NL, labels, m->d_hlogits, NL, m->scalars + 3, B, NL, 1.f / (m->loss_div * (float)B), st));
+      w2v_finalize_scalars<<<1, 1, 0, st>>>(m->scalars, 1.f / (float)B, 0.f);
+      TS_LAUNCH_OK(ctx);
+    }
+    m->fwd_done = with_loss;
+    return 0;
+  }
   // ---- projection heads (V:854-857) ------------------------------------------------------------------------
   TS_TRY(GemmB(dt, dt).A(m->enc_out, 0, H).B(m->W(m->ph_w), 1, Pj).C(m->ph_lin, Pj).bias(m->P + m->ph_b).mnk(M, Pj, H).run(ctx, st));
   TS_TRY(layernorm_fwd(ctx, dt, m->ph_lin, nullptr, m->P + m->ph_ln_g, m->P + m->ph_ln_b, m->ps, nullptr, m->ph_mean, m->ph_rstd, M, Pj, c.ln_eps, st));
@@ -345,16 +406,20 @@ static int w2v_forward(W2V* m, const float* wave, const int* neg, long long neg_
 // dense layer backward: dW += X^T dY (fp32; the gradient arena is zeroed at the start of backward, so split-K partials may be added), db += colsum(dY), dX = dY W^T (optional, + residual)
 static int dense_bwd(W2V* m, const void* X, int K, const void* dY, int Nn, long long w_off, long long ldw, long long b_off,
                      void* dX, const void* dres, int rows, cudaStream_t st, const void* gelu_u = nullptr, float drop = 0.f,
-                     uint64_t drop_seed = 0) {
+                     uint64_t drop_seed = 0, bool simt = false) {
   Ctx* ctx = m->ctx;
   const int dt = m->prec;
-  TS_TRY(GemmB(dt, TS_F32).A(X, 1, K).B(dY, 1, Nn).C(m->G + w_off, ldw).mnk(K, Nn, rows).acc().run(ctx, st));
+  GemmB gw(dt, TS_F32);
+  gw.A(X, 1, K).B(dY, 1, Nn).C(m->G + w_off, ldw).mnk(K, Nn, rows).acc();
+  if (simt) gw.simt();
+  TS_TRY(gw.run(ctx, st));
   if (b_off >= 0) TS_TRY(colsum_acc(ctx, dt, dY, Nn, rows, Nn, m->G + b_off, st));
   if (dX) {
     GemmB g(dt, dt);
     g.A(dY, 0, Nn).B(m->W(w_off), 0, ldw).C(dX, K).mnk(rows, K, Nn);
     if (dres) g.res(dres, K);
     if (gelu_u) g.gelu_grad(gelu_u, K).drop(drop, drop_seed);   // dX feeds a GELU (+dropout): its backward runs in the epilogue
+    if (simt) g.simt();
     TS_TRY(g.run(ctx, st));
   }
   return 0;
@@ -368,6 +433,22 @@ static int w2v_backward_stage(W2V* m, int stage, cudaStream_t st) {
   const int C = c.conv_dim[n - 1], D = c.cv_dim, Pj = c.proj_dim;
   const uint64_t seed = m->seed;
   const float hdrop = m->drop(c.hidden_dropout);
+  if (stage == 0 && c.head == 1) {
+    // ---- CTC head: lm_head backward, then back through the dropout on the encoder output (V:975-979) -----------
+    const void* hin = hdrop > 0 ? m->hd_in : m->enc_out;
+    TS_TRY(dense_bwd(m, hin, H, m->d_hlogits, c.vocab_size, m->lm_w, c.vocab_size, m->lm_b, m->g_a, nullptr, M, st, nullptr, 0.f, 0, true));
+    if (hdrop > 0) TS_TRY(dropout_apply(ctx, dt, m->g_a, m->g_a, (long long)M * H, hdrop, site_seed(seed, 5), st));
+    return 0;
+  }
+  if (stage == 0 && c.head == 2) {
+    // ---- classification head: classifier -> dropout/tanh -> classifier_proj -> mean pooling (V:1043-1048) ------
+    const int Pc = c.classifier_proj, NL = c.num_labels;
+    TS_TRY(dense_bwd(m, m->cp_drop, Pc, m->d_hlogits, NL, m->cl_w, NL, m->cl_b, m->d_cp, nullptr, B, st, nullptr, 0.f, 0, true));
+    TS_TRY(tanh_drop_bwd(ctx, dt, m->d_cp, m->cp_act, m->d_cp, (long long)B * Pc, hdrop, site_seed(seed, 6), st));
+    TS_TRY(dense_bwd(m, m->pooled, H, m->d_cp, Pc, m->cp_w, Pc, m->cp_b, m->d_pooled, nullptr, B, st, nullptr, 0.f, 0, true));
+    TS_TRY(mean_pool_bwd(ctx, dt, m->d_pooled, m->g_a, B, T, H, st));   // g_a = d(enc_out)
+    return 0;
+  }
   if (stage == 0) {
     // ---- heads: contrastive -> projection heads -> codebook --------------------------------------------
     void* dps = m->g_small1;
@@ -512,6 +593,10 @@ int ts_w2v_create(ts_ctx* ctx_, const ts_w2v_config* cfg, int precision, ts_w2v*
   if (!ctx || !cfg || !out) return TS_EINVAL;
   TS_REQUIRE(ctx, precision == TS_F32 || precision == TS_BF16, TS_EDTYPE, "w2v: precision must be TS_F32 or TS_BF16");
   TS_REQUIRE(ctx, cfg->n_conv >= 2 && cfg->n_conv <= 8 && cfg->layers <= 64, TS_EINVAL, "w2v: bad config");
+  TS_REQUIRE(ctx, cfg->head >= 0 && cfg->head <= 2, TS_EINVAL, "w2v: head must be 0 (pre-training), 1 (CTC) or 2 (classification)");
+  TS_REQUIRE(ctx, cfg->head != 1 || cfg->vocab_size > 0, TS_EINVAL, "w2v: CTC head needs vocab_size > 0");
+  TS_REQUIRE(ctx, cfg->head != 2 || (cfg->classifier_proj > 0 && cfg->num_labels > 0), TS_EINVAL,
+             "w2v: classification head needs classifier_proj > 0 and num_labels > 0");
   W2V* m = new W2V();
   m->ctx = ctx; m->cfg = *cfg; m->prec = precision; m->esz = precision == TS_BF16 ? 2 : 4;
   m->fused_attn = precision == TS_BF16 && cfg->heads > 0 && cfg->hidden / cfg->heads == 64 && !getenv("TETHYS_UNFUSED_ATTENTION");
@@ -567,6 +652,7 @@ int ts_w2v_forward(ts_w2v* h, const float* wave, int B, int N, const int* neg, i
   cudaStream_t st = (cudaStream_t)stream;
   TS_REQUIRE(ctx, m->P && m->ws, TS_EINVAL, "w2v_forward: call ts_w2v_bind first");
   TS_REQUIRE(ctx, B > 0 && N > 0 && wave && neg, TS_EINVAL, "w2v_forward: bad arguments");
+  TS_REQUIRE(ctx, m->cfg.head == 0, TS_EINVAL, "w2v_forward: this program has a task head (use ts_w2v_forward_head)");
   if (!m->planned || m->B != B || m->N != N) {
     Bump bp;
     bp.base = m->ws;
@@ -580,6 +666,28 @@ int ts_w2v_forward(ts_w2v* h, const float* wave, int B, int N, const int* neg, i
   TS_TRY(posconv_flip_weight(ctx, m->prec, m->W(m->pos_w), m->wt_flip, m->cfg.pos_kernel, m->cfg.conv_dim[m->cfg.n_conv - 1],
                              m->cfg.pos_groups, st));
   return w2v_forward(m, wave, neg, neg_bs, neg_ts, st);
+}
+int ts_w2v_forward_head(ts_w2v* h, const float* wave, int B, int N, const int* labels, float loss_div, uint64_t seed, int dropout,
+                        int training, void* stream) {
+  W2V* m = reinterpret_cast<W2V*>(h);
+  Ctx* ctx = m->ctx;
+  cudaStream_t st = (cudaStream_t)stream;
+  TS_REQUIRE(ctx, m->P && m->ws, TS_EINVAL, "w2v_forward_head: call ts_w2v_bind first");
+  TS_REQUIRE(ctx, B > 0 && N > 0 && wave, TS_EINVAL, "w2v_forward_head: bad arguments");
+  TS_REQUIRE(ctx, m->cfg.head == 1 || m->cfg.head == 2, TS_EINVAL, "w2v_forward_head: this is the pre-training program (use ts_w2v_forward)");
+  if (!m->planned || m->B != B || m->N != N) {
+    Bump bp;
+    bp.base = m->ws;
+    TS_TRY(plan(m, B, N, bp));
+    TS_REQUIRE(ctx, (long long)bp.off <= m->ws_bytes, TS_EINVAL, "w2v_forward_head: workspace too small (%lld < %lld bytes)",
+               (long long)m->ws_bytes, (long long)bp.off);
+    m->planned = true;
+  }
+  m->seed = seed; m->training = (dropout && training) ? 1 : 0; m->loss_div = loss_div > 0.f ? loss_div : 1.f; m->fwd_done = false;
+  if (training)
+    TS_TRY(posconv_flip_weight(ctx, m->prec, m->W(m->pos_w), m->wt_flip, m->cfg.pos_kernel, m->cfg.conv_dim[m->cfg.n_conv - 1],
+                               m->cfg.pos_groups, st));
+  return w2v_forward(m, wave, nullptr, 0, 0, st, false, labels, training != 0);
 }
 int ts_w2v_forward_features(ts_w2v* h, const float* wave, int B, int N, void* stream) {
   W2V* m = reinterpret_cast<W2V*>(h);
@@ -621,6 +729,11 @@ int ts_w2v_get_buffer(ts_w2v* h, const char* name, void** ptr, int32_t* dtype, i
   if (s == "quantized_features") return set(m->qfeat, m->prec, 3, B, T, c.cv_dim, 1);
   if (s == "quantizer_input") return set(m->z, m->prec, 3, B, T, c.cv_dim, 1);
   if (s == "code_indices") return set(m->code_idx, TS_I64, 3, c.cv_groups, B, T, 1);
+  if (s == "head_logits" && c.head == 1) return set(m->hlogits, TS_F32, 3, B, T, c.vocab_size, 1);
+  if (s == "head_logits" && c.head == 2) return set(m->hlogits, TS_F32, 2, B, c.num_labels, 1, 1);
+  if (s == "pooled_output" && c.head == 2) return set(m->pooled, m->prec, 2, B, c.hidden, 1, 1);
+  if (c.head != 0 && (s == "projected_states" || s == "projected_quantized_features" || s == "contrastive_logits"))
+    return set_err(m->ctx, TS_EINVAL, "w2v_get_buffer: '%s' exists in the pre-training program only", name);
   if (s == "projected_states") return set(m->ps, m->prec, 3, B, T, c.proj_dim, 1);
   if (s == "projected_quantized_features") return set(m->pq, m->prec, 3, B, T, c.proj_dim, 1);
   if (s == "contrastive_logits") return set(m->logits, TS_F32, 3, B, T, c.num_negatives + 1, 1);

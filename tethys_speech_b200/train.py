@@ -8,6 +8,7 @@ import time
 
 import torch
 
+from . import checkpoint
 from . import wav2vec2 as W2V
 from . import whisper as WH
 from .runtime import Adam, Strategy
@@ -28,13 +29,29 @@ def _log_step(step, loss_value, start_time, step_duration):
     print(f"Step {step}, Loss: {loss_value:.4f}, Time: {time.strftime('%H:%M:%S')} (경과: {elapsed:.2f}초, 스텝 시간: {step_duration:.2f}초)", flush=True)
 
 
-def _save_checkpoint(model, name):
+def _save_checkpoint(model, name, optimizer=None):
+    """checkpoint.save(os.path.join(checkpoint_dir, name)) — V:1341, V:1362, W:956: model + optimizer slots."""
     try:
         d = os.path.join(WORKSPACE, "checkpoints")
         os.makedirs(d, exist_ok=True)
-        model.save_weights(os.path.join(d, name + ".pt"))
+        return checkpoint.save(os.path.join(d, name + ".tsckpt"), model, optimizer)
     except Exception as e:  # the reference's checkpoint dir is container-specific
         print(f"checkpoint not written: {e}")
+        return None
+
+
+def _maybe_resume(resume_from, model, optimizer):
+    """Restore model + optimizer from a checkpoint file (or the newest one of a directory); returns the step to continue at.
+    Every rank reads the same file, so the replicas stay identical without a second broadcast."""
+    if not resume_from:
+        return 0
+    path = checkpoint.latest_checkpoint(resume_from) if os.path.isdir(resume_from) else resume_from
+    if path is None:
+        print(f"no checkpoint under {resume_from}; starting from scratch")
+        return 0
+    meta = checkpoint.restore(path, model, optimizer)
+    print(f"restored {path} (iterations = {optimizer.iterations})")
+    return int(meta.get("optimizer", {}).get("iterations", 0))
 
 
 def write_jct(jct, task_type, task_index):
@@ -51,17 +68,18 @@ def write_jct(jct, task_type, task_index):
 
 
 def train_whisper(strategy, model_type="small", num_epochs=1, learning_rate=1e-4, batch_size=1, num_batches=40,
-                  precision="bf16", seq_len=3000, from_waveform=False):
+                  precision="bf16", seq_len=3000, from_waveform=False, resume_from=None):
     """W:894-958. from_waveform=True (extension, SURVEY f-1): the dataset yields raw 30 s waveforms and the fused log-mel kernel
-    (extract_fbank_features, W:739-766) produces the model input inside the loop."""
+    (extract_fbank_features, W:739-766) produces the model input inside the loop. resume_from (extension, SURVEY f-3): a
+    checkpoint file, or a directory whose newest checkpoint is taken, restored into model + optimizer before the loop."""
     with strategy.scope():
         model = WH.create_whisper_model(model_type=model_type, precision=precision, device=strategy.local_rank)
         model.broadcast_weights(strategy)
         optimizer = Adam(learning_rate=learning_rate)
+    step = _maybe_resume(resume_from, model, optimizer)
     global_batch = batch_size * strategy.num_replicas_in_sync
     dataset = (WH.create_dummy_waveform_dataset(global_batch, audio_seconds=seq_len / 100.0) if from_waveform
                else WH.create_dummy_dataset(global_batch, seq_len=seq_len))
-    step = 0
     start_time = time.time()
     for epoch in range(num_epochs):
         print(f"Epoch {epoch + 1}/{num_epochs}")
@@ -79,18 +97,19 @@ def train_whisper(strategy, model_type="small", num_epochs=1, learning_rate=1e-4
             _log_step(step, loss_value, start_time, time.time() - step_start)
             step += 1
         if strategy.rank == 0:
-            _save_checkpoint(model, f"whisper_{model_type}_epoch_{epoch + 1}")
+            _save_checkpoint(model, f"whisper_{model_type}_epoch_{epoch + 1}", optimizer)
     return model
 
 
 def train_wav2vec2(strategy, model_type="pretraining", model_size="small", num_epochs=1, learning_rate=3e-5, batch_size=1,
-                   num_batches=5, precision="bf16", audio_length=32000, legacy=False):
+                   num_batches=5, precision="bf16", audio_length=32000, legacy=False, resume_from=None):
     """V:1263-1376 (legacy=True: the whisper_single.py / stable_jobs variant — WS:1183-1258: 5 s audio, unscaled loss,
     no clipping, Adam eps 1e-7, seed-42 shuffle sampler)."""
     with strategy.scope():
         model = W2V.create_full_model(model_type=model_type, model_size=model_size, precision=precision, device=strategy.local_rank)
         model.broadcast_weights(strategy)
         optimizer = Adam(learning_rate=learning_rate, epsilon=1e-7) if legacy else Adam(learning_rate=learning_rate, epsilon=1e-8, clipnorm=1.0)
+    step = _maybe_resume(resume_from, model, optimizer)
     global_batch = batch_size * strategy.num_replicas_in_sync
     dataset = W2V.create_dummy_dataset(global_batch, audio_length=audio_length)
     neg_legacy = None
@@ -100,7 +119,6 @@ def train_wav2vec2(strategy, model_type="pretraining", model_size="small", num_e
         t = torch.arange(T).unsqueeze(1)
         k = torch.arange(model.num_negatives).unsqueeze(0)
         neg_legacy = perm[(k - (t + 1)) % T].to(torch.int32).unsqueeze(0).expand(batch_size, -1, -1).contiguous()   # WS:799-839
-    step = 0
     start_time = time.time()
     for epoch in range(num_epochs):
         print(f"Epoch {epoch + 1}/{num_epochs}")
@@ -108,13 +126,13 @@ def train_wav2vec2(strategy, model_type="pretraining", model_size="small", num_e
             try:
                 feats, labels = next(dataset)
                 lo = strategy.rank * batch_size
-                feats = feats[lo:lo + batch_size]
+                feats, labels = feats[lo:lo + batch_size], labels[lo:lo + batch_size]
                 step_start = time.time()
                 if legacy:
                     loss = W2V.legacy_train_step(model, (feats, None), optimizer, neg_indices=neg_legacy)
                     loss = strategy.reduce("SUM", loss)
                 else:
-                    loss = W2V.distributed_train_step(strategy, model, (feats, None), optimizer)
+                    loss = W2V.distributed_train_step(strategy, model, (feats, labels), optimizer)
                 try:
                     loss_value = float(loss)
                 except Exception:
@@ -122,14 +140,14 @@ def train_wav2vec2(strategy, model_type="pretraining", model_size="small", num_e
                 _log_step(step, loss_value, start_time, time.time() - step_start)
                 step += 1
                 if step % 50 == 0 and strategy.rank == 0:
-                    _save_checkpoint(model, f"model_step_{step}")
+                    _save_checkpoint(model, f"model_step_{step}", optimizer)
             except StopIteration:
                 break
             except Exception as e:                               # V:1367-1371 swallows per-step errors
                 print(f"Error at step {step}: {e}")
                 raise
         if strategy.rank == 0:
-            _save_checkpoint(model, f"model_epoch_{epoch + 1}")
+            _save_checkpoint(model, f"model_epoch_{epoch + 1}", optimizer)
     return model
 
 

@@ -71,10 +71,16 @@ class Wav2Vec2Config:
         self.vocab_size = 32
         self.do_stable_layer_norm = True
         self.use_weighted_layer_sum = False
+        self.ctc_loss_reduction = "sum"   # read into Wav2Vec2ForCTC but unused by its stand-in loss (V:954-955, V:994-1000)
+        self.ctc_zero_infinity = False
+        self.num_labels = 10              # VS:131 (wav2vec2_dist.py's config lacks it: its classification model cannot be built)
 
 
 # Keras trainable_variables order of Wav2Vec2ForPreTraining (attribute-tracking order, V:746-766, V:229-281)
-def _keras_order(cfg):
+def _keras_order(cfg, head="pretraining"):
+    """head: 'pretraining' | 'ctc' | 'classification'. The task heads wrap the same Wav2Vec2Model; its project_hid / project_q
+    layers are never called there, so Keras never creates their variables; the quantizer is called (training=True) and its
+    variables exist with None -> zero gradients (VS:1163-1166). The head's own layers come last (V:950, V:1013-1015)."""
     names = []
     for i in range(len(cfg.conv_dim)):
         names += [f"fe.conv{i}.kernel", f"fe.conv{i}.gn.gamma", f"fe.conv{i}.gn.beta"]
@@ -89,17 +95,27 @@ def _keras_order(cfg):
                   p + "feed_forward.intermediate_dense.kernel", p + "feed_forward.intermediate_dense.bias",
                   p + "feed_forward.output_dense.kernel", p + "feed_forward.output_dense.bias",
                   p + "feed_forward_layer_norm.gamma", p + "feed_forward_layer_norm.beta"]
-    names += ["quantizer.codevectors", "quantizer.projection.kernel", "quantizer.projection.bias",
-              "project_hid.dense.kernel", "project_hid.dense.bias", "project_hid.layer_norm.gamma", "project_hid.layer_norm.beta",
-              "project_q.dense.kernel", "project_q.dense.bias", "project_q.layer_norm.gamma", "project_q.layer_norm.beta"]
+    names += ["quantizer.codevectors", "quantizer.projection.kernel", "quantizer.projection.bias"]
+    if head == "pretraining":
+        names += ["project_hid.dense.kernel", "project_hid.dense.bias", "project_hid.layer_norm.gamma", "project_hid.layer_norm.beta",
+                  "project_q.dense.kernel", "project_q.dense.bias", "project_q.layer_norm.gamma", "project_q.layer_norm.beta"]
+    elif head == "ctc":
+        names += ["lm_head.kernel", "lm_head.bias"]
+    else:
+        names += ["classifier_proj.kernel", "classifier_proj.bias", "classifier.kernel", "classifier.bias"]
     return names
+
+
+_HEADS = {"pretraining": 0, "ctc": 1, "classification": 2}
 
 
 class _Program(ProgramBase):
     """Arenas + the ts_w2v handle."""
 
-    def __init__(self, cfg, precision, device):
+    def __init__(self, cfg, precision, device, head="pretraining"):
         c = _lib.W2VConfig()
+        c.head = _HEADS[head]
+        c.vocab_size, c.classifier_proj, c.num_labels = cfg.vocab_size, cfg.classifier_proj_size, cfg.num_labels
         c.hidden, c.layers, c.heads, c.ffn = cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads, cfg.intermediate_size
         c.n_conv = len(cfg.conv_dim)
         for i in range(c.n_conv):
@@ -134,25 +150,23 @@ class Wav2Vec2Model:
         return self._owner._cached("projected_quantized_features", hidden_states)
 
 
-class Wav2Vec2ForPreTraining:
-    """Mirror of `Wav2Vec2ForPreTraining` — V:828-937. `model(inputs, training=True)` returns the same dict keys;
-    `_compute_contrastive_loss` / `_compute_diversity_loss` / `_sample_negative_indices` keep their signatures."""
+class _Wav2Vec2Task:
+    """What the three task models share: the native program + arenas, Keras-ordered variables, weight I/O, gradients."""
+
+    _head = "pretraining"
 
     def __init__(self, config, precision="bf16", device=None, seed=0):
         self.config = config
         if device is None:
             device = torch.cuda.current_device() if torch.cuda.is_available() else 0
-        self._prog = _Program(config, precision, device)
+        self._prog = _Program(config, precision, device, self._head)
         self.wav2vec2 = Wav2Vec2Model(self)
-        self.num_negatives = config.num_negatives
-        self.contrastive_logits_temperature = config.contrastive_logits_temperature
-        self.diversity_loss_weight = config.diversity_loss_weight
         self._rng = torch.Generator(device=self._prog.device)
         self._rng.manual_seed(1234 + seed)
         self._step_seed = seed * 1000003
         self._last = {}
         self._init_weights(seed)
-        names = _keras_order(config)
+        names = _keras_order(config, self._head)
         assert set(names) == set(self._prog.info), "parameter table mismatch"
         self.variable_names = names
         self.trainable_variables = [self._prog.view(self._prog.params, n) for n in names]
@@ -194,18 +208,7 @@ class Wav2Vec2ForPreTraining:
         strategy.broadcast_(self._prog.params)
         self._prog.weights_synced = False
 
-    # -- forward ------------------------------------------------------------------------------------------
-    def _sample_negative_indices(self, sequence_length, batch_size):
-        """V:907-937: per batch row, the positions of the `actual` smallest of T uniform ints (ties: lower index
-        first), tiled to num_negatives, then the same list for every time step. Returns int32 [B, T, K]."""
-        T, K = int(sequence_length), self.num_negatives
-        actual = max(min(K, T - 1), 1)
-        r = torch.randint(0, T, (int(batch_size), T), generator=self._rng, device=self._prog.device)
-        order = torch.sort(-r.float(), dim=1, descending=True, stable=True).indices[:, :actual]
-        if actual < K:
-            order = order.repeat(1, math.ceil(K / actual))[:, :K]
-        return order.to(torch.int32).unsqueeze(1).expand(-1, T, -1)
-
+    # -- shared ---------------------------------------------------------------------------------------------
     def num_frames(self, n_samples):
         t = int(n_samples)
         for s in self.config.conv_stride:
@@ -223,6 +226,52 @@ class Wav2Vec2ForPreTraining:
         p.ctx.check(p.lib.ts_w2v_forward_features(p.h, ptr(x), B, N, stream_ptr()))
         self._last = {"x": x}
         return p.buffer("extract_features")
+
+    def gradient(self, stage_from=0, stage_to=10 ** 6):
+        """tape.gradient(loss, model.trainable_variables) (V:1234) with None→zeros (V:1237-1240): fills the
+        gradient arena and returns views in `trainable_variables` order."""
+        p = self._prog
+        p.backward(stage_from, stage_to)
+        gl = GradientList(p.view(p.grads, n) for n in self.variable_names)
+        gl.owner = self
+        for g in gl:
+            g._ts_owner = self
+        return gl
+
+    def save_weights(self, path):
+        """Keras `model.save_weights` (W:1025): variables only, in the checkpoint.py container."""
+        from . import checkpoint
+        return checkpoint.save(path, self)
+
+    def load_weights(self, path, strict=True):
+        """The restore the reference never calls (SURVEY f-3): variables from a file written by save_weights / Checkpoint."""
+        from . import checkpoint
+        return checkpoint.restore(path, self, strict=strict)
+
+
+class Wav2Vec2ForPreTraining(_Wav2Vec2Task):
+    """Mirror of `Wav2Vec2ForPreTraining` — V:828-937. `model(inputs, training=True)` returns the same dict keys;
+    `_compute_contrastive_loss` / `_compute_diversity_loss` / `_sample_negative_indices` keep their signatures."""
+
+    _head = "pretraining"
+
+    def __init__(self, config, precision="bf16", device=None, seed=0):
+        super().__init__(config, precision, device, seed)
+        self.num_negatives = config.num_negatives
+        self.contrastive_logits_temperature = config.contrastive_logits_temperature
+        self.diversity_loss_weight = config.diversity_loss_weight
+
+    # -- forward ------------------------------------------------------------------------------------------
+    def _sample_negative_indices(self, sequence_length, batch_size):
+        """V:907-937: per batch row, the positions of the `actual` smallest of T uniform ints (ties: lower index
+        first), tiled to num_negatives, then the same list for every time step. Returns int32 [B, T, K]."""
+        T, K = int(sequence_length), self.num_negatives
+        actual = max(min(K, T - 1), 1)
+        r = torch.randint(0, T, (int(batch_size), T), generator=self._rng, device=self._prog.device)
+        order = torch.sort(-r.float(), dim=1, descending=True, stable=True).indices[:, :actual]
+        if actual < K:
+            order = order.repeat(1, math.ceil(K / actual))[:, :K]
+        return order.to(torch.int32).unsqueeze(1).expand(-1, T, -1)
 
     def __call__(self, inputs, attention_mask=None, output_attentions=False, output_hidden_states=False, training=False,
                  neg_indices=None, loss_div=1.0, dropout=True):
@@ -283,32 +332,73 @@ class Wav2Vec2ForPreTraining:
         """V:901-905."""
         return -perplexity
 
-    # -- backward -----------------------------------------------------------------------------------------
-    def gradient(self, stage_from=0, stage_to=10 ** 6):
-        """tape.gradient(loss, model.trainable_variables) (V:1234) with None→zeros (V:1237-1240): fills the
-        gradient arena and returns views in `trainable_variables` order."""
-        p = self._prog
-        p.backward(stage_from, stage_to)
-        gl = GradientList(p.view(p.grads, n) for n in self.variable_names)
-        gl.owner = self
-        for g in gl:
-            g._ts_owner = self
-        return gl
 
-    def save_weights(self, path):
-        torch.save({k: v.cpu() for k, v in self.get_weights().items()}, path)
+class _Wav2Vec2HeadModel(_Wav2Vec2Task):
+    """Shared call path of the two fine-tuning heads (ts_w2v_forward_head)."""
+
+    def __call__(self, inputs, attention_mask=None, labels=None, output_attentions=False, output_hidden_states=False,
+                 return_dict=True, training=False, loss_div=1.0, dropout=True):
+        if attention_mask is not None or output_attentions or output_hidden_states or not return_dict:
+            raise NotImplementedError("attention_mask / output_attentions / output_hidden_states / tuple outputs are not on the train path")
+        p = self._prog
+        x = to_device(inputs, torch.float32, p.device)
+        if x.dim() != 2:
+            raise ValueError("inputs must be [batch, samples]")
+        B, N = x.shape
+        p.ensure_workspace(B, N)
+        p.sync_weights()
+        with_loss = bool(training and labels is not None)          # V:982-985 / V:1052-1056: loss only when training with labels
+        lab = None
+        if with_loss and self._head == "classification":
+            lab = to_device(labels, torch.int32, p.device).reshape(-1)
+            if lab.numel() != B:
+                raise ValueError(f"labels must hold one class id per clip ({B}), got {tuple(lab.shape)}")
+        self._step_seed += 1
+        p.ctx.check(p.lib.ts_w2v_forward_head(p.h, ptr(x), B, N, ptr(lab), float(loss_div), self._step_seed,
+                                              1 if (training and dropout) else 0, 1 if with_loss else 0, stream_ptr()))
+        self._last = {"x": x, "labels": lab, "training": training}
+        out = {"loss": p.buffer("scalars")[0] if with_loss else None, "logits": p.buffer("head_logits"),
+               "hidden_states": None, "attentions": None}
+        self._last["out"] = out
+        return out
+
+    call = __call__
+
+
+class Wav2Vec2ForCTC(_Wav2Vec2HeadModel):
+    """Mirror of `Wav2Vec2ForCTC` — V:940-1001: dropout + lm_head(vocab_size) on the trunk. Its `_compute_ctc_loss` is the
+    reference's stand-in, the mean sparse cross-entropy of every frame against class 0 (V:994-1000), not tf.nn.ctc_loss."""
+
+    _head = "ctc"
+
+    def __init__(self, config, precision="bf16", device=None, seed=0):
+        super().__init__(config, precision, device, seed)
+        self.ctc_loss_reduction = config.ctc_loss_reduction
+        self.ctc_zero_infinity = config.ctc_zero_infinity
+
+
+class Wav2Vec2ForSequenceClassification(_Wav2Vec2HeadModel):
+    """Mirror of `Wav2Vec2ForSequenceClassification` — V:1004-1070: mean over time, Dense(classifier_proj_size, tanh),
+    dropout, Dense(num_labels), mean sparse cross-entropy with the integer labels."""
+
+    _head = "classification"
 
 
 def create_full_model(model_type="pretraining", model_size="small", num_negatives=100, mask_time_prob=0.065,
                       mask_time_length=10, precision="bf16", device=None, seed=0):
-    """V:1157-1182. Only model_type='pretraining' is on the hot path (SURVEY §8 f-2 lists the other heads as next)."""
+    """V:1157-1182 / VS:1094-1115: 'pretraining' -> Wav2Vec2ForPreTraining, 'asr' -> Wav2Vec2ForCTC, 'classification' ->
+    Wav2Vec2ForSequenceClassification. (The reference's fall-through, a bare Wav2Vec2Model, has no loss and cannot be trained.)"""
     config = Wav2Vec2Config(model_size=model_size)
     config.num_negatives = num_negatives
     config.mask_time_prob = mask_time_prob
     config.mask_time_length = mask_time_length
-    if model_type != "pretraining":
-        raise NotImplementedError(f"model_type={model_type!r}: only the pre-training step is implemented")
-    return Wav2Vec2ForPreTraining(config, precision=precision, device=device, seed=seed)
+    if model_type == "pretraining":
+        return Wav2Vec2ForPreTraining(config, precision=precision, device=device, seed=seed)
+    if model_type == "asr":
+        return Wav2Vec2ForCTC(config, precision=precision, device=device, seed=seed)
+    if model_type == "classification":
+        return Wav2Vec2ForSequenceClassification(config, precision=precision, device=device, seed=seed)
+    raise NotImplementedError(f"model_type={model_type!r}: a bare Wav2Vec2Model has no loss to train on")
 
 
 def create_dummy_dataset(batch_size, audio_length=32000, num_samples=50, seed=1234, device=None):
@@ -332,14 +422,18 @@ def create_dummy_dataset(batch_size, audio_length=32000, num_samples=50, seed=12
 
 
 def train_step(model, inputs, optimizer, neg_indices=None, dropout=True):
-    """Single-device step — VS:1119-1176: forward, contrastive + diversity loss, NaN guard, gradients (None→0),
-    clip_by_global_norm(1.0), optimizer.apply_gradients (clipnorm + Adam). Returns the loss (device scalar)."""
+    """Single-device step — VS:1119-1176: forward, loss (pre-training: contrastive + diversity; task heads: the model's own
+    "loss" for (features, labels), VS:1155-1157), NaN guard, gradients (None→0), clip_by_global_norm(1.0),
+    optimizer.apply_gradients (clipnorm + Adam). Returns the loss (device scalar)."""
     features, labels = inputs
     if features.shape[0] == 0:
         return torch.zeros(())
-    outputs = model(features, training=True, neg_indices=neg_indices, dropout=dropout)
-    logits, contrastive_loss = model._compute_contrastive_loss(outputs["projected_states"], outputs["projected_quantized_features"])
-    loss = outputs["loss"]  # = contrastive + diversity_loss_weight * (-perplexity), NaN→0 (V:1220-1228), fused on device
+    if isinstance(model, Wav2Vec2ForPreTraining):
+        outputs = model(features, training=True, neg_indices=neg_indices, dropout=dropout)
+        logits, contrastive_loss = model._compute_contrastive_loss(outputs["projected_states"], outputs["projected_quantized_features"])
+    else:
+        outputs = model(features, labels=labels, training=True, dropout=dropout)
+    loss = outputs["loss"]  # NaN→0 (V:1220-1228 / VS:1160) fused on the device
     gradients = model.gradient()
     optimizer.apply_gradients(gradients, global_clip_norm=1.0)
     return loss
@@ -364,7 +458,10 @@ def distributed_train_step(strategy, model, dist_inputs, optimizer, neg_indices=
         if features.shape[0] == 0:
             return torch.zeros((), device=model._prog.device)
         n = float(strategy.num_replicas_in_sync)
-        outputs = model(features, training=True, neg_indices=neg_indices, loss_div=n, dropout=dropout)
+        if isinstance(model, Wav2Vec2ForPreTraining):
+            outputs = model(features, training=True, neg_indices=neg_indices, loss_div=n, dropout=dropout)
+        else:   # V:1222-1224: outputs = model(features, labels=labels, training=True); loss = outputs["loss"]
+            outputs = model(features, labels=labels, training=True, loss_div=n, dropout=dropout)
         scaled_loss = outputs["loss"] / n
         gradients = model.gradient()
         optimizer.apply_gradients(gradients, strategy=strategy, global_clip_norm=1.0)

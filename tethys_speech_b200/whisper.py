@@ -196,7 +196,14 @@ class WhisperForConditionalGeneration:
         return gl
 
     def save_weights(self, path):
-        torch.save({k: v.cpu() for k, v in self.get_weights().items()}, path)
+        """Keras `model.save_weights` (W:1025): variables only, in the checkpoint.py container."""
+        from . import checkpoint
+        return checkpoint.save(path, self)
+
+    def load_weights(self, path, strict=True):
+        """The restore the reference never calls (SURVEY f-3): variables from a file written by save_weights / Checkpoint."""
+        from . import checkpoint
+        return checkpoint.restore(path, self, strict=strict)
 
 
 def create_whisper_model(model_type="small", precision="bf16", device=None, seed=0):
