@@ -280,6 +280,15 @@ int ts_whisper_bind(ts_whisper* m, float* params, float* grads, void* params_bf1
 int ts_whisper_sync_compute_weights(ts_whisper* m, void* stream);
 int ts_whisper_forward(ts_whisper* m, const float* features, int batch, int t_mel, const int32_t* labels, int seq, uint64_t seed,
                        int training, int compute_loss, void* stream);
+/* Greedy decoding — WhisperForConditionalGeneration.generate (W:636-709). ts_whisper_encode runs the encoder once in
+ * inference mode and projects the cross-attention keys/values of every decoder layer (the only part of the decoder state
+ * that can be cached: under the reference's anti-causal self-attention mask, W:414-418, earlier positions attend to later
+ * ones, so every step re-runs the decoder over the whole prefix, exactly as generate() does). ts_whisper_decode_step runs
+ * the decoder on ids = [decoder_start_token, tokens[b, 0 .. len-2]] and writes tokens[b, len-1] = argmax over the vocabulary
+ * of the last position's logits (first maximum, tf.argmax); 1 <= len <= max_len; `tokens` is int32 [batch, ld_tok] on the
+ * device. The last step's logits are the "next_token_logits" buffer. */
+int ts_whisper_encode(ts_whisper* m, const float* feats, int batch, int n_frames, int max_len, void* stream);
+int ts_whisper_decode_step(ts_whisper* m, int32_t* tokens, int64_t ld_tok, int len, void* stream);
 int ts_whisper_backward(ts_whisper* m, int stage_from, int stage_to, void* stream);
 int ts_whisper_get_buffer(ts_whisper* m, const char* name, void** ptr, int32_t* dtype, int32_t* ndim, int64_t* shape4);
 

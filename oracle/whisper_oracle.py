@@ -188,6 +188,25 @@ def forward(cfg, w, feats, labels):
     return {"loss": loss, "logits": logits, "encoder_last_hidden_state": enc, "last_hidden_state": dec}
 
 
+def generate(cfg, w, feats, max_length=None):
+    """WhisperForConditionalGeneration.generate — W:636-709: encoder once; each iteration runs the decoder on the whole
+    prefix (no past_key_values are passed, W:664-671), takes argmax of the last position's logits (temperature and the top-k
+    filter of W:676-689 do not move an argmax; tf.argmax returns the first maximum), appends it and stops once every sequence
+    emitted eos_token_id in the same step (W:697-705). Returns [B, 1 + steps] int64 starting with decoder_start_token_id."""
+    max_length = cfg.max_target_positions if max_length is None else max_length
+    B = feats.shape[0]
+    enc = encoder(cfg, w, feats)
+    ids = torch.full((B, 1), cfg.decoder_start_token_id, dtype=torch.long)
+    for _ in range(max_length):
+        dec = decoder(cfg, w, ids, enc)
+        logits = dec[:, -1, :] @ w["lm_head.kernel"]
+        nxt = torch.stack([torch.nonzero(r == r.max())[0, 0] for r in logits])     # first maximum
+        ids = torch.cat([ids, nxt.unsqueeze(1)], dim=1)
+        if bool((nxt == cfg.eos_token_id).all()):
+            break
+    return ids
+
+
 def loss_and_grads(cfg, w, feats, labels):
     ws = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in w.items())
     out = forward(cfg, ws, feats, labels)

@@ -135,6 +135,8 @@ SYMBOLS = {
     "ts_whisper_bind": (_I, [_P, _P, _P, _P, _P, _L]),
     "ts_whisper_sync_compute_weights": (_I, [_P, _P]),
     "ts_whisper_forward": (_I, [_P, _P, _I, _I, _P, _I, C.c_uint64, _I, _I, _P]),
+    "ts_whisper_encode": (_I, [_P, _P, _I, _I, _I, _P]),
+    "ts_whisper_decode_step": (_I, [_P, _P, _L, _I, _P]),
     "ts_whisper_backward": (_I, [_P, _I, _I, _P]),
     "ts_whisper_get_buffer": (_I, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L)]),
 }

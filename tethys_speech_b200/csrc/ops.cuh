@@ -115,7 +115,7 @@ int ce_fwd_bwd(Ctx*, int dt, const void* logits, void* dlogits, long long ldv, c
                int B, int S, int V, float grad_scale, cudaStream_t);
 // embedding gather + positional encoding (+ dropout): out[b,s,:] = drop(table[ids[b,s],:] + pe[s,:]); the ids are the
 // labels shifted right with the start token (W:559-563). embed_bwd scatter-adds drop(dout) into the fp32 table grad.
-int embed_fwd(Ctx*, int dt, const void* table, const int* labels, const float* pe, void* out, int B, int S, int D,
+int embed_fwd(Ctx*, int dt, const void* table, const int* labels, long long label_ld /*ints per batch row*/, const float* pe, void* out, int B, int S, int D,
               int start_token, float drop, uint64_t seed, cudaStream_t);
 int embed_bwd(Ctx*, int dt, const void* dout, const int* labels, float* dtable, int B, int S, int D,
               int start_token, float drop, uint64_t seed, cudaStream_t);

@@ -51,18 +51,18 @@ int ce_fwd_bwd(Ctx* ctx, int dt, const void* logits, void* dlogits, long long ld
 
 // ---- embedding -------------------------------------------------------------------------------------------------
 // decoder_input_ids = pad(labels[:, :-1], left, start_token)   (W:559-563)
-__device__ __forceinline__ int dec_id(const int* labels, int b, int s, int S, int start_token) {
-  return s == 0 ? start_token : labels[b * S + s - 1];
+__device__ __forceinline__ int dec_id(const int* labels, int b, int s, long long ld, int start_token) {
+  return s == 0 ? start_token : labels[b * ld + s - 1];
 }
 
 template <typename T>
 __global__ void embed_fwd_kernel(const T* __restrict__ table, const int* __restrict__ labels, const float* __restrict__ pe,
-                                 T* __restrict__ out, int S, int D, int start_token, uint32_t thr, float inv_keep, uint64_t seed,
-                                 const unsigned long long* __restrict__ salt) {
+                                 T* __restrict__ out, int S, long long label_ld, int D, int start_token, uint32_t thr, float inv_keep,
+                                 uint64_t seed, const unsigned long long* __restrict__ salt) {
   if (thr) seed = salted_seed(seed, salt);
   const long long row = blockIdx.x;
   const int b = (int)(row / S), s = (int)(row % S);
-  const long long id = dec_id(labels, b, s, S, start_token);
+  const long long id = dec_id(labels, b, s, label_ld, start_token);
   for (int j = threadIdx.x; j < D; j += blockDim.x) {
     float v = to_f<T>(table[id * D + j]) + pe[(long long)s * D + j];
     if (thr) v *= dropout_scale(seed, (uint64_t)(row * D + j), thr, inv_keep);
@@ -91,12 +91,12 @@ static inline void drop3(float drop, uint32_t* thr, float* ik) {
   *ik = 1.f / (1.f - drop);
 }
 
-int embed_fwd(Ctx* ctx, int dt, const void* table, const int* labels, const float* pe, void* out, int B, int S, int D,
+int embed_fwd(Ctx* ctx, int dt, const void* table, const int* labels, long long label_ld, const float* pe, void* out, int B, int S, int D,
               int start_token, float drop, uint64_t seed, cudaStream_t st) {
   uint32_t thr; float ik;
   drop3(drop, &thr, &ik);
-  if (dt == TS_F32) embed_fwd_kernel<float><<<B * S, 256, 0, st>>>((const float*)table, labels, pe, (float*)out, S, D, start_token, thr, ik, seed, ctx->d_state);
-  else embed_fwd_kernel<bf16><<<B * S, 256, 0, st>>>((const bf16*)table, labels, pe, (bf16*)out, S, D, start_token, thr, ik, seed, ctx->d_state);
+  if (dt == TS_F32) embed_fwd_kernel<float><<<B * S, 256, 0, st>>>((const float*)table, labels, pe, (float*)out, S, label_ld, D, start_token, thr, ik, seed, ctx->d_state);
+  else embed_fwd_kernel<bf16><<<B * S, 256, 0, st>>>((const bf16*)table, labels, pe, (bf16*)out, S, label_ld, D, start_token, thr, ik, seed, ctx->d_state);
   TS_LAUNCH_OK(ctx);
   return 0;
 }

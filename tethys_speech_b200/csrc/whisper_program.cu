@@ -52,6 +52,7 @@ struct Whisper {
   uint64_t seed = 0;
   int training = 1;
   bool planned = false, fwd_done = false;
+  bool gen_ready = false;   // ts_whisper_encode has run on the current plan: encoder output + cross K/V are valid
 
   const void* W(long long off) const { return prec == TS_BF16 ? (const void*)((const bf16*)P16 + off) : (const void*)(P + off); }
   size_t E(long long n) const { return (size_t)n * esz; }
@@ -294,14 +295,14 @@ __global__ void mel_to_rows_kernel(const float* __restrict__ f, T* __restrict__ 
 
 __global__ void whisper_finalize_scalars(float* s, float inv_rows) { s[0] = s[3] * inv_rows; }
 
-static int whisper_forward(Whisper* m, const float* feats, const int* labels, cudaStream_t st) {
+// conv stem + encoder layers + final LayerNorm -> enc_out (WhisperEncoder.call, W:324-372)
+static int whisper_encoder_forward(Whisper* m, const float* feats, cudaStream_t st) {
   Ctx* ctx = m->ctx;
   const ts_whisper_config& c = m->cfg;
-  const int dt = m->prec, B = m->B, T = m->T, Tp = m->Tp, S = m->S, Sp = m->Sp, d = c.d_model, F = c.d_ff, nh = c.heads, hd = d / nh;
-  const long long Me = (long long)B * T, Md = (long long)B * S;
+  const int dt = m->prec, B = m->B, T = m->T, Tp = m->Tp, d = c.d_model, F = c.d_ff, nh = c.heads, hd = d / nh;
+  const long long Me = (long long)B * T;
   const uint64_t seed = m->seed;
   const float scale = 1.f / sqrtf((float)hd);
-  m->labels = labels;
   TS_TRY(fill_zero(ctx, m->scalars, 64, st));
   // ---- conv stem (W:329-342) ------------------------------------------------------------------------------------
   TS_TRY(fill_zero(ctx, m->xT, m->E((long long)B * m->R0 * c.n_mels + 3 * c.n_mels), st));
@@ -337,9 +338,25 @@ static int whisper_forward(Whisper* m, const float* feats, const int* labels, cu
                .drop(m->drop(c.dropout), site_seed(seed, 103 + l * 8)).mnk((int)Me, d, F).run(ctx, st));
   }
   TS_TRY(layernorm_fwd(ctx, dt, m->h_final, nullptr, m->P + m->enc_ln_g, m->P + m->enc_ln_b, m->enc_out, nullptr, m->enc_m, m->enc_r, (int)Me, d, c.ln_eps, st));
+  return 0;
+}
+
+// WhisperDecoder.call + lm_head over S positions (S <= the planned length; the buffers are dense [B*S, ...], so a shorter
+// sequence uses a prefix of each). Decoder input ids = [start_token, labels[b, 0 .. S-2]] with `label_ld` ints per batch row
+// (W:559-563 for the train step; the growing decoder_input_ids of generate(), W:659-704).
+//   reuse_cross_kv: the cross-attention K/V projections of the encoder output are already in the layer buffers
+//   last_only:      lm_head on the last position only -> logits [B, Vp]
+static int whisper_decoder_forward(Whisper* m, const int* labels, long long label_ld, int S, bool reuse_cross_kv, bool last_only,
+                                   cudaStream_t st) {
+  Ctx* ctx = m->ctx;
+  const ts_whisper_config& c = m->cfg;
+  const int dt = m->prec, B = m->B, T = m->T, Tp = m->Tp, Sp = (S + 7) & ~7, d = c.d_model, F = c.d_ff, nh = c.heads, hd = d / nh;
+  const long long Me = (long long)B * T, Md = (long long)B * S;
+  const uint64_t seed = m->seed;
+  const float scale = 1.f / sqrtf((float)hd);
   // ---- decoder (W:394-466) --------------------------------------------------------------------------------------
   void* g0 = c.dec_layers ? m->DB[0].g_in : m->g_final;
-  TS_TRY(embed_fwd(ctx, dt, m->W(m->emb), labels, m->pe_dec, g0, B, S, d, c.start_token, m->drop(c.dropout), site_seed(seed, 2), st));
+  TS_TRY(embed_fwd(ctx, dt, m->W(m->emb), labels, label_ld, m->pe_dec, g0, B, S, d, c.start_token, m->drop(c.dropout), site_seed(seed, 2), st));
   for (int l = 0; l < c.dec_layers; ++l) {
     const DecLayerOff& o = m->DL[l];
     DecLayerBuf& b = m->DB[l];
@@ -354,7 +371,8 @@ static int whisper_forward(Whisper* m, const float* feats, const int* labels, cu
     // cross-attention over the encoder output (W:278-290)
     TS_TRY(layernorm_fwd(ctx, dt, b.g1, nullptr, m->P + o.ln2_g, m->P + o.ln2_b, b.x2, nullptr, b.m2, b.r2, (int)Md, d, c.ln_eps, st));
     TS_TRY(GemmB(dt, dt).A(b.x2, 0, d).B(m->W(o.ca.q_w), 1, d).C(b.q, d).bias(m->P + o.ca.q_b).mnk((int)Md, d, d).run(ctx, st));
-    TS_TRY(GemmB(dt, dt).A(m->enc_out, 0, d).B(m->W(o.ca.kv_w), 1, 2 * d).C(b.kv, 2 * d).bias(m->P + o.ca.kv_b).mnk((int)Me, 2 * d, d).run(ctx, st));
+    if (!reuse_cross_kv)
+      TS_TRY(GemmB(dt, dt).A(m->enc_out, 0, d).B(m->W(o.ca.kv_w), 1, 2 * d).C(b.kv, 2 * d).bias(m->P + o.ca.kv_b).mnk((int)Me, 2 * d, d).run(ctx, st));
     const char* kv = (const char*)b.kv;
     TS_TRY(attn_forward(m, b.q, d, kv, kv + m->E(d), 2 * d, b.Pc, b.ctxc, d, {B, nh, hd, S, T, Tp}, scale, 0,
                         m->drop(c.attention_dropout), site_seed(seed, 1001 + l * 8), st));
@@ -367,9 +385,45 @@ static int whisper_forward(Whisper* m, const float* feats, const int* labels, cu
                .drop(m->drop(c.dropout), site_seed(seed, 1003 + l * 8)).mnk((int)Md, d, F).run(ctx, st));
   }
   TS_TRY(layernorm_fwd(ctx, dt, m->g_final, nullptr, m->P + m->dec_ln_g, m->P + m->dec_ln_b, m->dec_out, nullptr, m->dec_m, m->dec_r, (int)Md, d, c.ln_eps, st));
-  // ---- lm_head + shifted CE (W:579-600) ---------------------------------------------------------------------------
-  TS_TRY(GemmB(dt, dt).A(m->dec_out, 0, d).B(m->W(m->lm_w), 1, m->Vp).C(m->logits, m->Vp).mnk((int)Md, (int)m->Vp, d).run(ctx, st));
+  // ---- lm_head (W:579) --------------------------------------------------------------------------------------------
+  if (last_only)
+    TS_TRY(GemmB(dt, dt).A((const char*)m->dec_out + m->E((long long)(S - 1) * d), 0, (long long)S * d).B(m->W(m->lm_w), 1, m->Vp)
+               .C(m->logits, m->Vp).mnk(B, (int)m->Vp, d).run(ctx, st));
+  else
+    TS_TRY(GemmB(dt, dt).A(m->dec_out, 0, d).B(m->W(m->lm_w), 1, m->Vp).C(m->logits, m->Vp).mnk((int)Md, (int)m->Vp, d).run(ctx, st));
   return 0;
+}
+
+static int whisper_forward(Whisper* m, const float* feats, const int* labels, cudaStream_t st) {
+  m->labels = labels;
+  TS_TRY(whisper_encoder_forward(m, feats, st));
+  return whisper_decoder_forward(m, labels, m->S, m->S, false, false, st);
+}
+
+// next token = argmax over the valid vocabulary columns of one logits row per batch item; ties -> lowest index (tf.argmax)
+template <typename T>
+__global__ void __launch_bounds__(256) argmax_rows_kernel(const T* __restrict__ x, long long ld, int V, int* __restrict__ out,
+                                                          long long out_ld) {
+  __shared__ float sv[256];
+  __shared__ int si[256];
+  const T* row = x + (long long)blockIdx.x * ld;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = threadIdx.x; j < V; j += 256) {
+    const float v = to_f<T>(row[j]);
+    if (v > best || (v == best && j < bi)) { best = v; bi = j; }
+  }
+  sv[threadIdx.x] = best; si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const float ov = sv[threadIdx.x + o];
+      const int oi = si[threadIdx.x + o];
+      if (ov > sv[threadIdx.x] || (ov == sv[threadIdx.x] && oi < si[threadIdx.x])) { sv[threadIdx.x] = ov; si[threadIdx.x] = oi; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[(long long)blockIdx.x * out_ld] = si[0] == 0x7fffffff ? 0 : si[0];
 }
 
 static int whisper_loss(Whisper* m, cudaStream_t st) {
@@ -575,9 +629,54 @@ int ts_whisper_forward(ts_whisper* h, const float* feats, int B, int Tm, const i
                (long long)m->ws_bytes, (long long)bp.off);
     m->planned = true;
   }
-  m->seed = seed; m->training = training; m->fwd_done = false;
+  m->seed = seed; m->training = training; m->fwd_done = false; m->gen_ready = false;
   TS_TRY(whisper_forward(m, feats, labels, st));
   if (compute_loss) TS_TRY(whisper_loss(m, st));
+  return 0;
+}
+// ---- greedy decoding: WhisperForConditionalGeneration.generate (W:636-709) -------------------------------------------
+static int whisper_ensure_plan(Whisper* m, int B, int Tm, int S, const char* who) {
+  Ctx* ctx = m->ctx;
+  TS_REQUIRE(ctx, m->P && m->ws, TS_EINVAL, "%s: call ts_whisper_bind first", who);
+  if (!m->planned || m->B != B || m->Tm != Tm || m->S != S) {
+    Bump bp;
+    bp.base = m->ws;
+    TS_TRY(plan(m, B, Tm, S, bp));
+    TS_REQUIRE(ctx, (long long)bp.off <= m->ws_bytes, TS_EINVAL, "%s: workspace too small (%lld < %lld bytes)", who,
+               (long long)m->ws_bytes, (long long)bp.off);
+    m->planned = true;
+  }
+  return 0;
+}
+int ts_whisper_encode(ts_whisper* h, const float* feats, int B, int Tm, int max_len, void* stream) {
+  Whisper* m = reinterpret_cast<Whisper*>(h);
+  Ctx* ctx = m->ctx;
+  cudaStream_t st = (cudaStream_t)stream;
+  TS_REQUIRE(ctx, B > 0 && feats && max_len >= 1, TS_EINVAL, "whisper_encode: bad arguments");
+  TS_TRY(whisper_ensure_plan(m, B, Tm, max_len < 2 ? 2 : max_len, "whisper_encode"));
+  m->seed = 0; m->training = 0; m->fwd_done = false; m->gen_ready = false;
+  TS_TRY(whisper_encoder_forward(m, feats, st));
+  // the cross-attention keys / values depend on the encoder output only: project them once for all decode steps
+  const ts_whisper_config& c = m->cfg;
+  const int d = c.d_model;
+  const long long Me = (long long)B * m->T;
+  for (int l = 0; l < c.dec_layers; ++l)
+    TS_TRY(GemmB(m->prec, m->prec).A(m->enc_out, 0, d).B(m->W(m->DL[l].ca.kv_w), 1, 2 * d).C(m->DB[l].kv, 2 * d)
+               .bias(m->P + m->DL[l].ca.kv_b).mnk((int)Me, 2 * d, d).run(ctx, st));
+  m->gen_ready = true;
+  return 0;
+}
+int ts_whisper_decode_step(ts_whisper* h, int32_t* tokens, int64_t ld_tok, int len, void* stream) {
+  Whisper* m = reinterpret_cast<Whisper*>(h);
+  Ctx* ctx = m->ctx;
+  cudaStream_t st = (cudaStream_t)stream;
+  TS_REQUIRE(ctx, m->planned && m->gen_ready, TS_EINVAL, "whisper_decode_step: call ts_whisper_encode first");
+  TS_REQUIRE(ctx, tokens && len >= 1 && len <= m->S && ld_tok >= len, TS_EINVAL,
+             "whisper_decode_step: len %d outside [1, %d] (the max_len given to ts_whisper_encode) or token stride too small", len, m->S);
+  TS_TRY(whisper_decoder_forward(m, tokens, ld_tok, len, true, true, st));
+  if (m->prec == TS_F32) argmax_rows_kernel<float><<<m->B, 256, 0, st>>>((const float*)m->logits, m->Vp, m->cfg.vocab, tokens + (len - 1), ld_tok);
+  else argmax_rows_kernel<bf16><<<m->B, 256, 0, st>>>((const bf16*)m->logits, m->Vp, m->cfg.vocab, tokens + (len - 1), ld_tok);
+  TS_LAUNCH_OK(ctx);
   return 0;
 }
 int ts_whisper_backward(ts_whisper* h, int stage_from, int stage_to, void* stream) {
@@ -602,6 +701,7 @@ int ts_whisper_get_buffer(ts_whisper* h, const char* name, void** ptr, int32_t* 
   if (s == "scalars") return set(m->scalars, TS_F32, 1, 4, 1, 1, 1);
   if (s == "encoder_last_hidden_state") return set(m->enc_out, m->prec, 3, B, m->T, d, 1);
   if (s == "last_hidden_state") return set(m->dec_out, m->prec, 3, B, m->S, d, 1);
+  if (s == "next_token_logits") return set(m->logits, m->prec, 2, B, m->Vp, 1, 1);   // after ts_whisper_decode_step
   if (s == "logits") return set(m->logits, m->prec, 3, B, m->S, m->Vp, 1);   // padded last dim; valid columns [0, vocab)
   if (s == "decoder_self_attn_probs0") {
     if (m->fused_attn) return set_err(m->ctx, TS_EUNSUPPORTED, "probabilities are not materialised by the fused attention kernels; read decoder_self_attn_stats0");

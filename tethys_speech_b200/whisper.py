@@ -175,6 +175,48 @@ class WhisperForConditionalGeneration:
 
     call = __call__
 
+    def generate(self, input_features, max_length=None, min_length=None, num_beams=None, temperature=1.0, top_k=None, top_p=None,
+                 repetition_penalty=None, attention_mask=None, sync_every=8, **kwargs):
+        """W:636-709: encoder once, then up to `max_length` (default max_target_positions) greedy steps, each re-running the
+        decoder on the whole prefix (the reference passes no past_key_values, and under its anti-causal mask a self-attention
+        cache would not be valid anyway); stops after the first step at which EVERY sequence emits eos_token_id (W:700-705).
+        Returns int32 [B, 1 + steps] starting with decoder_start_token_id.
+
+        temperature > 0 and the top-k filter (W:676-689) cannot change an argmax, min_length / top_p / repetition_penalty are
+        read and ignored by the reference, and num_beams > 1 is a `pass` there that leaves next_tokens undefined (W:692-694):
+        greedy is the only behaviour to reproduce. The host looks at the tokens every `sync_every` steps instead of after each
+        one; steps computed past the stopping point are discarded, so the result is the same."""
+        if attention_mask is not None:
+            raise NotImplementedError("attention_mask is not supported by generate()")
+        if num_beams not in (None, 1):
+            raise NotImplementedError("num_beams > 1: the reference's beam-search branch is empty (W:692-694)")
+        if temperature is not None and not temperature > 0:
+            raise ValueError("temperature must be > 0")
+        cfg = self.config
+        max_length = int(max_length) if max_length is not None else cfg.max_target_positions
+        if not 1 <= max_length <= cfg.max_target_positions:
+            raise ValueError(f"max_length must be in [1, {cfg.max_target_positions}] (size of the positional table, W:383)")
+        p = self._prog
+        x = to_device(input_features, torch.float32, p.device)
+        B, nm, Tm = x.shape
+        p.ensure_workspace(B, Tm, max(2, max_length))
+        p.sync_weights()
+        p.ctx.check(p.lib.ts_whisper_encode(p.h, ptr(x), B, Tm, max_length, stream_ptr()))
+        tokens = torch.zeros(B, max_length, dtype=torch.int32, device=p.device)
+        steps, checked = max_length, 0
+        for L in range(1, max_length + 1):
+            p.ctx.check(p.lib.ts_whisper_decode_step(p.h, ptr(tokens), max_length, L, stream_ptr()))
+            if L % max(1, int(sync_every)) == 0 or L == max_length:
+                all_eos = (tokens[:, checked:L] == cfg.eos_token_id).all(dim=0)
+                hit = torch.nonzero(all_eos)
+                if hit.numel():
+                    steps = checked + int(hit[0]) + 1
+                    break
+                checked = L
+        self._last = {"x": x}
+        start = torch.full((B, 1), cfg.decoder_start_token_id, dtype=torch.int32, device=p.device)
+        return torch.cat([start, tokens[:, :steps]], dim=1)
+
     def gradient(self, stage_from=0, stage_to=10 ** 6):
         """tape.gradient(loss, model.trainable_variables) — W:833."""
         p = self._prog
