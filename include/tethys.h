@@ -197,6 +197,11 @@ int ts_optim_step(ts_optim* o, float* params, const float* grads, float* m, floa
                   float lr, float beta1, float beta2, float eps, int32_t step, float global_clip /*<=0 off*/,
                   float clipnorm /*<=0 off*/, int32_t fuse_global_clip, void* stream);
 int ts_cast_f32_to_bf16(ts_ctx* ctx, const float* src, void* dst, int64_t n, void* stream);
+/* tf.keras.layers.Dropout in training mode (W:160, W:203-205, W:342; V:281, V:393-396, V:431) over a flat tensor:
+ * y[i] = x[i] * mask(seed, i) / (1 - rate), in place allowed. mask is the library's counter-based generator (element i of the
+ * tensor -> chunk i >> 5, position i & 31), the same one the GEMM epilogues (ts_gemm_desc.drop / .seed) and every backward
+ * kernel evaluate, so a mask can be regenerated anywhere from (seed, flat index) and is never stored. */
+int ts_dropout(ts_ctx* ctx, int dtype, const void* x, void* y, int64_t n, float rate, uint64_t seed, void* stream);
 
 /* ---- Wav2Vec2 pre-training program ---------------------------------------------------------------------
  * Replaces Wav2Vec2ForPreTraining.call(training=True) + _compute_contrastive_loss + _compute_diversity_loss

@@ -235,4 +235,12 @@ int ts_cast_f32_to_bf16(ts_ctx* ctx, const float* src, void* dst, int64_t n, voi
   return ts::cast_f32_to_bf16(reinterpret_cast<Ctx*>(ctx), src, dst, n, (cudaStream_t)stream);
 }
 
+int ts_dropout(ts_ctx* ctx_, int dtype, const void* x, void* y, int64_t n, float rate, uint64_t seed, void* stream) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  if (!ctx) return TS_EINVAL;
+  TS_REQUIRE(ctx, x && y && n >= 0 && rate >= 0.f && rate < 1.f, TS_EINVAL, "ts_dropout: bad arguments (rate must be in [0, 1))");
+  TS_REQUIRE(ctx, dtype == TS_F32 || dtype == TS_BF16, TS_EDTYPE, "ts_dropout: dtype %d", dtype);
+  return ts::dropout_apply(ctx, dtype, x, y, n, rate, seed, (cudaStream_t)stream);
+}
+
 }  // extern "C"

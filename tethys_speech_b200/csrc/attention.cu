@@ -61,8 +61,10 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(T* __restrict__ s, lon
       store8<T>(sr + col, o);
       if (pdrop) {
         round8<T>(o);
+        float ds[8];
+        dropout_scale8(flat_drop_key(seed, thr), (uint64_t)(row * ld + col), inv_keep, ds);   // ld, col multiples of 8
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] *= dropout_scale(seed, (uint64_t)(row * ld + col + i), thr, inv_keep);
+        for (int i = 0; i < 8; ++i) o[i] *= ds[i];
         store8<T>(pdrop + row * ld + col, o);
       }
     }
@@ -85,10 +87,12 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const T* __restrict__ 
     if (col < Tk) {
       load8<T>(p + row * ld + col, pv[ch]);
       load8<T>(dp + row * ld + col, dv[ch]);
+      float ds[8];
+      if (thr) dropout_scale8(flat_drop_key(seed, thr), (uint64_t)(row * ld + col), inv_keep, ds);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (col + i >= Tk) { pv[ch][i] = 0.f; dv[ch][i] = 0.f; }
-        if (thr) dv[ch][i] *= dropout_scale(seed, (uint64_t)(row * ld + col + i), thr, inv_keep);
+        if (thr) dv[ch][i] *= ds[i];
         dot += pv[ch][i] * dv[ch][i];
       }
     }

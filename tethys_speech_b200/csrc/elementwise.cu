@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(256) ew_kernel(const T* __restrict__ a, const 
                                                  long long n, uint32_t thr, float inv_keep, uint64_t seed,
                                                  const unsigned long long* __restrict__ salt) {
   if (MODE != 3 && thr) seed = salted_seed(seed, salt);
+  const DropKey key = flat_drop_key(seed, thr);
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
     float va[8], vb[8], o[8];
@@ -54,6 +55,8 @@ __global__ void __launch_bounds__(256) ew_kernel(const T* __restrict__ a, const 
         vb[j] = ((MODE == 1 || MODE == 3) && i + j < n) ? to_f<T>(b[i + j]) : 0.f;
       }
     }
+    float ds[8];
+    if (MODE != 3 && thr) dropout_scale8(key, (uint64_t)i, inv_keep, ds);   // i is a multiple of 8: one chunk hash for the 8 elements
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float r;
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(256) ew_kernel(const T* __restrict__ a, const 
       else if (MODE == 1) r = va[j] * gelu_grad_t<T>(vb[j]);
       else if (MODE == 2) r = va[j];
       else r = va[j] + vb[j];
-      if (MODE != 3 && thr) r *= dropout_scale(seed, (uint64_t)(i + j), thr, inv_keep);
+      if (MODE != 3 && thr) r *= ds[j];
       o[j] = r;
     }
     if (i + 8 <= n) store8<T>(out + i, o);

@@ -135,16 +135,13 @@ __device__ __forceinline__ void epi_act_drop(float (&v)[NV], const EpiParams& p,
     }
   }
   if (p.drop_thr) {
-    if ((e0 & 1) == 0) {
+    const DropKey key = flat_drop_key(seed, p.drop_thr);
+    if ((e0 & 31) == 0) {   // this thread's NV consecutive elements are whole 32-element chunks of the mask stream
 #pragma unroll
-      for (int i = 0; i < NV; i += 2) {
-        float s0, s1;
-        dropout_scale2(seed, e0 + i, p.drop_thr, p.inv_keep, s0, s1);
-        v[i] *= s0; v[i + 1] *= s1;
-      }
+      for (int c = 0; c < NV / 32; ++c) dropout_apply_chunk(v + 32 * c, key, (uint32_t)(e0 >> 5) + c, p.inv_keep);
     } else {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) v[i] *= dropout_scale(seed, e0 + i, p.drop_thr, p.inv_keep);
+      for (int i = 0; i < NV; ++i) v[i] *= dropout_scale(key, e0 + i, p.inv_keep);
     }
   }
 }
@@ -329,10 +326,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (lane == 0) {
               ptx::tma_store_4d(&tma_p, wbuf_s, col, row0, tc.b1, tc.b2);
               ptx::bulk_commit();
-              ptx::bulk_wait_read<0>();
             }
-            __syncwarp();
           }
+          // activation / dropout work on registers only: it overlaps the TMA engine reading the pre-activation box
           epi_act_drop<CW, OutT>(v, p, seed, (unsigned long long)(boff + (long long)row * p.ldc + col),
                                  reinterpret_cast<const OutT*>(p.aux) + boff + (long long)row * p.ld_aux + col, row < p.m, col, full);
           if (p.res && row < p.m) {
@@ -362,6 +358,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               for (int i = 0; i < CW; ++i)
                 if (col + i < p.n) v[i] += to_f<OutT>(rrow[i]);
             }
+          }
+          if (p.c_pre) {   // the pre-activation store must be done with the staging box before it is overwritten
+            if (lane == 0) ptx::bulk_wait_read<0>();
+            __syncwarp();
           }
           if (kF32) {
 #pragma unroll

@@ -125,10 +125,12 @@ __global__ void add_pe_kernel(const T* __restrict__ x, long long rpb_in, const f
     float v[8], p[8];
     load8<T>(x + (b * rpb_in + t) * D + c, v);
     load8<float>(pe + (long long)t * D + c, p);
+    float ds[8];
+    if (thr) dropout_scale8(flat_drop_key(seed, thr), (uint64_t)(r * D + c), inv_keep, ds);   // D % 8 == 0: 8-aligned
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       v[j] += p[j];
-      if (thr) v[j] *= dropout_scale(seed, (uint64_t)(r * D + c + j), thr, inv_keep);
+      if (thr) v[j] *= ds[j];
     }
     store8<T>(y + r * D + c, v);
   }

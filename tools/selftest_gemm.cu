@@ -24,6 +24,7 @@ struct Case {
   long long lda, ldb;  // 0 => dense
   int out_f32, bias, act, res, accumulate, preact;
   float alpha;
+  float drop;  // timing cases only (the mask is checked by the parity tests, not here)
 };
 
 static int run_case(ts_ctx* ctx, const Case& cs, int engine, bool timing) {
@@ -71,6 +72,7 @@ static int run_case(ts_ctx* ctx, const Case& cs, int engine, bool timing) {
   d.bias = cs.bias ? dbias : nullptr; d.act = cs.act; d.residual = cs.res ? dres : nullptr; d.ldr = ldc;
   d.r_bs1 = c_bs; d.r_bs2 = c_bs * cs.nb1; d.accumulate = cs.accumulate; d.c_preact = cs.preact ? dpre : nullptr;
   d.force_engine = engine;
+  d.drop = timing ? cs.drop : 0.f; d.seed = 0x1234;
   int rc = ts_gemm(ctx, &d, 0);
   if (rc) { printf("  [%s] ts_gemm rc=%d: %s\n", cs.name, rc, ts_last_error(ctx)); return 1; }
   cudaError_t e = cudaDeviceSynchronize();
@@ -189,6 +191,8 @@ int main(int argc, char** argv) {
         {"ffn2 6000x768x3072", 6000, 768, 3072, 0, 1, 1, 1, 0, 0, 0, 1, 0, 0, 0, 0, 1.f},
         {"dgrad 6000x768x3072", 6000, 768, 3072, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1.f},
         {"ffn1+gelu+preact", 6000, 3072, 768, 0, 1, 1, 1, 0, 0, 0, 1, 1, 0, 0, 1, 1.f},
+        {"ffn1+gelu+preact+drop", 6000, 3072, 768, 0, 1, 1, 1, 0, 0, 0, 1, 1, 0, 0, 1, 1.f, 0.1f},
+        {"ffn2+res+drop", 6000, 768, 3072, 0, 1, 1, 1, 0, 0, 0, 1, 0, 1, 0, 0, 1.f, 0.1f},
         {"qkv 6000x2304x768", 6000, 2304, 768, 0, 1, 1, 1, 0, 0, 0, 1, 0, 0, 0, 0, 1.f},
         {"out 6000x768x768 +res", 6000, 768, 768, 0, 1, 1, 1, 0, 0, 0, 1, 0, 1, 0, 0, 1.f},
         {"wgrad 768x3072x6000", 768, 3072, 6000, 1, 1, 1, 1, 0, 0, 1, 0, 0, 0, 1, 0, 1.f},
