@@ -516,6 +516,8 @@ def run_ours(args):
         "config": {"workload": args.workload, "model": model_name, "audio_seconds": secs, "per_gpu_batch": B,
                    "global_batch": B * world, "parallelism": f"dp{world}", "dropout": "on (0.1, as the reference's training=True)",
                    "step": step_desc, "cuda_graph": bool(use_graph),
+                   "allreduce": ("none (1 replica)" if world == 1 else
+                                 ("bf16 gradient buckets (fp32 master weights / Adam state)" if model._prog.ar_bf16() else "fp32 gradient buckets")),
                    "l2": "working set per step (GBs of activations) >> 126 MB L2; 4 distinct input batches cycled; "
                          "per-kernel timings flush L2 with a 256 MB memset between launches"},
         "clocks": clk,

@@ -197,6 +197,12 @@ int ts_optim_step(ts_optim* o, float* params, const float* grads, float* m, floa
                   float lr, float beta1, float beta2, float eps, int32_t step, float global_clip /*<=0 off*/,
                   float clipnorm /*<=0 off*/, int32_t fuse_global_clip, void* stream);
 int ts_cast_f32_to_bf16(ts_ctx* ctx, const float* src, void* dst, int64_t n, void* stream);
+/* Gradient buckets for the cross-replica SUM (the all-reduce inside apply_gradients, W:834 / V:1246) in bf16: pack = bf16(src *
+ * scale_dev[0]) (scale_dev nullable; the Wav2Vec2 step folds its local clip_by_global_norm factor, V:1243, in here), unpack =
+ * back to the fp32 gradient arena the optimizer reads. Halves the bytes on NVLink; used when the model computes in bf16
+ * (TETHYS_AR_DTYPE=fp32 keeps fp32 buckets), never in fp32 parity mode. */
+int ts_grad_pack_bf16(ts_ctx* ctx, const float* src, void* dst_bf16, int64_t n, const float* scale_dev, void* stream);
+int ts_grad_unpack_bf16(ts_ctx* ctx, const void* src_bf16, float* dst, int64_t n, void* stream);
 /* tf.keras.layers.Dropout in training mode (W:160, W:203-205, W:342; V:281, V:393-396, V:431) over a flat tensor:
  * y[i] = x[i] * mask(seed, i) / (1 - rate), in place allowed. mask is the library's counter-based generator (element i of the
  * tensor -> chunk i >> 5, position i & 31), the same one the GEMM epilogues (ts_gemm_desc.drop / .seed) and every backward

@@ -109,6 +109,8 @@ SYMBOLS = {
     "ts_optim_global_clip_scale": (_I, [_P, _P, _F, _P, _P]),
     "ts_optim_step": (_I, [_P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _I, _F, _F, _I, _P]),
     "ts_cast_f32_to_bf16": (_I, [_P, _P, _P, _L, _P]),
+    "ts_grad_pack_bf16": (_I, [_P, _P, _P, _L, _P, _P]),
+    "ts_grad_unpack_bf16": (_I, [_P, _P, _P, _L, _P]),
     "ts_dropout": (_I, [_P, _I, _P, _P, _L, _F, C.c_uint64, _P]),
     "ts_w2v_create": (_I, [_P, C.POINTER(W2VConfig), _I, C.POINTER(_P)]),
     "ts_w2v_destroy": (None, [_P]),

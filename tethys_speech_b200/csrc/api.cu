@@ -235,6 +235,14 @@ int ts_cast_f32_to_bf16(ts_ctx* ctx, const float* src, void* dst, int64_t n, voi
   return ts::cast_f32_to_bf16(reinterpret_cast<Ctx*>(ctx), src, dst, n, (cudaStream_t)stream);
 }
 
+int ts_grad_pack_bf16(ts_ctx* ctx, const float* src, void* dst, int64_t n, const float* scale_dev, void* stream) {
+  if (!ctx || !src || !dst) return TS_EINVAL;
+  return ts::grad_pack_bf16(reinterpret_cast<Ctx*>(ctx), src, dst, n, scale_dev, (cudaStream_t)stream);
+}
+int ts_grad_unpack_bf16(ts_ctx* ctx, const void* src, float* dst, int64_t n, void* stream) {
+  if (!ctx || !src || !dst) return TS_EINVAL;
+  return ts::grad_unpack_bf16(reinterpret_cast<Ctx*>(ctx), src, dst, n, (cudaStream_t)stream);
+}
 int ts_dropout(ts_ctx* ctx_, int dtype, const void* x, void* y, int64_t n, float rate, uint64_t seed, void* stream) {
   Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
   if (!ctx) return TS_EINVAL;

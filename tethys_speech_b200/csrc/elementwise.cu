@@ -30,6 +30,52 @@ int cast_f32_to_bf16(Ctx* ctx, const float* src, void* dst, long long n, cudaStr
   return 0;
 }
 
+// gradient buckets for the all-reduce in bf16 ("perf mode" of SURVEY §8e): dst = bf16(src * scale[0]) and back
+__global__ void __launch_bounds__(256) grad_pack_kernel(const float* __restrict__ s, bf16* __restrict__ d, long long n,
+                                                        const float* __restrict__ scale) {
+  const float sc = scale ? __ldg(scale) : 1.f;
+  const long long stride = (long long)gridDim.x * blockDim.x * 8;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      float v[8];
+      load8<float>(s + i, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= sc;
+      store8<bf16>(d + i, v);
+    } else {
+      for (long long j = i; j < n; ++j) d[j] = __float2bfloat16_rn(s[j] * sc);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) grad_unpack_kernel(const bf16* __restrict__ s, float* __restrict__ d, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 8;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      float v[8];
+      load8<bf16>(s + i, v);
+      store8<float>(d + i, v);
+    } else {
+      for (long long j = i; j < n; ++j) d[j] = __bfloat162float(s[j]);
+    }
+  }
+}
+int grad_pack_bf16(Ctx* ctx, const float* src, void* dst, long long n, const float* scale_dev, cudaStream_t st) {
+  if (n <= 0) return 0;
+  TS_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(src) & 31) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0), TS_EINVAL,
+             "grad_pack_bf16: buckets must start on a 32-byte (fp32) / 16-byte (bf16) boundary");
+  grad_pack_kernel<<<ew_grid(ctx, (n + 7) / 8), 256, 0, st>>>(src, (bf16*)dst, n, scale_dev);
+  TS_LAUNCH_OK(ctx);
+  return 0;
+}
+int grad_unpack_bf16(Ctx* ctx, const void* src, float* dst, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  TS_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0), TS_EINVAL,
+             "grad_unpack_bf16: buckets must start on a 32-byte (fp32) / 16-byte (bf16) boundary");
+  grad_unpack_kernel<<<ew_grid(ctx, (n + 7) / 8), 256, 0, st>>>((const bf16*)src, dst, n);
+  TS_LAUNCH_OK(ctx);
+  return 0;
+}
+
 int fill_zero(Ctx* ctx, void* p, long long bytes, cudaStream_t st) {
   if (bytes <= 0) return 0;
   TS_CUDA_OK(ctx, cudaMemsetAsync(p, 0, (size_t)bytes, st));

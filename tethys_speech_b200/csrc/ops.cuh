@@ -34,6 +34,9 @@ int groupnorm_gelu_bwd(Ctx*, int dt, const void* da, long long da_rpb, const Col
 // ---- elementwise.cu ------------------------------------------------------------------------------
 int cast_f32_to_bf16(Ctx*, const float* src, void* dst, long long n, cudaStream_t);
 int fill_zero(Ctx*, void* p, long long bytes, cudaStream_t);
+// gradient bucket fp32 -> bf16 (times an optional device scalar) and back, for the bf16 all-reduce
+int grad_pack_bf16(Ctx*, const float* src, void* dst, long long n, const float* scale_dev, cudaStream_t);
+int grad_unpack_bf16(Ctx*, const void* src, float* dst, long long n, cudaStream_t);
 // out = gelu(in) (optionally times dropout mask)
 int gelu_fwd(Ctx*, int dt, const void* u, void* out, long long n, float drop, uint64_t seed, cudaStream_t);
 // du = df * gelu'(u) (* dropout mask scale)

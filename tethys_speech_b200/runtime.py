@@ -150,6 +150,28 @@ class ProgramBase:
     def backward(self, stage_from=0, stage_to=10 ** 6):
         self.ctx.check(self._f("backward")(self.h, int(stage_from), int(stage_to), stream_ptr()))
 
+    # -- bf16 gradient buckets for the all-reduce ("perf mode") -----------------------------------------------
+    def ar_bf16(self):
+        """bf16 buckets when the model computes in bf16 (its gradients carry bf16-level error already); fp32 parity mode
+        always reduces in fp32. TETHYS_AR_DTYPE=fp32 forces fp32 buckets."""
+        return self.precision == _lib.TS_BF16 and os.environ.get("TETHYS_AR_DTYPE", "bf16").lower() not in ("fp32", "float32", "f32")
+
+    def grads_lp(self):
+        if getattr(self, "_grads_lp", None) is None:
+            self._grads_lp = torch.zeros(self.n, dtype=torch.bfloat16, device=self.device)
+        return self._grads_lp
+
+    def pack_grads(self, a0=0, a1=None, scale=None):
+        """grads_lp[a0:a1] = bf16(grads[a0:a1] * scale) — scale: device scalar or None."""
+        a1 = self.n if a1 is None else a1
+        g16 = self.grads_lp()
+        self.ctx.check(self.lib.ts_grad_pack_bf16(self.ctx.h, ptr(self.grads[a0:a1]), ptr(g16[a0:a1]), a1 - a0, ptr(scale), stream_ptr()))
+        return g16[a0:a1]
+
+    def unpack_grads(self, a0=0, a1=None):
+        a1 = self.n if a1 is None else a1
+        self.ctx.check(self.lib.ts_grad_unpack_bf16(self.ctx.h, ptr(self.grads_lp()[a0:a1]), ptr(self.grads[a0:a1]), a1 - a0, stream_ptr()))
+
     def backward_allreduce_overlapped(self, strategy, bucket_elems=16 * 1024 * 1024):
         """K21: backward stage by stage; as soon as the arena prefix of a group of stages is final (the arena is laid out
         in backward-completion order, ts_*_stage_end) its bucket is all-reduced (SUM) asynchronously: NCCL's stream is
@@ -158,14 +180,18 @@ class ProgramBase:
         ends = self.stage_ends
         works = []
         start = 0
+        lp = strategy.dist is not None and self.ar_bf16()
         for s, end in enumerate(ends):
             self.backward(s, s)
             last = s == len(ends) - 1
             if strategy.dist is not None and (end - start >= bucket_elems or last) and end > start:
-                works.append(strategy.dist.all_reduce(self.grads[start:end], op=strategy.dist.ReduceOp.SUM, async_op=True))
+                bucket = self.pack_grads(start, end) if lp else self.grads[start:end]
+                works.append(strategy.dist.all_reduce(bucket, op=strategy.dist.ReduceOp.SUM, async_op=True))
                 start = end
         for w in works:
             w.wait()
+        if lp and works:
+            self.unpack_grads()
         return len(works)
 
 
@@ -354,7 +380,11 @@ class Adam:
             else:
                 fuse, gclip = 1, float(global_clip_norm)
         if strategy.num_replicas_in_sync > 1 and not already_reduced:
-            strategy.all_reduce_sum_(prog.grads, bucket_elems=int(os.environ.get("TETHYS_AR_BUCKET_ELEMS", 0)))
+            if strategy.dist is not None and prog.ar_bf16():
+                strategy.all_reduce_sum_(prog.pack_grads())
+                prog.unpack_grads()
+            else:
+                strategy.all_reduce_sum_(prog.grads, bucket_elems=int(os.environ.get("TETHYS_AR_BUCKET_ELEMS", 0)))
         self.iterations += 1
         ctx.check(lib.ts_optim_step(st["optim"], ptr(prog.params), ptr(prog.grads), ptr(st["m"]), ptr(st["v"]),
                                     ptr(prog.params_lp), self.learning_rate, self.beta_1, self.beta_2, self.epsilon,

@@ -520,24 +520,33 @@ def make_graphed_distributed_step(strategy, model, optimizer, example_features, 
     premul = (strategy.dist is not None and strategy.dist.get_backend() == "nccl" and hasattr(strategy.dist, "_make_nccl_premul_sum")
               and not os.environ.get("TETHYS_NO_PREMUL"))
     clip_scale = torch.ones(1, device=prog.device)
+    # bf16 compute: the gradient arena crosses NVLink as bf16 (half the bytes); the local clip factor rides on the pack
+    lp = strategy.dist is not None and prog.ar_bf16()
 
     def seg_fwd_bwd():
         prog.ctx.check(prog.lib.ts_step_state_advance(prog.ctx.h, stream_ptr()))
         out = model(feats, training=True, neg_indices=neg, loss_div=n, dropout=dropout)
         state["scaled_loss"] = out["loss"] / n
         model.gradient()
-        if premul:
+        if lp:
+            optimizer.local_clip_scale(model, 1.0, clip_scale)
+            prog.pack_grads(scale=clip_scale)
+        elif premul:
             optimizer.local_clip_scale(model, 1.0, clip_scale)     # factor only; applied inside the all-reduce
         else:
             optimizer.local_clip(model, 1.0)
 
     def seg_reduce():
-        if premul:
+        if lp:
+            strategy.all_reduce_sum_(prog.grads_lp())
+        elif premul:
             strategy.all_reduce_premul_sum_(prog.grads, clip_scale)
         else:
             strategy.all_reduce_sum_(prog.grads, bucket_elems=int(os.environ.get("TETHYS_AR_BUCKET_ELEMS", 0)))
 
     def seg_update():
+        if lp:
+            prog.unpack_grads()
         optimizer.update(model)
 
     segs = GraphedSegments([("graph", seg_fwd_bwd), ("eager", seg_reduce), ("graph", seg_update)], model, optimizer, warmup=warmup)

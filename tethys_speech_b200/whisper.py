@@ -381,6 +381,7 @@ def make_graphed_distributed_step(strategy, model, optimizer, example_features, 
     # measured at N=2: updating reduced buckets on a side stream underneath backward does not pay (7.18 vs 7.10 ms: the Adam
     # passes compete with backward for HBM) — opt-in only
     side_adam = bool(os.environ.get("TETHYS_SIDE_ADAM"))
+    lp = strategy.dist is not None and prog.ar_bf16() and not side_adam     # bf16 gradient buckets (bf16 compute only)
     optims = [prog.make_optim_range(a0, a1) for (_, _, a0, a1) in groups] if side_adam else None
     side = torch.cuda.Stream(device=dev)
     plan = []
@@ -392,13 +393,16 @@ def make_graphed_distributed_step(strategy, model, optimizer, example_features, 
 
     works = []
     for gi, (s0, s1, a0, a1) in enumerate(groups):
-        def seg_bwd(s0=s0, s1=s1, gi=gi):
+        def seg_bwd(s0=s0, s1=s1, gi=gi, a0=a0, a1=a1):
             if gi == 0:
                 seg_forward()
             prog.backward(s0, s1)
+            if lp:
+                prog.pack_grads(a0, a1)
 
         def seg_reduce(a0=a0, a1=a1):
-            works.append(strategy.dist.all_reduce(prog.grads[a0:a1], op=strategy.dist.ReduceOp.SUM, async_op=True))
+            bucket = prog.grads_lp()[a0:a1] if lp else prog.grads[a0:a1]
+            works.append(strategy.dist.all_reduce(bucket, op=strategy.dist.ReduceOp.SUM, async_op=True))
 
         plan += [("graph", seg_bwd), ("eager", seg_reduce)]
         if side_adam:
@@ -420,8 +424,13 @@ def make_graphed_distributed_step(strategy, model, optimizer, example_features, 
                 works.pop(0).wait()
 
     plan += [("eager", seg_join)]
+    def seg_update():
+        if lp:
+            prog.unpack_grads()
+        optimizer.update(model)
+
     if not side_adam:
-        plan += [("graph", lambda: optimizer.update(model))]
+        plan += [("graph", seg_update)]
     segs = GraphedSegments(plan, model, optimizer, warmup=warmup, side_stream=side, bump_iterations=side_adam)
 
     def step(features, lab):
