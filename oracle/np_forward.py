@@ -69,8 +69,8 @@ def _heads(x, nh):
 
 
 # ---- Wav2Vec2 (V) ----------------------------------------------------------------------------------------------
-def w2v_forward(cfg, w, wave, neg_idx):
-    w = {k: np.asarray(v, dtype=np.float64) for k, v in w.items()}
+def w2v_trunk(cfg, w, wave):
+    """Wav2Vec2Model.call(training=True) up to last_hidden_state — V:768-825. Returns (extract_features, quantizer outputs, x)."""
     G = cfg.num_conv_pos_embedding_groups
     h = wave[..., None]
     for i, s in enumerate(cfg.conv_stride):                                                   # V:287-288
@@ -111,6 +111,33 @@ def w2v_forward(cfg, w, wave, neg_idx):
         f = layer_norm(x, w[p + "feed_forward_layer_norm.gamma"], w[p + "feed_forward_layer_norm.beta"])
         f = gelu(f @ w[p + "feed_forward.intermediate_dense.kernel"] + w[p + "feed_forward.intermediate_dense.bias"])
         x = x + f @ w[p + "feed_forward.output_dense.kernel"] + w[p + "feed_forward.output_dense.bias"]
+    return ef, (qf, np.stack(idxs, 0), perplexity), x
+
+
+def _sparse_ce(logits, target):
+    lse = np.log(np.exp(logits - logits.max(-1, keepdims=True)).sum(-1)) + logits.max(-1)
+    return lse - np.take_along_axis(logits, np.asarray(target)[..., None].astype(np.int64), -1)[..., 0]
+
+
+def w2v_head_forward(cfg, w, wave, labels, head):
+    """Wav2Vec2ForCTC (V:957-1000: mean CE of every frame against class 0) / Wav2Vec2ForSequenceClassification (V:1018-1056)."""
+    w = {k: np.asarray(v, dtype=np.float64) for k, v in w.items()}
+    _, _, x = w2v_trunk(cfg, w, wave)
+    if head == "ctc":
+        logits = x @ w["lm_head.kernel"] + w["lm_head.bias"]
+        loss = float(_sparse_ce(logits, np.zeros(logits.shape[:2], dtype=np.int64)).mean())
+    else:
+        pooled = x.mean(axis=1)
+        proj = np.tanh(pooled @ w["classifier_proj.kernel"] + w["classifier_proj.bias"])
+        logits = proj @ w["classifier.kernel"] + w["classifier.bias"]
+        loss = float(_sparse_ce(logits, labels).mean())
+    return {"last_hidden_state": x, "logits": logits, "loss": loss}
+
+
+def w2v_forward(cfg, w, wave, neg_idx):
+    w = {k: np.asarray(v, dtype=np.float64) for k, v in w.items()}
+    ef, (qf, code_idx, perplexity), x = w2v_trunk(cfg, w, wave)
+    B, T = x.shape[:2]
     ps = layer_norm(x @ w["project_hid.dense.kernel"] + w["project_hid.dense.bias"], w["project_hid.layer_norm.gamma"], w["project_hid.layer_norm.beta"])
     pq = layer_norm(qf @ w["project_q.dense.kernel"] + w["project_q.dense.bias"], w["project_q.layer_norm.gamma"], w["project_q.layer_norm.beta"])
     # contrastive V:865-899
@@ -125,7 +152,7 @@ def w2v_forward(cfg, w, wave, neg_idx):
     lse = np.log(np.exp(logits - logits.max(-1, keepdims=True)).sum(-1)) + logits.max(-1)
     closs = float((lse - logits[..., 0]).mean())
     loss = closs + cfg.diversity_loss_weight * (-perplexity)
-    return {"extract_features": ef, "last_hidden_state": x, "quantized_features": qf, "code_indices": np.stack(idxs, 0),
+    return {"extract_features": ef, "last_hidden_state": x, "quantized_features": qf, "code_indices": code_idx,
             "codevector_perplexity": perplexity, "projected_states": ps, "projected_quantized_features": pq,
             "contrastive_logits": logits, "contrastive_loss": closs, "loss": loss}
 
@@ -155,36 +182,56 @@ def _mha(w, p, x, nh, kv=None, mask=None):
     return ctx @ w[p + "out_proj.kernel"] + w[p + "out_proj.bias"]
 
 
-def whisper_forward(cfg, w, feats, labels):
-    w = {k: np.asarray(v, dtype=np.float64) for k, v in w.items()}
+def _whisper_encoder(cfg, w, feats):
     nh = cfg.encoder_attention_heads
-    labels = np.asarray(labels)
     x = feats.transpose(0, 2, 1)
     h = gelu(conv1d_same(x, w["encoder.conv1.kernel"], 1, bias=w["encoder.conv1.bias"]))
     h = gelu(conv1d_same(h, w["encoder.conv2.kernel"], 2, bias=w["encoder.conv2.bias"]))
     h = h + _pe(cfg.n_ctx, cfg.d_model)[None, :h.shape[1]]
-
-    def ln(name, t):
-        return layer_norm(t, w[name + ".gamma"], w[name + ".beta"])
-
-    def ffn(p, t):
-        return gelu(t @ w[p + "fc1.kernel"] + w[p + "fc1.bias"]) @ w[p + "fc2.kernel"] + w[p + "fc2.bias"]
-
     for l in range(cfg.encoder_layers):
         p = f"encoder.layers.{l}."
-        h = h + _mha(w, p + "self_attn.", ln(p + "self_attn_layer_norm", h), nh)
-        h = h + ffn(p + "feed_forward.", ln(p + "final_layer_norm", h))
-    enc = ln("encoder.layer_norm", h)
-    B, S = labels.shape
-    ids = np.concatenate([np.full((B, 1), cfg.decoder_start_token_id), labels[:, :-1]], axis=1)
+        h = h + _mha(w, p + "self_attn.", layer_norm(h, w[p + "self_attn_layer_norm.gamma"], w[p + "self_attn_layer_norm.beta"]), nh)
+        t = layer_norm(h, w[p + "final_layer_norm.gamma"], w[p + "final_layer_norm.beta"])
+        h = h + gelu(t @ w[p + "feed_forward.fc1.kernel"] + w[p + "feed_forward.fc1.bias"]) @ w[p + "feed_forward.fc2.kernel"] + w[p + "feed_forward.fc2.bias"]
+    return layer_norm(h, w["encoder.layer_norm.gamma"], w["encoder.layer_norm.beta"])
+
+
+def _whisper_decoder(cfg, w, ids, enc):
+    """WhisperDecoder.call with the anti-causal mask 1 - band_part(ones, -1, 0) of W:414-418."""
+    nh = cfg.decoder_attention_heads
+    S = ids.shape[1]
     g = w["decoder.embed_tokens.embeddings"][ids] + _pe(cfg.max_target_positions, cfg.d_model)[None, :S]
     mask = (1.0 - np.tril(np.ones((S, S))))[None, None]
     for l in range(cfg.decoder_layers):
         p = f"decoder.layers.{l}."
-        g = g + _mha(w, p + "self_attn.", ln(p + "self_attn_layer_norm", g), nh, mask=mask)
-        g = g + _mha(w, p + "encoder_attn.", ln(p + "encoder_attn_layer_norm", g), nh, kv=enc)
-        g = g + ffn(p + "feed_forward.", ln(p + "final_layer_norm", g))
-    dec = ln("decoder.layer_norm", g)
+        g = g + _mha(w, p + "self_attn.", layer_norm(g, w[p + "self_attn_layer_norm.gamma"], w[p + "self_attn_layer_norm.beta"]), nh, mask=mask)
+        g = g + _mha(w, p + "encoder_attn.", layer_norm(g, w[p + "encoder_attn_layer_norm.gamma"], w[p + "encoder_attn_layer_norm.beta"]), nh, kv=enc)
+        t = layer_norm(g, w[p + "final_layer_norm.gamma"], w[p + "final_layer_norm.beta"])
+        g = g + gelu(t @ w[p + "feed_forward.fc1.kernel"] + w[p + "feed_forward.fc1.bias"]) @ w[p + "feed_forward.fc2.kernel"] + w[p + "feed_forward.fc2.bias"]
+    return layer_norm(g, w["decoder.layer_norm.gamma"], w["decoder.layer_norm.beta"])
+
+
+def whisper_generate(cfg, w, feats, max_length):
+    """generate() — W:636-709: greedy, the whole prefix re-decoded every step, stop when every sequence emits EOS."""
+    w = {k: np.asarray(v, dtype=np.float64) for k, v in w.items()}
+    enc = _whisper_encoder(cfg, w, feats)
+    ids = np.full((feats.shape[0], 1), cfg.decoder_start_token_id, dtype=np.int64)
+    for _ in range(max_length):
+        logits = _whisper_decoder(cfg, w, ids, enc)[:, -1, :] @ w["lm_head.kernel"]
+        nxt = logits.argmax(-1)                                  # numpy argmax: first maximum, like tf.argmax
+        ids = np.concatenate([ids, nxt[:, None]], axis=1)
+        if (nxt == cfg.eos_token_id).all():
+            break
+    return ids
+
+
+def whisper_forward(cfg, w, feats, labels):
+    w = {k: np.asarray(v, dtype=np.float64) for k, v in w.items()}
+    labels = np.asarray(labels)
+    enc = _whisper_encoder(cfg, w, feats)
+    B, S = labels.shape
+    ids = np.concatenate([np.full((B, 1), cfg.decoder_start_token_id), labels[:, :-1]], axis=1)
+    dec = _whisper_decoder(cfg, w, ids, enc)
     logits = dec @ w["lm_head.kernel"]
     sl = logits[:, :-1]
     tgt = labels[:, 1:]

@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from oracle import wav2vec2_oracle as WO  # noqa: E402
 from oracle import whisper_oracle as HO  # noqa: E402
-from test_oracle_crosscheck import _w2v_case, _whisper_case  # noqa: E402
+from test_oracle_crosscheck import _generate_case, _head_case, _w2v_case, _whisper_case  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 
@@ -36,6 +36,23 @@ def main():
         os.path.join(OUT, "whisper_small_cfg.npz"), seed=seed, feats=feats.numpy(), labels=labels.numpy(), loss=float(out["loss"]),
         logits_sub=out["logits"].detach().numpy()[:, ::2, ::5],
         **{"grad::" + k: g[k].numpy() for k in ("encoder.conv1.kernel", "lm_head.kernel", "decoder.layers.0.self_attn.k_proj.kernel")})
+    # f-2: the task heads on the Wav2Vec2 trunk and greedy generate()
+    rec = {"seed": seed}
+    for head in ("ctc", "classification"):
+        cfg, w, wave, labels = _head_case(head, seed=seed)
+        out, g = WO.head_loss_and_grads(cfg, w, wave, labels, head)
+        rec["wave"], rec["labels"] = wave.numpy(), labels.numpy()
+        rec[head + "::loss"] = float(out["loss"])
+        rec[head + "::logits_sub"] = out["logits"].detach().numpy().reshape(-1)[::3]
+        k = "lm_head.kernel" if head == "ctc" else "classifier_proj.kernel"
+        rec[head + "::grad::" + k] = g[k].numpy()
+        rec[head + "::grad::fe.conv0.kernel"] = g["fe.conv0.kernel"].numpy()
+    rec["gen_seed"] = 28
+    cfg, w, feats = _generate_case(seed=28)
+    rec["feats"], rec["max_length"] = feats.numpy(), 12
+    with torch.no_grad():
+        rec["generate::ids"] = HO.generate(cfg, w, feats, max_length=12).numpy()
+    np.savez_compressed(os.path.join(OUT, "heads_generate.npz"), **rec)
     print("wrote", os.listdir(OUT))
 
 
