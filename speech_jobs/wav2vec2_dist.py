@@ -15,6 +15,7 @@ if __name__ == "__main__":
     parser.add_argument("--audio_length", type=int, default=32000, help="extension: samples per clip (reference: 32000)")
     parser.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
     parser.add_argument("--resume", type=str, default=None, help="extension (SURVEY f-3): checkpoint file or directory to restore model + optimizer from")
+    parser.add_argument("--no_cuda_graph", action="store_true", help="extension: launch every step kernel by kernel instead of replaying the captured CUDA graph")
     args = parser.parse_args()
     task_type, task_index = train.task_from_tf_config()
     strategy = train.make_strategy()
@@ -23,7 +24,7 @@ if __name__ == "__main__":
     print(f"num_batches: {args.num_batches}")
     start = time.time()
     train.train_wav2vec2(strategy, "pretraining", args.model_size, batch_size=args.batch_size, num_batches=args.num_batches,
-                         precision=args.precision, audio_length=args.audio_length, resume_from=args.resume)
+                         precision=args.precision, audio_length=args.audio_length, resume_from=args.resume, cuda_graph=not args.no_cuda_graph)
     jct = time.time() - start
     print("Training completed.")
     if strategy.rank == 0:

@@ -14,7 +14,7 @@ def main(strategy, args, task_type, task_index):
     start_time = time.time()
     train.train_whisper(strategy, "small" if args.model_type is None else args.model_type, batch_size=args.batch_size,
                         num_batches=args.num_batches, precision=args.precision, from_waveform=args.from_waveform,
-                        resume_from=args.resume)
+                        resume_from=args.resume, cuda_graph=not args.no_cuda_graph)
     jct = time.time() - start_time
     print("Training completed.")
     if strategy.rank == 0:
@@ -30,6 +30,7 @@ if __name__ == "__main__":
     parser.add_argument("--from_waveform", action="store_true",
                         help="extension (SURVEY f-1): feed raw 30 s waveforms through the fused log-mel kernel (W:739-766)")
     parser.add_argument("--resume", type=str, default=None, help="extension (SURVEY f-3): checkpoint file or directory to restore model + optimizer from")
+    parser.add_argument("--no_cuda_graph", action="store_true", help="extension: launch every step kernel by kernel instead of replaying the captured CUDA graph")
     args = parser.parse_args()
     task_type, task_index = train.task_from_tf_config()
     strategy = train.make_strategy()

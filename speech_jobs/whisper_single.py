@@ -17,14 +17,15 @@ if __name__ == "__main__":
     parser.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
     parser.add_argument("--from_waveform", action="store_true", help="feed raw 30 s waveforms through the fused log-mel kernel (W:739-766) instead of ready-made mel features")
     parser.add_argument("--resume", type=str, default=None, help="extension (SURVEY f-3): checkpoint file or directory to restore model + optimizer from")
+    parser.add_argument("--no_cuda_graph", action="store_true", help="extension: launch every step kernel by kernel instead of replaying the captured CUDA graph")
     args = parser.parse_args()
     strategy = train.make_strategy()
     start = time.time()
     if args.legacy_wav2vec2:
         train.train_wav2vec2(strategy, "pretraining", "base", batch_size=args.batch_size, num_batches=args.num_batches,
-                             precision=args.precision, audio_length=80000, legacy=True, resume_from=args.resume)
+                             precision=args.precision, audio_length=80000, legacy=True, resume_from=args.resume, cuda_graph=not args.no_cuda_graph)
     else:
         train.train_whisper(strategy, "small", batch_size=args.batch_size, num_batches=args.num_batches, precision=args.precision,
-                            from_waveform=args.from_waveform, resume_from=args.resume)
+                            from_waveform=args.from_waveform, resume_from=args.resume, cuda_graph=not args.no_cuda_graph)
     print("Training completed.")
     print("jct:", time.time() - start)

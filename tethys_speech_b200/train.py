@@ -11,7 +11,7 @@ import torch
 from . import checkpoint
 from . import wav2vec2 as W2V
 from . import whisper as WH
-from .runtime import Adam, Strategy
+from .runtime import Adam, GraphedTrainStep, Strategy, to_device
 
 WORKSPACE = os.environ.get("TETHYS_WORKSPACE", "/workspace")
 RESULT = os.environ.get("TETHYS_RESULT", "/result")
@@ -67,8 +67,42 @@ def write_jct(jct, task_type, task_index):
         print(f"JCT file not written: {e}")
 
 
+class _StepRunner:
+    """Runs the train step eagerly for the first batches of a given shape (which also allocates the workspace, the optimiser
+    state and the gradient buckets), then captures it as CUDA graph(s) and replays them for every later batch of that shape:
+    same arithmetic, none of the ~300-430 launch gaps of a step (runtime.GraphedTrainStep / GraphedSegments). A batch of another
+    shape (the ragged last batch of an epoch) is run eagerly and the graph is rebuilt afterwards, because the eager call
+    re-plans the workspace the captured kernels point into."""
+
+    def __init__(self, eager, build, enabled, eager_steps=2):
+        self.eager, self.build, self.enabled, self.eager_steps = eager, build, enabled, eager_steps
+        self.graph, self.key, self.count = None, None, 0
+
+    def __call__(self, feats, labels):
+        if not self.enabled:
+            return self.eager(feats, labels)
+        key = (tuple(feats.shape), None if labels is None else tuple(labels.shape))
+        if self.graph is not None and key == self.key:
+            return self.graph(feats, labels)
+        self.graph = None
+        self.count = self.count + 1 if key == self.key else 1
+        self.key = key
+        loss = self.eager(feats, labels)
+        if self.count >= self.eager_steps:
+            try:
+                self.graph = self.build(feats, labels)
+            except Exception as e:      # noqa: BLE001 — a failed capture must not end the run: stay eager
+                print(f"CUDA-graph capture failed ({e}); continuing with eager steps")
+                self.enabled = False
+        return loss
+
+
+def _use_graph(cuda_graph):
+    return bool(cuda_graph) and not os.environ.get("TETHYS_NO_CUDA_GRAPH")
+
+
 def train_whisper(strategy, model_type="small", num_epochs=1, learning_rate=1e-4, batch_size=1, num_batches=40,
-                  precision="bf16", seq_len=3000, from_waveform=False, resume_from=None):
+                  precision="bf16", seq_len=3000, from_waveform=False, resume_from=None, cuda_graph=True):
     """W:894-958. from_waveform=True (extension, SURVEY f-1): the dataset yields raw 30 s waveforms and the fused log-mel kernel
     (extract_fbank_features, W:739-766) produces the model input inside the loop. resume_from (extension, SURVEY f-3): a
     checkpoint file, or a directory whose newest checkpoint is taken, restored into model + optimizer before the loop."""
@@ -80,11 +114,30 @@ def train_whisper(strategy, model_type="small", num_epochs=1, learning_rate=1e-4
     global_batch = batch_size * strategy.num_replicas_in_sync
     dataset = (WH.create_dummy_waveform_dataset(global_batch, audio_seconds=seq_len / 100.0) if from_waveform
                else WH.create_dummy_dataset(global_batch, seq_len=seq_len))
+    world = strategy.num_replicas_in_sync
+
+    def eager(feats, labels):
+        return WH.distributed_train_step(strategy, model, (feats, labels), optimizer)
+
+    def build(feats, labels):
+        dev = model._prog.device
+        f, lab = to_device(feats, torch.float32, dev), to_device(labels, torch.int32, dev)
+        if world > 1:
+            gstep, _ = WH.make_graphed_distributed_step(strategy, model, optimizer, f, lab, warmup=0)
+            return gstep
+        graphed = GraphedTrainStep(lambda batch, aux: WH.train_step(model, batch, optimizer), model, optimizer, (f, lab), None, warmup=0)
+        return lambda a, b: graphed((a, b), None)
+
+    run_step = _StepRunner(eager, build, _use_graph(cuda_graph))
     start_time = time.time()
     for epoch in range(num_epochs):
         print(f"Epoch {epoch + 1}/{num_epochs}")
         for _ in range(num_batches):
             feats, labels = next(dataset)
+            if world > 1 and feats.shape[0] < global_batch:
+                # the ragged last batch of the 50-sample set (W:815) would leave some replicas without samples; every rank skips
+                # it so that the all-reduce stays matched (the reference lets TF run empty per-replica batches)
+                continue
             lo = strategy.rank * batch_size                      # rank r takes samples [r*B, (r+1)*B) of the global batch
             feats, labels = feats[lo:lo + batch_size], labels[lo:lo + batch_size]
             if feats.shape[0] == 0:
@@ -92,7 +145,7 @@ def train_whisper(strategy, model_type="small", num_epochs=1, learning_rate=1e-4
             step_start = time.time()
             if from_waveform:
                 feats = WH.waveform_to_features(feats, device=strategy.local_rank)
-            loss = WH.distributed_train_step(strategy, model, (feats, labels), optimizer)
+            loss = run_step(feats, labels)
             loss_value = float(loss)                              # device sync (the reference's loss.numpy(), W:951)
             _log_step(step, loss_value, start_time, time.time() - step_start)
             step += 1
@@ -102,7 +155,7 @@ def train_whisper(strategy, model_type="small", num_epochs=1, learning_rate=1e-4
 
 
 def train_wav2vec2(strategy, model_type="pretraining", model_size="small", num_epochs=1, learning_rate=3e-5, batch_size=1,
-                   num_batches=5, precision="bf16", audio_length=32000, legacy=False, resume_from=None):
+                   num_batches=5, precision="bf16", audio_length=32000, legacy=False, resume_from=None, cuda_graph=True):
     """V:1263-1376 (legacy=True: the whisper_single.py / stable_jobs variant — WS:1183-1258: 5 s audio, unscaled loss,
     no clipping, Adam eps 1e-7, seed-42 shuffle sampler)."""
     with strategy.scope():
@@ -119,6 +172,28 @@ def train_wav2vec2(strategy, model_type="pretraining", model_size="small", num_e
         t = torch.arange(T).unsqueeze(1)
         k = torch.arange(model.num_negatives).unsqueeze(0)
         neg_legacy = perm[(k - (t + 1)) % T].to(torch.int32).unsqueeze(0).expand(batch_size, -1, -1).contiguous()   # WS:799-839
+    world = strategy.num_replicas_in_sync
+
+    def eager(feats, labels):
+        return W2V.distributed_train_step(strategy, model, (feats, labels), optimizer)
+
+    def build(feats, labels):
+        dev = model._prog.device
+        f = to_device(feats, torch.float32, dev)
+        if world > 1:
+            gstep, _ = W2V.make_graphed_distributed_step(strategy, model, optimizer, f, warmup=0)
+            return lambda a, b: gstep(a)
+        T = model.num_frames(f.shape[1])
+
+        def sample_aux():
+            return {"neg": model._sample_negative_indices(T, f.shape[0])[:, 0, :].contiguous()}     # V:907-937, outside the graph
+
+        graphed = GraphedTrainStep(lambda batch, aux: W2V.train_step(model, batch, optimizer, neg_indices=aux["neg"]), model, optimizer,
+                                   (f, None), sample_aux(), warmup=0)
+        return lambda a, b: graphed((a, None), sample_aux())
+
+    # the graph path covers the pre-training step; the task heads and the legacy step stay eager
+    run_step = _StepRunner(eager, build, _use_graph(cuda_graph) and model_type == "pretraining" and not legacy)
     start_time = time.time()
     for epoch in range(num_epochs):
         print(f"Epoch {epoch + 1}/{num_epochs}")
@@ -132,7 +207,7 @@ def train_wav2vec2(strategy, model_type="pretraining", model_size="small", num_e
                     loss = W2V.legacy_train_step(model, (feats, None), optimizer, neg_indices=neg_legacy)
                     loss = strategy.reduce("SUM", loss)
                 else:
-                    loss = W2V.distributed_train_step(strategy, model, (feats, labels), optimizer)
+                    loss = run_step(feats, labels)
                 try:
                     loss_value = float(loss)
                 except Exception:
