@@ -1,18 +1,22 @@
 // K9 — tcgen05 GEMM engine (bf16 in, fp32 accumulate in TMEM, fused epilogue), persistent and warp-specialised.
 //
 // grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, then m, batch,
-// K-split) so that neighbouring CTAs share the same A rows in L2. Roles:
-//   warp 0    : TMA producer   (cp.async.bulk.tensor 4D boxes -> 128B-swizzled smem ring, mbarrier tx)
-//   warp 1    : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, kind::f16)
-//   warps 2-5 : epilogue       (tcgen05.ld TMEM -> registers -> warp-private smem transpose -> coalesced global I/O)
+// K-split) so that neighbouring CTAs share the same A rows in L2. Roles (320 threads):
+//   warp 0    : TMA producer   (cp.async.bulk.tensor 4D boxes -> 128B-swizzled smem ring of 4 / 6 / 8 stages, mbarrier tx)
+//   warp 1    : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, kind::f16, BN = 64 / 128 / 256)
+//   warps 2-9 : epilogue: warp % 4 = TMEM lane quarter (32 rows), (warp - 2) / 4 = which alternate 128-byte column chunks.
+//               tcgen05.ld -> registers -> alpha, bias, [pre-activation copy], GELU or GELU', dropout, residual in registers
+//               -> 128B-swizzled 32-row staging box in smem -> cp.async.bulk.tensor store (reduce-add for fp32 "C +=").
+//               The pre-activation copy is a second TMA store out of the same box; the activation / dropout math runs
+//               between issuing it and waiting for it. Outputs TMA cannot describe (unaligned C) take a generic path
+//               (32 x 32 transpose through the box, plain coalesced stores).
 // The accumulator is double buffered in TMEM (2 x BN columns): the epilogue of tile i overlaps the main loop of tile
-// i+1 (tmem_full / tmem_empty mbarriers). All epilogue math (alpha, bias, pre-activation copy, exact GELU, dropout,
-// residual, accumulate) runs after the transpose, where a lane owns a fixed column pair and consecutive lanes touch
-// consecutive addresses, so every global load/store of the epilogue is coalesced.
+// i+1 (tmem_full / tmem_empty mbarriers).
 // Split-K (only for fp32 "C += A*B" outputs, i.e. weight gradients with a long reduce dim and few output tiles):
-// each K-slice is its own tile and adds its partial with red.global.add.f32.
+// each K-slice is its own tile and adds its partial with the TMA reduce (or red.global.add.f32 on the generic path).
 // Both operands may be K-major or MN-major (see include/tethys.h); MN-major operands are loaded as
 // 64-wide MN chunks so Dense kernels [in,out], activations for wgrad and V for P.V need no transposes.
+// Tile width and split factor come from a cost model per shape (gemm_tc(): waves x k-blocks x BN x efficiency + tail).
 // Replaces cuBLAS/cuDNN calls behind W:89-92,141,147,167,174,194-205,311-312,545 and V:240-268,
 // 316-319,338-348,362,371,383-398 (+ their autodiff transposes).
 #include <unordered_map>
