@@ -7,7 +7,8 @@
     mel   = tf.tensordot(power, mel_w, 1)                                                   # W:761
     out   = tf.math.log(mel + 1e-6)                                                         # W:764   -> [frames, 80]
 
-TensorFlow is not importable here (parity unpinned); the op semantics restated below are those of TF 2.10
+TensorFlow is not importable here; the call sequence is pinned against the reference function run on oracle/tf_shim.py
+(tests/test_reference_pinning.py::test_logmel_front_end_matches_the_reference_function); the op semantics restated below are those of TF 2.10
 (SURVEY App. A-9): `stft` with pad_end=False -> frames = 1 + (N - 400) // 160; window = PERIODIC Hann
 0.5 - 0.5 cos(2 pi n / 400); rfft of length 400 -> 201 bins; `linear_to_mel_weight_matrix`: HTK mel scale
 1127 ln(1 + f / 700), 82 band edges linear in mel between mel(0) and mel(8000), triangles evaluated in the MEL domain,

@@ -4,7 +4,8 @@ apply_time_mask / apply_feature_mask (/root/reference/speech_jobs/wav2vec2_dist.
 The reference draws the span STARTS with tf.random.uniform(shape) < mask_prob (V:1078, V:1103) — a TF RNG stream that
 cannot be reproduced — and then dilates every start to the right by mask_length positions with a loop of shifted ORs
 (V:1083-1086, V:1108-1111). The integer work pinned here is the dilation; the starts are an input.
-(The reference defines these functions but never calls them — SURVEY D5; parity unpinned)"""
+(The reference defines these functions but never calls them — SURVEY D5. Pinned bit-exactly against the reference functions run on
+oracle/tf_shim.py: tests/test_reference_pinning.py::test_span_masks_match_the_reference_functions.)"""
 import numpy as np
 
 

@@ -143,7 +143,7 @@ def w2v_forward(cfg, w, wave, neg_idx):
     # contrastive V:865-899
     neg_idx = np.asarray(neg_idx)
     temp = cfg.contrastive_logits_temperature
-    logits = np.zeros((B, T, 1 + cfg.num_negatives))
+    logits = np.zeros((B, T, 1 + neg_idx.shape[-1]))      # K = num_negatives, or T for the legacy sampler when T < num_negatives
     for b in range(B):
         for t in range(T):
             nidx = neg_idx[b] if neg_idx.ndim == 2 else neg_idx[b, t]

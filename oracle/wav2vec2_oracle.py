@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE ONLY — PyTorch-CPU restatement (autograd, any float dtype) of the reference's
 Wav2Vec2 pre-training model and train step: speech_jobs/wav2vec2_dist.py (V), wav2vec2_single.py (VS),
-whisper_single.py (WS, the legacy Wav2Vec2-base script).  PARITY UNPINNED — see oracle/tf_ops.py.
+whisper_single.py (WS, the legacy Wav2Vec2-base script).  Structure pinned against the reference's own code on
+oracle/tf_shim.py (tests/test_reference_pinning.py); TF op semantics restated — see the header of oracle/tf_ops.py.
 
 Weights are an ordered dict name -> tensor in Keras layouts (Dense [in,out], Conv1D [k,Cin/g,Cout]);
 RNG-dependent quantities (negative indices, dropout) are explicit inputs (dropout is off: parity runs
@@ -150,8 +151,8 @@ def attention(cfg, w, p, x):
     k = split(T.dense(x, w[p + "k_proj.kernel"], w[p + "k_proj.bias"]))
     v = split(T.dense(x, w[p + "v_proj.kernel"], w[p + "v_proj.bias"]))
     s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
-    a = torch.softmax(s, dim=-1)
-    ctx = (a @ v).transpose(1, 2).reshape(B, L, H)
+    a = T.q(torch.softmax(s, dim=-1))          # T.q: identity except under the tests' bf16-storage emulation
+    ctx = T.q((a @ v).transpose(1, 2).reshape(B, L, H))
     return T.dense(ctx, w[p + "out_proj.kernel"], w[p + "out_proj.bias"])
 
 
@@ -161,19 +162,24 @@ def encoder(cfg, w, h):
     for l in range(cfg.num_hidden_layers):
         p = f"encoder.layers.{l}."
         a_in = T.layer_norm(h, w[p + "attention_layer_norm.gamma"], w[p + "attention_layer_norm.beta"], eps)
-        h = h + attention(cfg, w, p + "attention.", a_in)
+        h = T.q(h + attention(cfg, w, p + "attention.", a_in))
         f_in = T.layer_norm(h, w[p + "feed_forward_layer_norm.gamma"], w[p + "feed_forward_layer_norm.beta"], eps)
         f = T.gelu(T.dense(f_in, w[p + "feed_forward.intermediate_dense.kernel"],
                            w[p + "feed_forward.intermediate_dense.bias"]))
-        h = h + T.dense(f, w[p + "feed_forward.output_dense.kernel"], w[p + "feed_forward.output_dense.bias"])
+        h = T.q(h + T.dense(f, w[p + "feed_forward.output_dense.kernel"], w[p + "feed_forward.output_dense.bias"]))
     return h
 
 
-def quantizer(cfg, w, h):
+def quantizer(cfg, w, h, code_indices=None, legacy=False):
     """Wav2Vec2Quantizer.call — V:581-667: hard nearest-neighbour VQ. argmin (first minimum, int64),
     one-hot @ codebook; perplexity from the code histogram. The distance uses the literal
     sum((z-e)^2) over the group dim in the tensor's dtype, summed sequentially in index order so that
-    the CUDA kernel can reproduce the fp32 rounding exactly."""
+    the CUDA kernel can reproduce the fp32 rounding exactly.
+    code_indices [G,B,L] int64 (tests only): replaces the argmin result. The argmin is a discontinuous integer
+    decision; a reduced-precision run may legitimately pick a different near-tie code, after which every
+    downstream quantity is a different (equally valid) function. Injecting the run's own indices lets the
+    oracle evaluate the SAME function, so that loss and gradients stay comparable (the indices themselves are
+    checked bit-exactly against an argmin on the run's own quantiser input)."""
     B, L, _ = h.shape
     G, V = cfg.num_codevector_groups, cfg.num_codevectors_per_group
     z = T.dense(h, w["quantizer.projection.kernel"], w["quantizer.projection.bias"])
@@ -189,10 +195,14 @@ def quantizer(cfg, w, h):
         for j in range(gd):                                                 # fixed sequential order
             dist = dist + sq[..., j]
         idx = torch.argmin(dist, dim=-1)                                     # first min on ties (A-10)
+        if code_indices is not None:
+            idx = code_indices[gi].to(torch.long)
         onehot = torch.nn.functional.one_hot(idx, V).to(h.dtype)
-        quantized.append(onehot @ cb[gi])
+        quantized.append(T.q(onehot @ cb[gi]))
         indices.append(idx)
-        avg = onehot.mean(dim=(0, 1)).clamp(1e-10, 1.0)
+        avg = onehot.mean(dim=(0, 1))
+        if not legacy:                    # V:656 clips to [1e-10, 1]; the legacy script (WS:651-653) does not — a ~1e-9 relative
+            avg = avg.clamp(1e-10, 1.0)   # difference of the loss value through the unused codes (no gradient either way)
         perps.append(torch.exp(-(avg * torch.log(avg + 1e-10)).sum()))
     q = torch.cat(quantized, dim=-1)
     return q, torch.stack(indices, 0), torch.stack(perps).mean(), z
@@ -222,9 +232,11 @@ def negative_indices_from_random(random_ints, num_negatives):
 
 def legacy_negative_indices(seq_len, perm, num_negatives):
     """Legacy sampler of whisper_single.py — WS:789-839: perm = tf.random.shuffle(range(T), seed=42)
-    (injected); neg[t, k] = perm[(k - (t+1)) mod T]. Returns [T, num_negatives] (same for all b)."""
+    (injected); neg[t, k] = perm[(k - (t+1)) mod T]. Returns [T, min(num_negatives, T)] (same for all b): the reference
+    slices the rolled [B, T] index row with [:, :num_negatives] (WS:821-823), so a sequence shorter than num_negatives
+    yields only T negatives per step (pinned against the reference in tests/test_reference_pinning.py)."""
     t = torch.arange(seq_len).unsqueeze(1)
-    k = torch.arange(num_negatives).unsqueeze(0)
+    k = torch.arange(min(num_negatives, seq_len)).unsqueeze(0)
     return perm[(k - (t + 1)) % seq_len].to(torch.int32)
 
 
@@ -247,9 +259,9 @@ def contrastive_loss(cfg, ps, pq, neg_idx):
     return logits, loss
 
 
-def forward(cfg, w, wave, neg_idx):
+def forward(cfg, w, wave, neg_idx, code_indices=None, legacy=False):
     """Wav2Vec2ForPreTraining.call(training=True) + the loss of the step — V:768-825, V:841-863,
-    V:1202-1220."""
+    V:1202-1220. code_indices: see quantizer()."""
     out = {}
     ef = feature_extractor(cfg, w, wave)
     out["extract_features"] = ef
@@ -257,7 +269,7 @@ def forward(cfg, w, wave, neg_idx):
                       w["feature_projection_layer_norm.gamma"], w["feature_projection_layer_norm.beta"],
                       cfg.layer_norm_eps)
     out["hidden_states_in"] = hs
-    q, idx, perp, z = quantizer(cfg, w, hs)
+    q, idx, perp, z = quantizer(cfg, w, hs, code_indices, legacy)
     out["quantized_features"], out["code_indices"], out["codevector_perplexity"] = q, idx, perp
     enc = encoder(cfg, w, hs)
     out["last_hidden_state"] = enc
@@ -271,10 +283,10 @@ def forward(cfg, w, wave, neg_idx):
     return out
 
 
-def loss_and_grads(cfg, w, wave, neg_idx, loss_div=1.0):
+def loss_and_grads(cfg, w, wave, neg_idx, loss_div=1.0, code_indices=None, legacy=False):
     """tape.gradient(scaled_loss, trainable_variables) with None -> zeros — V:1231-1240."""
     ws = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in w.items())
-    out = forward(cfg, ws, wave, neg_idx)
+    out = forward(cfg, ws, wave, neg_idx, code_indices, legacy)
     scaled = out["loss"] / loss_div
     grads = torch.autograd.grad(scaled, list(ws.values()), allow_unused=True)
     g = OrderedDict((k, (torch.zeros_like(v) if gi is None else gi)) for (k, v), gi in zip(ws.items(), grads))
@@ -282,13 +294,14 @@ def loss_and_grads(cfg, w, wave, neg_idx, loss_div=1.0):
 
 
 def train_step(cfg, w, m, v, t, wave, neg_idx, lr=3e-5, eps=1e-8, legacy=False, num_replicas=1,
-               peer_grads=None):
+               peer_grads=None, code_indices=None):
     """One optimiser step, in place on (w, m, v).
     new  (V:1186-1260 / VS:1119-1176): loss/N -> grads -> clip_by_global_norm(1.0) locally ->
          [all-reduce SUM over replicas] -> per-variable clipnorm 1.0 -> Adam(lr, eps=1e-8).
     legacy (WS:1143-1180 / SV:1143-1190): plain loss, no clipping, Adam(3e-5, eps=1e-7).
     peer_grads: list of other replicas' (already locally clipped) gradient dicts, for the N>1 oracle."""
-    out, g = loss_and_grads(cfg, w, wave, neg_idx, loss_div=1.0 if legacy else float(num_replicas))
+    out, g = loss_and_grads(cfg, w, wave, neg_idx, loss_div=1.0 if legacy else float(num_replicas),
+                            code_indices=code_indices, legacy=legacy)
     names = list(w.keys())
     grads = [g[k] for k in names]
     if not legacy:

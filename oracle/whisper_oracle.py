@@ -1,5 +1,6 @@
 """TEST INFRASTRUCTURE ONLY — PyTorch-CPU restatement (autograd, any float dtype) of the reference's Whisper
-encoder-decoder model and train step: speech_jobs/whisper_dist.py (W).  PARITY UNPINNED — see oracle/tf_ops.py.
+encoder-decoder model and train step: speech_jobs/whisper_dist.py (W).  Structure pinned against the reference's own code on
+oracle/tf_shim.py (tests/test_reference_pinning.py); TF op semantics restated — see the header of oracle/tf_ops.py.
 
 Bug-compatible on purpose: anti-causal decoder mask with fp32 -1e9 absorption (C-1), double label
 shift (C-2), un-normalised gradient SUM across replicas (C-3), query scaling after the bias (C-4), interleaved
@@ -119,7 +120,7 @@ def mha(cfg, w, p, x, kv=None, mask=None):
 
     k = split(T.dense(src, w[p + "k_proj.kernel"], w[p + "k_proj.bias"]), Lk)
     v = split(T.dense(src, w[p + "v_proj.kernel"], w[p + "v_proj.bias"]), Lk)
-    q = split(T.dense(x, w[p + "q_proj.kernel"], w[p + "q_proj.bias"]) * (hd ** -0.5), L)
+    q = split(T.q(T.dense(x, w[p + "q_proj.kernel"], w[p + "q_proj.bias"]) * (hd ** -0.5)), L)
     s = q @ k.transpose(-1, -2)
     if mask is not None:
         add = ((1.0 - mask) * -1e9).to(torch.float32)              # [1,L,Lk]
@@ -129,8 +130,8 @@ def mha(cfg, w, p, x, kv=None, mask=None):
         else:
             s_abs = (s.to(torch.float32) + add).to(s.dtype)        # value TF would hold at the masked entries
             s = torch.where(add != 0, s + (s_abs - s).detach(), s)
-    a = torch.softmax(s, dim=-1)
-    ctx = (a @ v).transpose(1, 2).reshape(B, L, d)
+    a = T.q(torch.softmax(s, dim=-1))          # T.q: identity except under the tests' bf16-storage emulation
+    ctx = T.q((a @ v).transpose(1, 2).reshape(B, L, d))
     return T.dense(ctx, w[p + "out_proj.kernel"], w[p + "out_proj.bias"])
 
 
@@ -147,13 +148,13 @@ def encoder(cfg, w, feats):
     h = T.gelu(T.conv1d_same(x, w["encoder.conv1.kernel"], 1, bias=w["encoder.conv1.bias"]))
     h = T.gelu(T.conv1d_same(h, w["encoder.conv2.kernel"], 2, bias=w["encoder.conv2.bias"]))
     pe = T.sinusoid_pe(cfg.n_ctx, cfg.d_model, h.dtype)
-    h = h + pe[: h.shape[1]].unsqueeze(0)
+    h = T.q(h + pe[: h.shape[1]].unsqueeze(0))
     for l in range(cfg.encoder_layers):
         p = f"encoder.layers.{l}."
         a_in = T.layer_norm(h, w[p + "self_attn_layer_norm.gamma"], w[p + "self_attn_layer_norm.beta"], eps)
-        h = h + mha(cfg, w, p + "self_attn.", a_in)
+        h = T.q(h + mha(cfg, w, p + "self_attn.", a_in))
         f_in = T.layer_norm(h, w[p + "final_layer_norm.gamma"], w[p + "final_layer_norm.beta"], eps)
-        h = h + ffn(w, p + "feed_forward.", f_in)
+        h = T.q(h + ffn(w, p + "feed_forward.", f_in))
     return T.layer_norm(h, w["encoder.layer_norm.gamma"], w["encoder.layer_norm.beta"], eps)
 
 
@@ -163,16 +164,16 @@ def decoder(cfg, w, ids, enc):
     S = ids.shape[1]
     h = w["decoder.embed_tokens.embeddings"][ids.long()]
     pe = T.sinusoid_pe(cfg.max_target_positions, cfg.d_model, h.dtype)
-    h = h + pe[:S].unsqueeze(0)
+    h = T.q(h + pe[:S].unsqueeze(0))
     mask = (1.0 - torch.tril(torch.ones(S, S))).unsqueeze(0)                      # 1 - band_part(ones,-1,0)
     for l in range(cfg.decoder_layers):
         p = f"decoder.layers.{l}."
         x = T.layer_norm(h, w[p + "self_attn_layer_norm.gamma"], w[p + "self_attn_layer_norm.beta"], eps)
-        h = h + mha(cfg, w, p + "self_attn.", x, mask=mask)
+        h = T.q(h + mha(cfg, w, p + "self_attn.", x, mask=mask))
         x = T.layer_norm(h, w[p + "encoder_attn_layer_norm.gamma"], w[p + "encoder_attn_layer_norm.beta"], eps)
-        h = h + mha(cfg, w, p + "encoder_attn.", x, kv=enc)
+        h = T.q(h + mha(cfg, w, p + "encoder_attn.", x, kv=enc))
         x = T.layer_norm(h, w[p + "final_layer_norm.gamma"], w[p + "final_layer_norm.beta"], eps)
-        h = h + ffn(w, p + "feed_forward.", x)
+        h = T.q(h + ffn(w, p + "feed_forward.", x))
     return T.layer_norm(h, w["decoder.layer_norm.gamma"], w["decoder.layer_norm.beta"], eps)
 
 
@@ -183,7 +184,7 @@ def forward(cfg, w, feats, labels):
     dec_ids = torch.cat([start, labels[:, :-1]], dim=1)                            # W:559-563
     enc = encoder(cfg, w, feats)
     dec = decoder(cfg, w, dec_ids, enc)
-    logits = dec @ w["lm_head.kernel"]                                             # W:579 (no bias, untied)
+    logits = T.q(dec @ T.qw(w["lm_head.kernel"]))                                  # W:579 (no bias, untied)
     loss = T.softmax_xent_sparse(logits[:, :-1, :], labels[:, 1:]).mean()          # W:585-600 (pads included)
     return {"loss": loss, "logits": logits, "encoder_last_hidden_state": enc, "last_hidden_state": dec}
 

@@ -1,18 +1,19 @@
 """GPU parity of the Wav2Vec2 pre-training step (through the C-ABI) against the CPU oracle on identical seeded
 inputs and weights. Tolerances (north star): fp32 mode 1e-5 relative, bf16 mode 2e-2 relative; integer outputs
 (VQ code indices) bit-exact. Relative = ||gpu - oracle||_2 / ||oracle||_2 per tensor (oracle evaluated in fp64).
+bf16 gradients: 2e-2, lifted per tensor only to 1.5 x the error an independent CPU emulation of bf16 storage shows for
+that tensor (conftest.check_bf16_grads). Includes BASELINE-size parity (15 s audio) — the oracle needs ~3 s for it.
 Dropout is off in parity runs (TF's RNG stream is not reproducible)."""
 import math
 
 import pytest
 import torch
 
-from conftest import rel_l2, rel_max
+from conftest import BF16_TOL, check_bf16_grads, rel_l2, rel_max
 
 pytestmark = pytest.mark.gpu
 
 FP32_TOL = 1e-5
-BF16_TOL = 2e-2
 
 
 def _setup(size, B, N, precision, seed=0):
@@ -32,14 +33,20 @@ def _setup(size, B, N, precision, seed=0):
     return O, ocfg, w64, model, wave, neg, T
 
 
-def _check_forward_backward(size, B, N, precision, tol, grad_tol):
+def _check_forward_backward(size, B, N, precision, tol, grad_tol=None):
+    """Forward activations, loss and EVERY gradient against the fp64 oracle.
+    The VQ argmin is an integer decision: the GPU's indices are first checked bit-exactly against a sequential argmin over
+    the GPU's own quantiser input (and, in fp32 mode, against the fp64 oracle's indices), then INJECTED into the oracle so
+    that both sides evaluate the same function — in bf16 a near-tie code may legitimately differ from the fp64 argmin, and
+    everything downstream of the codebook lookup would otherwise not be comparable (it used to be silently skipped)."""
+    from oracle import tf_ops
+
     O, ocfg, w64, model, wave, neg, T = _setup(size, B, N, precision)
     out = model(wave.float(), training=True, neg_indices=neg, dropout=False)
     grads = model.gradient()
     torch.cuda.synchronize()
     model._prog.ctx.watchdog()
-    oout, og = O.loss_and_grads(ocfg, w64, wave, neg)
-    # integer work: indices from the GPU's own quantiser input must match the oracle's argmin exactly
+    # integer work: indices from the GPU's own quantiser input must match a sequential fp32 argmin exactly
     zq = model._prog.buffer("quantizer_input").float().cpu()
     G = ocfg.num_codevector_groups
     zq = zq.reshape(B, T, G, -1)
@@ -52,38 +59,44 @@ def _check_forward_backward(size, B, N, precision, tol, grad_tol):
         for j in range(sq.shape[-1]):
             dist = dist + sq[..., j]
         assert torch.equal(torch.argmin(dist, -1), idx_gpu[gi]), f"VQ indices differ in group {gi}"
+    oout, og = O.loss_and_grads(ocfg, w64, wave, neg, code_indices=None if precision == "fp32" else idx_gpu)
     if precision == "fp32":
         assert torch.equal(idx_gpu, oout["code_indices"]), "VQ indices differ from the fp64 oracle"
-    same_codes = torch.equal(idx_gpu, oout["code_indices"])
     errs = {}
-    for key in ("extract_features", "last_hidden_state", "projected_states"):
+    for key in ("extract_features", "last_hidden_state", "projected_states", "quantized_features", "projected_quantized_features",
+                "contrastive_logits"):
         errs[key] = rel_l2(out[key], oout[key])
-    if same_codes:
-        for key in ("quantized_features", "projected_quantized_features", "contrastive_logits"):
-            errs[key] = rel_l2(out[key], oout[key])
-        errs["loss"] = abs(float(out["loss"]) - float(oout["loss"])) / abs(float(oout["loss"]))
-        errs["perplexity"] = abs(float(out["codevector_perplexity"]) - float(oout["codevector_perplexity"])) / float(oout["codevector_perplexity"])
+    errs["loss"] = abs(float(out["loss"]) - float(oout["loss"])) / abs(float(oout["loss"]))
+    errs["perplexity"] = abs(float(out["codevector_perplexity"]) - float(oout["codevector_perplexity"])) / float(oout["codevector_perplexity"])
     bad = {k: v for k, v in errs.items() if not v <= tol}
     assert not bad, f"forward mismatch (tol {tol}): {bad}  all: {errs}"
-    if same_codes:
-        gerrs = {}
-        for name, g in zip(model.variable_names, grads):
-            ref = og[name]
-            if float(ref.abs().max()) == 0.0:
-                assert float(g.abs().max()) == 0.0, f"{name}: expected an all-zero gradient"
-                continue
-            if float(ref.abs().max()) < 1e-12:
-                # mathematically zero (softmax is invariant to the key bias): only rounding noise on both sides,
-                # judged against the scale of the real gradients
-                gscale = max(float(v.abs().max()) for v in og.values())
-                assert float(g.abs().max()) < (1e-5 if precision == "fp32" else 2e-2) * gscale, name
-                continue
-            gerrs[name] = rel_l2(g, ref)
+    gerrs = {}
+    gscale = max(float(v.abs().max()) for v in og.values())
+    for name, g in zip(model.variable_names, grads):
+        ref = og[name]
+        if float(ref.abs().max()) == 0.0:
+            assert float(g.abs().max()) == 0.0, f"{name}: expected an all-zero gradient"
+            continue
+        if float(ref.abs().max()) < 1e-12:
+            # mathematically zero (softmax is invariant to the key bias): only rounding noise on both sides,
+            # judged against the scale of the real gradients
+            assert float(g.abs().max()) < (1e-5 if precision == "fp32" else 2e-2) * gscale, name
+            continue
+        gerrs[name] = rel_l2(g, ref)
+    tag = f"w2v {size} {precision} B={B} N={N}"
+    print(f"[{tag}] fwd errs {errs}")
+    if precision == "fp32":
+        # 1-D tensors (biases, norm scales) are column sums over all B*T frames with heavy cancellation: 3x the bar in fp32
         worst = sorted(gerrs.items(), key=lambda kv: -kv[1])[:5]
-        print(f"[{size} {precision} B={B} N={N}] fwd errs {errs}; worst grads {worst}")
-        # 1-D tensors (biases, norm scales) are column sums over all frames with heavy cancellation: 3x the bar
+        print(f"[{tag}] worst grads {worst}")
         badg = {k: v for k, v in gerrs.items() if not v <= (grad_tol if og[k].dim() > 1 else 3 * grad_tol)}
         assert not badg, f"gradient mismatch (tol {grad_tol}): {len(badg)} tensors; worst {worst}"
+    else:
+        with tf_ops.bf16_storage():
+            _, eg = O.loss_and_grads(ocfg, w64, wave, neg, code_indices=idx_gpu)
+        emu = {k: rel_l2(eg[k], og[k]) for k in gerrs}
+        badg = check_bf16_grads(tag, gerrs, emu)
+        assert not badg, f"bf16 gradients over budget: {badg}"
     return errs
 
 
@@ -101,12 +114,25 @@ def test_w2v_small_fp32_2s():
 
 
 def test_w2v_tiny_bf16_forward_backward():
-    _check_forward_backward("tiny", 2, 3200, "bf16", BF16_TOL, 5e-2)
+    _check_forward_backward("tiny", 2, 3200, "bf16", BF16_TOL)
 
 
 def test_w2v_base_bf16_reference_shape():
     # the reference's own shape: base preset, 2 s of audio (V:1129), per-replica batch 2
-    _check_forward_backward("base", 2, 32000, "bf16", BF16_TOL, 6e-2)
+    _check_forward_backward("base", 2, 32000, "bf16", BF16_TOL)
+
+
+def test_w2v_base_bf16_baseline_size_15s():
+    # BASELINE.json configs[1]: Wav2Vec2-base, 15 s of 16 kHz audio (T = 750), the benchmarked tcgen05 / fused-attention path
+    _check_forward_backward("base", 1, 240000, "bf16", BF16_TOL)
+
+
+def test_w2v_base_fp32_baseline_size_15s():
+    _check_forward_backward("base", 1, 240000, "fp32", FP32_TOL, FP32_TOL)
+
+
+def test_w2v_small_bf16_2s():
+    _check_forward_backward("small", 2, 32000, "bf16", BF16_TOL)
 
 
 def test_w2v_train_step_fp32_matches_oracle_adam():
@@ -138,13 +164,15 @@ def test_w2v_legacy_step_and_sampler_fp32():
     no clipping, Adam eps 1e-7."""
     from tethys_speech_b200 import wav2vec2 as W
 
-    O, ocfg, w64, model, wave, neg, T = _setup("tiny", 2, 3200, "fp32", seed=5)
+    # T = 110 >= num_negatives: with a shorter sequence the reference's [:, :num_negatives] slice (WS:821-823) yields only T
+    # negatives per step (pinned in tests/test_reference_pinning.py); the legacy script itself always runs T = 250
+    O, ocfg, w64, model, wave, neg, T = _setup("tiny", 2, 4400, "fp32", seed=5)
     perm = torch.randperm(T, generator=torch.Generator().manual_seed(42))
     neg_tk = O.legacy_negative_indices(T, perm, ocfg.num_negatives)           # [T,K]
     neg_btk = neg_tk.unsqueeze(0).expand(2, -1, -1).contiguous()
     out = model(wave.float(), training=True, neg_indices=neg_btk, dropout=False)
     grads = model.gradient()
-    oout, og = O.loss_and_grads(ocfg, w64, wave, neg_btk)
+    oout, og = O.loss_and_grads(ocfg, w64, wave, neg_btk, legacy=True)
     assert abs(float(out["loss"]) - float(oout["loss"])) / abs(float(oout["loss"])) < FP32_TOL
     for name, g in zip(model.variable_names, grads):
         if float(og[name].abs().max()) > 1e-12:
@@ -168,7 +196,7 @@ def test_w2v_dropout_is_deterministic_and_unbiased():
 
 def test_w2v_tiny_bf16_batch1_multi_tile_attention():
     # T = 200 frames: two 128-row query tiles / key tiles with ragged tails through the fused attention kernels
-    _check_forward_backward("tiny", 1, 8000, "bf16", BF16_TOL, 6e-2)
+    _check_forward_backward("tiny", 1, 8000, "bf16", BF16_TOL)
 
 
 def test_w2v_too_short_audio_is_an_error():
