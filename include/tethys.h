@@ -51,6 +51,10 @@ const char* ts_last_error(ts_ctx* ctx);
 int ts_watchdog_check(ts_ctx* ctx);
 /* number of kernel-launch sites this context has passed since creation (bench.py's gpu_launches). */
 int64_t ts_launch_count(ts_ctx* ctx);
+/* number of bf16 GEMMs that could not be expressed as TMA tiles (unaligned pointer / leading dimension) and ran on the fp32
+ * CUDA-core engine instead of tcgen05 since creation: a perf cliff, never a numerical one. bench.py reports it; with the
+ * environment variable TETHYS_STRICT_TC=1 such a GEMM returns TS_EUNSUPPORTED instead. */
+int64_t ts_simt_downgrades(ts_ctx* ctx);
 
 /* ---- device-resident step state (CUDA-graph replay of a whole train step) ----------------------------------------------
  * The library keeps {dropout salt, optimizer step} in device memory. Every dropout kernel adds the salt to its seed, and
@@ -60,6 +64,9 @@ int64_t ts_launch_count(ts_ctx* ctx);
  */
 int ts_step_state_set(ts_ctx* ctx, uint64_t salt, int64_t step, void* stream);
 int ts_step_state_advance(ts_ctx* ctx, void* stream);
+/* reads the state back (synchronises the device): checkpoints store it so that a restored run draws the masks the straight
+ * run would have drawn, also when the step is replayed from a CUDA graph. */
+int ts_step_state_get(ts_ctx* ctx, uint64_t* salt, int64_t* step);
 
 /* ---- K9: GEMM with fused epilogue ------------------------------------------------------------
  * Replaces every tf.keras.layers.Dense / tf.matmul / Conv1D-as-GEMM on the path:

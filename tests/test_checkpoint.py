@@ -101,6 +101,36 @@ def test_latest_checkpoint_and_tf_keys(tmp_path):
     assert CK.latest_checkpoint(str(tmp_path)).endswith("model_step-10.tsckpt")
     assert CK.tf_object_key("encoder.layers.0.attention.q_proj.kernel") == \
         "model/encoder/layers/0/attention/q_proj/kernel/.ATTRIBUTES/VARIABLE_VALUE"
+    # files without a save counter (plain save(path, ...)) are found too, ranked by modification time below numbered ones
+    other = tmp_path / "plain"
+    other.mkdir()
+    CK.write_file(str(other / "model_epoch_1.tsckpt"), {}, {})
+    os.utime(str(other / "model_epoch_1.tsckpt"), (1, 1))
+    CK.write_file(str(other / "model_step_50.tsckpt"), {}, {})
+    assert CK.latest_checkpoint(str(other)).endswith("model_step_50.tsckpt")
+    CK.write_file(str(other / "model_step_10-1.tsckpt"), {}, {})
+    assert CK.latest_checkpoint(str(other)).endswith("model_step_10-1.tsckpt")
+
+
+@pytest.mark.gpu
+def test_resume_from_a_directory_written_by_the_train_loop(tmp_path, monkeypatch):
+    """train_wav2vec2 writes its epoch checkpoint through a Checkpoint object (TF-style `<name>-<n>` files); `--resume <dir>` must
+    find it and continue at the saved step instead of restarting from scratch."""
+    from tethys_speech_b200 import train as TR
+    from tethys_speech_b200.runtime import Strategy
+
+    monkeypatch.setattr(TR, "WORKSPACE", str(tmp_path))
+    st = Strategy()
+    TR.train_wav2vec2(st, model_size="tiny", batch_size=2, num_batches=3, audio_length=6400, precision="fp32", cuda_graph=False)
+    d = tmp_path / "checkpoints"
+    files = sorted(os.listdir(d))
+    assert files == ["model_epoch_1-1.tsckpt"], files
+    from tethys_speech_b200 import wav2vec2 as W
+    from tethys_speech_b200.runtime import Adam
+
+    model = W.create_full_model("pretraining", "tiny", precision="fp32", device=0)
+    opt = Adam(learning_rate=3e-5, epsilon=1e-8, clipnorm=1.0)
+    assert TR._maybe_resume(str(d), model, opt) == 3 and opt.iterations == 3
 
 
 # ---------------------------------------------------------------------------------------------------------------------

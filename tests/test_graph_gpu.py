@@ -28,10 +28,10 @@ def test_graphed_step_matches_eager_without_dropout():
     graphed = GraphedTrainStep(fn1, m1, o1, (wave, None), {"neg": neg}, warmup=2)
     for _ in range(3):
         loss_g = graphed((wave, None), {"neg": neg})
-    for _ in range(5):                                   # 2 warm-up + 3 replays on the graphed model
+    for _ in range(3):                                   # the 2 warm-up passes leave no trace: 3 replays == 3 eager steps
         loss_e = W.train_step(m2, (wave, None), o2, neg_indices=neg, dropout=False)
     torch.cuda.synchronize()
-    assert o1.iterations == o2.iterations == 5
+    assert o1.iterations == o2.iterations == 3
     # bf16 training is sensitive to the summation order of the split-K atomics (run-to-run differences of ~1e-3 in the loss
     # after a few steps, eager or graphed alike): compare loosely, the step COUNT (bias correction) is what must be exact
     assert abs(float(loss_g) - float(loss_e)) < 2e-2 * abs(float(loss_e))
@@ -61,9 +61,10 @@ def test_graphed_step_fp32_step_count_is_exact():
     p0 = m2._prog.params.clone()
     graphed = GraphedTrainStep(lambda batch, aux: W.train_step(m1, batch, o1, neg_indices=aux["neg"], dropout=False), m1, o1,
                                (wave, None), {"neg": neg}, warmup=1)
+    assert float((m1._prog.params - p0).abs().max()) == 0.0      # building the graph (1 warm-up pass) did not train
     for _ in range(3):
         graphed((wave, None), {"neg": neg})
-    for _ in range(4):
+    for _ in range(3):
         W.train_step(m2, (wave, None), o2, neg_indices=neg, dropout=False)
     torch.cuda.synchronize()
     upd = (m2._prog.params - p0).norm()

@@ -92,8 +92,10 @@ SYMBOLS = {
     "ts_last_error": (C.c_char_p, [_P]),
     "ts_watchdog_check": (_I, [_P]),
     "ts_launch_count": (_L, [_P]),
+    "ts_simt_downgrades": (_L, [_P]),
     "ts_step_state_set": (_I, [_P, C.c_uint64, _L, _P]),
     "ts_step_state_advance": (_I, [_P, _P]),
+    "ts_step_state_get": (_I, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]),
     "ts_gemm": (_I, [_P, C.POINTER(GemmDesc), _P]),
     "ts_attn_fwd": (_I, [_P, C.POINTER(AttnDesc), _P]),
     "ts_attn_bwd": (_I, [_P, C.POINTER(AttnDesc), _P]),

@@ -178,6 +178,10 @@ def save(path, model, optimizer=None, extra_meta=None):
     tensors = {"model/" + k: v for k, v in gather_variables(_to_host(prog.params), prog.info, names).items()}
     meta = {"format": 1, "kind": type(model).__name__, "precision": "bf16" if prog.params_lp is not None else "fp32",
             "step_seed": int(getattr(model, "_step_seed", 0)), "variables": names}
+    import ctypes as C
+    salt, dstep = C.c_uint64(), C.c_int64()
+    prog.ctx.check(prog.lib.ts_step_state_get(prog.ctx.h, C.byref(salt), C.byref(dstep)))
+    meta["device_salt"] = int(salt.value)          # the dropout salt a CUDA-graph replay of the step reads (ts_step_state_*)
     if optimizer is not None:
         st = optimizer._bind(model)
         for slot in ("m", "v"):
@@ -214,9 +218,12 @@ def restore(path, model, optimizer=None, strict=True):
                 scatter_variables(host, prog.info, {k[len(pre):]: v for k, v in tensors.items() if k.startswith(pre)}, strict=strict)
                 _from_host(host, st[slot])
             optimizer.iterations = int(meta["optimizer"]["iterations"])
-            if optimizer.device_step:   # a captured step reads the count from the library's device state
-                from .runtime import stream_ptr
-                prog.ctx.check(prog.lib.ts_step_state_set(prog.ctx.h, 0, optimizer.iterations, stream_ptr()))
+    # A step captured in a CUDA graph (GraphedTrainStep / GraphedSegments) reads the Adam step count and the dropout salt from
+    # the library's device state, not from the host objects: refresh it unconditionally, so that a restore AFTER the graphs were
+    # built continues with the right bias correction and the masks the straight run would have drawn.
+    from .runtime import stream_ptr
+    step_now = int(optimizer.iterations) if optimizer is not None else 0
+    prog.ctx.check(prog.lib.ts_step_state_set(prog.ctx.h, int(meta.get("device_salt", step_now)), step_now, stream_ptr()))
     return meta
 
 
@@ -249,12 +256,15 @@ class Checkpoint:
 
 
 def latest_checkpoint(checkpoint_dir, prefix=None):
-    """tf.train.latest_checkpoint: the file with the highest save counter in `checkpoint_dir` (None if there is none)."""
-    best, best_n = None, -1
+    """tf.train.latest_checkpoint: the file with the highest save counter (`<prefix>-<n>.tsckpt`, what Checkpoint.save writes)
+    in `checkpoint_dir`; files without a counter (written by plain `save(path, ...)`) rank by modification time below any
+    numbered file. None if the directory holds no checkpoint."""
+    best, best_key = None, None
     for p in glob.glob(os.path.join(checkpoint_dir, "*.tsckpt")):
-        m = re.search(r"-(\d+)\.tsckpt$", p)
-        if not m or (prefix and not os.path.basename(p).startswith(prefix)):
+        if prefix and not os.path.basename(p).startswith(prefix):
             continue
-        if int(m.group(1)) > best_n:
-            best, best_n = p, int(m.group(1))
+        m = re.search(r"-(\d+)\.tsckpt$", p)
+        key = (1, int(m.group(1)), os.path.getmtime(p)) if m else (0, 0, os.path.getmtime(p))
+        if best_key is None or key > best_key:
+            best, best_key = p, key
     return best

@@ -27,6 +27,16 @@ int gemm(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
   if (d->force_engine == 1) return gemm_simt(ctx, d, st);
   if (d->force_engine == 2) return gemm_tc(ctx, d, st);
   if (d->in_dtype == TS_BF16 && gemm_tc_supported(d)) return gemm_tc(ctx, d, st);
+  if (d->in_dtype == TS_BF16) {
+    // a bf16 GEMM that TMA cannot describe (unaligned leading dimension / pointer) runs on the CUDA-core engine: correct but
+    // ~20x slower. Never silent: counted (ts_simt_downgrades) and, under TETHYS_STRICT_TC=1, an error.
+    ctx->simt_downgrades++;
+    static const bool strict = getenv("TETHYS_STRICT_TC") && atoi(getenv("TETHYS_STRICT_TC")) != 0;
+    if (strict)
+      return set_err(ctx, TS_EUNSUPPORTED, "TETHYS_STRICT_TC: bf16 GEMM m=%lld n=%lld k=%lld (lda %lld ldb %lld ldc %lld) is not "
+                     "expressible as TMA tiles and would run on the CUDA-core engine", (long long)d->m, (long long)d->n,
+                     (long long)d->k, (long long)d->lda, (long long)d->ldb, (long long)d->ldc);
+  }
   return gemm_simt(ctx, d, st);
 }
 
@@ -85,8 +95,6 @@ int ts_watchdog_check(ts_ctx* ctx) {
   if (e != cudaSuccess) return ts::set_err(c, TS_ECUDA, "watchdog read failed: %s", cudaGetErrorString(e));
   if (v != 0) {
     cudaMemset(c->d_watchdog, 0, sizeof(int));
-  if (cudaMalloc(&c->d_state, 2 * sizeof(unsigned long long)) != cudaSuccess) { cudaFree(c->d_watchdog); delete c; return TS_ECUDA; }
-  cudaMemset(c->d_state, 0, 2 * sizeof(unsigned long long));
     return ts::set_err(c, TS_EWATCHDOG, "device mbarrier wait timed out (role code %d)", v);
   }
   return TS_OK;
@@ -97,6 +105,11 @@ int64_t ts_launch_count(ts_ctx* ctx) {
   return c ? (int64_t)c->launches : 0;
 }
 
+int64_t ts_simt_downgrades(ts_ctx* ctx) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  return c ? (int64_t)c->simt_downgrades : 0;
+}
+
 __global__ void step_state_set_kernel(unsigned long long* st, unsigned long long salt, unsigned long long step) { st[0] = salt; st[1] = step; }
 __global__ void step_state_advance_kernel(unsigned long long* st) { st[0] += 1ull; st[1] += 1ull; }
 
@@ -105,6 +118,15 @@ int ts_step_state_set(ts_ctx* ctx, uint64_t salt, int64_t step, void* stream) {
   if (!c || step < 0) return TS_EINVAL;
   step_state_set_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(c->d_state, salt, (unsigned long long)step);
   TS_LAUNCH_OK(c);
+  return 0;
+}
+int ts_step_state_get(ts_ctx* ctx, uint64_t* salt, int64_t* step) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c || !salt || !step) return TS_EINVAL;
+  unsigned long long h[2] = {0, 0};
+  TS_CUDA_OK(c, cudaDeviceSynchronize());
+  TS_CUDA_OK(c, cudaMemcpy(h, c->d_state, sizeof(h), cudaMemcpyDeviceToHost));
+  *salt = h[0]; *step = (int64_t)h[1];
   return 0;
 }
 int ts_step_state_advance(ts_ctx* ctx, void* stream) {
@@ -152,7 +174,8 @@ int ts_gemm(ts_ctx* ctx, const ts_gemm_desc* d, void* stream) {
 namespace ts {
 struct Optim {
   Ctx* ctx;
-  Segment* d_segs = nullptr;
+  WorkItem* d_items = nullptr;   // built once here, freed in ts_optim_destroy (no global cache)
+  int nitems = 0;
   int nseg = 0;
   long long arena = 0;
   float* d_sumsq = nullptr;   // [nseg]
@@ -175,10 +198,17 @@ int ts_optim_create(ts_ctx* ctx_, int32_t n, const int64_t* offsets, const int32
   }
   ts::Optim* o = new ts::Optim();
   o->ctx = ctx; o->nseg = n; o->arena = arena_elems;
-  TS_CUDA_OK(ctx, cudaMalloc(&o->d_segs, sizeof(ts::Segment) * n));
-  TS_CUDA_OK(ctx, cudaMemcpy(o->d_segs, h.data(), sizeof(ts::Segment) * n, cudaMemcpyHostToDevice));
-  TS_CUDA_OK(ctx, cudaMalloc(&o->d_sumsq, sizeof(float) * n));
-  TS_CUDA_OK(ctx, cudaMalloc(&o->d_scal, sizeof(float) * 4));
+  const std::vector<ts::WorkItem> items = ts::build_work_items(h);
+  o->nitems = (int)items.size();
+  cudaError_t e = cudaMalloc(&o->d_items, sizeof(ts::WorkItem) * items.size());
+  if (e == cudaSuccess) e = cudaMemcpy(o->d_items, items.data(), sizeof(ts::WorkItem) * items.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&o->d_sumsq, sizeof(float) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&o->d_scal, sizeof(float) * 4);
+  if (e != cudaSuccess) {
+    cudaFree(o->d_items); cudaFree(o->d_sumsq); cudaFree(o->d_scal);
+    delete o;
+    return ts::set_err(ctx, TS_ECUDA, "optim: device allocation failed: %s", cudaGetErrorString(e));
+  }
   *out = reinterpret_cast<ts_optim*>(o);
   return 0;
 }
@@ -186,15 +216,14 @@ int ts_optim_create(ts_ctx* ctx_, int32_t n, const int64_t* offsets, const int32
 void ts_optim_destroy(ts_optim* o_) {
   ts::Optim* o = reinterpret_cast<ts::Optim*>(o_);
   if (!o) return;
-  ts::optim_forget(o->d_segs);
-  cudaFree(o->d_segs); cudaFree(o->d_sumsq); cudaFree(o->d_scal);
+  cudaFree(o->d_items); cudaFree(o->d_sumsq); cudaFree(o->d_scal);
   delete o;
 }
 
 int ts_optim_clip_global(ts_optim* o_, float* grads, float clip, float* norm_out_dev, void* stream) {
   ts::Optim* o = reinterpret_cast<ts::Optim*>(o_);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = ts::grad_sumsq(o->ctx, grads, o->d_segs, o->nseg, o->d_sumsq, st);
+  int rc = ts::grad_sumsq(o->ctx, grads, o->d_items, o->nitems, o->nseg, o->d_sumsq, st);
   if (rc) return rc;
   rc = ts::global_clip_scale(o->ctx, o->d_sumsq, o->nseg, clip, o->d_scal, norm_out_dev ? norm_out_dev : o->d_scal + 1, st);
   if (rc) return rc;
@@ -205,7 +234,7 @@ int ts_optim_global_clip_scale(ts_optim* o_, const float* grads, float clip, flo
   ts::Optim* o = reinterpret_cast<ts::Optim*>(o_);
   cudaStream_t st = (cudaStream_t)stream;
   if (!o || !grads || !scale_out_dev) return TS_EINVAL;
-  int rc = ts::grad_sumsq(o->ctx, grads, o->d_segs, o->nseg, o->d_sumsq, st);
+  int rc = ts::grad_sumsq(o->ctx, grads, o->d_items, o->nitems, o->nseg, o->d_sumsq, st);
   if (rc) return rc;
   return ts::global_clip_scale(o->ctx, o->d_sumsq, o->nseg, clip, scale_out_dev, o->d_scal + 1, st);
 }
@@ -219,7 +248,7 @@ int ts_optim_step(ts_optim* o_, float* params, const float* grads, float* m, flo
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.step = step; a.clipnorm = clipnorm;
   a.pre_scale = nullptr; a.sumsq = nullptr;
   if (clipnorm > 0.f || (fuse_global_clip && global_clip > 0.f)) {
-    int rc = ts::grad_sumsq(o->ctx, grads, o->d_segs, o->nseg, o->d_sumsq, st);
+    int rc = ts::grad_sumsq(o->ctx, grads, o->d_items, o->nitems, o->nseg, o->d_sumsq, st);
     if (rc) return rc;
     a.sumsq = o->d_sumsq;
   }
@@ -228,7 +257,7 @@ int ts_optim_step(ts_optim* o_, float* params, const float* grads, float* m, flo
     if (rc) return rc;
     a.pre_scale = o->d_scal;
   }
-  return ts::adam_step(o->ctx, params, grads, m, v, params_bf16, o->d_segs, o->nseg, a, st);
+  return ts::adam_step(o->ctx, params, grads, m, v, params_bf16, o->d_items, o->nitems, a, st);
 }
 
 int ts_cast_f32_to_bf16(ts_ctx* ctx, const float* src, void* dst, int64_t n, void* stream) {

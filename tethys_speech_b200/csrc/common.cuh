@@ -26,6 +26,7 @@ struct Ctx {
   int* d_watchdog = nullptr;   // device int: set non-zero by a kernel whose mbarrier wait timed out
   void* tmap_cache = nullptr;  // opaque tensor-map cache (gemm_tc.cu)
   unsigned long long launches = 0;  // kernel-launch sites passed (TS_LAUNCH_OK); reported by ts_launch_count
+  unsigned long long simt_downgrades = 0;  // bf16 GEMMs that fell back to the CUDA-core engine (ts_simt_downgrades)
   // device-resident step state {dropout salt, optimizer step}: lets a whole train step be captured in a CUDA graph and still
   // draw fresh dropout masks / use the right Adam bias correction on every replay (ts_step_state_set / _advance)
   unsigned long long* d_state = nullptr;

@@ -1,6 +1,7 @@
 // Internal C++ API of the kernel library (namespace ts). `dt` is the activation dtype (TS_F32 / TS_BF16);
 // parameters, gradients of parameters, statistics and losses are always fp32.
 #pragma once
+#include <vector>
 #include "common.cuh"
 
 namespace ts {
@@ -133,8 +134,11 @@ int zero_rows(Ctx*, int dt, void* x, long long rpb, int row_from, int B, int C, 
 // ---- optim.cu ------------------------------------------------------------------------------------
 // A parameter "segment": rows x cols block with row stride ld inside the flat arena (dense: rows = 1).
 struct Segment { long long offset; int rows, cols; long long ld; };
+// One block's share of a segment (<= 64K elements); built once per optimizer object by build_work_items.
+struct WorkItem { long long start; long long ld; int rows, cols, seg, pad; };
+std::vector<WorkItem> build_work_items(const std::vector<Segment>& segs);
 // per-segment sum of squares of grads -> sumsq[nseg] (fp32, overwritten)
-int grad_sumsq(Ctx*, const float* grads, const Segment* d_segs, int nseg, float* sumsq, cudaStream_t);
+int grad_sumsq(Ctx*, const float* grads, const WorkItem* d_items, int nitems, int nseg, float* sumsq, cudaStream_t);
 // scales[0] = global clip scale from sum(sumsq) (clip_by_global_norm, V:1243) or 1
 int global_clip_scale(Ctx*, const float* sumsq, int nseg, float clip, float* scale_out, float* norm_out,
                       cudaStream_t);
@@ -147,8 +151,7 @@ struct AdamArgs {
   const float* sumsq;                        // per segment sum of squares of the (unscaled) grads, or NULL
 };
 int adam_step(Ctx*, float* params, const float* grads, float* m, float* v, void* params_bf16 /*or NULL*/,
-              const Segment* d_segs, int nseg, const AdamArgs& a, cudaStream_t);
-void optim_forget(const Segment* d_segs);
+              const WorkItem* d_items, int nitems, const AdamArgs& a, cudaStream_t);
 int scale_inplace(Ctx*, float* x, long long n, const float* scale_dev, float scale_host, cudaStream_t);
 
 }  // namespace ts

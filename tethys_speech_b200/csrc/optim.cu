@@ -7,26 +7,13 @@
 
 namespace ts {
 
-struct WorkItem { long long start; long long ld; int rows, cols, seg, pad; };
-
-struct ItemCache {
-  const Segment* key = nullptr;
-  int nseg = 0;
-  WorkItem* d_items = nullptr;
-  int nitems = 0;
-};
-static ItemCache g_items[8];
-
-static int get_items(Ctx* ctx, const Segment* d_segs, int nseg, WorkItem** out, int* nitems, cudaStream_t st) {
-  for (auto& c : g_items)
-    if (c.key == d_segs && c.nseg == nseg) { *out = c.d_items; *nitems = c.nitems; return 0; }
-  std::vector<Segment> h(nseg);
-  TS_CUDA_OK(ctx, cudaMemcpyAsync(h.data(), d_segs, sizeof(Segment) * nseg, cudaMemcpyDeviceToHost, st));
-  TS_CUDA_OK(ctx, cudaStreamSynchronize(st));
+// Work items are built ONCE per optimizer object (ts_optim_create) and owned by it: no process-global cache, nothing to evict
+// under a captured CUDA graph, no host synchronisation on the step path.
+std::vector<WorkItem> build_work_items(const std::vector<Segment>& segs) {
   std::vector<WorkItem> items;
   const long long chunk = 65536;
-  for (int s = 0; s < nseg; ++s) {
-    const Segment& sg = h[s];
+  for (int s = 0; s < (int)segs.size(); ++s) {
+    const Segment& sg = segs[s];
     if (sg.rows == 1) {
       for (long long c0 = 0; c0 < sg.cols; c0 += chunk)
         items.push_back({sg.offset + c0, sg.ld, 1, (int)std::min<long long>(chunk, sg.cols - c0), s, 0});
@@ -36,20 +23,7 @@ static int get_items(Ctx* ctx, const Segment* d_segs, int nseg, WorkItem** out, 
         items.push_back({sg.offset + (long long)r0 * sg.ld, sg.ld, std::min(rpi, sg.rows - r0), sg.cols, s, 0});
     }
   }
-  ItemCache* slot = nullptr;
-  for (auto& c : g_items) if (!c.key) { slot = &c; break; }
-  if (!slot) { slot = &g_items[0]; cudaFree(slot->d_items); }
-  TS_CUDA_OK(ctx, cudaMalloc(&slot->d_items, sizeof(WorkItem) * items.size()));
-  TS_CUDA_OK(ctx, cudaMemcpyAsync(slot->d_items, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice, st));
-  TS_CUDA_OK(ctx, cudaStreamSynchronize(st));
-  slot->key = d_segs; slot->nseg = nseg; slot->nitems = (int)items.size();
-  *out = slot->d_items; *nitems = slot->nitems;
-  return 0;
-}
-
-void optim_forget(const Segment* d_segs) {
-  for (auto& c : g_items)
-    if (c.key == d_segs) { cudaFree(c.d_items); c = ItemCache(); }
+  return items;
 }
 
 __global__ void zero_f32_kernel(float* p, int n) {
@@ -78,10 +52,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   if (threadIdx.x == 0) atomicAdd(&sumsq[it.seg], s);
 }
 
-int grad_sumsq(Ctx* ctx, const float* grads, const Segment* d_segs, int nseg, float* sumsq, cudaStream_t st) {
-  WorkItem* items; int n;
-  int rc = get_items(ctx, d_segs, nseg, &items, &n, st);
-  if (rc) return rc;
+int grad_sumsq(Ctx* ctx, const float* grads, const WorkItem* items, int n, int nseg, float* sumsq, cudaStream_t st) {
   zero_f32_kernel<<<cdiv(nseg, 256), 256, 0, st>>>(sumsq, nseg);
   sumsq_kernel<<<n, 256, 0, st>>>(grads, items, sumsq);
   TS_LAUNCH_OK(ctx);
@@ -164,12 +135,9 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
-int adam_step(Ctx* ctx, float* params, const float* grads, float* m, float* v, void* params_bf16, const Segment* d_segs,
-              int nseg, const AdamArgs& a, cudaStream_t st) {
+int adam_step(Ctx* ctx, float* params, const float* grads, float* m, float* v, void* params_bf16, const WorkItem* items, int n,
+              const AdamArgs& a, cudaStream_t st) {
   TS_REQUIRE(ctx, a.step >= 0, TS_EINVAL, "adam: step must be >= 1 (or 0 = take it from the device step state)");
-  WorkItem* items; int n;
-  int rc = get_items(ctx, d_segs, nseg, &items, &n, st);
-  if (rc) return rc;
   const double lr_t = a.step >= 1 ? (double)a.lr * sqrt(1.0 - pow((double)a.beta2, a.step)) / (1.0 - pow((double)a.beta1, a.step)) : 0.0;
   adam_kernel<<<n, 256, 0, st>>>(params, grads, m, v, (bf16*)params_bf16, items, (float)lr_t, 1.f - a.beta1, 1.f - a.beta2,
                                  a.eps, a.clipnorm, a.pre_scale, a.sumsq, a.lr, a.step >= 1 ? nullptr : ctx->d_state);

@@ -411,13 +411,25 @@ class GraphedTrainStep:
         self.static_batch = tuple(None if t is None else to_device(t, t.dtype if isinstance(t, torch.Tensor) else None, dev).clone()
                                   for t in example_batch)
         self.static_aux = {k: v.to(dev).clone() for k, v in (example_aux or {}).items()}
+        # `warmup` eager passes allocate the workspace / optimizer state and set kernel attributes. They are REAL steps on the
+        # example batch, so parameters, Adam moments, the iteration count and the dropout seed are snapshotted first and put
+        # back afterwards: building the graph has no training side effect.
+        st = optimizer._bind(model)
+        snap = (prog.params.clone(), st["m"].clone(), st["v"].clone(), optimizer.iterations, getattr(model, "_step_seed", None))
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(warmup):            # allocates the workspace / optimizer state, sets kernel attributes
+            for _ in range(warmup):
                 step_fn(self.static_batch, self.static_aux)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        if warmup:
+            prog.params.copy_(snap[0]); st["m"].copy_(snap[1]); st["v"].copy_(snap[2])
+            optimizer.iterations = snap[3]
+            if snap[4] is not None:
+                model._step_seed = snap[4]
+            prog.weights_synced = False
+            prog.sync_weights()
         self.ctx.check(self.ctx.lib.ts_step_state_set(self.ctx.h, 0, int(optimizer.iterations), stream_ptr()))
         optimizer.device_step = True
         l0 = self.ctx.lib.ts_launch_count(self.ctx.h)

@@ -3,6 +3,7 @@ reference (W:894-958, W:990-1058; V:1263-1376, V:1380-1487; VS:1180-1292; WS:118
 Same flags, same `Step N, Loss: x.xxxx, Time: …` log line, same jct file; hard-coded /workspace and /result paths are
 overridable (TETHYS_WORKSPACE / TETHYS_RESULT) and failures to write them are non-fatal, as SURVEY §5.6 asks."""
 import json
+import re
 import os
 import time
 
@@ -29,12 +30,25 @@ def _log_step(step, loss_value, start_time, step_duration):
     print(f"Step {step}, Loss: {loss_value:.4f}, Time: {time.strftime('%H:%M:%S')} (경과: {elapsed:.2f}초, 스텝 시간: {step_duration:.2f}초)", flush=True)
 
 
+_CHECKPOINTS = {}
+
+
 def _save_checkpoint(model, name, optimizer=None):
-    """checkpoint.save(os.path.join(checkpoint_dir, name)) — V:1341, V:1362, W:956: model + optimizer slots."""
+    """checkpoint.save(os.path.join(checkpoint_dir, name)) — V:1341, V:1362, W:956: model + optimizer slots. Goes through one
+    checkpoint.Checkpoint object per model, like the reference's tf.train.Checkpoint (V:1286-1288): files are numbered by its
+    save counter (`model_step_50-1.tsckpt`, `model_epoch_1-2.tsckpt`), which is what `--resume <dir>` / latest_checkpoint
+    orders by."""
     try:
         d = os.path.join(WORKSPACE, "checkpoints")
         os.makedirs(d, exist_ok=True)
-        return checkpoint.save(os.path.join(d, name + ".tsckpt"), model, optimizer)
+        ck = _CHECKPOINTS.get(id(model))
+        if ck is None or ck.optimizer is not optimizer:
+            ck = _CHECKPOINTS[id(model)] = checkpoint.Checkpoint(model=model, optimizer=optimizer)
+            last = checkpoint.latest_checkpoint(d)
+            if last:                                  # continue the numbering of an earlier (resumed) run
+                m = re.search(r"-(\d+)\.tsckpt$", last)
+                ck.save_counter = int(m.group(1)) if m else 0
+        return ck.save(os.path.join(d, name))
     except Exception as e:  # the reference's checkpoint dir is container-specific
         print(f"checkpoint not written: {e}")
         return None
