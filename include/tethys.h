@@ -55,6 +55,10 @@ int64_t ts_launch_count(ts_ctx* ctx);
  * CUDA-core engine instead of tcgen05 since creation: a perf cliff, never a numerical one. bench.py reports it; with the
  * environment variable TETHYS_STRICT_TC=1 such a GEMM returns TS_EUNSUPPORTED instead. */
 int64_t ts_simt_downgrades(ts_ctx* ctx);
+/* debug: `device_buf` (>= 16 * grid uint64, or NULL to stop) receives up to 16 %globaltimer stamps per CTA from every following tcgen05
+ * GEMM launch: 0 entry, 1 setup done, 2 first operands landed, 3 first tile issued, 4 last MMA issued, 5/6 accumulator ready
+ * (a tile / the last tile), 7 stores drained. tools/gemm_trace.py turns them into a head / main loop / tail breakdown. */
+int ts_debug_gemm_trace(ts_ctx* ctx, void* device_buf);
 
 /* ---- device-resident step state (CUDA-graph replay of a whole train step) ----------------------------------------------
  * The library keeps {dropout salt, optimizer step} in device memory. Every dropout kernel adds the salt to its seed, and
@@ -103,7 +107,7 @@ typedef struct {
   int64_t ldr, r_bs1, r_bs2;
   int32_t accumulate; /* 1: C += result (only with out_dtype TS_F32, no act/residual) */
   void* c_preact;     /* optional second output: value before act (same dtype/ld as C) or NULL */
-  int32_t force_engine; /* 0 auto, 1 force CUDA-core engine, 2 force tcgen05 (error if impossible) */
+  int32_t force_engine; /* 0 auto, 1 force CUDA-core engine, 2 force tcgen05 (error if impossible), 3 force tcgen05 CTA-pair (cta_group::2) tiles */
   float drop;           /* dropout rate applied after act (0 = off); keep-mask = hash(seed, element offset in C) */
   uint64_t seed;
   int64_t bias_bs1;     /* bias element stride per batch1 index (grouped conv: one bias slice per group) */

@@ -93,6 +93,7 @@ SYMBOLS = {
     "ts_watchdog_check": (_I, [_P]),
     "ts_launch_count": (_L, [_P]),
     "ts_simt_downgrades": (_L, [_P]),
+    "ts_debug_gemm_trace": (_I, [_P, _P]),
     "ts_step_state_set": (_I, [_P, C.c_uint64, _L, _P]),
     "ts_step_state_advance": (_I, [_P, _P]),
     "ts_step_state_get": (_I, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]),

@@ -25,7 +25,7 @@ void tmap_cache_free(Ctx* ctx);
 
 int gemm(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
   if (d->force_engine == 1) return gemm_simt(ctx, d, st);
-  if (d->force_engine == 2) return gemm_tc(ctx, d, st);
+  if (d->force_engine == 2 || d->force_engine == 3) return gemm_tc(ctx, d, st);
   if (d->in_dtype == TS_BF16 && gemm_tc_supported(d)) return gemm_tc(ctx, d, st);
   if (d->in_dtype == TS_BF16) {
     // a bf16 GEMM that TMA cannot describe (unaligned leading dimension / pointer) runs on the CUDA-core engine: correct but
@@ -103,6 +103,13 @@ int ts_watchdog_check(ts_ctx* ctx) {
 int64_t ts_launch_count(ts_ctx* ctx) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   return c ? (int64_t)c->launches : 0;
+}
+
+int ts_debug_gemm_trace(ts_ctx* ctx, void* device_buf) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c) return TS_EINVAL;
+  c->gemm_trace = device_buf;
+  return 0;
 }
 
 int64_t ts_simt_downgrades(ts_ctx* ctx) {

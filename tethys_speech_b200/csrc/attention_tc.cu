@@ -763,9 +763,14 @@ static int fill_params(Ctx* ctx, const ts_attn_desc* d, AttnParams* p) {
   return 0;
 }
 
+int attn_fwd2(Ctx* ctx, const ts_attn_desc* d, uint32_t drop_thr, float inv_keep, cudaStream_t st);   // attention_fwd2.cu
+
 int attn_fwd(Ctx* ctx, const ts_attn_desc* d, cudaStream_t st) {
   AttnParams p;
   TS_TRY_RC(fill_params(ctx, d, &p));
+  // second-generation forward (persistent, two query tiles in flight); TETHYS_ATTN_FWD=1 keeps the first one for A/B runs
+  static const bool gen1 = getenv("TETHYS_ATTN_FWD") && atoi(getenv("TETHYS_ATTN_FWD")) == 1;
+  if (!gen1) return attn_fwd2(ctx, d, p.drop_thr, p.inv_keep, st);
   CUtensorMap tq, tk, tv;
   TS_TRY_RC(head_tmap(ctx, &tq, d->q, d->q_ld, d->q_bs, d->tq, d->heads, d->batch));
   TS_TRY_RC(head_tmap(ctx, &tk, d->k, d->kv_ld, d->kv_bs, d->tk, d->heads, d->batch));

@@ -30,6 +30,7 @@ struct Ctx {
   // device-resident step state {dropout salt, optimizer step}: lets a whole train step be captured in a CUDA graph and still
   // draw fresh dropout masks / use the right Adam bias correction on every replay (ts_step_state_set / _advance)
   unsigned long long* d_state = nullptr;
+  void* gemm_trace = nullptr;  // debug: device buffer [grid x 8] of globaltimer stamps written by gemm_tc_kernel (ts_debug_gemm_trace)
 };
 
 int set_err(Ctx* c, int code, const char* fmt, ...);

@@ -43,7 +43,15 @@ struct EpiParams {
   int mt, nt, nb, splitk, kb_per_split, total_tiles;  // persistent tile schedule
   int use_red;                                        // fp32 output: add with red.global (split-K partials)
   int tma_epi;                                        // C (and c_pre) are TMA-storable: swizzled smem box + bulk tensor store
+  unsigned long long* trace;                          // debug (ts_debug_gemm_trace): 16 globaltimer stamps per CTA, else NULL
 };
+__device__ __forceinline__ void trace_stamp(const EpiParams& p, int slot) {
+  if (p.trace) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[blockIdx.x * 16 + slot] = t;
+  }
+}
 
 constexpr int BM = 128;
 constexpr int BK = 64;
@@ -51,22 +59,25 @@ constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quarter,
 constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kStageBytesPerWarp = 4096;     // one 32-row x 128-byte swizzled box per epilogue warp
 
-template <int BN> struct TcCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+// CTAS = 1: one CTA owns a 128 x BN tile. CTAS = 2: a CTA pair (cluster of two, cta_group::2) owns a 256 x BN tile; each CTA
+// stages its own 128 rows of A and its own BN/2 rows of B, the leader's single thread issues 256-row UMMAs that read both
+// CTAs' smem and write both CTAs' TMEM, so per FLOP each SM reads half as much B from smem / L2.
+template <int BN, int CTAS> struct TcCfg {
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (BN / CTAS) * BK * 2;
+  static constexpr int kStages = (196608 / (kABytes + kBBytes)) > 8 ? 8 : (196608 / (kABytes + kBBytes));
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmem = kStages * kStageBytes + kEpiWarps * kStageBytesPerWarp + 1024 /*align slack*/ + 128 /*barriers*/;
+  static constexpr int kSmem = kStages * kStageBytes + kEpiWarps * kStageBytesPerWarp + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = 2 * BN;                     // two accumulator stages (power of two >= 32)
 };
 
 struct TileCoord { int m0, n0, b1, b2, kb0, kb1; };
-__device__ __forceinline__ TileCoord decode_tile(const EpiParams& p, int t, int BN_) {
+__device__ __forceinline__ TileCoord decode_tile(const EpiParams& p, int t, int BN_, int BM_) {
   TileCoord tc;
   const int n = t % p.nt; t /= p.nt;
   const int m = t % p.mt; t /= p.mt;
   const int b = t % p.nb; t /= p.nb;
-  tc.m0 = m * BM; tc.n0 = n * BN_;
+  tc.m0 = m * BM_; tc.n0 = n * BN_;
   tc.b1 = b % p.nb1; tc.b2 = b / p.nb1;
   const int nkb = (p.k + BK - 1) / BK;
   tc.kb0 = t * p.kb_per_split;
@@ -150,12 +161,18 @@ __device__ __forceinline__ void epi_act_drop(float (&v)[NV], const EpiParams& p,
   }
 }
 
-template <int BN, int AMAJ, int BMAJ, typename OutT>
+template <int BN, int AMAJ, int BMAJ, typename OutT, int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_p,
                const EpiParams p, int* watchdog) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, CTAS>;
+  static_assert(CTAS == 1 || (CTAS == 2 && BN >= 128), "a CTA pair needs >= 64 B rows per CTA");
+  // CTA pair: rank 0 (leader) issues the MMAs; tiles are walked per cluster
+  const uint32_t rank = (CTAS == 2) ? ptx::cluster_ctarank() : 0u;
+  const int tile_first = (CTAS == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = (CTAS == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int BMT = BM * CTAS;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms need 1024 B alignment
@@ -169,68 +186,92 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) trace_stamp(p, 0);   // kernel entry
 
   if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tma_a);
+    ptx::prefetch_tmap(&tma_b);
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full_bar[s], 1);
-      ptx::mbar_init(&tmem_empty_bar[s], kEpiWarps);
+      ptx::mbar_init(&tmem_empty_bar[s], kEpiWarps * CTAS);   // pair: the leader's barrier collects both CTAs' epilogue warps
     }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    ptx::tmem_relinquish();
+    if (CTAS == 2) { ptx::tmem_alloc_2cta(tmem_slot, Cfg::kTmemCols); ptx::tmem_relinquish_2cta(); }
+    else { ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  // The producer warp of a (leader) CTA needs nothing but the barriers its own lane 0 has just initialised: it only ARRIVES at the
+  // setup barrier and starts the first TMA loads while warp 1 is still allocating TMEM (the head of a launch is not overlapped
+  // by anything else). Everyone else waits; a peer CTA's producer signals the LEADER's barriers and so must wait for the cluster.
+  const bool early = (warp == 0 && rank == 0);
+  if (CTAS == 2) {
+    ptx::cluster_arrive();
+    if (!early) ptx::cluster_wait();
+  } else {
+    if (early) ptx::named_bar_arrive(1, kThreads);
+    else ptx::named_bar_sync(1, kThreads);
+  }
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = early ? 0u : *tmem_slot;   // warp 0 never touches TMEM
+  if (threadIdx.x == 32) trace_stamp(p, 1);   // setup done (barriers, TMEM, CTA / cluster sync)
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      ptx::prefetch_tmap(&tma_a);
-      ptx::prefetch_tmap(&tma_b);
       uint32_t it = 0;
       bool ok = true;
-      for (int t = blockIdx.x; t < p.total_tiles && ok; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t, BN);
+      for (int t = tile_first; t < p.total_tiles && ok; t += tile_step) {
+        const TileCoord tc = decode_tile(p, t, BN, BMT);
+        const int m0 = tc.m0 + (int)rank * BM, n0 = tc.n0 + (int)rank * (BN / CTAS);   // this CTA's rows of A and of B
         for (int kb = tc.kb0; kb < tc.kb1; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           if (!ptx::mbar_wait(&empty_bar[s], ph ^ 1, watchdog, 1)) { ok = false; break; }
-          ptx::mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          // pair: all bytes of the stage (both CTAs' loads) are counted on the LEADER's barrier
+          const uint32_t fb = (CTAS == 2) ? ptx::mapa_u32(ptx::smem_u32(&full_bar[s]), 0) : 0u;
+          if (rank == 0) ptx::mbar_expect_tx(&full_bar[s], Cfg::kStageBytes * CTAS);
+          auto load = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+            if (CTAS == 2) ptx::tma_load_4d_2cta(dst, tm, fb, c0, c1, c2, c3);
+            else ptx::tma_load_4d(dst, tm, &full_bar[s], c0, c1, c2, c3);
+          };
           const uint32_t sa = ptx::smem_u32(smem + s * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
           if (AMAJ == 0) {
-            ptx::tma_load_4d(sa, &tma_a, &full_bar[s], kb * BK, tc.m0, tc.b1 * p.a_m1, tc.b2 * p.a_m2);
+            load(sa, &tma_a, kb * BK, m0, tc.b1 * p.a_m1, tc.b2 * p.a_m2);
           } else {
 #pragma unroll
             for (int c = 0; c < BM / 64; ++c)
-              ptx::tma_load_4d(sa + c * 8192, &tma_a, &full_bar[s], tc.m0 + c * 64, kb * BK, tc.b1 * p.a_m1, tc.b2 * p.a_m2);
+              load(sa + c * 8192, &tma_a, m0 + c * 64, kb * BK, tc.b1 * p.a_m1, tc.b2 * p.a_m2);
           }
           if (BMAJ == 0) {
-            ptx::tma_load_4d(sb, &tma_b, &full_bar[s], kb * BK, tc.n0, tc.b1 * p.b_m1, tc.b2 * p.b_m2);
+            load(sb, &tma_b, kb * BK, n0, tc.b1 * p.b_m1, tc.b2 * p.b_m2);
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              ptx::tma_load_4d(sb + c * 8192, &tma_b, &full_bar[s], tc.n0 + c * 64, kb * BK, tc.b1 * p.b_m1, tc.b2 * p.b_m2);
+            for (int c = 0; c < BN / CTAS / 64; ++c)
+              load(sb + c * 8192, &tma_b, n0 + c * 64, kb * BK, tc.b1 * p.b_m1, tc.b2 * p.b_m2);
           }
         }
       }
     }
+    if (CTAS == 2 && rank == 0) { __syncwarp(); ptx::cluster_wait(); }   // second half of the setup barrier (completed long ago)
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, AMAJ, BMAJ);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BMT, BN, AMAJ, BMAJ);
+      auto commit = [&](uint64_t* bar) {
+        if (CTAS == 2) ptx::umma_commit_2cta(bar, (uint16_t)3);   // same barrier offset in both CTAs
+        else ptx::umma_commit(bar);
+      };
       uint32_t it = 0, tl = 0;
       bool ok = true;
-      for (int t = blockIdx.x; t < p.total_tiles && ok; t += gridDim.x, ++tl) {
-        const TileCoord tc = decode_tile(p, t, BN);
+      for (int t = tile_first; t < p.total_tiles && ok; t += tile_step, ++tl) {
+        const TileCoord tc = decode_tile(p, t, BN, BMT);
         const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
         if (!ptx::mbar_wait(&tmem_empty_bar[as], aph ^ 1, watchdog, 4)) { ok = false; break; }
         ptx::tc_fence_after();
@@ -239,6 +280,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           if (!ptx::mbar_wait(&full_bar[s], ph, watchdog, 2)) { ok = false; break; }
+          if (it == 0) trace_stamp(p, 2);    // first operand stage landed
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + s * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
@@ -248,12 +290,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                                : ptx::make_smem_desc(sa + kk * 2048, 8192, 1024);
             const uint64_t bdesc = (BMAJ == 0) ? ptx::make_smem_desc(sb + kk * 32, 16, 1024)
                                                : ptx::make_smem_desc(sb + kk * 2048, 8192, 1024);
-            ptx::umma_f16(d_tmem, adesc, bdesc, idesc, (kb > tc.kb0 || kk > 0) ? 1u : 0u);
+            if (CTAS == 2) ptx::umma_f16_2cta(d_tmem, adesc, bdesc, idesc, (kb > tc.kb0 || kk > 0) ? 1u : 0u);
+            else ptx::umma_f16(d_tmem, adesc, bdesc, idesc, (kb > tc.kb0 || kk > 0) ? 1u : 0u);
           }
-          ptx::umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+          commit(&empty_bar[s]);  // frees the smem slot (in both CTAs of a pair) when these MMAs retire
         }
-        if (ok) ptx::umma_commit(&tmem_full_bar[as]);  // accumulator of this tile complete
+        if (ok) commit(&tmem_full_bar[as]);  // accumulator of this tile complete
+        if (tl == 0) trace_stamp(p, 3);      // first tile's MMAs issued
       }
+      trace_stamp(p, 4);                     // last MMA issued
     }
   } else {
     // ===== epilogue: warps 2..9; warp % 4 = TMEM lane quarter, (warp - 2) / 4 = which alternate column chunks =====
@@ -266,10 +311,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const unsigned long long seed = p.drop_thr ? salted_seed(p.seed, p.salt) : p.seed;
     const uint32_t wbuf_s = ptx::smem_u32(wbuf);
     uint32_t tl = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tl) {
-      const TileCoord tc = decode_tile(p, t, BN);
+    for (int t = tile_first; t < p.total_tiles; t += tile_step, ++tl) {
+      TileCoord tc = decode_tile(p, t, BN, BMT);
+      tc.m0 += (int)rank * BM;   // this CTA's 128 rows of the pair tile (its own TMEM lanes)
       const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
       if (!ptx::mbar_wait(&tmem_full_bar[as], aph, watchdog, 3)) break;
+      if (ew == 0 && lane == 0) trace_stamp(p, t + tile_step >= p.total_tiles ? 6 : 5);   // accumulator ready: a tile / the last tile
       ptx::tc_fence_after();
       const long long boff = (long long)tc.b1 * p.c_bs1 + (long long)tc.b2 * p.c_bs2;
       const float* bias = p.bias ? p.bias + (long long)tc.b1 * p.bias_bs1 : nullptr;
@@ -281,7 +328,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (!released) {
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+          if (lane == 0) {
+            if (CTAS == 2) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&tmem_empty_bar[as]), 0));
+            else ptx::mbar_arrive(&tmem_empty_bar[as]);
+          }
           released = true;
         }
       };
@@ -305,6 +355,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             } else {
               ptx::tmem_ld_wait();
             }
+            if (ew == 0 && lane == 0 && c0 == 0 && t + tile_step >= p.total_tiles) trace_stamp(p, 8);   // first chunk of the last tile in registers
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
           }
@@ -379,6 +430,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
+          if (ew == 0 && lane == 0 && t + tile_step >= p.total_tiles) trace_stamp(p, c0 == 0 ? 9 : 10);   // chunk staged (first / later)
           if (lane == 0) {
             if (p.accumulate) ptx::tma_reduce_add_4d(&tma_c, wbuf_s, col, row0, tc.b1, tc.b2);
             else ptx::tma_store_4d(&tma_c, wbuf_s, col, row0, tc.b1, tc.b2);
@@ -432,12 +484,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         release();
       }
     }
-    // all bulk stores of this warp must complete before the CTA exits (smem is released at exit)
-    if (lane == 0) ptx::bulk_wait<0>();
+    // the bulk stores of this warp must have READ their staging box before the CTA exits (smem is released at exit); their global
+    // writes complete by the end of the grid like any other store
+    if (lane == 0) ptx::bulk_wait_read<0>();
+    if (ew == 0 && lane == 0) trace_stamp(p, 7);   // this warp's stores have drained
   }
   ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (CTAS == 2) ptx::cluster_sync_all();   // the leader's MMAs read the peer's smem / write its TMEM until the last commit
+  else __syncthreads();
+  if (warp == 1) {
+    if (CTAS == 2) ptx::tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -534,29 +592,43 @@ bool gemm_tc_supported(const ts_gemm_desc* d) {
   return true;
 }
 
-template <int BN, int AMAJ, int BMAJ, typename OutT>
+template <int BN, int AMAJ, int BMAJ, typename OutT, int CTAS>
 static int launch_tc(Ctx* ctx, const ts_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                      const CUtensorMap& tp, const EpiParams& ep, cudaStream_t st) {
-  using Cfg = TcCfg<BN>;
-  auto kern = gemm_tc_kernel<BN, AMAJ, BMAJ, OutT>;
+  using Cfg = TcCfg<BN, CTAS>;
+  auto kern = gemm_tc_kernel<BN, AMAJ, BMAJ, OutT, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
     TS_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     attr_set = true;
   }
-  const int grid = ep.total_tiles < ctx->num_sms ? ep.total_tiles : ctx->num_sms;
-  kern<<<grid, kThreads, Cfg::kSmem, st>>>(ta, tb, tc, tp, ep, ctx->d_watchdog);
+  if (CTAS == 1) {
+    const int grid = ep.total_tiles < ctx->num_sms ? ep.total_tiles : ctx->num_sms;
+    kern<<<grid, kThreads, Cfg::kSmem, st>>>(ta, tb, tc, tp, ep, ctx->d_watchdog);
+  } else {
+    // one cluster of two CTAs (one TPC) per 256-row tile stream
+    const int pairs = ctx->num_sms / 2;
+    const int grid = 2 * (ep.total_tiles < pairs ? ep.total_tiles : pairs);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1); cfg.blockDim = dim3(kThreads, 1, 1); cfg.dynamicSmemBytes = Cfg::kSmem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int* wd = ctx->d_watchdog;
+    TS_CUDA_OK(ctx, cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tp, ep, wd));
+  }
   TS_LAUNCH_OK(ctx);
   return 0;
 }
 
-template <int BN, typename OutT>
+template <int BN, typename OutT, int CTAS>
 static int dispatch_major(Ctx* ctx, const ts_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                           const CUtensorMap& tp, const EpiParams& ep, cudaStream_t st) {
-  if (d->a_major == 0 && d->b_major == 0) return launch_tc<BN, 0, 0, OutT>(ctx, d, ta, tb, tc, tp, ep, st);
-  if (d->a_major == 0 && d->b_major == 1) return launch_tc<BN, 0, 1, OutT>(ctx, d, ta, tb, tc, tp, ep, st);
-  if (d->a_major == 1 && d->b_major == 0) return launch_tc<BN, 1, 0, OutT>(ctx, d, ta, tb, tc, tp, ep, st);
-  return launch_tc<BN, 1, 1, OutT>(ctx, d, ta, tb, tc, tp, ep, st);
+  if (d->a_major == 0 && d->b_major == 0) return launch_tc<BN, 0, 0, OutT, CTAS>(ctx, d, ta, tb, tc, tp, ep, st);
+  if (d->a_major == 0 && d->b_major == 1) return launch_tc<BN, 0, 1, OutT, CTAS>(ctx, d, ta, tb, tc, tp, ep, st);
+  if (d->a_major == 1 && d->b_major == 0) return launch_tc<BN, 1, 0, OutT, CTAS>(ctx, d, ta, tb, tc, tp, ep, st);
+  return launch_tc<BN, 1, 1, OutT, CTAS>(ctx, d, ta, tb, tc, tp, ep, st);
 }
 
 int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
@@ -569,31 +641,47 @@ int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
   //   cost = waves * k_blocks_per_work_item * bn * eff(bn) + tail_epilogue * bn
   // Wider tiles read less smem per FLOP (eff), more/smaller work items fill the 148 SMs and shorten the un-overlapped
   // last epilogue. Split-K only where partial sums may be added: fp32 "C += A*B" with a plain epilogue (wgrad).
-  const int mt = cdiv(d->m, BM), nkb = cdiv(d->k, BK), sms = ctx->num_sms;
+  // A CTA pair (256-row tiles, cta_group::2) halves the B bytes every SM pulls through smem per FLOP (the 1-CTA 128 x 256 tile
+  // needs 96 B/clk of operand reads + 96 B/clk of TMA writes against a 128 B/clk smem port); it has half as many work items.
+  const int nkb = cdiv(d->k, BK), sms = ctx->num_sms;
   const bool split_ok = d->out_dtype == TS_F32 && d->accumulate && !d->bias && !d->c_preact && d->drop <= 0.f && nkb >= 16;
-  int bn = 64, splitk = 1;
+  static const int force_ctas = getenv("TETHYS_GEMM_CTAS") ? atoi(getenv("TETHYS_GEMM_CTAS")) : 0;
+  const int want_ctas = d->force_engine == 3 ? 2 : force_ctas;
+  int bn = 64, splitk = 1, ctas = 1;
   {
     double best = 1e30;
     const int cand[3] = {256, 128, 64};
-    const double eff[3] = {1.0, 1.12, 1.45};
+    const double eff1[3] = {1.0, 1.12, 1.45}, eff2[3] = {0.85, 0.0, 0.0};
     const double tail = d->out_dtype == TS_F32 ? 12.0 : 6.0;
-    for (int i = 0; i < 3; ++i) {
-      if (cand[i] > 64 && d->n <= cand[i] / 2) continue;
-      const long long tiles = (long long)mt * cdiv(d->n, cand[i]) * nb1 * nb2;
-      int sk = 1;
-      if (split_ok && tiles < sms) {
-        sk = (int)(sms / tiles);
-        const int cap = nkb / 8;
-        if (sk > cap) sk = cap;
-        if (sk < 1) sk = 1;
+    for (int cs = 1; cs <= 2; ++cs) {
+      if (want_ctas && cs != want_ctas) continue;
+      if (cs == 2 && d->m <= BM) continue;
+      const int units = sms / cs;                     // CTAs or CTA pairs
+      const int mtc = cdiv(d->m, BM * cs);
+      for (int i = 0; i < (cs == 2 ? (want_ctas ? 2 : 1) : 3); ++i) {   // pair tiles: 256 wide (128 only when forced: measured slower)
+        if (cand[i] > 64 && d->n <= cand[i] / 2) continue;
+        const long long tiles = (long long)mtc * cdiv(d->n, cand[i]) * nb1 * nb2;
+        int sk = 1;
+        if (split_ok && tiles < units) {
+          sk = (int)(units / tiles);
+          const int cap = nkb / 8;
+          if (sk > cap) sk = cap;
+          if (sk < 1) sk = 1;
+        }
+        const int kb = cdiv(nkb, sk);
+        sk = cdiv(nkb, kb);
+        const double waves = (double)((tiles * sk + units - 1) / units);
+        // measured (tools/selftest_gemm, profiles/r02_selftest_gemm_pair.log): pair tiles win 5-18 % where a CTA's main loop is
+        // long (>= 40 k-blocks per CTA over the launch) and lose ~8 % on short launches that are all head and tail
+        if (cs == 2 && !want_ctas && waves * kb < 40) continue;
+        const double score = waves * kb * cand[i] * (cs == 2 ? (i == 0 ? eff2[0] : 1.3) : eff1[i]) + tail * cand[i];
+        if (score < best) { best = score; bn = cand[i]; splitk = sk; ctas = cs; }
       }
-      const int kb = cdiv(nkb, sk);
-      sk = cdiv(nkb, kb);
-      const double waves = (double)((tiles * sk + sms - 1) / sms);
-      const double score = waves * kb * cand[i] * eff[i] + tail * cand[i];
-      if (score < best) { best = score; bn = cand[i]; splitk = sk; }
     }
+    TS_REQUIRE(ctx, best < 1e30, TS_EUNSUPPORTED, "gemm_tc: no tile configuration for m=%lld n=%lld (TETHYS_GEMM_CTAS=%d)",
+               (long long)d->m, (long long)d->n, want_ctas);
   }
+  const int mt = cdiv(d->m, BM * ctas);
   const int nt = cdiv(d->n, bn);
   const long long tiles_ll = (long long)mt * nt * nb1 * nb2;
   TS_REQUIRE(ctx, tiles_ll * splitk < (1ll << 30), TS_ESHAPE, "gemm_tc: too many tiles");
@@ -617,7 +705,7 @@ int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
     if (d->b_major == 0) { dims[0] = d->k; dims[1] = d->n; } else { dims[0] = d->n; dims[1] = d->k; }
     dims[2] = bc1 ? 1 : nb1; dims[3] = bc2 ? 1 : nb2;
     str[0] = (uint64_t)d->ldb * 2; str[1] = bs1; str[2] = bs2;
-    int r = get_tmap(ctx, &tb, d->b, dims, str, 64, d->b_major == 0 ? (uint32_t)bn : BK);
+    int r = get_tmap(ctx, &tb, d->b, dims, str, 64, d->b_major == 0 ? (uint32_t)(bn / ctas) : BK);
     if (r) return r;
   }
   EpiParams ep;
@@ -630,6 +718,7 @@ int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
   ep.a_m1 = (nb1 > 1 && d->a_bs1 != 0) ? 1 : 0; ep.a_m2 = (nb2 > 1 && d->a_bs2 != 0) ? 1 : 0;
   ep.b_m1 = (nb1 > 1 && d->b_bs1 != 0) ? 1 : 0; ep.b_m2 = (nb2 > 1 && d->b_bs2 != 0) ? 1 : 0;
   ep.drop_thr = 0; ep.inv_keep = 1.f; ep.seed = d->seed; ep.salt = ctx->d_state;
+  ep.trace = reinterpret_cast<unsigned long long*>(ctx->gemm_trace);
   if (d->drop > 0.f) {
     double t = (double)d->drop * 4294967296.0;
     ep.drop_thr = (uint32_t)(t > 4294967295.0 ? 4294967295.0 : t);
@@ -660,13 +749,21 @@ int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
   ts_gemm_desc dd = *d;
   dd.batch1 = nb1; dd.batch2 = nb2;
   if (d->out_dtype == TS_BF16) {
-    if (bn == 64) return dispatch_major<64, bf16>(ctx, &dd, ta, tb, tc, tp, ep, st);
-    if (bn == 128) return dispatch_major<128, bf16>(ctx, &dd, ta, tb, tc, tp, ep, st);
-    return dispatch_major<256, bf16>(ctx, &dd, ta, tb, tc, tp, ep, st);
+    if (ctas == 2) {
+      if (bn == 128) return dispatch_major<128, bf16, 2>(ctx, &dd, ta, tb, tc, tp, ep, st);
+      return dispatch_major<256, bf16, 2>(ctx, &dd, ta, tb, tc, tp, ep, st);
+    }
+    if (bn == 64) return dispatch_major<64, bf16, 1>(ctx, &dd, ta, tb, tc, tp, ep, st);
+    if (bn == 128) return dispatch_major<128, bf16, 1>(ctx, &dd, ta, tb, tc, tp, ep, st);
+    return dispatch_major<256, bf16, 1>(ctx, &dd, ta, tb, tc, tp, ep, st);
   } else {
-    if (bn == 64) return dispatch_major<64, float>(ctx, &dd, ta, tb, tc, tp, ep, st);
-    if (bn == 128) return dispatch_major<128, float>(ctx, &dd, ta, tb, tc, tp, ep, st);
-    return dispatch_major<256, float>(ctx, &dd, ta, tb, tc, tp, ep, st);
+    if (ctas == 2) {
+      if (bn == 128) return dispatch_major<128, float, 2>(ctx, &dd, ta, tb, tc, tp, ep, st);
+      return dispatch_major<256, float, 2>(ctx, &dd, ta, tb, tc, tp, ep, st);
+    }
+    if (bn == 64) return dispatch_major<64, float, 1>(ctx, &dd, ta, tb, tc, tp, ep, st);
+    if (bn == 128) return dispatch_major<128, float, 1>(ctx, &dd, ta, tb, tc, tp, ep, st);
+    return dispatch_major<256, float, 1>(ctx, &dd, ta, tb, tc, tp, ep, st);
   }
 }
 

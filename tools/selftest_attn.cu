@@ -207,6 +207,11 @@ int main(int argc, char** argv) {
       {"anticausal_200", 1, 2, 200, 200, 1, 0.f, false},
       {"self_200_dropout", 1, 2, 200, 200, 0, 0.1f, false},
       {"cross_dropout", 1, 2, 100, 260, 0, 0.1f, true},
+      // persistent forward: several work items per CTA, odd tile counts (second query tile of the last pair absent), 6-tile rows
+      {"persist_300_192items", 8, 12, 300, 300, 0, 0.1f, false},
+      {"self_750_6tiles", 1, 2, 750, 750, 0, 0.1f, false},
+      {"self_520_anticausal", 1, 1, 520, 520, 1, 0.f, false},
+      {"cross_100x1500", 1, 2, 100, 1500, 0, 0.f, true},
   };
   int fails = 0;
   printf("== fused attention vs fp64 CPU reference ==\n");

@@ -27,6 +27,9 @@ struct Case {
   float drop;  // timing cases only (the mask is checked by the parity tests, not here)
 };
 
+static void* g_flush = nullptr;           // 512 MB scratch: written between launches to time a kernel with a cold L2
+static const size_t kFlushBytes = 512ull << 20;
+
 static int run_case(ts_ctx* ctx, const Case& cs, int engine, bool timing) {
   const int m = cs.m, n = cs.n, k = cs.k, nb = cs.nb1 * cs.nb2;
   const long long a_rows = cs.amaj == 0 ? m : k, a_cols = cs.amaj == 0 ? k : m;
@@ -136,8 +139,24 @@ static int run_case(ts_ctx* ctx, const Case& cs, int engine, bool timing) {
     cudaEventElapsedTime(&ms, e0, e1);
     ms /= iters;
     const double tf = 2.0 * m * n * (double)k * nb / (ms * 1e-3) / 1e12;
-    printf("  [time %-22s] eng=%d m=%d n=%d k=%d maj=%d%d nb=%d : %.3f ms  %.1f TFLOP/s\n", cs.name, engine, m, n, k,
-           cs.amaj, cs.bmaj, nb, ms, tf);
+    // cold: L2 flushed before every launch (what the kernel sees inside a train step, whose activations far exceed L2)
+    if (!g_flush) cudaMalloc(&g_flush, kFlushBytes);
+    float cold_ms = 0;
+    const int citers = 8;
+    for (int i = 0; i < citers; ++i) {
+      cudaMemsetAsync(g_flush, i, kFlushBytes);
+      cudaEventRecord(e0);
+      ts_gemm(ctx, &d, 0);
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float t = 0;
+      cudaEventElapsedTime(&t, e0, e1);
+      cold_ms += t;
+    }
+    cold_ms /= citers;
+    const double tfc = 2.0 * m * n * (double)k * nb / (cold_ms * 1e-3) / 1e12;
+    printf("  [time %-22s] eng=%d m=%d n=%d k=%d maj=%d%d nb=%d : warm %.1f us %.1f TFLOP/s | cold-L2 %.1f us %.1f TFLOP/s\n", cs.name, engine,
+           m, n, k, cs.amaj, cs.bmaj, nb, ms * 1e3, tf, cold_ms * 1e3, tfc);
   }
   cudaFree(da); cudaFree(db); cudaFree(dc); cudaFree(dres); cudaFree(dpre); cudaFree(dbias);
   return bad ? 4 : 0;
@@ -182,6 +201,18 @@ int main(int argc, char** argv) {
   int fails = 0;
   printf("== correctness: tcgen05 engine (2) vs fp64 CPU reference ==\n");
   for (auto& c : cases) fails += run_case(ctx, c, 2, false) != 0;
+  printf("== correctness: tcgen05 CTA-pair engine (3: cta_group::2, 256-row tiles) ==\n");
+  for (auto& c : cases)
+    if (c.m > 128 && c.n > 64) fails += run_case(ctx, c, 3, false) != 0;
+  {
+    std::vector<Case> more = {
+        {"pair_kk_rag_m", 6000 / 4, 768, 320, 0, 0, 1, 1, 0, 0, 0, 1, 0, 1, 0, 0, 1.f},
+        {"pair_kn_rag_m", 300, 3072 / 4, 256, 0, 1, 1, 1, 0, 0, 0, 1, 1, 0, 0, 1, 1.f},
+        {"pair_nn_splitk", 768, 512, 6000, 1, 1, 1, 1, 0, 0, 1, 0, 0, 0, 1, 0, 1.f},
+        {"pair_nk_batched", 400, 256, 192, 1, 0, 3, 2, 0, 0, 1, 0, 0, 0, 0, 0, 1.f},
+    };
+    for (auto& c : more) fails += run_case(ctx, c, 3, false) != 0;
+  }
   printf("== correctness: CUDA-core engine (1) ==\n");
   for (size_t i = 0; i < cases.size(); i += 3) fails += run_case(ctx, cases[i], 1, false) != 0;
   if (!quick) {
@@ -204,7 +235,11 @@ int main(int argc, char** argv) {
         {"qk 750x750x64 x96", 750, 750, 64, 0, 0, 12, 8, 0, 0, 0, 0, 0, 0, 0, 0, 0.125f},
         {"pv 750x64x750 x96", 750, 64, 750, 0, 1, 12, 8, 752, 0, 0, 0, 0, 0, 0, 0, 1.f},
     };
-    for (auto& c : tcases) run_case(ctx, c, 2, true);
+    // engine 2 = automatic tile choice (1-CTA or CTA-pair tiles; TETHYS_GEMM_CTAS=1 pins the former), 3 = CTA pair forced
+    for (auto& c : tcases) {
+      run_case(ctx, c, 2, true);
+      if (c.m > 128 && c.n > 64) run_case(ctx, c, 3, true);
+    }
     run_case(ctx, tcases[0], 1, true);
   }
   printf("== %s (%d failing cases) ==\n", fails ? "SELFTEST FAILED" : "SELFTEST PASSED", fails);
