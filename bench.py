@@ -354,19 +354,16 @@ def kernel_rooflines(ctx, peaks, B, T, H, F, nh, n_params):
     return dominant, out
 
 
-def run_ours(args):
+def measure_workload(args, strategy, workload, batch, steps, warmup, rank, world, local):
+    """Builds the model of `workload`, captures its train step and times it: `steps` device-resident steps (CUDA events on the
+    compute stream, max over ranks) and `steps` end-to-end steps (pinned host -> device copy of every batch + loss read back).
+    Returns (result dict, handles dict) — handles keep the model / context alive for the per-kernel rooflines of the main line."""
     import numpy as np
     import torch
-    from tethys_speech_b200.runtime import Adam, Strategy
+    from tethys_speech_b200.runtime import Adam
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py (our arm) needs a B200; there is no CPU fallback"
-    torch.cuda.set_device(local)
-    strategy = Strategy()
-    family, size, n_samples, secs, gflop = WORKLOADS[args.workload]
-    B = args.batch or DEFAULT_BATCH[family]
+    family, size, n_samples, secs, gflop = WORKLOADS[workload]
+    B = batch or DEFAULT_BATCH[family]
     dev = torch.device("cuda", local)
     rng = np.random.default_rng(1234 + rank)
     npool = 4
@@ -434,7 +431,7 @@ def run_ours(args):
         def step(batch):  # noqa: F811
             return graphed(batch, sample_aux())
     elif use_graph:
-        # N > 1: CUDA graphs around the eager NCCL all-reduces (collectives stay outside the graphs and keep overlapping)
+        # N > 1: CUDA graphs around the NCCL all-reduces
         if family == "w2v":
             gstep, segs = W.make_graphed_distributed_step(strategy, model, opt, resident[0][0])
 
@@ -453,7 +450,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing ------------------------------------------------------------------------
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(resident[i % npool])
     sync_all()
     clocks = ClockSampler(local)
@@ -462,13 +459,13 @@ def run_ours(args):
     l0 = ctx.lib.ts_launch_count(ctx.h)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        loss = step(resident[i % npool])
+    for i in range(steps):
+        loss = step(resident[i % npool])  # noqa: F841
     e1.record()
     sync_all()
     launches = int(ctx.lib.ts_launch_count(ctx.h) - l0)
     if use_graph:
-        launches = graph_launches * args.steps   # replays do not pass the host-side launch counter
+        launches = graph_launches * steps   # replays do not pass the host-side launch counter
     t_dev = e0.elapsed_time(e1) * 1e-3
     clk = clocks.stop() if rank == 0 else None
     # ---- end-to-end timing: pinned host -> device copy of every batch, loss read back every step ----------
@@ -486,7 +483,7 @@ def run_ours(args):
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     last = None
-    for i in range(args.steps):
+    for i in range(steps):
         last = e2e_step(i)
     e3.record()
     sync_all()
@@ -497,41 +494,86 @@ def run_ours(args):
         tt = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
         strategy.dist.all_reduce(tt, op=strategy.dist.ReduceOp.MAX)
         t_dev, t_e2e = float(tt[0]), float(tt[1])
-    if rank != 0:
-        strategy.dist.destroy_process_group()
-        return 0
     peaks = measured_peaks()
-    sps = B * world * args.steps / t_dev
-    sps_e2e = B * world * args.steps / t_e2e
-    n_params = int(model._prog.n)
-    del resident
-    torch.cuda.empty_cache()
-    dominant, kernels = kernel_rooflines(ctx, peaks, B, T if family == "w2v" else 1500, H, F, nh, n_params)
+    sps = B * world * steps / t_dev
+    sps_e2e = B * world * steps / t_e2e
     step_tflops = sps / world * gflop / 1e3
-    line = {
+    res = {
         "metric": "train_samples_per_sec", "value": sps, "unit": "samples/s", "audio_sec_per_sec": sps * secs,
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": t_dev / steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "model": model_name, "audio_seconds": secs, "per_gpu_batch": B,
+        "config": {"workload": workload, "model": model_name, "audio_seconds": secs, "per_gpu_batch": B,
                    "global_batch": B * world, "parallelism": f"dp{world}", "dropout": "on (0.1, as the reference's training=True)",
                    "step": step_desc, "cuda_graph": bool(use_graph),
-                   "allreduce": ("none (1 replica)" if world == 1 else
-                                 ("bf16 gradient buckets (fp32 master weights / Adam state)" if model._prog.ar_bf16() else "fp32 gradient buckets")),
+                   "allreduce": ("none (1 replica)" if world == 1 else strategy.allreduce_description(model._prog)),
                    "l2": "working set per step (GBs of activations) >> 126 MB L2; 4 distinct input batches cycled; "
                          "per-kernel timings flush L2 with a 256 MB memset between launches"},
         "clocks": clk,
         "e2e": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": t_e2e / args.steps * 1e3, "last_loss": last},
+                "ms_per_step": t_e2e / steps * 1e3, "last_loss": last},
         "gpu_launches": launches,
-        "launches_per_step": launches / args.steps,
+        "launches_per_step": launches / steps,
+        "simt_downgrades": int(ctx.lib.ts_simt_downgrades(ctx.h)),
         "step_tflops_per_gpu": step_tflops,
         "step_frac_of_bf16_sustained": step_tflops / peaks["bf16_tflops_sustained"],
-        "roofline": {"bound": "tensor", "kernel": dominant["kernel"], "achieved": dominant["achieved"], "peak": peaks["bf16_tflops"],
-                     "unit": "TFLOP/s", "frac": dominant["frac"], "traffic": dominant["traffic"],
-                     "peak_source": peaks["source"] + " (burst: kernel timed alone)"},
-        "kernel_rooflines": kernels,
     }
+    del resident, staging
+    handles = {"model": model, "opt": opt, "ctx": ctx, "B": B, "T": T if family == "w2v" else 1500, "H": H, "F": F, "nh": nh,
+               "n_params": int(model._prog.n), "family": family}
+    return res, handles
+
+
+# workloads measured besides the main line so that every BASELINE.json config is driver-visible (each: its own model, a few
+# steps, < 1 s of GPU time): N = 1 -> configs[0] (Whisper default preset, B = 4) and Whisper-base; N > 1 -> configs[2]
+# (Whisper-base, bf16, data parallel) and configs[3] (Wav2Vec2-large, 8 per GPU = global batch 64 at N = 8)
+EXTRA_WORKLOADS = {1: ("whisper_small_30s", "whisper_base_30s"), 0: ("whisper_base_30s", "w2v_large_15s", "whisper_small_30s")}
+
+
+def run_ours(args):
+    import gc
+
+    import torch
+    from tethys_speech_b200.runtime import Strategy
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a B200; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    strategy = Strategy()
+    line, hd = measure_workload(args, strategy, args.workload, args.batch, args.steps, args.warmup, rank, world, local)
+    peaks = measured_peaks()
+    if rank == 0:
+        torch.cuda.empty_cache()
+        dominant, kernels = kernel_rooflines(hd["ctx"], peaks, hd["B"], hd["T"], hd["H"], hd["F"], hd["nh"], hd["n_params"])
+        line["roofline"] = {"bound": "tensor", "kernel": dominant["kernel"], "achieved": dominant["achieved"], "peak": peaks["bf16_tflops"],
+                            "unit": "TFLOP/s", "frac": dominant["frac"], "traffic": dominant["traffic"],
+                            "peak_source": peaks["source"] + " (burst: kernel timed alone)"}
+        line["kernel_rooflines"] = kernels
+    hd.clear()
+    gc.collect()
+    torch.cuda.empty_cache()
+    extras = []
+    if not args.no_extra:
+        for wl in EXTRA_WORKLOADS[1 if world == 1 else 0]:
+            if wl == args.workload:
+                continue
+            try:
+                r, h2 = measure_workload(args, strategy, wl, 0, min(args.steps, 10), max(3, min(args.warmup, 5)), rank, world, local)
+                extras.append({k: r[k] for k in ("value", "unit", "audio_sec_per_sec", "ms_per_step", "n_gpus", "steps", "warmup", "dtype",
+                                                 "config", "clocks", "e2e", "gpu_launches", "launches_per_step", "step_tflops_per_gpu",
+                                                 "step_frac_of_bf16_sustained")})
+                h2.clear()
+            except Exception as ex:   # an extra workload never takes the main line down
+                extras.append({"config": {"workload": wl}, "error": f"{type(ex).__name__}: {ex}"[:300]})
+            gc.collect()
+            torch.cuda.empty_cache()
+    if rank != 0:
+        if world > 1:
+            strategy.dist.destroy_process_group()
+        return 0
+    line["extra"] = {"workloads": extras}
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_step_throughput(args.workload, 10, 1, max_seconds=40.0)   # ~10 s of CPU work (10 steps of batch 1), capped at 40 s
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -552,6 +594,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
+    ap.add_argument("--no-extra", dest="no_extra", action="store_true", help="skip the extra BASELINE workloads reported under extra.workloads")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

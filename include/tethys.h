@@ -214,6 +214,33 @@ int ts_cast_f32_to_bf16(ts_ctx* ctx, const float* src, void* dst, int64_t n, voi
  * (TETHYS_AR_DTYPE=fp32 keeps fp32 buckets), never in fp32 parity mode. */
 int ts_grad_pack_bf16(ts_ctx* ctx, const float* src, void* dst_bf16, int64_t n, const float* scale_dev, void* stream);
 int ts_grad_unpack_bf16(ts_ctx* ctx, const void* src_bf16, float* dst, int64_t n, void* stream);
+/* ---- K21-K23: the collective layer (NCCL over NVLink 5 / NVSwitch, called directly) --------------------------------------
+ * Replaces what tf.distribute.MultiWorkerMirroredStrategy does for the step: the gradient all-reduce inside
+ * optimizer.apply_gradients (W:834, V:1246), strategy.reduce(SUM) of the losses (W:848, V:1260), the broadcast of the chief's
+ * weights under strategy.scope() (W:896, V:1266), CommunicationOptions(NCCL, timeout 120 s) (V:1463-1475).
+ *   ts_comm_unique_id   rank 0 draws the 128-byte NCCL id; the HOST hands it to the other ranks (store / file / MPI).
+ *   ts_comm_init        ncclCommInitRank on the context's device. One communicator per (process, GPU).
+ *   ts_comm_alloc/free  ncclMemAlloc memory registered with the communicator (ncclCommRegister): buffers the switch can reduce
+ *                       in place (NVLS); the gradient arenas live there. Falls back to cudaMalloc on an NCCL without it.
+ *   ts_comm_broadcast   in place, from `root`.
+ *   ts_comm_allreduce_bucket  in-place SUM of `count` elements (TS_F32 / TS_BF16). premul_scale_dev (nullable): a device scalar
+ *                       of the same dtype; this rank contributes premul * x (ncclRedOpCreatePreMulSum) — the local
+ *                       clip_by_global_norm factor of V:1243 at no extra pass.
+ *   ts_comm_check       ncclCommGetAsyncError -> TS_ENCCL with the NCCL message (a hung / failed collective becomes an error).
+ *   ts_comm_finalize    frees the registered buffers and destroys the communicator.
+ * All collectives are enqueued on the caller's stream (stream-ordered, capturable into the step's CUDA graph). libnccl is
+ * resolved with dlopen at the first call (TETHYS_NCCL_LIB overrides the search). */
+typedef struct ts_comm ts_comm;
+int ts_comm_unique_id(ts_ctx* ctx, void* out128);
+int ts_comm_init(ts_ctx* ctx, const void* unique_id128, int nranks, int rank, ts_comm** out);
+int ts_comm_info(ts_comm* c, int* nranks, int* rank, int* nccl_version, int* registered_buffers);
+int ts_comm_alloc(ts_comm* c, int64_t bytes, void** ptr);
+int ts_comm_free(ts_comm* c, void* ptr);
+int ts_comm_broadcast(ts_comm* c, void* buf, int64_t count, int dtype, int root, void* stream);
+int ts_comm_allreduce_bucket(ts_comm* c, void* buf, int64_t count, int dtype, const void* premul_scale_dev, void* stream);
+int ts_comm_check(ts_comm* c);
+int ts_comm_finalize(ts_comm* c);
+
 /* tf.keras.layers.Dropout in training mode (W:160, W:203-205, W:342; V:281, V:393-396, V:431) over a flat tensor:
  * y[i] = x[i] * mask(seed, i) / (1 - rate), in place allowed. mask is the library's counter-based generator (element i of the
  * tensor -> chunk i >> 5, position i & 31), the same one the GEMM epilogues (ts_gemm_desc.drop / .seed) and every backward

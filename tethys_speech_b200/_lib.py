@@ -97,6 +97,15 @@ SYMBOLS = {
     "ts_step_state_set": (_I, [_P, C.c_uint64, _L, _P]),
     "ts_step_state_advance": (_I, [_P, _P]),
     "ts_step_state_get": (_I, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]),
+    "ts_comm_unique_id": (_I, [_P, _P]),
+    "ts_comm_init": (_I, [_P, _P, _I, _I, C.POINTER(_P)]),
+    "ts_comm_info": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "ts_comm_alloc": (_I, [_P, _L, C.POINTER(_P)]),
+    "ts_comm_free": (_I, [_P, _P]),
+    "ts_comm_broadcast": (_I, [_P, _P, _L, _I, _I, _P]),
+    "ts_comm_allreduce_bucket": (_I, [_P, _P, _L, _I, _P, _P]),
+    "ts_comm_check": (_I, [_P]),
+    "ts_comm_finalize": (_I, [_P]),
     "ts_gemm": (_I, [_P, C.POINTER(GemmDesc), _P]),
     "ts_attn_fwd": (_I, [_P, C.POINTER(AttnDesc), _P]),
     "ts_attn_bwd": (_I, [_P, C.POINTER(AttnDesc), _P]),

@@ -158,8 +158,21 @@ class ProgramBase:
 
     def grads_lp(self):
         if getattr(self, "_grads_lp", None) is None:
-            self._grads_lp = torch.zeros(self.n, dtype=torch.bfloat16, device=self.device)
+            st = getattr(self, "_comm_strategy", None)
+            self._grads_lp = (st.alloc(self.n, torch.bfloat16) if st is not None
+                              else torch.zeros(self.n, dtype=torch.bfloat16, device=self.device))
         return self._grads_lp
+
+    def use_comm_buffers(self, strategy):
+        """Move the gradient arenas (the buffers that cross NVLink) into memory registered with the native communicator, so that
+        NCCL reduces them in place (NVLS / zero-copy) instead of staging through its own buffers. Idempotent."""
+        if getattr(strategy, "comm", None) is None or getattr(self, "_comm_strategy", None) is strategy:
+            return
+        self._comm_strategy = strategy
+        self._grads_lp = None
+        if not self.ar_bf16():          # fp32 buckets: the fp32 gradient arena itself is reduced
+            self.grads = strategy.alloc(self.n, torch.float32)
+            self.ws_key = None          # re-bind the program to the new arena at the next ensure_workspace
 
     def pack_grads(self, a0=0, a1=None, scale=None):
         """grads_lp[a0:a1] = bf16(grads[a0:a1] * scale) — scale: device scalar or None."""
@@ -186,24 +199,31 @@ class ProgramBase:
             last = s == len(ends) - 1
             if strategy.dist is not None and (end - start >= bucket_elems or last) and end > start:
                 bucket = self.pack_grads(start, end) if lp else self.grads[start:end]
-                works.append(strategy.dist.all_reduce(bucket, op=strategy.dist.ReduceOp.SUM, async_op=True))
+                strategy.all_reduce_async_(bucket)
+                works.append(1)
                 start = end
-        for w in works:
-            w.wait()
+        if works:
+            strategy.join_async()
         if lp and works:
             self.unpack_grads()
         return len(works)
 
 
 class Strategy:
-    """Stand-in for tf.distribute.MultiWorkerMirroredStrategy (W:1047, V:1473): one process per GPU, NCCL over
-    NVLink/NVSwitch through torch.distributed. With a single process it degenerates to one replica."""
+    """Stand-in for tf.distribute.MultiWorkerMirroredStrategy (W:1047, V:1473): one process per GPU. torch.distributed is the
+    rendezvous (and the whole collective layer on CPU / gloo, for the host-logic tests); on GPUs the data path is the library's
+    own communicator (ts_comm_*, csrc/comm.cu): NCCL called directly on the compute stream — capturable into the step's CUDA
+    graph — over ncclMemAlloc-registered gradient arenas. TETHYS_NATIVE_COMM=0 keeps torch.distributed's NCCL for A/B runs.
+    With a single process it degenerates to one replica."""
 
     def __init__(self, backend=None):
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.rank = int(os.environ.get("RANK", "0"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         self.dist = None
+        self.comm = None            # ts_comm handle
+        self.comm_stream = None     # side stream for collectives that overlap the backward pass
+        self._ctx = None
         if self.world > 1:
             import torch.distributed as dist
 
@@ -214,6 +234,89 @@ class Strategy:
                     torch.cuda.set_device(self.local_rank)
                 dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world)
             self.dist = dist
+            if torch.cuda.is_available() and dist.get_backend() == "nccl" and os.environ.get("TETHYS_NATIVE_COMM", "1") != "0":
+                self._init_native()
+
+    # -- native communicator -----------------------------------------------------------------------------------------------
+    def _init_native(self):
+        ctx = _lib.context(torch.cuda.current_device())
+        uid = C.create_string_buffer(128)
+        if self.rank == 0:
+            ctx.check(ctx.lib.ts_comm_unique_id(ctx.h, uid))
+        box = [bytes(uid.raw)]
+        self.dist.broadcast_object_list(box, src=0)          # the only thing torch.distributed carries: 128 bytes, once
+        h = C.c_void_p()
+        ctx.check(ctx.lib.ts_comm_init(ctx.h, box[0], self.world, self.rank, C.byref(h)))
+        self.comm, self._ctx = h, ctx
+        self.comm_stream = torch.cuda.Stream()
+
+    def alloc(self, numel, dtype):
+        """A flat device tensor in communicator-registered memory (ncclMemAlloc + ncclCommRegister); owned by the communicator."""
+        p = C.c_void_p()
+        esz = 4 if dtype == torch.float32 else 2
+        self._ctx.check(self._ctx.lib.ts_comm_alloc(self.comm, int(numel) * esz, C.byref(p)))
+        return view_from_ptr(p.value, (int(numel),), _lib.TS_F32 if dtype == torch.float32 else _lib.TS_BF16,
+                             torch.device("cuda", torch.cuda.current_device()))
+
+    def _native_all_reduce(self, t, premul=None):
+        dt = _lib.TS_F32 if t.dtype == torch.float32 else _lib.TS_BF16
+        self._ctx.check(self._ctx.lib.ts_comm_allreduce_bucket(self.comm, ptr(t), t.numel(), dt, ptr(premul), stream_ptr()))
+
+    def all_reduce_async_(self, t, premul=None):
+        """SUM all-reduce of `t` that may run underneath the kernels issued after it: enqueued on the communicator's side stream,
+        ordered after everything already on the compute stream (a fork that a CUDA-graph capture records as such).
+        join_async() makes the compute stream wait for all of them."""
+        if self.comm is None:
+            self._works = getattr(self, "_works", [])
+            self._works.append(self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, async_op=True))
+            return
+        self.comm_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm_stream):
+            self._native_all_reduce(t, premul=premul)
+
+    def async_done_event(self):
+        """An event that fires when everything queued so far by all_reduce_async_ has finished (per-bucket joins)."""
+        if self.comm is None:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self.comm_stream)
+        return ev
+
+    def join_async(self):
+        if self.comm is None:
+            for w in getattr(self, "_works", []):
+                w.wait()
+            self._works = []
+            return
+        torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+    def check(self):
+        """ncclCommGetAsyncError of the native communicator (raises TethysError TS_ENCCL)."""
+        if self.comm is not None:
+            self._ctx.check(self._ctx.lib.ts_comm_check(self.comm))
+
+    def info(self):
+        if self.comm is None:
+            return None
+        a, b, v, r = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._ctx.check(self._ctx.lib.ts_comm_info(self.comm, C.byref(a), C.byref(b), C.byref(v), C.byref(r)))
+        return {"nranks": a.value, "rank": b.value, "nccl_version": v.value, "registered_buffers": r.value}
+
+    def allreduce_description(self, prog):
+        what = "bf16 gradient buckets (fp32 master weights / Adam state)" if prog.ar_bf16() else "fp32 gradient buckets"
+        if self.comm is None:
+            return what + "; torch.distributed NCCL, eager between graph segments"
+        i = self.info()
+        return (what + f"; ts_comm (NCCL {i['nccl_version']} called directly, captured in the step graph, "
+                f"{i['registered_buffers']} ncclMemAlloc-registered arenas)")
+
+    def shutdown(self):
+        """Frees the registered arenas and destroys the communicator. Every CUDA graph that captured one of its collectives must
+        have been destroyed first (NCCL requirement); a process that is about to exit can simply skip this."""
+        if self.comm is not None:
+            torch.cuda.synchronize()
+            self._ctx.lib.ts_comm_finalize(self.comm)
+            self.comm = None
 
     @property
     def num_replicas_in_sync(self):
@@ -231,6 +334,10 @@ class Strategy:
         """strategy.reduce(SUM, per_replica_losses, axis=None) — W:848, V:1260."""
         if self.dist is None:
             return value
+        if self.comm is not None and isinstance(value, torch.Tensor) and value.is_cuda:
+            t = value.detach().float().reshape(-1).clone()
+            self._native_all_reduce(t)
+            return t.reshape(value.shape)
         t = value if isinstance(value, torch.Tensor) else torch.tensor(float(value))
         t = t.detach().clone().float()
         if torch.cuda.is_available() and self.dist.get_backend() == "nccl":
@@ -244,6 +351,9 @@ class Strategy:
         if self.dist is None:
             flat.mul_(scale)
             return
+        if self.comm is not None and flat.is_cuda and flat.dtype == scale.dtype:
+            self._native_all_reduce(flat, premul=scale)
+            return
         try:
             op = self.dist._make_nccl_premul_sum(scale)
         except Exception:  # noqa: BLE001 — gloo, or a build without pre-multiplied sums
@@ -254,6 +364,9 @@ class Strategy:
     def all_reduce_sum_(self, flat, bucket_elems=None):
         """K21: in-place SUM all-reduce of a flat gradient arena, issued as a few large buckets."""
         if self.dist is None:
+            return
+        if self.comm is not None and flat.is_cuda:
+            self._native_all_reduce(flat)
             return
         n = flat.numel()
         if not bucket_elems or bucket_elems >= n:
@@ -267,7 +380,10 @@ class Strategy:
 
     def broadcast_(self, flat, src=0):
         """K23: weights created under strategy.scope() are mirrored from the chief (W:896-898, V:1266-1268)."""
-        if self.dist is not None:
+        if self.comm is not None and flat.is_cuda:
+            dt = _lib.TS_F32 if flat.dtype == torch.float32 else _lib.TS_BF16
+            self._ctx.check(self._ctx.lib.ts_comm_broadcast(self.comm, ptr(flat), flat.numel(), dt, int(src), stream_ptr()))
+        elif self.dist is not None:
             self.dist.broadcast(flat, src=src)
 
     def barrier(self):

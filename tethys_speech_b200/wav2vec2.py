@@ -205,6 +205,7 @@ class _Wav2Vec2Task:
         return {k: p.view(p.params, k).detach().clone() for k in self.variable_names}
 
     def broadcast_weights(self, strategy):
+        self._prog.use_comm_buffers(strategy)      # gradient arenas into communicator-registered memory (no-op for one replica)
         strategy.broadcast_(self._prog.params)
         self._prog.weights_synced = False
 
@@ -517,7 +518,8 @@ def make_graphed_distributed_step(strategy, model, optimizer, example_features, 
     neg = model._sample_negative_indices(T, B)[:, 0, :].contiguous().clone()
     state = {}
     # local clip_by_global_norm (V:1243) folded into the collective: sum_r scale_r * g_r in one NCCL pre-multiplied sum
-    premul = (strategy.dist is not None and strategy.dist.get_backend() == "nccl" and hasattr(strategy.dist, "_make_nccl_premul_sum")
+    premul = (strategy.dist is not None and strategy.dist.get_backend() == "nccl"
+              and (getattr(strategy, "comm", None) is not None or hasattr(strategy.dist, "_make_nccl_premul_sum"))
               and not os.environ.get("TETHYS_NO_PREMUL"))
     clip_scale = torch.ones(1, device=prog.device)
     # bf16 compute: the gradient arena crosses NVLink as bf16 (half the bytes); the local clip factor rides on the pack
@@ -549,6 +551,26 @@ def make_graphed_distributed_step(strategy, model, optimizer, example_features, 
             prog.unpack_grads()
         optimizer.update(model)
 
+    if getattr(strategy, "comm", None) is not None:
+        # native communicator: the all-reduce is a stream-ordered NCCL call on the compute stream — the whole step, collective and
+        # loss reduce included, is ONE CUDA graph (no host round trip at the fwd/bwd -> reduce -> Adam boundaries)
+        # (measured at N = 2, profiles/r02_bench_n2_*: splitting the arena into buckets whose clipnorm + Adam run underneath the next
+        # bucket's all-reduce LOSES 0.2 ms — the ring kernels and the update compete for HBM — so: one reduce, one update)
+        def seg_all():
+            seg_fwd_bwd()
+            seg_reduce()
+            seg_update()
+            state["loss_red"] = strategy.reduce(ReduceOp.SUM, state["scaled_loss"], axis=None)
+
+        segs = GraphedSegments([("graph", seg_all)], model, optimizer, warmup=warmup)
+
+        def step_native(features):
+            feats.copy_(features, non_blocking=True)
+            neg.copy_(model._sample_negative_indices(T, B)[:, 0, :])      # V:907-937, drawn outside the graph
+            segs()
+            return state["loss_red"]
+
+        return step_native, segs
     segs = GraphedSegments([("graph", seg_fwd_bwd), ("eager", seg_reduce), ("graph", seg_update)], model, optimizer, warmup=warmup)
 
     def step(features):
