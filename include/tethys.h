@@ -174,6 +174,9 @@ int ts_layernorm_bwd(ts_ctx* ctx, int dtype, const void* dy, const void* x, cons
                      const void* dres, void* dx, float* dgamma, float* dbeta, int rows, int cols, void* stream);
 int ts_groupnorm_gelu_fwd(ts_ctx* ctx, int dtype, const void* x, const float* gamma, const float* beta, void* y, float* mean,
                           float* rstd, double* accum, int batch, int t, int c, int groups, float eps, void* stream);
+/* GroupNormalization.call alone (V:167-196), same arguments, no activation. */
+int ts_groupnorm_fwd(ts_ctx* ctx, int dtype, const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                     double* accum, int batch, int t, int c, int groups, float eps, void* stream);
 
 /* ---- span masking utilities ------------------------------------------------------------------------
  * apply_time_mask (V:1073-1095, axis = 1) / apply_feature_mask (V:1098-1120, axis = 2) on x [batch, t, h]:
@@ -184,6 +187,12 @@ int ts_groupnorm_gelu_fwd(ts_ctx* ctx, int dtype, const void* x, const float* ga
  */
 int ts_span_mask_apply(ts_ctx* ctx, int dtype, const void* x, const unsigned char* start_mask, void* y, float* expanded_mask,
                        int batch, int t, int h, int axis, int mask_length, void* stream);
+
+/* Negative sample positions of the contrastive loss, _sample_negative_indices (V:907-937): per batch row the positions of the
+ * k = max(min(num_negatives, t - 1), 1) smallest of the t uniform ints `random_ints[b, :]` (smallest first, ties by lower index =
+ * tf.nn.top_k(-float(r))), tiled to num_negatives entries. out int32 [batch, num_negatives] — the same list serves every time
+ * step (V:933-935). Integer work, bit-exact; the random ints are an input (the caller's generator). */
+int ts_w2v_sample_negatives(ts_ctx* ctx, const int32_t* random_ints, int batch, int t, int num_negatives, int32_t* out, void* stream);
 
 /* ---- K19/K20: gradient clipping + Keras-2.10 legacy Adam over a flat arena ------------------------
  * Replaces tf.clip_by_global_norm (V:1243, VS:1171), the optimizer's clipnorm=1.0 (V:1274, VS:1206) and

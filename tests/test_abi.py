@@ -40,13 +40,50 @@ def test_ctypes_table_matches_header():
     _lib.load()
 
 
-def test_struct_layouts_match_c():
-    """sizeof of the ctypes mirrors must equal the C structs (checked against a tiny C program's output at build
-    time would need a compiler run; here: field-count and 8-byte alignment sanity + known sizes)."""
+def _c_layout(struct, fields):
+    """sizeof / offsetof of a struct of include/tethys.h as gcc lays it out (a tiny C program compiled on the spot)."""
+    import subprocess
+    import tempfile
+
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "tethys.h"\nint main(void) {\n'
+    src += f'  printf("%zu\\n", sizeof({struct}));\n'
+    for f in fields:
+        src += f'  printf("%zu\\n", offsetof({struct}, {f}));\n'
+    src += "  return 0;\n}\n"
+    with tempfile.TemporaryDirectory() as d:
+        c, exe = os.path.join(d, "l.c"), os.path.join(d, "l")
+        open(c, "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
+    return int(out[0]), [int(x) for x in out[1:]]
+
+
+@pytest.mark.parametrize("cname,mirror", [("ts_gemm_desc", "GemmDesc"), ("ts_attn_desc", "AttnDesc"), ("ts_w2v_config", "W2VConfig"),
+                                          ("ts_whisper_config", "WhisperCfg")])
+def test_struct_layouts_match_c(cname, mirror):
+    """Every ctypes mirror in _lib.py has the size and the field offsets gcc gives the struct of include/tethys.h."""
     from tethys_speech_b200 import _lib
 
-    assert ctypes.sizeof(_lib.GemmDesc) % 8 == 0
-    assert ctypes.sizeof(_lib.W2VConfig) == 4 * (5 + 24 + 7) + 4 * 6 + 4 * 4
+    m = getattr(_lib, mirror)
+    names = [f[0] for f in m._fields_]
+    size, offs = _c_layout(cname, names)
+    assert ctypes.sizeof(m) == size, (cname, ctypes.sizeof(m), size)
+    assert [getattr(m, n).offset for n in names] == offs, cname
+
+
+def test_integration_md_struct_snippet_is_current():
+    """The ctypes struct a maintainer would copy out of INTEGRATION.md is, field for field, the one the library reads."""
+    from tethys_speech_b200 import _lib
+
+    txt = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"class ts_w2v_config\(C\.Structure\):.*?\n(    _fields_ = \[.*?\])\n", txt, flags=re.S)
+    assert m, "INTEGRATION.md no longer shows the ts_w2v_config binding"
+    ns = {"C": ctypes}
+    exec("class S(C.Structure):\n" + m.group(1), ns)
+    doc = ns["S"]
+    assert [f[0] for f in doc._fields_] == [f[0] for f in _lib.W2VConfig._fields_]
+    assert ctypes.sizeof(doc) == ctypes.sizeof(_lib.W2VConfig)
+    assert [getattr(doc, f[0]).offset for f in doc._fields_] == [getattr(_lib.W2VConfig, f[0]).offset for f in _lib.W2VConfig._fields_]
 
 
 def test_no_cpu_fallback_without_gpu():

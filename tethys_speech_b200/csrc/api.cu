@@ -166,6 +166,16 @@ int ts_groupnorm_gelu_fwd(ts_ctx* ctx, int dtype, const void* x, const float* ga
   return ts::groupnorm_gelu_fwd(c, dtype, x, t, mean, rstd, gamma, beta, y, t, 0, batch, t, ch, groups, st);
 }
 
+int ts_groupnorm_fwd(ts_ctx* ctx, int dtype, const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                     double* accum, int batch, int t, int ch, int groups, float eps, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c) return TS_EINVAL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = ts::groupnorm_stats(c, dtype, x, accum, mean, rstd, batch, t, ch, groups, t, eps, st);
+  if (rc) return rc;
+  return ts::groupnorm_fwd(c, dtype, x, mean, rstd, gamma, beta, y, batch, t, ch, groups, st);
+}
+
 int ts_gemm(ts_ctx* ctx, const ts_gemm_desc* d, void* stream) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   if (!c || !d) return TS_EINVAL;

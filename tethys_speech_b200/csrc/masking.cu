@@ -60,7 +60,45 @@ int span_mask_apply(Ctx* ctx, int dt, const void* x, const unsigned char* start,
   return 0;
 }
 
+// ---- negative sample positions of the contrastive loss (V:907-937) — integer work, bit-exact -----------------------------------
+// Per batch row: tf.nn.top_k(-float(r), k) over T uniform ints r = the positions of the k smallest values, smallest first, ties
+// by lower index (top_k is stable on equal keys). One block per row: every element's rank = #{smaller} + #{equal, earlier index}
+// counted against the row held in smem (T^2 compares, T <= a few thousand); rank < k writes out[rank]; the list is tiled to
+// `num_neg` entries when k = min(num_neg, T - 1) < num_neg (V:925-931).
+__global__ void __launch_bounds__(256) negatives_kernel(const int* __restrict__ r, int T_, int k, int num_neg, int* __restrict__ out) {
+  extern __shared__ int srow[];
+  const int* row = r + (long long)blockIdx.x * T_;
+  int* o = out + (long long)blockIdx.x * num_neg;
+  for (int i = threadIdx.x; i < T_; i += blockDim.x) srow[i] = row[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < T_; i += blockDim.x) {
+    const int v = srow[i];
+    int rank = 0;
+    for (int j = 0; j < T_; ++j) rank += (srow[j] < v) || (srow[j] == v && j < i);
+    if (rank < k)
+      for (int q = rank; q < num_neg; q += k) o[q] = i;
+  }
+}
+
+int sample_negatives(Ctx* ctx, const int* rand, int B, int T_, int num_neg, int* out, cudaStream_t st) {
+  TS_REQUIRE(ctx, rand && out && B > 0 && T_ > 0 && num_neg > 0, TS_EINVAL, "sample_negatives: bad arguments");
+  TS_REQUIRE(ctx, T_ <= 48 * 1024, TS_ESHAPE, "sample_negatives: T = %d rows do not fit in shared memory", T_);
+  int k = num_neg < T_ - 1 ? num_neg : T_ - 1;
+  if (k < 1) k = 1;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(negatives_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024 * 4); attr = true; }
+  negatives_kernel<<<B, 256, (size_t)T_ * 4, st>>>(rand, T_, k, num_neg, out);
+  TS_LAUNCH_OK(ctx);
+  return 0;
+}
+
 }  // namespace ts
+
+extern "C" int ts_w2v_sample_negatives(ts_ctx* ctx, const int32_t* random_ints, int batch, int t, int num_negatives, int32_t* out,
+                                       void* stream) {
+  if (!ctx) return TS_EINVAL;
+  return ts::sample_negatives(reinterpret_cast<ts::Ctx*>(ctx), random_ints, batch, t, num_negatives, out, reinterpret_cast<cudaStream_t>(stream));
+}
 
 extern "C" int ts_span_mask_apply(ts_ctx* ctx, int dtype, const void* x, const unsigned char* start_mask, void* y, float* expanded_mask,
                                   int batch, int t, int h, int axis, int mask_length, void* stream) {

@@ -322,7 +322,7 @@ int groupnorm_stats(Ctx* ctx, int dt, const void* x, double* accum, float* mean,
   return 0;
 }
 
-template <typename T>
+template <typename T, bool ACT>   // ACT: GELU after the affine (the feature encoder's pairing, V:248-249); false = GroupNormalization alone
 __global__ void __launch_bounds__(256, 4) gn_gelu_fwd_kernel(const T* __restrict__ x, long long x_rpb,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -364,17 +364,17 @@ __global__ void __launch_bounds__(256, 4) gn_gelu_fwd_kernel(const T* __restrict
     load8<T>(xp, v0);
     load8<T>(xp + step, v1);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = gelu_t<T>(fmaf(v0[i], ga[i], be[i]));
+    for (int i = 0; i < 8; ++i) { const float u = fmaf(v0[i], ga[i], be[i]); o[i] = ACT ? gelu_t<T>(u) : u; }
     store8<T>(yp, o);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = gelu_t<T>(fmaf(v1[i], ga[i], be[i]));
+    for (int i = 0; i < 8; ++i) { const float u = fmaf(v1[i], ga[i], be[i]); o[i] = ACT ? gelu_t<T>(u) : u; }
     store8<T>(yp + step, o);
   }
   if (r < d1) {
     float v0[8], o[8];
     load8<T>(xp, v0);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = gelu_t<T>(fmaf(v0[i], ga[i], be[i]));
+    for (int i = 0; i < 8; ++i) { const float u = fmaf(v0[i], ga[i], be[i]); o[i] = ACT ? gelu_t<T>(u) : u; }
     store8<T>(yp, o);
   }
 }
@@ -385,11 +385,24 @@ int groupnorm_gelu_fwd(Ctx* ctx, int dt, const void* x, long long x_rpb, const f
   const int rows = gn_rows_per_block(ctx, y_rpb, B, C);
   dim3 grid(cdiv(y_rpb, rows), B);
   if (dt == TS_F32)
-    gn_gelu_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, x_rpb, mean, rstd, gamma, beta, (float*)y, y_rpb,
-                                                    y_left, T_, C, G, rows);
+    gn_gelu_fwd_kernel<float, true><<<grid, 256, 0, st>>>((const float*)x, x_rpb, mean, rstd, gamma, beta, (float*)y, y_rpb,
+                                                          y_left, T_, C, G, rows);
   else
-    gn_gelu_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, x_rpb, mean, rstd, gamma, beta, (bf16*)y, y_rpb,
-                                                   y_left, T_, C, G, rows);
+    gn_gelu_fwd_kernel<bf16, true><<<grid, 256, 0, st>>>((const bf16*)x, x_rpb, mean, rstd, gamma, beta, (bf16*)y, y_rpb,
+                                                         y_left, T_, C, G, rows);
+  TS_LAUNCH_OK(ctx);
+  return 0;
+}
+
+// GroupNormalization.call alone (V:167-196), no activation: the b-1 sub-layer surface.
+int groupnorm_fwd(Ctx* ctx, int dt, const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                  void* y, int B, int T_, int C, int G, cudaStream_t st) {
+  const int rows = gn_rows_per_block(ctx, T_, B, C);
+  dim3 grid(cdiv(T_, rows), B);
+  if (dt == TS_F32)
+    gn_gelu_fwd_kernel<float, false><<<grid, 256, 0, st>>>((const float*)x, T_, mean, rstd, gamma, beta, (float*)y, T_, 0, T_, C, G, rows);
+  else
+    gn_gelu_fwd_kernel<bf16, false><<<grid, 256, 0, st>>>((const bf16*)x, T_, mean, rstd, gamma, beta, (bf16*)y, T_, 0, T_, C, G, rows);
   TS_LAUNCH_OK(ctx);
   return 0;
 }

@@ -21,6 +21,8 @@ int groupnorm_stats(Ctx*, int dt, const void* x, double* accum /*[B,G,2] scratch
 int groupnorm_gelu_fwd(Ctx*, int dt, const void* x, long long x_rows_per_batch, const float* mean,
                        const float* rstd, const float* gamma, const float* beta, void* y,
                        long long y_rows_per_batch, int y_left, int B, int T, int C, int G, cudaStream_t);
+int groupnorm_fwd(Ctx*, int dt, const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta, void* y,
+                  int B, int T, int C, int G, cudaStream_t);
 // Backward of gelu(GN(x)). The upstream gradient is either dense `da` [B,T,C] (rows_per_batch da_rpb) or
 // an im2col gradient `dcol` [B, Tn(+dummy), k*C] of the next strided conv (col2im fused on load):
 //   da[b,tau,c] = sum_j dcol[b, (tau+left-j)/s, j*C+c]  for (tau+left-j) % s == 0 and in range.

@@ -268,11 +268,11 @@ class Wav2Vec2ForPreTraining(_Wav2Vec2Task):
         first), tiled to num_negatives, then the same list for every time step. Returns int32 [B, T, K]."""
         T, K = int(sequence_length), self.num_negatives
         actual = max(min(K, T - 1), 1)
-        r = torch.randint(0, T, (int(batch_size), T), generator=self._rng, device=self._prog.device)
-        order = torch.sort(-r.float(), dim=1, descending=True, stable=True).indices[:, :actual]
-        if actual < K:
-            order = order.repeat(1, math.ceil(K / actual))[:, :K]
-        return order.to(torch.int32).unsqueeze(1).expand(-1, T, -1)
+        p = self._prog
+        r = torch.randint(0, T, (int(batch_size), T), generator=self._rng, device=p.device, dtype=torch.int32)
+        order = torch.empty(int(batch_size), K, dtype=torch.int32, device=p.device)
+        p.ctx.check(p.lib.ts_w2v_sample_negatives(p.ctx.h, ptr(r), int(batch_size), T, K, ptr(order), stream_ptr()))   # top_k(-r), tiled
+        return order.unsqueeze(1).expand(-1, T, -1)
 
     def __call__(self, inputs, attention_mask=None, output_attentions=False, output_hidden_states=False, training=False,
                  neg_indices=None, loss_div=1.0, dropout=True):
