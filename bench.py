@@ -303,20 +303,21 @@ def kernel_rooflines(ctx, peaks, B, T, H, F, nh, n_params):
     do = torch.randn(B, T, H, device=dev).to(bf)
     dqkv = torch.empty_like(qkv)
     stats = torch.empty(B, nh, T, 2, device=dev); dsum = torch.empty(B, nh, T, device=dev)
+    dqacc = torch.empty(B, T, H, device=dev)           # fp32 dQ accumulator: selects the fused one-kernel backward
     a = _lib.AttnDesc()
     a.q, a.k, a.v, a.o, a.o_lo = qkv.data_ptr(), qkv.data_ptr() + 2 * H, qkv.data_ptr() + 4 * H, o.data_ptr(), olo.data_ptr()
     a.q_ld = a.kv_ld = 3 * H; a.q_bs = a.kv_bs = T * 3 * H; a.o_ld = H; a.o_bs = T * H
     a.stats = stats.data_ptr(); a.batch, a.heads, a.tq, a.tk, a.head_dim = B, nh, T, T, H // nh
     a.scale, a.mask_mode, a.drop, a.seed = 0.125, 0, 0.1, 3
     a.d_o, a.dq, a.dk, a.dv = do.data_ptr(), dqkv.data_ptr(), dqkv.data_ptr() + 2 * H, dqkv.data_ptr() + 4 * H
-    a.dq_ld = a.dkv_ld = 3 * H; a.dq_bs = a.dkv_bs = T * 3 * H; a.dsum = dsum.data_ptr()
+    a.dq_ld = a.dkv_ld = 3 * H; a.dq_bs = a.dkv_bs = T * 3 * H; a.dsum = dsum.data_ptr(); a.dq_accum = dqacc.data_ptr()
     fl = 4.0 * B * nh * T * T * (H // nh)
     t = _timed(lambda: ctx.check(ctx.lib.ts_attn_fwd(ctx.h, C.byref(a), stream_ptr())), flush)
-    out.append({"kernel": f"attn_fwd_kernel B{B} H{nh} T{T} hd64 dropout 0.1 (V:348-362)", "bound": "tensor", "achieved": fl / t / 1e12,
+    out.append({"kernel": f"attn_fwd2_kernel B{B} H{nh} T{T} hd64 dropout 0.1 (V:348-362)", "bound": "tensor", "achieved": fl / t / 1e12,
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": fl / t / 1e12 / peaks["bf16_tflops"], "us": t * 1e6,
                 "traffic": ncu_traffic("attn_fwd")})
     t = _timed(lambda: ctx.check(ctx.lib.ts_attn_bwd(ctx.h, C.byref(a), stream_ptr())), flush)
-    out.append({"kernel": "attn_bwd_dq_kernel + attn_bwd_dkv_kernel (same shape; 2x forward FLOPs counted, recompute not)", "bound": "tensor",
+    out.append({"kernel": "attn_bwd_prep + attn_bwd2_kernel (fused dQ/dK/dV) + dq_store (same shape; 2x forward FLOPs counted, recompute not)", "bound": "tensor",
                 "achieved": 2 * fl / t / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": 2 * fl / t / 1e12 / peaks["bf16_tflops"],
                 "us": t * 1e6, "traffic": None})
 

@@ -145,6 +145,9 @@ typedef struct {
   int64_t dq_ld, dq_bs, dkv_ld, dkv_bs;
   float* dsum;
   void* o_lo;
+  /* backward, optional: fp32 scratch [batch, tq, heads * 64]. When given, backward runs as ONE fused kernel (dQ partials are
+   * reduce-added here by TMA, then rounded to dq); without it the two-kernel backward (dQ | dK, dV) is used. */
+  float* dq_accum;
 } ts_attn_desc;
 int ts_attn_fwd(ts_ctx* ctx, const ts_attn_desc* d, void* stream);
 int ts_attn_bwd(ts_ctx* ctx, const ts_attn_desc* d, void* stream);

@@ -55,7 +55,7 @@ class AttnDesc(C.Structure):
         ("d_o", C.c_void_p), ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
         ("dq_ld", C.c_int64), ("dq_bs", C.c_int64), ("dkv_ld", C.c_int64), ("dkv_bs", C.c_int64),
         ("dsum", C.c_void_p),
-        ("o_lo", C.c_void_p),
+        ("o_lo", C.c_void_p), ("dq_accum", C.c_void_p),
     ]
 
 

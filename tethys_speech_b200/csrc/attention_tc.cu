@@ -788,12 +788,20 @@ int attn_fwd(Ctx* ctx, const ts_attn_desc* d, cudaStream_t st) {
   return 0;
 }
 
+int attn_bwd2(Ctx* ctx, const ts_attn_desc* d, uint32_t drop_thr, float inv_keep, cudaStream_t st);   // attention_bwd2.cu
+
 int attn_bwd(Ctx* ctx, const ts_attn_desc* d, cudaStream_t st) {
   AttnParams p;
   TS_TRY_RC(fill_params(ctx, d, &p));
   auto al = [](const void* q) { return q && (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   TS_REQUIRE(ctx, al(d->d_o) && al(d->dq) && al(d->dk) && al(d->dv) && d->dsum, TS_EINVAL, "attention backward: dO, dQ, dK, dV (16-byte aligned) and dsum required");
   TS_REQUIRE(ctx, d->dq_ld % 8 == 0 && d->dkv_ld % 8 == 0 && d->dq_bs % 8 == 0 && d->dkv_bs % 8 == 0, TS_ESHAPE, "attention backward: gradient strides must be multiples of 8");
+  // fused one-kernel backward when the caller provides the fp32 dQ accumulator; TETHYS_ATTN_BWD=1 keeps the two-kernel one (A/B)
+  static const bool gen1 = getenv("TETHYS_ATTN_BWD") && atoi(getenv("TETHYS_ATTN_BWD")) == 1;
+  if (d->dq_accum && !gen1) {
+    TS_REQUIRE(ctx, al(d->dq_accum) && al(d->o), TS_EINVAL, "attention backward: dq_accum / o must be 16-byte aligned");
+    return attn_bwd2(ctx, d, p.drop_thr, p.inv_keep, st);
+  }
   p.o_in = (const bf16*)d->o; p.d_o = (const bf16*)d->d_o; p.dsum = d->dsum;
   p.dq = (bf16*)d->dq; p.dq_ld = d->dq_ld; p.dq_bs = d->dq_bs;
   p.dk = (bf16*)d->dk; p.dv = (bf16*)d->dv; p.dkv_ld = d->dkv_ld; p.dkv_bs = d->dkv_bs;

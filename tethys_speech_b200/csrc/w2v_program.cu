@@ -54,7 +54,7 @@ struct W2V {
   std::vector<W2VLayerBuf> LB;
   void* enc_out;
   // backward scratch
-  void *g_a, *g_b, *g_t, *g_x, *g_f, *g_ctx, *g_qkv, *g_P, *g_Pd, *g_small1, *g_small2, *g_dcol, *g_dc, *g_dyg;
+  void *g_a, *g_b, *g_t, *g_x, *g_f, *g_ctx, *g_qkv, *g_P, *g_Pd, *g_dqacc, *g_small1, *g_small2, *g_dcol, *g_dc, *g_dyg;
   // state of the last forward
   uint64_t seed = 0;
   int training = 1;
@@ -240,8 +240,8 @@ static int plan(W2V* m, int B, int N, Bump& bp) {
   m->g_f = bp.get(m->E((long long)M * F));
   m->g_ctx = bp.get(m->E((long long)M * H));
   m->g_qkv = bp.get(m->E((long long)M * 3 * H));
-  if (m->fused_attn) { m->g_P = bp.get(4ll * B * nh * T); m->g_Pd = nullptr; }   // fused: D = rowsum(dO o O) scratch
-  else { m->g_P = bp.get(m->E((long long)B * nh * T * Tp)); m->g_Pd = bp.get(m->E((long long)B * nh * T * Tp)); }
+  if (m->fused_attn) { m->g_P = bp.get(4ll * B * nh * T); m->g_Pd = nullptr; m->g_dqacc = bp.get(4ll * B * T * H); }   // fused: D = rowsum(dO o O) scratch + the fp32 dQ accumulator
+  else { m->g_P = bp.get(m->E((long long)B * nh * T * Tp)); m->g_Pd = bp.get(m->E((long long)B * nh * T * Tp)); m->g_dqacc = nullptr; }
   m->g_small1 = bp.get(m->E((long long)M * std::max(Pj, D)));
   m->g_small2 = bp.get(m->E((long long)M * std::max(Pj, D)));
   m->g_dyg = bp.get(m->E((long long)G * B * Rp * cpg + (long long)K * cpg));
@@ -505,7 +505,7 @@ static int w2v_backward_stage(W2V* m, int stage, cudaStream_t st) {
       a.stats = (float*)b.P; a.batch = B; a.heads = nh; a.tq = a.tk = T; a.head_dim = hd;
       a.scale = 1.f / sqrtf((float)hd); a.mask_mode = 0; a.drop = adrop; a.seed = aseed; a.o_lo = b.ctx_lo;
       a.d_o = m->g_ctx; a.dq = dqkv; a.dk = dqkv + m->E(H); a.dv = dqkv + m->E(2 * H);
-      a.dq_ld = a.dkv_ld = 3 * H; a.dq_bs = a.dkv_bs = (long long)T * 3 * H; a.dsum = (float*)m->g_P;
+      a.dq_ld = a.dkv_ld = 3 * H; a.dq_bs = a.dkv_bs = (long long)T * 3 * H; a.dsum = (float*)m->g_P; a.dq_accum = (float*)m->g_dqacc;
       TS_TRY(attn_bwd(ctx, &a, st));
     } else {
       const void* Puse = b.P;

@@ -48,7 +48,7 @@ struct Whisper {
   float* scalars;  // [0] loss, [3] raw sum
   const int* labels = nullptr;
   // scratch
-  void *s_a, *s_b, *s_t, *s_x, *s_f, *s_ctx, *s_qkv, *s_P, *s_Pd, *s_denc, *s_dq, *s_dkv, *s_dcol, *s_du;
+  void *s_a, *s_b, *s_t, *s_x, *s_f, *s_ctx, *s_qkv, *s_P, *s_Pd, *s_dqacc, *s_denc, *s_dq, *s_dkv, *s_dcol, *s_du;
   uint64_t seed = 0;
   int training = 1;
   bool planned = false, fwd_done = false;
@@ -187,8 +187,8 @@ static int plan(Whisper* m, int B, int Tm, int S, Bump& bp) {
   m->s_a = bp.get(m->E(Mx * d)); m->s_b = bp.get(m->E(Mx * d)); m->s_t = bp.get(m->E(Mx * d)); m->s_x = bp.get(m->E(Mx * d));
   m->s_f = bp.get(m->E(Mx * F)); m->s_ctx = bp.get(m->E(Mx * d)); m->s_qkv = bp.get(m->E(Mx * 3 * d));
   const long long pmax = std::max((long long)B * nh * T * Tp, std::max((long long)B * nh * S * Tp, (long long)B * nh * S * Sp));
-  if (m->fused_attn) { m->s_P = bp.get(4ll * B * nh * std::max(T, S)); m->s_Pd = nullptr; }   // fused: D = rowsum(dO o O) scratch
-  else { m->s_P = bp.get(m->E(pmax)); m->s_Pd = bp.get(m->E(pmax)); }
+  if (m->fused_attn) { m->s_P = bp.get(4ll * B * nh * std::max(T, S)); m->s_Pd = nullptr; m->s_dqacc = bp.get(4ll * B * std::max(T, S) * d); }   // fused: D scratch + fp32 dQ accumulator
+  else { m->s_P = bp.get(m->E(pmax)); m->s_Pd = bp.get(m->E(pmax)); m->s_dqacc = nullptr; }
   m->s_denc = bp.get(m->E(Me * d)); m->s_dq = bp.get(m->E(Md * d)); m->s_dkv = bp.get(m->E(Me * 2 * d));
   m->s_dcol = bp.get(m->E((long long)B * m->Rq2 * 3 * d));
   m->s_du = bp.get(m->E((long long)B * m->Rq1 * d));
@@ -236,6 +236,7 @@ static int attn_backward(Whisper* m, const void* q, long long ldq, const void* k
     a.scale = scale; a.mask_mode = mask; a.drop = drop; a.seed = seed;
     a.d_o = dctx; a.dq = dq; a.dk = dk; a.dv = dv; a.dq_ld = lddq; a.dq_bs = (long long)s.Tq * lddq; a.dkv_ld = lddkv; a.dkv_bs = (long long)s.Tk * lddkv;
     a.dsum = (float*)m->s_P;
+    a.dq_accum = (float*)m->s_dqacc;
     a.o_lo = (char*)const_cast<void*>(P) + fused_stats_bytes(s.B, s.nh, s.Tq);
     return attn_bwd(ctx, &a, st);
   }

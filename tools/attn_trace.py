@@ -28,6 +28,8 @@ def main():
     a.q_ld = a.kv_ld = 3 * H; a.q_bs = a.kv_bs = T * 3 * H; a.o_ld = H; a.o_bs = T * H
     a.stats = stats.data_ptr(); a.batch, a.heads, a.tq, a.tk, a.head_dim = B, nh, T, T, 64
     a.scale, a.mask_mode, a.drop, a.seed = 0.125, 0, drop, 3
+    if len(sys.argv) > 5 and sys.argv[5] == "bwd":
+        return trace_bwd(ctx, a, B, T, H, dev)
     trace = torch.zeros(2 * 16 * 10 + 2 * 4 * 8 + 64, dtype=torch.int64, device=dev)
     for _ in range(3):
         ctx.check(ctx.lib.ts_attn_fwd(ctx.h, C.byref(a), stream_ptr()))
@@ -57,6 +59,36 @@ def main():
             if int(te[g, n, 0]) == 0:
                 continue
             print(f"   {g}   {n}  " + "".join(f"{int(te[g, n, k]) - t0:11d}" for k in range(7)))
+
+
+def trace_bwd(ctx, a, B, T, H, dev):
+    """Timeline of the fused backward's element-wise warp 2 and MMA warp (CTA 0)."""
+    bf = torch.bfloat16
+    do = torch.randn(B, T, H, device=dev).to(bf)
+    dqkv = torch.empty(B, T, 3 * H, device=dev, dtype=bf)
+    dsum = torch.empty(B, a.heads, T, device=dev)
+    dqacc = torch.empty(B, T, H, device=dev)
+    a.d_o, a.dq, a.dk, a.dv = do.data_ptr(), dqkv.data_ptr(), dqkv.data_ptr() + 2 * H, dqkv.data_ptr() + 4 * H
+    a.dq_ld = a.dkv_ld = 3 * H; a.dq_bs = a.dkv_bs = T * 3 * H; a.dsum = dsum.data_ptr(); a.dq_accum = dqacc.data_ptr()
+    ctx.check(ctx.lib.ts_attn_fwd(ctx.h, C.byref(a), stream_ptr()))
+    for _ in range(3):
+        ctx.check(ctx.lib.ts_attn_bwd(ctx.h, C.byref(a), stream_ptr()))
+    trace = torch.zeros(256, dtype=torch.int64, device=dev)
+    ctx.check(ctx.lib.ts_debug_gemm_trace(ctx.h, C.c_void_p(trace.data_ptr())))
+    ctx.check(ctx.lib.ts_attn_bwd(ctx.h, C.byref(a), stream_ptr()))
+    torch.cuda.synchronize()
+    ctx.check(ctx.lib.ts_debug_gemm_trace(ctx.h, C.c_void_p(0)))
+    t = trace.cpu()
+    ew, mm = t[:128].view(16, 8), t[128:].view(16, 8)
+    t0 = int(ew[0, 0])
+    print("element-wise warp 2: tile  loop top  stats synced  S/dP ready  in regs+released  computed  PZ/dS free  stored+arrived")
+    for j in range(16):
+        if int(ew[j, 0]):
+            print(f"                     {j:3d} " + "".join(f"{int(ew[j, k]) - t0:11d}" for k in range(7)))
+    print("MMA warp:            tile  loop top  S/dP released  next S/dP issued  PZ/dS ready  dV/dK/dQ issued")
+    for j in range(16):
+        if int(mm[j, 0]):
+            print(f"                     {j:3d} " + "".join(f"{int(mm[j, k]) - t0:11d}" for k in range(5)))
 
 
 def _unused():

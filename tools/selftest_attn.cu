@@ -73,6 +73,7 @@ static int run_case(ts_ctx* ctx, const Case& cs, bool timing) {
   __nv_bfloat16* d_olo; cudaMalloc(&d_olo, (size_t)B * Tq * H * 2); cudaMemset(d_olo, 0, (size_t)B * Tq * H * 2);
   cudaMalloc(&d_do, do16.size() * 2); cudaMemcpy(d_do, do16.data(), do16.size() * 2, cudaMemcpyHostToDevice);
   cudaMalloc(&d_stats, (size_t)B * nh * Tq * 2 * 4); cudaMalloc(&d_dsum, (size_t)B * nh * Tq * 4);
+  float* d_dqacc; cudaMalloc(&d_dqacc, (size_t)B * Tq * H * 4);   // fp32 dQ accumulator: selects the fused one-kernel backward
   ts_attn_desc d;
   memset(&d, 0, sizeof(d));
   d.q = dq_in; d.k = cs.cross ? dkv_in : dq_in + H; d.v = cs.cross ? dkv_in + H : dq_in + 2 * H;
@@ -80,7 +81,7 @@ static int run_case(ts_ctx* ctx, const Case& cs, bool timing) {
   d.stats = d_stats; d.batch = B; d.heads = nh; d.tq = Tq; d.tk = Tk; d.head_dim = 64; d.scale = 0.125f; d.mask_mode = cs.mask;
   d.drop = cs.drop; d.seed = 0x1234567887654321ull; d.o_lo = d_olo;
   d.d_o = d_do; d.dq = g_q; d.dq_ld = q_ld; d.dq_bs = q_bs;
-  d.dk = cs.cross ? g_kv : g_q + H; d.dv = cs.cross ? g_kv + H : g_q + 2 * H; d.dkv_ld = kv_ld; d.dkv_bs = kv_bs; d.dsum = d_dsum;
+  d.dk = cs.cross ? g_kv : g_q + H; d.dv = cs.cross ? g_kv + H : g_q + 2 * H; d.dkv_ld = kv_ld; d.dkv_bs = kv_bs; d.dsum = d_dsum; d.dq_accum = d_dqacc;
   int rc = ts_attn_fwd(ctx, &d, 0);
   if (rc) { printf("  [%s] fwd rc=%d %s\n", cs.name, rc, ts_last_error(ctx)); return 1; }
   rc = ts_attn_bwd(ctx, &d, 0);
@@ -182,7 +183,7 @@ static int run_case(ts_ctx* ctx, const Case& cs, bool timing) {
            cs.name, B, nh, Tq, Tk, cs.drop, mf, fl / (mf * 1e-3) / 1e12, mb, 2 * fl / (mb * 1e-3) / 1e12);
   }
   cudaFree(dq_in); cudaFree(g_q); if (dkv_in) cudaFree(dkv_in); if (g_kv) cudaFree(g_kv);
-  cudaFree(d_o); cudaFree(d_olo); cudaFree(d_do); cudaFree(d_stats); cudaFree(d_dsum);
+  cudaFree(d_o); cudaFree(d_olo); cudaFree(d_do); cudaFree(d_stats); cudaFree(d_dsum); cudaFree(d_dqacc);
   return bad;
 }
 
@@ -212,6 +213,8 @@ int main(int argc, char** argv) {
       {"self_750_6tiles", 1, 2, 750, 750, 0, 0.1f, false},
       {"self_520_anticausal", 1, 1, 520, 520, 1, 0.f, false},
       {"cross_100x1500", 1, 2, 100, 1500, 0, 0.f, true},
+      {"dec_anticausal_24", 2, 2, 24, 24, 1, 0.f, false},     // padded key rows under the -1e9 mask (exp2 overflow guard)
+      {"anticausal_130", 1, 1, 130, 130, 1, 0.1f, false},
   };
   int fails = 0;
   printf("== fused attention vs fp64 CPU reference ==\n");
