@@ -333,7 +333,7 @@ def kernel_rooflines(ctx, peaks, B, T, H, F, nh, n_params):
     dg = torch.zeros(H, device=dev); db = torch.zeros(H, device=dev)
     hbm(f"ln_fwd_kernel [{M},{H}] bf16 (V:411)", 2.0 * M * H * 2,
         lambda: ctx.check(ctx.lib.ts_layernorm_fwd(ctx.h, _lib.TS_BF16, P(x), P(gam), P(bet), P(y), P(mean), P(rstd), M, H, 1e-5, stream_ptr())))
-    hbm(f"ln_bwd_dx_kernel + ln_bwd_param_kernel [{M},{H}] bf16", 3.0 * M * H * 2,
+    hbm(f"ln_bwd_fused_kernel (dx + dgamma + dbeta in one pass) [{M},{H}] bf16", 3.0 * M * H * 2,
         lambda: ctx.check(ctx.lib.ts_layernorm_bwd(ctx.h, _lib.TS_BF16, P(dy), P(x), P(gam), P(mean), P(rstd), None, P(dx), P(dg), P(db), M, H,
                                                    stream_ptr())))
     # GroupNorm + GELU forward on the conv0 output [B, 48000, 512] bf16 (the largest activation of the step)

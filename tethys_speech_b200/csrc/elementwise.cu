@@ -237,6 +237,91 @@ int colsum_acc(Ctx* ctx, int dt, const void* x, long long ld, int rows, int cols
   return 0;
 }
 
+// Element-wise pass fused with the column sums of its OUTPUT (= the bias gradient of the Dense layer whose dY this output is):
+//   mode 1: out = a * gelu'(b) * mask   (backward of GELU + dropout: dU of fc1 from dF, W:194-205 / V:391-396)
+//   mode 2: out = a * mask              (backward of a Dropout: the dY of the Dense in front of it)
+// Dense [rows, cols] tensors, cols % 8 == 0. Same thread layout as colsum_vec_kernel (a lane owns 8 consecutive columns, the 8
+// warps of a block interleave the rows of the block's row range), so the sums stay in registers; one atomic per column and block.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) ew_colsum_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int rows,
+                                                        int cols, float* __restrict__ csum, int rows_per_block, uint32_t thr, float inv_keep,
+                                                        uint64_t seed, const unsigned long long* __restrict__ salt) {
+  __shared__ float red[8][256 + 8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  if (thr) seed = salted_seed(seed, salt);
+  const DropKey key = flat_drop_key(seed, thr);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (col < cols) {
+    for (int r = r0 + w; r < r1; r += 16) {
+      float va[2][8], vb[2][8];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int rr = r + 8 * u;
+        if (rr < r1) {
+          load8<T>(a + (long long)rr * cols + col, va[u]);
+          if (MODE == 1) load8<T>(b + (long long)rr * cols + col, vb[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int rr = r + 8 * u;
+        if (rr >= r1) break;
+        const long long e = (long long)rr * cols + col;
+        float o[8], ds[8];
+        if (thr) dropout_scale8(key, (uint64_t)e, inv_keep, ds);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float v = MODE == 1 ? va[u][i] * gelu_grad_t<T>(vb[u][i]) : va[u][i];
+          if (thr) v *= ds[i];
+          o[i] = v;
+        }
+        store8<T>(out + e, o);
+        round8<T>(o);                       // the sum of what the weight-gradient GEMM will read
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += o[i];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[w][lane * 8 + i] = acc[i];
+  __syncthreads();
+  const int c = threadIdx.x;
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += red[i][c];
+  if (blockIdx.x * 256 + c < cols) atomicAdd(&csum[blockIdx.x * 256 + c], t);
+}
+
+template <int MODE>
+static int ew_colsum_launch(Ctx* ctx, int dt, const void* a, const void* b, void* out, int rows, int cols, float* csum, float drop,
+                            uint64_t seed, cudaStream_t st) {
+  TS_REQUIRE(ctx, rows > 0 && cols > 0 && cols % 8 == 0 && csum, TS_ESHAPE, "ew_colsum: rows=%d cols=%d", rows, cols);
+  uint32_t thr; float ik;
+  drop_params(drop, &thr, &ik);
+  const int cb = cdiv(cols, 256);
+  int rb = (ctx->num_sms * 4) / cb;
+  if (rb < 1) rb = 1;
+  int rpb = cdiv(rows, rb);
+  rpb = ((rpb + 15) / 16) * 16;
+  dim3 grid(cb, cdiv(rows, rpb));
+  if (dt == TS_F32) ew_colsum_kernel<float, MODE><<<grid, 256, 0, st>>>((const float*)a, (const float*)b, (float*)out, rows, cols, csum, rpb, thr, ik, seed, ctx->d_state);
+  else if (dt == TS_BF16) ew_colsum_kernel<bf16, MODE><<<grid, 256, 0, st>>>((const bf16*)a, (const bf16*)b, (bf16*)out, rows, cols, csum, rpb, thr, ik, seed, ctx->d_state);
+  else return set_err(ctx, TS_EDTYPE, "ew_colsum: dtype %d", dt);
+  TS_LAUNCH_OK(ctx);
+  return 0;
+}
+int gelu_bwd_colsum(Ctx* ctx, int dt, const void* df, const void* u, void* du, int rows, int cols, float* csum, float drop, uint64_t seed,
+                    cudaStream_t st) {
+  return ew_colsum_launch<1>(ctx, dt, df, u, du, rows, cols, csum, drop, seed, st);
+}
+int dropout_colsum(Ctx* ctx, int dt, const void* x, void* y, int rows, int cols, float* csum, float drop, uint64_t seed, cudaStream_t st) {
+  return ew_colsum_launch<2>(ctx, dt, x, nullptr, y, rows, cols, csum, drop, seed, st);
+}
+
 // [B,R,C] -> [B,C,R] through a 32x32 smem tile (coalesced both ways)
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) transpose_kernel(const TI* __restrict__ x, TO* __restrict__ y, int R, int C) {

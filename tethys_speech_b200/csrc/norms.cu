@@ -168,6 +168,109 @@ __global__ void __launch_bounds__(256) ln_bwd_param_kernel(const T* __restrict__
   }
 }
 
+// backward, fused: ONE pass over (dy, x) produces dx (+ dres), the parameter gradients AND — optionally — the dropped copy
+// of dx the next dense layer's backward consumes, with its column sums (= that layer's bias gradient):
+//   dx        = rstd * (g o dy - mean(g o dy) - xhat * mean(g o dy o xhat))  [+ dres]
+//   dgamma   += sum_rows dy o xhat,  dbeta += sum_rows dy
+//   drop_out  = dropout(dx, drop_seed)           (the Dropout in front of the previous Dense in forward order; nullable)
+//   drop_csum+= sum_rows drop_out                (nullable)
+// A warp owns one row at a time and walks rows block_first + warp, + 8 * gridDim.x, ...; a lane's columns are fixed (8 per
+// 256-column chunk), so the per-column partial sums live in registers for the whole kernel and leave through one smem
+// reduction over the 8 warps and one atomic per column and block. Replaces ln_bwd_param + ln_bwd_dx (+ dropout + colsum): the
+// [rows, cols] tensors are read once instead of two to four times, and 2-4 launches become one.
+template <typename T, int NCH, bool DROP>
+__global__ void __launch_bounds__(256, 2) ln_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma,
+                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           const T* __restrict__ dres, T* __restrict__ dx, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, T* __restrict__ drop_out, float* __restrict__ drop_csum,
+                                                           uint32_t thr, float inv_keep, uint64_t seed, const unsigned long long* __restrict__ salt,
+                                                           int rows, int cols) {
+  __shared__ float red[8][256 + 8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float ag[NCH][8], ab[NCH][8], ac[NCH][8];   // ac: column sums of the dropped copy (dead code without DROP)
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ag[ch][i] = 0.f; ab[ch][i] = 0.f; ac[ch][i] = 0.f; }
+  }
+  DropKey key = flat_drop_key(0, 0);
+  if (DROP) key = flat_drop_key(salted_seed(seed, salt), thr);
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += 8 * gridDim.x) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[NCH][8], d[NCH][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int col = ch * 256 + lane * 8;
+      if (col < cols) {
+        float g[8];                       // gamma stays in L1 (3 KB): re-read per row, 24 registers per thread not pinned
+        load8<T>(x + (long long)row * cols + col, xh[ch]);
+        load8<T>(dy + (long long)row * cols + col, d[ch]);
+        load8<float>(gamma + col, g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xh[ch][i] = (xh[ch][i] - mu) * rs;
+          ag[ch][i] = fmaf(d[ch][i], xh[ch][i], ag[ch][i]);
+          ab[ch][i] += d[ch][i];
+          d[ch][i] *= g[i];
+          s1 += d[ch][i];
+          s2 += d[ch][i] * xh[ch][i];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / cols;
+    s2 = warp_sum(s2) / cols;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int col = ch * 256 + lane * 8;
+      if (col < cols) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = rs * (d[ch][i] - s1 - xh[ch][i] * s2);
+        if (dres) {
+          float r[8];
+          load8<T>(dres + (long long)row * cols + col, r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += r[i];
+        }
+        store8<T>(dx + (long long)row * cols + col, o);
+        if (DROP) {
+          // the dropped copy is taken from the value the consumer would have read: dx rounded to the activation dtype
+          round8<T>(o);
+          float ds[8];
+          dropout_scale8(key, (uint64_t)((long long)row * cols + col), inv_keep, ds);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] *= ds[i];
+          store8<T>(drop_out + (long long)row * cols + col, o);
+          round8<T>(o);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ac[ch][i] += o[i];
+        }
+      }
+    }
+  }
+  // per-column partials of the 8 warps -> one atomic per column
+  auto reduce_to = [&](float (&acc)[NCH][8], float* out) {
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[ch][i];
+      __syncthreads();
+      const int c = threadIdx.x;
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[i][c];
+      if (ch * 256 + c < cols) atomicAdd(&out[ch * 256 + c], t);
+    }
+  };
+  reduce_to(ag, dgamma);
+  reduce_to(ab, dbeta);
+  if (DROP) {
+    if (drop_csum) reduce_to(ac, drop_csum);
+  }
+}
+
 template <typename T>
 static int ln_fwd_t(Ctx* ctx, const void* x, const void* res, const float* gamma, const float* beta, void* y,
                     void* sum_out, float* mean, float* rstd, int rows, int cols, float eps, cudaStream_t st) {
@@ -198,23 +301,26 @@ int layernorm_fwd(Ctx* ctx, int dt, const void* x, const void* res, const float*
 template <typename T>
 static int ln_bwd_t(Ctx* ctx, const void* dy, const void* x, const float* gamma, const float* mean,
                     const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta, int rows, int cols,
-                    cudaStream_t st) {
+                    void* drop_out, float* drop_csum, float drop, uint64_t drop_seed, cudaStream_t st) {
   const int nch = cdiv(cols, 256);
-  const int grid = cdiv(rows, 8);
-  {  // parameter gradients first: dx may alias dy (in-place callers)
-    const int cb = cdiv(cols, 256);
-    int rb = (ctx->num_sms * 3) / cb;
-    if (rb < 1) rb = 1;
-    int rpb = cdiv(rows, rb);
-    rpb = ((rpb + 15) / 16) * 16;
-    dim3 g2(cb, cdiv(rows, rpb));
-    ln_bwd_param_kernel<T><<<g2, 256, 0, st>>>((const T*)dy, (const T*)x, mean, rstd, dgamma, dbeta, rows, cols, rpb);
-    TS_LAUNCH_OK(ctx);
+  int grid = cdiv(rows, 8);
+  const int cap = ctx->num_sms * 2;      // two resident blocks per SM, every warp walks ~2.5 rows of a [6000, 768] tensor
+  if (grid > cap) grid = cap;
+  uint32_t thr = 0; float ik = 1.f;
+  if (drop_out && drop > 0.f) {
+    double t = (double)drop * 4294967296.0;
+    thr = (uint32_t)(t > 4294967295.0 ? 4294967295.0 : t);
+    ik = 1.f / (1.f - drop);
   }
-#define LN_BWD_CASE(N)                                                                                          \
-  case N:                                                                                                       \
-    ln_bwd_dx_kernel<T, N><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres,  \
-                                                 (T*)dx, rows, cols);                                           \
+#define LN_BWD_CASE(N)                                                                                                               \
+  case N:                                                                                                                            \
+    if (drop_out)                                                                                                                    \
+      ln_bwd_fused_kernel<T, N, true><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx,     \
+                                                            dgamma, dbeta, (T*)drop_out, drop_csum, thr, ik, drop_seed, ctx->d_state, \
+                                                            rows, cols);                                                             \
+    else                                                                                                                             \
+      ln_bwd_fused_kernel<T, N, false><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx,    \
+                                                             dgamma, dbeta, nullptr, nullptr, 0u, 1.f, 0ull, ctx->d_state, rows, cols); \
     break;
   switch (nch) {
     LN_BWD_CASE(1) LN_BWD_CASE(2) LN_BWD_CASE(3) LN_BWD_CASE(4) LN_BWD_CASE(5)
@@ -225,13 +331,19 @@ static int ln_bwd_t(Ctx* ctx, const void* dy, const void* x, const float* gamma,
   return 0;
 }
 
+int layernorm_bwd_drop(Ctx* ctx, int dt, const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                       const void* dres, void* dx, float* dgamma, float* dbeta, int rows, int cols, void* drop_out, float* drop_csum,
+                       float drop, uint64_t drop_seed, cudaStream_t st) {
+  TS_REQUIRE(ctx, cols % 8 == 0 && cols > 0 && rows > 0, TS_ESHAPE, "layernorm_bwd: rows=%d cols=%d", rows, cols);
+  if (dt == TS_F32) return ln_bwd_t<float>(ctx, dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, cols, drop_out, drop_csum, drop, drop_seed, st);
+  if (dt == TS_BF16) return ln_bwd_t<bf16>(ctx, dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, cols, drop_out, drop_csum, drop, drop_seed, st);
+  return set_err(ctx, TS_EDTYPE, "layernorm_bwd: dtype %d", dt);
+}
+
 int layernorm_bwd(Ctx* ctx, int dt, const void* dy, const void* x, const float* gamma, const float* mean,
                   const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta, int rows, int cols,
                   cudaStream_t st) {
-  TS_REQUIRE(ctx, cols % 8 == 0 && cols > 0 && rows > 0, TS_ESHAPE, "layernorm_bwd: rows=%d cols=%d", rows, cols);
-  if (dt == TS_F32) return ln_bwd_t<float>(ctx, dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, cols, st);
-  if (dt == TS_BF16) return ln_bwd_t<bf16>(ctx, dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, cols, st);
-  return set_err(ctx, TS_EDTYPE, "layernorm_bwd: dtype %d", dt);
+  return layernorm_bwd_drop(ctx, dt, dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, cols, nullptr, nullptr, 0.f, 0, st);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -14,6 +14,11 @@ int layernorm_fwd(Ctx*, int dt, const void* x, const void* res, const float* gam
 int layernorm_bwd(Ctx*, int dt, const void* dy, const void* x, const float* gamma, const float* mean,
                   const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta, int rows, int cols,
                   cudaStream_t);
+// layernorm_bwd that also emits drop_out = dropout(dx, drop, drop_seed) (flat index row * cols + col) and adds its column sums to
+// drop_csum (nullable): the Dropout + bias gradient of the Dense layer that precedes this LayerNorm's input in forward order.
+int layernorm_bwd_drop(Ctx*, int dt, const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                       const void* dres, void* dx, float* dgamma, float* dbeta, int rows, int cols, void* drop_out, float* drop_csum,
+                       float drop, uint64_t drop_seed, cudaStream_t);
 // GroupNorm over [B, T(valid rows), C] stored with `rows_per_batch` rows per batch item.
 int groupnorm_stats(Ctx*, int dt, const void* x, double* accum /*[B,G,2] scratch*/, float* mean, float* rstd,
                     int B, int T, int C, int G, long long rows_per_batch, float eps, cudaStream_t);
@@ -49,6 +54,11 @@ int gelu_bwd(Ctx*, int dt, const void* df, const void* u, void* du, long long n,
 int dropout_apply(Ctx*, int dt, const void* x, void* y, long long n, float drop, uint64_t seed, cudaStream_t);
 // out[n] (+)= column sums of x [rows, cols] (ld). fp32 output, accumulating (atomicAdd).
 int colsum_acc(Ctx*, int dt, const void* x, long long ld, int rows, int cols, float* out, cudaStream_t);
+// element-wise backward passes fused with the column sums of their output (the bias gradient of the Dense whose dY it is):
+// du = df * gelu'(u) * mask / y = x * mask over dense [rows, cols] tensors (cols % 8 == 0); csum[c] += sum_r out[r, c].
+int gelu_bwd_colsum(Ctx*, int dt, const void* df, const void* u, void* du, int rows, int cols, float* csum, float drop, uint64_t seed,
+                    cudaStream_t);
+int dropout_colsum(Ctx*, int dt, const void* x, void* y, int rows, int cols, float* csum, float drop, uint64_t seed, cudaStream_t);
 // y = a + b
 int add_tensors(Ctx*, int dt, const void* a, const void* b, void* y, long long n, cudaStream_t);
 // [B, R, C] -> [B, C, R] style transpose of the two inner dims

@@ -476,22 +476,29 @@ static int w2v_backward_stage(W2V* m, int stage, cudaStream_t st) {
     const W2VLayerOff& o = m->L[l];
     W2VLayerBuf& b = m->LB[l];
     void* dh = m->g_a;        // gradient wrt this layer's output; final dh_in is written back to g_a
+    // Every bias gradient below is the column sum of a tensor some element-wise pass has just produced, so that pass takes it along
+    // (dropout_colsum / gelu_bwd_colsum / layernorm_bwd_drop) and dense_bwd is told not to re-read dY (bias offset -1).
     void* t1 = dh;
-    if (hdrop > 0) { t1 = m->g_t; TS_TRY(dropout_apply(ctx, dt, dh, t1, (long long)M * H, hdrop, site_seed(seed, 103 + l * 8), st)); }
+    if (hdrop > 0) { t1 = m->g_t; TS_TRY(dropout_colsum(ctx, dt, dh, t1, M, H, m->G + o.fc2_b, hdrop, site_seed(seed, 103 + l * 8), st)); }
     // fc2
     // (the GEMM engine can apply GELU'(u) o dropout in the dgrad epilogue — ts_gemm_desc.act = 2 — but with K = 768 that GEMM is
     // epilogue-bound and the separate HBM-bound pass is faster: measured 534 us vs 375 us per step)
-    TS_TRY(dense_bwd(m, b.f, F, t1, H, o.fc2_w, H, o.fc2_b, m->g_f, nullptr, M, st));
-    TS_TRY(gelu_bwd(ctx, dt, m->g_f, b.u, m->g_f, (long long)M * F, m->drop(c.activation_dropout), site_seed(seed, 102 + l * 8), st));
+    TS_TRY(dense_bwd(m, b.f, F, t1, H, o.fc2_w, H, hdrop > 0 ? -1 : o.fc2_b, m->g_f, nullptr, M, st));
+    TS_TRY(gelu_bwd_colsum(ctx, dt, m->g_f, b.u, m->g_f, M, F, m->G + o.fc1_b, m->drop(c.activation_dropout), site_seed(seed, 102 + l * 8), st));
     // fc1
-    TS_TRY(dense_bwd(m, b.x2, H, m->g_f, F, o.fc1_w, F, o.fc1_b, m->g_x, nullptr, M, st));
-    // LN2: dh_mid = dh + LNbwd(dx2)
+    TS_TRY(dense_bwd(m, b.x2, H, m->g_f, F, o.fc1_w, F, -1, m->g_x, nullptr, M, st));
+    // LN2: dh_mid = dh + LNbwd(dx2); the same pass emits t2 = dropout(dh_mid) (the Dropout behind out_proj, V:431) and its column sums
     void* dh_mid = m->g_b;
-    TS_TRY(layernorm_bwd(ctx, dt, m->g_x, b.h_mid, m->P + o.ln2_g, b.ln2_mean, b.ln2_rstd, dh, dh_mid, m->G + o.ln2_g, m->G + o.ln2_b, M, H, st));
     void* t2 = dh_mid;
-    if (hdrop > 0) { t2 = m->g_t; TS_TRY(dropout_apply(ctx, dt, dh_mid, t2, (long long)M * H, hdrop, site_seed(seed, 101 + l * 8), st)); }
+    if (hdrop > 0) {
+      t2 = m->g_t;
+      TS_TRY(layernorm_bwd_drop(ctx, dt, m->g_x, b.h_mid, m->P + o.ln2_g, b.ln2_mean, b.ln2_rstd, dh, dh_mid, m->G + o.ln2_g, m->G + o.ln2_b, M, H,
+                                t2, m->G + o.o_b, hdrop, site_seed(seed, 101 + l * 8), st));
+    } else {
+      TS_TRY(layernorm_bwd(ctx, dt, m->g_x, b.h_mid, m->P + o.ln2_g, b.ln2_mean, b.ln2_rstd, dh, dh_mid, m->G + o.ln2_g, m->G + o.ln2_b, M, H, st));
+    }
     // out_proj
-    TS_TRY(dense_bwd(m, b.ctx, H, t2, H, o.o_w, H, o.o_b, m->g_ctx, nullptr, M, st));
+    TS_TRY(dense_bwd(m, b.ctx, H, t2, H, o.o_w, H, hdrop > 0 ? -1 : o.o_b, m->g_ctx, nullptr, M, st));
     // attention core
     const float adrop = m->drop(c.attention_dropout);
     const uint64_t aseed = site_seed(seed, 100 + l * 8);

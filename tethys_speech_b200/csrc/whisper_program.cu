@@ -442,11 +442,13 @@ static int ffn_bwd(Whisper* m, const void* dh, const void* x_in, const void* u, 
   Ctx* ctx = m->ctx;
   const ts_whisper_config& c = m->cfg;
   const int dt = m->prec, d = c.d_model, F = c.d_ff;
+  // the two bias gradients are column sums of tensors the element-wise passes produce anyway: they take them along
   const void* t1 = dh;
-  if (m->drop(c.dropout) > 0) { TS_TRY(dropout_apply(ctx, dt, dh, m->s_t, rows * d, c.dropout, seed_out, st)); t1 = m->s_t; }
-  TS_TRY(dense_bwd(m, f, F, t1, d, fc2_w, d, fc2_b, m->s_f, nullptr, rows, st));
-  TS_TRY(gelu_bwd(ctx, dt, m->s_f, u, m->s_f, rows * F, m->drop(c.activation_dropout), seed_act, st));
-  TS_TRY(dense_bwd(m, x_in, d, m->s_f, F, fc1_w, F, fc1_b, dx_out, nullptr, rows, st));
+  const bool dr = m->drop(c.dropout) > 0;
+  if (dr) { TS_TRY(dropout_colsum(ctx, dt, dh, m->s_t, (int)rows, d, m->G + fc2_b, c.dropout, seed_out, st)); t1 = m->s_t; }
+  TS_TRY(dense_bwd(m, f, F, t1, d, fc2_w, d, dr ? -1 : fc2_b, m->s_f, nullptr, rows, st));
+  TS_TRY(gelu_bwd_colsum(ctx, dt, m->s_f, u, m->s_f, (int)rows, F, m->G + fc1_b, m->drop(c.activation_dropout), seed_act, st));
+  TS_TRY(dense_bwd(m, x_in, d, m->s_f, F, fc1_w, F, -1, dx_out, nullptr, rows, st));
   return 0;
 }
 
