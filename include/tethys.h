@@ -197,6 +197,16 @@ int ts_span_mask_apply(ts_ctx* ctx, int dtype, const void* x, const unsigned cha
  * step (V:933-935). Integer work, bit-exact; the random ints are an input (the caller's generator). */
 int ts_w2v_sample_negatives(ts_ctx* ctx, const int32_t* random_ints, int batch, int t, int num_negatives, int32_t* out, void* stream);
 
+/* ---- tf.nn.ctc_loss as Wav2Vec2ForCTC._compute_ctc_loss calls it (speech_jobs/whisper_single.py:897-929; SURVEY f-2) -------------
+ * logits fp32 [batch, t, vocab] (batch-major: the reference's transpose to time-major is a view), labels int32 [batch, label_len]
+ * dense, label_length = number of labels > 0 (WS:907), logit_length = t, `blank` = blank_index (0 there). loss_per_sample [batch]
+ * = -log p(labels | logits) (+inf when no alignment exists; 0 instead with zero_infinity, WS:920-921); dlogits (nullable, dtype
+ * grad_dtype, same shape as logits) = d loss_b / d logits * grad_scale — the caller folds the reduction ("sum": 1, "mean":
+ * 1 / batch, WS:924-927) and the replica divisor into grad_scale. workspace: ts_ctc_workspace_floats(...) floats. */
+int64_t ts_ctc_workspace_floats(int batch, int t, int label_len);
+int ts_ctc_loss(ts_ctx* ctx, int grad_dtype, const float* logits, const int32_t* labels, int batch, int t, int vocab, int label_len, int blank,
+                float* workspace, float* loss_per_sample, void* dlogits, float grad_scale, int zero_infinity, void* stream);
+
 /* ---- K19/K20: gradient clipping + Keras-2.10 legacy Adam over a flat arena ------------------------
  * Replaces tf.clip_by_global_norm (V:1243, VS:1171), the optimizer's clipnorm=1.0 (V:1274, VS:1206) and
  * tf.keras.optimizers.Adam.apply_gradients (W:834, V:1246, VS:1174, WS:1179) minus its all-reduce.

@@ -388,6 +388,21 @@ def head_train_step(cfg, w, m, v, t, wave, labels, head, lr=3e-5, eps=1e-8):
     return out
 
 
+def ctc_loss(logits, labels, reduction="sum", zero_infinity=False):
+    """Wav2Vec2ForCTC._compute_ctc_loss of the legacy file — speech_jobs/whisper_single.py:897-929: tf.nn.ctc_loss(labels [B, L] int,
+    logits time-major, label_length = #(labels > 0), logit_length = T, blank_index = 0), optional inf -> 0, then "mean" / "sum" over
+    the batch. tf.nn.ctc_loss is the published CTC forward algorithm (Graves et al. 2006) on log-softmax(logits); restated here with
+    torch's independent implementation of the same algorithm in the dtype of `logits` (float64 in the tests), and pinned by brute-force
+    enumeration of all alignments in tests/test_oracle_tf_semantics.py. Returns (loss scalar, per-sample losses)."""
+    B, Tn, V = logits.shape
+    lp = torch.log_softmax(logits, dim=-1).transpose(0, 1)                     # [T, B, V]: logits_time_major=True (WS:912)
+    tl = (labels > 0).sum(dim=1)                                               # WS:907
+    il = torch.full((B,), Tn, dtype=torch.long)                                # WS:899 (attention_mask is None on this path)
+    # WS:920-921 (tf.where(is_inf(loss), 0, loss)): the replaced entries carry no gradient; torch's flag zeroes loss and gradient alike
+    per = torch.nn.functional.ctc_loss(lp, labels.long(), il, tl.long(), blank=0, reduction="none", zero_infinity=bool(zero_infinity))
+    return (per.mean() if reduction == "mean" else per.sum()), per
+
+
 def num_frames(cfg, n_samples):
     t = n_samples
     for s in cfg.conv_stride:

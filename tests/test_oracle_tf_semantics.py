@@ -163,3 +163,45 @@ def test_param_counts_match_survey():
     assert sum(v.numel() for v in WO.init_weights(WO.Wav2Vec2Config("small")).values()) == 20_466_816
     assert sum(v.numel() for v in WO.init_weights(WO.Wav2Vec2Config("base")).values()) == 92_297_728
     assert sum(v.numel() for v in HO.init_weights(HO.WhisperConfig("tiny")).values()) == 56_933_376
+
+
+def test_ctc_loss_restatement_against_brute_force_enumeration():
+    """WS:897-929: tf.nn.ctc_loss(blank_index=0) = -log of the total probability of every frame-level path that collapses (merge
+    repeats, drop blanks) to the label sequence. The oracle's restatement is checked against literally that sum, over all V^T
+    paths, for sequences with a repeated label (needs a blank between), a padded label row, and an impossible one (inf)."""
+    import itertools
+
+    g = torch.Generator().manual_seed(5)
+    Tn, V = 5, 4
+    logits = torch.randn(3, Tn, V, generator=g, dtype=torch.float64)
+    labels = torch.tensor([[1, 1, 0], [2, 3, 1], [3, 0, 0]])
+    probs = torch.softmax(logits, dim=-1)
+
+    def collapse(path):
+        out, prev = [], None
+        for k in path:
+            if k != prev and k != 0:
+                out.append(k)
+            prev = k
+        return out
+
+    want = []
+    for b in range(3):
+        tgt = [int(x) for x in labels[b] if x > 0]
+        total = 0.0
+        for path in itertools.product(range(V), repeat=Tn):
+            if collapse(path) == tgt:
+                pr = 1.0
+                for t, k in enumerate(path):
+                    pr *= float(probs[b, t, k])
+                total += pr
+        want.append(-np.log(total))
+    loss, per = WO.ctc_loss(logits, labels, reduction="sum")
+    assert np.allclose(per.numpy(), want, rtol=1e-12)
+    assert abs(float(loss) - sum(want)) < 1e-10
+    assert abs(float(WO.ctc_loss(logits, labels, reduction="mean")[0]) - np.mean(want)) < 1e-10
+    # no alignment: 3 distinct labels + a repeat need >= 5 frames; with 3 frames the loss is +inf, 0 under zero_infinity (WS:920-921)
+    lab = torch.tensor([[1, 1, 2]])
+    _, per = WO.ctc_loss(logits[:1, :3], lab)
+    assert torch.isinf(per).all()
+    assert float(WO.ctc_loss(logits[:1, :3], lab, zero_infinity=True)[0]) == 0.0

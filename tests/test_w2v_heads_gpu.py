@@ -138,3 +138,84 @@ def test_head_inference_call_and_errors():
     assert tuple(o["logits"].shape) == (2, T, ctc.config.vocab_size) and float(o["loss"]) > 0
     with pytest.raises(NotImplementedError):
         W.create_full_model("something_else", "tiny")
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_ctc_loss_operator_matches_oracle(dtype):
+    """ts_ctc_loss (tf.nn.ctc_loss of WS:897-929) against the oracle: per-sample losses and d loss / d logits, with a repeated label,
+    padded label rows, an empty transcript, an impossible alignment (inf, zero gradient; 0 under zero_infinity) and T = 750."""
+    import ctypes as C  # noqa: F401
+
+    from oracle import wav2vec2_oracle as O
+    from tethys_speech_b200 import _lib
+    from tethys_speech_b200.runtime import ptr, stream_ptr
+
+    ctx = _lib.context(0)
+    g = torch.Generator().manual_seed(21)
+    for (B, Tn, V, L) in ((4, 50, 32, 12), (2, 750, 32, 100), (3, 6, 5, 4)):
+        logits = torch.randn(B, Tn, V, generator=g, dtype=torch.float64) * 2
+        labels = torch.randint(1, V, (B, L), generator=g)
+        for b in range(B):
+            n = int(torch.randint(0, L + 1, (1,), generator=g)) if b else L
+            labels[b, n:] = 0
+        if B > 2:
+            labels[1, :2] = labels[1, 0]                      # a repeat
+            labels[2, :] = 0                                  # empty transcript
+        if Tn == 6:
+            labels[0] = torch.tensor([1, 1, 2, 2])            # needs 6 frames exactly; row 1 below cannot be aligned in 6
+            labels[1] = torch.tensor([3, 3, 3, 3])
+        lg = logits.clone().requires_grad_(True)
+        loss, per = O.ctc_loss(lg, labels, reduction="sum", zero_infinity=True)
+        loss.backward()
+        want_g = lg.grad
+        _, per_raw = O.ctc_loss(logits, labels)
+        d_lg = logits.float().cuda().contiguous()
+        d_lab = labels.to(torch.int32).cuda().contiguous()
+        ws = torch.empty(int(ctx.lib.ts_ctc_workspace_floats(B, Tn, L)), device="cuda")
+        per_gpu = torch.empty(B, device="cuda")
+        dl = torch.empty(B, Tn, V, device="cuda", dtype=torch.float32 if dtype == "fp32" else torch.bfloat16)
+        for zi in (0, 1):
+            ctx.check(ctx.lib.ts_ctc_loss(ctx.h, _lib.TS_F32 if dtype == "fp32" else _lib.TS_BF16, ptr(d_lg), ptr(d_lab), B, Tn, V, L, 0, ptr(ws),
+                                          ptr(per_gpu), ptr(dl), 1.0, zi, stream_ptr()))
+            ref = (per if zi else per_raw).detach()
+            got = per_gpu.cpu().double()
+            fin = torch.isfinite(ref)
+            assert bool((torch.isinf(got) == torch.isinf(ref)).all())
+            assert float(((got[fin] - ref[fin]).abs() / ref[fin].abs().clamp_min(1e-6)).max()) < 2e-5, (B, Tn, got, ref)
+        assert rel_l2(dl, want_g) < (2e-5 if dtype == "fp32" else 4e-3)      # bf16: one rounding of each gradient element
+
+
+def test_ctc_model_real_loss_and_gradients_fp32():
+    """Wav2Vec2ForCTC with a transcript (labels [B, L]) takes the real CTC loss of the legacy file (WS:897-929, reduction "sum"):
+    loss and every gradient of the train-step body against the oracle (autograd through the restated trunk + ctc_loss)."""
+    from collections import OrderedDict
+
+    from oracle import wav2vec2_oracle as O
+    from tethys_speech_b200 import wav2vec2 as W
+
+    ocfg = O.Wav2Vec2Config("tiny")
+    w0 = O.randomize_weights(O.init_head_weights(ocfg, "ctc", seed=0, dtype=torch.float64), seed=1)
+    model = W.Wav2Vec2ForCTC(W.Wav2Vec2Config("tiny"), precision="fp32", seed=0)
+    model.set_weights({k: v.float() for k, v in w0.items()})
+    g = torch.Generator().manual_seed(31)
+    wave = torch.randn(2, 6400, generator=g, dtype=torch.float64)
+    labels = torch.randint(1, ocfg.vocab_size, (2, 6), generator=g)
+    labels[1, 4:] = 0
+    out = model(wave.float(), labels=labels, training=True, dropout=False)
+    model.gradient()
+    ws = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in w0.items())
+    oo = O.forward_head(ocfg, ws, wave, None, "ctc")
+    loss, per = O.ctc_loss(oo["logits"], labels, reduction="sum")
+    grads = torch.autograd.grad(loss, list(ws.values()), allow_unused=True)
+    assert abs(float(out["loss"]) - float(loss)) < 1e-5 * abs(float(loss))
+    prog = model._prog
+    worst = 0.0
+    for (k, v), gi in zip(ws.items(), grads):
+        if gi is None or float(gi.abs().max()) < 1e-12:
+            continue
+        e = rel_l2(prog.view(prog.grads, k), gi)
+        worst = max(worst, e / (1.0 if gi.dim() > 1 else 3.0))
+    assert worst < 1e-5, worst
+    # the dummy dataset's per-clip label keeps the reference's stand-in loss (V:994-1000)
+    out2 = model(wave.float(), labels=torch.zeros(2), training=True, dropout=False)
+    assert abs(float(out2["loss"]) - float(oo["loss"])) < 1e-5 * abs(float(oo["loss"]))

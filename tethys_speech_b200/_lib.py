@@ -116,6 +116,8 @@ SYMBOLS = {
     "ts_groupnorm_gelu_fwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "ts_groupnorm_fwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "ts_w2v_sample_negatives": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "ts_ctc_workspace_floats": (_L, [_I, _I, _I]),
+    "ts_ctc_loss": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _F, _I, _P]),
     "ts_span_mask_apply": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ts_optim_create": (_I, [_P, _I, C.POINTER(_L), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L), _L, C.POINTER(_P)]),
     "ts_optim_destroy": (None, [_P]),

@@ -143,6 +143,10 @@ int gelu_bwd_rows(Ctx*, int dt, const void* da, long long da_rpb, const Col2imSr
                   long long rpb, int B, int T, int C, cudaStream_t);
 int zero_rows(Ctx*, int dt, void* x, long long rpb, int row_from, int B, int C, cudaStream_t);
 
+// ---- ctc.cu: tf.nn.ctc_loss (dense labels, blank_index given) per sample + d loss / d logits * grad_scale (dlogits nullable) ----
+int ctc_loss(Ctx*, int dt, const float* logits, const int* labels, int B, int T, int V, int L, int blank, float* workspace,
+             float* loss_out, void* dlogits, float grad_scale, int zero_infinity, cudaStream_t);
+
 // ---- optim.cu ------------------------------------------------------------------------------------
 // A parameter "segment": rows x cols block with row stride ld inside the flat arena (dense: rows = 1).
 struct Segment { long long offset; int rows, cols; long long ld; };

@@ -737,6 +737,7 @@ int ts_w2v_get_buffer(ts_w2v* h, const char* name, void** ptr, int32_t* dtype, i
   if (s == "quantizer_input") return set(m->z, m->prec, 3, B, T, c.cv_dim, 1);
   if (s == "code_indices") return set(m->code_idx, TS_I64, 3, c.cv_groups, B, T, 1);
   if (s == "head_logits" && c.head == 1) return set(m->hlogits, TS_F32, 3, B, T, c.vocab_size, 1);
+  if (s == "d_head_logits" && c.head == 1) return set(m->d_hlogits, m->prec, 3, B, T, c.vocab_size, 1);   // loss gradient the backward reads
   if (s == "head_logits" && c.head == 2) return set(m->hlogits, TS_F32, 2, B, c.num_labels, 1, 1);
   if (s == "pooled_output" && c.head == 2) return set(m->pooled, m->prec, 2, B, c.hidden, 1, 1);
   if (c.head != 0 && (s == "projected_states" || s == "projected_quantized_features" || s == "contrastive_logits"))

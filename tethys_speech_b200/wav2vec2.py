@@ -377,6 +377,36 @@ class Wav2Vec2ForCTC(_Wav2Vec2HeadModel):
         self.ctc_loss_reduction = config.ctc_loss_reduction
         self.ctc_zero_infinity = config.ctc_zero_infinity
 
+    def __call__(self, inputs, attention_mask=None, labels=None, output_attentions=False, output_hidden_states=False,
+                 return_dict=True, training=False, loss_div=1.0, dropout=True):
+        """labels None / per-clip scalars (the dummy dataset's, V:1139): the reference's stand-in loss (V:994-1000).
+        labels [B, L] int (a transcript, 0 = padding): the real CTC loss of the legacy file's Wav2Vec2ForCTC (WS:897-929) —
+        tf.nn.ctc_loss with blank 0, reduced with config.ctc_loss_reduction; its gradient replaces the stand-in's in the program."""
+        lab2d = None
+        if labels is not None:
+            t = labels if isinstance(labels, torch.Tensor) else torch.as_tensor(np.asarray(labels))
+            if t.dim() == 2 and t.shape[1] > 1:
+                lab2d = t
+        out = super().__call__(inputs, attention_mask, labels if lab2d is None else torch.zeros(lab2d.shape[0]), output_attentions,
+                               output_hidden_states, return_dict, training, loss_div, dropout)
+        if lab2d is None or not training:
+            return out
+        p = self._prog
+        logits = out["logits"]                                         # fp32 [B, T, vocab]
+        B, T, V = logits.shape
+        lab = to_device(lab2d, torch.int32, p.device).contiguous()
+        L = lab.shape[1]
+        ws = torch.empty(int(p.lib.ts_ctc_workspace_floats(B, T, L)), dtype=torch.float32, device=p.device)
+        per = torch.empty(B, dtype=torch.float32, device=p.device)
+        scale = (1.0 / B if self.ctc_loss_reduction == "mean" else 1.0) / float(loss_div)
+        p.ctx.check(p.lib.ts_ctc_loss(p.ctx.h, p.precision, ptr(logits), ptr(lab), B, T, V, L, 0, ptr(ws), ptr(per), ptr(p.buffer("d_head_logits")),
+                                      scale, 1 if self.ctc_zero_infinity else 0, stream_ptr()))
+        out["loss"] = per.mean() if self.ctc_loss_reduction == "mean" else per.sum()     # unscaled, like every model's "loss" (the step divides)
+        out["ctc_loss_per_sample"] = per
+        return out
+
+    call = __call__
+
 
 class Wav2Vec2ForSequenceClassification(_Wav2Vec2HeadModel):
     """Mirror of `Wav2Vec2ForSequenceClassification` — V:1004-1070: mean over time, Dense(classifier_proj_size, tanh),
