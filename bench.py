@@ -216,21 +216,33 @@ def run_reference(args):
 # our arm
 # ------------------------------------------------------------------------------------------------------------
 def _timed(fn, flush, iters=10, warm=3):
-    """Average CUDA-event time (s) of fn() on the current stream, L2 flushed (256 MB memset) between launches."""
+    """Average device time (s) of fn()'s kernels on the current stream with a cold L2. Two CUDA graphs are replayed `iters` times
+    between CUDA events: [256 MB memset; fn()] and [256 MB memset]; the difference of the two totals / iters is the kernels' time
+    as they run inside a step graph (node-to-node gap included, host launch latency and the flush itself excluded). The earlier
+    event-around-one-launch timing carried 3-5 us of launch gap per sample — half of a 10 us LayerNorm."""
     import torch
 
     for _ in range(warm):
         fn()
-    total = 0.0
-    for _ in range(iters):
+    torch.cuda.synchronize()
+    g_with, g_without = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_with):
         flush.zero_()
+        fn()
+    with torch.cuda.graph(g_without):
+        flush.zero_()
+    tot = []
+    for g in (g_with, g_without):
+        g.replay()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        for _ in range(iters):
+            g.replay()
         e1.record()
         e1.synchronize()
-        total += e0.elapsed_time(e1)
-    return total / iters * 1e-3
+        tot.append(e0.elapsed_time(e1))
+    return max(tot[0] - tot[1], 1e-6) / iters * 1e-3
 
 
 def ncu_traffic(key):
@@ -509,7 +521,7 @@ def measure_workload(args, strategy, workload, batch, steps, warmup, rank, world
                    "step": step_desc, "cuda_graph": bool(use_graph),
                    "allreduce": ("none (1 replica)" if world == 1 else strategy.allreduce_description(model._prog)),
                    "l2": "working set per step (GBs of activations) >> 126 MB L2; 4 distinct input batches cycled; "
-                         "per-kernel timings flush L2 with a 256 MB memset between launches"},
+                         "per-kernel timings: CUDA-graph replays of [256 MB memset (L2 flush); kernel] minus replays of the memset alone"},
         "clocks": clk,
         "e2e": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": t_e2e / steps * 1e3, "last_loss": last},

@@ -158,3 +158,36 @@ def test_whisper_bf16_ragged_cross_attention_and_full_length_targets():
     # encoder T = 300 (three 128-row tiles, ragged), decoder S = 100 (W:786): cross-attention 100 x 300, anti-causal 100 x 100
     O, W, ocfg, cfg = _small_cfgs(d=128, heads=2, ff=256, n_ctx=320)
     _run(O, W, ocfg, cfg, 1, 600, 100, "bf16", BF16_TOL, seed=3)
+
+
+def test_whisper_call_contract_without_labels_and_argument_errors():
+    """W:547-616: model(features, decoder_input_ids=ids) returns logits and no loss; ids equal to the right-shifted labels are
+    accepted next to labels; arguments without a kernel raise."""
+    from oracle import whisper_oracle as O
+    from tethys_speech_b200 import whisper as W
+
+    ocfg, cfg = O.WhisperConfig("small"), W.WhisperConfig()
+    for c in (ocfg, cfg):
+        c.d_model, c.d_ff = 128, 256
+        c.encoder_layers = c.decoder_layers = 2
+        c.encoder_attention_heads = c.decoder_attention_heads = 2
+        c.vocab_size, c.n_mels, c.n_ctx, c.decoder_start_token_id = 203, 16, 64, 200
+    w0 = O.randomize_weights(O.init_weights(ocfg, seed=4, dtype=torch.float64), seed=5)
+    model = W.WhisperForConditionalGeneration(cfg, precision="fp32", seed=4)
+    model.set_weights({k: v.float() for k, v in w0.items()})
+    g = torch.Generator().manual_seed(9)
+    feats = torch.randn(2, ocfg.n_mels, 100, generator=g, dtype=torch.float64)
+    labels = torch.randint(0, 100, (2, 24), generator=g, dtype=torch.int32)
+    ids = torch.cat([torch.full((2, 1), cfg.decoder_start_token_id, dtype=torch.int32), labels[:, :-1]], dim=1)
+    want = O.forward(ocfg, w0, feats, labels)
+    out = model(feats.float(), decoder_input_ids=ids)
+    assert out["loss"] is None and out["past_key_values"] is None
+    assert rel_l2(out["logits"], want["logits"]) < 1e-5
+    out = model(feats.float(), decoder_input_ids=ids, labels=labels, training=True, dropout=False)
+    assert abs(float(out["loss"]) - float(want["loss"])) < 1e-5 * abs(float(want["loss"]))
+    with pytest.raises(NotImplementedError):
+        model(feats.float(), labels=labels, decoder_attention_mask=torch.ones(2, 24), training=True)
+    with pytest.raises(NotImplementedError):
+        model(feats.float(), decoder_input_ids=ids + 1)
+    with pytest.raises(ValueError):
+        model(feats.float())

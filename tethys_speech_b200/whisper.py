@@ -147,13 +147,34 @@ class WhisperForConditionalGeneration:
     def __call__(self, input_features, decoder_input_ids=None, attention_mask=None, decoder_attention_mask=None,
                  encoder_outputs=None, past_key_values=None, labels=None, use_cache=None, return_dict=True, training=False,
                  dropout=True):
-        """input_features [B, n_mels, T_mel]; labels [B, S] int. Only the train-path arguments are supported:
-        decoder_input_ids are derived from the labels (W:557-563); masks / caches must be None."""
-        if any(a is not None for a in (decoder_input_ids, attention_mask, decoder_attention_mask, encoder_outputs, past_key_values)):
-            raise NotImplementedError("only the training call (features, labels=…, training=True) is on the hot path")
-        if labels is None:
-            raise NotImplementedError("labels are required (generation / encoder-only calls are not on the hot path)")
+        """input_features [B, n_mels, T_mel]; labels [B, S] int. The train call model(features, labels=..., training=True) (W:826) and
+        the inference calls model(features, labels=...) / model(features, decoder_input_ids=...) are supported; masks / caches are
+        not (generate() is the cached decode)."""
+        if decoder_attention_mask is not None:
+            # W:594-597 weights the loss with the mask, but W:575 also hands the same [B, S] tensor to the decoder as ITS attention mask,
+            # where it replaces the causal mask and is added to [B, heads, S, S] scores (W:150-154): that broadcast only type-checks for
+            # B == 1 or B == S. The reference's own loops never pass it (W:826, W:1003); there is no kernel for that attention pattern.
+            raise NotImplementedError("decoder_attention_mask: not on the train path (see the comment above; the reference never passes it)")
+        if any(a is not None for a in (attention_mask, encoder_outputs, past_key_values)):
+            raise NotImplementedError("attention_mask / encoder_outputs / past_key_values: use generate() for cached decoding")
         p = self._prog
+        if labels is None:
+            # inference call model(features, decoder_input_ids=ids): logits only (W:579), loss None (W:585). The program builds its
+            # decoder inputs as pad(labels[:, :-1], start) (W:559-563), so ids must begin with decoder_start_token_id.
+            if decoder_input_ids is None:
+                raise ValueError("either labels or decoder_input_ids are required (W:557-563)")
+            if training:
+                raise ValueError("training=True needs labels (the loss of W:585-600)")
+            ids = to_device(decoder_input_ids, torch.int32, p.device)
+            if not bool((ids[:, 0] == int(self.config.decoder_start_token_id)).all()):
+                raise NotImplementedError("decoder_input_ids must begin with decoder_start_token_id")
+            labels = torch.cat([ids[:, 1:], torch.zeros_like(ids[:, :1])], dim=1)
+        elif decoder_input_ids is not None:
+            ids = to_device(decoder_input_ids, torch.int32, p.device)
+            lab_ = to_device(labels, torch.int32, p.device)
+            want = torch.cat([torch.full_like(lab_[:, :1], int(self.config.decoder_start_token_id)), lab_[:, :-1]], dim=1)
+            if ids.shape != want.shape or not bool((ids == want).all()):
+                raise NotImplementedError("decoder_input_ids other than the right-shifted labels (W:559-563) are not on the train path")
         x = to_device(input_features, torch.float32, p.device)
         lab = to_device(labels, torch.int32, p.device)
         B, nm, Tm = x.shape
