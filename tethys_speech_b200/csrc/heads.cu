@@ -59,8 +59,129 @@ __global__ void __launch_bounds__(VQ_WARPS * 32) vq_fwd_kernel(const T* __restri
     q[(long long)m * G * D + g * D + j] = from_f<T>(cb[((long long)g * V + best_i) * D + j]);
 }
 
+// Second layout, for the group widths the presets use (D = 32 / 64 / 128) and a codebook that fits in shared memory: a lane owns one
+// FRAME (its D inputs live in registers), the block's 8 warps split the V codes of the group into 8 slices, and a code vector is
+// read as a warp-wide broadcast (one LDS.128 per 4 dimensions) — ~0.3 shared loads per subtract/multiply/add triple instead of
+// the 2 of the layout above, which made that one LDS-bound. The arithmetic of a distance is unchanged (sequential over j, separate
+// sub / mul / add roundings, no FMA) and ties keep the lowest code index (within a slice by strict <, across slices by visiting
+// them in index order), so the int64 indices are bit-identical to the kernel above and to the fp32-sequential restatement.
+template <typename T, int D>
+__global__ void __launch_bounds__(256) vq_fwd_frames_kernel(const T* __restrict__ z, const float* __restrict__ cb, T* __restrict__ q,
+                                                            long long* __restrict__ idx, int* __restrict__ hist, int M, int G, int V) {
+  extern __shared__ float sm[];
+  float* scb = sm;                                   // [V][D]
+  float* sbest = sm + (size_t)V * D;                 // [8][32]
+  int* sidx = reinterpret_cast<int*>(sbest + 256);   // [8][32], then [32] winners
+  const int g = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 32, m = m0 + lane;
+  const bool valid = m < M;
+  for (int i = threadIdx.x * 4; i < V * D; i += 256 * 4)
+    *reinterpret_cast<float4*>(scb + i) = *reinterpret_cast<const float4*>(cb + (size_t)g * V * D + i);
+  float zr[D];
+  if (valid) {
+    const T* zp = z + (long long)m * G * D + g * D;
+#pragma unroll
+    for (int j = 0; j < D; j += 8) {
+      float v8[8];
+      load8<T>(zp + j, v8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) zr[j + e] = v8[e];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < D; ++j) zr[j] = 0.f;
+  }
+  __syncthreads();
+  const int per = (V + 7) / 8, c_lo = warp * per, c_hi = min(V, c_lo + per);
+  float best = INFINITY;
+  int best_i = 0x7fffffff;
+  int c = c_lo;
+  for (; c + 1 < c_hi; c += 2) {                     // two codes at a time: two independent accumulation chains
+    float d0 = 0.f, d1 = 0.f;
+    const float4* e0 = reinterpret_cast<const float4*>(scb + (size_t)c * D);
+    const float4* e1 = reinterpret_cast<const float4*>(scb + (size_t)(c + 1) * D);
+#pragma unroll
+    for (int j = 0; j < D / 4; ++j) {
+      const float4 a = e0[j], b = e1[j];
+      float t;
+      t = __fsub_rn(zr[4 * j], a.x); d0 = __fadd_rn(d0, __fmul_rn(t, t));
+      t = __fsub_rn(zr[4 * j], b.x); d1 = __fadd_rn(d1, __fmul_rn(t, t));
+      t = __fsub_rn(zr[4 * j + 1], a.y); d0 = __fadd_rn(d0, __fmul_rn(t, t));
+      t = __fsub_rn(zr[4 * j + 1], b.y); d1 = __fadd_rn(d1, __fmul_rn(t, t));
+      t = __fsub_rn(zr[4 * j + 2], a.z); d0 = __fadd_rn(d0, __fmul_rn(t, t));
+      t = __fsub_rn(zr[4 * j + 2], b.z); d1 = __fadd_rn(d1, __fmul_rn(t, t));
+      t = __fsub_rn(zr[4 * j + 3], a.w); d0 = __fadd_rn(d0, __fmul_rn(t, t));
+      t = __fsub_rn(zr[4 * j + 3], b.w); d1 = __fadd_rn(d1, __fmul_rn(t, t));
+    }
+    if (d0 < best) { best = d0; best_i = c; }
+    if (d1 < best) { best = d1; best_i = c + 1; }
+  }
+  if (c < c_hi) {
+    float d0 = 0.f;
+    const float4* e0 = reinterpret_cast<const float4*>(scb + (size_t)c * D);
+#pragma unroll
+    for (int j = 0; j < D / 4; ++j) {
+      const float4 a = e0[j];
+      float t;
+      t = __fsub_rn(zr[4 * j], a.x); d0 = __fadd_rn(d0, __fmul_rn(t, t));
+      t = __fsub_rn(zr[4 * j + 1], a.y); d0 = __fadd_rn(d0, __fmul_rn(t, t));
+      t = __fsub_rn(zr[4 * j + 2], a.z); d0 = __fadd_rn(d0, __fmul_rn(t, t));
+      t = __fsub_rn(zr[4 * j + 3], a.w); d0 = __fadd_rn(d0, __fmul_rn(t, t));
+    }
+    if (d0 < best) { best = d0; best_i = c; }
+  }
+  sbest[warp * 32 + lane] = best;
+  sidx[warp * 32 + lane] = best_i;
+  __syncthreads();
+  if (warp == 0) {
+    float b = INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {                    // slices in increasing code order: the first minimum wins
+      const float ob = sbest[w * 32 + lane];
+      if (ob < b) { b = ob; bi = sidx[w * 32 + lane]; }
+    }
+    sidx[256 + lane] = bi;
+    if (valid) {
+      idx[(long long)g * M + m] = bi;
+      atomicAdd(&hist[g * V + bi], 1);
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * D; e += 256) {
+    const int f = e / D, j = e % D;
+    if (m0 + f < M) q[(long long)(m0 + f) * G * D + g * D + j] = from_f<T>(scb[(size_t)sidx[256 + f] * D + j]);
+  }
+}
+
+template <typename T, int D>
+static int vq_fwd_frames(Ctx* ctx, const void* z, const float* codebook, void* q, long long* idx, int* hist, int M, int G, int V,
+                         cudaStream_t st) {
+  const size_t smem = ((size_t)V * D + 256) * sizeof(float) + (256 + 32) * sizeof(int);
+  static bool attr = false;
+  if (!attr) { TS_CUDA_OK(ctx, cudaFuncSetAttribute(vq_fwd_frames_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+  dim3 grid(cdiv(M, 32), G);
+  vq_fwd_frames_kernel<T, D><<<grid, 256, smem, st>>>((const T*)z, codebook, (T*)q, idx, hist, M, G, V);
+  TS_LAUNCH_OK(ctx);
+  return 0;
+}
+
 int vq_fwd(Ctx* ctx, int dt, const void* z, const float* codebook, void* q, long long* idx, int* hist, int M, int G, int V,
            int D, cudaStream_t st) {
+  // frames-in-registers layout when the group's codebook fits in shared memory and rows are 16-byte aligned
+  if (((size_t)V * D + 256) * 4 + 288 * 4 <= 200 * 1024 && (V * D) % 4 == 0 && ((size_t)G * D * (dt == TS_F32 ? 4 : 2)) % 16 == 0 &&
+      (reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(codebook) & 15) == 0) {
+    if (dt == TS_BF16) {
+      if (D == 128) return vq_fwd_frames<bf16, 128>(ctx, z, codebook, q, idx, hist, M, G, V, st);
+      if (D == 64) return vq_fwd_frames<bf16, 64>(ctx, z, codebook, q, idx, hist, M, G, V, st);
+      if (D == 32) return vq_fwd_frames<bf16, 32>(ctx, z, codebook, q, idx, hist, M, G, V, st);
+    } else if (dt == TS_F32) {
+      if (D == 128) return vq_fwd_frames<float, 128>(ctx, z, codebook, q, idx, hist, M, G, V, st);
+      if (D == 64) return vq_fwd_frames<float, 64>(ctx, z, codebook, q, idx, hist, M, G, V, st);
+      if (D == 32) return vq_fwd_frames<float, 32>(ctx, z, codebook, q, idx, hist, M, G, V, st);
+    }
+  }
   const size_t smem = (32 * (D + 1) + VQ_WARPS * D) * sizeof(float);
   TS_REQUIRE(ctx, smem <= 200 * 1024, TS_EUNSUPPORTED, "vq: group dim %d too large", D);
   dim3 grid(cdiv(M, VQ_WARPS), G);
