@@ -463,6 +463,12 @@ def measure_workload(args, strategy, workload, batch, steps, warmup, rank, world
         torch.cuda.synchronize()
 
     # ---- device-resident timing ------------------------------------------------------------------------
+    # N > 1: the first replays of a graph with captured collectives still pay NCCL's lazy channel / NVLS set-up on 8 ranks (measured:
+    # 13.8 ms for the first 13 steps against 12.6 ms steady state, profiles/r02_comm_bench_n8.log); those are taken as part of
+    # building the step, before the W warm-up steps the contract asks for
+    settle = 8 if world > 1 else 0
+    for i in range(settle):
+        step(resident[i % npool])
     for i in range(warmup):
         step(resident[i % npool])
     sync_all()
@@ -518,7 +524,7 @@ def measure_workload(args, strategy, workload, batch, steps, warmup, rank, world
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": workload, "model": model_name, "audio_seconds": secs, "per_gpu_batch": B,
                    "global_batch": B * world, "parallelism": f"dp{world}", "dropout": "on (0.1, as the reference's training=True)",
-                   "step": step_desc, "cuda_graph": bool(use_graph),
+                   "step": step_desc, "cuda_graph": bool(use_graph), "settle_steps_before_warmup": settle,
                    "allreduce": ("none (1 replica)" if world == 1 else strategy.allreduce_description(model._prog)),
                    "l2": "working set per step (GBs of activations) >> 126 MB L2; 4 distinct input batches cycled; "
                          "per-kernel timings: CUDA-graph replays of [256 MB memset (L2 flush); kernel] minus replays of the memset alone"},

@@ -259,6 +259,8 @@ class Strategy:
                              torch.device("cuda", torch.cuda.current_device()))
 
     def _native_all_reduce(self, t, premul=None):
+        if os.environ.get("TETHYS_SKIP_AR") == "1":      # timing experiments only (tools/comm_bench.py): numerically wrong
+            return
         dt = _lib.TS_F32 if t.dtype == torch.float32 else _lib.TS_BF16
         self._ctx.check(self._ctx.lib.ts_comm_allreduce_bucket(self.comm, ptr(t), t.numel(), dt, ptr(premul), stream_ptr()))
 
