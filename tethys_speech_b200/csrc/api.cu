@@ -8,6 +8,11 @@ namespace ts {
 
 struct CtxHolder { Ctx c; };
 
+bool pdl_enabled() {
+  static const bool on = !(getenv("TETHYS_PDL") && atoi(getenv("TETHYS_PDL")) == 0);
+  return on;
+}
+
 int set_err(Ctx* c, int code, const char* fmt, ...) {
   char buf[1024];
   va_list ap;
@@ -117,13 +122,15 @@ int64_t ts_simt_downgrades(ts_ctx* ctx) {
   return c ? (int64_t)c->simt_downgrades : 0;
 }
 
-__global__ void step_state_set_kernel(unsigned long long* st, unsigned long long salt, unsigned long long step) { st[0] = salt; st[1] = step; }
-__global__ void step_state_advance_kernel(unsigned long long* st) { st[0] += 1ull; st[1] += 1ull; }
+__global__ void step_state_set_kernel(unsigned long long* st, unsigned long long salt, unsigned long long step) {
+  ts::pdl_enter(); st[0] = salt; st[1] = step; }
+__global__ void step_state_advance_kernel(unsigned long long* st) {
+  ts::pdl_enter(); st[0] += 1ull; st[1] += 1ull; }
 
 int ts_step_state_set(ts_ctx* ctx, uint64_t salt, int64_t step, void* stream) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   if (!c || step < 0) return TS_EINVAL;
-  step_state_set_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(c->d_state, salt, (unsigned long long)step);
+  ts::launch_k(step_state_set_kernel, 1, 1, 0, reinterpret_cast<cudaStream_t>(stream), c->d_state, salt, (unsigned long long)step);
   TS_LAUNCH_OK(c);
   return 0;
 }
@@ -139,7 +146,7 @@ int ts_step_state_get(ts_ctx* ctx, uint64_t* salt, int64_t* step) {
 int ts_step_state_advance(ts_ctx* ctx, void* stream) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   if (!c) return TS_EINVAL;
-  step_state_advance_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(c->d_state);
+  ts::launch_k(step_state_advance_kernel, 1, 1, 0, reinterpret_cast<cudaStream_t>(stream), c->d_state);
   TS_LAUNCH_OK(c);
   return 0;
 }

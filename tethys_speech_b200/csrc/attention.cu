@@ -13,6 +13,7 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(T* __restrict__ s, lon
                                                           float scale, int mask_mode, uint32_t thr, float inv_keep,
                                                           uint64_t seed, T* __restrict__ pdrop,
                                                           const unsigned long long* __restrict__ salt) {
+  ts::pdl_enter();
   if (thr) seed = salted_seed(seed, salt);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + warp;
@@ -75,6 +76,7 @@ template <typename T, int NCH>
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const T* __restrict__ p, T* __restrict__ dp, long long ld,
                                                           long long rows, int Tk, float scale, uint32_t thr, float inv_keep,
                                                           uint64_t seed, const unsigned long long* __restrict__ salt) {
+  ts::pdl_enter();
   if (thr) seed = salted_seed(seed, salt);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + warp;
@@ -128,7 +130,7 @@ static int softmax_fwd_t(Ctx* ctx, void* s, long long ld, int nbatch, int Tq, in
   T* pd = thr ? (T*)p_drop : nullptr;
   dim3 grid((unsigned)((rows + 7) / 8));
 #define SM_CASE(N)                                                                                                   \
-  case N: softmax_fwd_kernel<T, N><<<grid, 256, 0, st>>>((T*)s, ld, rows, Tq, Tk, scale, mask_mode, thr, ik, seed, pd, ctx->d_state); break;
+  case N: ts::launch_k(softmax_fwd_kernel<T, N>, grid, 256, 0, st, (T*)s, ld, rows, Tq, Tk, scale, mask_mode, thr, ik, seed, pd, ctx->d_state); break;
   switch (nch) {
     SM_CASE(1) SM_CASE(2) SM_CASE(3) SM_CASE(4) SM_CASE(5) SM_CASE(6) SM_CASE(7) SM_CASE(8)
     default: return set_err(ctx, TS_EUNSUPPORTED, "softmax: Tk=%d > 2048 unsupported", Tk);
@@ -156,7 +158,7 @@ static int softmax_bwd_t(Ctx* ctx, const void* p, void* dp, long long ld, int nb
   drop_params2(drop, &thr, &ik);
   dim3 grid((unsigned)((rows + 7) / 8));
 #define SMB_CASE(N) \
-  case N: softmax_bwd_kernel<T, N><<<grid, 256, 0, st>>>((const T*)p, (T*)dp, ld, rows, Tk, scale, thr, ik, seed, ctx->d_state); break;
+  case N: ts::launch_k(softmax_bwd_kernel<T, N>, grid, 256, 0, st, (const T*)p, (T*)dp, ld, rows, Tk, scale, thr, ik, seed, ctx->d_state); break;
   switch (nch) {
     SMB_CASE(1) SMB_CASE(2) SMB_CASE(3) SMB_CASE(4) SMB_CASE(5) SMB_CASE(6) SMB_CASE(7) SMB_CASE(8)
     default: return set_err(ctx, TS_EUNSUPPORTED, "softmax_bwd: Tk=%d > 2048 unsupported", Tk);

@@ -135,6 +135,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  ts::pdl_enter();   // prologue above overlaps the previous grid's tail (PDL, common.cuh)
   const uint32_t tST = tmem, tDPT = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384, tPZ = tmem + 448;
 
   if (warp == 0) {
@@ -158,6 +159,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
       }
     }
+    __syncwarp();
+    ts::pdl_tail();   // every operand load of this CTA is in flight: let the next grid's CTAs take the SMs as they free up
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp walks the schedule, one elected lane issues =====
     constexpr uint32_t idesc_s = ptx::make_idesc_bf16(B2_T, B2_T, 0, 0);       // S^T / dP^T: [128 keys] x [128 queries]
@@ -440,6 +443,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __restrict__ o_lo, const bf16* __restrict__ d_o,
                                                             long long o_ld, long long o_bs, int B, int nh, int Tq, float* __restrict__ dsum,
                                                             float* __restrict__ dq_accum) {
+  ts::pdl_enter();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * Tq * nh) return;
   const int h = (int)(idx % nh);
@@ -473,6 +477,7 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const bf16* __restri
 // dq (bf16, caller's strides) = dq_accum (fp32 [B, Tq, nh * 64])
 __global__ void __launch_bounds__(256) attn_bwd_dq_store_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, long long dq_ld,
                                                                 long long dq_bs, int B, int nh, int Tq) {
+  ts::pdl_enter();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;    // one thread per 8 elements
   const long long per_row = (long long)nh * B2_D / 8;
   if (idx >= (long long)B * Tq * per_row) return;
@@ -523,15 +528,15 @@ int attn_bwd2(Ctx* ctx, const ts_attn_desc* d, uint32_t drop_thr, float inv_keep
     attr = true;
   }
   const long long rows = (long long)d->batch * d->tq * d->heads;
-  attn_bwd_prep_kernel<<<cdiv(rows, 256), 256, 0, st>>>((const bf16*)d->o, (const bf16*)d->o_lo, (const bf16*)d->d_o, d->o_ld, d->o_bs, d->batch,
+  ts::launch_k(attn_bwd_prep_kernel, cdiv(rows, 256), 256, 0, st, (const bf16*)d->o, (const bf16*)d->o_lo, (const bf16*)d->d_o, d->o_ld, d->o_bs, d->batch,
                                                        d->heads, d->tq, d->dsum, d->dq_accum);
   TS_LAUNCH_OK(ctx);
   const int grid = p.items < ctx->num_sms ? p.items : ctx->num_sms;
-  if (d->mask_mode == 0) attn_bwd2_kernel<0><<<grid, kThreadsB2, kSmemB2, st>>>(tq, tk, tv, tdo, tdq, p, ctx->d_watchdog);
-  else attn_bwd2_kernel<1><<<grid, kThreadsB2, kSmemB2, st>>>(tq, tk, tv, tdo, tdq, p, ctx->d_watchdog);
+  if (d->mask_mode == 0) ts::launch_k(attn_bwd2_kernel<0>, grid, kThreadsB2, kSmemB2, st, tq, tk, tv, tdo, tdq, p, ctx->d_watchdog);
+  else ts::launch_k(attn_bwd2_kernel<1>, grid, kThreadsB2, kSmemB2, st, tq, tk, tv, tdo, tdq, p, ctx->d_watchdog);
   TS_LAUNCH_OK(ctx);
   const long long vec = (long long)d->batch * d->tq * d->heads * B2_D / 8;
-  attn_bwd_dq_store_kernel<<<cdiv(vec, 256), 256, 0, st>>>(d->dq_accum, (bf16*)d->dq, d->dq_ld, d->dq_bs, d->batch, d->heads, d->tq);
+  ts::launch_k(attn_bwd_dq_store_kernel, cdiv(vec, 256), 256, 0, st, d->dq_accum, (bf16*)d->dq, d->dq_ld, d->dq_bs, d->batch, d->heads, d->tq);
   TS_LAUNCH_OK(ctx);
   return 0;
 }

@@ -115,6 +115,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  ts::pdl_enter();   // prologue above overlaps the previous grid's tail (PDL, common.cuh)
   // TMEM columns: S0 [0,128) (P0 packed bf16 over [0,64)), S1 [128,256) (P1 over [128,192)), O0 [256,320), O1 [320,384)
 
   if (warp == 0) {
@@ -138,6 +139,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
       }
     }
+    __syncwarp();
+    ts::pdl_tail();   // every operand load of this CTA is in flight: let the next grid's CTAs take the SMs as they free up
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp walks the schedule (uniform control flow and addresses), one elected lane issues =====
     {
@@ -418,8 +421,8 @@ int attn_fwd2(Ctx* ctx, const ts_attn_desc* d, uint32_t drop_thr, float inv_keep
     attr = true;
   }
   const int grid = p.items < ctx->num_sms ? p.items : ctx->num_sms;
-  if (d->mask_mode == 0) attn_fwd2_kernel<0><<<grid, kThreads2, kSmem2, st>>>(tq, tk, tv, p, ctx->d_watchdog);
-  else attn_fwd2_kernel<1><<<grid, kThreads2, kSmem2, st>>>(tq, tk, tv, p, ctx->d_watchdog);
+  if (d->mask_mode == 0) ts::launch_k(attn_fwd2_kernel<0>, grid, kThreads2, kSmem2, st, tq, tk, tv, p, ctx->d_watchdog);
+  else ts::launch_k(attn_fwd2_kernel<1>, grid, kThreads2, kSmem2, st, tq, tk, tv, p, ctx->d_watchdog);
   TS_LAUNCH_OK(ctx);
   return 0;
 }

@@ -133,6 +133,7 @@ template <int MASK>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const AttnParams p, int* watchdog) {
+  ts::pdl_enter();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;  // 1024-byte aligned by declaration (no static shared memory in this kernel)
   if (!smem_aligned(smem, watchdog)) return;
@@ -393,6 +394,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do, const AttnParams p,
                    int* watchdog) {
+  ts::pdl_enter();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if (!smem_aligned(smem, watchdog)) return;
@@ -549,6 +551,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do, const AttnParams p,
                     int* watchdog) {
+  ts::pdl_enter();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if (!smem_aligned(smem, watchdog)) return;
@@ -782,8 +785,8 @@ int attn_fwd(Ctx* ctx, const ts_attn_desc* d, cudaStream_t st) {
     attr = true;
   }
   dim3 grid(cdiv(d->tq, AT_M), d->heads, d->batch);
-  if (d->mask_mode == 0) attn_fwd_kernel<0><<<grid, kFwdThreads, kFwdSmem, st>>>(tq, tk, tv, p, ctx->d_watchdog);
-  else attn_fwd_kernel<1><<<grid, kFwdThreads, kFwdSmem, st>>>(tq, tk, tv, p, ctx->d_watchdog);
+  if (d->mask_mode == 0) ts::launch_k(attn_fwd_kernel<0>, grid, kFwdThreads, kFwdSmem, st, tq, tk, tv, p, ctx->d_watchdog);
+  else ts::launch_k(attn_fwd_kernel<1>, grid, kFwdThreads, kFwdSmem, st, tq, tk, tv, p, ctx->d_watchdog);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
@@ -825,13 +828,13 @@ int attn_bwd(Ctx* ctx, const ts_attn_desc* d, cudaStream_t st) {
   }
   dim3 gq(cdiv(d->tq, AT_M), d->heads, d->batch), gk(cdiv(d->tk, AT_N), d->heads, d->batch);
   if (d->mask_mode == 0) {
-    attn_bwd_dq_kernel<0><<<gq, kBwdThreads, kDqSmem, st>>>(tq, tk64, tv64, tdo, p, ctx->d_watchdog);
+    ts::launch_k(attn_bwd_dq_kernel<0>, gq, kBwdThreads, kDqSmem, st, tq, tk64, tv64, tdo, p, ctx->d_watchdog);
     TS_LAUNCH_OK(ctx);
-    attn_bwd_dkv_kernel<0><<<gk, kBwdThreads, kDkvSmem, st>>>(tq64, tk, tv, tdo64, p, ctx->d_watchdog);
+    ts::launch_k(attn_bwd_dkv_kernel<0>, gk, kBwdThreads, kDkvSmem, st, tq64, tk, tv, tdo64, p, ctx->d_watchdog);
   } else {
-    attn_bwd_dq_kernel<1><<<gq, kBwdThreads, kDqSmem, st>>>(tq, tk64, tv64, tdo, p, ctx->d_watchdog);
+    ts::launch_k(attn_bwd_dq_kernel<1>, gq, kBwdThreads, kDqSmem, st, tq, tk64, tv64, tdo, p, ctx->d_watchdog);
     TS_LAUNCH_OK(ctx);
-    attn_bwd_dkv_kernel<1><<<gk, kBwdThreads, kDkvSmem, st>>>(tq64, tk, tv, tdo64, p, ctx->d_watchdog);
+    ts::launch_k(attn_bwd_dkv_kernel<1>, gk, kBwdThreads, kDkvSmem, st, tq64, tk, tv, tdo64, p, ctx->d_watchdog);
   }
   TS_LAUNCH_OK(ctx);
   return 0;

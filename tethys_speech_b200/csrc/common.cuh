@@ -60,6 +60,39 @@ int set_err(Ctx* c, int code, const char* fmt, ...);
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL). A train step is ~400 dependent launches of 5-200 us each; between two plain launches
+// the GPU drains the grid, flushes, and only then schedules the next grid's CTAs, which then run their own prologue
+// (barrier init, TMEM allocation, tensor-map fetch, index math). With the programmatic-stream-serialization attribute the next
+// grid's CTAs are scheduled as soon as every CTA of the running grid has passed pdl_enter() and an SM has room; they run
+// their prologue and block in griddepcontrol.wait until the previous grid has completed and its memory is visible.
+// Contract: EVERY kernel of this library executes pdl_enter() (all threads) before its first global-memory access, so the
+// chain is transitive (grid N+1 passes its wait only after grid N completed, which had itself waited for N-1).
+// TETHYS_PDL=0 launches without the attribute (griddepcontrol.* are then no-ops).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#ifndef TS_PDL_MODE
+#define TS_PDL_MODE 1
+#endif
+// mode 0: wait + trigger at entry; 1: wait only (the trigger is implicit at grid completion); 2: wait at entry, the persistent
+// tcgen05 kernels trigger from their producer warp once the last operand load has been issued (pdl_tail)
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); if (TS_PDL_MODE == 0) pdl_launch_dependents(); }
+__device__ __forceinline__ void pdl_tail() { if (TS_PDL_MODE == 2) pdl_launch_dependents(); }
+
+bool pdl_enabled();   // api.cu: reads TETHYS_PDL once
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<Args&&>(args)...);
+}
+
+// ----------------------------------------------------------------------------------------------
 // dtype helpers
 // ----------------------------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f(T v);

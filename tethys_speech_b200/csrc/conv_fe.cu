@@ -13,6 +13,7 @@ template <typename T, int K>
 __global__ void __launch_bounds__(256) conv0_fwd_kernel(const float* __restrict__ wave, const float* __restrict__ w,
                                                         T* __restrict__ y, long long y_rpb, int N, int T_, int C, int s,
                                                         int left) {
+  ts::pdl_enter();
   extern __shared__ float sw[];  // wave segment: C0_TILE_T*s + K floats
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * C0_TILE_T;
@@ -50,8 +51,8 @@ int conv0_fwd(Ctx* ctx, int dt, const float* wave, const void* w, void* y, long 
   TS_REQUIRE(ctx, C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, TS_ESHAPE, "conv0: C=%d unsupported", C);
   dim3 grid(cdiv(T_, C0_TILE_T), B);
   const size_t smem = (C0_TILE_T * s + 10) * sizeof(float);
-  if (dt == TS_F32) conv0_fwd_kernel<float, 10><<<grid, 256, smem, st>>>(wave, (const float*)w, (float*)y, y_rpb, N, T_, C, s, left);
-  else conv0_fwd_kernel<bf16, 10><<<grid, 256, smem, st>>>(wave, (const float*)w, (bf16*)y, y_rpb, N, T_, C, s, left);
+  if (dt == TS_F32) ts::launch_k(conv0_fwd_kernel<float, 10>, grid, 256, smem, st, wave, (const float*)w, (float*)y, y_rpb, N, T_, C, s, left);
+  else ts::launch_k(conv0_fwd_kernel<bf16, 10>, grid, 256, smem, st, wave, (const float*)w, (bf16*)y, y_rpb, N, T_, C, s, left);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
@@ -62,6 +63,7 @@ template <typename T, int K>
 __global__ void __launch_bounds__(256) conv0_wgrad_kernel(const float* __restrict__ wave, const T* __restrict__ dy,
                                                           long long dy_rpb, float* __restrict__ dw, int N, int T_, int C,
                                                           int s, int left) {
+  ts::pdl_enter();
   extern __shared__ float sm[];  // wave segment [C0_WG_ROWS*s + K] then accumulators [K*C]
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * C0_WG_ROWS;
@@ -118,11 +120,11 @@ int conv0_wgrad(Ctx* ctx, int dt, const float* wave, const void* dy, long long d
   if (dt == TS_F32) {
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(conv0_wgrad_kernel<float, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); set = true; }
-    conv0_wgrad_kernel<float, 10><<<grid, 256, smem, st>>>(wave, (const float*)dy, dy_rpb, dw, N, T_, C, s, left);
+    ts::launch_k(conv0_wgrad_kernel<float, 10>, grid, 256, smem, st, wave, (const float*)dy, dy_rpb, dw, N, T_, C, s, left);
   } else {
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(conv0_wgrad_kernel<bf16, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); set = true; }
-    conv0_wgrad_kernel<bf16, 10><<<grid, 256, smem, st>>>(wave, (const bf16*)dy, dy_rpb, dw, N, T_, C, s, left);
+    ts::launch_k(conv0_wgrad_kernel<bf16, 10>, grid, 256, smem, st, wave, (const bf16*)dy, dy_rpb, dw, N, T_, C, s, left);
   }
   TS_LAUNCH_OK(ctx);
   return 0;
@@ -132,6 +134,7 @@ int conv0_wgrad(Ctx* ctx, int dt, const float* wave, const void* dy, long long d
 template <typename T>
 __global__ void __launch_bounds__(256) posconv_pack_kernel(const T* __restrict__ x, T* __restrict__ xg, int B, int T_,
                                                            int C, int G, int R, int left) {
+  ts::pdl_enter();
   const int cpg = C / G, v8 = cpg / 8;
   const long long total = (long long)G * B * R * v8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -155,8 +158,8 @@ int posconv_pack(Ctx* ctx, int dt, const void* x, void* xg, int B, int T_, int C
   const int R = T_ + K - 1;
   const long long total = (long long)G * B * R * (C / G / 8);
   const int grid = (int)min((total + 255) / 256, (long long)ctx->num_sms * 16);
-  if (dt == TS_F32) posconv_pack_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)xg, B, T_, C, G, R, left);
-  else posconv_pack_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)xg, B, T_, C, G, R, left);
+  if (dt == TS_F32) ts::launch_k(posconv_pack_kernel<float>, grid, 256, 0, st, (const float*)x, (float*)xg, B, T_, C, G, R, left);
+  else ts::launch_k(posconv_pack_kernel<bf16>, grid, 256, 0, st, (const bf16*)x, (bf16*)xg, B, T_, C, G, R, left);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
@@ -164,6 +167,7 @@ int posconv_pack(Ctx* ctx, int dt, const void* x, void* xg, int B, int T_, int C
 // wt[g][K-1-j][o][c] = w[j][c][g*cpg+o]
 template <typename T>
 __global__ void posconv_flip_kernel(const T* __restrict__ w, T* __restrict__ wt, int K, int C, int G) {
+  ts::pdl_enter();
   const int cpg = C / G;
   const long long total = (long long)K * cpg * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -180,8 +184,8 @@ __global__ void posconv_flip_kernel(const T* __restrict__ w, T* __restrict__ wt,
 int posconv_flip_weight(Ctx* ctx, int dt, const void* w, void* wt, int K, int C, int G, cudaStream_t st) {
   const long long total = (long long)K * (C / G) * C;
   const int grid = (int)min((total + 255) / 256, (long long)ctx->num_sms * 16);
-  if (dt == TS_F32) posconv_flip_kernel<float><<<grid, 256, 0, st>>>((const float*)w, (float*)wt, K, C, G);
-  else posconv_flip_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)w, (bf16*)wt, K, C, G);
+  if (dt == TS_F32) ts::launch_k(posconv_flip_kernel<float>, grid, 256, 0, st, (const float*)w, (float*)wt, K, C, G);
+  else ts::launch_k(posconv_flip_kernel<bf16>, grid, 256, 0, st, (const bf16*)w, (bf16*)wt, K, C, G);
   TS_LAUNCH_OK(ctx);
   return 0;
 }

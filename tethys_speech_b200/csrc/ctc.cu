@@ -30,6 +30,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) ctc_kernel(const float* __restrict__ logits, const int* __restrict__ labels, int T_, int V, int L, int blank,
                                                   double* __restrict__ alpha_ws, double* __restrict__ lse_ws, float* __restrict__ loss_out,
                                                   T* __restrict__ dlogits, float grad_scale, int zero_infinity) {
+  ts::pdl_enter();
   extern __shared__ double sm[];         // [2][2L+1] recursion rows (fp64), then the extended labels [2L+1] (ints)
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const int* lab = labels + (long long)b * L;
@@ -127,8 +128,8 @@ int ctc_loss(Ctx* ctx, int dt, const float* logits, const int* labels, int B, in
   TS_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(workspace) & 7) == 0, TS_EINVAL, "ctc_loss: workspace must be 8-byte aligned");
   double* alpha = reinterpret_cast<double*>(workspace);
   double* lse = alpha + (long long)B * T_ * Smax;
-  if (dt == TS_F32) ctc_kernel<float><<<B, 256, smem, st>>>(logits, labels, T_, V, L, blank, alpha, lse, loss_out, (float*)dlogits, grad_scale, zero_infinity);
-  else if (dt == TS_BF16) ctc_kernel<bf16><<<B, 256, smem, st>>>(logits, labels, T_, V, L, blank, alpha, lse, loss_out, (bf16*)dlogits, grad_scale, zero_infinity);
+  if (dt == TS_F32) ts::launch_k(ctc_kernel<float>, B, 256, smem, st, logits, labels, T_, V, L, blank, alpha, lse, loss_out, (float*)dlogits, grad_scale, zero_infinity);
+  else if (dt == TS_BF16) ts::launch_k(ctc_kernel<bf16>, B, 256, smem, st, logits, labels, T_, V, L, blank, alpha, lse, loss_out, (bf16*)dlogits, grad_scale, zero_infinity);
   else return set_err(ctx, TS_EDTYPE, "ctc_loss: dlogits dtype %d", dt);
   TS_LAUNCH_OK(ctx);
   return 0;

@@ -12,6 +12,7 @@ static inline int ew_grid(Ctx* ctx, long long nvec) {
 }
 
 __global__ void cast_kernel(const float* __restrict__ s, bf16* __restrict__ d, long long n) {
+  ts::pdl_enter();
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
     if (i + 8 <= n) {
@@ -25,7 +26,7 @@ __global__ void cast_kernel(const float* __restrict__ s, bf16* __restrict__ d, l
 }
 int cast_f32_to_bf16(Ctx* ctx, const float* src, void* dst, long long n, cudaStream_t st) {
   if (n <= 0) return 0;
-  cast_kernel<<<ew_grid(ctx, (n + 7) / 8), 256, 0, st>>>(src, (bf16*)dst, n);
+  ts::launch_k(cast_kernel, ew_grid(ctx, (n + 7) / 8), 256, 0, st, src, (bf16*)dst, n);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
@@ -33,6 +34,7 @@ int cast_f32_to_bf16(Ctx* ctx, const float* src, void* dst, long long n, cudaStr
 // gradient buckets for the all-reduce in bf16 ("perf mode" of SURVEY §8e): dst = bf16(src * scale[0]) and back
 __global__ void __launch_bounds__(256) grad_pack_kernel(const float* __restrict__ s, bf16* __restrict__ d, long long n,
                                                         const float* __restrict__ scale) {
+  ts::pdl_enter();
   const float sc = scale ? __ldg(scale) : 1.f;
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
@@ -48,6 +50,7 @@ __global__ void __launch_bounds__(256) grad_pack_kernel(const float* __restrict_
   }
 }
 __global__ void __launch_bounds__(256) grad_unpack_kernel(const bf16* __restrict__ s, float* __restrict__ d, long long n) {
+  ts::pdl_enter();
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
     if (i + 8 <= n) {
@@ -63,7 +66,7 @@ int grad_pack_bf16(Ctx* ctx, const float* src, void* dst, long long n, const flo
   if (n <= 0) return 0;
   TS_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(src) & 31) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0), TS_EINVAL,
              "grad_pack_bf16: buckets must start on a 32-byte (fp32) / 16-byte (bf16) boundary");
-  grad_pack_kernel<<<ew_grid(ctx, (n + 7) / 8), 256, 0, st>>>(src, (bf16*)dst, n, scale_dev);
+  ts::launch_k(grad_pack_kernel, ew_grid(ctx, (n + 7) / 8), 256, 0, st, src, (bf16*)dst, n, scale_dev);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
@@ -71,7 +74,7 @@ int grad_unpack_bf16(Ctx* ctx, const void* src, float* dst, long long n, cudaStr
   if (n <= 0) return 0;
   TS_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0), TS_EINVAL,
              "grad_unpack_bf16: buckets must start on a 32-byte (fp32) / 16-byte (bf16) boundary");
-  grad_unpack_kernel<<<ew_grid(ctx, (n + 7) / 8), 256, 0, st>>>((const bf16*)src, dst, n);
+  ts::launch_k(grad_unpack_kernel, ew_grid(ctx, (n + 7) / 8), 256, 0, st, (const bf16*)src, dst, n);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
@@ -87,6 +90,7 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(256) ew_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
                                                  long long n, uint32_t thr, float inv_keep, uint64_t seed,
                                                  const unsigned long long* __restrict__ salt) {
+  ts::pdl_enter();
   if (MODE != 3 && thr) seed = salted_seed(seed, salt);
   const DropKey key = flat_drop_key(seed, thr);
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
@@ -134,8 +138,8 @@ static int ew_launch(Ctx* ctx, int dt, const void* a, const void* b, void* out, 
   uint32_t thr; float ik;
   drop_params(drop, &thr, &ik);
   const int grid = ew_grid(ctx, (n + 7) / 8);
-  if (dt == TS_F32) ew_kernel<float, MODE><<<grid, 256, 0, st>>>((const float*)a, (const float*)b, (float*)out, n, thr, ik, seed, ctx->d_state);
-  else if (dt == TS_BF16) ew_kernel<bf16, MODE><<<grid, 256, 0, st>>>((const bf16*)a, (const bf16*)b, (bf16*)out, n, thr, ik, seed, ctx->d_state);
+  if (dt == TS_F32) ts::launch_k(ew_kernel<float, MODE>, grid, 256, 0, st, (const float*)a, (const float*)b, (float*)out, n, thr, ik, seed, ctx->d_state);
+  else if (dt == TS_BF16) ts::launch_k(ew_kernel<bf16, MODE>, grid, 256, 0, st, (const bf16*)a, (const bf16*)b, (bf16*)out, n, thr, ik, seed, ctx->d_state);
   else return set_err(ctx, TS_EDTYPE, "elementwise: dtype %d", dt);
   TS_LAUNCH_OK(ctx);
   return 0;
@@ -159,6 +163,7 @@ int add_tensors(Ctx* ctx, int dt, const void* a, const void* b, void* y, long lo
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long ld, int rows, int cols,
                                                      float* __restrict__ out, int rows_per_block) {
+  ts::pdl_enter();
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + lane;
@@ -180,6 +185,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, long long ld, int rows, int cols,
                                                          float* __restrict__ out, int rows_per_block) {
+  ts::pdl_enter();
   __shared__ float red[8][256 + 8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + lane * 8;
@@ -224,15 +230,15 @@ int colsum_acc(Ctx* ctx, int dt, const void* x, long long ld, int rows, int cols
     int rpb = cdiv(rows, rb);
     rpb = ((rpb + 31) / 32) * 32;
     dim3 grid(cb, cdiv(rows, rpb));
-    if (dt == TS_F32) colsum_vec_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ld, rows, cols, out, rpb);
-    else colsum_vec_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, ld, rows, cols, out, rpb);
+    if (dt == TS_F32) ts::launch_k(colsum_vec_kernel<float>, grid, 256, 0, st, (const float*)x, ld, rows, cols, out, rpb);
+    else ts::launch_k(colsum_vec_kernel<bf16>, grid, 256, 0, st, (const bf16*)x, ld, rows, cols, out, rpb);
     TS_LAUNCH_OK(ctx);
     return 0;
   }
   const int rpb = 512;
   dim3 grid(cdiv(cols, 32), cdiv(rows, rpb));
-  if (dt == TS_F32) colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ld, rows, cols, out, rpb);
-  else colsum_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, ld, rows, cols, out, rpb);
+  if (dt == TS_F32) ts::launch_k(colsum_kernel<float>, grid, 256, 0, st, (const float*)x, ld, rows, cols, out, rpb);
+  else ts::launch_k(colsum_kernel<bf16>, grid, 256, 0, st, (const bf16*)x, ld, rows, cols, out, rpb);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
@@ -246,6 +252,7 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(256) ew_colsum_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int rows,
                                                         int cols, float* __restrict__ csum, int rows_per_block, uint32_t thr, float inv_keep,
                                                         uint64_t seed, const unsigned long long* __restrict__ salt) {
+  ts::pdl_enter();
   __shared__ float red[8][256 + 8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + lane * 8;
@@ -308,8 +315,8 @@ static int ew_colsum_launch(Ctx* ctx, int dt, const void* a, const void* b, void
   int rpb = cdiv(rows, rb);
   rpb = ((rpb + 15) / 16) * 16;
   dim3 grid(cb, cdiv(rows, rpb));
-  if (dt == TS_F32) ew_colsum_kernel<float, MODE><<<grid, 256, 0, st>>>((const float*)a, (const float*)b, (float*)out, rows, cols, csum, rpb, thr, ik, seed, ctx->d_state);
-  else if (dt == TS_BF16) ew_colsum_kernel<bf16, MODE><<<grid, 256, 0, st>>>((const bf16*)a, (const bf16*)b, (bf16*)out, rows, cols, csum, rpb, thr, ik, seed, ctx->d_state);
+  if (dt == TS_F32) ts::launch_k(ew_colsum_kernel<float, MODE>, grid, 256, 0, st, (const float*)a, (const float*)b, (float*)out, rows, cols, csum, rpb, thr, ik, seed, ctx->d_state);
+  else if (dt == TS_BF16) ts::launch_k(ew_colsum_kernel<bf16, MODE>, grid, 256, 0, st, (const bf16*)a, (const bf16*)b, (bf16*)out, rows, cols, csum, rpb, thr, ik, seed, ctx->d_state);
   else return set_err(ctx, TS_EDTYPE, "ew_colsum: dtype %d", dt);
   TS_LAUNCH_OK(ctx);
   return 0;
@@ -325,6 +332,7 @@ int dropout_colsum(Ctx* ctx, int dt, const void* x, void* y, int rows, int cols,
 // [B,R,C] -> [B,C,R] through a 32x32 smem tile (coalesced both ways)
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) transpose_kernel(const TI* __restrict__ x, TO* __restrict__ y, int R, int C) {
+  ts::pdl_enter();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -341,9 +349,9 @@ __global__ void __launch_bounds__(256) transpose_kernel(const TI* __restrict__ x
 }
 int transpose_inner(Ctx* ctx, int dt_in, int dt_out, const void* x, void* y, int B, int R, int C, cudaStream_t st) {
   dim3 grid(cdiv(C, 32), cdiv(R, 32), B);
-  if (dt_in == TS_F32 && dt_out == TS_F32) transpose_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, R, C);
-  else if (dt_in == TS_F32 && dt_out == TS_BF16) transpose_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)x, (bf16*)y, R, C);
-  else if (dt_in == TS_BF16 && dt_out == TS_BF16) transpose_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)y, R, C);
+  if (dt_in == TS_F32 && dt_out == TS_F32) ts::launch_k(transpose_kernel<float, float>, grid, 256, 0, st, (const float*)x, (float*)y, R, C);
+  else if (dt_in == TS_F32 && dt_out == TS_BF16) ts::launch_k(transpose_kernel<float, bf16>, grid, 256, 0, st, (const float*)x, (bf16*)y, R, C);
+  else if (dt_in == TS_BF16 && dt_out == TS_BF16) ts::launch_k(transpose_kernel<bf16, bf16>, grid, 256, 0, st, (const bf16*)x, (bf16*)y, R, C);
   else return set_err(ctx, TS_EDTYPE, "transpose: dtype %d->%d", dt_in, dt_out);
   TS_LAUNCH_OK(ctx);
   return 0;

@@ -20,6 +20,7 @@ constexpr int SB_M = 64, SB_N = 64, SB_K = 16;
 
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
+  ts::pdl_enter();
   __shared__ float As[SB_K][SB_M + 4];
   __shared__ float Bs[SB_K][SB_N + 4];
   const int b1 = blockIdx.z % p.nb1, b2 = blockIdx.z / p.nb1;
@@ -112,9 +113,9 @@ int gemm_simt(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
   }
   TS_REQUIRE(ctx, d->m > 0 && d->n > 0 && d->k > 0, TS_ESHAPE, "gemm: empty problem m=%d n=%d k=%d", d->m, d->n, d->k);
   dim3 grid(cdiv(d->m, SB_M), cdiv(d->n, SB_N), nb1 * nb2);
-  if (d->in_dtype == TS_F32 && d->out_dtype == TS_F32) gemm_simt_kernel<float, float><<<grid, 256, 0, st>>>(p);
-  else if (d->in_dtype == TS_BF16 && d->out_dtype == TS_BF16) gemm_simt_kernel<bf16, bf16><<<grid, 256, 0, st>>>(p);
-  else if (d->in_dtype == TS_BF16 && d->out_dtype == TS_F32) gemm_simt_kernel<bf16, float><<<grid, 256, 0, st>>>(p);
+  if (d->in_dtype == TS_F32 && d->out_dtype == TS_F32) ts::launch_k(gemm_simt_kernel<float, float>, grid, 256, 0, st, p);
+  else if (d->in_dtype == TS_BF16 && d->out_dtype == TS_BF16) ts::launch_k(gemm_simt_kernel<bf16, bf16>, grid, 256, 0, st, p);
+  else if (d->in_dtype == TS_BF16 && d->out_dtype == TS_F32) ts::launch_k(gemm_simt_kernel<bf16, float>, grid, 256, 0, st, p);
   else return set_err(ctx, TS_EDTYPE, "gemm_simt: unsupported dtype combination in=%d out=%d", d->in_dtype, d->out_dtype);
   TS_LAUNCH_OK(ctx);
   return 0;

@@ -219,6 +219,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
   ptx::tc_fence_after();
   const uint32_t tmem_base = early ? 0u : *tmem_slot;   // warp 0 never touches TMEM
+  ts::pdl_enter();   // prologue above overlaps the previous grid's tail (PDL, common.cuh)
   if (threadIdx.x == 32) trace_stamp(p, 1);   // setup done (barriers, TMEM, CTA / cluster sync)
 
   if (warp == 0) {
@@ -260,6 +261,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
     if (CTAS == 2 && rank == 0) { __syncwarp(); ptx::cluster_wait(); }   // second half of the setup barrier (completed long ago)
+    __syncwarp();
+    ts::pdl_tail();   // every operand load of this CTA is in flight: let the next grid's CTAs take the SMs as they free up
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0 && rank == 0) {
@@ -604,17 +607,19 @@ static int launch_tc(Ctx* ctx, const ts_gemm_desc* d, const CUtensorMap& ta, con
   }
   if (CTAS == 1) {
     const int grid = ep.total_tiles < ctx->num_sms ? ep.total_tiles : ctx->num_sms;
-    kern<<<grid, kThreads, Cfg::kSmem, st>>>(ta, tb, tc, tp, ep, ctx->d_watchdog);
+    ts::launch_k(kern, grid, kThreads, Cfg::kSmem, st, ta, tb, tc, tp, ep, ctx->d_watchdog);
   } else {
     // one cluster of two CTAs (one TPC) per 256-row tile stream
     const int pairs = ctx->num_sms / 2;
     const int grid = 2 * (ep.total_tiles < pairs ? ep.total_tiles : pairs);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid, 1, 1); cfg.blockDim = dim3(kThreads, 1, 1); cfg.dynamicSmemBytes = Cfg::kSmem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     int* wd = ctx->d_watchdog;
     TS_CUDA_OK(ctx, cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tp, ep, wd));
   }

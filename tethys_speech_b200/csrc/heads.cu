@@ -14,6 +14,7 @@ template <typename T>
 __global__ void __launch_bounds__(VQ_WARPS * 32) vq_fwd_kernel(const T* __restrict__ z, const float* __restrict__ cb,
                                                                T* __restrict__ q, long long* __restrict__ idx,
                                                                int* __restrict__ hist, int M, int G, int V, int D) {
+  ts::pdl_enter();
   extern __shared__ float sm[];
   float* scb = sm;                       // [32][D+1] codebook chunk
   float* sz = sm + 32 * (D + 1);         // [VQ_WARPS][D] frames
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(VQ_WARPS * 32) vq_fwd_kernel(const T* __restri
 template <typename T, int D>
 __global__ void __launch_bounds__(256) vq_fwd_frames_kernel(const T* __restrict__ z, const float* __restrict__ cb, T* __restrict__ q,
                                                             long long* __restrict__ idx, int* __restrict__ hist, int M, int G, int V) {
+  ts::pdl_enter();
   extern __shared__ float sm[];
   float* scb = sm;                                   // [V][D]
   float* sbest = sm + (size_t)V * D;                 // [8][32]
@@ -162,7 +164,7 @@ static int vq_fwd_frames(Ctx* ctx, const void* z, const float* codebook, void* q
   static bool attr = false;
   if (!attr) { TS_CUDA_OK(ctx, cudaFuncSetAttribute(vq_fwd_frames_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
   dim3 grid(cdiv(M, 32), G);
-  vq_fwd_frames_kernel<T, D><<<grid, 256, smem, st>>>((const T*)z, codebook, (T*)q, idx, hist, M, G, V);
+  ts::launch_k(vq_fwd_frames_kernel<T, D>, grid, 256, smem, st, (const T*)z, codebook, (T*)q, idx, hist, M, G, V);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
@@ -187,10 +189,10 @@ int vq_fwd(Ctx* ctx, int dt, const void* z, const float* codebook, void* q, long
   dim3 grid(cdiv(M, VQ_WARPS), G);
   if (dt == TS_F32) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(vq_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    vq_fwd_kernel<float><<<grid, VQ_WARPS * 32, smem, st>>>((const float*)z, codebook, (float*)q, idx, hist, M, G, V, D);
+    ts::launch_k(vq_fwd_kernel<float>, grid, VQ_WARPS * 32, smem, st, (const float*)z, codebook, (float*)q, idx, hist, M, G, V, D);
   } else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(vq_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    vq_fwd_kernel<bf16><<<grid, VQ_WARPS * 32, smem, st>>>((const bf16*)z, codebook, (bf16*)q, idx, hist, M, G, V, D);
+    ts::launch_k(vq_fwd_kernel<bf16>, grid, VQ_WARPS * 32, smem, st, (const bf16*)z, codebook, (bf16*)q, idx, hist, M, G, V, D);
   }
   TS_LAUNCH_OK(ctx);
   return 0;
@@ -198,6 +200,7 @@ int vq_fwd(Ctx* ctx, int dt, const void* z, const float* codebook, void* q, long
 
 // perplexity = mean_g exp(-sum_v p*log(p+1e-10)), p = clip(count/M, 1e-10, 1)   (V:653-660)
 __global__ void vq_perplexity_kernel(const int* __restrict__ hist, float* __restrict__ out, int M, int G, int V) {
+  ts::pdl_enter();
   __shared__ float red[32];
   float total = 0.f;
   for (int g = 0; g < G; ++g) {
@@ -213,7 +216,7 @@ __global__ void vq_perplexity_kernel(const int* __restrict__ hist, float* __rest
   if (threadIdx.x == 0) out[0] = total / G;
 }
 int vq_perplexity(Ctx* ctx, const int* hist, float* perplexity, int M, int G, int V, cudaStream_t st) {
-  vq_perplexity_kernel<<<1, 256, 0, st>>>(hist, perplexity, M, G, V);
+  ts::launch_k(vq_perplexity_kernel, 1, 256, 0, st, hist, perplexity, M, G, V);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
@@ -221,6 +224,7 @@ int vq_perplexity(Ctx* ctx, const int* hist, float* perplexity, int M, int G, in
 template <typename T>
 __global__ void vq_bwd_kernel(const T* __restrict__ dq, const long long* __restrict__ idx, float* __restrict__ dcb, int M,
                               int G, int V, int D) {
+  ts::pdl_enter();
   const long long total = (long long)M * G * D;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(i % D);
@@ -235,8 +239,8 @@ int vq_bwd(Ctx* ctx, int dt, const void* dq, const long long* idx, float* dcodeb
            cudaStream_t st) {
   const long long total = (long long)M * G * D;
   const int grid = (int)min((total + 255) / 256, (long long)ctx->num_sms * 16);
-  if (dt == TS_F32) vq_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dq, idx, dcodebook, M, G, V, D);
-  else vq_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dq, idx, dcodebook, M, G, V, D);
+  if (dt == TS_F32) ts::launch_k(vq_bwd_kernel<float>, grid, 256, 0, st, (const float*)dq, idx, dcodebook, M, G, V, D);
+  else ts::launch_k(vq_bwd_kernel<bf16>, grid, 256, 0, st, (const bf16*)dq, idx, dcodebook, M, G, V, D);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
@@ -250,6 +254,7 @@ __global__ void __launch_bounds__(CL_WARPS * 32) contrastive_kernel(const float*
                                                                     long long neg_ts, T* __restrict__ dS, long long ld_ds,
                                                                     float* __restrict__ logits, float* __restrict__ loss_sum,
                                                                     int B, int T_, int K, float inv_temp, float gscale) {
+  ts::pdl_enter();
   extern __shared__ float sm[];  // [CL_WARPS][ld_ds] gradient rows
   __shared__ float sloss[CL_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -306,11 +311,11 @@ int contrastive_fwd_bwd(Ctx* ctx, int dt, const float* S, long long ld, const in
   dim3 grid((unsigned)((rows + CL_WARPS - 1) / CL_WARPS));
   if (dt == TS_F32) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(contrastive_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    contrastive_kernel<float><<<grid, CL_WARPS * 32, smem, st>>>(S, ld, neg, neg_bs, neg_ts, (float*)dS, ld_ds, logits,
+    ts::launch_k(contrastive_kernel<float>, grid, CL_WARPS * 32, smem, st, S, ld, neg, neg_bs, neg_ts, (float*)dS, ld_ds, logits,
                                                                  loss_sum, B, T_, K, 1.f / temp, grad_scale);
   } else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(contrastive_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    contrastive_kernel<bf16><<<grid, CL_WARPS * 32, smem, st>>>(S, ld, neg, neg_bs, neg_ts, (bf16*)dS, ld_ds, logits, loss_sum,
+    ts::launch_k(contrastive_kernel<bf16>, grid, CL_WARPS * 32, smem, st, S, ld, neg, neg_bs, neg_ts, (bf16*)dS, ld_ds, logits, loss_sum,
                                                                 B, T_, K, 1.f / temp, grad_scale);
   }
   TS_LAUNCH_OK(ctx);

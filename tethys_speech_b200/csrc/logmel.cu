@@ -88,6 +88,7 @@ template <typename TO>
 __global__ void __launch_bounds__(256, 4) logmel_kernel(const float* __restrict__ wave, long long wave_bs, int n_samples,
                                                      const LogmelTables* __restrict__ tab, TO* __restrict__ out, int n_frames,
                                                      int mel_major /*0: [B,F,80]  1: [B,80,F]*/) {
+  ts::pdl_enter();
   extern __shared__ __align__(16) unsigned char lm_smem[];
   float* s_wave = reinterpret_cast<float*>(lm_smem);
   float2* s_buf = reinterpret_cast<float2*>(s_wave + LM_WAVE);
@@ -231,8 +232,8 @@ int logmel(Ctx* ctx, const float* wave, long long wave_bs, int batch, int n_samp
     attr = true;
   }
   dim3 grid(cdiv(nf, LM_FPB), batch);
-  if (out_dtype == TS_F32) logmel_kernel<float><<<grid, 256, kLogmelSmem, st>>>(wave, wave_bs, n_samples, tab, (float*)out, nf, mel_major);
-  else if (out_dtype == TS_BF16) logmel_kernel<bf16><<<grid, 256, kLogmelSmem, st>>>(wave, wave_bs, n_samples, tab, (bf16*)out, nf, mel_major);
+  if (out_dtype == TS_F32) ts::launch_k(logmel_kernel<float>, grid, 256, kLogmelSmem, st, wave, wave_bs, n_samples, tab, (float*)out, nf, mel_major);
+  else if (out_dtype == TS_BF16) ts::launch_k(logmel_kernel<bf16>, grid, 256, kLogmelSmem, st, wave, wave_bs, n_samples, tab, (bf16*)out, nf, mel_major);
   else return set_err(ctx, TS_EDTYPE, "logmel: output dtype %d", out_dtype);
   TS_LAUNCH_OK(ctx);
   return 0;

@@ -10,6 +10,7 @@ namespace ts {
 // expanded [B, L] (float 0/1) from starts [B, L] (uint8)
 __global__ void span_expand_kernel(const unsigned char* __restrict__ start, float* __restrict__ expanded, int L, int mask_length,
                                    long long total) {
+  ts::pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int t = (int)(i % L);
@@ -24,6 +25,7 @@ __global__ void span_expand_kernel(const unsigned char* __restrict__ start, floa
 template <typename T>
 __global__ void __launch_bounds__(256) span_apply_kernel(const T* __restrict__ x, const float* __restrict__ expanded, T* __restrict__ y,
                                                          int T_, int H, int axis, long long nvec) {
+  ts::pdl_enter();
   const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nvec) return;
   const long long e = v * 8;
@@ -50,11 +52,11 @@ int span_mask_apply(Ctx* ctx, int dt, const void* x, const unsigned char* start,
   TS_REQUIRE(ctx, x && start && y && expanded, TS_EINVAL, "span_mask: null pointer");
   const int L = axis == 1 ? T_ : H;
   const long long total = (long long)B * L;
-  span_expand_kernel<<<cdiv(total, 256), 256, 0, st>>>(start, expanded, L, mask_length, total);
+  ts::launch_k(span_expand_kernel, cdiv(total, 256), 256, 0, st, start, expanded, L, mask_length, total);
   TS_LAUNCH_OK(ctx);
   const long long nvec = (long long)B * T_ * H / 8;
-  if (dt == TS_F32) span_apply_kernel<float><<<cdiv(nvec, 256), 256, 0, st>>>((const float*)x, expanded, (float*)y, T_, H, axis, nvec);
-  else if (dt == TS_BF16) span_apply_kernel<bf16><<<cdiv(nvec, 256), 256, 0, st>>>((const bf16*)x, expanded, (bf16*)y, T_, H, axis, nvec);
+  if (dt == TS_F32) ts::launch_k(span_apply_kernel<float>, cdiv(nvec, 256), 256, 0, st, (const float*)x, expanded, (float*)y, T_, H, axis, nvec);
+  else if (dt == TS_BF16) ts::launch_k(span_apply_kernel<bf16>, cdiv(nvec, 256), 256, 0, st, (const bf16*)x, expanded, (bf16*)y, T_, H, axis, nvec);
   else return set_err(ctx, TS_EDTYPE, "span_mask: dtype %d", dt);
   TS_LAUNCH_OK(ctx);
   return 0;
@@ -66,6 +68,7 @@ int span_mask_apply(Ctx* ctx, int dt, const void* x, const unsigned char* start,
 // counted against the row held in smem (T^2 compares, T <= a few thousand); rank < k writes out[rank]; the list is tiled to
 // `num_neg` entries when k = min(num_neg, T - 1) < num_neg (V:925-931).
 __global__ void __launch_bounds__(256) negatives_kernel(const int* __restrict__ r, int T_, int k, int num_neg, int* __restrict__ out) {
+  ts::pdl_enter();
   extern __shared__ int srow[];
   const int* row = r + (long long)blockIdx.x * T_;
   int* o = out + (long long)blockIdx.x * num_neg;
@@ -87,7 +90,7 @@ int sample_negatives(Ctx* ctx, const int* rand, int B, int T_, int num_neg, int*
   if (k < 1) k = 1;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(negatives_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024 * 4); attr = true; }
-  negatives_kernel<<<B, 256, (size_t)T_ * 4, st>>>(rand, T_, k, num_neg, out);
+  ts::launch_k(negatives_kernel, B, 256, (size_t)T_ * 4, st, rand, T_, k, num_neg, out);
   TS_LAUNCH_OK(ctx);
   return 0;
 }

@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, co
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      T* __restrict__ y, T* __restrict__ sum_out, float* __restrict__ mean,
                                                      float* __restrict__ rstd, int rows, int cols, float eps) {
+  ts::pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const T* __restrict__ dy
                                                         const float* __restrict__ gamma, const float* __restrict__ mean,
                                                         const float* __restrict__ rstd, const T* __restrict__ dres,
                                                         T* __restrict__ dx, int rows, int cols) {
+  ts::pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -125,6 +127,7 @@ __global__ void __launch_bounds__(256) ln_bwd_param_kernel(const T* __restrict__
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta, int rows,
                                                            int cols, int rows_per_block) {
+  ts::pdl_enter();
   __shared__ float red[2][8][256 + 8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + lane * 8;
@@ -185,6 +188,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_fused_kernel(const T* __restric
                                                            float* __restrict__ dbeta, T* __restrict__ drop_out, float* __restrict__ drop_csum,
                                                            uint32_t thr, float inv_keep, uint64_t seed, const unsigned long long* __restrict__ salt,
                                                            int rows, int cols) {
+  ts::pdl_enter();
   __shared__ float red[8][256 + 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float ag[NCH][8], ab[NCH][8], ac[NCH][8];   // ac: column sums of the dropped copy (dead code without DROP)
@@ -278,7 +282,7 @@ static int ln_fwd_t(Ctx* ctx, const void* x, const void* res, const float* gamma
   dim3 grid(cdiv(rows, 8));
 #define LN_FWD_CASE(N)                                                                                         \
   case N:                                                                                                      \
-    ln_fwd_kernel<T, N><<<grid, 256, 0, st>>>((const T*)x, (const T*)res, gamma, beta, (T*)y, (T*)sum_out, mean, \
+    ts::launch_k(ln_fwd_kernel<T, N>, grid, 256, 0, st, (const T*)x, (const T*)res, gamma, beta, (T*)y, (T*)sum_out, mean, \
                                               rstd, rows, cols, eps);                                          \
     break;
   switch (nch) {
@@ -315,11 +319,11 @@ static int ln_bwd_t(Ctx* ctx, const void* dy, const void* x, const float* gamma,
 #define LN_BWD_CASE(N)                                                                                                               \
   case N:                                                                                                                            \
     if (drop_out)                                                                                                                    \
-      ln_bwd_fused_kernel<T, N, true><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx,     \
+      ts::launch_k(ln_bwd_fused_kernel<T, N, true>, grid, 256, 0, st, (const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx,     \
                                                             dgamma, dbeta, (T*)drop_out, drop_csum, thr, ik, drop_seed, ctx->d_state, \
                                                             rows, cols);                                                             \
     else                                                                                                                             \
-      ln_bwd_fused_kernel<T, N, false><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx,    \
+      ts::launch_k(ln_bwd_fused_kernel<T, N, false>, grid, 256, 0, st, (const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx,    \
                                                              dgamma, dbeta, nullptr, nullptr, 0u, 1.f, 0ull, ctx->d_state, rows, cols); \
     break;
   switch (nch) {
@@ -366,6 +370,7 @@ static inline int gn_rows_per_block(Ctx* ctx, long long rows_per_batch, int B, i
 }
 
 __global__ void gn_zero_accum(double* accum, int n) {
+  ts::pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) accum[i] = 0.0;
 }
@@ -373,6 +378,7 @@ __global__ void gn_zero_accum(double* accum, int n) {
 template <typename T>
 __global__ void __launch_bounds__(256, 4) gn_stats_kernel(const T* __restrict__ x, double* __restrict__ accum, int T_,
                                                        int C, int G, long long rpb, int rows_per_block) {
+  ts::pdl_enter();
   __shared__ double sacc[64 * 2];
   const int b = blockIdx.y;
   const int tpr = C / 8, rpi = 256 / tpr;
@@ -411,6 +417,7 @@ __global__ void __launch_bounds__(256, 4) gn_stats_kernel(const T* __restrict__ 
 
 __global__ void gn_finalize_kernel(const double* __restrict__ accum, float* mean, float* rstd, int n, double cnt,
                                    float eps) {
+  ts::pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double mu = accum[2 * i] / cnt;
@@ -424,12 +431,12 @@ int groupnorm_stats(Ctx* ctx, int dt, const void* x, double* accum, float* mean,
                     int G, long long rpb, float eps, cudaStream_t st) {
   TS_REQUIRE(ctx, C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0 && G <= 64 && C % G == 0 && (C / G) % 8 == 0,
              TS_ESHAPE, "groupnorm: unsupported C=%d G=%d", C, G);
-  gn_zero_accum<<<cdiv(B * G * 2, 256), 256, 0, st>>>(accum, B * G * 2);
+  ts::launch_k(gn_zero_accum, cdiv(B * G * 2, 256), 256, 0, st, accum, B * G * 2);
   const int rows = gn_rows_per_block(ctx, T_, B, C);
   dim3 grid(cdiv(T_, rows), B);
-  if (dt == TS_F32) gn_stats_kernel<float><<<grid, 256, 0, st>>>((const float*)x, accum, T_, C, G, rpb, rows);
-  else gn_stats_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, accum, T_, C, G, rpb, rows);
-  gn_finalize_kernel<<<cdiv(B * G, 256), 256, 0, st>>>(accum, mean, rstd, B * G, (double)T_ * (C / G), eps);
+  if (dt == TS_F32) ts::launch_k(gn_stats_kernel<float>, grid, 256, 0, st, (const float*)x, accum, T_, C, G, rpb, rows);
+  else ts::launch_k(gn_stats_kernel<bf16>, grid, 256, 0, st, (const bf16*)x, accum, T_, C, G, rpb, rows);
+  ts::launch_k(gn_finalize_kernel, cdiv(B * G, 256), 256, 0, st, accum, mean, rstd, B * G, (double)T_ * (C / G), eps);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
@@ -440,6 +447,7 @@ __global__ void __launch_bounds__(256, 4) gn_gelu_fwd_kernel(const T* __restrict
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           T* __restrict__ y, long long y_rpb, int y_left, int T_, int C,
                                                           int G, int rows_per_block) {
+  ts::pdl_enter();
   const int b = blockIdx.y;
   const int tpr = C / 8, rpi = 256 / tpr;
   const int tc = threadIdx.x % tpr, tr = threadIdx.x / tpr;
@@ -497,10 +505,10 @@ int groupnorm_gelu_fwd(Ctx* ctx, int dt, const void* x, long long x_rpb, const f
   const int rows = gn_rows_per_block(ctx, y_rpb, B, C);
   dim3 grid(cdiv(y_rpb, rows), B);
   if (dt == TS_F32)
-    gn_gelu_fwd_kernel<float, true><<<grid, 256, 0, st>>>((const float*)x, x_rpb, mean, rstd, gamma, beta, (float*)y, y_rpb,
+    ts::launch_k(gn_gelu_fwd_kernel<float, true>, grid, 256, 0, st, (const float*)x, x_rpb, mean, rstd, gamma, beta, (float*)y, y_rpb,
                                                           y_left, T_, C, G, rows);
   else
-    gn_gelu_fwd_kernel<bf16, true><<<grid, 256, 0, st>>>((const bf16*)x, x_rpb, mean, rstd, gamma, beta, (bf16*)y, y_rpb,
+    ts::launch_k(gn_gelu_fwd_kernel<bf16, true>, grid, 256, 0, st, (const bf16*)x, x_rpb, mean, rstd, gamma, beta, (bf16*)y, y_rpb,
                                                          y_left, T_, C, G, rows);
   TS_LAUNCH_OK(ctx);
   return 0;
@@ -512,9 +520,9 @@ int groupnorm_fwd(Ctx* ctx, int dt, const void* x, const float* mean, const floa
   const int rows = gn_rows_per_block(ctx, T_, B, C);
   dim3 grid(cdiv(T_, rows), B);
   if (dt == TS_F32)
-    gn_gelu_fwd_kernel<float, false><<<grid, 256, 0, st>>>((const float*)x, T_, mean, rstd, gamma, beta, (float*)y, T_, 0, T_, C, G, rows);
+    ts::launch_k(gn_gelu_fwd_kernel<float, false>, grid, 256, 0, st, (const float*)x, T_, mean, rstd, gamma, beta, (float*)y, T_, 0, T_, C, G, rows);
   else
-    gn_gelu_fwd_kernel<bf16, false><<<grid, 256, 0, st>>>((const bf16*)x, T_, mean, rstd, gamma, beta, (bf16*)y, T_, 0, T_, C, G, rows);
+    ts::launch_k(gn_gelu_fwd_kernel<bf16, false>, grid, 256, 0, st, (const bf16*)x, T_, mean, rstd, gamma, beta, (bf16*)y, T_, 0, T_, C, G, rows);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
@@ -569,6 +577,7 @@ __global__ void __launch_bounds__(256, 2) gn_gelu_bwd1_kernel(const T* __restric
                                                               T* __restrict__ dx, long long dx_rpb, float* __restrict__ dgamma,
                                                               float* __restrict__ dbeta, double* __restrict__ accum, int T_,
                                                               int C, int G, int rows_per_block) {
+  ts::pdl_enter();
   extern __shared__ float smf[];  // [2][C] floats then [2*G] doubles (8-byte aligned by construction)
   float* sg = smf;
   float* sb = smf + C;
@@ -642,6 +651,7 @@ __global__ void __launch_bounds__(256, 4) gn_gelu_bwd2_kernel(const T* __restric
                                                            const float* __restrict__ gamma, T* __restrict__ dx,
                                                            long long dx_rpb, const double* __restrict__ accum, int T_, int C,
                                                            int G, int rows_per_block) {
+  ts::pdl_enter();
   const int b = blockIdx.y;
   const int tpr = C / 8, rpi = 256 / tpr;
   const int tc = threadIdx.x % tpr, tr = threadIdx.x / tpr;
@@ -697,7 +707,7 @@ int groupnorm_gelu_bwd(Ctx* ctx, int dt, const void* da, long long da_rpb, const
                        cudaStream_t st) {
   Col2imSrc c;
   if (col) c = *col; else { c.dcol = nullptr; c.rows_per_batch = 0; c.t_next = 0; c.k = 0; c.s = 1; c.left = 0; }
-  gn_zero_accum<<<cdiv(B * G * 2, 256), 256, 0, st>>>(accum, B * G * 2);
+  ts::launch_k(gn_zero_accum, cdiv(B * G * 2, 256), 256, 0, st, accum, B * G * 2);
   const size_t smem = 2 * C * sizeof(float) + 2 * G * sizeof(double);
   const int rows1 = gn_rows_per_block(ctx, T_, B, C), rows2 = gn_rows_per_block(ctx, dx_rpb, B, C);
   dim3 g1(cdiv(T_, rows1), B), g2(cdiv(dx_rpb, rows2), B);
@@ -706,15 +716,15 @@ int groupnorm_gelu_bwd(Ctx* ctx, int dt, const void* da, long long da_rpb, const
   else if (c.k == 3 && c.s == 2) ks = 3 * 8 + 2;
   else if (c.k == 2 && c.s == 2) ks = 2 * 8 + 2;
 #define GN_BWD1(TT, KS)                                                                                                   \
-  gn_gelu_bwd1_kernel<TT, KS><<<g1, 256, smem, st>>>((const TT*)da, da_rpb, c, (const TT*)x, x_rpb, mean, rstd, gamma, beta, \
+  ts::launch_k(gn_gelu_bwd1_kernel<TT, KS>, g1, 256, smem, st, (const TT*)da, da_rpb, c, (const TT*)x, x_rpb, mean, rstd, gamma, beta, \
                                                      (TT*)dx, dx_rpb, dgamma, dbeta, accum, T_, C, G, rows1)
   if (dt == TS_F32) {
     if (ks == 0) GN_BWD1(float, 0); else if (ks == 26) GN_BWD1(float, 26); else if (ks == 18) GN_BWD1(float, 18); else GN_BWD1(float, -1);
-    gn_gelu_bwd2_kernel<float><<<g2, 256, 0, st>>>((const float*)x, x_rpb, mean, rstd, gamma, (float*)dx, dx_rpb, accum,
+    ts::launch_k(gn_gelu_bwd2_kernel<float>, g2, 256, 0, st, (const float*)x, x_rpb, mean, rstd, gamma, (float*)dx, dx_rpb, accum,
                                                    T_, C, G, rows2);
   } else {
     if (ks == 0) GN_BWD1(bf16, 0); else if (ks == 26) GN_BWD1(bf16, 26); else if (ks == 18) GN_BWD1(bf16, 18); else GN_BWD1(bf16, -1);
-    gn_gelu_bwd2_kernel<bf16><<<g2, 256, 0, st>>>((const bf16*)x, x_rpb, mean, rstd, gamma, (bf16*)dx, dx_rpb, accum, T_,
+    ts::launch_k(gn_gelu_bwd2_kernel<bf16>, g2, 256, 0, st, (const bf16*)x, x_rpb, mean, rstd, gamma, (bf16*)dx, dx_rpb, accum, T_,
                                                   C, G, rows2);
   }
 #undef GN_BWD1

@@ -27,12 +27,14 @@ std::vector<WorkItem> build_work_items(const std::vector<Segment>& segs) {
 }
 
 __global__ void zero_f32_kernel(float* p, int n) {
+  ts::pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = 0.f;
 }
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, const WorkItem* __restrict__ items,
                                                     float* __restrict__ sumsq) {
+  ts::pdl_enter();
   __shared__ float red[32];
   const WorkItem it = items[blockIdx.x];
   float s = 0.f;
@@ -53,13 +55,14 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 }
 
 int grad_sumsq(Ctx* ctx, const float* grads, const WorkItem* items, int n, int nseg, float* sumsq, cudaStream_t st) {
-  zero_f32_kernel<<<cdiv(nseg, 256), 256, 0, st>>>(sumsq, nseg);
-  sumsq_kernel<<<n, 256, 0, st>>>(grads, items, sumsq);
+  ts::launch_k(zero_f32_kernel, cdiv(nseg, 256), 256, 0, st, sumsq, nseg);
+  ts::launch_k(sumsq_kernel, n, 256, 0, st, grads, items, sumsq);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
 
 __global__ void global_clip_kernel(const float* __restrict__ sumsq, int nseg, float clip, float* scale_out, float* norm_out) {
+  ts::pdl_enter();
   __shared__ float red[32];
   float s = 0.f;
   for (int i = threadIdx.x; i < nseg; i += blockDim.x) s += sumsq[i];
@@ -71,7 +74,7 @@ __global__ void global_clip_kernel(const float* __restrict__ sumsq, int nseg, fl
   }
 }
 int global_clip_scale(Ctx* ctx, const float* sumsq, int nseg, float clip, float* scale_out, float* norm_out, cudaStream_t st) {
-  global_clip_kernel<<<1, 256, 0, st>>>(sumsq, nseg, clip, scale_out, norm_out);
+  ts::launch_k(global_clip_kernel, 1, 256, 0, st, sumsq, nseg, clip, scale_out, norm_out);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
@@ -82,6 +85,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float eps, float clipnorm, const float* __restrict__ pre_scale,
                                                    const float* __restrict__ sumsq, float lr,
                                                    const unsigned long long* __restrict__ step_state) {
+  ts::pdl_enter();
   if (step_state) {  // CUDA-graph mode: the step count lives on the device (Ctx::d_state[1]); same formula as the host path
     const double t = (double)step_state[1];
     lr_t = (float)((double)lr * sqrt(1.0 - pow(1.0 - (double)omb2, t)) / (1.0 - pow(1.0 - (double)omb1, t)));
@@ -139,20 +143,21 @@ int adam_step(Ctx* ctx, float* params, const float* grads, float* m, float* v, v
               const AdamArgs& a, cudaStream_t st) {
   TS_REQUIRE(ctx, a.step >= 0, TS_EINVAL, "adam: step must be >= 1 (or 0 = take it from the device step state)");
   const double lr_t = a.step >= 1 ? (double)a.lr * sqrt(1.0 - pow((double)a.beta2, a.step)) / (1.0 - pow((double)a.beta1, a.step)) : 0.0;
-  adam_kernel<<<n, 256, 0, st>>>(params, grads, m, v, (bf16*)params_bf16, items, (float)lr_t, 1.f - a.beta1, 1.f - a.beta2,
+  ts::launch_k(adam_kernel, n, 256, 0, st, params, grads, m, v, (bf16*)params_bf16, items, (float)lr_t, 1.f - a.beta1, 1.f - a.beta2,
                                  a.eps, a.clipnorm, a.pre_scale, a.sumsq, a.lr, a.step >= 1 ? nullptr : ctx->d_state);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
 
 __global__ void scale_kernel(float* __restrict__ x, long long n, const float* __restrict__ sdev, float shost) {
+  ts::pdl_enter();
   const float s = (sdev ? sdev[0] : 1.f) * shost;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] *= s;
 }
 int scale_inplace(Ctx* ctx, float* x, long long n, const float* scale_dev, float scale_host, cudaStream_t st) {
   if (n <= 0) return 0;
   const int grid = (int)min((n + 255) / 256, (long long)ctx->num_sms * 16);
-  scale_kernel<<<grid, 256, 0, st>>>(x, n, scale_dev, scale_host);
+  ts::launch_k(scale_kernel, grid, 256, 0, st, x, n, scale_dev, scale_host);
   TS_LAUNCH_OK(ctx);
   return 0;
 }

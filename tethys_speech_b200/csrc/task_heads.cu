@@ -13,6 +13,7 @@ template <typename TD>
 __global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ x, long long ld, const int* __restrict__ labels,
                                                       TD* __restrict__ d, long long ld_d, float* __restrict__ loss_sum, int R,
                                                       int V, float grad_scale) {
+  ts::pdl_enter();
   __shared__ float part[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;
@@ -51,8 +52,8 @@ int ce_rows_fwd_bwd(Ctx* ctx, int dt, const float* logits, long long ld, const i
                     float* loss_sum, int R, int V, float grad_scale, cudaStream_t st) {
   if (R <= 0) return 0;
   const int grid = cdiv(R, 8);
-  if (dt == TS_F32) ce_rows_kernel<float><<<grid, 256, 0, st>>>(logits, ld, labels, (float*)dlogits, ld_d, loss_sum, R, V, grad_scale);
-  else if (dt == TS_BF16) ce_rows_kernel<bf16><<<grid, 256, 0, st>>>(logits, ld, labels, (bf16*)dlogits, ld_d, loss_sum, R, V, grad_scale);
+  if (dt == TS_F32) ts::launch_k(ce_rows_kernel<float>, grid, 256, 0, st, logits, ld, labels, (float*)dlogits, ld_d, loss_sum, R, V, grad_scale);
+  else if (dt == TS_BF16) ts::launch_k(ce_rows_kernel<bf16>, grid, 256, 0, st, logits, ld, labels, (bf16*)dlogits, ld_d, loss_sum, R, V, grad_scale);
   else return set_err(ctx, TS_EDTYPE, "ce_rows: dtype %d", dt);
   TS_LAUNCH_OK(ctx);
   return 0;
@@ -62,6 +63,7 @@ int ce_rows_fwd_bwd(Ctx* ctx, int dt, const float* logits, long long ld, const i
 // consecutive threads on consecutive channels (coalesced); fp32 accumulation in time order.
 template <typename T>
 __global__ void __launch_bounds__(256) mean_pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Tn, int C) {
+  ts::pdl_enter();
   const int c = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
   if (c >= C) return;
   const T* p = x + (long long)b * Tn * C + c;
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(256) mean_pool_fwd_kernel(const T* __restrict_
 // dx[b, t, c] = dy[b, c] / T
 template <typename T>
 __global__ void __launch_bounds__(256) mean_pool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int Tn, int C) {
+  ts::pdl_enter();
   const long long n = (long long)B * Tn * C;
   const float inv = 1.f / (float)Tn;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
@@ -83,8 +86,8 @@ __global__ void __launch_bounds__(256) mean_pool_bwd_kernel(const T* __restrict_
 
 int mean_pool_fwd(Ctx* ctx, int dt, const void* x, void* y, int B, int Tn, int C, cudaStream_t st) {
   dim3 grid(cdiv(C, 256), B);
-  if (dt == TS_F32) mean_pool_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, B, Tn, C);
-  else if (dt == TS_BF16) mean_pool_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)y, B, Tn, C);
+  if (dt == TS_F32) ts::launch_k(mean_pool_fwd_kernel<float>, grid, 256, 0, st, (const float*)x, (float*)y, B, Tn, C);
+  else if (dt == TS_BF16) ts::launch_k(mean_pool_fwd_kernel<bf16>, grid, 256, 0, st, (const bf16*)x, (bf16*)y, B, Tn, C);
   else return set_err(ctx, TS_EDTYPE, "mean_pool: dtype %d", dt);
   TS_LAUNCH_OK(ctx);
   return 0;
@@ -94,8 +97,8 @@ int mean_pool_bwd(Ctx* ctx, int dt, const void* dy, void* dx, int B, int Tn, int
   long long g = (n + 255) / 256;
   const long long cap = (long long)ctx->num_sms * 16;
   const int grid = (int)(g > cap ? cap : g);
-  if (dt == TS_F32) mean_pool_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, (float*)dx, B, Tn, C);
-  else if (dt == TS_BF16) mean_pool_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dy, (bf16*)dx, B, Tn, C);
+  if (dt == TS_F32) ts::launch_k(mean_pool_bwd_kernel<float>, grid, 256, 0, st, (const float*)dy, (float*)dx, B, Tn, C);
+  else if (dt == TS_BF16) ts::launch_k(mean_pool_bwd_kernel<bf16>, grid, 256, 0, st, (const bf16*)dy, (bf16*)dx, B, Tn, C);
   else return set_err(ctx, TS_EDTYPE, "mean_pool: dtype %d", dt);
   TS_LAUNCH_OK(ctx);
   return 0;
@@ -107,6 +110,7 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(256) tanh_drop_kernel(const T* __restrict__ a, const T* __restrict__ y, T* __restrict__ out,
                                                         T* __restrict__ out2, long long n, uint32_t thr, float inv_keep,
                                                         uint64_t seed, const unsigned long long* __restrict__ salt) {
+  ts::pdl_enter();
   if (thr) seed = salted_seed(seed, salt);
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
     const float mask = thr ? dropout_scale(seed, (uint64_t)i, thr, inv_keep) : 1.f;
@@ -135,8 +139,8 @@ int tanh_drop_fwd(Ctx* ctx, int dt, const void* x, void* y, void* y_drop, long l
   uint32_t thr; float ik;
   drop_thr(drop, &thr, &ik);
   const int grid = (int)std::min<long long>((n + 255) / 256, (long long)ctx->num_sms * 16);
-  if (dt == TS_F32) tanh_drop_kernel<float, 0><<<grid, 256, 0, st>>>((const float*)x, nullptr, (float*)y, (float*)y_drop, n, thr, ik, seed, ctx->d_state);
-  else if (dt == TS_BF16) tanh_drop_kernel<bf16, 0><<<grid, 256, 0, st>>>((const bf16*)x, nullptr, (bf16*)y, (bf16*)y_drop, n, thr, ik, seed, ctx->d_state);
+  if (dt == TS_F32) ts::launch_k(tanh_drop_kernel<float, 0>, grid, 256, 0, st, (const float*)x, nullptr, (float*)y, (float*)y_drop, n, thr, ik, seed, ctx->d_state);
+  else if (dt == TS_BF16) ts::launch_k(tanh_drop_kernel<bf16, 0>, grid, 256, 0, st, (const bf16*)x, nullptr, (bf16*)y, (bf16*)y_drop, n, thr, ik, seed, ctx->d_state);
   else return set_err(ctx, TS_EDTYPE, "tanh_drop: dtype %d", dt);
   TS_LAUNCH_OK(ctx);
   return 0;
@@ -146,8 +150,8 @@ int tanh_drop_bwd(Ctx* ctx, int dt, const void* dy, const void* y, void* dx, lon
   uint32_t thr; float ik;
   drop_thr(drop, &thr, &ik);
   const int grid = (int)std::min<long long>((n + 255) / 256, (long long)ctx->num_sms * 16);
-  if (dt == TS_F32) tanh_drop_kernel<float, 1><<<grid, 256, 0, st>>>((const float*)dy, (const float*)y, (float*)dx, nullptr, n, thr, ik, seed, ctx->d_state);
-  else if (dt == TS_BF16) tanh_drop_kernel<bf16, 1><<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)y, (bf16*)dx, nullptr, n, thr, ik, seed, ctx->d_state);
+  if (dt == TS_F32) ts::launch_k(tanh_drop_kernel<float, 1>, grid, 256, 0, st, (const float*)dy, (const float*)y, (float*)dx, nullptr, n, thr, ik, seed, ctx->d_state);
+  else if (dt == TS_BF16) ts::launch_k(tanh_drop_kernel<bf16, 1>, grid, 256, 0, st, (const bf16*)dy, (const bf16*)y, (bf16*)dx, nullptr, n, thr, ik, seed, ctx->d_state);
   else return set_err(ctx, TS_EDTYPE, "tanh_drop: dtype %d", dt);
   TS_LAUNCH_OK(ctx);
   return 0;

@@ -256,6 +256,7 @@ static int plan(W2V* m, int B, int N, Bump& bp) {
 }
 
 __global__ void w2v_finalize_scalars(float* s, float inv_rows, float div_w) {
+  ts::pdl_enter();
   const float closs = s[3] * inv_rows;
   float loss = closs + div_w * (-s[2]);
   if (isnan(loss)) loss = 0.f;   // tf.where(is_nan(loss), 0, loss) — V:1228
@@ -362,7 +363,7 @@ static int w2v_forward(W2V* m, const float* wave, const int* neg, long long neg_
     TS_TRY(GemmB(dt, TS_F32).A(hin, 0, H).B(m->W(m->lm_w), 1, V).C(m->hlogits, V).bias(m->P + m->lm_b).mnk(M, V, H).simt().run(ctx, st));
     if (with_loss) {
       TS_TRY(ce_rows_fwd_bwd(ctx, dt, m->hlogits, V, nullptr, m->d_hlogits, V, m->scalars + 3, M, V, 1.f / (m->loss_div * (float)M), st));
-      w2v_finalize_scalars<<<1, 1, 0, st>>>(m->scalars, 1.f / (float)M, 0.f);
+      ts::launch_k(w2v_finalize_scalars, 1, 1, 0, st, m->scalars, 1.f / (float)M, 0.f);
       TS_LAUNCH_OK(ctx);
     }
     m->fwd_done = with_loss;
@@ -377,7 +378,7 @@ static int w2v_forward(W2V* m, const float* wave, const int* neg, long long neg_
     TS_TRY(GemmB(dt, TS_F32).A(m->cp_drop, 0, Pc).B(m->W(m->cl_w), 1, NL).C(m->hlogits, NL).bias(m->P + m->cl_b).mnk(B, NL, Pc).simt().run(ctx, st));
     if (with_loss) {
       TS_TRY(ce_rows_fwd_bwd(ctx, dt, m->hlogits, NL, labels, m->d_hlogits, NL, m->scalars + 3, B, NL, 1.f / (m->loss_div * (float)B), st));
-      w2v_finalize_scalars<<<1, 1, 0, st>>>(m->scalars, 1.f / (float)B, 0.f);
+      ts::launch_k(w2v_finalize_scalars, 1, 1, 0, st, m->scalars, 1.f / (float)B, 0.f);
       TS_LAUNCH_OK(ctx);
     }
     m->fwd_done = with_loss;
@@ -397,7 +398,7 @@ static int w2v_forward(W2V* m, const float* wave, const int* neg, long long neg_
              .C(m->S, Tp).cstride((long long)T * Tp, 0).mnk(T, T, Pj).batch(B, 1).run(ctx, st));
   TS_TRY(contrastive_fwd_bwd(ctx, dt, m->S, Tp, neg, neg_bs, neg_ts, m->dS, Tp, m->logits, m->scalars + 3, B, T,
                              c.num_negatives, c.temperature, 1.f / (m->loss_div * (float)M), st));
-  w2v_finalize_scalars<<<1, 1, 0, st>>>(m->scalars, 1.f / (float)M, c.diversity_weight);
+  ts::launch_k(w2v_finalize_scalars, 1, 1, 0, st, m->scalars, 1.f / (float)M, c.diversity_weight);
   TS_LAUNCH_OK(ctx);
   m->fwd_done = true;
   return 0;

@@ -13,6 +13,7 @@ template <typename T>
 __global__ void __launch_bounds__(512) ce_kernel(const T* logits, T* dlogits /* may alias logits */, long long ldv,
                                                  const int* __restrict__ labels, float* __restrict__ loss_sum, int S, int V,
                                                  float gscale) {
+  ts::pdl_enter();
   __shared__ float red[32];
   const long long row = blockIdx.x;
   const int b = (int)(row / S), s = (int)(row % S);
@@ -42,8 +43,8 @@ __global__ void __launch_bounds__(512) ce_kernel(const T* logits, T* dlogits /* 
 int ce_fwd_bwd(Ctx* ctx, int dt, const void* logits, void* dlogits, long long ldv, const int* labels, float* loss_sum, int B,
                int S, int V, float grad_scale, cudaStream_t st) {
   const float gs = grad_scale / (float)(B * (S - 1));
-  if (dt == TS_F32) ce_kernel<float><<<B * S, 512, 0, st>>>((const float*)logits, (float*)dlogits, ldv, labels, loss_sum, S, V, gs);
-  else if (dt == TS_BF16) ce_kernel<bf16><<<B * S, 512, 0, st>>>((const bf16*)logits, (bf16*)dlogits, ldv, labels, loss_sum, S, V, gs);
+  if (dt == TS_F32) ts::launch_k(ce_kernel<float>, B * S, 512, 0, st, (const float*)logits, (float*)dlogits, ldv, labels, loss_sum, S, V, gs);
+  else if (dt == TS_BF16) ts::launch_k(ce_kernel<bf16>, B * S, 512, 0, st, (const bf16*)logits, (bf16*)dlogits, ldv, labels, loss_sum, S, V, gs);
   else return set_err(ctx, TS_EDTYPE, "ce: dtype %d", dt);
   TS_LAUNCH_OK(ctx);
   return 0;
@@ -59,6 +60,7 @@ template <typename T>
 __global__ void embed_fwd_kernel(const T* __restrict__ table, const int* __restrict__ labels, const float* __restrict__ pe,
                                  T* __restrict__ out, int S, long long label_ld, int D, int start_token, uint32_t thr, float inv_keep,
                                  uint64_t seed, const unsigned long long* __restrict__ salt) {
+  ts::pdl_enter();
   if (thr) seed = salted_seed(seed, salt);
   const long long row = blockIdx.x;
   const int b = (int)(row / S), s = (int)(row % S);
@@ -73,6 +75,7 @@ template <typename T>
 __global__ void embed_bwd_kernel(const T* __restrict__ dout, const int* __restrict__ labels, float* __restrict__ dtable, int S,
                                  int D, int start_token, uint32_t thr, float inv_keep, uint64_t seed,
                                  const unsigned long long* __restrict__ salt) {
+  ts::pdl_enter();
   if (thr) seed = salted_seed(seed, salt);
   const long long row = blockIdx.x;
   const int b = (int)(row / S), s = (int)(row % S);
@@ -95,8 +98,8 @@ int embed_fwd(Ctx* ctx, int dt, const void* table, const int* labels, long long 
               int start_token, float drop, uint64_t seed, cudaStream_t st) {
   uint32_t thr; float ik;
   drop3(drop, &thr, &ik);
-  if (dt == TS_F32) embed_fwd_kernel<float><<<B * S, 256, 0, st>>>((const float*)table, labels, pe, (float*)out, S, label_ld, D, start_token, thr, ik, seed, ctx->d_state);
-  else embed_fwd_kernel<bf16><<<B * S, 256, 0, st>>>((const bf16*)table, labels, pe, (bf16*)out, S, label_ld, D, start_token, thr, ik, seed, ctx->d_state);
+  if (dt == TS_F32) ts::launch_k(embed_fwd_kernel<float>, B * S, 256, 0, st, (const float*)table, labels, pe, (float*)out, S, label_ld, D, start_token, thr, ik, seed, ctx->d_state);
+  else ts::launch_k(embed_fwd_kernel<bf16>, B * S, 256, 0, st, (const bf16*)table, labels, pe, (bf16*)out, S, label_ld, D, start_token, thr, ik, seed, ctx->d_state);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
@@ -104,8 +107,8 @@ int embed_bwd(Ctx* ctx, int dt, const void* dout, const int* labels, float* dtab
               float drop, uint64_t seed, cudaStream_t st) {
   uint32_t thr; float ik;
   drop3(drop, &thr, &ik);
-  if (dt == TS_F32) embed_bwd_kernel<float><<<B * S, 256, 0, st>>>((const float*)dout, labels, dtable, S, D, start_token, thr, ik, seed, ctx->d_state);
-  else embed_bwd_kernel<bf16><<<B * S, 256, 0, st>>>((const bf16*)dout, labels, dtable, S, D, start_token, thr, ik, seed, ctx->d_state);
+  if (dt == TS_F32) ts::launch_k(embed_bwd_kernel<float>, B * S, 256, 0, st, (const float*)dout, labels, dtable, S, D, start_token, thr, ik, seed, ctx->d_state);
+  else ts::launch_k(embed_bwd_kernel<bf16>, B * S, 256, 0, st, (const bf16*)dout, labels, dtable, S, D, start_token, thr, ik, seed, ctx->d_state);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
@@ -115,6 +118,7 @@ template <typename T>
 __global__ void add_pe_kernel(const T* __restrict__ x, long long rpb_in, const float* __restrict__ pe, T* __restrict__ y, int T_,
                               int D, uint32_t thr, float inv_keep, uint64_t seed, long long total8,
                               const unsigned long long* __restrict__ salt) {
+  ts::pdl_enter();
   if (thr) seed = salted_seed(seed, salt);
   const int d8 = D / 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
@@ -142,8 +146,8 @@ int add_pe_rows(Ctx* ctx, int dt, const void* x, long long rpb_in, const float* 
   drop3(drop, &thr, &ik);
   const long long total8 = (long long)B * T_ * (D / 8);
   const int grid = (int)min((total8 + 255) / 256, (long long)ctx->num_sms * 16);
-  if (dt == TS_F32) add_pe_kernel<float><<<grid, 256, 0, st>>>((const float*)x, rpb_in, pe, (float*)y, T_, D, thr, ik, seed, total8, ctx->d_state);
-  else add_pe_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, rpb_in, pe, (bf16*)y, T_, D, thr, ik, seed, total8, ctx->d_state);
+  if (dt == TS_F32) ts::launch_k(add_pe_kernel<float>, grid, 256, 0, st, (const float*)x, rpb_in, pe, (float*)y, T_, D, thr, ik, seed, total8, ctx->d_state);
+  else ts::launch_k(add_pe_kernel<bf16>, grid, 256, 0, st, (const bf16*)x, rpb_in, pe, (bf16*)y, T_, D, thr, ik, seed, total8, ctx->d_state);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
@@ -152,6 +156,7 @@ int add_pe_rows(Ctx* ctx, int dt, const void* x, long long rpb_in, const float* 
 template <typename T>
 __global__ void gelu_bwd_rows_kernel(const T* __restrict__ da, long long da_rpb, Col2imSrc col, const T* __restrict__ u,
                                      T* __restrict__ du, long long rpb, int T_, int C, long long total8) {
+  ts::pdl_enter();
   const int c8 = C / 8;
   const T* dcol = reinterpret_cast<const T*>(col.dcol);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
@@ -194,8 +199,8 @@ int gelu_bwd_rows(Ctx* ctx, int dt, const void* da, long long da_rpb, const Col2
   if (col) c = *col; else { c.dcol = nullptr; c.rows_per_batch = 0; c.t_next = 0; c.k = 0; c.s = 1; c.left = 0; }
   const long long total8 = (long long)B * rpb * (C / 8);
   const int grid = (int)min((total8 + 255) / 256, (long long)ctx->num_sms * 16);
-  if (dt == TS_F32) gelu_bwd_rows_kernel<float><<<grid, 256, 0, st>>>((const float*)da, da_rpb, c, (const float*)u, (float*)du, rpb, T_, C, total8);
-  else gelu_bwd_rows_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)da, da_rpb, c, (const bf16*)u, (bf16*)du, rpb, T_, C, total8);
+  if (dt == TS_F32) ts::launch_k(gelu_bwd_rows_kernel<float>, grid, 256, 0, st, (const float*)da, da_rpb, c, (const float*)u, (float*)du, rpb, T_, C, total8);
+  else ts::launch_k(gelu_bwd_rows_kernel<bf16>, grid, 256, 0, st, (const bf16*)da, da_rpb, c, (const bf16*)u, (bf16*)du, rpb, T_, C, total8);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
@@ -203,6 +208,7 @@ int gelu_bwd_rows(Ctx* ctx, int dt, const void* da, long long da_rpb, const Col2
 // ---- zero rows [row_from, rpb) of every batch block ---------------------------------------------------------------
 template <typename T>
 __global__ void zero_rows_kernel(T* __restrict__ x, long long rpb, int row_from, int C, long long total) {
+  ts::pdl_enter();
   const int nz = (int)(rpb - row_from);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -216,8 +222,8 @@ int zero_rows(Ctx* ctx, int dt, void* x, long long rpb, int row_from, int B, int
   if (row_from >= rpb) return 0;
   const long long total = (long long)B * (rpb - row_from) * C;
   const int grid = (int)min((total + 255) / 256, (long long)ctx->num_sms * 8);
-  if (dt == TS_F32) zero_rows_kernel<float><<<grid, 256, 0, st>>>((float*)x, rpb, row_from, C, total);
-  else zero_rows_kernel<bf16><<<grid, 256, 0, st>>>((bf16*)x, rpb, row_from, C, total);
+  if (dt == TS_F32) ts::launch_k(zero_rows_kernel<float>, grid, 256, 0, st, (float*)x, rpb, row_from, C, total);
+  else ts::launch_k(zero_rows_kernel<bf16>, grid, 256, 0, st, (bf16*)x, rpb, row_from, C, total);
   TS_LAUNCH_OK(ctx);
   return 0;
 }

@@ -279,6 +279,7 @@ static int dense_bwd(Whisper* m, const void* X, int K, const void* dY, int Nn, l
 // [B, n_mels, Tm] fp32 -> rows [B, R0, n_mels] (act dtype), data at rows [1, 1+Tm), the rest zero (W:329 + SAME pad of conv1)
 template <typename T>
 __global__ void mel_to_rows_kernel(const float* __restrict__ f, T* __restrict__ y, int nm, int Tm, long long R0) {
+  ts::pdl_enter();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -294,7 +295,8 @@ __global__ void mel_to_rows_kernel(const float* __restrict__ f, T* __restrict__ 
   }
 }
 
-__global__ void whisper_finalize_scalars(float* s, float inv_rows) { s[0] = s[3] * inv_rows; }
+__global__ void whisper_finalize_scalars(float* s, float inv_rows) {
+  ts::pdl_enter(); s[0] = s[3] * inv_rows; }
 
 // conv stem + encoder layers + final LayerNorm -> enc_out (WhisperEncoder.call, W:324-372)
 static int whisper_encoder_forward(Whisper* m, const float* feats, cudaStream_t st) {
@@ -309,8 +311,8 @@ static int whisper_encoder_forward(Whisper* m, const float* feats, cudaStream_t 
   TS_TRY(fill_zero(ctx, m->xT, m->E((long long)B * m->R0 * c.n_mels + 3 * c.n_mels), st));
   {
     dim3 grid(cdiv(m->Tm, 32), cdiv(c.n_mels, 32), B);
-    if (dt == TS_F32) mel_to_rows_kernel<float><<<grid, 256, 0, st>>>(feats, (float*)m->xT, c.n_mels, m->Tm, m->R0);
-    else mel_to_rows_kernel<bf16><<<grid, 256, 0, st>>>(feats, (bf16*)m->xT, c.n_mels, m->Tm, m->R0);
+    if (dt == TS_F32) ts::launch_k(mel_to_rows_kernel<float>, grid, 256, 0, st, feats, (float*)m->xT, c.n_mels, m->Tm, m->R0);
+    else ts::launch_k(mel_to_rows_kernel<bf16>, grid, 256, 0, st, feats, (bf16*)m->xT, c.n_mels, m->Tm, m->R0);
     TS_LAUNCH_OK(ctx);
   }
   TS_TRY(GemmB(dt, dt).A(m->xT, 0, c.n_mels).B(m->W(m->conv1_w), 1, d).C(m->a1, d).bias(m->P + m->conv1_b).gelu(m->u1)
@@ -405,6 +407,7 @@ static int whisper_forward(Whisper* m, const float* feats, const int* labels, cu
 template <typename T>
 __global__ void __launch_bounds__(256) argmax_rows_kernel(const T* __restrict__ x, long long ld, int V, int* __restrict__ out,
                                                           long long out_ld) {
+  ts::pdl_enter();
   __shared__ float sv[256];
   __shared__ int si[256];
   const T* row = x + (long long)blockIdx.x * ld;
@@ -431,7 +434,7 @@ static int whisper_loss(Whisper* m, cudaStream_t st) {
   // dlogits = (softmax - onehot) / (B*(S-1)) for the shifted targets; accumulates the loss
   Ctx* ctx = m->ctx;
   TS_TRY(ce_fwd_bwd(ctx, m->prec, m->logits, m->dlogits, m->Vp, m->labels, m->scalars + 3, m->B, m->S, m->cfg.vocab, 1.f, st));
-  whisper_finalize_scalars<<<1, 1, 0, st>>>(m->scalars, 1.f / (float)(m->B * (m->S - 1)));
+  ts::launch_k(whisper_finalize_scalars, 1, 1, 0, st, m->scalars, 1.f / (float)(m->B * (m->S - 1)));
   TS_LAUNCH_OK(ctx);
   m->fwd_done = true;
   return 0;
@@ -677,8 +680,8 @@ int ts_whisper_decode_step(ts_whisper* h, int32_t* tokens, int64_t ld_tok, int l
   TS_REQUIRE(ctx, tokens && len >= 1 && len <= m->S && ld_tok >= len, TS_EINVAL,
              "whisper_decode_step: len %d outside [1, %d] (the max_len given to ts_whisper_encode) or token stride too small", len, m->S);
   TS_TRY(whisper_decoder_forward(m, tokens, ld_tok, len, true, true, st));
-  if (m->prec == TS_F32) argmax_rows_kernel<float><<<m->B, 256, 0, st>>>((const float*)m->logits, m->Vp, m->cfg.vocab, tokens + (len - 1), ld_tok);
-  else argmax_rows_kernel<bf16><<<m->B, 256, 0, st>>>((const bf16*)m->logits, m->Vp, m->cfg.vocab, tokens + (len - 1), ld_tok);
+  if (m->prec == TS_F32) ts::launch_k(argmax_rows_kernel<float>, m->B, 256, 0, st, (const float*)m->logits, m->Vp, m->cfg.vocab, tokens + (len - 1), ld_tok);
+  else ts::launch_k(argmax_rows_kernel<bf16>, m->B, 256, 0, st, (const bf16*)m->logits, m->Vp, m->cfg.vocab, tokens + (len - 1), ld_tok);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
