@@ -353,10 +353,19 @@ def kernel_rooflines(ctx, peaks, B, T, H, F, nh, n_params):
     xg = torch.randn(B, T0, 512, device=dev).to(bf); yg = torch.empty_like(xg)
     gmean = torch.empty(B, 16, device=dev); grstd = torch.empty(B, 16, device=dev); acc = torch.zeros(2 * B * 16, dtype=torch.float64, device=dev)
     g512 = torch.ones(512, device=dev); b512 = torch.zeros(512, device=dev)
-    hbm(f"gn_stats_kernel + gn_gelu_fwd_kernel [{B},{T0},512] bf16 (V:140-196, V:248-249; x read twice: 3 passes of {B * T0 * 512 * 2 / 1e6:.0f} MB)",
-        3.0 * B * T0 * 512 * 2,
-        lambda: ctx.check(ctx.lib.ts_groupnorm_gelu_fwd(ctx.h, _lib.TS_BF16, P(xg), P(g512), P(b512), P(yg), P(gmean), P(grstd), P(acc), B, T0,
+    # algorithmic bytes per SURVEY §8(d): every distinct tensor once in, once out = 2 passes of the activation.
+    # (1) as the train step runs it: the moments come from the producer (conv0 store loop / conv GEMM epilogue), x is read once
+    ctx.check(ctx.lib.ts_groupnorm_gelu_fwd(ctx.h, _lib.TS_BF16, P(xg), P(g512), P(b512), P(yg), P(gmean), P(grstd), P(acc), B, T0, 512, 16, 1e-5,
+                                            stream_ptr()))
+    hbm(f"gn_gelu_fwd_kernel [{B},{T0},512] bf16, moments from the conv epilogue (V:140-196, V:248-249; 2 passes of {B * T0 * 512 * 2 / 1e6:.0f} MB)",
+        2.0 * B * T0 * 512 * 2,
+        lambda: ctx.check(ctx.lib.ts_groupnorm_gelu_fwd(ctx.h, _lib.TS_BF16, P(xg), P(g512), P(b512), P(yg), P(gmean), P(grstd), None, B, T0,
                                                         512, 16, 1e-5, stream_ptr())), key="gn_gelu_fwd")
+    # (2) the stand-alone layer (no producer to take the moments): x is read twice, still 2 algorithmic passes
+    hbm(f"gn_stats_kernel + gn_gelu_fwd_kernel [{B},{T0},512] bf16, stand-alone GroupNormalization + GELU (x read twice, 2 algorithmic passes)",
+        2.0 * B * T0 * 512 * 2,
+        lambda: ctx.check(ctx.lib.ts_groupnorm_gelu_fwd(ctx.h, _lib.TS_BF16, P(xg), P(g512), P(b512), P(yg), P(gmean), P(grstd), P(acc), B, T0,
+                                                        512, 16, 1e-5, stream_ptr())))
     del xg, yg
     # log-mel front end, B x 30 s
     wav = torch.randn(B, 480000, device=dev)

@@ -113,6 +113,13 @@ typedef struct {
   int64_t bias_bs1;     /* bias element stride per batch1 index (grouped conv: one bias slice per group) */
   const void* act_aux;  /* act == 2: the GELU input u, same dtype and batch strides as C, row stride ld_aux */
   int64_t ld_aux;
+  /* GroupNormalization statistics taken in the epilogue (V:167-176: moments over time x channels-of-the-group): when gn_accum is
+   * non-NULL the kernel adds, for every output row r = b * gn_rows_per_batch + t with t < gn_valid_rows, the sums of C[r, cols of
+   * group g] and of their squares (fp32 accumulator values) to gn_accum[(b * gn_groups + g) * 2 + {0, 1}] (fp64 atomics; the
+   * caller zeroes it before and turns it into mean / rstd after). tcgen05 engine only, bf16 or fp32 C through the TMA epilogue,
+   * no act / residual / batching, n / gn_groups a multiple of 32. Saves the separate pass that re-reads the conv output. */
+  double* gn_accum;
+  int32_t gn_rows_per_batch, gn_valid_rows, gn_groups;
 } ts_gemm_desc;
 
 int ts_gemm(ts_ctx* ctx, const ts_gemm_desc* d, void* stream);
@@ -169,7 +176,8 @@ int ts_logmel(ts_ctx* ctx, const float* wave, int64_t wave_batch_stride, int bat
  *   mean, rstd and the parameter gradients are fp32. bwd ADDS into dgamma / dbeta; dres (optional) is added to dx.
  * ts_groupnorm_gelu_fwd: GroupNormalization(groups) + exact-erf GELU of the conv feature encoder (V:132-196, V:248-249) on
  *   x [batch, T, C]: statistics over (T, C/groups) per (batch, group); writes mean/rstd [batch, groups] and y = gelu(gn(x)).
- *   accum is scratch of 2 * batch * groups doubles.
+ *   accum is scratch of 2 * batch * groups doubles. accum == NULL: mean / rstd are INPUTS (the moments were taken by the producer
+ *   of x — conv0's store loop or the conv GEMM epilogue, ts_gemm_desc.gn_accum — as the train step does), x is read once.
  */
 int ts_layernorm_fwd(ts_ctx* ctx, int dtype, const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                      int rows, int cols, float eps, void* stream);

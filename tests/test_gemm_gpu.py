@@ -109,3 +109,41 @@ def test_misaligned_operands_fall_to_cuda_core_engine_not_cpu():
     c = torch.empty(33, 20, dtype=torch.bfloat16, device=dev)
     _gemm(a, b, c, 33, 20, 30, 0, 1, 30, 20, _lib.TS_BF16, _lib.TS_BF16)
     assert _rel(c, a.float() @ b.float()) < 1e-2
+
+
+@pytest.mark.parametrize("force", [2, 3])   # 1-CTA tiles / CTA-pair tiles
+def test_groupnorm_statistics_in_the_epilogue(force):
+    """ts_gemm_desc.gn_accum: the conv GEMM takes the GroupNormalization moments (V:167-176, over time x channels of a group, per
+    batch element) of its own output, skipping the window-slack rows behind every batch block; warps that straddle a batch
+    boundary and the clipped last tile are part of the shape."""
+    from tethys_speech_b200 import _lib
+    from tethys_speech_b200.runtime import stream_ptr
+
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(11)
+    B, rpb, valid, k, n, G = 3, 237, 229, 192, 256, 4                       # 64 channels per group; 711 rows = 5.55 tiles of 128
+    m = B * rpb
+    x = torch.randn(m, k, generator=g).bfloat16().to(dev)
+    w = (torch.randn(k, n, generator=g) * 0.1).bfloat16().to(dev)
+    y = torch.empty(m, n, dtype=torch.bfloat16, device=dev)
+    accum = torch.zeros(B, G, 2, dtype=torch.float64, device=dev)
+    ctx = _lib.context(0)
+    d = _lib.GemmDesc()
+    d.a, d.b, d.c = x.data_ptr(), w.data_ptr(), y.data_ptr()
+    d.m, d.n, d.k, d.a_major, d.b_major = m, n, k, 0, 1
+    d.lda, d.ldb, d.ldc = k, n, n
+    d.batch1 = d.batch2 = 1
+    d.in_dtype = d.out_dtype = _lib.TS_BF16
+    d.alpha, d.force_engine = 1.0, force
+    d.gn_accum, d.gn_rows_per_batch, d.gn_valid_rows, d.gn_groups = accum.data_ptr(), rpb, valid, G
+    ctx.check(ctx.lib.ts_gemm(ctx.h, C.byref(d), stream_ptr()))
+    torch.cuda.synchronize()
+    ctx.watchdog()
+    u = (x.float() @ w.float()).double().view(B, rpb, G, n // G)[:, :valid]
+    ref = torch.stack([u.sum(dim=(1, 3)), (u * u).sum(dim=(1, 3))], dim=-1)
+    assert _rel(y, x.float() @ w.float()) < 1e-2
+    assert float(((accum - ref).abs() / ref.abs().clamp_min(1.0)).max()) < 1e-5, (accum, ref)
+    # an epilogue that cannot take them says so
+    d.act = 1
+    with pytest.raises(_lib.TethysError):
+        ctx.check(ctx.lib.ts_gemm(ctx.h, C.byref(d), stream_ptr()))

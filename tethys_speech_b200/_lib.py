@@ -40,6 +40,7 @@ class GemmDesc(C.Structure):
         ("seed", C.c_uint64),
         ("bias_bs1", C.c_int64),
         ("act_aux", C.c_void_p), ("ld_aux", C.c_int64),
+        ("gn_accum", C.c_void_p), ("gn_rows_per_batch", C.c_int32), ("gn_valid_rows", C.c_int32), ("gn_groups", C.c_int32),
     ]
 
 

@@ -29,6 +29,8 @@ bool gemm_tc_supported(const ts_gemm_desc* d);
 void tmap_cache_free(Ctx* ctx);
 
 int gemm(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
+  if (d->gn_accum && (d->force_engine == 1 || d->in_dtype != TS_BF16 || !gemm_tc_supported(d)))
+    return set_err(ctx, TS_EUNSUPPORTED, "gemm: epilogue GroupNorm statistics (gn_accum) exist on the tcgen05 engine only");
   if (d->force_engine == 1) return gemm_simt(ctx, d, st);
   if (d->force_engine == 2 || d->force_engine == 3) return gemm_tc(ctx, d, st);
   if (d->in_dtype == TS_BF16 && gemm_tc_supported(d)) return gemm_tc(ctx, d, st);
@@ -168,8 +170,10 @@ int ts_groupnorm_gelu_fwd(ts_ctx* ctx, int dtype, const void* x, const float* ga
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   if (!c) return TS_EINVAL;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int rc = ts::groupnorm_stats(c, dtype, x, accum, mean, rstd, batch, t, ch, groups, t, eps, st);
-  if (rc) return rc;
+  if (accum) {
+    int rc = ts::groupnorm_stats(c, dtype, x, accum, mean, rstd, batch, t, ch, groups, t, eps, st);
+    if (rc) return rc;
+  }
   return ts::groupnorm_gelu_fwd(c, dtype, x, t, mean, rstd, gamma, beta, y, t, 0, batch, t, ch, groups, st);
 }
 

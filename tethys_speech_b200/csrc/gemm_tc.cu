@@ -44,6 +44,8 @@ struct EpiParams {
   int use_red;                                        // fp32 output: add with red.global (split-K partials)
   int tma_epi;                                        // C (and c_pre) are TMA-storable: swizzled smem box + bulk tensor store
   unsigned long long* trace;                          // debug (ts_debug_gemm_trace): 16 globaltimer stamps per CTA, else NULL
+  double* gn_accum;                                   // GroupNorm statistics in the epilogue (ts_gemm_desc.gn_accum), else NULL
+  int gn_rpb, gn_valid, gn_groups, gn_cpg;            // rows per batch block, data rows of it, groups, channels per group
 };
 __device__ __forceinline__ void trace_stamp(const EpiParams& p, int slot) {
   if (p.trace) {
@@ -157,6 +159,37 @@ __device__ __forceinline__ void epi_act_drop(float (&v)[NV], const EpiParams& p,
     } else {
 #pragma unroll
       for (int i = 0; i < NV; ++i) v[i] *= dropout_scale(key, e0 + i, p.inv_keep);
+    }
+  }
+}
+
+// GroupNorm statistics of the tile in flight (V:167-176: moments over time x channels of a group, per batch element): the thread
+// owns NV consecutive channels of output row `row`; channel sub-chunks of 32 never straddle a group (host check: cpg % 32 == 0).
+// A warp's 32 rows normally lie in one batch element: one shuffle reduction, then lane 0 adds the two sums with fp64 atomics
+// (~4 atomics per warp and 64-column chunk). A warp that straddles a batch boundary falls back to per-lane atomics.
+template <int NV>
+__device__ __forceinline__ void gn_epilogue_stats(const float (&v)[NV], const EpiParams& p, int row, int col, int lane) {
+  const int bb = row / p.gn_rpb;
+  const bool valid = row < p.m && row - bb * p.gn_rpb < p.gn_valid;
+  const int b_first = __shfl_sync(0xffffffffu, bb, 0), b_last = __shfl_sync(0xffffffffu, bb, 31);
+  const bool uniform = b_first == b_last;
+#pragma unroll
+  for (int j = 0; j < NV / 32; ++j) {
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { s += v[32 * j + i]; ss = fmaf(v[32 * j + i], v[32 * j + i], ss); }
+    if (!valid) { s = 0.f; ss = 0.f; }
+    const int g = (col + 32 * j) / p.gn_cpg;
+    if (uniform) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+      if (lane == 0) {
+        double* a = p.gn_accum + ((long long)bb * p.gn_groups + g) * 2;
+        atomicAdd(a, (double)s); atomicAdd(a + 1, (double)ss);
+      }
+    } else if (valid) {
+      double* a = p.gn_accum + ((long long)bb * p.gn_groups + g) * 2;
+      atomicAdd(a, (double)s); atomicAdd(a + 1, (double)ss);
     }
   }
 }
@@ -365,6 +398,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (c0 + 2 * CW >= BN || tc.n0 + c0 + 2 * CW >= p.n) release();  // last TMEM read of this warp for this tile
           const bool full = col + CW <= p.n;
           epi_bias<CW>(v, p, bias, col, full);
+          if (p.gn_accum) gn_epilogue_stats<CW>(v, p, row, col, lane);
           // the previous TMA store of this warp must have finished reading the staging box
           if (lane == 0) ptx::bulk_wait_read<0>();
           __syncwarp();
@@ -641,6 +675,12 @@ int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
              "gemm_tc: operands must be bf16 with 16-byte aligned bases/strides");
   TS_REQUIRE(ctx, !(d->accumulate && (d->act || d->residual)), TS_EINVAL, "gemm: accumulate excludes act/residual");
   TS_REQUIRE(ctx, d->act != 2 || d->act_aux, TS_EINVAL, "gemm: act 2 needs act_aux");
+  if (d->gn_accum)
+    TS_REQUIRE(ctx, !d->act && !d->residual && !d->accumulate && !d->c_preact && d->drop <= 0.f && d->batch1 <= 1 && d->batch2 <= 1 &&
+                   d->gn_groups > 0 && d->n % d->gn_groups == 0 && (d->n / d->gn_groups) % 32 == 0 && d->gn_rows_per_batch > 0 &&
+                   d->gn_valid_rows > 0 && d->gn_valid_rows <= d->gn_rows_per_batch,
+               TS_EINVAL, "gemm: gn_accum needs a plain epilogue, no batching and n / gn_groups a multiple of 32 (n=%lld groups=%d)",
+               (long long)d->n, (int)d->gn_groups);
   const int nb1 = d->batch1 > 0 ? d->batch1 : 1, nb2 = d->batch2 > 0 ? d->batch2 : 1;
   // Tile-N and split-K choice from a small cost model (units: 64-deep k-blocks of one 128 x 1 column strip):
   //   cost = waves * k_blocks_per_work_item * bn * eff(bn) + tail_epilogue * bn
@@ -724,6 +764,8 @@ int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
   ep.b_m1 = (nb1 > 1 && d->b_bs1 != 0) ? 1 : 0; ep.b_m2 = (nb2 > 1 && d->b_bs2 != 0) ? 1 : 0;
   ep.drop_thr = 0; ep.inv_keep = 1.f; ep.seed = d->seed; ep.salt = ctx->d_state;
   ep.trace = reinterpret_cast<unsigned long long*>(ctx->gemm_trace);
+  ep.gn_accum = d->gn_accum; ep.gn_rpb = d->gn_rows_per_batch; ep.gn_valid = d->gn_valid_rows; ep.gn_groups = d->gn_groups;
+  ep.gn_cpg = d->gn_accum ? d->n / d->gn_groups : 1;
   if (d->drop > 0.f) {
     double t = (double)d->drop * 4294967296.0;
     ep.drop_thr = (uint32_t)(t > 4294967295.0 ? 4294967295.0 : t);
@@ -749,6 +791,7 @@ int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
       if (d->c_preact) { r = get_tmap(ctx, &tp, d->c_preact, dims, str, f32 ? 32 : 64, 32, f32); if (r) return r; }
     }
     ep.tma_epi = ok ? 1 : 0;
+    TS_REQUIRE(ctx, ok || !d->gn_accum, TS_EUNSUPPORTED, "gemm: gn_accum needs a TMA-storable C (16-byte aligned base and row stride)");
     if (ok && splitk > 1) ep.accumulate = 1;   // split-K partials are added by the TMA reduce
   }
   ts_gemm_desc dd = *d;

@@ -527,6 +527,20 @@ int groupnorm_fwd(Ctx* ctx, int dt, const void* x, const float* mean, const floa
   return 0;
 }
 
+// Statistics taken by the producer of x (conv0_fwd / the conv GEMM epilogue, ts_gemm_desc.gn_accum) instead of a second pass
+// over x: zero the [B, G, 2] fp64 accumulator before the producer, turn it into mean / rstd after it.
+int groupnorm_stats_begin(Ctx* ctx, double* accum, int B, int G, cudaStream_t st) {
+  ts::launch_k(gn_zero_accum, cdiv(B * G * 2, 256), 256, 0, st, accum, B * G * 2);
+  TS_LAUNCH_OK(ctx);
+  return 0;
+}
+int groupnorm_stats_finalize(Ctx* ctx, const double* accum, float* mean, float* rstd, int B, int T_, int C, int G, float eps,
+                             cudaStream_t st) {
+  ts::launch_k(gn_finalize_kernel, cdiv(B * G, 256), 256, 0, st, accum, mean, rstd, B * G, (double)T_ * (C / G), eps);
+  TS_LAUNCH_OK(ctx);
+  return 0;
+}
+
 // gradient arriving at activation row t: dense `da`, or the col2im gather of the next strided conv's dcol
 // (da[b,t,c] = sum_j dcol[b, (t+left-j)/s, j*C + c] over taps j with (t+left-j) % s == 0 and a valid window index).
 // KS = k * 8 + s for the specialised (k, s) pairs of the Wav2Vec2 conv stacks; 0 = dense da; -1 = generic.
@@ -704,7 +718,7 @@ __global__ void __launch_bounds__(256, 4) gn_gelu_bwd2_kernel(const T* __restric
 int groupnorm_gelu_bwd(Ctx* ctx, int dt, const void* da, long long da_rpb, const Col2imSrc* col, const void* x,
                        long long x_rpb, const float* mean, const float* rstd, const float* gamma, const float* beta,
                        void* dx, long long dx_rpb, float* dgamma, float* dbeta, double* accum, int B, int T_, int C, int G,
-                       cudaStream_t st) {
+                       cudaStream_t st, bool skip_pass2) {
   Col2imSrc c;
   if (col) c = *col; else { c.dcol = nullptr; c.rows_per_batch = 0; c.t_next = 0; c.k = 0; c.s = 1; c.left = 0; }
   ts::launch_k(gn_zero_accum, cdiv(B * G * 2, 256), 256, 0, st, accum, B * G * 2);
@@ -720,11 +734,11 @@ int groupnorm_gelu_bwd(Ctx* ctx, int dt, const void* da, long long da_rpb, const
                                                      (TT*)dx, dx_rpb, dgamma, dbeta, accum, T_, C, G, rows1)
   if (dt == TS_F32) {
     if (ks == 0) GN_BWD1(float, 0); else if (ks == 26) GN_BWD1(float, 26); else if (ks == 18) GN_BWD1(float, 18); else GN_BWD1(float, -1);
-    ts::launch_k(gn_gelu_bwd2_kernel<float>, g2, 256, 0, st, (const float*)x, x_rpb, mean, rstd, gamma, (float*)dx, dx_rpb, accum,
+    if (!skip_pass2) ts::launch_k(gn_gelu_bwd2_kernel<float>, g2, 256, 0, st, (const float*)x, x_rpb, mean, rstd, gamma, (float*)dx, dx_rpb, accum,
                                                    T_, C, G, rows2);
   } else {
     if (ks == 0) GN_BWD1(bf16, 0); else if (ks == 26) GN_BWD1(bf16, 26); else if (ks == 18) GN_BWD1(bf16, 18); else GN_BWD1(bf16, -1);
-    ts::launch_k(gn_gelu_bwd2_kernel<bf16>, g2, 256, 0, st, (const bf16*)x, x_rpb, mean, rstd, gamma, (bf16*)dx, dx_rpb, accum, T_,
+    if (!skip_pass2) ts::launch_k(gn_gelu_bwd2_kernel<bf16>, g2, 256, 0, st, (const bf16*)x, x_rpb, mean, rstd, gamma, (bf16*)dx, dx_rpb, accum, T_,
                                                   C, G, rows2);
   }
 #undef GN_BWD1

@@ -23,6 +23,8 @@ int layernorm_bwd_drop(Ctx*, int dt, const void* dy, const void* x, const float*
 int groupnorm_stats(Ctx*, int dt, const void* x, double* accum /*[B,G,2] scratch*/, float* mean, float* rstd,
                     int B, int T, int C, int G, long long rows_per_batch, float eps, cudaStream_t);
 // y[b, out_left + t, :] = gelu(gamma*(x-mean)*rstd+beta); all other rows of y's batch block are zeroed.
+int groupnorm_stats_begin(Ctx*, double* accum, int B, int G, cudaStream_t);
+int groupnorm_stats_finalize(Ctx*, const double* accum, float* mean, float* rstd, int B, int T, int C, int G, float eps, cudaStream_t);
 int groupnorm_gelu_fwd(Ctx*, int dt, const void* x, long long x_rows_per_batch, const float* mean,
                        const float* rstd, const float* gamma, const float* beta, void* y,
                        long long y_rows_per_batch, int y_left, int B, int T, int C, int G, cudaStream_t);
@@ -37,7 +39,7 @@ struct Col2imSrc { const void* dcol; long long rows_per_batch; int t_next, k, s,
 int groupnorm_gelu_bwd(Ctx*, int dt, const void* da, long long da_rpb, const Col2imSrc* col, const void* x,
                        long long x_rpb, const float* mean, const float* rstd, const float* gamma,
                        const float* beta, void* dx, long long dx_rpb, float* dgamma, float* dbeta,
-                       double* accum /*[B,G,2] scratch*/, int B, int T, int C, int G, cudaStream_t);
+                       double* accum /*[B,G,2] scratch*/, int B, int T, int C, int G, cudaStream_t, bool skip_pass2 = false);
 
 // ---- elementwise.cu ------------------------------------------------------------------------------
 int cast_f32_to_bf16(Ctx*, const float* src, void* dst, long long n, cudaStream_t);
@@ -66,10 +68,15 @@ int transpose_inner(Ctx*, int dt_in, int dt_out, const void* x, void* y, int B, 
 
 // ---- conv_fe.cu ----------------------------------------------------------------------------------
 // conv0 (Cin = 1): y[b,t,c] = sum_j wave[b, s*t + j - left] * w[j,c];  y has y_rpb rows per batch.
+// gn_accum != NULL: also adds the GroupNorm moments of the stored y to gn_accum[B, G, 2] (groupnorm_stats_begin / _finalize).
 int conv0_fwd(Ctx*, int dt, const float* wave, const void* w /*act dtype [k,C]*/, void* y, long long y_rpb,
-              int B, int N, int T, int C, int k, int s, int left, cudaStream_t);
+              int B, int N, int T, int C, int k, int s, int left, cudaStream_t, double* gn_accum = nullptr, int G = 0);
+// gn_z != NULL: dy is the GELU-backward product of groupnorm_gelu_bwd(..., skip_pass2 = true) and the GroupNorm input gradient
+// is formed on load from (dy, gn_z, statistics, pass-1 sums in gn_accum) instead of being written and re-read.
 int conv0_wgrad(Ctx*, int dt, const float* wave, const void* dy, long long dy_rpb, float* dw /*[k,C] +=*/,
-                int B, int N, int T, int C, int k, int s, int left, cudaStream_t);
+                int B, int N, int T, int C, int k, int s, int left, cudaStream_t, const void* gn_z = nullptr, long long gn_z_rpb = 0,
+                const float* gn_mean = nullptr, const float* gn_rstd = nullptr, const float* gn_gamma = nullptr,
+                const double* gn_accum = nullptr, int G = 0);
 // group-major repack for the grouped positional conv: x [B,T,C] -> xg [G][B][T+K-1][C/G] with
 // `left` zero rows before and K-1-left after each block.
 int posconv_pack(Ctx*, int dt, const void* x, void* xg, int B, int T, int C, int G, int K, int left,

@@ -91,6 +91,9 @@ struct GemmB {
   GemmB& alpha(float a) { d.alpha = a; return *this; }
   GemmB& drop(float rate, uint64_t seed) { d.drop = rate; d.seed = seed; return *this; }
   GemmB& acc() { d.accumulate = 1; return *this; }
+  GemmB& gn_stats(double* accum, int rows_per_batch, int valid_rows, int groups) {
+    d.gn_accum = accum; d.gn_rows_per_batch = rows_per_batch; d.gn_valid_rows = valid_rows; d.gn_groups = groups; return *this;
+  }
   GemmB& simt() { d.force_engine = 1; return *this; }   // tiny / oddly strided problems: CUDA-core engine
   int run(Ctx* ctx, cudaStream_t st) { return gemm(ctx, &d, st); }
 };

@@ -37,6 +37,22 @@ template <> __device__ __forceinline__ void store8<bf16>(bf16* p, const float (&
   u.w = *reinterpret_cast<uint32_t*>(&h3);
   *reinterpret_cast<uint4*>(p) = u;
 }
+// raw 8-element vectors: the load is issued now, the conversion happens where the values are used (software pipelining)
+template <typename T> struct Raw8;
+template <> struct Raw8<float> { float4 a, b; };
+template <> struct Raw8<bf16> { uint4 u; };
+__device__ __forceinline__ void load_raw8(const float* p, Raw8<float>& r) {
+  r.a = reinterpret_cast<const float4*>(p)[0]; r.b = reinterpret_cast<const float4*>(p)[1];
+}
+__device__ __forceinline__ void load_raw8(const bf16* p, Raw8<bf16>& r) { r.u = *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void unpack8(const Raw8<float>& r, float (&v)[8]) {
+  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+__device__ __forceinline__ void unpack8(const Raw8<bf16>& r, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
 // round values to the storage dtype (no-op for fp32)
 template <typename T> __device__ __forceinline__ void round8(float (&v)[8]);
 template <> __device__ __forceinline__ void round8<float>(float (&v)[8]) {}

@@ -41,6 +41,7 @@ struct W2V {
   void *c[8], *a[8];
   float *gn_mean[8], *gn_rstd[8];
   double* gn_accum;
+  bool no_fused_gn = getenv("TETHYS_NO_FUSED_GN") && atoi(getenv("TETHYS_NO_FUSED_GN")) != 0;   // A/B switch: separate statistics pass
   void *hg, *possum, *ef, *fp_out, *hs, *z, *qfeat, *ph_lin, *ps, *pq_lin, *pq, *dS, *wt_flip;
   float *S, *logits;
   // task heads: dropped encoder output, fp32 logits + their gradient; pooled / projected states of the classifier
@@ -277,15 +278,22 @@ static int w2v_forward(W2V* m, const float* wave, const int* neg, long long neg_
   // ---- conv feature encoder (V:283-288) --------------------------------------------------------------
   for (int i = 0; i < n; ++i) {
     const int Ci = c.conv_dim[i];
+    // GroupNorm moments (V:167-176) are taken by the producer of the conv output where it can: conv0's store loop and the tcgen05
+    // GEMM epilogue (channels per group a multiple of 32); otherwise (fp32 parity engine, tiny test configs) by a pass over c[i]
+    const bool fused_stats = !m->no_fused_gn && (i == 0 || (dt == TS_BF16 && (Ci / G) % 32 == 0));
+    if (fused_stats) TS_TRY(groupnorm_stats_begin(ctx, m->gn_accum, B, G, st));
     if (i == 0) {
       TS_TRY(conv0_fwd(ctx, dt, wave, m->P + m->conv_w[0], m->c[0], m->rpb_c[0], B, m->N, m->Tc[0], Ci, c.conv_kernel[0],
-                       c.conv_stride[0], m->padl[0], st));
+                       c.conv_stride[0], m->padl[0], st, fused_stats ? m->gn_accum : nullptr, G));
     } else {
       const int Cin = c.conv_dim[i - 1], k = c.conv_kernel[i], s = c.conv_stride[i];
-      TS_TRY(GemmB(dt, dt).A(m->a[i - 1], 0, (long long)s * Cin).B(m->W(m->conv_w[i]), 1, Ci).C(m->c[i], Ci)
-                 .mnk(B * m->Rq[i], Ci, k * Cin).run(ctx, st));
+      GemmB g(dt, dt);
+      g.A(m->a[i - 1], 0, (long long)s * Cin).B(m->W(m->conv_w[i]), 1, Ci).C(m->c[i], Ci).mnk(B * m->Rq[i], Ci, k * Cin);
+      if (fused_stats) g.gn_stats(m->gn_accum, m->Rq[i], m->Tc[i], G);
+      TS_TRY(g.run(ctx, st));
     }
-    TS_TRY(groupnorm_stats(ctx, dt, m->c[i], m->gn_accum, m->gn_mean[i], m->gn_rstd[i], B, m->Tc[i], Ci, G, m->rpb_c[i], 1e-5f, st));
+    if (fused_stats) TS_TRY(groupnorm_stats_finalize(ctx, m->gn_accum, m->gn_mean[i], m->gn_rstd[i], B, m->Tc[i], Ci, G, 1e-5f, st));
+    else TS_TRY(groupnorm_stats(ctx, dt, m->c[i], m->gn_accum, m->gn_mean[i], m->gn_rstd[i], B, m->Tc[i], Ci, G, m->rpb_c[i], 1e-5f, st));
     TS_TRY(groupnorm_gelu_fwd(ctx, dt, m->c[i], m->rpb_c[i], m->gn_mean[i], m->gn_rstd[i], m->P + m->conv_g[i],
                               m->P + m->conv_b[i], m->a[i], m->rpb_a[i], m->a_left[i], B, m->Tc[i], Ci, G, st));
     if (i + 1 < n)  // finite slack behind the last batch block (window reads of the dummy rows)
@@ -563,6 +571,7 @@ static int w2v_backward_stage(W2V* m, int stage, cudaStream_t st) {
                .C(da_last, C).cstride(cpg, (long long)T * C).res(dsum, C, cpg, (long long)T * C)
                .mnk(T, cpg, K * cpg).batch(G, B).run(ctx, st));
   }
+  const bool fuse_l0 = !m->no_fused_gn;
   for (int i = n - 1; i >= 0; --i) {
     const int Ci = c.conv_dim[i];
     Col2imSrc col;
@@ -574,8 +583,14 @@ static int w2v_backward_stage(W2V* m, int stage, cudaStream_t st) {
     }
     TS_TRY(groupnorm_gelu_bwd(ctx, dt, (i + 1 < n) ? nullptr : da_last, T, colp, m->c[i], m->rpb_c[i], m->gn_mean[i], m->gn_rstd[i],
                               m->P + m->conv_g[i], m->P + m->conv_b[i], m->g_dc, m->rpb_c[i], m->G + m->conv_g[i], m->G + m->conv_b[i],
-                              m->gn_accum, B, m->Tc[i], Ci, G, st));
+                              m->gn_accum, B, m->Tc[i], Ci, G, st, /*skip_pass2=*/fuse_l0 && i == 0));
     if (i == 0) {
+      // layer 0: the only consumer of d(conv0 output) is this weight gradient, which forms it on load (conv_fe.cu Conv0GnPass2)
+      if (fuse_l0)
+        TS_TRY(conv0_wgrad(ctx, dt, m->wave, m->g_dc, m->rpb_c[0], m->G + m->conv_w[0], B, m->N, m->Tc[0], Ci, c.conv_kernel[0],
+                           c.conv_stride[0], m->padl[0], st, m->c[0], m->rpb_c[0], m->gn_mean[0], m->gn_rstd[0], m->P + m->conv_g[0],
+                           m->gn_accum, G));
+      else
       TS_TRY(conv0_wgrad(ctx, dt, m->wave, m->g_dc, m->rpb_c[0], m->G + m->conv_w[0], B, m->N, m->Tc[0], Ci, c.conv_kernel[0],
                          c.conv_stride[0], m->padl[0], st));
     } else {
