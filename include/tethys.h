@@ -237,6 +237,12 @@ int ts_optim_global_clip_scale(ts_optim* o, const float* grads, float clip, floa
 int ts_optim_step(ts_optim* o, float* params, const float* grads, float* m, float* v, void* params_bf16 /*nullable*/,
                   float lr, float beta1, float beta2, float eps, int32_t step, float global_clip /*<=0 off*/,
                   float clipnorm /*<=0 off*/, int32_t fuse_global_clip, void* stream);
+/* The same step reading the gradients from a bf16 arena of the same layout — the all-reduced gradient bucket of the bf16
+ * data-parallel step (ts_grad_pack_bf16 + ts_comm_allreduce_bucket): saves the unpack pass (6 B/param) and 2 B/param of gradient
+ * reads; every gradient value is widened exactly: the same arithmetic as ts_grad_unpack_bf16 followed by ts_optim_step. */
+int ts_optim_step_lp(ts_optim* o, float* params, const void* grads_bf16, float* m, float* v, void* params_bf16 /*nullable*/,
+                     float lr, float beta1, float beta2, float eps, int32_t step, float global_clip /*<=0 off*/,
+                     float clipnorm /*<=0 off*/, int32_t fuse_global_clip, void* stream);
 int ts_cast_f32_to_bf16(ts_ctx* ctx, const float* src, void* dst, int64_t n, void* stream);
 /* Gradient buckets for the cross-replica SUM (the all-reduce inside apply_gradients, W:834 / V:1246) in bf16: pack = bf16(src *
  * scale_dev[0]) (scale_dev nullable; the Wav2Vec2 step folds its local clip_by_global_norm factor, V:1243, in here), unpack =

@@ -125,6 +125,7 @@ SYMBOLS = {
     "ts_optim_clip_global": (_I, [_P, _P, _F, _P, _P]),
     "ts_optim_global_clip_scale": (_I, [_P, _P, _F, _P, _P]),
     "ts_optim_step": (_I, [_P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _I, _F, _F, _I, _P]),
+    "ts_optim_step_lp": (_I, [_P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _I, _F, _F, _I, _P]),
     "ts_cast_f32_to_bf16": (_I, [_P, _P, _P, _L, _P]),
     "ts_grad_pack_bf16": (_I, [_P, _P, _P, _L, _P, _P]),
     "ts_grad_unpack_bf16": (_I, [_P, _P, _P, _L, _P]),

@@ -251,7 +251,7 @@ void ts_optim_destroy(ts_optim* o_) {
 int ts_optim_clip_global(ts_optim* o_, float* grads, float clip, float* norm_out_dev, void* stream) {
   ts::Optim* o = reinterpret_cast<ts::Optim*>(o_);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = ts::grad_sumsq(o->ctx, grads, o->d_items, o->nitems, o->nseg, o->d_sumsq, st);
+  int rc = ts::grad_sumsq(o->ctx, grads, TS_F32, o->d_items, o->nitems, o->nseg, o->d_sumsq, st);
   if (rc) return rc;
   rc = ts::global_clip_scale(o->ctx, o->d_sumsq, o->nseg, clip, o->d_scal, norm_out_dev ? norm_out_dev : o->d_scal + 1, st);
   if (rc) return rc;
@@ -262,21 +262,22 @@ int ts_optim_global_clip_scale(ts_optim* o_, const float* grads, float clip, flo
   ts::Optim* o = reinterpret_cast<ts::Optim*>(o_);
   cudaStream_t st = (cudaStream_t)stream;
   if (!o || !grads || !scale_out_dev) return TS_EINVAL;
-  int rc = ts::grad_sumsq(o->ctx, grads, o->d_items, o->nitems, o->nseg, o->d_sumsq, st);
+  int rc = ts::grad_sumsq(o->ctx, grads, TS_F32, o->d_items, o->nitems, o->nseg, o->d_sumsq, st);
   if (rc) return rc;
   return ts::global_clip_scale(o->ctx, o->d_sumsq, o->nseg, clip, scale_out_dev, o->d_scal + 1, st);
 }
 
-int ts_optim_step(ts_optim* o_, float* params, const float* grads, float* m, float* v, void* params_bf16, float lr,
-                  float beta1, float beta2, float eps, int32_t step, float global_clip, float clipnorm,
-                  int32_t fuse_global_clip, void* stream) {
+static int optim_step_impl(ts_optim* o_, float* params, const void* grads, int grad_dt, float* m, float* v, void* params_bf16, float lr,
+                           float beta1, float beta2, float eps, int32_t step, float global_clip, float clipnorm,
+                           int32_t fuse_global_clip, void* stream) {
   ts::Optim* o = reinterpret_cast<ts::Optim*>(o_);
+  if (!o || !params || !grads || !m || !v) return TS_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   ts::AdamArgs a;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.step = step; a.clipnorm = clipnorm;
   a.pre_scale = nullptr; a.sumsq = nullptr;
   if (clipnorm > 0.f || (fuse_global_clip && global_clip > 0.f)) {
-    int rc = ts::grad_sumsq(o->ctx, grads, o->d_items, o->nitems, o->nseg, o->d_sumsq, st);
+    int rc = ts::grad_sumsq(o->ctx, grads, grad_dt, o->d_items, o->nitems, o->nseg, o->d_sumsq, st);
     if (rc) return rc;
     a.sumsq = o->d_sumsq;
   }
@@ -285,7 +286,17 @@ int ts_optim_step(ts_optim* o_, float* params, const float* grads, float* m, flo
     if (rc) return rc;
     a.pre_scale = o->d_scal;
   }
-  return ts::adam_step(o->ctx, params, grads, m, v, params_bf16, o->d_items, o->nitems, a, st);
+  return ts::adam_step(o->ctx, params, grads, grad_dt, m, v, params_bf16, o->d_items, o->nitems, a, st);
+}
+int ts_optim_step(ts_optim* o, float* params, const float* grads, float* m, float* v, void* params_bf16, float lr,
+                  float beta1, float beta2, float eps, int32_t step, float global_clip, float clipnorm,
+                  int32_t fuse_global_clip, void* stream) {
+  return optim_step_impl(o, params, grads, TS_F32, m, v, params_bf16, lr, beta1, beta2, eps, step, global_clip, clipnorm, fuse_global_clip, stream);
+}
+int ts_optim_step_lp(ts_optim* o, float* params, const void* grads_bf16, float* m, float* v, void* params_bf16, float lr,
+                     float beta1, float beta2, float eps, int32_t step, float global_clip, float clipnorm,
+                     int32_t fuse_global_clip, void* stream) {
+  return optim_step_impl(o, params, grads_bf16, TS_BF16, m, v, params_bf16, lr, beta1, beta2, eps, step, global_clip, clipnorm, fuse_global_clip, stream);
 }
 
 int ts_cast_f32_to_bf16(ts_ctx* ctx, const float* src, void* dst, int64_t n, void* stream) {

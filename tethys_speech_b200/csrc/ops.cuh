@@ -161,7 +161,7 @@ struct Segment { long long offset; int rows, cols; long long ld; };
 struct WorkItem { long long start; long long ld; int rows, cols, seg, pad; };
 std::vector<WorkItem> build_work_items(const std::vector<Segment>& segs);
 // per-segment sum of squares of grads -> sumsq[nseg] (fp32, overwritten)
-int grad_sumsq(Ctx*, const float* grads, const WorkItem* d_items, int nitems, int nseg, float* sumsq, cudaStream_t);
+int grad_sumsq(Ctx*, const void* grads, int grad_dt /*TS_F32 | TS_BF16*/, const WorkItem* d_items, int nitems, int nseg, float* sumsq, cudaStream_t);
 // scales[0] = global clip scale from sum(sumsq) (clip_by_global_norm, V:1243) or 1
 int global_clip_scale(Ctx*, const float* sumsq, int nseg, float clip, float* scale_out, float* norm_out,
                       cudaStream_t);
@@ -173,7 +173,7 @@ struct AdamArgs {
   const float* pre_scale;                    // device scalar or NULL (=1)
   const float* sumsq;                        // per segment sum of squares of the (unscaled) grads, or NULL
 };
-int adam_step(Ctx*, float* params, const float* grads, float* m, float* v, void* params_bf16 /*or NULL*/,
+int adam_step(Ctx*, float* params, const void* grads, int grad_dt /*TS_F32 | TS_BF16*/, float* m, float* v, void* params_bf16 /*or NULL*/,
               const WorkItem* d_items, int nitems, const AdamArgs& a, cudaStream_t);
 int scale_inplace(Ctx*, float* x, long long n, const float* scale_dev, float scale_host, cudaStream_t);
 

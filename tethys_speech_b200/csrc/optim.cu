@@ -32,7 +32,19 @@ __global__ void zero_f32_kernel(float* p, int n) {
   if (i < n) p[i] = 0.f;
 }
 
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, const WorkItem* __restrict__ items,
+// gradient arena element type GT: float (the arena the backward kernels write) or bf16 (the all-reduced gradient bucket, read as is)
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ldg4(const bf16* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float ldg1(const float* p) { return *p; }
+__device__ __forceinline__ float ldg1(const bf16* p) { return __bfloat162float(*p); }
+
+template <typename GT>
+__global__ void __launch_bounds__(256) sumsq_kernel(const GT* __restrict__ g, const WorkItem* __restrict__ items,
                                                     float* __restrict__ sumsq) {
   ts::pdl_enter();
   __shared__ float red[32];
@@ -40,23 +52,24 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   float s = 0.f;
   const bool vec = ((it.start | it.ld | (long long)it.cols) & 3) == 0;   // arena blocks are 64-element aligned: the usual case
   for (int r = 0; r < it.rows; ++r) {
-    const float* p = g + it.start + (long long)r * it.ld;
+    const GT* p = g + it.start + (long long)r * it.ld;
     if (vec) {
       for (int c = threadIdx.x * 4; c < it.cols; c += 1024) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(p + c));
+        const float4 v = ldg4(p + c);
         s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
       }
     } else {
-      for (int c = threadIdx.x; c < it.cols; c += 256) { const float v = p[c]; s += v * v; }
+      for (int c = threadIdx.x; c < it.cols; c += 256) { const float v = ldg1(p + c); s += v * v; }
     }
   }
   s = block_sum(s, red);
   if (threadIdx.x == 0) atomicAdd(&sumsq[it.seg], s);
 }
 
-int grad_sumsq(Ctx* ctx, const float* grads, const WorkItem* items, int n, int nseg, float* sumsq, cudaStream_t st) {
+int grad_sumsq(Ctx* ctx, const void* grads, int grad_dt, const WorkItem* items, int n, int nseg, float* sumsq, cudaStream_t st) {
   ts::launch_k(zero_f32_kernel, cdiv(nseg, 256), 256, 0, st, sumsq, nseg);
-  ts::launch_k(sumsq_kernel, n, 256, 0, st, grads, items, sumsq);
+  if (grad_dt == TS_BF16) ts::launch_k(sumsq_kernel<bf16>, n, 256, 0, st, (const bf16*)grads, items, sumsq);
+  else ts::launch_k(sumsq_kernel<float>, n, 256, 0, st, (const float*)grads, items, sumsq);
   TS_LAUNCH_OK(ctx);
   return 0;
 }
@@ -79,7 +92,8 @@ int global_clip_scale(Ctx* ctx, const float* sumsq, int nseg, float clip, float*
   return 0;
 }
 
-__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+template <typename GT>
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const GT* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, bf16* __restrict__ p16,
                                                    const WorkItem* __restrict__ items, float lr_t, float omb1, float omb2,
                                                    float eps, float clipnorm, const float* __restrict__ pre_scale,
@@ -102,7 +116,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     if (vec) {  // 16-byte accesses: 4 parameters per thread and iteration
       for (int c = threadIdx.x * 4; c < it.cols; c += 1024) {
         const long long i = base + c;
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(g + i));
+        const float4 g4 = ldg4(g + i);
         float4 m4 = *reinterpret_cast<const float4*>(m + i), v4 = *reinterpret_cast<const float4*>(v + i);
         float4 p4 = *reinterpret_cast<const float4*>(p + i);
         const float gg[4] = {g4.x * sc, g4.y * sc, g4.z * sc, g4.w * sc};
@@ -127,7 +141,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     } else {
       for (int c = threadIdx.x; c < it.cols; c += 256) {
         const long long i = base + c;
-        const float gi = g[i] * sc;
+        const float gi = ldg1(g + i) * sc;
         float mi = m[i], vi = v[i];
         mi = mi + (gi - mi) * omb1;
         vi = vi + (gi * gi - vi) * omb2;
@@ -139,12 +153,16 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
-int adam_step(Ctx* ctx, float* params, const float* grads, float* m, float* v, void* params_bf16, const WorkItem* items, int n,
+int adam_step(Ctx* ctx, float* params, const void* grads, int grad_dt, float* m, float* v, void* params_bf16, const WorkItem* items, int n,
               const AdamArgs& a, cudaStream_t st) {
   TS_REQUIRE(ctx, a.step >= 0, TS_EINVAL, "adam: step must be >= 1 (or 0 = take it from the device step state)");
   const double lr_t = a.step >= 1 ? (double)a.lr * sqrt(1.0 - pow((double)a.beta2, a.step)) / (1.0 - pow((double)a.beta1, a.step)) : 0.0;
-  ts::launch_k(adam_kernel, n, 256, 0, st, params, grads, m, v, (bf16*)params_bf16, items, (float)lr_t, 1.f - a.beta1, 1.f - a.beta2,
-                                 a.eps, a.clipnorm, a.pre_scale, a.sumsq, a.lr, a.step >= 1 ? nullptr : ctx->d_state);
+  if (grad_dt == TS_BF16)
+    ts::launch_k(adam_kernel<bf16>, n, 256, 0, st, params, (const bf16*)grads, m, v, (bf16*)params_bf16, items, (float)lr_t, 1.f - a.beta1,
+                 1.f - a.beta2, a.eps, a.clipnorm, a.pre_scale, a.sumsq, a.lr, a.step >= 1 ? nullptr : ctx->d_state);
+  else
+    ts::launch_k(adam_kernel<float>, n, 256, 0, st, params, (const float*)grads, m, v, (bf16*)params_bf16, items, (float)lr_t, 1.f - a.beta1,
+                 1.f - a.beta2, a.eps, a.clipnorm, a.pre_scale, a.sumsq, a.lr, a.step >= 1 ? nullptr : ctx->d_state);
   TS_LAUNCH_OK(ctx);
   return 0;
 }

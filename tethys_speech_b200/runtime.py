@@ -446,12 +446,14 @@ class Adam:
         st = self._bind(model)
         prog.ctx.check(prog.lib.ts_optim_global_clip_scale(st["optim"], ptr(prog.grads), float(global_clip_norm), ptr(out), stream_ptr()))
 
-    def update(self, model):
-        """Phase 3 (after the all-reduce): per-variable clipnorm + Adam, advancing `iterations`."""
+    def update(self, model, grads_lp=None):
+        """Phase 3 (after the all-reduce): per-variable clipnorm + Adam, advancing `iterations`. grads_lp: the all-reduced bf16
+        gradient bucket (whole arena) — read as is (ts_optim_step_lp) instead of being unpacked into the fp32 arena first."""
         prog = model._prog
         st = self._bind(model)
         self.iterations += 1
-        prog.ctx.check(prog.lib.ts_optim_step(st["optim"], ptr(prog.params), ptr(prog.grads), ptr(st["m"]), ptr(st["v"]),
+        fn = prog.lib.ts_optim_step if grads_lp is None else prog.lib.ts_optim_step_lp
+        prog.ctx.check(fn(st["optim"], ptr(prog.params), ptr(prog.grads if grads_lp is None else grads_lp), ptr(st["m"]), ptr(st["v"]),
                                               ptr(prog.params_lp), self.learning_rate, self.beta_1, self.beta_2, self.epsilon,
                                               0 if self.device_step else self.iterations, 0.0, float(self.clipnorm or 0.0), 0,
                                               stream_ptr()))

@@ -577,9 +577,8 @@ def make_graphed_distributed_step(strategy, model, optimizer, example_features, 
             strategy.all_reduce_sum_(prog.grads, bucket_elems=int(os.environ.get("TETHYS_AR_BUCKET_ELEMS", 0)))
 
     def seg_update():
-        if lp:
-            prog.unpack_grads()
-        optimizer.update(model)
+        # bf16 buckets: clipnorm + Adam read the reduced bucket directly (no unpack pass; prog.grads keeps the LOCAL gradients)
+        optimizer.update(model, grads_lp=prog.grads_lp() if lp else None)
 
     if getattr(strategy, "comm", None) is not None:
         # native communicator: the all-reduce is a stream-ordered NCCL call on the compute stream — the whole step, collective and

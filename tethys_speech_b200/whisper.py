@@ -421,9 +421,7 @@ def make_graphed_distributed_step(strategy, model, optimizer, example_features, 
                     prog.pack_grads(a0, a1)
                 strategy.all_reduce_async_(prog.grads_lp()[a0:a1] if lp else prog.grads[a0:a1])
             strategy.join_async()
-            if lp:
-                prog.unpack_grads()
-            optimizer.update(model)     # (per-bucket updates underneath the last all-reduce were measured slower at N = 2: 7.61 vs 7.21 ms)
+            optimizer.update(model, grads_lp=prog.grads_lp() if lp else None)     # bf16 buckets are read as they are; (per-bucket updates underneath the last all-reduce were measured slower at N = 2: 7.61 vs 7.21 ms)
             state["loss_red"] = strategy.reduce(ReduceOp.SUM, state["loss"], axis=None)     # W:848, inside the graph as well
 
         segs = GraphedSegments([("graph", seg_all)], model, optimizer, warmup=warmup)
