@@ -48,6 +48,7 @@ struct Whisper {
   float* scalars;  // [0] loss, [3] raw sum
   const int* labels = nullptr;
   // scratch
+  float* s_x32;   // fp32 [B*S, d]: split-K target of the lm_head input gradient (K = vocabulary)
   void *s_a, *s_b, *s_t, *s_x, *s_f, *s_ctx, *s_qkv, *s_P, *s_Pd, *s_dqacc, *s_denc, *s_dq, *s_dkv, *s_dcol, *s_du;
   uint64_t seed = 0;
   int training = 1;
@@ -185,6 +186,7 @@ static int plan(Whisper* m, int B, int Tm, int S, Bump& bp) {
   // scratch (sized for the encoder, which has the larger row count)
   const long long Mx = std::max(Me, Md);
   m->s_a = bp.get(m->E(Mx * d)); m->s_b = bp.get(m->E(Mx * d)); m->s_t = bp.get(m->E(Mx * d)); m->s_x = bp.get(m->E(Mx * d));
+  m->s_x32 = (float*)bp.get(sizeof(float) * (size_t)Md * d);
   m->s_f = bp.get(m->E(Mx * F)); m->s_ctx = bp.get(m->E(Mx * d)); m->s_qkv = bp.get(m->E(Mx * 3 * d));
   const long long pmax = std::max((long long)B * nh * T * Tp, std::max((long long)B * nh * S * Tp, (long long)B * nh * S * Sp));
   if (m->fused_attn) { m->s_P = bp.get(4ll * B * nh * std::max(T, S)); m->s_Pd = nullptr; m->s_dqacc = bp.get(4ll * B * std::max(T, S) * d); }   // fused: D scratch + fp32 dQ accumulator
@@ -466,7 +468,16 @@ static int whisper_backward_stage(Whisper* m, int stage, cudaStream_t st) {
   if (stage == 0) {
     // lm_head: dW = dec_out^T dlogits ; d(dec_out) = dlogits W^T ; final decoder LN
     TS_TRY(GemmB(dt, TS_F32).A(m->dec_out, 1, d).B(m->dlogits, 1, m->Vp).C(m->G + m->lm_w, m->Vp).mnk(d, (int)m->Vp, (int)Md).acc().run(ctx, st));
-    TS_TRY(GemmB(dt, dt).A(m->dlogits, 0, m->Vp).B(m->W(m->lm_w), 0, m->Vp).C(m->s_x, d).mnk((int)Md, d, (int)m->Vp).run(ctx, st));
+    if (dt == TS_BF16) {
+      // [B*S, d] = [B*S, vocab] x [vocab, d]: 4 x 12 output tiles with an 811-k-block reduce dim (vocab 51 865). As a bf16-output
+      // GEMM that is 48 CTAs walking the whole vocabulary each (228 us); into an fp32 target the engine may split K over all SMs
+      // (TMA reduce-add of the partials) and a 1.2 MB cast finishes it.
+      TS_TRY(fill_zero(ctx, m->s_x32, (long long)sizeof(float) * Md * d, st));
+      TS_TRY(GemmB(dt, TS_F32).A(m->dlogits, 0, m->Vp).B(m->W(m->lm_w), 0, m->Vp).C(m->s_x32, d).mnk((int)Md, d, (int)m->Vp).acc().run(ctx, st));
+      TS_TRY(cast_f32_to_bf16(ctx, m->s_x32, m->s_x, Md * d, st));
+    } else {
+      TS_TRY(GemmB(dt, dt).A(m->dlogits, 0, m->Vp).B(m->W(m->lm_w), 0, m->Vp).C(m->s_x, d).mnk((int)Md, d, (int)m->Vp).run(ctx, st));
+    }
     TS_TRY(layernorm_bwd(ctx, dt, m->s_x, m->g_final, m->P + m->dec_ln_g, m->dec_m, m->dec_r, nullptr, m->s_a, m->G + m->dec_ln_g, m->G + m->dec_ln_b, (int)Md, d, st));
     TS_TRY(fill_zero(ctx, m->s_denc, m->E(Me * d), st));
     return 0;

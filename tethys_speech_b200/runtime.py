@@ -264,16 +264,21 @@ class Strategy:
         dt = _lib.TS_F32 if t.dtype == torch.float32 else _lib.TS_BF16
         self._ctx.check(self._ctx.lib.ts_comm_allreduce_bucket(self.comm, ptr(t), t.numel(), dt, ptr(premul), stream_ptr()))
 
-    def all_reduce_async_(self, t, premul=None):
+    def all_reduce_async_(self, t, premul=None, pre=None):
         """SUM all-reduce of `t` that may run underneath the kernels issued after it: enqueued on the communicator's side stream,
         ordered after everything already on the compute stream (a fork that a CUDA-graph capture records as such).
-        join_async() makes the compute stream wait for all of them."""
+        join_async() makes the compute stream wait for all of them. `pre` (optional callable) runs on the same side stream right
+        before the collective — the fp32 -> bf16 packing of the bucket, so that it too stays off the compute stream."""
         if self.comm is None:
+            if pre is not None:
+                pre()
             self._works = getattr(self, "_works", [])
             self._works.append(self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, async_op=True))
             return
         self.comm_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.comm_stream):
+            if pre is not None:
+                pre()
             self._native_all_reduce(t, premul=premul)
 
     def async_done_event(self):

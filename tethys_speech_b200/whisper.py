@@ -411,15 +411,21 @@ def make_graphed_distributed_step(strategy, model, optimizer, example_features, 
         # native communicator: the collectives are stream-ordered NCCL calls, so the WHOLE step is one CUDA graph — every bucket's
         # all-reduce forks onto the communicator's side stream inside the capture and runs underneath the remaining backward
         # stages; no host round trip at any boundary
+        pack_on_main = bool(os.environ.get("TETHYS_PACK_ON_MAIN"))   # A/B switch
+
         def seg_all():
             prog.ctx.check(prog.lib.ts_step_state_advance(prog.ctx.h, stream_ptr()))
             out = model(feats, labels=labels, training=True, dropout=dropout)
             state["loss"] = out["loss"]
             for (s0, s1, a0, a1) in groups:
                 prog.backward(s0, s1)
-                if lp:
+                if lp and pack_on_main:
                     prog.pack_grads(a0, a1)
-                strategy.all_reduce_async_(prog.grads_lp()[a0:a1] if lp else prog.grads[a0:a1])
+                    strategy.all_reduce_async_(prog.grads_lp()[a0:a1])
+                elif lp:  # the bucket is packed to bf16 on the communicator's stream too, underneath the next backward stages
+                    strategy.all_reduce_async_(prog.grads_lp()[a0:a1], pre=lambda a0=a0, a1=a1: prog.pack_grads(a0, a1))
+                else:
+                    strategy.all_reduce_async_(prog.grads[a0:a1])
             strategy.join_async()
             optimizer.update(model, grads_lp=prog.grads_lp() if lp else None)     # bf16 buckets are read as they are; (per-bucket updates underneath the last all-reduce were measured slower at N = 2: 7.61 vs 7.21 ms)
             state["loss_red"] = strategy.reduce(ReduceOp.SUM, state["loss"], axis=None)     # W:848, inside the graph as well
