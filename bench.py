@@ -215,6 +215,28 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------
+def _timed_warm(fn, iters=20, warm=3):
+    """Device time (s) of fn()'s kernels replayed back to back as one CUDA graph of `iters` launches, operands L2-resident where they
+    fit: what a GEMM sees inside the step when its producer has just written its input. Reported next to the cold-L2 figure."""
+    import torch
+
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
 def _timed(fn, flush, iters=10, warm=3):
     """Average device time (s) of fn()'s kernels on the current stream with a cold L2. Two CUDA graphs are replayed `iters` times
     between CUDA events: [256 MB memset; fn()] and [256 MB memset]; the difference of the two totals / iters is the kernels' time
@@ -296,9 +318,11 @@ def kernel_rooflines(ctx, peaks, B, T, H, F, nh, n_params):
             rv = torch.zeros_like(c); d.residual = rv.data_ptr(); d.ldr = n; keep.append(rv)
         d.act, d.drop, d.seed, d.accumulate = act, drop, 7, 1 if acc else 0
         t = _timed(lambda: ctx.check(ctx.lib.ts_gemm(ctx.h, C.byref(d), stream_ptr())), flush)
+        tw = _timed_warm(lambda: ctx.check(ctx.lib.ts_gemm(ctx.h, C.byref(d), stream_ptr())))
         tf = 2.0 * m * n * k / t / 1e12
         out.append({"kernel": name, "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                    "frac": tf / peaks["bf16_tflops"], "us": t * 1e6, "traffic": ncu_traffic(key) if key else None})
+                    "frac": tf / peaks["bf16_tflops"], "us": t * 1e6, "us_warm_l2": tw * 1e6, "frac_warm_l2": 2.0 * m * n * k / tw / 1e12 / peaks["bf16_tflops"],
+                    "traffic": ncu_traffic(key) if key else None})
         return out[-1]
 
     dominant = gemm(f"gemm_tc_kernel FFN fc1 {M}x{F}x{H} +bias+GELU+dropout (W:194-195 / V:391-393)", M, F, H, 0, 1, bias=True, act=1,

@@ -91,11 +91,6 @@ struct Conv0GnPass2 {
 
 constexpr int C0_WG_STAGES = 4;   // cp.async ring depth (two rows of dy [+ z] per thread and stage)
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <typename T, bool GN> struct C0Wg {
   static constexpr int NV = sizeof(T) / 2;                 // 16-byte vectors per 8 elements

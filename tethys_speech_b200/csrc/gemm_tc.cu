@@ -102,20 +102,21 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 // Per-element epilogue math on a thread's NV consecutive columns of one output row.
 template <int NV>
 __device__ __forceinline__ void epi_bias(float (&v)[NV], const EpiParams& p, const float* bias, int col, bool full) {
-#pragma unroll
-  for (int i = 0; i < NV; ++i) v[i] *= p.alpha;
-  if (bias) {
+  if (bias) {   // alpha and the bias in one FMA per element
+    const float a = p.alpha;
     if (full && (reinterpret_cast<uintptr_t>(bias + col) & 15) == 0) {
 #pragma unroll
       for (int i = 0; i < NV; i += 4) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col + i));  // warp-uniform address: one broadcast
-        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+        v[i] = fmaf(v[i], a, b.x); v[i + 1] = fmaf(v[i + 1], a, b.y); v[i + 2] = fmaf(v[i + 2], a, b.z); v[i + 3] = fmaf(v[i + 3], a, b.w);
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < NV; ++i)
-        if (col + i < p.n) v[i] += __ldg(bias + col + i);
+      for (int i = 0; i < NV; ++i) v[i] = fmaf(v[i], a, col + i < p.n ? __ldg(bias + col + i) : 0.f);
     }
+  } else if (p.alpha != 1.f) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] *= p.alpha;
   }
 }
 template <int NV, typename OutT>

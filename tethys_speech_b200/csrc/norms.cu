@@ -659,6 +659,135 @@ __global__ void __launch_bounds__(256, 2) gn_gelu_bwd1_kernel(const T* __restric
   for (int i = threadIdx.x; i < 2 * G; i += 256) atomicAdd(&accum[(long long)b * G * 2 + i], sacc[i]);
 }
 
+// Pass 1 with the upstream gradient / dcol taps and x streamed through a per-thread cp.async ring (KS = 0, 26, 18): the direct
+// version above holds every in-flight 16-byte load in registers (122 registers, 2 blocks/SM, 24 % of the warp slots; ncu: 4.4 warps
+// stalled on long-scoreboard per issue, 3.3 TB/s). Here up to (S-1) stages x 2 rows x (2-3) vectors per thread are in flight in
+// shared memory; out-of-range taps are zero-filled by the copy itself (src-size 0), so the math is the dense path's.
+template <typename T, int KS>
+__global__ void __launch_bounds__(256, 2) gn_gelu_bwd1_ring_kernel(const T* __restrict__ da, long long da_rpb, Col2imSrc col,
+                                                                   const T* __restrict__ x, long long x_rpb,
+                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   T* __restrict__ dx, long long dx_rpb, float* __restrict__ dgamma,
+                                                                   float* __restrict__ dbeta, double* __restrict__ accum, int T_,
+                                                                   int C, int G, int rows_per_block) {
+  ts::pdl_enter();
+  static_assert(KS == 0 || KS == 26 || KS == 18, "ring version: dense upstream, (k 3, s 2) or (k 2, s 2) taps");
+  constexpr int NV = sizeof(T) / 2;               // 16-byte vectors per 8 elements
+  constexpr int NSRC = KS == 26 ? 3 : 2;          // tap a, [tap b,] x
+  constexpr int VPS = 2 * NSRC * NV;              // vectors per thread and stage (two rows)
+  constexpr int S = sizeof(T) == 2 ? 4 : 2;       // ring depth
+  extern __shared__ __align__(16) uint8_t smraw[];
+  uint4* stg = reinterpret_cast<uint4*>(smraw);                      // [S][VPS][256]
+  float* sg = reinterpret_cast<float*>(stg + S * VPS * 256);         // [C] dgamma partials
+  float* sb = sg + C;                                                // [C] dbeta partials
+  double* sacc = reinterpret_cast<double*>(sb + C);                  // [2 G]
+  const int b = blockIdx.y;
+  const int tpr = C / 8, rpi = 256 / tpr;
+  const int tc = threadIdx.x % tpr, tr = threadIdx.x / tpr;
+  const int cpg = C / G, g = (tc * 8) / cpg;
+  const int t0 = blockIdx.x * rows_per_block, t1 = min(T_, t0 + rows_per_block);
+  const bool active = tr < rpi;
+  const T* da_b = KS == 0 ? da + (long long)b * da_rpb * C + tc * 8 : nullptr;
+  const T* dcol_b = KS == 0 ? nullptr
+                            : reinterpret_cast<const T*>(col.dcol) + (long long)b * col.rows_per_batch * ((long long)col.k * C) + tc * 8;
+  const T* xb = x + (long long)b * x_rpb * C + tc * 8;
+  auto slot_ptr = [&](int slot, int u, int src) { return stg + ((slot * VPS) + (u * NSRC + src) * NV) * 256 + threadIdx.x; };
+  auto copy8 = [&](uint4* dst, const T* src, bool ok) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) cp_async16_zfill(dst + v * 256, reinterpret_cast<const uint8_t*>(ok ? src : xb) + (ok ? 16 * v : 0), ok ? 16 : 0);
+  };
+  auto issue = [&](int t, int slot) {
+    if (active) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int tt = t + u * rpi;
+        const bool inb = tt < t1;
+        if constexpr (KS == 0) {
+          copy8(slot_ptr(slot, u, 0), da_b + (long long)tt * C, inb);
+        } else if constexpr (KS == 26) {
+          // k = 3, s = 2: an even q = t + left receives taps 0 (window q/2) and 2 (window q/2 - 1), an odd one tap 1 (window (q-1)/2)
+          const int q0 = tt + col.left, e = q0 & 1, w = q0 >> 1;
+          const long long rowlen = 3ll * C;
+          copy8(slot_ptr(slot, u, 0), dcol_b + w * rowlen + e * C, inb && w < col.t_next);
+          copy8(slot_ptr(slot, u, 1), dcol_b + (w - 1) * rowlen + 2 * C, inb && e == 0 && w >= 1 && w - 1 < col.t_next);
+        } else {
+          // k = 2, s = 2: exactly one tap (q & 1) of window q / 2
+          const int q0 = tt + col.left, e = q0 & 1, w = q0 >> 1;
+          copy8(slot_ptr(slot, u, 0), dcol_b + (long long)w * (2 * C) + e * C, inb && w < col.t_next);
+        }
+        copy8(slot_ptr(slot, u, NSRC - 1), xb + (long long)tt * C, inb);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int p0 = 0; p0 < S - 1; ++p0) issue(t0 + tr + p0 * 2 * rpi, p0);
+  for (int i = threadIdx.x; i < 2 * C; i += 256) sg[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * G; i += 256) sacc[i] = 0.0;
+  __syncthreads();
+  float ga[8], be[8], ag[8], ab[8];
+  float rs = 0.f, nmr = 0.f;
+  if (active) {
+    rs = rstd[b * G + g]; nmr = -mean[b * G + g] * rs;
+    load8<float>(gamma + tc * 8, ga);
+    load8<float>(beta + tc * 8, be);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
+  T* dxb = dx + (long long)b * dx_rpb * C + tc * 8;
+  int it = 0;
+  for (int t = t0 + tr; t < t1; t += 2 * rpi, ++it) {
+    issue(t + (S - 1) * 2 * rpi, (it + S - 1) % S);
+    cp_async_wait<S - 1>();
+    const int slot = it % S;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int tt = t + u * rpi;
+      if (tt >= t1) break;
+      float d[8], v[8], o[8];
+      Raw8<T> r;
+      load_raw8_smem(slot_ptr(slot, u, 0), 256, r);
+      unpack8(r, d);
+      if constexpr (KS == 26) {
+        float d2[8];
+        load_raw8_smem(slot_ptr(slot, u, 1), 256, r);
+        unpack8(r, d2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] += d2[i];
+      }
+      load_raw8_smem(slot_ptr(slot, u, NSRC - 1), 256, r);
+      unpack8(r, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xh = fmaf(v[i], rs, nmr);
+        const float dact = d[i] * gelu_grad_t<T>(fmaf(ga[i], xh, be[i]));
+        o[i] = dact;
+        ag[i] = fmaf(dact, xh, ag[i]);
+        ab[i] += dact;
+      }
+      store8<T>(dxb + (long long)tt * C, o);
+    }
+  }
+  cp_async_wait<0>();
+  if (active) {
+    // group sums for pass 2 follow from the per-channel sums: sum(dact*gamma) and sum(dact*gamma*xhat)
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s1 = fmaf(ga[i], ab[i], s1);
+      s2 = fmaf(ga[i], ag[i], s2);
+      atomicAdd(&sg[tc * 8 + i], ag[i]);
+      atomicAdd(&sb[tc * 8 + i], ab[i]);
+    }
+    atomicAdd(&sacc[2 * g], (double)s1);
+    atomicAdd(&sacc[2 * g + 1], (double)s2);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) { atomicAdd(&dgamma[i], sg[i]); atomicAdd(&dbeta[i], sb[i]); }
+  for (int i = threadIdx.x; i < 2 * G; i += 256) atomicAdd(&accum[(long long)b * G * 2 + i], sacc[i]);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256, 4) gn_gelu_bwd2_kernel(const T* __restrict__ x, long long x_rpb,
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -715,6 +844,28 @@ __global__ void __launch_bounds__(256, 4) gn_gelu_bwd2_kernel(const T* __restric
   }
 }
 
+// ring version (cp.async staging) for the specialised tap patterns; TETHYS_GN_BWD_DIRECT=1 keeps the register-staged kernel
+template <typename TT, int KS>
+static int gn_bwd1_launch(Ctx* ctx, dim3 g1, size_t smem, cudaStream_t st, const void* da, long long da_rpb, const Col2imSrc& c, const void* x,
+                          long long x_rpb, const float* mean, const float* rstd, const float* gamma, const float* beta, void* dx,
+                          long long dx_rpb, float* dgamma, float* dbeta, double* accum, int T_, int C, int G, int rows1) {
+  static const bool direct = getenv("TETHYS_GN_BWD_DIRECT") && atoi(getenv("TETHYS_GN_BWD_DIRECT")) != 0;
+  if constexpr (KS == 0 || KS == 26 || KS == 18) {
+    constexpr int NSRC_ = KS == 26 ? 3 : 2, S_ = sizeof(TT) == 2 ? 4 : 2;
+    const size_t rsmem = (size_t)S_ * 2 * NSRC_ * (sizeof(TT) / 2) * 256 * 16 + smem;
+    if (!direct && rsmem <= 200 * 1024) {
+      TS_CUDA_OK(ctx, cudaFuncSetAttribute(gn_gelu_bwd1_ring_kernel<TT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+      ts::launch_k(gn_gelu_bwd1_ring_kernel<TT, KS>, g1, 256, rsmem, st, (const TT*)da, da_rpb, c, (const TT*)x, x_rpb, mean, rstd, gamma, beta,
+                   (TT*)dx, dx_rpb, dgamma, dbeta, accum, T_, C, G, rows1);
+      return 0;
+    }
+  }
+  ts::launch_k(gn_gelu_bwd1_kernel<TT, KS>, g1, 256, smem, st, (const TT*)da, da_rpb, c, (const TT*)x, x_rpb, mean, rstd, gamma, beta, (TT*)dx,
+               dx_rpb, dgamma, dbeta, accum, T_, C, G, rows1);
+  return 0;
+}
+#define TS_TRY_RC(...) do { int _rc = (__VA_ARGS__); if (_rc) return _rc; } while (0)
+
 int groupnorm_gelu_bwd(Ctx* ctx, int dt, const void* da, long long da_rpb, const Col2imSrc* col, const void* x,
                        long long x_rpb, const float* mean, const float* rstd, const float* gamma, const float* beta,
                        void* dx, long long dx_rpb, float* dgamma, float* dbeta, double* accum, int B, int T_, int C, int G,
@@ -729,9 +880,8 @@ int groupnorm_gelu_bwd(Ctx* ctx, int dt, const void* da, long long da_rpb, const
   if (!c.dcol) ks = 0;
   else if (c.k == 3 && c.s == 2) ks = 3 * 8 + 2;
   else if (c.k == 2 && c.s == 2) ks = 2 * 8 + 2;
-#define GN_BWD1(TT, KS)                                                                                                   \
-  ts::launch_k(gn_gelu_bwd1_kernel<TT, KS>, g1, 256, smem, st, (const TT*)da, da_rpb, c, (const TT*)x, x_rpb, mean, rstd, gamma, beta, \
-                                                     (TT*)dx, dx_rpb, dgamma, dbeta, accum, T_, C, G, rows1)
+#define GN_BWD1(TT, KS) TS_TRY_RC(gn_bwd1_launch<TT, KS>(ctx, g1, smem, st, da, da_rpb, c, x, x_rpb, mean, rstd, gamma, beta, dx, dx_rpb, dgamma, dbeta, \
+                                                         accum, T_, C, G, rows1))
   if (dt == TS_F32) {
     if (ks == 0) GN_BWD1(float, 0); else if (ks == 26) GN_BWD1(float, 26); else if (ks == 18) GN_BWD1(float, 18); else GN_BWD1(float, -1);
     if (!skip_pass2) ts::launch_k(gn_gelu_bwd2_kernel<float>, g2, 256, 0, st, (const float*)x, x_rpb, mean, rstd, gamma, (float*)dx, dx_rpb, accum,

@@ -53,6 +53,21 @@ __device__ __forceinline__ void unpack8(const Raw8<bf16>& r, float (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
 }
+// per-thread cp.async staging (LDGSTS): loads in flight hold no registers; a thread that reads back only what it copied itself needs
+// no block barrier, just cp.async.wait_group. The zfill form copies `bytes` (0 or 16) and zero-fills the rest of the 16.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void load_raw8_smem(const uint4* base, int stride, Raw8<float>& r) {
+  const float4* f = reinterpret_cast<const float4*>(base);
+  r.a = f[0]; r.b = f[stride];
+}
+__device__ __forceinline__ void load_raw8_smem(const uint4* base, int stride, Raw8<bf16>& r) { r.u = base[0]; }
 // round values to the storage dtype (no-op for fp32)
 template <typename T> __device__ __forceinline__ void round8(float (&v)[8]);
 template <> __device__ __forceinline__ void round8<float>(float (&v)[8]) {}

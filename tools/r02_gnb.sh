@@ -1,0 +1,11 @@
+cd $GRAFT_REPO_ROOT
+timeout -k 5 600 python -m pytest tests/test_w2v_gpu.py tests/test_norm_ops_gpu.py tests/test_golden_gpu.py tests/test_ref_golden_gpu.py tests/test_w2v_heads_gpu.py -q -m gpu -x > gpurun_out/gnb_pytest.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/gnb_pytest.log | cut -c1-300
+for v in 0 1; do
+TETHYS_GN_BWD_DIRECT=$v timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/gnb${v}.json 2> gpurun_out/gnb${v}.err; echo "bench direct=$v rc=$?"
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/gnb${v}.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step')}, d['e2e']['value'])
+PY
+done
