@@ -303,6 +303,85 @@ __global__ void __launch_bounds__(256) ew_colsum_kernel(const T* __restrict__ a,
   if (blockIdx.x * 256 + c < cols) atomicAdd(&csum[blockIdx.x * 256 + c], t);
 }
 
+// The same pass with its operands streamed through a per-thread cp.async ring (see vec.cuh): (S - 1) stages x 2 rows x (1-2) vectors
+// per thread in flight without holding registers; used for the big GELU-backward pass ([B*T, ffn] = 3 x 37 MB per layer).
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256, 3) ew_colsum_ring_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int rows,
+                                                                int cols, float* __restrict__ csum, int rows_per_block, uint32_t thr,
+                                                                float inv_keep, uint64_t seed, const unsigned long long* __restrict__ salt) {
+  ts::pdl_enter();
+  constexpr int NV = sizeof(T) / 2, NSRC = MODE == 1 ? 2 : 1, VPS = 2 * NSRC * NV, S = 4;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  uint4* stg = reinterpret_cast<uint4*>(smraw);                               // [S][VPS][256]
+  float (*red)[256 + 8] = reinterpret_cast<float (*)[256 + 8]>(stg + S * VPS * 256);   // [8][264]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  if (thr) seed = salted_seed(seed, salt);
+  const DropKey key = flat_drop_key(seed, thr);
+  const bool active = col < cols;
+  auto slot_ptr = [&](int slot, int u, int src) { return stg + ((slot * VPS) + (u * NSRC + src) * NV) * 256 + threadIdx.x; };
+  auto issue = [&](int r, int slot) {
+    if (active) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int rr = r + 8 * u;
+        const bool ok = rr < r1;
+        const long long e = ok ? (long long)rr * cols + col : (long long)col;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          cp_async16_zfill(slot_ptr(slot, u, 0) + v * 256, reinterpret_cast<const uint8_t*>(a + e) + 16 * v, ok ? 16 : 0);
+          if (MODE == 1) cp_async16_zfill(slot_ptr(slot, u, 1) + v * 256, reinterpret_cast<const uint8_t*>(b + e) + 16 * v, ok ? 16 : 0);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int p0 = 0; p0 < S - 1; ++p0) issue(r0 + w + 16 * p0, p0);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  int it = 0;
+  for (int r = r0 + w; r < r1; r += 16, ++it) {
+    issue(r + 16 * (S - 1), (it + S - 1) % S);
+    cp_async_wait<S - 1>();
+    if (!active) continue;
+    const int slot = it % S;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int rr = r + 8 * u;
+      if (rr >= r1) break;
+      const long long e = (long long)rr * cols + col;
+      float va[8], vb[8], o[8], ds[8];
+      Raw8<T> raw;
+      load_raw8_smem(slot_ptr(slot, u, 0), 256, raw);
+      unpack8(raw, va);
+      if (MODE == 1) { load_raw8_smem(slot_ptr(slot, u, 1), 256, raw); unpack8(raw, vb); }
+      if (thr) dropout_scale8(key, (uint64_t)e, inv_keep, ds);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = MODE == 1 ? va[i] * gelu_grad_t<T>(vb[i]) : va[i];
+        if (thr) v *= ds[i];
+        o[i] = v;
+      }
+      store8<T>(out + e, o);
+      round8<T>(o);                       // the sum of what the weight-gradient GEMM will read
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += o[i];
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[w][lane * 8 + i] = acc[i];
+  __syncthreads();
+  const int c = threadIdx.x;
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += red[i][c];
+  if (blockIdx.x * 256 + c < cols) atomicAdd(&csum[blockIdx.x * 256 + c], t);
+}
+
 template <int MODE>
 static int ew_colsum_launch(Ctx* ctx, int dt, const void* a, const void* b, void* out, int rows, int cols, float* csum, float drop,
                             uint64_t seed, cudaStream_t st) {
@@ -315,6 +394,14 @@ static int ew_colsum_launch(Ctx* ctx, int dt, const void* a, const void* b, void
   int rpb = cdiv(rows, rb);
   rpb = ((rpb + 15) / 16) * 16;
   dim3 grid(cb, cdiv(rows, rpb));
+  static const bool direct = getenv("TETHYS_EW_DIRECT") && atoi(getenv("TETHYS_EW_DIRECT")) != 0;
+  if (dt == TS_BF16 && MODE == 1 && !direct && (long long)rows * cols >= (1ll << 22)) {   // big passes: cp.async ring
+    const size_t smem = (size_t)4 * (2 * 2) * 256 * 16 + sizeof(float) * 8 * (256 + 8);
+    TS_CUDA_OK(ctx, cudaFuncSetAttribute(ew_colsum_ring_kernel<bf16, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ts::launch_k(ew_colsum_ring_kernel<bf16, MODE>, grid, 256, smem, st, (const bf16*)a, (const bf16*)b, (bf16*)out, rows, cols, csum, rpb, thr, ik, seed, ctx->d_state);
+    TS_LAUNCH_OK(ctx);
+    return 0;
+  }
   if (dt == TS_F32) ts::launch_k(ew_colsum_kernel<float, MODE>, grid, 256, 0, st, (const float*)a, (const float*)b, (float*)out, rows, cols, csum, rpb, thr, ik, seed, ctx->d_state);
   else if (dt == TS_BF16) ts::launch_k(ew_colsum_kernel<bf16, MODE>, grid, 256, 0, st, (const bf16*)a, (const bf16*)b, (bf16*)out, rows, cols, csum, rpb, thr, ik, seed, ctx->d_state);
   else return set_err(ctx, TS_EDTYPE, "ew_colsum: dtype %d", dt);
