@@ -275,6 +275,145 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_fused_kernel(const T* __restric
   }
 }
 
+// The same one-pass backward with x / dy / dres streamed through a per-thread cp.async ring (bf16 tensors): S - 1 rows per warp are in
+// flight in shared memory while the current one is reduced, instead of one row's loads held in registers (the [6000, 768] passes ran at
+// ~2 TB/s, latency-bound). In-place use (dx aliasing dy or dres) stays valid: a row is read and written by the same thread, the read
+// of row r is complete (wait_group) before its store, and rows are distinct across warps. The ring's memory is reused for the column
+// reduction after the loop.
+template <int NCH, bool DROP>
+__global__ void __launch_bounds__(256, 2) ln_bwd_ring_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                             const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ dgamma,
+                                                             float* __restrict__ dbeta, bf16* __restrict__ drop_out, float* __restrict__ drop_csum,
+                                                             uint32_t thr, float inv_keep, uint64_t seed, const unsigned long long* __restrict__ salt,
+                                                             int rows, int cols) {
+  ts::pdl_enter();
+  constexpr int S = 3, VPS = 3 * NCH;                     // per stage: x, dy, dres chunks of one row
+  extern __shared__ __align__(16) uint8_t smraw[];
+  uint4* stg = reinterpret_cast<uint4*>(smraw);           // [S][VPS][256]
+  float (*red)[256 + 8] = reinterpret_cast<float (*)[256 + 8]>(smraw);   // [8][264] after the loop
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float ag[NCH][8], ab[NCH][8], ac[NCH][8];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ag[ch][i] = 0.f; ab[ch][i] = 0.f; ac[ch][i] = 0.f; }
+  }
+  DropKey key = flat_drop_key(0, 0);
+  if (DROP) key = flat_drop_key(salted_seed(seed, salt), thr);
+  const int stride = 8 * gridDim.x;
+  auto slot_ptr = [&](int slot, int src, int ch) { return stg + ((slot * VPS) + src * NCH + ch) * 256 + threadIdx.x; };
+  auto issue = [&](int row, int slot) {
+    const bool rok = row < rows;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int col = ch * 256 + lane * 8;
+      const bool ok = rok && col < cols;
+      const long long e = ok ? (long long)row * cols + col : 0;
+      cp_async16_zfill(slot_ptr(slot, 0, ch), x + e, ok ? 16 : 0);
+      cp_async16_zfill(slot_ptr(slot, 1, ch), dy + e, ok ? 16 : 0);
+      if (dres) cp_async16_zfill(slot_ptr(slot, 2, ch), dres + e, ok ? 16 : 0);
+    }
+    cp_async_commit();
+  };
+  const int row0 = blockIdx.x * 8 + warp;
+#pragma unroll
+  for (int p0 = 0; p0 < S - 1; ++p0) issue(row0 + p0 * stride, p0);
+  int it = 0;
+  for (int row = row0; row < rows; row += stride, ++it) {
+    issue(row + (S - 1) * stride, (it + S - 1) % S);
+    cp_async_wait<S - 1>();
+    const int slot = it % S;
+    const float mu = mean[row], rs = rstd[row];
+    float xh[NCH][8], d[NCH][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int col = ch * 256 + lane * 8;
+      if (col < cols) {
+        float g[8];
+        Raw8<bf16> r;
+        r.u = *slot_ptr(slot, 0, ch); unpack8(r, xh[ch]);
+        r.u = *slot_ptr(slot, 1, ch); unpack8(r, d[ch]);
+        load8<float>(gamma + col, g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xh[ch][i] = (xh[ch][i] - mu) * rs;
+          ag[ch][i] = fmaf(d[ch][i], xh[ch][i], ag[ch][i]);
+          ab[ch][i] += d[ch][i];
+          d[ch][i] *= g[i];
+          s1 += d[ch][i];
+          s2 += d[ch][i] * xh[ch][i];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / cols;
+    s2 = warp_sum(s2) / cols;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int col = ch * 256 + lane * 8;
+      if (col < cols) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = rs * (d[ch][i] - s1 - xh[ch][i] * s2);
+        if (dres) {
+          float r8[8];
+          Raw8<bf16> r;
+          r.u = *slot_ptr(slot, 2, ch); unpack8(r, r8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += r8[i];
+        }
+        store8<bf16>(dx + (long long)row * cols + col, o);
+        if (DROP) {
+          round8<bf16>(o);
+          float ds[8];
+          dropout_scale8(key, (uint64_t)((long long)row * cols + col), inv_keep, ds);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] *= ds[i];
+          store8<bf16>(drop_out + (long long)row * cols + col, o);
+          round8<bf16>(o);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ac[ch][i] += o[i];
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  auto reduce_to = [&](float (&acc)[NCH][8], float* out) {
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[ch][i];
+      __syncthreads();
+      const int c = threadIdx.x;
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[i][c];
+      if (ch * 256 + c < cols) atomicAdd(&out[ch * 256 + c], t);
+    }
+  };
+  reduce_to(ag, dgamma);
+  reduce_to(ab, dbeta);
+  if (DROP) {
+    if (drop_csum) reduce_to(ac, drop_csum);
+  }
+}
+
+template <int N, bool DROP>
+static int ln_bwd_ring_launch(Ctx* ctx, int grid, cudaStream_t st, const void* dy, const void* x, const float* gamma, const float* mean,
+                              const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta, void* drop_out, float* drop_csum,
+                              uint32_t thr, float ik, uint64_t seed, int rows, int cols) {
+  size_t smem = (size_t)3 * 3 * N * 256 * 16;
+  const size_t red = sizeof(float) * 8 * (256 + 8);
+  if (smem < red) smem = red;
+  TS_CUDA_OK(ctx, cudaFuncSetAttribute(ln_bwd_ring_kernel<N, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ts::launch_k(ln_bwd_ring_kernel<N, DROP>, grid, 256, smem, st, (const bf16*)dy, (const bf16*)x, gamma, mean, rstd, (const bf16*)dres, (bf16*)dx,
+               dgamma, dbeta, (bf16*)drop_out, drop_csum, thr, ik, seed, ctx->d_state, rows, cols);
+  TS_LAUNCH_OK(ctx);
+  return 0;
+}
+
 template <typename T>
 static int ln_fwd_t(Ctx* ctx, const void* x, const void* res, const float* gamma, const float* beta, void* y,
                     void* sum_out, float* mean, float* rstd, int rows, int cols, float eps, cudaStream_t st) {
@@ -315,6 +454,18 @@ static int ln_bwd_t(Ctx* ctx, const void* dy, const void* x, const float* gamma,
     double t = (double)drop * 4294967296.0;
     thr = (uint32_t)(t > 4294967295.0 ? 4294967295.0 : t);
     ik = 1.f / (1.f - drop);
+  }
+  // bf16 tensors of a few thousand rows: the cp.async ring version (TETHYS_LN_BWD_DIRECT=1 keeps the register-staged kernel)
+  static const bool direct = getenv("TETHYS_LN_BWD_DIRECT") && atoi(getenv("TETHYS_LN_BWD_DIRECT")) != 0;
+  if (sizeof(T) == 2 && !direct && nch <= 3 && rows >= 1024) {
+#define LN_RING_CASE(N)                                                                                                                    \
+  case N:                                                                                                                                  \
+    return drop_out ? ln_bwd_ring_launch<N, true>(ctx, grid, st, dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, drop_out, drop_csum, thr, \
+                                                  ik, drop_seed, rows, cols)                                                               \
+                    : ln_bwd_ring_launch<N, false>(ctx, grid, st, dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, nullptr, nullptr, 0u, \
+                                                   1.f, 0ull, rows, cols);
+    switch (nch) { LN_RING_CASE(1) LN_RING_CASE(2) LN_RING_CASE(3) }
+#undef LN_RING_CASE
   }
 #define LN_BWD_CASE(N)                                                                                                               \
   case N:                                                                                                                            \
