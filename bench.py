@@ -355,7 +355,7 @@ def kernel_rooflines(ctx, peaks, B, T, H, F, nh, n_params):
     t = _timed(lambda: ctx.check(ctx.lib.ts_attn_bwd(ctx.h, C.byref(a), stream_ptr())), flush)
     out.append({"kernel": "attn_bwd_prep + attn_bwd2_kernel (fused dQ/dK/dV) + dq_store (same shape; 2x forward FLOPs counted, recompute not)", "bound": "tensor",
                 "achieved": 2 * fl / t / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": 2 * fl / t / 1e12 / peaks["bf16_tflops"],
-                "us": t * 1e6, "traffic": None})
+                "us": t * 1e6, "traffic": ncu_traffic("attn_bwd")})
 
     def hbm(name, nbytes, fn, key=None):
         t = _timed(fn, flush)
