@@ -107,7 +107,7 @@ typedef struct {
   int64_t ldr, r_bs1, r_bs2;
   int32_t accumulate; /* 1: C += result (only with out_dtype TS_F32, no act/residual) */
   void* c_preact;     /* optional second output: value before act (same dtype/ld as C) or NULL */
-  int32_t force_engine; /* 0 auto, 1 force CUDA-core engine, 2 force tcgen05 (error if impossible), 3 force tcgen05 CTA-pair (cta_group::2) tiles */
+  int32_t force_engine; /* 0 auto, 1 force CUDA-core engine, 2 force tcgen05 (error if impossible), 3 force tcgen05 CTA-pair (cta_group::2) tiles, 4 force the 4-CTA cluster form (two pairs, B operand TMA-multicast) */
   float drop;           /* dropout rate applied after act (0 = off); keep-mask = hash(seed, element offset in C) */
   uint64_t seed;
   int64_t bias_bs1;     /* bias element stride per batch1 index (grouped conv: one bias slice per group) */

@@ -111,7 +111,7 @@ def test_misaligned_operands_fall_to_cuda_core_engine_not_cpu():
     assert _rel(c, a.float() @ b.float()) < 1e-2
 
 
-@pytest.mark.parametrize("force", [2, 3])   # 1-CTA tiles / CTA-pair tiles
+@pytest.mark.parametrize("force", [2, 3, 4])   # 1-CTA tiles / CTA-pair tiles / 4-CTA cluster (two pairs, B multicast)
 def test_groupnorm_statistics_in_the_epilogue(force):
     """ts_gemm_desc.gn_accum: the conv GEMM takes the GroupNormalization moments (V:167-176, over time x channels of a group, per
     batch element) of its own output, skipping the window-slack rows behind every batch block; warps that straddle a batch
@@ -147,3 +147,36 @@ def test_groupnorm_statistics_in_the_epilogue(force):
     d.act = 1
     with pytest.raises(_lib.TethysError):
         ctx.check(ctx.lib.ts_gemm(ctx.h, C.byref(d), stream_ptr()))
+
+
+@pytest.mark.parametrize("amaj,bmaj", [(0, 0), (0, 1), (1, 1)])
+def test_four_cta_multicast_engine(amaj, bmaj):
+    """force_engine = 4: a cluster of two CTA pairs on vertically adjacent 256-row tiles; each CTA fetches a quarter of the B operand
+    and TMA-multicasts it to its counterpart in the other pair. Ragged m (clipped last cluster tile), several tiles per cluster,
+    K-major and MN-major operands, bias + residual epilogue, against fp32 torch on the same bf16 inputs."""
+    from tethys_speech_b200 import _lib
+    from tethys_speech_b200.runtime import stream_ptr
+
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(21 + amaj * 2 + bmaj)
+    m, n, k = 2900, 768, 448
+    a = torch.randn((m, k) if amaj == 0 else (k, m), generator=g).bfloat16().to(dev)
+    b = (torch.randn((n, k) if bmaj == 0 else (k, n), generator=g) * 0.1).bfloat16().to(dev)
+    bias = torch.randn(n, generator=g).to(dev)
+    res = torch.randn(m, n, generator=g).bfloat16().to(dev)
+    y = torch.empty(m, n, dtype=torch.bfloat16, device=dev)
+    ctx = _lib.context(0)
+    d = _lib.GemmDesc()
+    d.a, d.b, d.c = a.data_ptr(), b.data_ptr(), y.data_ptr()
+    d.m, d.n, d.k, d.a_major, d.b_major = m, n, k, amaj, bmaj
+    d.lda, d.ldb, d.ldc = a.shape[1], b.shape[1], n
+    d.batch1 = d.batch2 = 1
+    d.in_dtype = d.out_dtype = _lib.TS_BF16
+    d.alpha, d.force_engine = 1.0, 4
+    d.bias, d.residual, d.ldr = bias.data_ptr(), res.data_ptr(), n
+    ctx.check(ctx.lib.ts_gemm(ctx.h, C.byref(d), stream_ptr()))
+    torch.cuda.synchronize()
+    ctx.watchdog()
+    af = a.float() if amaj == 0 else a.float().t()
+    bf = b.float().t() if bmaj == 0 else b.float()
+    assert _rel(y, af @ bf + bias + res.float()) < 1e-2

@@ -32,7 +32,7 @@ int gemm(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
   if (d->gn_accum && (d->force_engine == 1 || d->in_dtype != TS_BF16 || !gemm_tc_supported(d)))
     return set_err(ctx, TS_EUNSUPPORTED, "gemm: epilogue GroupNorm statistics (gn_accum) exist on the tcgen05 engine only");
   if (d->force_engine == 1) return gemm_simt(ctx, d, st);
-  if (d->force_engine == 2 || d->force_engine == 3) return gemm_tc(ctx, d, st);
+  if (d->force_engine >= 2 && d->force_engine <= 4) return gemm_tc(ctx, d, st);
   if (d->in_dtype == TS_BF16 && gemm_tc_supported(d)) return gemm_tc(ctx, d, st);
   if (d->in_dtype == TS_BF16) {
     // a bf16 GEMM that TMA cannot describe (unaligned leading dimension / pointer) runs on the CUDA-core engine: correct but

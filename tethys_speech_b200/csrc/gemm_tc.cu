@@ -67,7 +67,7 @@ constexpr int kStageBytesPerWarp = 4096;     // one 32-row x 128-byte swizzled b
 // CTAs' smem and write both CTAs' TMEM, so per FLOP each SM reads half as much B from smem / L2.
 template <int BN, int CTAS> struct TcCfg {
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = (BN / CTAS) * BK * 2;
+  static constexpr int kBBytes = (BN / (CTAS == 1 ? 1 : 2)) * BK * 2;   // a CTA of a pair holds half of the tile's B columns
   static constexpr int kStages = (196608 / (kABytes + kBBytes)) > 8 ? 8 : (196608 / (kABytes + kBBytes));
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSmem = kStages * kStageBytes + kEpiWarps * kStageBytesPerWarp + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -203,11 +203,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_p,
                const EpiParams p, int* watchdog) {
   using Cfg = TcCfg<BN, CTAS>;
-  static_assert(CTAS == 1 || (CTAS == 2 && BN >= 128), "a CTA pair needs >= 64 B rows per CTA");
-  // CTA pair: rank 0 (leader) issues the MMAs; tiles are walked per cluster
-  const uint32_t rank = (CTAS == 2) ? ptx::cluster_ctarank() : 0u;
-  const int tile_first = (CTAS == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int tile_step = (CTAS == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  static_assert(CTAS == 1 || (CTAS == 2 && BN >= 128) || (CTAS == 4 && BN == 256), "a CTA pair needs >= 64 B rows per CTA; the 4-CTA form 256 columns");
+  // CTAS = 2: a CTA pair; the even rank (leader) issues the MMAs; tiles are walked per cluster.
+  // CTAS = 4: a cluster of TWO pairs on vertically adjacent 256-row tiles of the same column block: the B operand is the same for both
+  // pairs, so every CTA fetches only a quarter of it (64 rows) and TMA-multicasts it to its counterpart in the other pair — per SM and
+  // k-block 16 KB of A + 8 KB of B come out of L2 instead of 16 + 16 (operand delivery is what bounds these main loops, gemm_tc()).
+  constexpr bool PAIR = CTAS >= 2, MC = CTAS == 4;
+  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;   // 0 .. CTAS-1
+  const uint32_t rp = rank & 1u;                               // rank inside the pair
+  const uint32_t pr = rank >> 1;                               // pair inside the cluster
+  const uint32_t lead = rank & ~1u;                            // cluster rank of this pair's leader
+  const int tile_first = PAIR ? (int)(blockIdx.x / CTAS) : (int)blockIdx.x;
+  const int tile_step = PAIR ? (int)(gridDim.x / CTAS) : (int)gridDim.x;
   constexpr int BMT = BM * CTAS;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -229,24 +236,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     ptx::prefetch_tmap(&tma_b);
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], MC ? 2 : 1);   // 4-CTA form: a slot is free when BOTH pairs' MMAs have retired (each multicasts into it)
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full_bar[s], 1);
-      ptx::mbar_init(&tmem_empty_bar[s], kEpiWarps * CTAS);   // pair: the leader's barrier collects both CTAs' epilogue warps
+      ptx::mbar_init(&tmem_empty_bar[s], kEpiWarps * (PAIR ? 2 : 1));   // pair: the leader's barrier collects both CTAs' epilogue warps
     }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    if (CTAS == 2) { ptx::tmem_alloc_2cta(tmem_slot, Cfg::kTmemCols); ptx::tmem_relinquish_2cta(); }
+    if (PAIR) { ptx::tmem_alloc_2cta(tmem_slot, Cfg::kTmemCols); ptx::tmem_relinquish_2cta(); }
     else { ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
   // The producer warp of a (leader) CTA needs nothing but the barriers its own lane 0 has just initialised: it only ARRIVES at the
   // setup barrier and starts the first TMA loads while warp 1 is still allocating TMEM (the head of a launch is not overlapped
   // by anything else). Everyone else waits; a peer CTA's producer signals the LEADER's barriers and so must wait for the cluster.
-  const bool early = (warp == 0 && rank == 0);
-  if (CTAS == 2) {
+  // (4-CTA form: every producer multicasts into, and signals barriers of, other CTAs: all of them wait for the cluster.)
+  const bool early = (warp == 0 && rank == 0 && !MC);
+  if (PAIR) {
     ptx::cluster_arrive();
     if (!early) ptx::cluster_wait();
   } else {
@@ -265,17 +273,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       bool ok = true;
       for (int t = tile_first; t < p.total_tiles && ok; t += tile_step) {
         const TileCoord tc = decode_tile(p, t, BN, BMT);
-        const int m0 = tc.m0 + (int)rank * BM, n0 = tc.n0 + (int)rank * (BN / CTAS);   // this CTA's rows of A and of B
+        // this CTA's rows of A, and the rows of B it fetches: its half of the tile's columns (pair), or the quarter it multicasts (4-CTA)
+        const int m0 = tc.m0 + (int)rank * BM, n0 = tc.n0 + (int)rp * (BN / 2) + (MC ? (int)pr * (BN / 4) : 0);
         for (int kb = tc.kb0; kb < tc.kb1; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           if (!ptx::mbar_wait(&empty_bar[s], ph ^ 1, watchdog, 1)) { ok = false; break; }
           // pair: all bytes of the stage (both CTAs' loads) are counted on the LEADER's barrier
-          const uint32_t fb = (CTAS == 2) ? ptx::mapa_u32(ptx::smem_u32(&full_bar[s]), 0) : 0u;
-          if (rank == 0) ptx::mbar_expect_tx(&full_bar[s], Cfg::kStageBytes * CTAS);
+          const uint32_t fb = PAIR ? ptx::mapa_u32(ptx::smem_u32(&full_bar[s]), lead) : 0u;
+          if (rp == 0) ptx::mbar_expect_tx(&full_bar[s], Cfg::kStageBytes * (PAIR ? 2 : 1));   // what lands in this pair's two CTAs
           auto load = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
-            if (CTAS == 2) ptx::tma_load_4d_2cta(dst, tm, fb, c0, c1, c2, c3);
+            if (PAIR) ptx::tma_load_4d_2cta(dst, tm, fb, c0, c1, c2, c3);
             else ptx::tma_load_4d(dst, tm, &full_bar[s], c0, c1, c2, c3);
+          };
+          // 4-CTA form: the same smem offset in this CTA and in its counterpart (same rank-in-pair) of the other pair; the
+          // transaction bytes are counted on each destination pair's leader barrier (cta_group::2 barrier addressing)
+          const uint16_t mc_mask = (uint16_t)((1u << rp) | (1u << (2 + rp)));
+          auto load_mc = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+            ptx::tma_load_4d_2cta_mc(dst, tm, fb, c0, c1, c2, c3, mc_mask);
           };
           const uint32_t sa = ptx::smem_u32(smem + s * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
@@ -286,25 +301,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             for (int c = 0; c < BM / 64; ++c)
               load(sa + c * 8192, &tma_a, m0 + c * 64, kb * BK, tc.b1 * p.a_m1, tc.b2 * p.a_m2);
           }
-          if (BMAJ == 0) {
+          if (MC) {   // 64 rows (K-major box) / one 64-wide chunk (MN-major) of B: 8 KB at offset pr * 8 KB of the B half
+            if (BMAJ == 0) load_mc(sb + pr * 8192, &tma_b, kb * BK, n0, tc.b1 * p.b_m1, tc.b2 * p.b_m2);
+            else load_mc(sb + pr * 8192, &tma_b, n0, kb * BK, tc.b1 * p.b_m1, tc.b2 * p.b_m2);
+          } else if (BMAJ == 0) {
             load(sb, &tma_b, kb * BK, n0, tc.b1 * p.b_m1, tc.b2 * p.b_m2);
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / CTAS / 64; ++c)
+            for (int c = 0; c < BN / (PAIR ? 2 : 1) / 64; ++c)
               load(sb + c * 8192, &tma_b, n0 + c * 64, kb * BK, tc.b1 * p.b_m1, tc.b2 * p.b_m2);
           }
         }
       }
     }
-    if (CTAS == 2 && rank == 0) { __syncwarp(); ptx::cluster_wait(); }   // second half of the setup barrier (completed long ago)
+    if (CTAS == 2 && rank == 0) { __syncwarp(); ptx::cluster_wait(); }   // second half of the setup barrier (completed long ago); early producer only
     __syncwarp();
     ts::pdl_tail();   // every operand load of this CTA is in flight: let the next grid's CTAs take the SMs as they free up
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
-    if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(BMT, BN, AMAJ, BMAJ);
-      auto commit = [&](uint64_t* bar) {
-        if (CTAS == 2) ptx::umma_commit_2cta(bar, (uint16_t)3);   // same barrier offset in both CTAs
+    if (lane == 0 && rp == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(PAIR ? 2 * BM : BM, BN, AMAJ, BMAJ);
+      const uint16_t pair_mask = (uint16_t)(3u << lead);
+      auto commit = [&](uint64_t* bar) {          // accumulator ready: both CTAs of this pair
+        if (PAIR) ptx::umma_commit_2cta(bar, pair_mask);
+        else ptx::umma_commit(bar);
+      };
+      auto commit_slot = [&](uint64_t* bar) {     // operand slot free: every CTA that writes into it (4-CTA form: the whole cluster)
+        if (PAIR) ptx::umma_commit_2cta(bar, MC ? (uint16_t)0xF : pair_mask);
         else ptx::umma_commit(bar);
       };
       uint32_t it = 0, tl = 0;
@@ -329,10 +352,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                                : ptx::make_smem_desc(sa + kk * 2048, 8192, 1024);
             const uint64_t bdesc = (BMAJ == 0) ? ptx::make_smem_desc(sb + kk * 32, 16, 1024)
                                                : ptx::make_smem_desc(sb + kk * 2048, 8192, 1024);
-            if (CTAS == 2) ptx::umma_f16_2cta(d_tmem, adesc, bdesc, idesc, (kb > tc.kb0 || kk > 0) ? 1u : 0u);
+            if (PAIR) ptx::umma_f16_2cta(d_tmem, adesc, bdesc, idesc, (kb > tc.kb0 || kk > 0) ? 1u : 0u);
             else ptx::umma_f16(d_tmem, adesc, bdesc, idesc, (kb > tc.kb0 || kk > 0) ? 1u : 0u);
           }
-          commit(&empty_bar[s]);  // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          commit_slot(&empty_bar[s]);  // frees the smem slot (in both CTAs of a pair / all four of the cluster) when these MMAs retire
         }
         if (ok) commit(&tmem_full_bar[as]);  // accumulator of this tile complete
         if (tl == 0) trace_stamp(p, 3);      // first tile's MMAs issued
@@ -368,7 +391,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (CTAS == 2) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&tmem_empty_bar[as]), 0));
+            if (PAIR) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&tmem_empty_bar[as]), lead));
             else ptx::mbar_arrive(&tmem_empty_bar[as]);
           }
           released = true;
@@ -530,10 +553,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (ew == 0 && lane == 0) trace_stamp(p, 7);   // this warp's stores have drained
   }
   ptx::tc_fence_before();
-  if (CTAS == 2) ptx::cluster_sync_all();   // the leader's MMAs read the peer's smem / write its TMEM until the last commit
+  if (PAIR) ptx::cluster_sync_all();   // the leader's MMAs read the peer's smem / write its TMEM until the last commit
   else __syncthreads();
   if (warp == 1) {
-    if (CTAS == 2) ptx::tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
+    if (PAIR) ptx::tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
     else ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
@@ -646,14 +669,25 @@ static int launch_tc(Ctx* ctx, const ts_gemm_desc* d, const CUtensorMap& ta, con
     const int grid = ep.total_tiles < ctx->num_sms ? ep.total_tiles : ctx->num_sms;
     ts::launch_k(kern, grid, kThreads, Cfg::kSmem, st, ta, tb, tc, tp, ep, ctx->d_watchdog);
   } else {
-    // one cluster of two CTAs (one TPC) per 256-row tile stream
-    const int pairs = ctx->num_sms / 2;
-    const int grid = 2 * (ep.total_tiles < pairs ? ep.total_tiles : pairs);
+    // one cluster of two CTAs (one TPC) per 256-row tile stream, or of four (two TPCs of one GPC) per 512-row stream
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid, 1, 1); cfg.blockDim = dim3(kThreads, 1, 1); cfg.dynamicSmemBytes = Cfg::kSmem; cfg.stream = st;
+    cfg.blockDim = dim3(kThreads, 1, 1); cfg.dynamicSmemBytes = Cfg::kSmem; cfg.stream = st;
     cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.x = CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    int units = ctx->num_sms / CTAS;
+    if (CTAS == 4) {   // clusters of four do not tile every GPC: size the persistent grid to what is co-resident
+      static int max_clusters = 0;
+      if (!max_clusters) {
+        cfg.gridDim = dim3(CTAS * units, 1, 1); cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = units * 3 / 4; }
+        max_clusters = n;
+      }
+      if (units > max_clusters) units = max_clusters;
+    }
+    const int grid = CTAS * (ep.total_tiles < units ? ep.total_tiles : units);
+    cfg.gridDim = dim3(grid, 1, 1);
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
@@ -694,7 +728,7 @@ int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
   const int nkb = cdiv(d->k, BK), sms = ctx->num_sms;
   const bool split_ok = d->out_dtype == TS_F32 && d->accumulate && !d->bias && !d->c_preact && d->drop <= 0.f && nkb >= 16;
   static const int force_ctas = getenv("TETHYS_GEMM_CTAS") ? atoi(getenv("TETHYS_GEMM_CTAS")) : 0;
-  const int want_ctas = d->force_engine == 3 ? 2 : force_ctas;
+  const int want_ctas = d->force_engine == 3 ? 2 : d->force_engine == 4 ? 4 : force_ctas;
   int bn = 64, splitk = 1, ctas = 1;
   {
     // Cost model in SM cycles, fitted to tools/selftest_gemm timings (profiles/r02e_gemm_tile_sweep.log). What bounds a main loop
@@ -707,12 +741,13 @@ int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
     double best = 1e30;
     const int cand[3] = {256, 128, 64};
     static const int force_bn = getenv("TETHYS_GEMM_BN") ? atoi(getenv("TETHYS_GEMM_BN")) : 0;
-    for (int cs = 1; cs <= 2; ++cs) {
+    for (int cs = 1; cs <= 4; cs *= 2) {
       if (want_ctas && cs != want_ctas) continue;
-      if (cs == 2 && d->m <= BM) continue;
+      if (cs == 4 && want_ctas != 4) continue;          // 4-CTA multicast form: opt-in (TETHYS_GEMM_CTAS=4 / force_engine 4)
+      if (cs >= 2 && d->m <= BM * (cs / 2)) continue;
       const int units = sms / cs;                     // CTAs or CTA pairs
       const int mtc = cdiv(d->m, BM * cs);
-      for (int i = 0; i < (cs == 2 ? (want_ctas ? 2 : 1) : 3); ++i) {   // pair tiles: 256 wide (128 only when forced: measured slower)
+      for (int i = 0; i < (cs == 4 ? 1 : cs == 2 ? (want_ctas ? 2 : 1) : 3); ++i) {   // pair tiles: 256 wide (128 only when forced: measured slower)
         if (cand[i] > 64 && d->n <= cand[i] / 2) continue;
         if (force_bn && cand[i] != force_bn) continue;
         const long long tiles = (long long)mtc * cdiv(d->n, cand[i]) * nb1 * nb2;
@@ -726,9 +761,9 @@ int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
         const int kb = cdiv(nkb, sk);
         sk = cdiv(nkb, kb);
         const double waves = (double)((tiles * sk + units - 1) / units);
-        const double kbc = fmax(2.0 * cand[i], (16384.0 + (double)cand[i] / cs * 128.0) / 42.6);
+        const double kbc = fmax(2.0 * cand[i], (16384.0 + (double)cand[i] / cs * 128.0) / 42.6);   // cs 4: a quarter of B per SM
         const double tail = 24.0 * cand[i] * (d->out_dtype == TS_F32 ? 1.5 : 1.0);
-        const double score = waves * kb * kbc + (waves - 1.0) * 1500.0 + tail + (cs == 2 ? 9000.0 : 0.0);
+        const double score = waves * kb * kbc + (waves - 1.0) * 1500.0 + tail + (cs >= 2 ? 9000.0 : 0.0);
         if (score < best) { best = score; bn = cand[i]; splitk = sk; ctas = cs; }
       }
     }
@@ -808,6 +843,7 @@ int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
   ts_gemm_desc dd = *d;
   dd.batch1 = nb1; dd.batch2 = nb2;
   if (d->out_dtype == TS_BF16) {
+    if (ctas == 4) return dispatch_major<256, bf16, 4>(ctx, &dd, ta, tb, tc, tp, ep, st);
     if (ctas == 2) {
       if (bn == 128) return dispatch_major<128, bf16, 2>(ctx, &dd, ta, tb, tc, tp, ep, st);
       return dispatch_major<256, bf16, 2>(ctx, &dd, ta, tb, tc, tp, ep, st);
@@ -816,6 +852,7 @@ int gemm_tc(Ctx* ctx, const ts_gemm_desc* d, cudaStream_t st) {
     if (bn == 128) return dispatch_major<128, bf16, 1>(ctx, &dd, ta, tb, tc, tp, ep, st);
     return dispatch_major<256, bf16, 1>(ctx, &dd, ta, tb, tc, tp, ep, st);
   } else {
+    if (ctas == 4) return dispatch_major<256, float, 4>(ctx, &dd, ta, tb, tc, tp, ep, st);
     if (ctas == 2) {
       if (bn == 128) return dispatch_major<128, float, 2>(ctx, &dd, ta, tb, tc, tp, ep, st);
       return dispatch_major<256, float, 2>(ctx, &dd, ta, tb, tc, tp, ep, st);

@@ -261,6 +261,17 @@ __device__ __forceinline__ void tma_load_4d_2cta(uint32_t smem_dst, const void* 
       ::"r"(smem_dst), "l"((uint64_t)tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// The same, multicast: the box lands at the same smem offset in every CTA of `cta_mask`; with cta_group::2 the transaction bytes of
+// each destination are counted on the mbarrier at `bar_cluster_addr`'s offset in that destination's pair (the pair's leader when
+// the address names the issuer's leader).
+__device__ __forceinline__ void tma_load_4d_2cta_mc(uint32_t smem_dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1,
+                                                    int c2, int c3, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(smem_dst), "l"((uint64_t)tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_slot, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
                : "memory");

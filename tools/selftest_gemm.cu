@@ -215,6 +215,18 @@ int main(int argc, char** argv) {
     };
     for (auto& c : more) fails += run_case(ctx, c, 3, false) != 0;
   }
+  if (getenv("TETHYS_SELFTEST_MC")) {
+    printf("== correctness: 4-CTA cluster engine (4: two CTA pairs, B multicast) ==\n");
+    for (auto& c : cases)
+      if (c.m > 256 && c.n > 128) fails += run_case(ctx, c, 4, false) != 0;
+    std::vector<Case> more = {
+        {"mc_kk_rag_m", 6000 / 4, 768, 320, 0, 0, 1, 1, 0, 0, 0, 1, 0, 1, 0, 0, 1.f},
+        {"mc_kn_rag_m", 700, 3072 / 4, 256, 0, 1, 1, 1, 0, 0, 0, 1, 1, 0, 0, 1, 1.f},
+        {"mc_nn_splitk", 768, 512, 6000, 1, 1, 1, 1, 0, 0, 1, 0, 0, 0, 1, 0, 1.f},
+        {"mc_nk_batched", 600, 256, 192, 1, 0, 3, 2, 0, 0, 1, 0, 0, 0, 0, 0, 1.f},
+    };
+    for (auto& c : more) fails += run_case(ctx, c, 4, false) != 0;
+  }
   printf("== correctness: CUDA-core engine (1) ==\n");
   for (size_t i = 0; i < cases.size(); i += 3) fails += run_case(ctx, cases[i], 1, false) != 0;
   }
@@ -248,6 +260,7 @@ int main(int argc, char** argv) {
     for (auto& c : tcases) {
       run_case(ctx, c, 2, true);
       if (c.m > 128 && c.n > 64) run_case(ctx, c, 3, true);
+      if (getenv("TETHYS_SELFTEST_MC") && c.m > 256 && c.n > 128) run_case(ctx, c, 4, true);
     }
     if (!time_only) run_case(ctx, tcases[0], 1, true);
   }
