@@ -159,7 +159,7 @@ def test_four_cta_multicast_engine(amaj, bmaj):
 
     dev = torch.device("cuda", 0)
     g = torch.Generator().manual_seed(21 + amaj * 2 + bmaj)
-    m, n, k = 2900, 768, 448
+    m, n, k = 2896, 768, 448      # 5.66 cluster tiles of 512 rows; m % 8 == 0 so that an MN-major A has 16-byte row strides
     a = torch.randn((m, k) if amaj == 0 else (k, m), generator=g).bfloat16().to(dev)
     b = (torch.randn((n, k) if bmaj == 0 else (k, n), generator=g) * 0.1).bfloat16().to(dev)
     bias = torch.randn(n, generator=g).to(dev)

@@ -10,6 +10,9 @@
 //               The pre-activation copy is a second TMA store out of the same box; the activation / dropout math runs
 //               between issuing it and waiting for it. Outputs TMA cannot describe (unaligned C) take a generic path
 //               (32 x 32 transpose through the box, plain coalesced stores).
+// (A 16-warp epilogue — two warps per staging box, 32 columns per thread, 96 registers — was built and measured in round 2: correct,
+// but 3-4 % SLOWER on every shape (fc1 + GELU + dropout 38.7 -> 40.1 us, conv1 226 -> 236 us): the pair barriers around the shared
+// box and the tighter register budget cost more than the extra warps hide. Eight warps it stays.)
 // The accumulator is double buffered in TMEM (2 x BN columns): the epilogue of tile i overlaps the main loop of tile
 // i+1 (tmem_full / tmem_empty mbarriers).
 // Split-K (only for fp32 "C += A*B" outputs, i.e. weight gradients with a long reduce dim and few output tiles):
@@ -156,7 +159,7 @@ __device__ __forceinline__ void epi_act_drop(float (&v)[NV], const EpiParams& p,
   }
   if (p.drop_thr) {
     const DropKey key = flat_drop_key(seed, p.drop_thr);
-    if ((e0 & 31) == 0) {   // this thread's NV consecutive elements are whole 32-element chunks of the mask stream
+    if ((e0 & 31) == 0 && NV >= 32) {   // this thread's NV consecutive elements are whole 32-element chunks of the mask stream
 #pragma unroll
       for (int c = 0; c < NV / 32; ++c) dropout_apply_chunk(v + 32 * c, key, (uint32_t)(e0 >> 5) + c, p.inv_keep);
     } else {
