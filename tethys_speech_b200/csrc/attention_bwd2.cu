@@ -439,25 +439,29 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (warp == 1) ptx::tmem_dealloc(tmem, 512);
 }
 
-// D[b, h, i] = sum_d dO * (O + O_lo); zero the fp32 dQ accumulator. One thread per (b, i, h): 64 contiguous elements.
+// D[b, h, i] = sum_d dO * (O + O_lo); zero the fp32 dQ accumulator. Eight consecutive lanes share one (b, i, h) row of 64 elements:
+// each loads ONE 16-byte vector of O, O_lo and dO (a warp reads 512 contiguous bytes per tensor and instruction), the partial dot
+// products are combined with three shuffles, and every lane zeroes its own 32 bytes of the accumulator row — fully coalesced
+// (the one-thread-per-row version touched 32 different 128-byte lines per instruction: 17.5 us for 46 MB).
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __restrict__ o_lo, const bf16* __restrict__ d_o,
                                                             long long o_ld, long long o_bs, int B, int nh, int Tq, float* __restrict__ dsum,
                                                             float* __restrict__ dq_accum) {
   ts::pdl_enter();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)B * Tq * nh) return;
-  const int h = (int)(idx % nh);
-  const long long bi = idx / nh;
-  const int i = (int)(bi % Tq), b = (int)(bi / Tq);
-  const long long off = (long long)b * o_bs + (long long)i * o_ld + h * B2_D;
-  const uint4* po = reinterpret_cast<const uint4*>(o + off);
-  const uint4* pd = reinterpret_cast<const uint4*>(d_o + off);
-  const uint4* pl = o_lo ? reinterpret_cast<const uint4*>(o_lo + off) : nullptr;
+  const long long rows = (long long)B * Tq * nh;
+  const long long r = idx >> 3;                // (b, i, h) row; the 8 lanes of a row are in one warp (blockDim % 8 == 0)
+  const int part = (int)(idx & 7);
+  const bool ok = r < rows;
   float D = 0.f;
-#pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    const uint4 a = __ldg(po + t), g = __ldg(pd + t);
-    const uint4 lo = pl ? __ldg(pl + t) : make_uint4(0, 0, 0, 0);
+  long long bi = 0;
+  int h = 0;
+  if (ok) {
+    h = (int)(r % nh);
+    bi = r / nh;
+    const int i = (int)(bi % Tq), b = (int)(bi / Tq);
+    const long long off = (long long)b * o_bs + (long long)i * o_ld + h * B2_D + part * 8;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(o + off)), g = __ldg(reinterpret_cast<const uint4*>(d_o + off));
+    const uint4 lo = o_lo ? __ldg(reinterpret_cast<const uint4*>(o_lo + off)) : make_uint4(0, 0, 0, 0);
     const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
     const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&g);
     const __nv_bfloat162* lh = reinterpret_cast<const __nv_bfloat162*>(&lo);
@@ -467,11 +471,17 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const bf16* __restri
       D = fmaf(x.x + z.x, y.x, D);
       D = fmaf(x.y + z.y, y.y, D);
     }
+    float4* z = reinterpret_cast<float4*>(dq_accum + bi * nh * B2_D + h * B2_D + part * 8);
+    z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  dsum[((long long)b * nh + h) * Tq + i] = D;
-  float4* z = reinterpret_cast<float4*>(dq_accum + ((long long)b * Tq + i) * nh * B2_D + h * B2_D);
-#pragma unroll
-  for (int t = 0; t < 16; ++t) z[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  D += __shfl_xor_sync(0xffffffffu, D, 1);
+  D += __shfl_xor_sync(0xffffffffu, D, 2);
+  D += __shfl_xor_sync(0xffffffffu, D, 4);
+  if (ok && part == 0) {
+    const int i = (int)(bi % Tq), b = (int)(bi / Tq);
+    dsum[((long long)b * nh + h) * Tq + i] = D;
+  }
 }
 
 // dq (bf16, caller's strides) = dq_accum (fp32 [B, Tq, nh * 64])
@@ -528,7 +538,7 @@ int attn_bwd2(Ctx* ctx, const ts_attn_desc* d, uint32_t drop_thr, float inv_keep
     attr = true;
   }
   const long long rows = (long long)d->batch * d->tq * d->heads;
-  ts::launch_k(attn_bwd_prep_kernel, cdiv(rows, 256), 256, 0, st, (const bf16*)d->o, (const bf16*)d->o_lo, (const bf16*)d->d_o, d->o_ld, d->o_bs, d->batch,
+  ts::launch_k(attn_bwd_prep_kernel, cdiv(rows * 8, 256), 256, 0, st, (const bf16*)d->o, (const bf16*)d->o_lo, (const bf16*)d->d_o, d->o_ld, d->o_bs, d->batch,
                                                        d->heads, d->tq, d->dsum, d->dq_accum);
   TS_LAUNCH_OK(ctx);
   const int grid = p.items < ctx->num_sms ? p.items : ctx->num_sms;
