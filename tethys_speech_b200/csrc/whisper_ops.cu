@@ -40,14 +40,84 @@ __global__ void __launch_bounds__(512) ce_kernel(const T* logits, T* dlogits /* 
   }
 }
 
+// The same with the row held in shared memory: ONE pass over HBM in 16-byte vectors (the row — 51 872 bf16 = 104 KB for Whisper's
+// vocabulary — is staged while its maximum is taken), the sum of exponentials and the gradient are computed from the staged copy and
+// the gradient row is written in 16-byte vectors. (The scalar kernel above made three passes of 2-byte loads: 107 us for 82 MB.)
+template <typename T>
+__global__ void __launch_bounds__(512) ce_row_smem_kernel(const T* logits, T* dlogits /* may alias logits */, long long ldv,
+                                                          const int* __restrict__ labels, float* __restrict__ loss_sum, int S, int V,
+                                                          float gscale) {
+  ts::pdl_enter();
+  extern __shared__ __align__(16) uint8_t ce_smem[];
+  __shared__ float red[32];
+  T* srow = reinterpret_cast<T*>(ce_smem);
+  const long long row = blockIdx.x;
+  const int b = (int)(row / S), s = (int)(row % S);
+  const T* lr = logits + row * ldv;
+  T* dr = dlogits + row * ldv;
+  const int nvec = (int)(ldv / 8);
+  if (s == S - 1) {
+    float z[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z[i] = 0.f;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) store8<T>(dr + (long long)v * 8, z);
+    return;
+  }
+  const int target = labels[b * S + s + 1];
+  float mx = -INFINITY;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    float x[8];
+    load8<T>(lr + (long long)v * 8, x);
+    store8<T>(srow + v * 8, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (v * 8 + i < V) mx = fmaxf(mx, x[i]);
+  }
+  mx = block_max(mx, red);     // (block_* synchronise: the staged row is complete for every thread after this)
+  float se = 0.f;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    float x[8];
+    load8<T>(srow + v * 8, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (v * 8 + i < V) se += __expf(x[i] - mx);
+  }
+  se = block_sum(se, red);
+  const float lse = mx + logf(se);
+  if (threadIdx.x == 0) atomicAdd(loss_sum, lse - to_f<T>(srow[target]));
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    float x[8], g[8];
+    load8<T>(srow + v * 8, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = v * 8 + i;
+      g[i] = j < V ? (__expf(x[i] - lse) - (j == target ? 1.f : 0.f)) * gscale : 0.f;
+    }
+    store8<T>(dr + (long long)v * 8, g);
+  }
+}
+
+template <typename T>
+static int ce_launch(Ctx* ctx, const void* logits, void* dlogits, long long ldv, const int* labels, float* loss_sum, int B, int S, int V,
+                     float gs, cudaStream_t st) {
+  const size_t smem = (size_t)ldv * sizeof(T);
+  const bool al = ldv % 8 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && (reinterpret_cast<uintptr_t>(dlogits) & 15) == 0;
+  if (al && smem <= 200 * 1024) {
+    TS_CUDA_OK(ctx, cudaFuncSetAttribute(ce_row_smem_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ts::launch_k(ce_row_smem_kernel<T>, B * S, 512, smem, st, (const T*)logits, (T*)dlogits, ldv, labels, loss_sum, S, V, gs);
+  } else {
+    ts::launch_k(ce_kernel<T>, B * S, 512, 0, st, (const T*)logits, (T*)dlogits, ldv, labels, loss_sum, S, V, gs);
+  }
+  TS_LAUNCH_OK(ctx);
+  return 0;
+}
+
 int ce_fwd_bwd(Ctx* ctx, int dt, const void* logits, void* dlogits, long long ldv, const int* labels, float* loss_sum, int B,
                int S, int V, float grad_scale, cudaStream_t st) {
   const float gs = grad_scale / (float)(B * (S - 1));
-  if (dt == TS_F32) ts::launch_k(ce_kernel<float>, B * S, 512, 0, st, (const float*)logits, (float*)dlogits, ldv, labels, loss_sum, S, V, gs);
-  else if (dt == TS_BF16) ts::launch_k(ce_kernel<bf16>, B * S, 512, 0, st, (const bf16*)logits, (bf16*)dlogits, ldv, labels, loss_sum, S, V, gs);
-  else return set_err(ctx, TS_EDTYPE, "ce: dtype %d", dt);
-  TS_LAUNCH_OK(ctx);
-  return 0;
+  if (dt == TS_F32) return ce_launch<float>(ctx, logits, dlogits, ldv, labels, loss_sum, B, S, V, gs, st);
+  if (dt == TS_BF16) return ce_launch<bf16>(ctx, logits, dlogits, ldv, labels, loss_sum, B, S, V, gs, st);
+  return set_err(ctx, TS_EDTYPE, "ce: dtype %d", dt);
 }
 
 // ---- embedding -------------------------------------------------------------------------------------------------
