@@ -48,6 +48,9 @@ struct Whisper {
   float* scalars;  // [0] loss, [3] raw sum
   const int* labels = nullptr;
   // scratch
+  // side stream for the decoder's weight gradients (dense_bwd): fork / join events, all inside the caller's stream order
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   float* s_x32;   // fp32 [B*S, d]: split-K target of the lm_head input gradient (K = vocabulary)
   void *s_a, *s_b, *s_t, *s_x, *s_f, *s_ctx, *s_qkv, *s_P, *s_Pd, *s_dqacc, *s_denc, *s_dq, *s_dkv, *s_dcol, *s_du;
   uint64_t seed = 0;
@@ -266,8 +269,23 @@ static int dense_bwd(Whisper* m, const void* X, int K, const void* dY, int Nn, l
                      uint64_t drop_seed = 0) {
   Ctx* ctx = m->ctx;
   const int dt = m->prec;
-  TS_TRY(GemmB(dt, TS_F32).A(X, 1, K).B(dY, 1, Nn).C(m->G + w_off, ldw).mnk(K, Nn, (int)rows).acc().run(ctx, st));
-  if (b_off >= 0) TS_TRY(colsum_acc(ctx, dt, dY, Nn, (int)rows, Nn, m->G + b_off, st));
+  // Decoder-sized problems (a few hundred rows) occupy a third of the SMs and are mostly launch head and tail: the weight gradient
+  // (and the bias column sums) run on a side stream next to the input gradient and are joined right after it — inside a CUDA-graph
+  // capture this becomes a fork / join of two branches. Large problems fill the machine on their own and stay in line.
+  const bool fork = m->side && dX && rows <= 2048;
+  cudaStream_t ws = st;
+  if (fork) {
+    TS_CUDA_OK(ctx, cudaEventRecord(m->ev_fork, st));
+    TS_CUDA_OK(ctx, cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+    ws = m->side;
+  }
+  TS_TRY(GemmB(dt, TS_F32).A(X, 1, K).B(dY, 1, Nn).C(m->G + w_off, ldw).mnk(K, Nn, (int)rows).acc().run(ctx, ws));
+  if (b_off >= 0) TS_TRY(colsum_acc(ctx, dt, dY, Nn, (int)rows, Nn, m->G + b_off, ws));
+  if (fork) TS_CUDA_OK(ctx, cudaEventRecord(m->ev_join, m->side));
+  struct Join {   // the join is queued on every exit path below
+    Whisper* m; cudaStream_t st; bool on;
+    ~Join() { if (on) cudaStreamWaitEvent(st, m->ev_join, 0); }
+  } join{m, st, fork};
   if (dX) {
     GemmB g(dt, dt);
     g.A(dY, 0, Nn).B(m->W(w_off), 0, ldw).C(dX, K).mnk((int)rows, K, Nn);
@@ -583,6 +601,14 @@ int ts_whisper_create(ts_ctx* ctx_, const ts_whisper_config* cfg, int precision,
     return 0;
   };
   if (make_pe(cfg->n_ctx, &m->pe_enc) || make_pe(cfg->max_target, &m->pe_dec)) { delete m; return TS_ECUDA; }
+  if (!(getenv("TETHYS_NO_SIDE_WGRAD") && atoi(getenv("TETHYS_NO_SIDE_WGRAD")) != 0)) {
+    if (cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      m->side = nullptr;   // no side stream: everything stays on the caller's stream
+    }
+  }
   *out = reinterpret_cast<ts_whisper*>(m);
   return 0;
 }
@@ -590,6 +616,9 @@ void ts_whisper_destroy(ts_whisper* h) {
   Whisper* m = reinterpret_cast<Whisper*>(h);
   if (!m) return;
   cudaFree(m->pe_enc); cudaFree(m->pe_dec);
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  if (m->ev_join) cudaEventDestroy(m->ev_join);
+  if (m->side) cudaStreamDestroy(m->side);
   delete m;
 }
 int64_t ts_whisper_arena_elems(ts_whisper* h) { return reinterpret_cast<Whisper*>(h)->pt.n; }
