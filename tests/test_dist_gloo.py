@@ -43,6 +43,11 @@ def _worker(rank, world, port, q):
     res["allreduce_ok"] = bool(torch.equal(g, torch.arange(1000, dtype=torch.float32) * 3))
     # K22 loss reduce
     res["loss_sum"] = float(st.reduce(ReduceOp.SUM, torch.tensor(0.5 + rank)))
+    # asynchronous bucket reduce with a packing hook: `pre` must have run before the collective reads the bucket
+    bucket = torch.zeros(64)
+    st.all_reduce_async_(bucket, pre=lambda: bucket.fill_(float(rank + 1)))
+    st.join_async()
+    res["async_pre"] = float(bucket[0])
     # Wav2Vec2 convention end to end on the oracle's gradients
     cfg = O.Wav2Vec2Config("tiny")
     w = O.randomize_weights(O.init_weights(cfg, seed=0, dtype=torch.float64), seed=1)
@@ -79,6 +84,7 @@ def test_strategy_shim_world2_gloo():
         assert got[r]["bcast"] == 1000.0            # everyone holds the chief's (rank 0) values
         assert got[r]["allreduce_ok"]
         assert got[r]["loss_sum"] == 0.5 + 1.5
+        assert got[r]["async_pre"] == 3.0           # 1 + 2: both replicas' buckets were packed before the SUM
     # the reduced gradient is the SUM of the two locally clipped gradients, identical on both ranks
     import numpy as np
 
