@@ -334,29 +334,52 @@ def kernel_rooflines(ctx, peaks, B, T, H, F, nh, n_params):
     gemm(f"gemm_tc_kernel wgrad {H}x{F}x{M} fp32 split-K", H, F, M, 1, 1, out_f32=True, acc=True)
     gemm(f"gemm_tc_kernel conv1 window-GEMM {B * 24000}x512x1536 (k3 s2, no im2col; V:254-268)", B * 24000, 512, 1536, 0, 1, lda=1024)
 
-    # fused attention
-    qkv = (torch.randn(B, T, 3 * H, device=dev)).to(bf)
-    o = torch.empty(B, T, H, device=dev, dtype=bf); olo = torch.empty_like(o)
-    do = torch.randn(B, T, H, device=dev).to(bf)
-    dqkv = torch.empty_like(qkv)
-    stats = torch.empty(B, nh, T, 2, device=dev); dsum = torch.empty(B, nh, T, device=dev)
-    dqacc = torch.empty(B, T, H, device=dev)           # fp32 dQ accumulator: selects the fused one-kernel backward
-    a = _lib.AttnDesc()
-    a.q, a.k, a.v, a.o, a.o_lo = qkv.data_ptr(), qkv.data_ptr() + 2 * H, qkv.data_ptr() + 4 * H, o.data_ptr(), olo.data_ptr()
-    a.q_ld = a.kv_ld = 3 * H; a.q_bs = a.kv_bs = T * 3 * H; a.o_ld = H; a.o_bs = T * H
-    a.stats = stats.data_ptr(); a.batch, a.heads, a.tq, a.tk, a.head_dim = B, nh, T, T, H // nh
-    a.scale, a.mask_mode, a.drop, a.seed = 0.125, 0, 0.1, 3
-    a.d_o, a.dq, a.dk, a.dv = do.data_ptr(), dqkv.data_ptr(), dqkv.data_ptr() + 2 * H, dqkv.data_ptr() + 4 * H
-    a.dq_ld = a.dkv_ld = 3 * H; a.dq_bs = a.dkv_bs = T * 3 * H; a.dsum = dsum.data_ptr(); a.dq_accum = dqacc.data_ptr()
-    fl = 4.0 * B * nh * T * T * (H // nh)
-    t = _timed(lambda: ctx.check(ctx.lib.ts_attn_fwd(ctx.h, C.byref(a), stream_ptr())), flush)
-    out.append({"kernel": f"attn_fwd2_kernel B{B} H{nh} T{T} hd64 dropout 0.1 (V:348-362)", "bound": "tensor", "achieved": fl / t / 1e12,
-                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": fl / t / 1e12 / peaks["bf16_tflops"], "us": t * 1e6,
-                "traffic": ncu_traffic("attn_fwd")})
-    t = _timed(lambda: ctx.check(ctx.lib.ts_attn_bwd(ctx.h, C.byref(a), stream_ptr())), flush)
-    out.append({"kernel": "attn_bwd_prep + attn_bwd2_kernel (fused dQ/dK/dV) + dq_store (same shape; 2x forward FLOPs counted, recompute not)", "bound": "tensor",
-                "achieved": 2 * fl / t / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": 2 * fl / t / 1e12 / peaks["bf16_tflops"],
-                "us": t * 1e6, "traffic": ncu_traffic("attn_bwd")})
+    # fused attention: the workload's own self-attention shape, plus Whisper's encoder self-attention (B4 H12 T1500) and cross-attention
+    # (100 queries x 1500 keys) shapes
+    def attn_case(tag, Bc, nhc, Tq, Tk, drop, ref, keyf=None, keyb=None):
+        Hc = nhc * 64
+        cross = Tq != Tk
+        if cross:
+            qt = torch.randn(Bc, Tq, Hc, device=dev).to(bf); kvt = torch.randn(Bc, Tk, 2 * Hc, device=dev).to(bf)
+            dqt = torch.empty_like(qt); dkvt = torch.empty_like(kvt)
+        else:
+            qkv_ = torch.randn(Bc, Tq, 3 * Hc, device=dev).to(bf); dqkv_ = torch.empty_like(qkv_)
+        o_ = torch.empty(Bc, Tq, Hc, device=dev, dtype=bf); olo_ = torch.empty_like(o_)
+        do_ = torch.randn(Bc, Tq, Hc, device=dev).to(bf)
+        stats_ = torch.empty(Bc, nhc, Tq, 2, device=dev); dsum_ = torch.empty(Bc, nhc, Tq, device=dev)
+        dqacc_ = torch.empty(Bc, Tq, Hc, device=dev)           # fp32 dQ accumulator: selects the fused one-kernel backward
+        a = _lib.AttnDesc()
+        if cross:
+            a.q, a.k, a.v = qt.data_ptr(), kvt.data_ptr(), kvt.data_ptr() + 2 * Hc
+            a.q_ld, a.q_bs, a.kv_ld, a.kv_bs = Hc, Tq * Hc, 2 * Hc, Tk * 2 * Hc
+            a.dq, a.dk, a.dv = dqt.data_ptr(), dkvt.data_ptr(), dkvt.data_ptr() + 2 * Hc
+            a.dq_ld, a.dq_bs, a.dkv_ld, a.dkv_bs = Hc, Tq * Hc, 2 * Hc, Tk * 2 * Hc
+        else:
+            a.q, a.k, a.v = qkv_.data_ptr(), qkv_.data_ptr() + 2 * Hc, qkv_.data_ptr() + 4 * Hc
+            a.q_ld = a.kv_ld = 3 * Hc; a.q_bs = a.kv_bs = Tq * 3 * Hc
+            a.dq, a.dk, a.dv = dqkv_.data_ptr(), dqkv_.data_ptr() + 2 * Hc, dqkv_.data_ptr() + 4 * Hc
+            a.dq_ld = a.dkv_ld = 3 * Hc; a.dq_bs = a.dkv_bs = Tq * 3 * Hc
+        a.o, a.o_lo, a.o_ld, a.o_bs = o_.data_ptr(), olo_.data_ptr(), Hc, Tq * Hc
+        a.stats = stats_.data_ptr(); a.batch, a.heads, a.tq, a.tk, a.head_dim = Bc, nhc, Tq, Tk, 64
+        a.scale, a.mask_mode, a.drop, a.seed = 0.125, 0, drop, 3
+        a.d_o, a.dsum, a.dq_accum = do_.data_ptr(), dsum_.data_ptr(), dqacc_.data_ptr()
+        fl = 4.0 * Bc * nhc * Tq * Tk * 64
+        t = _timed(lambda: ctx.check(ctx.lib.ts_attn_fwd(ctx.h, C.byref(a), stream_ptr())), flush)
+        out.append({"kernel": f"attn_fwd2_kernel {tag} B{Bc} H{nhc} Tq{Tq} Tk{Tk} hd64 dropout {drop} ({ref})", "bound": "tensor", "achieved": fl / t / 1e12,
+                    "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": fl / t / 1e12 / peaks["bf16_tflops"], "us": t * 1e6,
+                    "traffic": ncu_traffic(keyf) if keyf else None})
+        t = _timed(lambda: ctx.check(ctx.lib.ts_attn_bwd(ctx.h, C.byref(a), stream_ptr())), flush)
+        out.append({"kernel": f"attn_bwd_prep + attn_bwd2_kernel (fused dQ/dK/dV) + dq_store {tag} (same shape; 2x forward FLOPs counted, recompute not)",
+                    "bound": "tensor", "achieved": 2 * fl / t / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": 2 * fl / t / 1e12 / peaks["bf16_tflops"], "us": t * 1e6, "traffic": ncu_traffic(keyb) if keyb else None})
+
+    attn_case("self", B, nh, T, T, 0.1, "V:348-362" if T != 1500 else "W:147-167", "attn_fwd", "attn_bwd")
+    try:
+        if T != 1500:
+            attn_case("whisper encoder self", 4, 12, 1500, 1500, 0.1, "W:147-167")
+        attn_case("whisper cross", 4, 12, 100, 1500, 0.1, "W:278-290")
+    except Exception as ex:      # the extra shapes never take the line down
+        out.append({"kernel": "attention extra shapes", "error": str(ex)[:200]})
 
     def hbm(name, nbytes, fn, key=None):
         t = _timed(fn, flush)
