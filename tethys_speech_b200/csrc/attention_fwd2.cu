@@ -29,7 +29,7 @@ constexpr int F2_M = 128, F2_N = 128, F2_D = 64;
 constexpr int kTile = F2_M * F2_D * 2;          // 16 KB operand tile: [128 x 64] bf16, 128-byte rows, SWIZZLE_128B
 constexpr int kKvStages = 4;
 constexpr int kThreads2 = 64 + 8 * 32;          // TMA warp, MMA warp, 2 softmax warp-groups
-constexpr int kSmem2 = 2 * 2 * kTile /*Q ring: 2 items x (Q0, Q1)*/ + kKvStages * 2 * kTile /*K, V*/ + 256 /*barriers*/;
+constexpr int kSmem2 = 2 * 2 * kTile /*Q ring: 2 items x (Q0, Q1)*/ + kKvStages * 2 * kTile /*K, V*/ + 256 /*barriers*/ + 1024 /*split mode: (m, l) of group 1*/;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThr = 5.5f;
 
@@ -100,6 +100,12 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkv = (p.Tk + F2_N - 1) / F2_N;
+  // Split mode (one query tile per item — Tq <= 128, e.g. Whisper's cross-attention 100 x 1500 — and at least two key tiles): the second
+  // softmax group would idle, so the key tiles ALTERNATE between the two groups (group g takes tiles g, g + 2, ...), both on query tile 0
+  // with their own S / P / O columns and running (max, sum); at the end of the item group 1 hands its partial (m, l, O) to group 0
+  // through the unused Q1 tiles of the Q ring and group 0 merges, normalises and stores. Same semantics, half the serial chain.
+  const bool split = p.Tq <= F2_M && nkv >= 2;
+  float* sm_ml = reinterpret_cast<float*>(smem + (4 + 2 * kKvStages) * kTile + 256);   // [128][2]
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tm_q); ptx::prefetch_tmap(&tm_k); ptx::prefetch_tmap(&tm_v);
@@ -152,7 +158,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       for (int it = blockIdx.x; it < p.items && ok; it += gridDim.x, ++n) {
         const Item w = decode_item(p, it);
         const uint32_t qs = n & 1;
-        const uint32_t q_t[2] = {sQ + qs * 2 * kTile, sQ + qs * 2 * kTile + kTile};
+        const uint32_t q_t[2] = {sQ + qs * 2 * kTile, split ? sQ + qs * 2 * kTile : sQ + qs * 2 * kTile + kTile};
         // descriptors differ only in their 14-bit start-address field (bytes >> 4): one 64-bit add per MMA instead of rebuilding
         // them — the single issuing thread is on the critical path of both softmax groups
         auto issue_s = [&](int g, uint32_t stage) {
@@ -180,6 +186,33 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           __syncwarp();
         };
         if (!ptx::mbar_wait(&q_full[qs], (n >> 1) & 1, watchdog, 43)) break;
+        if (split) {
+          // key tile j belongs to group j & 1; S of tile j + 2 follows P V of tile j of the same group (P aliases S)
+          auto kvwait = [&](uint32_t c) { return ptx::mbar_wait(&kv_full[c % kKvStages], (c / kKvStages) & 1, watchdog, 44); };
+          if (!kvwait(kvc)) break;
+          ptx::tc_fence_after();
+          issue_s(0, kvc % kKvStages);
+          if (!kvwait(kvc + 1)) break;
+          ptx::tc_fence_after();
+          issue_s(1, (kvc + 1) % kKvStages);
+          for (int j = 0; j < nkv && ok; ++j) {
+            const int gj = j & 1;
+            const uint32_t st_j = (kvc + j) % kKvStages;
+            if (!ptx::mbar_wait(&p_full[gj], pc[gj] & 1, watchdog, 45)) { ok = false; break; }
+            ++pc[gj];
+            ptx::tc_fence_after();
+            issue_pv(gj, st_j, j >= 2);
+            if (j + 2 < nkv) {
+              if (!kvwait(kvc + j + 2)) { ok = false; break; }
+              ptx::tc_fence_after();
+              issue_s(gj, (kvc + j + 2) % kKvStages);
+            }
+            commit(&kv_empty[st_j]);
+          }
+          kvc += nkv;
+          if (ok) commit(&q_empty[qs]);
+          continue;
+        }
         if (!ptx::mbar_wait(&kv_full[kvc % kKvStages], (kvc / kKvStages) & 1, watchdog, 44)) break;
         ptx::tc_fence_after();
         issue_s(0, kvc % kKvStages);
@@ -221,12 +254,14 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     bool ok = true;
     for (int it = blockIdx.x; it < p.items && ok; it += gridDim.x) {
       const Item w = decode_item(p, it);
-      if (g == 1 && !w.has1) continue;
-      const int i = w.q0 + g * F2_M + r;                      // query index of this thread
+      if (g == 1 && !w.has1 && !split) continue;
+      const int i = w.q0 + (split ? 0 : g * F2_M) + r;        // query index of this thread
+      const int myn = split ? (nkv - g + 1) / 2 : nkv;        // key tiles of this group
       const DropKey dkey = make_drop_key(p.drop_thr ? salted_seed(p.seed, p.salt) : p.seed, (unsigned long long)(w.b * p.nh + w.h), p.drop_thr);
       const uint32_t drow = (uint32_t)i * (uint32_t)p.drop_pitch;
       float m_run = -INFINITY, l_run = 0.f;
-      for (int j = 0; j < nkv && ok; ++j, ++sc) {
+      for (int jj = 0; jj < myn && ok; ++jj, ++sc) {
+        const int j = split ? 2 * jj + g : jj;
         const bool tr = p.trace && blockIdx.x == 0 && (warp == 2 || warp == 6) && lane == 0 && sc < 16;
         long long* trp = p.trace + (g * 16 + (sc & 15)) * 10;
 #define F2_STAMP(k) do { if (tr) trp[k] = clock64(); } while (0)
@@ -275,8 +310,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           const float m_new = fmaxf(m_run, mx);
           const float alpha = ex2f((m_run - m_new) * kLog2e);  // 0 on the first tile
           l_run *= alpha;
-          if (j > 0) {   // rescale this row of O once P V of the previous tile has retired (it was issued after our last arrive)
-            if (!ptx::mbar_wait(&pv_done[g], (pvc + j - 1) & 1, watchdog, 48)) { ok = false; break; }
+          if (jj > 0) {   // rescale this row of O once P V of the previous tile has retired (it was issued after our last arrive)
+            if (!ptx::mbar_wait(&pv_done[g], (pvc + jj - 1) & 1, watchdog, 48)) { ok = false; break; }
             ptx::tc_fence_after();
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -338,10 +373,38 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       long long* tep = p.trace + 320 + (g * 4 + (pvc / nkv)) * 8;
 #define F2_ESTAMP(k) do { if (tre) tep[k] = clock64(); } while (0)
       F2_ESTAMP(0);
-      if (!ptx::mbar_wait(&pv_done[g], (pvc + nkv - 1) & 1, watchdog, 49)) { ok = false; break; }
+      if (!ptx::mbar_wait(&pv_done[g], (pvc + myn - 1) & 1, watchdog, 49)) { ok = false; break; }
       F2_ESTAMP(1);
-      pvc += nkv;
+      pvc += myn;
       ptx::tc_fence_after();
+      // split mode: group 1 parks (m, l, O) of its half of the keys in shared memory, group 0 merges the two partial softmaxes
+      float a0 = 1.f, a1 = 0.f;
+      float4* part[2] = {reinterpret_cast<float4*>(smem + 1 * kTile), reinterpret_cast<float4*>(smem + 3 * kTile)};   // the Q1 tiles
+      if (split) {
+        if (g == 1) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t ro[32];
+            ptx::tmem_ld_32x32(tO + c * 32, ro);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 8; ++t)    // row r: 8 chunks of 16 bytes, XOR-swizzled against bank conflicts
+              part[c][r * 8 + (t ^ (r & 7))] = make_float4(__uint_as_float(ro[4 * t]), __uint_as_float(ro[4 * t + 1]),
+                                                           __uint_as_float(ro[4 * t + 2]), __uint_as_float(ro[4 * t + 3]));
+          }
+          sm_ml[2 * r] = m_run; sm_ml[2 * r + 1] = l_run;
+          ptx::tc_fence_before();
+          ptx::named_bar_sync(3, 256);      // partial visible to group 0
+          ptx::named_bar_sync(4, 256);      // group 0 has read it: the scratch may be rewritten by the next item
+          continue;
+        }
+        ptx::named_bar_sync(3, 256);
+        const float m1 = sm_ml[2 * r], l1 = sm_ml[2 * r + 1];
+        const float m_all = fmaxf(m_run, m1);
+        a0 = ex2f((m_run - m_all) * kLog2e); a1 = ex2f((m1 - m_all) * kLog2e);
+        l_run = l_run * a0 + l1 * a1;
+        m_run = m_all;
+      }
       const float inv = p.inv_keep / l_run;
       const bool live = i < p.Tq;
       const long long ooff = (long long)w.b * p.o_bs + (long long)i * p.o_ld + w.h * F2_D;
@@ -351,6 +414,17 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         ptx::tmem_ld_32x32(tO + c * 32, ro);
         ptx::tmem_ld_wait();
         F2_ESTAMP(2 + 2 * c);
+        if (split) {   // O = O0 a0 + O1 a1 (group 1's partial from shared memory)
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const float4 o1 = part[c][r * 8 + (t ^ (r & 7))];
+            ro[4 * t] = __float_as_uint(fmaf(__uint_as_float(ro[4 * t]), a0, o1.x * a1));
+            ro[4 * t + 1] = __float_as_uint(fmaf(__uint_as_float(ro[4 * t + 1]), a0, o1.y * a1));
+            ro[4 * t + 2] = __float_as_uint(fmaf(__uint_as_float(ro[4 * t + 2]), a0, o1.z * a1));
+            ro[4 * t + 3] = __float_as_uint(fmaf(__uint_as_float(ro[4 * t + 3]), a0, o1.w * a1));
+          }
+          if (c == 1) ptx::named_bar_sync(4, 256);   // both halves of the partial have been read
+        }
         if (live) {
           float ov[32];
 #pragma unroll
