@@ -35,6 +35,7 @@ constexpr float kRescaleThr = 5.5f;
 
 struct Fwd2Params {
   int B, nh, Tq, Tk, npairs, items;
+  int split;   // 1: every item is ONE 128-row query tile whose key tiles alternate between the two softmax groups
   float scale;
   uint32_t drop_thr; float inv_keep; unsigned long long seed;
   const unsigned long long* salt;
@@ -72,8 +73,8 @@ __device__ __forceinline__ Item decode_item(const Fwd2Params& p, int it) {
   const int pair = it % p.npairs;
   const int bh = it / p.npairs;
   w.h = bh % p.nh; w.b = bh / p.nh;
-  w.q0 = pair * 2 * F2_M;
-  w.has1 = w.q0 + F2_M < p.Tq;
+  w.q0 = pair * (p.split ? F2_M : 2 * F2_M);
+  w.has1 = !p.split && w.q0 + F2_M < p.Tq;
   return w;
 }
 
@@ -104,7 +105,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   // softmax group would idle, so the key tiles ALTERNATE between the two groups (group g takes tiles g, g + 2, ...), both on query tile 0
   // with their own S / P / O columns and running (max, sum); at the end of the item group 1 hands its partial (m, l, O) to group 0
   // through the unused Q1 tiles of the Q ring and group 0 merges, normalises and stores. Same semantics, half the serial chain.
-  const bool split = p.Tq <= F2_M && nkv >= 2;
+  const bool split = p.split != 0;   // host: single-query-tile shapes, or where single-tile items fill the SMs better than pairs
   float* sm_ml = reinterpret_cast<float*>(smem + (4 + 2 * kKvStages) * kTile + 256);   // [128][2]
 
   if (threadIdx.x == 0) {
@@ -471,8 +472,18 @@ int attn_fwd2(Ctx* ctx, const ts_attn_desc* d, uint32_t drop_thr, float inv_keep
   Fwd2Params p;
   memset(&p, 0, sizeof(p));
   p.B = d->batch; p.nh = d->heads; p.Tq = d->tq; p.Tk = d->tk; p.scale = d->scale;
-  p.npairs = cdiv(cdiv(d->tq, F2_M), 2);
-  p.items = p.B * p.nh * p.npairs;
+  {
+    // work items: pairs of query tiles (K/V tiles shared by the two softmax groups), or single tiles in split mode. Split when there is
+    // only one query tile anyway, or when the finer items waste less of the last wave (cost in units of one tile x all its keys on one
+    // SM; a split item pays 12-22 % for the merge and the unshared K/V loads: profiles/r02f_selftest_attn_split.log)
+    const int nq = cdiv(d->tq, F2_M), nkv = cdiv(d->tk, F2_N), bh = p.B * p.nh, sms = ctx->num_sms;
+    const double cost_pair = (double)cdiv((long long)bh * cdiv(nq, 2), sms) * 2.0;
+    const double cost_split = (double)cdiv((long long)bh * nq, sms) * 1.25;   // measured 1.12-1.22 per tile against a pair item
+    static const int force_split = getenv("TETHYS_ATTN_SPLIT") ? atoi(getenv("TETHYS_ATTN_SPLIT")) : -1;
+    p.split = nkv >= 2 && (force_split >= 0 ? force_split != 0 : (nq == 1 || cost_split < cost_pair)) ? 1 : 0;
+    p.npairs = p.split ? nq : cdiv(nq, 2);
+    p.items = bh * p.npairs;
+  }
   p.drop_thr = drop_thr; p.inv_keep = inv_keep; p.seed = d->seed; p.salt = ctx->d_state;
   p.drop_pitch = (d->tk + 31) >> 5;
   p.o = (bf16*)d->o; p.o_lo = (bf16*)d->o_lo; p.o_ld = d->o_ld; p.o_bs = d->o_bs;
