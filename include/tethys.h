@@ -277,6 +277,35 @@ int ts_comm_allreduce_bucket(ts_comm* c, void* buf, int64_t count, int dtype, co
 int ts_comm_check(ts_comm* c);
 int ts_comm_finalize(ts_comm* c);
 
+/* ---- composite train step ("whole fwd + bwd + reduce + update on pre-bound arenas") -------------------------
+ * One call = one step of the reference's train loop body on the arenas given to ts_*_bind:
+ *   ts_w2v_step      train_step VS:1119-1176 (comm == NULL) / distributed_train_step V:1186-1260 (comm != NULL): forward with
+ *                    loss / N (V:1231), backward, LOCAL clip_by_global_norm (V:1243, VS:1171), all-reduce SUM (inside
+ *                    apply_gradients, V:1246), per-variable clipnorm (V:1274) + Adam, return value sum_r loss_r / N (V:1260).
+ *   ts_whisper_step  distributed_train_step W:819-848: forward + shifted CE, backward, all-reduce SUM NOT divided by N (W:834),
+ *                    Adam (W:901: no clipping -> global_clip = clipnorm = 0), return value sum_r loss_r (W:848).
+ * Everything, the NCCL collectives included, is enqueued on `stream`: the call is asynchronous and may be captured in a CUDA
+ * graph (use step = 0 and ts_step_state_advance then). The caller keeps the bf16 compute weights in sync before the first
+ * step (ts_*_sync_compute_weights); every step refreshes them in its update pass. Activations, logits and the per-replica
+ * loss stay readable through ts_*_get_buffer afterwards. */
+typedef struct ts_step_args {
+  ts_optim* optim;        /* over the program's variable table (ts_*_param_info), see ts_optim_create */
+  float* adam_m;          /* fp32 [arena_elems] */
+  float* adam_v;          /* fp32 [arena_elems] */
+  float lr, beta1, beta2, eps;
+  int32_t step;           /* Keras `iterations + 1` (>= 1); 0 = read it from the device step state */
+  float global_clip;      /* tf.clip_by_global_norm on this replica's gradients, before the reduce; <= 0: none */
+  float clipnorm;         /* the optimizer's per-variable clipnorm, after the reduce; <= 0: none */
+  uint64_t seed;          /* dropout seed of this step */
+  int32_t dropout;        /* 0: dropout layers off (parity runs) */
+  int32_t reserved;
+  ts_comm* comm;          /* NULL: one replica */
+  void* grads_bf16;       /* with comm, optional: bf16 [arena_elems] (ts_comm_alloc) - the gradients cross the link as a bf16
+                             bucket and Adam reads the reduced bucket directly; NULL: the fp32 gradient arena is reduced in place */
+  float* scratch_dev;     /* with comm and global_clip > 0: 2 floats of device scratch (the local clip factor) */
+  float* loss_out_dev;    /* nullable: device scalar that receives the step's return value */
+} ts_step_args;
+
 /* tf.keras.layers.Dropout in training mode (W:160, W:203-205, W:342; V:281, V:393-396, V:431) over a flat tensor:
  * y[i] = x[i] * mask(seed, i) / (1 - rate), in place allowed. mask is the library's counter-based generator (element i of the
  * tensor -> chunk i >> 5, position i & 31), the same one the GEMM epilogues (ts_gemm_desc.drop / .seed) and every backward
@@ -339,6 +368,11 @@ int ts_w2v_backward(ts_w2v* m, int stage_from, int stage_to, void* stream);
 /* named views into the workspace of the last forward ("scalars" = {loss, contrastive, perplexity, raw sum}). */
 int ts_w2v_get_buffer(ts_w2v* m, const char* name, void** ptr, int32_t* dtype, int32_t* ndim, int64_t* shape4);
 
+/* Pre-training program (cfg.head == 0): neg / neg_bs / neg_ts as in ts_w2v_forward, labels ignored. Task-head programs
+ * (cfg.head 1 / 2, VS:1155-1157): labels as in ts_w2v_forward_head, neg ignored. */
+int ts_w2v_step(ts_w2v* m, const float* wave, int batch, int n_samples, const int32_t* neg, int64_t neg_bs, int64_t neg_ts,
+                const int32_t* labels, const ts_step_args* args, void* stream);
+
 /* ---- Whisper encoder-decoder program ---------------------------------------------------------------------
  * Replaces WhisperForConditionalGeneration.call(features, labels=labels, training=True) and tape.gradient of
  * distributed_train_step's per-replica body (W:547-616, W:826-833). features [B, n_mels, T_mel] fp32,
@@ -376,6 +410,8 @@ int ts_whisper_encode(ts_whisper* m, const float* feats, int batch, int n_frames
 int ts_whisper_decode_step(ts_whisper* m, int32_t* tokens, int64_t ld_tok, int len, void* stream);
 int ts_whisper_backward(ts_whisper* m, int stage_from, int stage_to, void* stream);
 int ts_whisper_get_buffer(ts_whisper* m, const char* name, void** ptr, int32_t* dtype, int32_t* ndim, int64_t* shape4);
+int ts_whisper_step(ts_whisper* m, const float* features, int batch, int t_mel, const int32_t* labels, int seq,
+                    const ts_step_args* args, void* stream);
 
 #ifdef __cplusplus
 }

@@ -59,7 +59,7 @@ def _c_layout(struct, fields):
 
 
 @pytest.mark.parametrize("cname,mirror", [("ts_gemm_desc", "GemmDesc"), ("ts_attn_desc", "AttnDesc"), ("ts_w2v_config", "W2VConfig"),
-                                          ("ts_whisper_config", "WhisperCfg")])
+                                          ("ts_whisper_config", "WhisperCfg"), ("ts_step_args", "StepArgs")])
 def test_struct_layouts_match_c(cname, mirror):
     """Every ctypes mirror in _lib.py has the size and the field offsets gcc gives the struct of include/tethys.h."""
     from tethys_speech_b200 import _lib
@@ -84,6 +84,21 @@ def test_integration_md_struct_snippet_is_current():
     assert [f[0] for f in doc._fields_] == [f[0] for f in _lib.W2VConfig._fields_]
     assert ctypes.sizeof(doc) == ctypes.sizeof(_lib.W2VConfig)
     assert [getattr(doc, f[0]).offset for f in doc._fields_] == [getattr(_lib.W2VConfig, f[0]).offset for f in _lib.W2VConfig._fields_]
+
+
+def test_integration_md_step_args_snippet_is_current():
+    """Same check for the ts_step_args binding INTEGRATION.md shows for the composite step entries."""
+    from tethys_speech_b200 import _lib
+
+    txt = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"class ts_step_args\(C\.Structure\):.*?\n(    _fields_ = \[.*?\])\n", txt, flags=re.S)
+    assert m, "INTEGRATION.md no longer shows the ts_step_args binding"
+    ns = {"C": ctypes}
+    exec("class S(C.Structure):\n" + m.group(1), ns)
+    doc = ns["S"]
+    assert [f[0] for f in doc._fields_] == [f[0] for f in _lib.StepArgs._fields_]
+    assert [getattr(doc, f[0]).offset for f in doc._fields_] == [getattr(_lib.StepArgs, f[0]).offset for f in _lib.StepArgs._fields_]
+    assert ctypes.sizeof(doc) == ctypes.sizeof(_lib.StepArgs)
 
 
 def test_no_cpu_fallback_without_gpu():

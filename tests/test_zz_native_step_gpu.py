@@ -1,0 +1,163 @@
+"""The composite C-ABI entries ts_w2v_step / ts_whisper_step (whole forward + backward + reduce + update on the
+pre-bound arenas in ONE call) against the ORACLE's train step, and against the Python-composed step functions.
+
+fp32 mode: three optimiser steps, post-step weights and losses vs oracle.train_step (the same bars as
+test_w2v_train_step_fp32_matches_oracle_adam / test_whisper_train_steps_fp32_match_oracle_adam).
+The replica branch (comm != NULL: local clip factor -> pre-multiplied NCCL SUM -> clipnorm + Adam -> reduced loss; bf16 bucket
+variant) runs on this 1-GPU box over a ONE-rank native communicator: the collectives are real NCCL calls on the step's stream
+and with N = 1 the result must equal the single-replica step — which the oracle pins. The 2-GPU form of the same comparison is
+tools/check_dist_oracle.py."""
+import ctypes as C
+
+import pytest
+import torch
+
+from conftest import rel_l2, rel_max
+
+pytestmark = pytest.mark.gpu
+
+
+def _w2v_setup(precision, seed=3):
+    from oracle import wav2vec2_oracle as O
+    from tethys_speech_b200 import wav2vec2 as W
+
+    ocfg = O.Wav2Vec2Config("tiny")
+    w64 = O.randomize_weights(O.init_weights(ocfg, seed=seed, dtype=torch.float64), seed=seed + 1)
+    model = W.Wav2Vec2ForPreTraining(W.Wav2Vec2Config("tiny"), precision=precision, seed=seed)
+    model.set_weights({k: v.float() for k, v in w64.items()})
+    g = torch.Generator().manual_seed(100 + seed)
+    wave = torch.randn(2, 3200, generator=g, dtype=torch.float64)
+    T = O.num_frames(ocfg, 3200)
+    neg = O.negative_indices_from_random(torch.randint(0, T, (2, T), generator=g), ocfg.num_negatives)
+    return O, W, ocfg, w64, model, wave, neg
+
+
+class _OneRankStrategy:
+    """A Strategy-shaped holder of a one-rank native communicator (ts_comm_unique_id / ts_comm_init with nranks = 1)."""
+
+    def __init__(self):
+        from tethys_speech_b200 import _lib
+
+        self._ctx = _lib.context(torch.cuda.current_device())
+        uid = C.create_string_buffer(128)
+        self._ctx.check(self._ctx.lib.ts_comm_unique_id(self._ctx.h, uid))
+        h = C.c_void_p()
+        self._ctx.check(self._ctx.lib.ts_comm_init(self._ctx.h, uid.raw, 1, 0, C.byref(h)))
+        self.comm = h
+        self.world, self.rank, self.local_rank, self.dist = 1, 0, 0, None
+
+    def close(self):
+        torch.cuda.synchronize()
+        self._ctx.check(self._ctx.lib.ts_comm_finalize(self.comm))
+        self.comm = None
+
+
+def test_w2v_native_step_fp32_matches_oracle_adam():
+    """ts_w2v_step, one replica: VS:1119-1176 (clip_by_global_norm 1.0 + clipnorm 1.0 + Keras-legacy Adam 3e-5)."""
+    O, W, ocfg, w64, model, wave, neg = _w2v_setup("fp32")
+    opt = W.Adam(learning_rate=3e-5, epsilon=1e-8, clipnorm=1.0)
+    w = {k: v.clone() for k, v in w64.items()}
+    m = {k: torch.zeros_like(v) for k, v in w.items()}
+    v_ = {k: torch.zeros_like(v) for k, v in w.items()}
+    for t in range(1, 4):
+        loss = W.native_train_step(model, (wave.float(), None), opt, neg_indices=neg, dropout=False)
+        oout = O.train_step(ocfg, w, m, v_, t, wave, neg, lr=3e-5, eps=1e-8)
+        assert abs(float(loss) - float(oout["loss"])) / abs(float(oout["loss"])) < 1e-4
+    assert opt.iterations == 3
+    model._prog.ctx.watchdog()
+    got = model.get_weights()
+    for k in ("encoder.layers.0.attention.q_proj.kernel", "fe.conv1.kernel", "project_hid.dense.kernel", "quantizer.codevectors",
+              "fe.conv0.gn.gamma", "encoder.layers.1.feed_forward.output_dense.bias"):
+        d_gpu = got[k].double().cpu() - w64[k]
+        d_ref = w[k] - w64[k]
+        assert rel_l2(d_gpu, d_ref) < 2e-3, (k, rel_l2(d_gpu, d_ref))
+        assert rel_max(got[k], w[k]) < 1e-5, k
+
+
+def test_w2v_native_step_replica_branch_one_rank_fp32_matches_oracle():
+    """ts_w2v_step with a communicator (V:1186-1260): local clip factor folded into an NCCL pre-multiplied SUM, clipnorm + Adam,
+    loss / N reduced. N = 1, so the oracle's single-replica step is the expected result."""
+    O, W, ocfg, w64, model, wave, neg = _w2v_setup("fp32", seed=5)
+    st = _OneRankStrategy()
+    try:
+        opt = W.Adam(learning_rate=3e-5, epsilon=1e-8, clipnorm=1.0)
+        w = {k: v.clone() for k, v in w64.items()}
+        m = {k: torch.zeros_like(v) for k, v in w.items()}
+        v_ = {k: torch.zeros_like(v) for k, v in w.items()}
+        for t in range(1, 3):
+            loss = W.native_train_step(model, (wave.float(), None), opt, neg_indices=neg, dropout=False, strategy=st)
+            oout = O.train_step(ocfg, w, m, v_, t, wave, neg, lr=3e-5, eps=1e-8)
+            assert abs(float(loss) - float(oout["loss"])) / abs(float(oout["loss"])) < 1e-4
+        got = model.get_weights()
+        for k in ("encoder.layers.0.attention.q_proj.kernel", "fe.conv1.kernel", "quantizer.codevectors", "fe.conv0.gn.gamma"):
+            d_gpu = got[k].double().cpu() - w64[k]
+            d_ref = w[k] - w64[k]
+            assert rel_l2(d_gpu, d_ref) < 2e-3, (k, rel_l2(d_gpu, d_ref))
+    finally:
+        st.close()
+
+
+def test_w2v_native_step_bf16_bucket_tracks_python_step():
+    """bf16 compute, dropout on, bf16 gradient bucket through the one-rank communicator: same update as the Python-composed
+    single-replica step up to the bucket's bf16 rounding of the (clipped) gradients — compared loosely like
+    test_graph_gpu (split-K atomics make bf16 runs differ run to run), the step count exactly."""
+    O, W, ocfg, w64, m1, wave, neg = _w2v_setup("bf16", seed=7)
+    _, _, _, _, m2, _, _ = _w2v_setup("bf16", seed=7)
+    st = _OneRankStrategy()
+    try:
+        o1 = W.Adam(learning_rate=1e-4, epsilon=1e-8, clipnorm=1.0)
+        o2 = W.Adam(learning_rate=1e-4, epsilon=1e-8, clipnorm=1.0)
+        p0 = m2._prog.params.clone()
+        for _ in range(3):
+            l1 = W.native_train_step(m1, (wave.float(), None), o1, neg_indices=neg, dropout=False, strategy=st)
+            l2 = W.train_step(m2, (wave.float(), None), o2, neg_indices=neg, dropout=False)
+        torch.cuda.synchronize()
+        assert o1.iterations == o2.iterations == 3
+        assert abs(float(l1) - float(l2)) < 2e-2 * abs(float(l2))
+        p1, p2 = m1._prog.params, m2._prog.params
+        assert float((p1 - p2).norm() / p2.norm()) < 2e-3
+        u1, u2 = (p1 - p0).double(), (p2 - p0).double()          # Adam's early steps are sign-like: the two updates must point the same way
+        assert float((u1 * u2).sum() / (u1.norm() * u2.norm())) > 0.5
+        loss = W.native_train_step(m1, (wave.float(), None), o1, dropout=True, strategy=st)      # sampler + dropout path
+        assert torch.isfinite(loss).item()
+        m1._prog.ctx.watchdog()
+    finally:
+        st.close()
+
+
+def test_whisper_native_step_fp32_matches_oracle_adam():
+    """ts_whisper_step: W:819-848 + W:901, three Adam(1e-4, eps 1e-7) steps without clipping; the last one through the replica
+    branch on a one-rank communicator (raw SUM, W:834)."""
+    from oracle import whisper_oracle as O
+    from tethys_speech_b200 import whisper as W
+
+    ocfg, cfg = O.WhisperConfig("small"), W.WhisperConfig()
+    for c in (ocfg, cfg):
+        c.d_model, c.d_ff = 64, 128
+        c.encoder_layers = c.decoder_layers = 2
+        c.encoder_attention_heads = c.decoder_attention_heads = 2
+        c.vocab_size, c.n_mels, c.n_ctx, c.decoder_start_token_id = 203, 16, 64, 200
+    w64 = O.randomize_weights(O.init_weights(ocfg, seed=4, dtype=torch.float64), seed=5)
+    model = W.WhisperForConditionalGeneration(cfg, precision="fp32", seed=4)
+    model.set_weights({k: v.float() for k, v in w64.items()})
+    g = torch.Generator().manual_seed(11)
+    feats = torch.randn(2, ocfg.n_mels, 100, generator=g, dtype=torch.float64)
+    labels = torch.randint(0, 100, (2, 12), generator=g, dtype=torch.int32)
+    opt = W.Adam(learning_rate=1e-4)
+    w = {k: v.clone() for k, v in w64.items()}
+    m = {k: torch.zeros_like(v) for k, v in w.items()}
+    v_ = {k: torch.zeros_like(v) for k, v in w.items()}
+    st = _OneRankStrategy()
+    try:
+        for t in range(1, 4):
+            loss = W.native_train_step(model, (feats.float(), labels), opt, dropout=False, strategy=st if t == 3 else None)
+            oout = O.train_step(ocfg, w, m, v_, t, feats, labels)
+            assert abs(float(loss) - float(oout["loss"])) / abs(float(oout["loss"])) < 1e-4
+        got = model.get_weights()
+        for k in ("lm_head.kernel", "decoder.embed_tokens.embeddings", "encoder.conv1.kernel", "decoder.layers.1.encoder_attn.k_proj.kernel",
+                  "encoder.layers.0.self_attn.q_proj.bias", "decoder.layer_norm.gamma"):
+            d_gpu = got[k].double().cpu() - w64[k]
+            d_ref = w[k] - w64[k]
+            assert rel_l2(d_gpu, d_ref) < 5e-3, (k, rel_l2(d_gpu, d_ref))
+    finally:
+        st.close()

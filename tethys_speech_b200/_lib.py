@@ -84,6 +84,18 @@ class WhisperCfg(C.Structure):
     ]
 
 
+class StepArgs(C.Structure):
+    """ts_step_args: optimizer / replica arguments of the composite entries ts_w2v_step / ts_whisper_step."""
+    _fields_ = [
+        ("optim", C.c_void_p), ("adam_m", C.c_void_p), ("adam_v", C.c_void_p),
+        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+        ("step", C.c_int32), ("global_clip", C.c_float), ("clipnorm", C.c_float),
+        ("seed", C.c_uint64),
+        ("dropout", C.c_int32), ("reserved", C.c_int32),
+        ("comm", C.c_void_p), ("grads_bf16", C.c_void_p), ("scratch_dev", C.c_void_p), ("loss_out_dev", C.c_void_p),
+    ]
+
+
 # every symbol include/tethys.h declares: name -> (restype, argtypes)
 _P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SYMBOLS = {
@@ -144,6 +156,7 @@ SYMBOLS = {
     "ts_w2v_forward_head": (_I, [_P, _P, _I, _I, _P, _F, C.c_uint64, _I, _I, _P]),
     "ts_w2v_forward_features": (_I, [_P, _P, _I, _I, _P]),
     "ts_w2v_backward": (_I, [_P, _I, _I, _P]),
+    "ts_w2v_step": (_I, [_P, _P, _I, _I, _P, _L, _L, _P, C.POINTER(StepArgs), _P]),
     "ts_w2v_get_buffer": (_I, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L)]),
     "ts_whisper_create": (_I, [_P, C.POINTER(WhisperCfg), _I, C.POINTER(_P)]),
     "ts_whisper_destroy": (None, [_P]),
@@ -159,6 +172,7 @@ SYMBOLS = {
     "ts_whisper_encode": (_I, [_P, _P, _I, _I, _I, _P]),
     "ts_whisper_decode_step": (_I, [_P, _P, _L, _I, _P]),
     "ts_whisper_backward": (_I, [_P, _I, _I, _P]),
+    "ts_whisper_step": (_I, [_P, _P, _I, _I, _P, _I, C.POINTER(StepArgs), _P]),
     "ts_whisper_get_buffer": (_I, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L)]),
 }
 

@@ -113,4 +113,48 @@ static inline void same_pad(int t_in, int k, int s, int* t_out, int* left, int* 
   *t_out = to; *left = pt / 2; *right = pt - pt / 2;
 }
 
+// ---- composite train step (ts_w2v_step / ts_whisper_step) ---------------------------------------------------
+// Everything after backward: [local clip_by_global_norm factor] -> cross-replica SUM of the gradient arena -> per-variable
+// clipnorm + Keras-legacy Adam (+ refresh of the bf16 compute weights) -> the step's return value. All of it is enqueued on
+// `st` (NCCL included), so a caller may capture the whole step in one CUDA graph.
+//   loss_mean_over_replicas: Wav2Vec2's convention (V:1231, V:1260: sum_r loss_r / N); Whisper returns sum_r loss_r (W:848).
+static inline int step_reduce_update(Ctx* ctx, float* P, float* G, void* P16, long long n, const float* loss_dev,
+                                     bool loss_mean_over_replicas, const ts_step_args* a, cudaStream_t st) {
+  TS_REQUIRE(ctx, a && a->optim && a->adam_m && a->adam_v, TS_EINVAL, "step: optimizer handle and Adam state arenas are required");
+  int nranks = 1;
+  if (a->comm) {
+    int rank = 0, ver = 0, reg = 0;
+    TS_TRY(ts_comm_info(a->comm, &nranks, &rank, &ver, &reg));
+  }
+  if (!a->comm) {
+    // one replica: clip_by_global_norm folded into the update pass (VS:1171-1174)
+    TS_TRY(ts_optim_step(a->optim, P, G, a->adam_m, a->adam_v, P16, a->lr, a->beta1, a->beta2, a->eps, a->step, a->global_clip,
+                         a->clipnorm, a->global_clip > 0.f ? 1 : 0, st));
+  } else {
+    const float* scale = nullptr;
+    if (a->global_clip > 0.f) {   // V:1243: the clip is LOCAL and happens before the reduce
+      TS_REQUIRE(ctx, a->scratch_dev, TS_EINVAL, "step: scratch_dev (2 floats) is required with comm and global_clip");
+      TS_TRY(ts_optim_global_clip_scale(a->optim, G, a->global_clip, a->scratch_dev, st));
+      scale = a->scratch_dev;
+    }
+    if (a->grads_bf16) {          // bf16 bucket: the clip factor rides on the pack; Adam reads the reduced bucket as it is
+      TS_TRY(grad_pack_bf16(ctx, G, a->grads_bf16, n, scale, st));
+      TS_TRY(ts_comm_allreduce_bucket(a->comm, a->grads_bf16, n, TS_BF16, nullptr, st));
+      TS_TRY(ts_optim_step_lp(a->optim, P, a->grads_bf16, a->adam_m, a->adam_v, P16, a->lr, a->beta1, a->beta2, a->eps, a->step, 0.f,
+                              a->clipnorm, 0, st));
+    } else {                      // fp32 arena in place; sum_r scale_r * g_r as one pre-multiplied sum
+      TS_TRY(ts_comm_allreduce_bucket(a->comm, G, n, TS_F32, scale, st));
+      TS_TRY(ts_optim_step(a->optim, P, G, a->adam_m, a->adam_v, P16, a->lr, a->beta1, a->beta2, a->eps, a->step, 0.f, a->clipnorm, 0, st));
+    }
+  }
+  if (a->loss_out_dev) {
+    TS_CUDA_OK(ctx, cudaMemcpyAsync(a->loss_out_dev, loss_dev, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (a->comm) {
+      if (loss_mean_over_replicas && nranks > 1) TS_TRY(scale_inplace(ctx, a->loss_out_dev, 1, nullptr, 1.f / (float)nranks, st));
+      TS_TRY(ts_comm_allreduce_bucket(a->comm, a->loss_out_dev, 1, TS_F32, nullptr, st));
+    }
+  }
+  return 0;
+}
+
 }  // namespace ts

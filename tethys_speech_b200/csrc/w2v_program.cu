@@ -737,6 +737,25 @@ int ts_w2v_backward(ts_w2v* h, int stage_from, int stage_to, void* stream) {
   for (int s = std::max(0, stage_from); s <= std::min(ns - 1, stage_to); ++s) TS_TRY(w2v_backward_stage(m, s, st));
   return 0;
 }
+int ts_w2v_step(ts_w2v* h, const float* wave, int B, int N, const int* neg, int64_t neg_bs, int64_t neg_ts, const int* labels,
+                const ts_step_args* a, void* stream) {
+  W2V* m = reinterpret_cast<W2V*>(h);
+  if (!m) return TS_EINVAL;
+  Ctx* ctx = m->ctx;
+  TS_REQUIRE(ctx, a, TS_EINVAL, "w2v_step: args are required");
+  int nranks = 1;
+  if (a->comm) {
+    int rank = 0, ver = 0, reg = 0;
+    TS_TRY(ts_comm_info(a->comm, &nranks, &rank, &ver, &reg));
+  }
+  // V:1231: the loss (and with it every gradient) is divided by the number of replicas before backward
+  if (m->cfg.head == 0)
+    TS_TRY(ts_w2v_forward(h, wave, B, N, neg, neg_bs, neg_ts, (float)nranks, a->seed, a->dropout ? 1 : 0, stream));
+  else
+    TS_TRY(ts_w2v_forward_head(h, wave, B, N, labels, (float)nranks, a->seed, a->dropout ? 1 : 0, 1, stream));
+  TS_TRY(ts_w2v_backward(h, 0, 1 << 20, stream));
+  return step_reduce_update(ctx, m->P, m->G, m->P16, m->pt.n, m->scalars, /*loss_mean_over_replicas=*/true, a, (cudaStream_t)stream);
+}
 int ts_w2v_get_buffer(ts_w2v* h, const char* name, void** ptr, int32_t* dtype, int32_t* ndim, int64_t* shape4) {
   W2V* m = reinterpret_cast<W2V*>(h);
   if (!m->planned) return set_err(m->ctx, TS_EINVAL, "w2v_get_buffer: no plan yet");

@@ -788,6 +788,16 @@ int ts_whisper_backward(ts_whisper* h, int stage_from, int stage_to, void* strea
   (void)ns;
   return 0;
 }
+int ts_whisper_step(ts_whisper* h, const float* feats, int B, int Tm, const int32_t* labels, int S, const ts_step_args* a, void* stream) {
+  Whisper* m = reinterpret_cast<Whisper*>(h);
+  if (!m) return TS_EINVAL;
+  Ctx* ctx = m->ctx;
+  TS_REQUIRE(ctx, a, TS_EINVAL, "whisper_step: args are required");
+  TS_TRY(ts_whisper_forward(h, feats, B, Tm, labels, S, a->seed, a->dropout ? 1 : 0, 1, stream));
+  TS_TRY(ts_whisper_backward(h, 0, 1 << 20, stream));
+  // W:829-836: raw SUM of the replicas' gradients (no 1/N), Adam without clipping unless the caller asks for it
+  return step_reduce_update(ctx, m->P, m->G, m->P16, m->pt.n, m->scalars, /*loss_mean_over_replicas=*/false, a, (cudaStream_t)stream);
+}
 int ts_whisper_get_buffer(ts_whisper* h, const char* name, void** ptr, int32_t* dtype, int32_t* ndim, int64_t* shape4) {
   Whisper* m = reinterpret_cast<Whisper*>(h);
   if (!m->planned) return set_err(m->ctx, TS_EINVAL, "whisper_get_buffer: no plan yet");

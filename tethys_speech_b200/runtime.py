@@ -517,6 +517,32 @@ class Adam:
         prog.weights_synced = True  # the update refreshed the bf16 compute copy in the same pass
 
 
+def native_step_args(model, optimizer, strategy=None, global_clip=0.0, dropout=True, seed=0):
+    """ts_step_args for the composite C-ABI entries (ts_w2v_step / ts_whisper_step): the optimizer state this
+    Adam object keeps for `model`, the replica group of `strategy` (its native communicator; None / one replica: no collective)
+    and a device scalar for the step's return value. Returns (args, loss_out); keep both alive until the step has run."""
+    prog = model._prog
+    st = optimizer._bind(model)
+    a = _lib.StepArgs()
+    a.optim, a.adam_m, a.adam_v = st["optim"], ptr(st["m"]), ptr(st["v"])
+    a.lr, a.beta1, a.beta2, a.eps = optimizer.learning_rate, optimizer.beta_1, optimizer.beta_2, optimizer.epsilon
+    a.step = 0 if optimizer.device_step else optimizer.iterations + 1
+    a.global_clip, a.clipnorm = float(global_clip or 0.0), float(optimizer.clipnorm or 0.0)
+    a.seed, a.dropout = int(seed), 1 if dropout else 0
+    comm = getattr(strategy, "comm", None) if strategy is not None else None
+    if comm is not None:
+        a.comm = comm
+        if prog.ar_bf16():
+            a.grads_bf16 = ptr(prog.grads_lp())
+        if "scratch" not in st:
+            st["scratch"] = torch.zeros(2, dtype=torch.float32, device=prog.device)
+        a.scratch_dev = ptr(st["scratch"])
+    if "loss_out" not in st:
+        st["loss_out"] = torch.zeros(1, dtype=torch.float32, device=prog.device)
+    a.loss_out_dev = ptr(st["loss_out"])
+    return a, st["loss_out"]
+
+
 class GraphedTrainStep:
     """One whole train step (forward, loss, backward, clip, Adam) captured in a CUDA graph and replayed: removes the ~430
     kernel-launch gaps of a step. The library's device-resident step state (ts_step_state_*) gives every replay fresh
@@ -526,7 +552,8 @@ class GraphedTrainStep:
                                    example_batch, example_aux)
         loss = graphed(batch, aux)          # loss is a device scalar (a view of the workspace)
 
-    Single-process use only (a captured NCCL all-reduce would tie the graph to the communicator's streams)."""
+    With more than one replica the step functions capture the native communicator's collectives into the same graph
+    (make_graphed_distributed_step in wav2vec2.py / whisper.py)."""
 
     def __init__(self, step_fn, model, optimizer, example_batch, example_aux=None, warmup=3):
         self.step_fn, self.model, self.opt = step_fn, model, optimizer

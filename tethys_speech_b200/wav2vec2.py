@@ -470,6 +470,50 @@ def train_step(model, inputs, optimizer, neg_indices=None, dropout=True):
     return loss
 
 
+def native_train_step(model, inputs, optimizer, neg_indices=None, dropout=True, strategy=None):
+    """train_step (VS:1119-1176; strategy None / one replica) or distributed_train_step (V:1186-1260) as ONE C-ABI call —
+    ts_w2v_step, the composite entry of SURVEY §8 b-2: forward (loss / N), backward, local clip_by_global_norm(1.0), all-reduce
+    SUM, clipnorm + Adam, and the reduced loss, all enqueued on the current stream. Same arithmetic and the same kernels as the
+    Python-composed step functions above; returns the step's loss (device scalar, valid until the next native step)."""
+    from .runtime import native_step_args
+
+    features, labels = inputs
+    p = model._prog
+    x = to_device(features, torch.float32, p.device)
+    if x.dim() != 2:
+        raise ValueError("inputs must be [batch, samples]")
+    B, N = x.shape
+    if B == 0:
+        return torch.zeros((), device=p.device)
+    p.ensure_workspace(B, N)
+    p.sync_weights()
+    neg, neg_bs, neg_ts, lab = None, 0, 0, None
+    if isinstance(model, Wav2Vec2ForPreTraining):
+        T = model.num_frames(N)
+        if neg_indices is None:
+            neg = model._sample_negative_indices(T, B)[:, 0, :].contiguous()
+        else:
+            neg = to_device(neg_indices, torch.int32, p.device)
+        if neg.dim() == 2:
+            neg_bs, neg_ts = neg.shape[1], 0
+        else:
+            neg = neg.contiguous()
+            neg_bs, neg_ts = neg.shape[1] * neg.shape[2], neg.shape[2]
+        if neg.shape[-1] != model.num_negatives:
+            raise ValueError(f"neg_indices last dim must be num_negatives={model.num_negatives}")
+    elif model._head == "classification" and labels is not None:
+        lab = to_device(labels, torch.int32, p.device).reshape(-1)
+        if lab.numel() != B:
+            raise ValueError(f"labels must hold one class id per clip ({B}), got {tuple(lab.shape)}")
+    model._step_seed += 1
+    args, loss = native_step_args(model, optimizer, strategy, global_clip=1.0, dropout=dropout, seed=model._step_seed)
+    p.ctx.check(p.lib.ts_w2v_step(p.h, ptr(x), B, N, ptr(neg), neg_bs, neg_ts, ptr(lab), C.byref(args), stream_ptr()))
+    optimizer.iterations += 1
+    p.weights_synced = True            # the update pass refreshed the bf16 compute copy
+    model._last = {"x": x, "neg": neg, "labels": lab, "training": True}
+    return loss[0]
+
+
 def legacy_train_step(model, inputs, optimizer, neg_indices=None, dropout=True):
     """Legacy step of whisper_single.py — WS:1143-1180: no clipping, no NaN guard."""
     features, labels = inputs

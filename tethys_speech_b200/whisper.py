@@ -369,6 +369,30 @@ def distributed_train_step(strategy, model, dist_inputs, optimizer, dropout=True
     return strategy.reduce(ReduceOp.SUM, per_replica_losses, axis=None)
 
 
+def native_train_step(model, inputs, optimizer, dropout=True, strategy=None):
+    """The per-replica body and the reduce of distributed_train_step (W:819-848) as ONE C-ABI call — ts_whisper_step, the composite
+    entry of SURVEY §8 b-2: forward + shifted CE, backward, all-reduce SUM of the gradients (not divided by N), Adam, and the SUM of the
+    replicas' losses, all enqueued on the current stream (strategy None / one replica: no collective). Same kernels as train_step;
+    the all-reduce is one message after backward (the Python distributed step overlaps its buckets with backward instead)."""
+    from .runtime import native_step_args
+
+    features, labels = inputs
+    p = model._prog
+    x = to_device(features, torch.float32, p.device)
+    lab = to_device(labels, torch.int32, p.device)
+    B, nm, Tm = x.shape
+    S = lab.shape[1]
+    p.ensure_workspace(B, Tm, S)
+    p.sync_weights()
+    model._step_seed += 1
+    args, loss = native_step_args(model, optimizer, strategy, global_clip=0.0, dropout=dropout, seed=model._step_seed)
+    p.ctx.check(p.lib.ts_whisper_step(p.h, ptr(x), B, Tm, ptr(lab), S, C.byref(args), stream_ptr()))
+    optimizer.iterations += 1
+    p.weights_synced = True
+    model._last = {"x": x, "labels": lab}
+    return loss[0]
+
+
 def _adam_buckets(model, bucket_elems=16 * 1024 * 1024):
     """Arena ranges that become final together (groups of backward stages, ts_whisper_stage_end), their per-range ts_optim and a
     side stream; built once per model."""
