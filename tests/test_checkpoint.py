@@ -100,7 +100,13 @@ def test_latest_checkpoint_and_tf_keys(tmp_path):
         CK.write_file(str(tmp_path / f"model_step-{n}.tsckpt"), {}, {})
     assert CK.latest_checkpoint(str(tmp_path)).endswith("model_step-10.tsckpt")
     assert CK.tf_object_key("encoder.layers.0.attention.q_proj.kernel") == \
-        "model/encoder/layers/0/attention/q_proj/kernel/.ATTRIBUTES/VARIABLE_VALUE"
+        "model/wav2vec2/encoder/layers/0/attention/q_proj/kernel/.ATTRIBUTES/VARIABLE_VALUE"
+    assert CK.tf_object_key("fe.conv2.gn.gamma") == \
+        "model/wav2vec2/feature_extractor/conv_layers/2/layer_with_weights-1/gamma/.ATTRIBUTES/VARIABLE_VALUE"
+    assert CK.tf_object_key("decoder.layers.1.encoder_attn.k_proj.bias", kind="whisper") == \
+        "model/model/decoder/layers/1/encoder_attn/k_proj/bias/.ATTRIBUTES/VARIABLE_VALUE"
+    assert CK.tf_slot_key("lm_head.kernel", "m", kind="whisper") == \
+        "model/lm_head/kernel/.OPTIMIZER_SLOT/optimizer/m/.ATTRIBUTES/VARIABLE_VALUE"
     # files without a save counter (plain save(path, ...)) are found too, ranked by modification time below numbered ones
     other = tmp_path / "plain"
     other.mkdir()
@@ -173,6 +179,12 @@ def test_restore_continues_the_run_w2v_fp32(tmp_path):
     _, tensors = CK.read_file(path)
     assert {k[6:] for k in tensors if k.startswith("model/")} == set(m1.variable_names)
     assert tensors["model/encoder.layers.0.attention.q_proj.kernel"].shape == (m1.config.hidden_size, m1.config.hidden_size)
+    # the same tensors under the names the reference's tf.train.Checkpoint(model=, optimizer=) gives them
+    named = CK.tf_named_tensors(path)
+    assert len(named) == 3 * len(m1.variable_names) + 1 and int(named["optimizer/iter/.ATTRIBUTES/VARIABLE_VALUE"]) == 2
+    k = "model/wav2vec2/encoder/layers/0/attention/q_proj/kernel"
+    assert named[k + "/.ATTRIBUTES/VARIABLE_VALUE"].shape == (m1.config.hidden_size, m1.config.hidden_size)
+    assert named[k + "/.OPTIMIZER_SLOT/optimizer/m/.ATTRIBUTES/VARIABLE_VALUE"].shape == (m1.config.hidden_size, m1.config.hidden_size)
     m1._prog.ctx.watchdog()
 
 
@@ -203,3 +215,79 @@ def test_save_weights_load_weights_whisper_bf16(tmp_path):
     from tethys_speech_b200.runtime import Adam
     with pytest.raises(KeyError):
         CK.restore(path, m2, Adam())                  # asks for optimizer state the file does not hold
+
+
+def test_tf_object_keys_follow_the_reference_object_graph():
+    """checkpoint.tf_object_key against the reference's OWN model objects: the unmodified constructors of wav2vec2_single.py /
+    whisper_dist.py are run on the TF shim, their attribute graph is walked breadth first with TensorFlow 2.10's trackable
+    naming rules (oracle/tf_object_graph.py) and every variable's first path must be the key the product maps that variable to.
+    (Needs /root/reference; skipped where it is absent.)"""
+    import torch
+
+    from oracle import ref_runner as R
+    from oracle import tf_object_graph as G
+
+    if not R.available():
+        pytest.skip("/root/reference is not present on this machine")
+    ref = R.load("wav2vec2_single")
+    wave = torch.randn(2, 3200, dtype=torch.float64)
+    labels = torch.tensor([3, 7], dtype=torch.int32)
+    for model_type, head in (("pretraining", "pretraining"), ("asr", "ctc"), ("classification", "classification")):
+        model = R.build_w2v(ref, "tiny", wave, model_type=model_type, labels=labels)
+        vm = R.w2v_variable_map(model, head=head)
+        keys = G.variable_keys({"model": model})
+        assert set(keys) == {id(v) for v in vm.values()}, model_type
+        for name, var in vm.items():
+            assert CK.tf_object_key(name, kind="wav2vec2") == keys[id(var)], (model_type, name)
+    wref = R.load("whisper_dist")
+
+    def small(c):
+        c.d_model, c.d_ff, c.encoder_layers, c.decoder_layers = 64, 128, 2, 2
+        c.encoder_attention_heads = c.decoder_attention_heads = 2
+        c.vocab_size, c.n_mels, c.n_ctx, c.decoder_start_token_id = 203, 16, 64, 200
+
+    wm = R.build_whisper(wref, small, torch.randn(1, 16, 100, dtype=torch.float64), torch.randint(0, 100, (1, 8), dtype=torch.int32))
+    vm = R.whisper_variable_map(wm)
+    keys = G.variable_keys({"model": wm})
+    assert set(keys) == {id(v) for v in vm.values()}
+    for name, var in vm.items():
+        assert CK.tf_object_key(name, kind="whisper") == keys[id(var)], name
+
+
+def test_export_tf_names_and_tf_named_tensors(tmp_path):
+    """export_tf_names (what save() records as meta["tf_keys"]) and the TF-keyed view of a file, on a stub model (no GPU)."""
+    import numpy as np
+
+    class WhisperForConditionalGeneration:                       # the class name selects the rule table
+        variable_names = ["encoder.conv1.kernel", "decoder.embed_tokens.embeddings", "lm_head.kernel"]
+
+    class Wav2Vec2ForCTC:
+        variable_names = ["fe.conv0.kernel", "fe.conv0.gn.beta", "fe.pos_conv.bias", "fe.layer_norm.gamma", "quantizer.codevectors",
+                          "project_hid.dense.kernel", "lm_head.bias"]
+
+    t = CK.export_tf_names(WhisperForConditionalGeneration(), with_optimizer=True)
+    assert t["encoder.conv1.kernel"] == "model/model/encoder/conv1/kernel/.ATTRIBUTES/VARIABLE_VALUE"
+    assert t["lm_head.kernel"] == "model/lm_head/kernel/.ATTRIBUTES/VARIABLE_VALUE"
+    assert t["optimizer/v/decoder.embed_tokens.embeddings"] == \
+        "model/model/decoder/embed_tokens/embeddings/.OPTIMIZER_SLOT/optimizer/v/.ATTRIBUTES/VARIABLE_VALUE"
+    assert t["optimizer/iterations"] == "optimizer/iter/.ATTRIBUTES/VARIABLE_VALUE"
+    w = CK.export_tf_names(Wav2Vec2ForCTC())
+    assert w["fe.conv0.gn.beta"] == "model/wav2vec2/feature_extractor/conv_layers/0/layer_with_weights-1/beta/.ATTRIBUTES/VARIABLE_VALUE"
+    assert w["fe.pos_conv.bias"] == "model/wav2vec2/feature_extractor/pos_conv_embed/bias/.ATTRIBUTES/VARIABLE_VALUE"
+    assert w["fe.layer_norm.gamma"] == "model/wav2vec2/feature_extractor/layer_norm/gamma/.ATTRIBUTES/VARIABLE_VALUE"
+    assert w["project_hid.dense.kernel"] == "model/wav2vec2/project_hid/dense/kernel/.ATTRIBUTES/VARIABLE_VALUE"
+    assert w["lm_head.bias"] == "model/lm_head/bias/.ATTRIBUTES/VARIABLE_VALUE"
+    assert len(set(w.values())) == len(w)
+    # a file whose meta carries tf_keys reads back keyed by TF names
+    path = str(tmp_path / "m-1.tsckpt")
+    tensors = {"model/lm_head.bias": np.arange(4, dtype=np.float32), "optimizer/m/lm_head.bias": np.ones(4, np.float32)}
+    meta = {"optimizer": {"iterations": 7}, "tf_keys": {"model/lm_head.bias": w["lm_head.bias"],
+                                                        "optimizer/m/lm_head.bias": CK.tf_slot_key("lm_head.bias", "m")}}
+    CK.write_file(path, tensors, meta)
+    named = CK.tf_named_tensors(path)
+    assert np.array_equal(named["model/lm_head/bias/.ATTRIBUTES/VARIABLE_VALUE"], np.arange(4, dtype=np.float32))
+    assert int(named["optimizer/iter/.ATTRIBUTES/VARIABLE_VALUE"]) == 7
+    assert "model/lm_head/bias/.OPTIMIZER_SLOT/optimizer/m/.ATTRIBUTES/VARIABLE_VALUE" in named
+    CK.write_file(path, tensors, {})
+    with pytest.raises(KeyError):
+        CK.tf_named_tensors(path)

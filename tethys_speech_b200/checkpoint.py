@@ -133,18 +133,69 @@ def read_file(path, keys=None):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# TF object-graph keys (export side): tf.train.Checkpoint(model=…) names a Keras variable by the attribute path from the
-# root object. The reference's attribute names are the ones in its constructors (V:746-766, V:464-546, W:470-545 …).
-# TensorFlow is not installable here, so this mapping is written from the reference source and is NOT verified against a
-# TF-written checkpoint; it is used only for `export_tf_names`.
+# TF object-graph keys (export side). tf.train.Checkpoint(model=model, optimizer=optimizer) (V:1303, W:919) names a variable by
+# the FIRST breadth-first path of Python attribute names from the root: attribute names of sub-layers, list indices
+# (`layers/0`), `layer_with_weights-<k>` for the layers of a tf.keras.Sequential (the conv blocks of V:239-268), the
+# add_weight / attribute name of the variable itself, then "/.ATTRIBUTES/VARIABLE_VALUE". The library's variable paths differ
+# from the reference's attribute structure in a few places (`fe.` = wav2vec2.feature_extractor, the Sequential conv blocks, the
+# task heads that live on the outer model), so the mapping is a short rule table. It is pinned by walking the reference's OWN
+# model objects (its unmodified constructors, running on oracle/tf_shim.py) with those naming rules:
+# tests/test_checkpoint.py::test_tf_object_keys_follow_the_reference_object_graph. The rules themselves are restated from
+# TensorFlow 2.10's trackable code (TensorFlow is not installable here): the keys are not checked against a TF-written file.
 # ----------------------------------------------------------------------------------------------------------------------
-def tf_object_key(variable_path, root="model"):
-    return root + "/" + variable_path.replace(".", "/") + "/.ATTRIBUTES/VARIABLE_VALUE"
+_TF_SUFFIX = "/.ATTRIBUTES/VARIABLE_VALUE"
 
 
-def export_tf_names(model):
-    """variable path -> TF object-graph key for every trainable variable (same order as model.trainable_variables)."""
-    return {n: tf_object_key(n) for n in model.variable_names}
+def _tf_object_path(variable_path, kind):
+    if kind == "whisper":
+        # WhisperForConditionalGeneration: self.model = WhisperModel(config) (W:541), self.lm_head (W:545)
+        if variable_path.startswith("lm_head."):
+            return variable_path.replace(".", "/")
+        return "model/" + variable_path.replace(".", "/")
+    # Wav2Vec2ForPreTraining / ForCTC / ForSequenceClassification: self.wav2vec2 = Wav2Vec2Model(config) (V:832, V:944, V:1008)
+    m = re.match(r"fe\.conv(\d+)\.(gn\.)?(\w+)$", variable_path)
+    if m:       # conv_layers[i] = Sequential([Conv1D, GroupNormalization, Activation]) (V:239-268)
+        return f"wav2vec2/feature_extractor/conv_layers/{m.group(1)}/layer_with_weights-{1 if m.group(2) else 0}/{m.group(3)}"
+    if variable_path.startswith("fe.pos_conv."):
+        return "wav2vec2/feature_extractor/pos_conv_embed/" + variable_path[len("fe.pos_conv."):]
+    if variable_path.startswith("fe."):
+        return "wav2vec2/feature_extractor/" + variable_path[3:].replace(".", "/")
+    if variable_path.startswith("lm_head."):                 # Wav2Vec2ForCTC.lm_head (V:948)
+        return variable_path.replace(".", "/")
+    if variable_path.startswith("classifier_proj."):         # Wav2Vec2ForSequenceClassification.projector (V:1012)
+        return "projector/" + variable_path[len("classifier_proj."):]
+    if variable_path.startswith("classifier."):              # .classifier (V:1015)
+        return variable_path.replace(".", "/")
+    return "wav2vec2/" + variable_path.replace(".", "/")
+
+
+def tf_object_key(variable_path, kind="wav2vec2", root="model"):
+    """Checkpoint key of one model variable in a file written by the reference's tf.train.Checkpoint(model=...)."""
+    return root + "/" + _tf_object_path(variable_path, kind) + _TF_SUFFIX
+
+
+def tf_slot_key(variable_path, slot, kind="wav2vec2", root="model", optimizer="optimizer"):
+    """Key of an optimizer slot variable (Adam's "m" / "v") of the same checkpoint: TF hangs slots under the variable they
+    belong to, `<variable>/.OPTIMIZER_SLOT/<optimizer attribute>/<slot>`."""
+    return f"{root}/{_tf_object_path(variable_path, kind)}/.OPTIMIZER_SLOT/{optimizer}/{slot}{_TF_SUFFIX}"
+
+
+def _kind_of(model):
+    return "whisper" if type(model).__name__.startswith("Whisper") else "wav2vec2"
+
+
+def export_tf_names(model, with_optimizer=False):
+    """variable path -> TF object-graph key for every trainable variable (same order as model.trainable_variables); with
+    `with_optimizer` also "optimizer/m/<path>", "optimizer/v/<path>" (this file format's keys) -> the TF slot keys and
+    "optimizer/iterations" -> Keras' `optimizer/iter`."""
+    kind = _kind_of(model)
+    out = {n: tf_object_key(n, kind) for n in model.variable_names}
+    if with_optimizer:
+        for n in model.variable_names:
+            out["optimizer/m/" + n] = tf_slot_key(n, "m", kind)
+            out["optimizer/v/" + n] = tf_slot_key(n, "v", kind)
+        out["optimizer/iterations"] = "optimizer/iter" + _TF_SUFFIX
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -190,9 +241,26 @@ def save(path, model, optimizer=None, extra_meta=None):
         meta["optimizer"] = {"iterations": int(optimizer.iterations), "learning_rate": optimizer.learning_rate,
                              "beta_1": optimizer.beta_1, "beta_2": optimizer.beta_2, "epsilon": optimizer.epsilon,
                              "clipnorm": optimizer.clipnorm}
+    # every stored tensor's name in a checkpoint the reference's tf.train.Checkpoint(model=, optimizer=) writes (see tf_object_key)
+    tfk = export_tf_names(model, with_optimizer=optimizer is not None)
+    meta["tf_keys"] = {("model/" + k if not k.startswith("optimizer/") else k): v for k, v in tfk.items() if k != "optimizer/iterations"}
     if extra_meta:
         meta.update(extra_meta)
     return write_file(path, tensors, meta)
+
+
+def tf_named_tensors(path):
+    """The tensors of a checkpoint file keyed by their TF object-graph names ({tf key: array}; plus `optimizer/iter` when the
+    file holds optimizer state) — what a TF-side importer assigns to a freshly built reference model
+    (`tf.train.load_variable`-style names; SURVEY f-3 "TF-checkpoint-name-compatible export")."""
+    meta, tensors = read_file(path)
+    tfk = meta.get("tf_keys")
+    if tfk is None:
+        raise KeyError(f"{path} was written before TF names were recorded; re-save it")
+    out = {tfk[k]: v for k, v in tensors.items()}
+    if "optimizer" in meta:
+        out["optimizer/iter" + _TF_SUFFIX] = np.asarray(int(meta["optimizer"]["iterations"]), dtype=np.int64)
+    return out
 
 
 def restore(path, model, optimizer=None, strict=True):
