@@ -291,3 +291,76 @@ def test_export_tf_names_and_tf_named_tensors(tmp_path):
     CK.write_file(path, tensors, {})
     with pytest.raises(KeyError):
         CK.tf_named_tensors(path)
+
+
+def test_save_restore_host_logic_on_a_stub_program(tmp_path, monkeypatch):
+    """save() / restore() end to end on CPU arenas behind a stub of the native program (no kernels involved in a checkpoint):
+    fused-block column slices, Adam slots, iteration count, dropout step seed, device step state, the recorded TF keys."""
+    import ctypes as C
+
+    import torch
+
+    from tethys_speech_b200 import runtime as RT
+
+    calls = {}
+
+    class Lib:
+        def ts_step_state_get(self, h, salt, step):
+            salt._obj.value, step._obj.value = 11, 2
+            return 0
+
+        def ts_step_state_set(self, h, salt, step, stream):
+            calls["state_set"] = (int(salt), int(step))
+            return 0
+
+    class Ctx:
+        h, lib = None, Lib()
+
+        def check(self, rc):
+            assert rc == 0
+
+    class Prog:
+        def __init__(self, fill):
+            # a dense 3-D conv kernel, a [4, 4] column slice of a fused q/k/v block (row stride 12), a bias
+            self.info = {"fe.conv0.kernel": (0, (10, 1, 4), 40), "encoder.layers.0.attention.q_proj.kernel": (64, (4, 4), 12),
+                         "encoder.layers.0.attention.k_proj.kernel": (68, (4, 4), 12), "lm_head.bias": (128, (4,), 4)}
+            self.params = torch.arange(192, dtype=torch.float32) * fill
+            self.params_lp, self.ctx, self.weights_synced = None, Ctx(), True
+            self.lib = self.ctx.lib
+
+    class Wav2Vec2ForCTC:
+        def __init__(self, fill):
+            self._prog = Prog(fill)
+            self.variable_names = list(self._prog.info)
+            self._step_seed = 3
+
+    class Opt:
+        learning_rate, beta_1, beta_2, epsilon, clipnorm = 1e-3, 0.9, 0.999, 1e-8, 1.0
+
+        def __init__(self, it, fill):
+            self.iterations = it
+            self.st = {"m": torch.full((192,), 1.0 * fill), "v": torch.full((192,), 2.0 * fill)}
+
+        def _bind(self, model):
+            return self.st
+
+    monkeypatch.setattr(RT, "stream_ptr", lambda: C.c_void_p(0))
+    m1, o1 = Wav2Vec2ForCTC(1.0), Opt(2, 1.0)
+    path = CK.Checkpoint(model=m1, optimizer=o1).save(str(tmp_path / "ck" / "model_step_50"))
+    assert path.endswith("model_step_50-1.tsckpt")
+    meta, tensors = CK.read_file(path)
+    assert meta["device_salt"] == 11 and meta["step_seed"] == 3 and meta["optimizer"]["iterations"] == 2
+    q = tensors["model/encoder.layers.0.attention.q_proj.kernel"]
+    assert q.shape == (4, 4) and q[1, 0] == 64 + 12 and q[3, 3] == 64 + 36 + 3          # rows 12 apart inside the fused block
+    assert meta["tf_keys"]["model/fe.conv0.kernel"].startswith("model/wav2vec2/feature_extractor/conv_layers/0/layer_with_weights-0/kernel")
+    m2, o2 = Wav2Vec2ForCTC(0.0), Opt(0, 0.0)
+    ck2 = CK.Checkpoint(model=m2, optimizer=o2)
+    ck2.restore(path)
+    assert ck2.save_counter == 1 and o2.iterations == 2 and m2._step_seed == 3 and calls["state_set"] == (11, 2)
+    assert m2._prog.weights_synced is False
+    for name, (off, shp, ld) in m1._prog.info.items():
+        a = CK.gather_variables(m1._prog.params.numpy(), m1._prog.info, [name])[name]
+        b = CK.gather_variables(m2._prog.params.numpy(), m2._prog.info, [name])[name]
+        assert (a == b).all(), name
+    assert float(m2._prog.params[76 + 8]) == 0.0                  # the v_proj columns of the fused block were not in the file: untouched
+    assert float(o2.st["m"][64]) == 1.0 and float(o2.st["v"][129]) == 2.0
