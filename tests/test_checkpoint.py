@@ -364,3 +364,33 @@ def test_save_restore_host_logic_on_a_stub_program(tmp_path, monkeypatch):
         assert (a == b).all(), name
     assert float(m2._prog.params[76 + 8]) == 0.0                  # the v_proj columns of the fused block were not in the file: untouched
     assert float(o2.st["m"][64]) == 1.0 and float(o2.st["v"][129]) == 2.0
+
+
+def test_checkpoint_file_imports_into_the_reference_model_by_tf_names(tmp_path):
+    """Export -> import across the boundary: a checkpoint file holding the oracle's Wav2Vec2 weights under the product's variable
+    paths (+ their TF keys, as save() records them) is assigned to the REFERENCE's own Wav2Vec2ForPreTraining (unmodified
+    constructor, on the TF shim) by TF object-graph name; every reference variable must then hold exactly the tensor the
+    name map of the pinning tests (oracle/ref_runner.py) associates with it. (Needs /root/reference.)"""
+    import numpy as np
+    import torch
+
+    from oracle import ref_runner as R
+    from oracle import wav2vec2_oracle as O
+
+    if not R.available():
+        pytest.skip("/root/reference is not present on this machine")
+    ref = R.load("wav2vec2_dist")
+    ocfg = O.Wav2Vec2Config("tiny")
+    w = O.randomize_weights(O.init_weights(ocfg, seed=0, dtype=torch.float64), seed=1)
+
+    class Wav2Vec2ForPreTraining:                    # stands in for the GPU model object: only the names matter for the export
+        variable_names = list(w)
+
+    tfk = CK.export_tf_names(Wav2Vec2ForPreTraining())
+    path = str(tmp_path / "export-1.tsckpt")
+    CK.write_file(path, {"model/" + k: v.numpy().astype(np.float32) for k, v in w.items()},
+                  {"tf_keys": {"model/" + k: t for k, t in tfk.items()}})
+    model = R.build_w2v(ref, "tiny", torch.randn(1, 3200, dtype=torch.float64))
+    assert CK.assign_to_keras(model, path) == len(w)
+    for name, var in R.w2v_variable_map(model).items():
+        assert torch.equal(var.detach().to(torch.float32), w[name].to(torch.float32)), name

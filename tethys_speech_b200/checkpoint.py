@@ -263,6 +263,53 @@ def tf_named_tensors(path):
     return out
 
 
+def assign_to_keras(model, path_or_named, optimizer=None, root="model"):
+    """The import side of the TF-name export, for a process that runs the REFERENCE's Keras model: resolve every TF
+    object-graph key of a checkpoint file (or of a {tf key: array} dict from tf_named_tensors) on `model` by walking the same
+    attribute path TensorFlow's tracking walks — attribute names, list indices, `layer_with_weights-<k>` of a Sequential — and
+    `assign` the stored value to the tf.Variable found there. With a Keras optimizer (`get_slot`, `iterations`) the Adam
+    slots and the iteration count are assigned too. Pure Python: no TensorFlow import here; anything that exposes the
+    reference's attribute structure works (tests run it on the reference classes over oracle/tf_shim.py). Returns the number of
+    model variables assigned."""
+    named = tf_named_tensors(path_or_named) if isinstance(path_or_named, str) else dict(path_or_named)
+
+    def resolve(obj, segs):
+        for seg in segs:
+            m = re.match(r"layer_with_weights-(\d+)$", seg)
+            if m:
+                layers = [l for l in obj.layers if (getattr(l, "weights", None) or getattr(l, "trainable_variables", None))]
+                obj = layers[int(m.group(1))]
+            elif seg.isdigit() and not hasattr(obj, seg):
+                obj = obj[int(seg)]
+            else:
+                obj = getattr(obj, seg)
+        return obj
+
+    done = 0
+    for key, value in named.items():
+        if not key.endswith(_TF_SUFFIX):
+            continue
+        body = key[:-len(_TF_SUFFIX)]
+        if body == "optimizer/iter":
+            if optimizer is not None and hasattr(getattr(optimizer, "iterations", None), "assign"):
+                optimizer.iterations.assign(int(value))
+            continue
+        slot = None
+        if "/.OPTIMIZER_SLOT/" in body:
+            body, tail = body.split("/.OPTIMIZER_SLOT/")
+            slot = tail.split("/")[-1]
+        segs = body.split("/")
+        if segs[0] != root:
+            continue
+        var = resolve(model, segs[1:])
+        if slot is None:
+            var.assign(np.array(value))
+            done += 1
+        elif optimizer is not None and hasattr(optimizer, "get_slot"):
+            optimizer.get_slot(var, slot).assign(np.array(value))
+    return done
+
+
 def restore(path, model, optimizer=None, strict=True):
     """Load `path` into the model's arenas (and the optimizer's, when both the file and the call have one). The bf16
     compute copy is refreshed on the next forward. Returns the checkpoint's meta dict."""
