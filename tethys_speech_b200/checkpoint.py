@@ -139,7 +139,7 @@ def read_file(path, keys=None):
 # add_weight / attribute name of the variable itself, then "/.ATTRIBUTES/VARIABLE_VALUE". The library's variable paths differ
 # from the reference's attribute structure in a few places (`fe.` = wav2vec2.feature_extractor, the Sequential conv blocks, the
 # task heads that live on the outer model), so the mapping is a short rule table. It is pinned by walking the reference's OWN
-# model objects (its unmodified constructors, running on oracle/tf_shim.py) with those naming rules:
+# model objects (its unmodified constructors, running on the test suite's TensorFlow stand-in) with those naming rules:
 # tests/test_checkpoint.py::test_tf_object_keys_follow_the_reference_object_graph. The rules themselves are restated from
 # TensorFlow 2.10's trackable code (TensorFlow is not installable here): the keys are not checked against a TF-written file.
 # ----------------------------------------------------------------------------------------------------------------------
@@ -269,7 +269,7 @@ def assign_to_keras(model, path_or_named, optimizer=None, root="model"):
     attribute path TensorFlow's tracking walks — attribute names, list indices, `layer_with_weights-<k>` of a Sequential — and
     `assign` the stored value to the tf.Variable found there. With a Keras optimizer (`get_slot`, `iterations`) the Adam
     slots and the iteration count are assigned too. Pure Python: no TensorFlow import here; anything that exposes the
-    reference's attribute structure works (tests run it on the reference classes over oracle/tf_shim.py). Returns the number of
+    reference's attribute structure works (the tests run it on the reference's own classes). Returns the number of
     model variables assigned."""
     named = tf_named_tensors(path_or_named) if isinstance(path_or_named, str) else dict(path_or_named)
 
