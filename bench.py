@@ -277,6 +277,48 @@ def ncu_traffic(key):
         return None
 
 
+def frontend_rooflines(peaks, device_index, B=8, seconds=15):
+    """BASELINE config 5 inside the bench line: the Wav2Vec2 conv feature encoder FORWARD as a whole (conv0 .. conv6 with
+    GroupNorm + GELU, grouped positional conv, LayerNorm: Wav2Vec2FeatureExtractor.call V:283-298 through ts_w2v_forward_features)
+    at the workload's shape. It sits at the ridge, so both fractions are reported: algorithmic bytes
+    (404.8 e + 4) N per sample (every activation written once and read once by its consumer, e = 2 for bf16) against the measured
+    copy bandwidth, and 2 x MACs (24.53 GFLOP per 5 s of audio + 1.05 of the positional conv) against the sustained bf16 peak.
+    Timed with CUDA events around eager launches, L2 flushed before each sample (the ~20 kernels of the pass take >> their launch gaps)."""
+    import ctypes as C
+
+    import torch
+    from tethys_speech_b200 import wav2vec2 as W
+    from tethys_speech_b200.runtime import stream_ptr
+
+    dev = torch.device("cuda", device_index)
+    N = 16000 * seconds
+    model = W.Wav2Vec2ForPreTraining(W.Wav2Vec2Config("base"), precision="bf16", device=device_index, seed=0)
+    p = model._prog
+    x = torch.randn(B, N, device=dev)
+    model.extract_features(x)                                  # plans the workspace, syncs the bf16 weights
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    xp = C.c_void_p(x.data_ptr())
+    for _ in range(2):
+        p.ctx.check(p.lib.ts_w2v_forward_features(p.h, xp, B, N, stream_ptr()))
+    torch.cuda.synchronize()
+    tot, iters = 0.0, 5
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        p.ctx.check(p.lib.ts_w2v_forward_features(p.h, xp, B, N, stream_ptr()))
+        e1.record()
+        e1.synchronize()
+        tot += e0.elapsed_time(e1)
+    t = tot / iters * 1e-3
+    nbytes = B * ((404.8 * 2 + 4.0) * N)
+    flops = B * (24.53e9 + 1.05e9) * (seconds / 5.0)
+    name = f"conv feature encoder forward as a whole [{B} x {seconds} s] bf16 (V:283-298, ts_w2v_forward_features)"
+    return [{"kernel": name, "bound": "hbm", "achieved": nbytes / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+             "frac": nbytes / t / 1e9 / peaks["hbm_gbs"], "us": t * 1e6, "traffic": None,
+             "tensor_tflops": flops / t / 1e12, "frac_of_bf16_sustained": flops / t / 1e12 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])}]
+
+
 def kernel_rooflines(ctx, peaks, B, T, H, F, nh, n_params):
     """Live per-kernel roofline fractions at this workload's shapes, each kernel timed alone through the C-ABI.
     Tensor-bound kernels: algorithmic FLOPs / time vs the measured cuBLAS bf16 burst peak. HBM-bound kernels: algorithmic
@@ -653,6 +695,10 @@ def run_ours(args):
     if rank == 0:
         torch.cuda.empty_cache()
         dominant, kernels = kernel_rooflines(hd["ctx"], peaks, hd["B"], hd["T"], hd["H"], hd["F"], hd["nh"], hd["n_params"])
+        try:      # BASELINE config 5 (front-end microbench) at this workload's shape; never takes the line down
+            kernels += frontend_rooflines(peaks, local)
+        except Exception as ex:  # noqa: BLE001
+            kernels.append({"kernel": "conv feature encoder forward as a whole", "error": f"{type(ex).__name__}: {ex}"[:200]})
         line["roofline"] = {"bound": "tensor", "kernel": dominant["kernel"], "achieved": dominant["achieved"], "peak": peaks["bf16_tflops"],
                             "unit": "TFLOP/s", "frac": dominant["frac"], "traffic": dominant["traffic"],
                             "peak_source": peaks["source"] + " (burst: kernel timed alone)"}
