@@ -578,9 +578,10 @@ def apply_feature_mask(hidden_states, mask_prob=0.05, mask_length=10, start_mask
 
 
 def make_graphed_distributed_step(strategy, model, optimizer, example_features, dropout=True, warmup=3):
-    """distributed_train_step (V:1186-1260) as CUDA graphs around the eager NCCL all-reduce:
-       graph [advance state, forward (loss / N), backward, local clip_by_global_norm] -> eager all-reduce SUM of the gradient
-       arena (3 buckets) -> graph [per-variable clipnorm + Adam] -> eager strategy.reduce(SUM) of the scaled losses.
+    """distributed_train_step (V:1186-1260) replayed from CUDA graphs. With the native communicator (the default on GPUs) the whole
+    step is ONE graph: [advance state, forward (loss / N), backward, local clip factor, pack] -> NCCL SUM of the gradient arena
+    (captured) -> [per-variable clipnorm + Adam] -> NCCL SUM of the scaled losses (captured). With torch.distributed collectives
+    (TETHYS_NATIVE_COMM=0) the two compute parts are graph segments around the eager all-reduce and the eager strategy.reduce.
     Returns (step(features) -> reduced loss, segments)."""
     from .runtime import GraphedSegments
 
