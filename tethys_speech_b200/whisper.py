@@ -446,8 +446,10 @@ def train_step(model, inputs, optimizer, dropout=True):
 
 def make_graphed_distributed_step(strategy, model, optimizer, example_features, example_labels, dropout=True, warmup=3,
                                   bucket_elems=16 * 1024 * 1024):
-    """distributed_train_step (W:819-848) as CUDA graphs between the eager NCCL all-reduces. The backward stages are grouped
-    into buckets (arena prefixes that are final, ts_whisper_stage_end). Per bucket g:
+    """distributed_train_step (W:819-848) replayed from CUDA graphs. With the native communicator (default on GPUs) the whole step is
+    ONE graph in which every bucket's NCCL all-reduce is a node on the communicator's side stream (a fork / join the capture
+    records); with torch.distributed collectives (TETHYS_NATIVE_COMM=0) the compute parts are graph segments between eager
+    all-reduces. The backward stages are grouped into buckets (arena prefixes that are final, ts_whisper_stage_end). Per bucket g:
         main stream : graph [backward stages of g] -> async all-reduce SUM of bucket g (un-normalised — App. C-3)
     so the reductions of earlier buckets run underneath the remaining backward graphs; after the last bucket the step waits
     for all reductions and replays the Adam graph. With TETHYS_SIDE_ADAM=1 each bucket is instead updated on a side stream as
