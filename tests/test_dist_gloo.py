@@ -95,3 +95,53 @@ def test_strategy_shim_world2_gloo():
     # the reported loss is the SUM over replicas of loss/N = the mean of the per-replica losses (V:1231, V:1260)
     mean_loss = 0.5 * (got[0]["loss"] + got[1]["loss"])
     assert abs(got[0]["scaled_loss"] - mean_loss) < 1e-6 * mean_loss       # the scalar travels as float32, like TF's loss
+
+
+# ---- the reference's own launch: no torchrun, every pod runs `python speech_jobs/*_dist.py` with the TFJob operator's TF_CONFIG ----
+def _tf_config_worker(task_type, task_index, cluster, q):
+    import json
+
+    sys.path.insert(0, ROOT)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        os.environ.pop(k, None)
+    os.environ["TF_CONFIG"] = json.dumps({"cluster": cluster, "task": {"type": task_type, "index": task_index}, "environment": "cloud"})
+    from tethys_speech_b200.runtime import Strategy
+
+    torch.set_num_threads(1)
+    st = Strategy(backend="gloo")
+    g = torch.full((8,), float(st.rank + 1))
+    st.all_reduce_sum_(g)
+    arena = torch.full((4,), float(10 * (st.rank + 1)))
+    st.broadcast_(arena)
+    q.put((task_type, task_index, st.rank, st.num_replicas_in_sync, float(g[0]), float(arena[0])))
+    st.barrier()
+
+
+@pytest.mark.timeout(300)
+def test_strategy_rendezvous_from_tf_config_world3_gloo():
+    """W:1037-1047 / sample_tfjobs/*.yaml: CHIEF + 2 WORKER pods, TF_CONFIG only. Replica order = chief, worker 0, worker 1; the chief's
+    TFJob port is the rendezvous address."""
+    from tethys_speech_b200.runtime import rendezvous_from_tf_config
+
+    port = _free_port()
+    cluster = {"chief": [f"127.0.0.1:{port}"], "worker": ["127.0.0.1:2223", "127.0.0.1:2224"]}
+    assert rendezvous_from_tf_config({"cluster": cluster, "task": {"type": "worker", "index": 1}}) == (3, 2, "127.0.0.1", port)
+    assert rendezvous_from_tf_config({"cluster": {"CHIEF": cluster["chief"], "WORKER": cluster["worker"], "ps": ["x:1"]},
+                                      "task": {"type": "chief", "index": 0}}) == (3, 0, "127.0.0.1", port)
+    assert rendezvous_from_tf_config({}) is None and rendezvous_from_tf_config("") is None
+    assert rendezvous_from_tf_config({"cluster": {"worker": ["h:1"]}, "task": {"type": "worker", "index": 0}}) is None     # one task
+    with pytest.raises(ValueError):
+        rendezvous_from_tf_config({"cluster": cluster, "task": {"type": "ps", "index": 0}})
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    tasks = [("chief", 0), ("worker", 0), ("worker", 1)]
+    procs = [ctx.Process(target=_tf_config_worker, args=(t, i, cluster, q)) for t, i in tasks]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=240) for _ in tasks)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [(t, i, r) for t, i, r, *_ in got] == [("chief", 0, 0), ("worker", 0, 1), ("worker", 1, 2)]
+    for _, _, _, world, red, bc in got:
+        assert world == 3 and red == 6.0 and bc == 10.0          # 1 + 2 + 3; everyone holds the chief's arena

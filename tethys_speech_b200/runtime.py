@@ -209,6 +209,35 @@ class ProgramBase:
         return len(works)
 
 
+def rendezvous_from_tf_config(tf_config=None):
+    """The replica group a TFJob pod belongs to, from the TF_CONFIG the operator injects (W:1037-1040, job_name.py:3-13;
+    sample_tfjobs/*.yaml: one CHIEF + WORKER pods, one GPU and one `python speech_jobs/*_dist.py` process each):
+        {"cluster": {"chief": ["host:2222"], "worker": ["host:2222", ...]}, "task": {"type": "worker", "index": 0}}
+    -> (world, rank, master_host, master_port) with MultiWorkerMirroredStrategy's replica order (chief first, then the workers by
+    index; `ps` / `evaluator` tasks do not train) and the chief's own TFJob port as the rendezvous address — nothing else is
+    listening there, TensorFlow's gRPC server being gone. None when TF_CONFIG is absent or names a single task (W:1047 then
+    degenerates to one worker)."""
+    import json
+
+    if tf_config is None:
+        tf_config = os.environ.get("TF_CONFIG")
+    if isinstance(tf_config, str):
+        tf_config = json.loads(tf_config or "{}")
+    if not tf_config:
+        return None
+    cluster = {str(k).lower(): list(v) for k, v in (tf_config.get("cluster") or {}).items()}
+    task = tf_config.get("task") or {}
+    order = [(job, i, addr) for job in ("chief", "master", "worker") for i, addr in enumerate(cluster.get(job, []))]
+    if len(order) <= 1:
+        return None
+    me = (str(task.get("type", "")).lower(), int(task.get("index", 0)))
+    ranks = [r for r, (job, i, _) in enumerate(order) if (job, i) == me]
+    if not ranks:
+        raise ValueError(f"TF_CONFIG task {me} is not a training task of the cluster {sorted(cluster)}")
+    host, _, port = order[0][2].rpartition(":")
+    return len(order), ranks[0], host, int(port)
+
+
 class Strategy:
     """Stand-in for tf.distribute.MultiWorkerMirroredStrategy (W:1047, V:1473): one process per GPU. torch.distributed is the
     rendezvous (and the whole collective layer on CPU / gloo, for the host-logic tests); on GPUs the data path is the library's
@@ -220,6 +249,14 @@ class Strategy:
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.rank = int(os.environ.get("RANK", "0"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        init_method = None
+        if "WORLD_SIZE" not in os.environ:
+            # launched the reference's way — `python speech_jobs/*_dist.py` in every TFJob pod, no torchrun: the replica group
+            # comes from TF_CONFIG like MultiWorkerMirroredStrategy's own cluster resolver (W:1037-1047)
+            rdv = rendezvous_from_tf_config()
+            if rdv is not None:
+                self.world, self.rank, host, port = rdv
+                init_method = f"tcp://{host}:{port}"
         self.dist = None
         self.comm = None            # ts_comm handle
         self.comm_stream = None     # side stream for collectives that overlap the backward pass
@@ -232,7 +269,10 @@ class Strategy:
                     backend = "nccl" if torch.cuda.is_available() else "gloo"
                 if backend == "nccl":
                     torch.cuda.set_device(self.local_rank)
-                dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world)
+                if init_method is not None:
+                    dist.init_process_group(backend=backend, init_method=init_method, rank=self.rank, world_size=self.world)
+                else:
+                    dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world)
             self.dist = dist
             if torch.cuda.is_available() and dist.get_backend() == "nccl" and os.environ.get("TETHYS_NATIVE_COMM", "1") != "0":
                 self._init_native()
