@@ -232,7 +232,10 @@ def train_wav2vec2(strategy, model_type="pretraining", model_size="small", num_e
                     _save_checkpoint(model, f"model_step_{step}", optimizer)
             except StopIteration:
                 break
-            except Exception as e:                               # V:1367-1371 swallows per-step errors
+            except Exception as e:
+                # V:1367-1371 prints this line, restarts the dataset iterator and carries on. Deliberate deviation: the same line is
+                # printed, then the error is re-raised (as W:837-842 does) — a failed CUDA launch or collective is sticky, a loop that
+                # swallows it would log the same error for every remaining step and leave the other replicas waiting in NCCL.
                 print(f"Error at step {step}: {e}")
                 raise
         if strategy.rank == 0:
