@@ -505,6 +505,12 @@ def native_train_step(model, inputs, optimizer, neg_indices=None, dropout=True, 
         lab = to_device(labels, torch.int32, p.device).reshape(-1)
         if lab.numel() != B:
             raise ValueError(f"labels must hold one class id per clip ({B}), got {tuple(lab.shape)}")
+    elif model._head == "ctc" and labels is not None:
+        t = labels if isinstance(labels, torch.Tensor) else torch.as_tensor(np.asarray(labels))
+        if t.dim() == 2 and t.shape[1] > 1:
+            # transcripts select the real tf.nn.ctc_loss of the legacy file (WS:897-929), which Wav2Vec2ForCTC.__call__ computes with a
+            # separate operator (ts_ctc_loss) between forward and backward; the composite entry runs the reference's stand-in loss only
+            raise NotImplementedError("native_train_step: transcript labels (real CTC loss) go through train_step, not the composite entry")
     model._step_seed += 1
     args, loss = native_step_args(model, optimizer, strategy, global_clip=1.0, dropout=dropout, seed=model._step_seed)
     p.ctx.check(p.lib.ts_w2v_step(p.h, ptr(x), B, N, ptr(neg), neg_bs, neg_ts, ptr(lab), C.byref(args), stream_ptr()))
