@@ -140,6 +140,28 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle's train step on host cores
 # ------------------------------------------------------------------------------------------------------------
+STEP_DESC = {
+    ("w2v", True): "VS:1119-1176 (clip_by_global_norm 1.0 + clipnorm 1.0 + Keras-legacy Adam 3e-5)",
+    ("w2v", False): "V:1186-1260 (loss/N, local clip, NCCL all-reduce SUM, clipnorm, Adam)",
+    ("whisper", True): "W:823-836 single replica (forward, shifted CE, backward, Keras-legacy Adam 1e-4)",
+    ("whisper", False): "W:819-848 (un-normalised NCCL all-reduce SUM in buckets overlapped with backward, Adam)",
+}
+
+
+def workload_config(workload, batch, world):
+    """The `config` object of the JSON line: it NAMES THE WORKLOAD (a BASELINE.json config at N replicas) and nothing about how an
+    arm runs it, so that both arms — ours and `--impl reference` — print the same object for the same command line. What is
+    specific to a run goes elsewhere: ours in `run` (CUDA graph, collective layer), the reference arm's in `cpu_baseline.sample`."""
+    family, size, n_samples, secs, _ = WORKLOADS[workload]
+    B = batch or DEFAULT_BATCH[family]
+    return {"workload": workload, "model": f"{'wav2vec2' if family == 'w2v' else 'whisper'}-{size}", "audio_seconds": secs,
+            "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+            "dropout": "on (0.1, as the reference's training=True)", "step": STEP_DESC[(family, world == 1)],
+            "allreduce": "none (1 replica)" if world == 1 else "SUM of the replicas' gradients inside apply_gradients (W:834 / V:1246)",
+            "l2": "working set per step (GBs of activations) >> 126 MB L2; 4 distinct input batches cycled; "
+                  "per-kernel timings: CUDA-graph replays of [256 MB memset (L2 flush); kernel] minus replays of the memset alone"}
+
+
 def cpu_step_throughput(workload, steps, warmup, max_seconds=150.0):
     """The oracle's PyTorch-CPU fp32 restatement of the same train step on all host cores, batch 1 (bounded sample)."""
     import numpy as np
@@ -190,8 +212,8 @@ def cpu_step_throughput(workload, steps, warmup, max_seconds=150.0):
     except Exception:
         pass
     return {"value": B / mean, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": f"{len(times)} timed step(s) of batch {B} x {secs:g} s audio ({workload}), PyTorch-CPU fp32 restatement "
-                      f"of the reference step (TensorFlow not installable), cpu='{cpu_model}'",
+            "sample": f"{len(times)} timed step(s) of batch {B} x {secs:g} s audio ({workload}: one sample of the per-GPU batch, dropout "
+                      f"layers off), PyTorch-CPU fp32 restatement of the reference step (TensorFlow not installable), cpu='{cpu_model}'",
             "ms_per_step": mean * 1e3, "steps_timed": len(times)}
 
 
@@ -205,8 +227,9 @@ def run_reference(args):
             "audio_sec_per_sec": r["value"] * secs, "n_gpus": args.gpus, "steps": r["steps_timed"], "warmup": max(0, args.warmup),
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "model": f"{'wav2vec2' if family == 'w2v' else 'whisper'}-{size}", "audio_seconds": secs, "batch_per_step": 1,
-                       "note": "reference arm = CPU restatement of the reference's TF step on host cores (rank 0 only)"},
+            "config": workload_config(args.workload, args.batch, max(1, int(os.environ.get("WORLD_SIZE", "1")))),
+            "note": "reference arm = CPU restatement of the reference's TF step on host cores (rank 0 only); every timed step is a bounded "
+                    "sample of the workload `config` names (cpu_baseline.sample says which)",
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -651,12 +674,9 @@ def measure_workload(args, strategy, workload, batch, steps, warmup, rank, world
         "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": t_dev / steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": workload, "model": model_name, "audio_seconds": secs, "per_gpu_batch": B,
-                   "global_batch": B * world, "parallelism": f"dp{world}", "dropout": "on (0.1, as the reference's training=True)",
-                   "step": step_desc, "cuda_graph": bool(use_graph), "settle_steps_before_warmup": settle,
-                   "allreduce": ("none (1 replica)" if world == 1 else strategy.allreduce_description(model._prog)),
-                   "l2": "working set per step (GBs of activations) >> 126 MB L2; 4 distinct input batches cycled; "
-                         "per-kernel timings: CUDA-graph replays of [256 MB memset (L2 flush); kernel] minus replays of the memset alone"},
+        "config": workload_config(workload, B, world),
+        "run": {"cuda_graph": bool(use_graph), "settle_steps_before_warmup": settle,
+                "collectives": ("none (1 replica)" if world == 1 else strategy.allreduce_description(model._prog))},
         "clocks": clk,
         "e2e": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": t_e2e / steps * 1e3, "last_loss": last},
@@ -719,7 +739,7 @@ def run_ours(args):
             try:
                 r, h2 = measure_workload(args, strategy, wl, 0, min(args.steps, 10), max(3, min(args.warmup, 5)), rank, world, local)
                 extras.append({k: r[k] for k in ("value", "unit", "audio_sec_per_sec", "ms_per_step", "n_gpus", "steps", "warmup", "dtype",
-                                                 "config", "clocks", "e2e", "gpu_launches", "launches_per_step", "step_tflops_per_gpu",
+                                                 "config", "run", "clocks", "e2e", "gpu_launches", "launches_per_step", "step_tflops_per_gpu",
                                                  "step_frac_of_bf16_sustained")})
                 h2.clear()
             except Exception as ex:   # an extra workload never takes the main line down
