@@ -113,7 +113,9 @@ def test_w2v_native_step_bf16_bucket_tracks_python_step():
             l2 = W.train_step(m2, (wave.float(), None), o2, neg_indices=neg, dropout=False)
         torch.cuda.synchronize()
         assert o1.iterations == o2.iterations == 3
-        assert abs(float(l1) - float(l2)) < 2e-2 * abs(float(l2))
+        # a wiring check, not a precision bar (the fp32 tests above carry that): in this fast-descending toy run a near-tie flip of the hard VQ
+        # argmin moves the loss by ~1e-3 per update whatever perturbs the weights (tools/bf16_bucket_drift.py), the 2-GPU check saw up to 1.2e-2
+        assert abs(float(l1) - float(l2)) < 5e-2 * abs(float(l2))
         p1, p2 = m1._prog.params, m2._prog.params
         assert float((p1 - p2).norm() / p2.norm()) < 2e-3
         u1, u2 = (p1 - p0).double(), (p2 - p0).double()          # Adam's early steps are sign-like: the two updates must point the same way
